@@ -1,0 +1,196 @@
+/*
+ * rten_b200.h -- C ABI of librten_b200.so: the B200 (sm_100a) operator execution backend for RTen.
+ *
+ * This is the drop-in boundary for ONE path of robertknight/rten: `Operator::run` /
+ * `run_in_place` / `prepack` (src/operator.rs:486-613) of the dense operators of ResNet-50 /
+ * BERT-base / GPT-2, replacing rten-gemm's packed GEMM (rten-gemm/src/lib.rs:199-391) and the
+ * rten-vecmath row kernels.  A Rust `impl Operator` shim fills `rten_tensor` descriptors from
+ * `ValueView`s (src/value.rs:299) and calls one function below per operator.
+ *
+ * Conventions
+ *  - Every entry point takes a context (one per host thread / stream: rten's ops are `Send + Sync`
+ *    and `Model::run` may be re-entered concurrently, src/operator.rs:622).
+ *  - `rten_tensor.strides` are ELEMENT strides like rten-tensor layouts; arbitrary (non-negative)
+ *    strides are accepted, including the permuted views `TransformInputs` hands to MatMul
+ *    (src/ops/transform_inputs.rs:23-34).
+ *  - `device >= 0`: `data` is a device pointer on that CUDA ordinal (buffers resident in HBM).
+ *    `device == RTEN_DEVICE_HOST`: `data` is host memory; the library stages it through HBM on the
+ *    context's stream (host<->device copies are part of the call) -- this is how an unmodified
+ *    rten `Vec<T>`-backed tensor crosses the boundary.
+ *  - Output tensors: `out->data == NULL` => the library allocates from the context pool (plays
+ *    `ctx.pool()`, src/operator.rs:360) on device and fills shape/strides/device; the caller later
+ *    returns it with rten_b200_free().  Otherwise `out` must already have the result shape.
+ *  - Calls enqueue work on the context stream and return without synchronising unless a host
+ *    tensor is involved; asynchronous CUDA errors surface on the next call or rten_b200_sync().
+ *  - Errors: status codes mirror `OpError` (src/operator.rs:116-144); rten_b200_last_error()
+ *    returns the reference's static message string for that error.
+ *  - No CPU fallback exists: without a B200 + driver every op fails with RTEN_ERR_CUDA.
+ */
+#ifndef RTEN_B200_H
+#define RTEN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RTEN_MAX_DIMS 8
+#define RTEN_DEVICE_HOST (-1)
+
+/* = `DataType` (src/value.rs:20-40) */
+typedef enum { RTEN_F32 = 0, RTEN_I32 = 1, RTEN_I8 = 2, RTEN_U8 = 3 } rten_dtype;
+
+typedef struct {
+    void* data;
+    int32_t dtype; /* rten_dtype */
+    int32_t ndim;
+    int64_t shape[RTEN_MAX_DIMS];
+    int64_t strides[RTEN_MAX_DIMS]; /* elements */
+    int32_t device;                 /* RTEN_DEVICE_HOST or CUDA ordinal */
+    int32_t _reserved;
+} rten_tensor;
+
+/* = `OpError` variants (src/operator.rs:116-144) + device errors */
+typedef enum {
+    RTEN_OK = 0,
+    RTEN_ERR_CAST_FAILED = 1,
+    RTEN_ERR_UNSUPPORTED_TYPE = 2,
+    RTEN_ERR_INCOMPATIBLE_SHAPES = 3, /* IncompatibleInputShapes(&'static str) */
+    RTEN_ERR_MISSING_INPUTS = 4,
+    RTEN_ERR_INVALID_VALUE = 5,      /* InvalidValue(&'static str) */
+    RTEN_ERR_UNSUPPORTED_VALUE = 6,  /* UnsupportedValue(&'static str) */
+    RTEN_ERR_UNSUPPORTED_OUTPUT = 7, /* UnsupportedOutput(&'static str) */
+    RTEN_ERR_CUDA = 100,
+    RTEN_ERR_NCCL = 101
+} rten_status;
+
+typedef struct rten_ctx rten_ctx;
+/* = `PrepackedInput` (src/operator.rs:25-31): a weight re-laid out once for the tensor cores. */
+typedef struct rten_packed rten_packed;
+
+/* fp32 GEMM/Conv arithmetic mode (SURVEY.md hard part A). */
+typedef enum {
+    RTEN_F32_TF32 = 0,  /* single tcgen05 kind::tf32 pass (default; tolerance in DESIGN.md) */
+    RTEN_F32_TF32X3 = 1 /* 3-pass error-compensated split: ~fp32 accuracy at 1/3 tensor rate */
+} rten_f32_mode;
+
+/* ---- context, memory, diagnostics ----------------------------------------------------------- */
+rten_status rten_b200_ctx_create(int device, void* cuda_stream_or_null, size_t workspace_bytes, rten_ctx** out);
+void rten_b200_ctx_destroy(rten_ctx* ctx);
+const char* rten_b200_last_error(rten_ctx* ctx);
+rten_status rten_b200_sync(rten_ctx* ctx);
+rten_status rten_b200_set_f32_mode(rten_ctx* ctx, int mode /* rten_f32_mode */);
+/* Caching, stream-ordered device allocator = `BufferPool` (src/buffer_pool.rs:1-140). */
+rten_status rten_b200_alloc(rten_ctx* ctx, size_t bytes, void** dev_ptr);
+rten_status rten_b200_free(rten_ctx* ctx, void* dev_ptr);
+/* Pinned host buffers for callers that want asynchronous staging of host tensors. */
+rten_status rten_b200_host_alloc(rten_ctx* ctx, size_t bytes, void** host_ptr);
+rten_status rten_b200_host_free(rten_ctx* ctx, void* host_ptr);
+/* Copies between host and device tensors of identical shape (strided on both sides). */
+rten_status rten_b200_copy(rten_ctx* ctx, const rten_tensor* src, rten_tensor* dst);
+/* Number of CUDA kernels this context has launched so far (bench.py `gpu_launches`). */
+uint64_t rten_b200_launch_count(rten_ctx* ctx);
+const char* rten_b200_version(void);
+/* Capture everything enqueued between begin/end into a CUDA graph; replay with graph_launch.
+ * (launch-bound op lists: the `Graph::run_plan` loop, src/graph.rs:880-1286, as one graph) */
+typedef struct rten_graph rten_graph;
+rten_status rten_b200_graph_begin(rten_ctx* ctx);
+rten_status rten_b200_graph_end(rten_ctx* ctx, rten_graph** out);
+rten_status rten_b200_graph_launch(rten_ctx* ctx, rten_graph* g);
+void rten_b200_graph_destroy(rten_graph* g);
+
+/* ---- prepack == `Operator::prepack` (src/operator.rs:587-601) ------------------------------- */
+/* MatMul/FusedMatMul/MatMulInteger input 1 (src/ops/matmul.rs:410-420,687-697): B [K,N] (f32, i8 or
+ * u8) -> K-major [N,K] tensor-core layout (+ per-column sums for the int8 zero-point epilogue). */
+rten_status rten_b200_prepack_b(rten_ctx* ctx, const rten_tensor* b, rten_packed** out);
+/* Conv/ConvInteger kernel OIHW (the reference prepacks it per call, src/ops/conv.rs:302-315):
+ * -> [O, kh, kw, C/g] K-major (+ per-output-channel sums for ConvInteger). */
+rten_status rten_b200_prepack_conv_weight(rten_ctx* ctx, const rten_tensor* w, int groups, rten_packed** out);
+void rten_b200_packed_free(rten_ctx* ctx, rten_packed* p);
+
+/* ---- operators == `Operator::run` ------------------------------------------------------------ */
+/* Gemm (src/ops/matmul.rs:32-167): out = alpha * op(a) @ op(b) + beta * broadcast(c). */
+rten_status rten_b200_gemm(rten_ctx* ctx, const rten_tensor* a, const rten_tensor* b, const rten_tensor* c_or_null,
+                           float alpha, float beta, int trans_a, int trans_b, rten_tensor* out);
+
+/* MatMul (src/ops/matmul.rs:390-434) / FusedMatMul (:462-507): numpy-matmul broadcasting; optional row
+ * bias over N; alpha scales the product before the bias is added.  `packed_b_or_null` = the
+ * PrepackedInput for input 1 (then `b` is only consulted for its shape). */
+rten_status rten_b200_matmul(rten_ctx* ctx, const rten_tensor* a, const rten_tensor* b,
+                             const rten_packed* packed_b_or_null, const rten_tensor* row_bias_or_null, float alpha,
+                             rten_tensor* out);
+/* Extension used by whole-model runners: fused activation after bias (0 none, 1 relu, 2 gelu(erf),
+ * 3 gelu(tanh)) and optional residual add (same shape as out) before the activation. */
+rten_status rten_b200_matmul_ex(rten_ctx* ctx, const rten_tensor* a, const rten_tensor* b,
+                                const rten_packed* packed_b_or_null, const rten_tensor* row_bias_or_null, float alpha,
+                                const rten_tensor* residual_or_null, int activation, rten_tensor* out);
+
+/* MatMulInteger (src/ops/matmul.rs:582-697): a u8|i8, b u8|i8, zero points scalar or vector, out i32
+ * exact.  `scale_or_null` != NULL => MatMulIntegerToFloat (:776-811): out f32 = f32(acc) * scale
+ * (scalar or per column). */
+rten_status rten_b200_matmul_integer(rten_ctx* ctx, const rten_tensor* a, const rten_tensor* b,
+                                     const rten_packed* packed_b_or_null, const rten_tensor* a_zero_point_or_null,
+                                     const rten_tensor* b_zero_point_or_null, const rten_tensor* scale_or_null,
+                                     rten_tensor* out);
+
+/* Conv (src/ops/conv.rs:124-419).  x NCHW (or NCW), w OIHW, bias [O].  pads = {top,left,bottom,right};
+ * auto_pad_same != 0 => `Padding::Same` (pads ignored).  n_spatial = 1 or 2 gives the expected
+ * number of stride/dilation values (error strings as the reference). */
+typedef struct {
+    int32_t pads[4];
+    int32_t auto_pad_same;
+    int32_t groups;
+    int32_t strides[2];
+    int32_t dilations[2];
+    int32_t n_strides;   /* number of valid entries in strides (reference validates == spatial dims) */
+    int32_t n_dilations; /* idem */
+} rten_conv_params;
+rten_status rten_b200_conv2d(rten_ctx* ctx, const rten_tensor* x, const rten_tensor* w,
+                             const rten_packed* packed_w_or_null, const rten_tensor* bias_or_null,
+                             const rten_conv_params* p, rten_tensor* out);
+/* Extension: fused residual add (same shape as out) + activation (see matmul_ex). */
+rten_status rten_b200_conv2d_ex(rten_ctx* ctx, const rten_tensor* x, const rten_tensor* w,
+                                const rten_packed* packed_w_or_null, const rten_tensor* bias_or_null,
+                                const rten_conv_params* p, const rten_tensor* residual_or_null, int activation,
+                                rten_tensor* out);
+/* ConvInteger (src/ops/conv.rs:421-533); scale_or_null != NULL => ConvIntegerToFloat (:535-587). */
+rten_status rten_b200_conv_integer(rten_ctx* ctx, const rten_tensor* x, const rten_tensor* w,
+                                   const rten_packed* packed_w_or_null, const rten_tensor* x_zero_point_or_null,
+                                   const rten_tensor* w_zero_point_or_null, const rten_tensor* scale_or_null,
+                                   const rten_conv_params* p, rten_tensor* out);
+
+/* Softmax (src/ops/norm.rs:825-899) and AddSoftmax (src/ops/attention.rs:30-165) when mask != NULL
+ * (mask broadcast to x, added lane-wise before the softmax over `axis`; AddSoftmax uses axis -1).
+ * `out` may alias `x` (= run_in_place). */
+rten_status rten_b200_softmax(rten_ctx* ctx, const rten_tensor* x, const rten_tensor* mask_or_null, int axis,
+                              int flush_nans_to_zero, rten_tensor* out);
+/* LayerNormalization (src/ops/norm.rs:437-569); epsilon < 0 => default 1e-5. */
+rten_status rten_b200_layer_norm(rten_ctx* ctx, const rten_tensor* x, const rten_tensor* scale,
+                                 const rten_tensor* bias_or_null, int axis, float epsilon, rten_tensor* out);
+/* Erf / Gelu (src/ops/unary_elementwise.rs:384-435); approximate != 0 => tanh form. */
+rten_status rten_b200_erf(rten_ctx* ctx, const rten_tensor* x, rten_tensor* out);
+rten_status rten_b200_gelu(rten_ctx* ctx, const rten_tensor* x, int approximate, rten_tensor* out);
+/* DynamicQuantizeLinear (src/ops/quantize.rs:352-468): y u8, scale f32 scalar, zero_point u8 scalar.
+ * nccl_comm_or_null: when the batch is sharded over ranks, all-reduce (min,max) over this
+ * ncclComm_t first so every rank picks the unsharded tensor's scale/zero point. */
+rten_status rten_b200_dynamic_quantize_linear(rten_ctx* ctx, const rten_tensor* x, rten_tensor* y,
+                                              rten_tensor* scale, rten_tensor* zero_point, void* nccl_comm_or_null);
+
+/* ---- residency glue so whole models stay in HBM ------------------------------ */
+rten_status rten_b200_relu(rten_ctx* ctx, const rten_tensor* x, rten_tensor* out);
+/* Add with numpy broadcasting (src/ops/binary_elementwise.rs). */
+rten_status rten_b200_add(rten_ctx* ctx, const rten_tensor* a, const rten_tensor* b, rten_tensor* out);
+/* MaxPool 2-D (src/ops/pooling.rs): kernel {kh,kw}; pads/strides as conv; padding never wins. */
+rten_status rten_b200_max_pool(rten_ctx* ctx, const rten_tensor* x, const int32_t kernel[2], const int32_t pads[4],
+                               const int32_t strides[2], rten_tensor* out);
+rten_status rten_b200_global_average_pool(rten_ctx* ctx, const rten_tensor* x, rten_tensor* out);
+/* Gather along axis 0 of a 2-D table with i32 indices (embedding lookups, src/ops/gather.rs). */
+rten_status rten_b200_gather_rows(rten_ctx* ctx, const rten_tensor* table, const rten_tensor* indices_i32,
+                                  rten_tensor* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RTEN_B200_H */

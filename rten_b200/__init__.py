@@ -1,0 +1,11 @@
+"""rten_b200 -- B200 (sm_100a) operator execution backend for the RTen hot path.
+
+The product is `librten_b200.so` (hand-written CUDA behind the C ABI in include/rten_b200.h);
+`rten_b200.ops` is the host-side mirror of RTen's operator interface used by the tests, the model
+runners and bench.py.  There is no CPU implementation in this package."""
+from . import _lib  # noqa: F401
+from .ops import (  # noqa: F401
+    ACT_GELU, ACT_GELU_TANH, ACT_NONE, ACT_RELU, Add, AddSoftmax, Context, Conv, ConvInteger, ConvIntegerToFloat,
+    DeviceTensor, DynamicQuantizeLinear, Erf, FusedMatMul, GatherRows, Gelu, Gemm, GlobalAveragePool,
+    LayerNormalization, MatMul, MatMulInteger, MatMulIntegerToFloat, MaxPool, OpError, Packed, Relu, Softmax, from_torch,
+)

@@ -1,0 +1,33 @@
+// Per-call scope used by every operator entry point: stages host tensors through HBM, allocates /
+// validates outputs, and at the end copies host outputs back and releases temporaries.
+#pragma once
+#include <vector>
+
+#include "common.h"
+
+namespace rtb {
+
+struct OpScope {
+    rten_ctx* ctx;
+    bool host_involved = false;
+    struct Copyback {
+        void* host;
+        void* dev;
+        size_t bytes;
+    };
+    std::vector<Copyback> copybacks;
+    std::vector<rten_tensor*> allocated;
+
+    explicit OpScope(rten_ctx* c) : ctx(c) { cudaSetDevice(c->device); }
+
+    // device view of an input (H2D copy of the spanned region for host tensors)
+    rten_status in(const rten_tensor* t, rten_tensor* view);
+    // device view of an output; allocates when o->data == NULL (optionally with the given strides)
+    rten_status out(rten_tensor* o, int dtype, int ndim, const int64_t* shape, rten_tensor* view,
+                    const int64_t* preferred_strides);
+    // contiguous device copy (no-op when already contiguous)
+    rten_status contiguous(const rten_tensor* v, rten_tensor* c);
+    rten_status finish(rten_status st);
+};
+
+}  // namespace rtb

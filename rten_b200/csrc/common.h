@@ -1,0 +1,121 @@
+// Host-side plumbing shared by the C-ABI entry points and the kernel launchers:
+// context (= the caller's OpRunContext + BufferPool), error strings, caching allocator.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/rten_b200.h"
+
+struct rten_graph {
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    uint64_t kernels = 0;  // kernels captured (added to the launch counter on every replay)
+};
+
+// Device-side caching allocator, stream-ordered on the context stream
+// (plays src/buffer_pool.rs: size-bucketed reuse within and across runs).
+struct DevicePool {
+    std::unordered_map<void*, size_t> live;             // ptr -> bucket size
+    std::map<size_t, std::vector<void*>> free_buckets;  // bucket size -> free buffers
+    size_t bytes_reserved = 0;
+
+    static size_t bucket(size_t bytes) {
+        if (bytes < 512) bytes = 512;
+        if (bytes <= (1u << 20)) {
+            size_t b = 512;
+            while (b < bytes) b <<= 1;
+            return b;
+        }
+        const size_t mb = 1u << 20;
+        return (bytes + mb - 1) / mb * mb;
+    }
+};
+
+struct rten_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int num_sms = 148;
+    int f32_mode = RTEN_F32_TF32;
+    uint64_t launches = 0;
+    bool capturing = false;
+    uint64_t capture_start_launches = 0;
+    std::string err;
+    DevicePool pool;
+    // scratch released at the end of each op call
+    std::vector<void*> temps;
+    void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled (driver entry point)
+};
+
+namespace rtb {
+
+// ---- errors -------------------------------------------------------------------------------
+inline rten_status fail(rten_ctx* ctx, rten_status st, const char* msg) {
+    if (ctx) ctx->err = msg ? msg : "";
+    return st;
+}
+inline rten_status fail_cuda(rten_ctx* ctx, cudaError_t e, const char* where) {
+    if (ctx) {
+        ctx->err = std::string("CUDA error at ") + where + ": " + cudaGetErrorString(e);
+    }
+    return RTEN_ERR_CUDA;
+}
+#define RTB_CUDA(ctx, expr)                                         \
+    do {                                                            \
+        cudaError_t _e = (expr);                                    \
+        if (_e != cudaSuccess) return rtb::fail_cuda(ctx, _e, #expr); \
+    } while (0)
+#define RTB_TRY(expr)                      \
+    do {                                   \
+        rten_status _s = (expr);           \
+        if (_s != RTEN_OK) return _s;      \
+    } while (0)
+
+// ---- allocator ----------------------------------------------------------------------------
+rten_status pool_alloc(rten_ctx* ctx, size_t bytes, void** out);
+rten_status pool_free(rten_ctx* ctx, void* p);
+// temp = freed automatically by release_temps() at the end of the op
+rten_status temp_alloc(rten_ctx* ctx, size_t bytes, void** out);
+void release_temps(rten_ctx* ctx);
+
+// ---- tensor helpers -----------------------------------------------------------------------
+inline int dtype_size(int dt) { return (dt == RTEN_F32 || dt == RTEN_I32) ? 4 : 1; }
+inline int64_t numel(const rten_tensor* t) {
+    int64_t n = 1;
+    for (int i = 0; i < t->ndim; i++) n *= t->shape[i];
+    return n;
+}
+inline bool is_contiguous(const rten_tensor* t) {
+    int64_t s = 1;
+    for (int i = t->ndim - 1; i >= 0; i--) {
+        if (t->shape[i] != 1 && t->strides[i] != s) return false;
+        s *= t->shape[i];
+    }
+    return true;
+}
+inline void set_contiguous(rten_tensor* t) {
+    int64_t s = 1;
+    for (int i = t->ndim - 1; i >= 0; i--) {
+        t->strides[i] = s;
+        s *= t->shape[i];
+    }
+}
+// number of elements spanned from data (positive strides)
+inline int64_t span_elems(const rten_tensor* t) {
+    if (numel(t) == 0) return 0;
+    int64_t s = 1;
+    for (int i = 0; i < t->ndim; i++) s += (t->shape[i] - 1) * t->strides[i];
+    return s;
+}
+
+inline void count_launch(rten_ctx* ctx, int n = 1) { ctx->launches += (uint64_t)n; }
+
+}  // namespace rtb

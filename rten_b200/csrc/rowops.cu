@@ -1,0 +1,754 @@
+// HBM-bound kernels of the hot path: Softmax / AddSoftmax, LayerNormalization, Erf / Gelu,
+// DynamicQuantizeLinear, plus the layout / glue kernels that keep whole models resident.
+//
+// Accumulation ORDER follows the reference's AVX-512 path (16 f32 lanes, fold_unroll<4>), so
+// Softmax and LayerNormalization results are bit-identical to it, not merely close:
+//   softmax lane sums  : rten-vecmath/src/softmax.rs:192-228 (per-SIMD-lane partial sums, lanes summed in order)
+//   Sum / SumSquareSub : rten-vecmath/src/sum.rs:22-35,111-130 + rten-simd/src/iter.rs:70-120
+//   Normalize          : rten-vecmath/src/normalize.rs:101-169
+#include <cuda_runtime.h>
+
+#include <cfloat>
+#include <cstdint>
+
+#include "common.h"
+#include "math.cuh"
+#include "rowops.h"
+
+namespace rtb {
+
+constexpr int VL = 16;  // AVX-512 f32 lanes of the reference path
+
+// =========================================================================================
+// Softmax: one warp per row of n contiguous floats.
+// =========================================================================================
+struct SoftmaxParams {
+    const float* x;
+    float* y;
+    long long rows;
+    int n;
+    int flush_nan;
+    // optional mask, broadcast over up to 4 leading dims of x (row index decomposed over lead[])
+    const float* mask;
+    int nlead;
+    long long lead[4];
+    long long mstride[4];
+    long long mstride_last;
+};
+
+__global__ void __launch_bounds__(256) softmax_kernel(const SoftmaxParams p) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= p.rows) return;
+    const float* x = p.x + row * p.n;
+    float* y = p.y + row * p.n;
+    const float* m = nullptr;
+    if (p.mask) {
+        long long rem = row, off = 0;
+        for (int d = p.nlead - 1; d >= 0; d--) {
+            const long long idx = rem % p.lead[d];
+            rem /= p.lead[d];
+            off += idx * p.mstride[d];
+        }
+        m = p.mask + off;
+    }
+    const int n = p.n;
+    // pass 1: z = x (+ mask), max  (softmax.rs:176-190; max is order independent)
+    float mx = -FLT_MAX;
+    for (int i = lane; i < n; i += 32) {
+        float v = x[i];
+        if (m) v = __fadd_rn(v, m[(long long)i * p.mstride_last]);
+        mx = fmaxf(mx, v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    // pass 2: e = ReducedRangeExp(z - max); partial[l] accumulates elements i == l (mod 16) in
+    // ascending i -- thread l (< 16) adds its own element, then the one held by thread l + 16.
+    float partial = 0.0f;
+    for (int i0 = 0; i0 < n; i0 += 32) {
+        const int i = i0 + lane;
+        float e = 0.0f;
+        if (i < n) {
+            float v = x[i];
+            if (m) v = __fadd_rn(v, m[(long long)i * p.mstride_last]);
+            e = reduced_range_exp(__fsub_rn(v, mx));
+            y[i] = e;
+        }
+        const float e_hi = __shfl_down_sync(0xffffffffu, e, 16);
+        if (lane < VL) {
+            if (i < n) partial = __fadd_rn(partial, e);
+            if (i + 16 < n) partial = __fadd_rn(partial, e_hi);
+        }
+    }
+    float s = 0.0f;
+#pragma unroll
+    for (int l = 0; l < VL; l++) s = __fadd_rn(s, __shfl_sync(0xffffffffu, partial, l));
+    const float inv = __fdiv_rn(1.0f, s);
+    __syncwarp();
+    // pass 3: y = e * (1/sum), optional NaN flush
+    for (int i = lane; i < n; i += 32) {
+        float v = __fmul_rn(y[i], inv);
+        if (p.flush_nan && v != v) v = 0.0f;
+        y[i] = v;
+    }
+}
+
+rten_status launch_softmax(rten_ctx* ctx, const float* x, float* y, long long rows, int n, int flush_nan,
+                           const float* mask, int nlead, const long long* lead, const long long* mstride,
+                           long long mstride_last) {
+    if (rows == 0 || n == 0) return RTEN_OK;
+    SoftmaxParams p;
+    p.x = x;
+    p.y = y;
+    p.rows = rows;
+    p.n = n;
+    p.flush_nan = flush_nan;
+    p.mask = mask;
+    p.nlead = nlead;
+    for (int i = 0; i < 4; i++) {
+        p.lead[i] = i < nlead ? lead[i] : 1;
+        p.mstride[i] = i < nlead ? mstride[i] : 0;
+    }
+    p.mstride_last = mstride_last;
+    const int wpb = 8;
+    const long long blocks = (rows + wpb - 1) / wpb;
+    softmax_kernel<<<(unsigned)blocks, wpb * 32, 0, ctx->stream>>>(p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "softmax launch");
+    count_launch(ctx);
+    return RTEN_OK;
+}
+
+// =========================================================================================
+// LayerNormalization: one warp per row.
+// fold_unroll<4> with V=16: position p = i % 64 owns accumulator (u = p / 16, l = p % 16) for the
+// full 64-element chunks; thread t owns p = t and p = t + 32.
+// =========================================================================================
+template <bool SQSUB>
+__device__ __forceinline__ float fold_step(float acc, float x, float off) {
+    if (SQSUB) {
+        const float d = __fsub_rn(x, off);
+        return __fmaf_rn(d, d, acc);
+    }
+    return __fadd_rn(acc, x);
+}
+
+template <bool SQSUB>
+__device__ __forceinline__ float simd_fold_unroll4(const float* x, int n, float off, int lane) {
+    float a0 = 0.0f, a1 = 0.0f;
+    const int nfull = n / 64;
+    for (int c = 0; c < nfull; c++) {
+        a0 = fold_step<SQSUB>(a0, x[c * 64 + lane], off);
+        a1 = fold_step<SQSUB>(a1, x[c * 64 + 32 + lane], off);
+    }
+    // acc[0][l] = ((acc[0][l] + acc[1][l]) + acc[2][l]) + acc[3][l]
+    const float b = __shfl_down_sync(0xffffffffu, a0, 16);
+    const float d = __shfl_down_sync(0xffffffffu, a1, 16);
+    float acc = __fadd_rn(__fadd_rn(__fadd_rn(a0, b), a1), d);  // valid for lane < 16
+    // remaining full 16-chunks and the masked tail go into acc[0]
+    int i = nfull * 64;
+    if (lane < VL) {
+        for (; i + VL <= n; i += VL) acc = fold_step<SQSUB>(acc, x[i + lane], off);
+        if (i + lane < n) acc = fold_step<SQSUB>(acc, x[i + lane], off);
+    }
+    float s = 0.0f;
+#pragma unroll
+    for (int l = 0; l < VL; l++) s = __fadd_rn(s, __shfl_sync(0xffffffffu, acc, l));
+    return s;
+}
+
+struct LayerNormParams {
+    const float* x;
+    float* y;
+    long long rows;
+    int n;
+    const float* gamma;  // per element or null
+    float gamma_scalar;
+    const float* beta;  // per element or null
+    float beta_scalar;
+    float eps;
+};
+
+__global__ void __launch_bounds__(256) layer_norm_kernel(const LayerNormParams p) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= p.rows) return;
+    const float* x = p.x + row * p.n;
+    float* y = p.y + row * p.n;
+    const int n = p.n;
+    const float mean = __fdiv_rn(simd_fold_unroll4<false>(x, n, 0.0f, lane), (float)n);
+    const float var = __fdiv_rn(simd_fold_unroll4<true>(x, n, mean, lane), (float)n);
+    const float rstd = __fdiv_rn(p.gamma_scalar, __fsqrt_rn(__fadd_rn(var, p.eps)));
+    if (!p.gamma && !p.beta) {
+        for (int i = lane; i < n; i += 32) y[i] = __fmaf_rn(__fsub_rn(x[i], mean), rstd, p.beta_scalar);
+    } else if (p.gamma && !p.beta && p.beta_scalar == 0.0f) {
+        for (int i = lane; i < n; i += 32) y[i] = __fmul_rn(__fsub_rn(x[i], mean), __fmul_rn(p.gamma[i], rstd));
+    } else {
+        for (int i = lane; i < n; i += 32) {
+            const float sv = __fmul_rn(p.gamma ? p.gamma[i] : 1.0f, rstd);
+            const float bv = __fadd_rn(p.beta ? p.beta[i] : 0.0f, p.beta_scalar);
+            y[i] = __fmaf_rn(__fsub_rn(x[i], mean), sv, bv);
+        }
+    }
+}
+
+rten_status launch_layer_norm(rten_ctx* ctx, const float* x, float* y, long long rows, int n, const float* gamma,
+                              float gamma_scalar, const float* beta, float beta_scalar, float eps) {
+    if (rows == 0 || n == 0) return RTEN_OK;
+    LayerNormParams p{x, y, rows, n, gamma, gamma_scalar, beta, beta_scalar, eps};
+    const int wpb = 8;
+    const long long blocks = (rows + wpb - 1) / wpb;
+    layer_norm_kernel<<<(unsigned)blocks, wpb * 32, 0, ctx->stream>>>(p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "layer_norm launch");
+    count_launch(ctx);
+    return RTEN_OK;
+}
+
+// Row sums in the reference's Sum order (GlobalAveragePool = Sum / len, src/ops/pooling.rs:516-521).
+// Element k of row r lives at x[r_off(r) + k * kstride].
+__global__ void __launch_bounds__(256)
+row_mean_kernel(const float* x, float* y, long long rows, int n, long long rows_inner, long long s_outer,
+                long long s_inner, long long kstride) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const float* xr = x + (row / rows_inner) * s_outer + (row % rows_inner) * s_inner;
+    float a0 = 0.0f, a1 = 0.0f;
+    const int nfull = n / 64;
+    for (int c = 0; c < nfull; c++) {
+        a0 = __fadd_rn(a0, xr[(long long)(c * 64 + lane) * kstride]);
+        a1 = __fadd_rn(a1, xr[(long long)(c * 64 + 32 + lane) * kstride]);
+    }
+    const float b = __shfl_down_sync(0xffffffffu, a0, 16);
+    const float d = __shfl_down_sync(0xffffffffu, a1, 16);
+    float acc = __fadd_rn(__fadd_rn(__fadd_rn(a0, b), a1), d);
+    int i = nfull * 64;
+    if (lane < VL) {
+        for (; i + VL <= n; i += VL) acc = __fadd_rn(acc, xr[(long long)(i + lane) * kstride]);
+        if (i + lane < n) acc = __fadd_rn(acc, xr[(long long)(i + lane) * kstride]);
+    }
+    float s = 0.0f;
+#pragma unroll
+    for (int l = 0; l < VL; l++) s = __fadd_rn(s, __shfl_sync(0xffffffffu, acc, l));
+    if (lane == 0) y[row] = __fdiv_rn(s, (float)n);
+}
+
+rten_status launch_row_mean(rten_ctx* ctx, const float* x, float* y, long long rows, int n, long long rows_inner,
+                            long long s_outer, long long s_inner, long long kstride) {
+    if (rows == 0) return RTEN_OK;
+    const int wpb = 8;
+    row_mean_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, ctx->stream>>>(x, y, rows, n, rows_inner,
+                                                                                       s_outer, s_inner, kstride);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "row_mean launch");
+    count_launch(ctx);
+    return RTEN_OK;
+}
+
+// =========================================================================================
+// Elementwise (contiguous): Erf, Gelu, ApproxGelu, Relu, and same-shape Add (+ optional Relu)
+// 128-bit loads/stores, grid sized to fill the SMs.
+// =========================================================================================
+template <int OP>
+__device__ __forceinline__ float unary_apply(float v) {
+    if (OP == UNARY_ERF) return erf_ref(v);
+    if (OP == UNARY_GELU) return gelu_ref(v);
+    if (OP == UNARY_APPROX_GELU) return approx_gelu_ref(v);
+    return v > 0.0f ? v : 0.0f;  // UNARY_RELU
+}
+
+template <int OP>
+__global__ void __launch_bounds__(256)
+unary_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, int vec) {
+    const long long n4 = vec ? (n >> 2) : 0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i < n4; i += stride) {
+        float4 v = reinterpret_cast<const float4*>(x)[i];
+        v.x = unary_apply<OP>(v.x);
+        v.y = unary_apply<OP>(v.y);
+        v.z = unary_apply<OP>(v.z);
+        v.w = unary_apply<OP>(v.w);
+        reinterpret_cast<float4*>(y)[i] = v;
+    }
+    // tail (everything when the buffers are not 16-B aligned)
+    for (long long j = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride)
+        y[j] = unary_apply<OP>(x[j]);
+}
+
+static int ew_grid(rten_ctx* ctx, long long work_items) {
+    long long blocks = (work_items + 255) / 256;
+    long long cap = (long long)ctx->num_sms * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+rten_status launch_unary(rten_ctx* ctx, int op, const float* x, float* y, long long n) {
+    if (n == 0) return RTEN_OK;
+    const int vec = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0 ? 1 : 0;
+    const int grid = ew_grid(ctx, vec ? (n + 3) / 4 : n);
+    switch (op) {
+        case UNARY_ERF: unary_kernel<UNARY_ERF><<<grid, 256, 0, ctx->stream>>>(x, y, n, vec); break;
+        case UNARY_GELU: unary_kernel<UNARY_GELU><<<grid, 256, 0, ctx->stream>>>(x, y, n, vec); break;
+        case UNARY_APPROX_GELU: unary_kernel<UNARY_APPROX_GELU><<<grid, 256, 0, ctx->stream>>>(x, y, n, vec); break;
+        case UNARY_RELU: unary_kernel<UNARY_RELU><<<grid, 256, 0, ctx->stream>>>(x, y, n, vec); break;
+        default: return fail(ctx, RTEN_ERR_INVALID_VALUE, "unknown unary op");
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "unary launch");
+    count_launch(ctx);
+    return RTEN_OK;
+}
+
+// General N-d strided kernels (up to 8 dims): copy / broadcast add.  Used for layout changes
+// (NCHW <-> NHWC views, weight prepack), host staging of strided tensors and broadcast Add.
+struct NdParams {
+    int ndim;
+    long long shape[RTEN_MAX_DIMS];
+    long long sa[RTEN_MAX_DIMS];
+    long long sb[RTEN_MAX_DIMS];
+    long long sd[RTEN_MAX_DIMS];
+    long long n;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) nd_copy_kernel(const T* __restrict__ src, T* __restrict__ dst, const NdParams p) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += stride) {
+        long long rem = i, so = 0, dof = 0;
+#pragma unroll 1
+        for (int d = p.ndim - 1; d >= 0; d--) {
+            const long long idx = rem % p.shape[d];
+            rem /= p.shape[d];
+            so += idx * p.sa[d];
+            dof += idx * p.sd[d];
+        }
+        dst[dof] = src[so];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+nd_add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ d, const NdParams p, int relu) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += stride) {
+        long long rem = i, ao = 0, bo = 0, dof = 0;
+#pragma unroll 1
+        for (int k = p.ndim - 1; k >= 0; k--) {
+            const long long idx = rem % p.shape[k];
+            rem /= p.shape[k];
+            ao += idx * p.sa[k];
+            bo += idx * p.sb[k];
+            dof += idx * p.sd[k];
+        }
+        float v = __fadd_rn(a[ao], b[bo]);
+        if (relu) v = v > 0.0f ? v : 0.0f;
+        d[dof] = v;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+add_flat_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ d, long long n, int relu) {
+    const long long n4 = n >> 2;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const float4 x = reinterpret_cast<const float4*>(a)[i];
+        const float4 y = reinterpret_cast<const float4*>(b)[i];
+        float4 o = make_float4(__fadd_rn(x.x, y.x), __fadd_rn(x.y, y.y), __fadd_rn(x.z, y.z), __fadd_rn(x.w, y.w));
+        if (relu) {
+            o.x = o.x > 0.f ? o.x : 0.f;
+            o.y = o.y > 0.f ? o.y : 0.f;
+            o.z = o.z > 0.f ? o.z : 0.f;
+            o.w = o.w > 0.f ? o.w : 0.f;
+        }
+        reinterpret_cast<float4*>(d)[i] = o;
+    }
+    for (long long j = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+        float v = __fadd_rn(a[j], b[j]);
+        if (relu) v = v > 0.f ? v : 0.f;
+        d[j] = v;
+    }
+}
+
+// Collapse to the iteration order that makes the DESTINATION contiguous-fastest: dims are visited in
+// the given order; callers pass dims sorted so that the last has the smallest dst stride.
+rten_status launch_nd_copy(rten_ctx* ctx, int esize, const void* src, void* dst, int ndim, const long long* shape,
+                           const long long* sstride, const long long* dstride) {
+    NdParams p;
+    memset(&p, 0, sizeof(p));
+    p.ndim = ndim;
+    p.n = 1;
+    for (int i = 0; i < ndim; i++) {
+        p.shape[i] = shape[i];
+        p.sa[i] = sstride[i];
+        p.sd[i] = dstride[i];
+        p.n *= shape[i];
+    }
+    if (p.n == 0) return RTEN_OK;
+    const int grid = ew_grid(ctx, p.n);
+    if (esize == 4)
+        nd_copy_kernel<uint32_t><<<grid, 256, 0, ctx->stream>>>((const uint32_t*)src, (uint32_t*)dst, p);
+    else if (esize == 1)
+        nd_copy_kernel<uint8_t><<<grid, 256, 0, ctx->stream>>>((const uint8_t*)src, (uint8_t*)dst, p);
+    else
+        return fail(ctx, RTEN_ERR_UNSUPPORTED_TYPE, "unsupported element size");
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "nd_copy launch");
+    count_launch(ctx);
+    return RTEN_OK;
+}
+
+rten_status launch_nd_add(rten_ctx* ctx, const float* a, const float* b, float* d, int ndim, const long long* shape,
+                          const long long* sa, const long long* sb, const long long* sd, int relu) {
+    NdParams p;
+    memset(&p, 0, sizeof(p));
+    p.ndim = ndim;
+    p.n = 1;
+    for (int i = 0; i < ndim; i++) {
+        p.shape[i] = shape[i];
+        p.sa[i] = sa[i];
+        p.sb[i] = sb[i];
+        p.sd[i] = sd[i];
+        p.n *= shape[i];
+    }
+    if (p.n == 0) return RTEN_OK;
+    nd_add_kernel<<<ew_grid(ctx, p.n), 256, 0, ctx->stream>>>(a, b, d, p, relu);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "nd_add launch");
+    count_launch(ctx);
+    return RTEN_OK;
+}
+
+rten_status launch_add_flat(rten_ctx* ctx, const float* a, const float* b, float* d, long long n, int relu) {
+    if (n == 0) return RTEN_OK;
+    const bool aligned =
+        ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(d)) & 15) == 0;
+    if (!aligned) {
+        long long shape[1] = {n}, s1[1] = {1};
+        return launch_nd_add(ctx, a, b, d, 1, shape, s1, s1, s1, relu);
+    }
+    add_flat_kernel<<<ew_grid(ctx, (n + 3) / 4), 256, 0, ctx->stream>>>(a, b, d, n, relu);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "add launch");
+    count_launch(ctx);
+    return RTEN_OK;
+}
+
+// =========================================================================================
+// DynamicQuantizeLinear (src/ops/quantize.rs:352-434; rten-vecmath/src/quantize.rs:38-77)
+//   pass 1: min / max  (order independent) -> 2 floats (ordered-int atomics)
+//   pass 2: scale, zero point (every thread recomputes the 6 scalar ops) + quantise
+// =========================================================================================
+__device__ __forceinline__ int float_to_ordered(float f) {
+    int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float ordered_to_float(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+__global__ void minmax_init_kernel(int* mm) {
+    mm[0] = float_to_ordered(__int_as_float(0x7f800000));  // +inf
+    mm[1] = float_to_ordered(__int_as_float(0xff800000));  // -inf
+}
+
+__global__ void __launch_bounds__(256) minmax_kernel(const float* __restrict__ x, long long n, int* mm) {
+    float lo = __int_as_float(0x7f800000), hi = __int_as_float(0xff800000);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long n4 = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) ? (n >> 2) : 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const float4 v = reinterpret_cast<const float4*>(x)[i];
+        lo = fminf(fminf(lo, v.x), fminf(v.y, fminf(v.z, v.w)));
+        hi = fmaxf(fmaxf(hi, v.x), fmaxf(v.y, fmaxf(v.z, v.w)));
+    }
+    for (long long j = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+        lo = fminf(lo, x[j]);
+        hi = fmaxf(hi, x[j]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    __shared__ float slo[8], shi[8];
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) {
+        slo[w] = lo;
+        shi[w] = hi;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < 8; k++) {
+            lo = fminf(lo, slo[k]);
+            hi = fmaxf(hi, shi[k]);
+        }
+        atomicMin(&mm[0], float_to_ordered(lo));
+        atomicMax(&mm[1], float_to_ordered(hi));
+    }
+}
+
+__device__ __forceinline__ void dql_params(const int* mm, float& scale, float& inv_scale, int& zp) {
+    const float x_min = ordered_to_float(mm[0]), x_max = ordered_to_float(mm[1]);
+    const float lo = fminf(x_min, 0.0f), hi = fmaxf(x_max, 0.0f);
+    scale = __fdiv_rn(__fsub_rn(hi, lo), 255.0f);
+    const float min_scaled = __fdiv_rn(lo, scale);
+    float z = __fsub_rn(0.0f, min_scaled);
+    z = fminf(fmaxf(z, 0.0f), 255.0f);  // clamp (NaN -> 0 after the cast below)
+    z = rintf(z);                       // round_ties_even
+    zp = (z != z) ? 0 : (int)z;
+    inv_scale = __fdiv_rn(1.0f, scale);
+}
+
+__device__ __forceinline__ int rne_i32_x86(float v) {
+    if (!(v >= -2147483648.0f && v < 2147483648.0f)) return (int)0x80000000;
+    return __float2int_rn(v);
+}
+__device__ __forceinline__ uint8_t quant1(float x, float inv_scale, int zp) {
+    long long q = (long long)rne_i32_x86(__fmul_rn(x, inv_scale)) + zp;
+    q = q < 0 ? 0 : (q > 255 ? 255 : q);
+    return (uint8_t)q;
+}
+
+__global__ void __launch_bounds__(256)
+dql_quantize_kernel(const float* __restrict__ x, uint8_t* __restrict__ y, long long n, const int* mm, float* scale_out,
+                    uint8_t* zp_out) {
+    float scale, inv;
+    int zp;
+    dql_params(mm, scale, inv, zp);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        *scale_out = scale;
+        *zp_out = (uint8_t)zp;
+    }
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const bool al = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((reinterpret_cast<uintptr_t>(y) & 3) == 0);
+    const long long n4 = al ? (n >> 2) : 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const float4 v = reinterpret_cast<const float4*>(x)[i];
+        uchar4 o;
+        o.x = quant1(v.x, inv, zp);
+        o.y = quant1(v.y, inv, zp);
+        o.z = quant1(v.z, inv, zp);
+        o.w = quant1(v.w, inv, zp);
+        reinterpret_cast<uchar4*>(y)[i] = o;
+    }
+    for (long long j = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride)
+        y[j] = quant1(x[j], inv, zp);
+}
+
+rten_status launch_minmax(rten_ctx* ctx, const float* x, long long n, int* mm) {
+    minmax_init_kernel<<<1, 1, 0, ctx->stream>>>(mm);
+    count_launch(ctx);
+    if (n > 0) {
+        minmax_kernel<<<ew_grid(ctx, (n + 3) / 4), 256, 0, ctx->stream>>>(x, n, mm);
+        count_launch(ctx);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "minmax launch");
+    return RTEN_OK;
+}
+
+rten_status launch_dql_quantize(rten_ctx* ctx, const float* x, uint8_t* y, long long n, const int* mm, float* scale_out,
+                                uint8_t* zp_out) {
+    dql_quantize_kernel<<<ew_grid(ctx, (n + 3) / 4), 256, 0, ctx->stream>>>(x, y, n, mm, scale_out, zp_out);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "dql launch");
+    count_launch(ctx);
+    return RTEN_OK;
+}
+
+// =========================================================================================
+// Integer helpers for the zero-point epilogue
+// =========================================================================================
+// sums over k of an 8-bit [rows, K] K-major matrix (row stride ld) -> i32
+__global__ void __launch_bounds__(256)
+rowsum8_kernel(const uint8_t* __restrict__ a, int is_signed, long long rows, int K, long long ld, int* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const uint8_t* r = a + row * ld;
+    int s = 0;
+    for (int k = lane; k < K; k += 32) s += is_signed ? (int)(int8_t)r[k] : (int)r[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[row] = s;
+}
+
+rten_status launch_rowsum8(rten_ctx* ctx, const void* a, int is_signed, long long rows, int K, long long ld, int* out) {
+    if (rows == 0) return RTEN_OK;
+    const int wpb = 8;
+    rowsum8_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, ctx->stream>>>((const uint8_t*)a, is_signed, rows,
+                                                                                      K, ld, out);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "rowsum launch");
+    count_launch(ctx);
+    return RTEN_OK;
+}
+
+// zero points (u8 or i8, element stride zs) -> i32
+__global__ void zp_to_i32_kernel(const uint8_t* zp, int is_signed, int n, long long zs, int* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = is_signed ? (int)(int8_t)zp[i * zs] : (int)zp[i * zs];
+}
+
+rten_status launch_zp_to_i32(rten_ctx* ctx, const void* zp, int is_signed, int n, long long zs, int* out) {
+    if (n == 0) return RTEN_OK;
+    zp_to_i32_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>((const uint8_t*)zp, is_signed, n, zs, out);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "zp_to_i32 launch");
+    count_launch(ctx);
+    return RTEN_OK;
+}
+
+__global__ void fill8_kernel(uint8_t* p, long long n, uint8_t v) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = v;
+}
+rten_status launch_fill8(rten_ctx* ctx, void* p, long long n, uint8_t v) {
+    if (n == 0) return RTEN_OK;
+    fill8_kernel<<<ew_grid(ctx, n), 256, 0, ctx->stream>>>((uint8_t*)p, n, v);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "fill launch");
+    count_launch(ctx);
+    return RTEN_OK;
+}
+
+// cast_scale (src/ops/matmul.rs:734-773) for the unfused case
+__global__ void __launch_bounds__(256)
+cast_scale_kernel(const int* __restrict__ in, float* __restrict__ out, long long n, int cols, const float* scale,
+                  int scale_len) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = __fmul_rn(__int2float_rn(in[i]), scale[scale_len == 1 ? 0 : (int)(i % cols)]);
+}
+rten_status launch_cast_scale(rten_ctx* ctx, const int* in, float* out, long long n, int cols, const float* scale,
+                              int scale_len) {
+    if (n == 0) return RTEN_OK;
+    cast_scale_kernel<<<ew_grid(ctx, n), 256, 0, ctx->stream>>>(in, out, n, cols, scale, scale_len);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "cast_scale launch");
+    count_launch(ctx);
+    return RTEN_OK;
+}
+
+// =========================================================================================
+// Explicit im2col (fallback for convolutions the TMA path cannot address: C*esize % 16 != 0, groups)
+// out[(b,oy,ox), (ky,kx,c)] with row pitch kpad; taps outside the image get `pad_value`.
+// =========================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256)
+im2col_kernel(const T* __restrict__ x, T* __restrict__ out, Im2ColParams p, T pad_value) {
+    const long long total = (long long)p.B * p.OH * p.OW * p.kpad;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int k = (int)(i % p.kpad);
+        const long long pix = i / p.kpad;
+        T v = 0;
+        if (k < p.kh * p.kw * p.C) {
+            const int c = k % p.C;
+            const int tap = k / p.C;
+            const int kx = tap % p.kw, ky = tap / p.kw;
+            const int ox = (int)(pix % p.OW);
+            const long long r2 = pix / p.OW;
+            const int oy = (int)(r2 % p.OH);
+            const int b = (int)(r2 / p.OH);
+            const int iy = oy * p.sy - p.pt + ky * p.dy;
+            const int ix = ox * p.sx - p.pl + kx * p.dx;
+            if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W)
+                v = x[(long long)b * p.xs_b + (long long)(c + p.c0) * p.xs_c + (long long)iy * p.xs_h + (long long)ix * p.xs_w];
+            else
+                v = pad_value;
+        }
+        out[i] = v;
+    }
+}
+
+rten_status launch_im2col(rten_ctx* ctx, int esize, const void* x, void* out, const Im2ColParams& p, int pad_value) {
+    const long long total = (long long)p.B * p.OH * p.OW * p.kpad;
+    if (total == 0) return RTEN_OK;
+    if (esize == 4) {
+        float pv = 0.0f;
+        im2col_kernel<float><<<ew_grid(ctx, total), 256, 0, ctx->stream>>>((const float*)x, (float*)out, p, pv);
+    } else {
+        im2col_kernel<uint8_t><<<ew_grid(ctx, total), 256, 0, ctx->stream>>>((const uint8_t*)x, (uint8_t*)out, p,
+                                                                             (uint8_t)pad_value);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "im2col launch");
+    count_launch(ctx);
+    return RTEN_OK;
+}
+
+// =========================================================================================
+// Pooling / gather
+// =========================================================================================
+__global__ void __launch_bounds__(256) maxpool_kernel(const float* __restrict__ x, float* __restrict__ y, PoolParams p) {
+    const long long total = (long long)p.B * p.C * p.OH * p.OW;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        int b, c, oy, ox;
+        long long rem = i;
+        if (p.channels_fastest) {
+            c = (int)(rem % p.C);
+            rem /= p.C;
+            ox = (int)(rem % p.OW);
+            rem /= p.OW;
+            oy = (int)(rem % p.OH);
+            b = (int)(rem / p.OH);
+        } else {
+            ox = (int)(rem % p.OW);
+            rem /= p.OW;
+            oy = (int)(rem % p.OH);
+            rem /= p.OH;
+            c = (int)(rem % p.C);
+            b = (int)(rem / p.C);
+        }
+        float m = __int_as_float(0xff800000);
+        for (int ky = 0; ky < p.kh; ky++) {
+            const int iy = oy * p.sy - p.pt + ky;
+            if (iy < 0 || iy >= p.H) continue;
+            for (int kx = 0; kx < p.kw; kx++) {
+                const int ix = ox * p.sx - p.pl + kx;
+                if (ix < 0 || ix >= p.W) continue;
+                const float v = x[(long long)b * p.xs_b + (long long)c * p.xs_c + (long long)iy * p.xs_h + (long long)ix * p.xs_w];
+                m = v > m ? v : m;
+            }
+        }
+        y[(long long)b * p.ys_b + (long long)c * p.ys_c + (long long)oy * p.ys_h + (long long)ox * p.ys_w] = m;
+    }
+}
+
+rten_status launch_maxpool(rten_ctx* ctx, const float* x, float* y, const PoolParams& p) {
+    const long long total = (long long)p.B * p.C * p.OH * p.OW;
+    if (total == 0) return RTEN_OK;
+    maxpool_kernel<<<ew_grid(ctx, total), 256, 0, ctx->stream>>>(x, y, p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "maxpool launch");
+    count_launch(ctx);
+    return RTEN_OK;
+}
+
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const float* __restrict__ table, const int* __restrict__ idx, float* __restrict__ out, long long nidx,
+                   int width, long long t_rs, long long t_cs, long long rows) {
+    const long long total = nidx * width;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const long long r = i / width;
+        const int c = (int)(i % width);
+        long long id = idx[r];
+        if (id < 0) id += rows;  // negative indices count from the end (src/ops/gather.rs)
+        out[i] = table[id * t_rs + c * t_cs];
+    }
+}
+
+rten_status launch_gather_rows(rten_ctx* ctx, const float* table, const int* idx, float* out, long long nidx, int width,
+                               long long t_rs, long long t_cs, long long rows) {
+    if (nidx * width == 0) return RTEN_OK;
+    gather_rows_kernel<<<ew_grid(ctx, nidx * width), 256, 0, ctx->stream>>>(table, idx, out, nidx, width, t_rs, t_cs,
+                                                                            rows);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "gather launch");
+    count_launch(ctx);
+    return RTEN_OK;
+}
+
+}  // namespace rtb

@@ -1,0 +1,531 @@
+// tcgen05 GEMM / implicit-GEMM convolution for sm_100a.
+//
+// Replaces rten-gemm's packed BLIS-style GEMM (rten-gemm/src/lib.rs:794-1093, micro-kernels
+// rten-gemm/src/kernels/simd_generic.rs:285,576) and the im2col packing
+// (rten-gemm/src/im2col.rs:110-389) on the MatMul / MatMulInteger / Conv / ConvInteger path.
+//
+// Persistent, warp-specialised kernel, one CTA per SM (256 threads):
+//   warp 0   : TMA producer   -- cp.async.bulk.tensor tiles of A (128 rows x 128 B) and B (bn rows x 128 B)
+//                                into a ring of 128B-swizzled shared-memory stages
+//   warp 1   : MMA issuer     -- one elected thread issues tcgen05.mma (kind::tf32 or kind::i8),
+//                                4 instructions per 128-byte K block, accumulating in TMEM
+//   warp 2   : TMEM allocator -- 512 columns = 2 accumulator stages of up to 256 columns
+//   warps 4-7: epilogue       -- tcgen05.ld accumulator rows -> registers -> fused epilogue
+//                                (alpha, residual/beta*C, bias, activation; or the integer zero-point
+//                                correction and cast*scale) -> global memory.  Runs concurrently with
+//                                the next tile's main loop thanks to the second TMEM stage.
+// For Conv the A tile is a TMA box over the NHWC activation tensor at (c0, ox0*sx - pad + kx*dx,
+// oy0*sy - pad + ky*dy, b0): padding comes from TMA out-of-bounds zero fill, the stride from the
+// tensor map's element strides; the im2col matrix is never materialised.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdint>
+
+#include "math.cuh"
+#include "ptx.cuh"
+#include "umma_gemm.h"
+
+namespace rtb {
+
+constexpr int BM = 128;            // UMMA M (cta_group::1)
+constexpr int KBYTES = 128;        // bytes of K per stage row = one 128B swizzle atom
+constexpr int A_STAGE_BYTES = BM * KBYTES;
+constexpr int TMEM_COLS = 512;
+constexpr int ACC_STRIDE = 256;    // TMEM columns per accumulator stage
+constexpr int NUM_THREADS = 256;
+constexpr int MAX_STAGES = 8;
+
+struct KParams {
+    int M, N, K, z0, z1;
+    int tiles_m, tiles_n, tiles_total;
+    int k_blocks, kelems;
+    int bn, stages;
+    uint32_t stage_bytes, tx_bytes;
+    uint32_t idesc;
+    int conv;
+    int tw, th, tb, tiles_x, tiles_y;
+    int OH, OW, Bn;
+    int sy, sx, dy, dx, pt, pl, kw, c_blocks;
+    int a_bcast0, a_bcast1, b_bcast0, b_bcast1;
+    EpilogueDesc epi;
+};
+
+struct TileCoord {
+    int n0;
+    int m0;          // plain: first row; conv: unused
+    int z0, z1;      // plain batch coords
+    int ox0, oy0, b0;  // conv
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const KParams& p, int t) {
+    TileCoord c;
+    int n_blk = t % p.tiles_n;
+    int rest = t / p.tiles_n;
+    int m_blk = rest % p.tiles_m;
+    int z = rest / p.tiles_m;
+    c.n0 = n_blk * p.bn;
+    c.m0 = m_blk * BM;
+    c.z0 = z % p.z0;
+    c.z1 = z / p.z0;
+    c.ox0 = c.oy0 = c.b0 = 0;
+    if (p.conv) {
+        int xt = m_blk % p.tiles_x;
+        int r2 = m_blk / p.tiles_x;
+        int yt = r2 % p.tiles_y;
+        int bt = r2 / p.tiles_y;
+        c.ox0 = xt * p.tw;
+        c.oy0 = yt * p.th;
+        c.b0 = bt * p.tb;
+    }
+    return c;
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                 const KParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    // 1024-B alignment required by the 128B swizzle atoms / UMMA descriptors (base_offset = 0).
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * p.stage_bytes);
+    uint64_t* empty_bar = full_bar + MAX_STAGES;
+    uint64_t* tmem_full = empty_bar + MAX_STAGES;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tma_a);
+        tma_prefetch_desc(&tma_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < p.stages; s++) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; s++) {
+            mbar_init(&tmem_full[s], 1);
+            mbar_init(&tmem_empty[s], 4);  // one arrival per epilogue warp
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_ptr, TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < p.tiles_total; t += gridDim.x) {
+                const TileCoord tc = decode_tile(p, t);
+                for (int kb = 0; kb < p.k_blocks; kb++) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + (size_t)stage * p.stage_bytes;
+                    uint8_t* sb = sa + A_STAGE_BYTES;
+                    mbar_expect_tx(&full_bar[stage], p.tx_bytes);
+                    if (p.conv) {
+                        const int tap = kb / p.c_blocks;
+                        const int cb = kb - tap * p.c_blocks;
+                        const int ky = tap / p.kw;
+                        const int kx = tap - ky * p.kw;
+                        tma_load_4d(sa, &tma_a, &full_bar[stage], cb * p.kelems, tc.ox0 * p.sx - p.pl + kx * p.dx,
+                                    tc.oy0 * p.sy - p.pt + ky * p.dy, tc.b0);
+                        tma_load_4d(sb, &tma_b, &full_bar[stage], cb * p.kelems, tc.n0, tap, 0);
+                    } else {
+                        tma_load_4d(sa, &tma_a, &full_bar[stage], kb * p.kelems, tc.m0, p.a_bcast0 ? 0 : tc.z0,
+                                    p.a_bcast1 ? 0 : tc.z1);
+                        tma_load_4d(sb, &tma_b, &full_bar[stage], kb * p.kelems, tc.n0, p.b_bcast0 ? 0 : tc.z0,
+                                    p.b_bcast1 ? 0 : tc.z1);
+                    }
+                    if (++stage == p.stages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int t = blockIdx.x; t < p.tiles_total; t += gridDim.x, it++) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
+                for (int kb = 0; kb < p.k_blocks; kb++) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + (size_t)stage * p.stage_bytes);
+                    const uint64_t adesc = make_kmajor_sw128_desc(sa);
+                    const uint64_t bdesc = make_kmajor_sw128_desc(sa + A_STAGE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        // advance 32 B along K inside the swizzle atom: +2 in the (addr >> 4) field
+                        const uint32_t accum = (kb | k) != 0 ? 1u : 0u;
+                        if (KIND == 0)
+                            umma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, accum);
+                        else
+                            umma_i8(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, accum);
+                    }
+                    umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+                    if (++stage == p.stages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        const EpilogueDesc& e = p.epi;
+        const int q = warp & 3;  // TMEM lane quadrant this warp may access
+        const int r = q * 32 + lane;
+        int it = 0;
+        for (int t = blockIdx.x; t < p.tiles_total; t += gridDim.x, it++) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            const TileCoord tc = decode_tile(p, t);
+            // ---- row bookkeeping
+            bool row_ok;
+            long long d_off, r_off;
+            int m_idx;
+            if (p.conv) {
+                const int xi = r % p.tw;
+                const int r2 = r / p.tw;
+                const int yi = r2 % p.th;
+                const int bi = r2 / p.th;
+                const int ox = tc.ox0 + xi, oy = tc.oy0 + yi, b = tc.b0 + bi;
+                row_ok = (bi < p.tb) && (ox < p.OW) && (oy < p.OH) && (b < p.Bn);
+                d_off = (long long)b * e.s_z0 + (long long)oy * e.s_row + (long long)ox * e.s_z1;
+                r_off = (long long)b * e.r_z0 + (long long)oy * e.r_row + (long long)ox * e.r_z1;
+                m_idx = (b * p.OH + oy) * p.OW + ox;
+            } else {
+                const int m = tc.m0 + r;
+                row_ok = m < p.M;
+                d_off = (long long)tc.z0 * e.s_z0 + (long long)tc.z1 * e.s_z1 + (long long)m * e.s_row;
+                r_off = (long long)tc.z0 * e.r_z0 + (long long)tc.z1 * e.r_z1 + (long long)m * e.r_row;
+                m_idx = m;
+            }
+            float row_bias = 0.0f;
+            int za_v = 0, rs_v = 0;
+            if (row_ok) {
+                if (KIND == 0) {
+                    if (e.bias_kind == 2) row_bias = e.bias[m_idx];
+                } else {
+                    if (e.za) za_v = e.za[m_idx % e.za_len];
+                    if (e.zb) rs_v = e.rowsum[m_idx];
+                }
+            }
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_STRIDE;
+            for (int c0 = 0; c0 < p.bn; c0 += 32) {
+                uint32_t v[32];
+                const int ncols = (p.bn - c0) >= 32 ? 32 : 16;
+                if (ncols == 32) {
+                    tmem_ld_32x32(t_row + c0, v);
+                } else {
+                    uint32_t w[16];
+                    tmem_ld_32x16(t_row + c0, w);
+#pragma unroll
+                    for (int j = 0; j < 16; j++) v[j] = w[j];
+#pragma unroll
+                    for (int j = 16; j < 32; j++) v[j] = 0;
+                }
+                tmem_ld_wait();
+                const int nbase = tc.n0 + c0;
+                if (!row_ok) {
+                    // nothing to store for this row; stay converged for the next aligned tcgen05.ld
+                } else if (KIND == 0) {
+                    float* dptr = reinterpret_cast<float*>(e.d) + d_off;
+                    const bool vec = (e.s_col == 1) && (nbase + ncols <= p.N) &&
+                                     ((reinterpret_cast<uintptr_t>(dptr + nbase) & 15) == 0) &&
+                                     (e.r == nullptr || (e.r_col == 1 && ((reinterpret_cast<uintptr_t>(e.r + r_off + nbase) & 15) == 0)));
+                    if (vec) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            if (j < ncols) {
+                                float o[4];
+                                float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (e.r) rv = *reinterpret_cast<const float4*>(e.r + r_off + nbase + j);
+                                const float rr[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                                for (int u = 0; u < 4; u++) {
+                                    float x = __uint_as_float(v[j + u]) * e.alpha;
+                                    if (e.r) x = fmaf(e.r_scale, rr[u], x);
+                                    if (e.bias_kind == 1) x += e.bias[nbase + j + u];
+                                    x += row_bias;
+                                    o[u] = apply_act(x, e.act);
+                                }
+                                *reinterpret_cast<float4*>(dptr + nbase + j) = make_float4(o[0], o[1], o[2], o[3]);
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) {
+                            const int n = nbase + j;
+                            if (j < ncols && n < p.N) {
+                                float x = __uint_as_float(v[j]) * e.alpha;
+                                if (e.r) x = fmaf(e.r_scale, e.r[r_off + (long long)n * e.r_col], x);
+                                if (e.bias_kind == 1) x += e.bias[n];
+                                x += row_bias;
+                                dptr[(long long)n * e.s_col] = apply_act(x, e.act);
+                            }
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        const int n = nbase + j;
+                        if (j < ncols && n < p.N) {
+                            // exact i32 arithmetic with wrap-around (unsigned ops)
+                            unsigned c = v[j];
+                            if (e.za) c -= (unsigned)za_v * (unsigned)e.colsum[n];
+                            if (e.zb) {
+                                const unsigned zbv = (unsigned)e.zb[n % e.zb_len];
+                                c -= zbv * (unsigned)rs_v;
+                                if (e.za) c += (unsigned)p.K * (unsigned)za_v * zbv;
+                            }
+                            const long long off = d_off + (long long)n * e.s_col;
+                            if (e.scale) {
+                                reinterpret_cast<float*>(e.d)[off] = __int2float_rn((int)c) * e.scale[n % e.scale_len];
+                            } else {
+                                reinterpret_cast<int*>(e.d)[off] = (int)c;
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode(rten_ctx* ctx) {
+    if (!ctx->encode_tiled) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            return nullptr;
+        ctx->encode_tiled = fn;
+    }
+    return reinterpret_cast<EncodeTiledFn>(ctx->encode_tiled);
+}
+
+bool tma_compatible(const OperandDesc& od, int esize, int rank) {
+    if (reinterpret_cast<uintptr_t>(od.base) & 15) return false;
+    if (od.strides[0] != 1) return false;
+    for (int i = 1; i < rank; i++) {
+        if (od.dims[i] > 1) {
+            if ((od.strides[i] * esize) % 16 != 0) return false;
+            if (od.strides[i] * esize >= (1ll << 40)) return false;
+        }
+    }
+    for (int i = 0; i < rank; i++)
+        if (od.dims[i] < 1 || od.dims[i] > 0xFFFFFFFFll) return false;
+    return true;
+}
+
+static bool encode_map(rten_ctx* ctx, CUtensorMap* map, const OperandDesc& od, int esize, bool is_f32,
+                       const uint32_t box[4], const uint32_t estr[4]) {
+    EncodeTiledFn enc = get_encode(ctx);
+    if (!enc) return false;
+    cuuint64_t dims[4];
+    cuuint64_t strides[3];
+    cuuint32_t b[4], es[4];
+    for (int i = 0; i < 4; i++) {
+        dims[i] = (cuuint64_t)od.dims[i];
+        b[i] = box[i];
+        es[i] = estr[i];
+    }
+    for (int i = 1; i < 4; i++) {
+        long long s = od.strides[i] * esize;
+        // size-1 / broadcast dims: any legal multiple of 16 works, the coordinate is always 0
+        if (s == 0 || od.dims[i] == 1) s = 16;
+        strides[i - 1] = (cuuint64_t)s;
+    }
+    CUresult r = enc(map, is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 4,
+                     const_cast<void*>(od.base), dims, strides, b, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+// Pick the output-pixel box (tw x th x tb <= 128 rows) that wastes the fewest MMA rows.
+static void pick_conv_tile(const ConvGeom& g, int& tw, int& th, int& tb) {
+    double best = -1.0;
+    tw = th = tb = 1;
+    for (int w = 1; w <= std::min(g.OW, 128); w++) {
+        if (w * g.sx > 256) break;
+        for (int h = 1; h <= std::min(g.OH, 128 / w); h++) {
+            if (h * g.sy > 256) break;
+            int b = std::min(g.B, 128 / (w * h));
+            if (b < 1) continue;
+            long long tiles = (long long)((g.OW + w - 1) / w) * ((g.OH + h - 1) / h) * ((g.B + b - 1) / b);
+            double eff = (double)g.B * g.OH * g.OW / ((double)tiles * 128.0);
+            // prefer wider boxes on ties (longer contiguous runs for TMA and the epilogue)
+            if (eff > best + 1e-9 || (eff > best - 1e-9 && w > tw)) {
+                best = eff;
+                tw = w;
+                th = h;
+                tb = b;
+            }
+        }
+    }
+}
+
+static int pick_bn(int N, long long tiles_m_total, int num_sms) {
+    // minimise (waves) x (per-tile cost ~ bn + fixed overhead)
+    int best_bn = 16;
+    double best_cost = 1e30;
+    int n16 = (N + 15) / 16 * 16;
+    for (int bn = 16; bn <= 256; bn += 16) {
+        if (bn > n16 && bn != 16) break;
+        long long tiles = tiles_m_total * ((N + bn - 1) / bn);
+        long long waves = (tiles + num_sms - 1) / num_sms;
+        double cost = (double)waves * (bn + 24.0);
+        if (cost < best_cost - 1e-9) {
+            best_cost = cost;
+            best_bn = bn;
+        }
+    }
+    return best_bn;
+}
+
+rten_status launch_umma_gemm(rten_ctx* ctx, const GemmLaunch& L) {
+    const int esize = L.kind == 0 ? 4 : 1;
+    const int kelems = KBYTES / esize;
+    if (!tma_compatible(L.a, esize, 4) || !tma_compatible(L.b, esize, 4)) return RTEN_ERR_UNSUPPORTED_VALUE;
+    if (L.M <= 0 || L.N <= 0 || L.K <= 0) return RTEN_ERR_UNSUPPORTED_VALUE;
+
+    KParams p;
+    memset(&p, 0, sizeof(p));
+    p.M = L.M;
+    p.N = L.N;
+    p.K = L.K;
+    p.z0 = L.z0;
+    p.z1 = L.z1;
+    p.kelems = kelems;
+    p.conv = L.conv;
+    p.epi = L.epi;
+    uint32_t abox[4], aes[4] = {1, 1, 1, 1}, bbox[4], bes[4] = {1, 1, 1, 1};
+    long long tiles_m_total;
+    uint32_t a_rows;
+    if (L.conv) {
+        const ConvGeom& g = L.g;
+        pick_conv_tile(g, p.tw, p.th, p.tb);
+        p.tiles_x = (g.OW + p.tw - 1) / p.tw;
+        p.tiles_y = (g.OH + p.th - 1) / p.th;
+        int tiles_b = (g.B + p.tb - 1) / p.tb;
+        p.tiles_m = p.tiles_x * p.tiles_y * tiles_b;
+        p.OH = g.OH;
+        p.OW = g.OW;
+        p.Bn = g.B;
+        p.sy = g.sy;
+        p.sx = g.sx;
+        p.dy = g.dy;
+        p.dx = g.dx;
+        p.pt = g.pt;
+        p.pl = g.pl;
+        p.kw = g.kw;
+        p.c_blocks = (g.C + kelems - 1) / kelems;
+        p.k_blocks = g.kh * g.kw * p.c_blocks;
+        p.z0 = p.z1 = 1;
+        abox[0] = kelems;
+        abox[1] = p.tw * g.sx;
+        abox[2] = p.th * g.sy;
+        abox[3] = p.tb;
+        aes[1] = g.sx;
+        aes[2] = g.sy;
+        a_rows = p.tw * p.th * p.tb;
+        tiles_m_total = p.tiles_m;
+    } else {
+        p.tiles_m = (L.M + BM - 1) / BM;
+        p.k_blocks = (L.K + kelems - 1) / kelems;
+        abox[0] = kelems;
+        abox[1] = BM;
+        abox[2] = 1;
+        abox[3] = 1;
+        a_rows = BM;
+        tiles_m_total = (long long)p.tiles_m * L.z0 * L.z1;
+        p.a_bcast0 = (L.a.dims[2] == 1 && L.z0 > 1) ? 1 : 0;
+        p.a_bcast1 = (L.a.dims[3] == 1 && L.z1 > 1) ? 1 : 0;
+        p.b_bcast0 = (L.b.dims[2] == 1 && L.z0 > 1) ? 1 : 0;
+        p.b_bcast1 = (L.b.dims[3] == 1 && L.z1 > 1) ? 1 : 0;
+    }
+    p.bn = pick_bn(L.N, tiles_m_total, ctx->num_sms);
+    p.tiles_n = (L.N + p.bn - 1) / p.bn;
+    long long tt = tiles_m_total * p.tiles_n;
+    if (tt > 0x7FFFFFFFll) return RTEN_ERR_UNSUPPORTED_VALUE;
+    p.tiles_total = (int)tt;
+    bbox[0] = kelems;
+    bbox[1] = p.bn;
+    bbox[2] = 1;
+    bbox[3] = 1;
+    p.stage_bytes = A_STAGE_BYTES + p.bn * KBYTES;
+    p.tx_bytes = a_rows * KBYTES + p.bn * KBYTES;
+    const int smem_budget = 227 * 1024 - 2048;
+    p.stages = std::min(MAX_STAGES, smem_budget / (int)p.stage_bytes);
+    if (p.stages < 2) return RTEN_ERR_UNSUPPORTED_VALUE;
+    if (L.kind == 0)
+        p.idesc = make_idesc(1 /*F32*/, 2 /*TF32*/, 2, BM, p.bn);
+    else
+        p.idesc = make_idesc(2 /*S32*/, L.a_signed ? 1 : 0, L.b_signed ? 1 : 0, BM, p.bn);
+
+    CUtensorMap map_a, map_b;
+    if (!encode_map(ctx, &map_a, L.a, esize, L.kind == 0, abox, aes)) return RTEN_ERR_UNSUPPORTED_VALUE;
+    if (!encode_map(ctx, &map_b, L.b, esize, L.kind == 0, bbox, bes)) return RTEN_ERR_UNSUPPORTED_VALUE;
+
+    const size_t smem_bytes = (size_t)p.stages * p.stage_bytes + 1024 /*align*/ + 256 /*barriers*/;
+    const int grid = std::min(p.tiles_total, ctx->num_sms);
+    cudaError_t e;
+    if (L.kind == 0) {
+        e = cudaFuncSetAttribute(umma_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return fail_cuda(ctx, e, "cudaFuncSetAttribute(umma_gemm<tf32>)");
+        umma_gemm_kernel<0><<<grid, NUM_THREADS, smem_bytes, ctx->stream>>>(map_a, map_b, p);
+    } else {
+        e = cudaFuncSetAttribute(umma_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return fail_cuda(ctx, e, "cudaFuncSetAttribute(umma_gemm<i8>)");
+        umma_gemm_kernel<1><<<grid, NUM_THREADS, smem_bytes, ctx->stream>>>(map_a, map_b, p);
+    }
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "umma_gemm launch");
+    count_launch(ctx);
+    return RTEN_OK;
+}
+
+}  // namespace rtb

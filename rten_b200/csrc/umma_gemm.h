@@ -1,0 +1,76 @@
+// Launch interface of the tcgen05 GEMM / implicit-GEMM-conv kernel (umma_gemm.cu).
+//
+// Computes, per batch z:   D[m, n] = epilogue( sum_k A[m, k] * B[n, k] )
+// with BOTH operands K-major in global memory (k contiguous), fetched by TMA into 128B-swizzled
+// shared-memory tiles and multiplied by tcgen05.mma (kind::tf32 for f32 data, kind::i8 for
+// u8/i8 data) with the accumulator in TMEM.
+//
+// The A operand is either a plain (k, m, z0, z1) tensor or an NHWC activation tensor addressed
+// as an implicit im2col matrix: row = output pixel (b, oy, ox), k = (ky, kx, c).
+#pragma once
+#include <cstdint>
+
+#include "common.h"
+
+namespace rtb {
+
+// Up-to-rank-4 strided operand description in ELEMENTS (inner dim has stride 1).
+struct OperandDesc {
+    const void* base = nullptr;
+    int64_t dims[4] = {1, 1, 1, 1};     // dims[0] = innermost (k or c)
+    int64_t strides[4] = {1, 0, 0, 0};  // elements; strides[0] must be 1
+};
+
+struct EpilogueDesc {
+    void* d = nullptr;
+    int d_is_i32 = 0;  // output element type: 0 f32, 1 i32
+    // plain mode: offset = z0*s_z0 + z1*s_z1 + m*s_row + n*s_col
+    // conv  mode: offset = b*s_z0 + oy*s_row + ox*s_z1 + n*s_col     (s_z1 plays the x stride)
+    int64_t s_z0 = 0, s_z1 = 0, s_row = 0, s_col = 1;
+    // optional residual / Gemm "C" term: v += r_scale * R[...] with its own (broadcastable) strides
+    const float* r = nullptr;
+    float r_scale = 1.0f;
+    int64_t r_z0 = 0, r_z1 = 0, r_row = 0, r_col = 0;
+    const float* bias = nullptr;
+    int bias_kind = 0;  // 1: per column n, 2: per row m
+    float alpha = 1.0f;
+    int act = 0;  // 0 none, 1 relu, 2 gelu(erf), 3 gelu(tanh)
+    // integer path: C = acc - za[m % za_len]*colsum[n] - zb[n % zb_len]*rowsum[m] + K*za*zb
+    const int32_t* za = nullptr;
+    int za_len = 0;
+    const int32_t* zb = nullptr;
+    int zb_len = 0;
+    const int32_t* rowsum = nullptr;  // sum_k A[m,k]   (needed iff zb != null)
+    const int32_t* colsum = nullptr;  // sum_k B[n,k]   (needed iff za != null)
+    const float* scale = nullptr;     // cast_scale fused: f32 out = f32(C) * scale[n % scale_len]
+    int scale_len = 0;
+};
+
+struct ConvGeom {
+    int B = 0, H = 0, W = 0, C = 0;  // NHWC input (C = channels of this group)
+    int OH = 0, OW = 0;
+    int kh = 1, kw = 1, sy = 1, sx = 1, dy = 1, dx = 1, pt = 0, pl = 0;
+};
+
+struct GemmLaunch {
+    int kind = 0;      // 0: f32 data via kind::tf32; 1: 8-bit integers via kind::i8
+    int a_signed = 0;  // kind 1: A is i8 (else u8)
+    int b_signed = 1;  // kind 1: B is i8 (else u8)
+    int M = 0, N = 0, K = 0;
+    int z0 = 1, z1 = 1;  // batch dims (plain mode)
+    int conv = 0;        // A addressed as implicit im2col of an NHWC tensor
+    ConvGeom g;
+    OperandDesc a;  // plain: (k, m, z0, z1); conv: (c, x, y, b)
+    OperandDesc b;  // plain: (k, n, z0, z1) (stride 0 = broadcast); conv: (c, o, tap, 1)
+    EpilogueDesc epi;
+};
+
+// Returns RTEN_OK and enqueues the kernel, or RTEN_ERR_UNSUPPORTED_VALUE (without touching ctx->err
+// semantics of the caller) when the operands violate a TMA constraint -- the caller then packs
+// the operand into an aligned K-major workspace and retries.
+rten_status launch_umma_gemm(rten_ctx* ctx, const GemmLaunch& L);
+
+// true if `od` can be fed to TMA directly (16-B aligned base and strides, inner stride 1).
+bool tma_compatible(const OperandDesc& od, int esize, int rank);
+
+}  // namespace rtb

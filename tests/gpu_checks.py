@@ -1,0 +1,464 @@
+"""Parity checks of the CUDA path against the CPU oracle, shared by `pytest -m gpu` (tests/test_gpu_*.py)
+and tools/gpu_probe.py.  Every check calls the product through the C ABI (rten_b200.ops -> ctypes ->
+librten_b200.so) and the oracle through oracle/oracle.py.
+
+Tolerances
+  integer / index work, elementwise f32 math, Softmax, LayerNormalization: bit-exact.
+  f32 GEMM / Conv (tcgen05 kind::tf32, single pass): |got - exact| <= 2^-9 * sum_k |a_k b_k| + 1e-6
+  (both operands lose at most 2^-10 relative each to TF32 rounding; fp32 accumulation in TMEM).
+"""
+import numpy as np
+
+TF32_REL = 2.0 ** -9
+
+
+def _ulp_diff(a, b):
+    a = np.ascontiguousarray(a, np.float32).view(np.int32).astype(np.int64)
+    b = np.ascontiguousarray(b, np.float32).view(np.int32).astype(np.int64)
+    return int(np.abs(a - b).max()) if a.size else 0
+
+
+def assert_bit_exact(got, exp, what):
+    got = np.asarray(got)
+    exp = np.asarray(exp)
+    assert got.shape == exp.shape, f"{what}: shape {got.shape} != {exp.shape}"
+    if np.issubdtype(exp.dtype, np.floating):
+        same = (got.view(np.int32) == exp.view(np.int32)) | (np.isnan(got) & np.isnan(exp))
+        assert same.all(), f"{what}: {int((~same).sum())} of {same.size} elements differ, max ulp {_ulp_diff(got, exp)}"
+    else:
+        assert np.array_equal(got, exp), f"{what}: {int((got != exp).sum())} of {exp.size} elements differ"
+
+
+def assert_tf32_close(got, exact, absum, what, extra_abs=0.0):
+    got = np.asarray(got, np.float64)
+    err = np.abs(got - exact)
+    bound = TF32_REL * absum + 1e-6 + extra_abs
+    worst = float((err / bound).max()) if err.size else 0.0
+    assert worst <= 1.0, f"{what}: error {float(err.max()):.3e} exceeds the TF32 bound (worst ratio {worst:.2f})"
+    return worst
+
+
+# ------------------------------------------------------------------------------------------
+def check_context(rt, oracle):
+    ctx = rt.Context(0)
+    x = oracle.XorShiftRng(1234).f32((3, 5, 7))
+    t = ctx.to_device(x)
+    assert_bit_exact(t.numpy(), x, "copy roundtrip")
+    p = t.permute(2, 0, 1)
+    assert_bit_exact(p.numpy(), x.transpose(2, 0, 1), "strided D2H copy")
+    assert ctx.launches > 0
+    return "ok"
+
+
+def check_unary(rt, oracle):
+    ctx = rt.Context(0)
+    x = np.concatenate([np.arange(-6, 6, 0.001, dtype=np.float32), oracle.XorShiftRng(7).uniform((100003,), -10, 10),
+                        np.array([0.0, -0.0, np.inf, -np.inf, 1e-30, -88.0, 104.0], np.float32)])
+    assert_bit_exact(rt.Erf().run(ctx, x).numpy(), oracle.erf(x), "Erf")
+    assert_bit_exact(rt.Gelu().run(ctx, x).numpy(), oracle.gelu(x), "Gelu")
+    assert_bit_exact(rt.Gelu(approximate=True).run(ctx, x).numpy(), oracle.gelu(x, True), "ApproxGelu")
+    assert_bit_exact(rt.Relu().run(ctx, x).numpy(), oracle.relu(x), "Relu")
+    d = ctx.to_device(x[:4099])
+    y = rt.Gelu().run(ctx, d, in_place=True)
+    assert y is d
+    assert_bit_exact(d.numpy(), oracle.gelu(x[:4099]), "Gelu in place")
+    x2 = oracle.XorShiftRng(9).uniform((4, 6, 10))
+    assert_bit_exact(rt.Erf().run(ctx, x2.transpose(2, 0, 1)).numpy(), oracle.erf(x2.transpose(2, 0, 1)), "Erf strided")
+    sp = rt.Erf().run(ctx, np.array([np.nan, 0.0, np.inf, -np.inf], np.float32)).numpy()
+    assert np.isnan(sp[0]) and sp[1] == 0 and sp[2] == 1 and sp[3] == -1
+    return "ok"
+
+
+def check_softmax(rt, oracle):
+    ctx = rt.Context(0)
+    r = oracle.XorShiftRng(1234)
+    for shape, axis in [((6,), 0), ((2, 3), 1), ((2, 3), 0), ((4, 4), 1), ((5, 17), -1), ((3, 4, 130), -1),
+                        ((2, 12, 128, 128), -1), ((7, 1000), 1), ((3, 5, 9), 1), ((0, 4), 1), ((2, 2050), -1)]:
+        x = r.uniform(shape, -4, 4)
+        got = rt.Softmax(axis=axis).run(ctx, x).numpy()
+        assert_bit_exact(got, oracle.softmax(x, axis), f"Softmax{shape} axis={axis}")
+    x = np.array([0.1634, 0.8647, 0.6401, 0.8265, 0.0560, 0.2304], np.float32)
+    assert np.allclose(rt.Softmax(0).run(ctx, x).numpy(), [0.1172, 0.2362, 0.1887, 0.2274, 0.1052, 0.1253], atol=1e-4)
+    xt = r.uniform((4, 4)).T
+    assert_bit_exact(rt.Softmax(1).run(ctx, xt).numpy(), oracle.softmax(xt, 1), "Softmax transposed")
+    ninf = np.full(3, -np.inf, np.float32)
+    assert np.isnan(rt.Softmax(0).run(ctx, ninf).numpy()).all()
+    assert rt.Softmax(0, flush_nans_to_zero=True).run(ctx, ninf).numpy().tolist() == [0, 0, 0]
+    # AddSoftmax: BERT-shaped mask broadcast + commutativity + in place
+    qk = r.uniform((2, 3, 16, 128), -3, 3)
+    for mshape in [(2, 1, 1, 128), (1, 1, 16, 128), (128,), (2, 3, 16, 128), (2, 3, 1, 1)]:
+        m = r.uniform(mshape, -2, 0)
+        exp = oracle.add_softmax(qk, m)
+        assert_bit_exact(rt.AddSoftmax().run(ctx, qk, m).numpy(), exp, f"AddSoftmax mask{mshape}")
+        assert_bit_exact(rt.AddSoftmax().run(ctx, m, qk).numpy(), exp, f"AddSoftmax swapped mask{mshape}")
+    d = ctx.to_device(qk)
+    m = r.uniform((2, 1, 1, 128), -2, 0)
+    y = rt.AddSoftmax().run(ctx, d, ctx.to_device(m), in_place=True)
+    assert y is d
+    assert_bit_exact(d.numpy(), oracle.add_softmax(qk, m), "AddSoftmax in place")
+    try:
+        rt.AddSoftmax().run(ctx, qk, np.zeros((3, 5), np.float32))
+        raise AssertionError("expected broadcast error")
+    except rt.OpError as e:
+        assert e.kind == "IncompatibleInputShapes" and e.msg == "Cannot broadcast inputs", str(e)
+    return "ok"
+
+
+def check_layer_norm(rt, oracle):
+    ctx = rt.Context(0)
+    r = oracle.XorShiftRng(1234)
+    for shape, axis in [((1, 5, 2), -1), ((1, 5, 2), -2), ((7, 768), -1), ((3, 4, 100), -1), ((2, 3, 64), -1),
+                        ((5, 1000), -1), ((4, 15), -1), ((2, 16, 17), 1)]:
+        x = r.uniform(shape, -2, 3)
+        nshape = shape[axis:] if axis < 0 else shape[axis:]
+        g = r.uniform(nshape, 0.5, 1.5)
+        b = r.uniform(nshape, -0.5, 0.5)
+        for eps in (None, 1e-12):
+            assert_bit_exact(rt.LayerNormalization(axis, eps).run(ctx, x, g, b).numpy(), oracle.layer_norm(x, g, b, axis, eps),
+                             f"LayerNorm{shape} axis={axis} eps={eps}")
+        assert_bit_exact(rt.LayerNormalization(axis).run(ctx, x, g).numpy(), oracle.layer_norm(x, g, None, axis),
+                         f"LayerNorm{shape} no bias")
+    x = np.array([[0., 1., 2., 3.]], np.float32)
+    assert_bit_exact(rt.LayerNormalization().run(ctx, x, np.float32(2.0), np.float32(0.5)).numpy(),
+                     oracle.layer_norm(x, np.float32(2.0), np.float32(0.5)), "LayerNorm scalar scale+bias")
+    assert_bit_exact(rt.LayerNormalization().run(ctx, x, np.float32(2.0)).numpy(), oracle.layer_norm(x, np.float32(2.0)),
+                     "LayerNorm scalar scale")
+    for bad, msg in [((np.ones((2, 3), np.float32), np.ones((2, 3), np.float32), None),
+                      "`scale` is not broadcastable to normalized axes of input"),
+                     ((np.ones((2, 3), np.float32), np.ones(3, np.float32), np.ones((2, 3), np.float32)),
+                      "`bias` is not broadcastable to normalized axes of input")]:
+        try:
+            rt.LayerNormalization(-1).run(ctx, *bad)
+            raise AssertionError("expected error")
+        except rt.OpError as e:
+            assert e.kind == "InvalidValue" and e.msg == msg, str(e)
+    return "ok"
+
+
+def check_dql(rt, oracle):
+    ctx = rt.Context(0)
+    r = oracle.XorShiftRng(1234)
+    for shape, lo, hi in [((5, 1000), -1.2, 2.8), ((4096, 768), -3, 3), ((3, 7, 11), 0.5, 2.0), ((17,), -5, -1), ((0, 3), 0, 1)]:
+        x = r.uniform(shape, lo, hi)
+        y, s, z = rt.DynamicQuantizeLinear().run(ctx, x)
+        ey, es, ez = oracle.dynamic_quantize_linear(x)
+        assert_bit_exact(s.numpy(), np.float32(es), f"DQL scale {shape}")
+        assert_bit_exact(z.numpy(), np.uint8(ez), f"DQL zero point {shape}")
+        assert_bit_exact(y.numpy(), ey, f"DQL y {shape}")
+    return "ok"
+
+
+def check_glue(rt, oracle):
+    ctx = rt.Context(0)
+    r = oracle.XorShiftRng(1234)
+    a, b = r.uniform((2, 3, 4, 5)), r.uniform((2, 3, 4, 5))
+    assert_bit_exact(rt.Add().run(ctx, a, b).numpy(), a + b, "Add")
+    c = r.uniform((3, 1, 1))
+    assert_bit_exact(rt.Add().run(ctx, a, c).numpy(), a + c, "Add broadcast")
+    x = r.uniform((2, 6, 13, 11))
+    for cl in (False, True):
+        d = ctx.to_device(x, channels_last=cl)
+        assert_bit_exact(rt.MaxPool((3, 3), (1, 1, 1, 1), (2, 2)).run(ctx, d).numpy(), oracle.max_pool(x, (3, 3), [1, 1, 1, 1], (2, 2)),
+                         f"MaxPool cl={cl}")
+        assert_bit_exact(rt.GlobalAveragePool().run(ctx, d).numpy(), oracle.global_average_pool(x), f"GlobalAveragePool cl={cl}")
+    x = r.uniform((3, 70, 7, 7))
+    assert_bit_exact(rt.GlobalAveragePool().run(ctx, ctx.to_device(x, True)).numpy(), oracle.global_average_pool(x), "GAP 7x7")
+    table = r.uniform((50, 12))
+    idx = np.array([[0, 49, 7], [3, 3, -1]], np.int32)
+    assert_bit_exact(rt.GatherRows().run(ctx, table, idx).numpy(), table[idx], "GatherRows")
+    return "ok"
+
+
+# ------------------------------------------------------------------------------------------
+def _matmul_case(rt, oracle, ctx, ashape, bshape, bias=False, alpha=None, b_kmajor=False, prepack=False, seed=1234):
+    r = oracle.XorShiftRng(seed)
+    a = r.uniform(ashape)
+    if b_kmajor:  # B given as a transposed view of [.., N, K] storage (what TransposeFusion hands to MatMul)
+        bt = r.uniform(tuple(bshape[:-2]) + (bshape[-1], bshape[-2]))
+        b = np.swapaxes(bt, -1, -2)
+    else:
+        b = r.uniform(bshape)
+    bv = r.uniform((bshape[-1],)) if bias else None
+    op = rt.FusedMatMul(alpha) if (bias or alpha is not None) else rt.MatMul()
+    kw = {}
+    if prepack:
+        kw["packed_b"] = op.prepack(ctx, 1, b)
+    got = (op.run(ctx, a, b, bv, **kw) if isinstance(op, rt.FusedMatMul) else op.run(ctx, a, b, **kw)).numpy()
+    exp = oracle.matmul(a, b, bv, alpha)
+    assert got.shape == exp.shape, f"matmul{ashape}x{bshape}: shape {got.shape} != {exp.shape}"
+    a2 = a.reshape(-1, a.shape[-1]) if a.ndim > 1 else a[None, :]
+    exact = np.matmul(a.astype(np.float64), b.astype(np.float64)) * (1.0 if alpha is None else alpha)
+    absum = np.matmul(np.abs(a).astype(np.float64), np.abs(b).astype(np.float64)) * abs(1.0 if alpha is None else alpha)
+    if bias:
+        exact = exact + bv
+    worst = assert_tf32_close(got, exact, absum, f"matmul{ashape}x{bshape}")
+    # and the oracle (fp32 reference arithmetic) must sit inside the same band
+    assert_tf32_close(exp, exact, absum, "oracle self-check")
+    return worst
+
+
+def check_matmul_small(rt, oracle):
+    ctx = rt.Context(0)
+    a = np.array([[1, 2], [3, 4]], np.float32)
+    b = np.array([[5, 6], [7, 8]], np.float32)
+    assert_bit_exact(rt.MatMul().run(ctx, a, b).numpy(), np.array([[19, 22], [43, 50]], np.float32), "2x2 f32 (exact in tf32)")
+    w = _matmul_case(rt, oracle, ctx, (128, 32), (32, 128))
+    w = max(w, _matmul_case(rt, oracle, ctx, (128, 64), (64, 128), b_kmajor=True))
+    return f"worst err/bound {w:.3f}"
+
+
+def check_matmul_shapes(rt, oracle):
+    ctx = rt.Context(0)
+    worst = 0.0
+    cases = [((3, 10), (10, 8)), ((2, 3, 10), (10, 8)), ((3, 10), (2, 10, 8)), ((2, 3, 10), (2, 10, 8)),
+             ((2, 1, 3, 10), (1, 4, 10, 8)), ((10,), (10, 8)), ((3, 10), (10,)), ((10,), (10,)),
+             ((130, 300), (300, 257)), ((1, 768), (768, 1000)), ((255, 33), (33, 129)), ((64, 1), (1, 64)),
+             ((2, 5, 12), (12, 7))]
+    for ash, bsh in cases:
+        worst = max(worst, _matmul_case(rt, oracle, ctx, ash, bsh))
+    worst = max(worst, _matmul_case(rt, oracle, ctx, (2, 5, 12), (12, 7), bias=True, alpha=0.125))
+    worst = max(worst, _matmul_case(rt, oracle, ctx, (200, 96), (96, 80), bias=True, prepack=True))
+    worst = max(worst, _matmul_case(rt, oracle, ctx, (4, 3, 128, 64), (4, 3, 64, 128), alpha=0.125, b_kmajor=True))
+    # zero sized dims (src/ops/matmul.rs:1344-1361)
+    for ash, bsh in [((2, 0, 10), (10, 8)), ((3, 10), (10, 0)), ((3, 0), (0, 4))]:
+        got = rt.MatMul().run(ctx, np.zeros(ash, np.float32), np.zeros(bsh, np.float32)).numpy()
+        exp = np.matmul(np.zeros(ash, np.float32), np.zeros(bsh, np.float32))
+        assert got.shape == exp.shape and not got.any(), f"matmul zero-size {ash}x{bsh}"
+    for ash, bsh, kind, msg in [((1, 2), (3, 1), "IncompatibleInputShapes", "Columns of first matrix does not match rows of second matrix"),
+                                ((), (3, 1), "InvalidValue", "Inputs must have >= 1 dimensions"),
+                                ((2, 2, 2), (3, 2, 2), "IncompatibleInputShapes", "Cannot broadcast shapes")]:
+        try:
+            rt.MatMul().run(ctx, np.zeros(ash, np.float32), np.zeros(bsh, np.float32))
+            raise AssertionError("expected error")
+        except rt.OpError as e:
+            assert e.kind == kind and e.msg == msg, str(e)
+    return f"worst err/bound {worst:.3f}"
+
+
+def check_matmul_bert(rt, oracle):
+    ctx = rt.Context(0)
+    w = _matmul_case(rt, oracle, ctx, (4, 128, 768), (768, 768), bias=True, prepack=True)
+    w = max(w, _matmul_case(rt, oracle, ctx, (512, 768), (768, 3072), bias=True))
+    w = max(w, _matmul_case(rt, oracle, ctx, (256, 3072), (3072, 768), prepack=True))
+    return f"worst err/bound {w:.3f}"
+
+
+def check_gemm_op(rt, oracle):
+    ctx = rt.Context(0)
+    r = oracle.XorShiftRng(1234)
+    worst = 0.0
+    for (m, n, k), ta, tb, alpha, beta, cshape in [((3, 8, 10), False, False, 1.0, 1.0, (8,)), ((32, 1000, 2048), False, True, 1.0, 1.0, (1000,)),
+                                                   ((5, 7, 9), True, True, 0.5, 2.0, (5, 7)), ((5, 7, 9), False, False, 2.0, 0.0, None),
+                                                   ((6, 4, 3), False, False, 1.0, 0.5, (6, 1))]:
+        a = r.uniform((k, m) if ta else (m, k))
+        b = r.uniform((n, k) if tb else (k, n))
+        c = r.uniform(cshape) if cshape else None
+        got = rt.Gemm(alpha, beta, ta, tb).run(ctx, a, b, c).numpy()
+        a2, b2 = (a.T if ta else a), (b.T if tb else b)
+        exact = alpha * (a2.astype(np.float64) @ b2.astype(np.float64)) + (beta * c if c is not None else 0.0)
+        absum = abs(alpha) * (np.abs(a2).astype(np.float64) @ np.abs(b2).astype(np.float64))
+        worst = max(worst, assert_tf32_close(got, exact, absum, f"Gemm {m}x{n}x{k} ta={ta} tb={tb}"))
+    for args, kind, msg in [((np.zeros((3, 10), np.float32), np.zeros((8, 10), np.float32)), "IncompatibleInputShapes",
+                             "Columns of first matrix does not match rows of second matrix"),
+                            ((np.zeros((3, 10), np.float32), np.zeros((10, 8), np.float32), np.zeros((5,), np.float32)),
+                             "IncompatibleInputShapes", "Cannot broadcast c to output shape")]:
+        try:
+            rt.Gemm().run(ctx, *args)
+            raise AssertionError("expected error")
+        except rt.OpError as e:
+            assert e.kind == kind and e.msg == msg, str(e)
+    return f"worst err/bound {worst:.3f}"
+
+
+# ------------------------------------------------------------------------------------------
+def check_matmul_integer(rt, oracle):
+    ctx = rt.Context(0)
+    A = np.array([[1, 2], [3, 4]], np.uint8)
+    B = np.array([[5, 6], [7, 8]], np.int8)
+    lit = [(A, B, None, None), (A, B, np.uint8(127), np.int8(-50)), (A, B, np.array([1, 2], np.uint8), np.array([3, 4], np.int8)),
+           (np.zeros((3, 2, 2), np.uint8), B, np.array([1, 2], np.uint8), np.array([3, 4], np.int8)),
+           (np.array([[1, 2, 3, 4]], np.uint8), np.array([[5, 6], [7, 8], [9, 10], [11, 12]], np.int8), np.array([1], np.uint8), np.array([3, 4], np.int8)),
+           (np.array([1, 2], np.uint8), np.array([[1, 2], [3, 4]], np.int8), np.array([1], np.uint8), np.array([2, 3], np.int8)),
+           (A, np.array([1, 2], np.int8), np.array([1, 2], np.uint8), np.array([3], np.int8)),
+           (np.zeros((0, 2), np.uint8), np.zeros((2, 3), np.int8), None, None)]
+    for a, b, az, bz in lit:
+        assert_bit_exact(rt.MatMulInteger().run(ctx, a, b, az, bz).numpy(), oracle.matmul_integer(a, b, az, bz), f"MatMulInteger literal {a.shape}x{b.shape}")
+    r = oracle.XorShiftRng(1234)
+    for adt in (np.uint8, np.int8):
+        for bdt in (np.uint8, np.int8):
+            for (ash, bsh) in [((2, 5, 20), (20, 9)), ((130, 300), (300, 257)), ((1, 768), (768, 64)), ((8, 768), (768, 2304)), ((64, 1000), (1000, 17))]:
+                a = r.u8(ash).view(adt)
+                b = r.u8(bsh).view(bdt)
+                az = r.u8((ash[-2],)).view(adt)
+                bz = r.u8((bsh[-1],)).view(bdt)
+                for azp, bzp in [(None, None), (az, None), (None, bz), (az, bz), (az[:1].reshape(()), bz[:1].reshape(()))]:
+                    got = rt.MatMulInteger().run(ctx, a, b, azp, bzp).numpy()
+                    assert_bit_exact(got, oracle.matmul_integer(a, b, azp, bzp), f"MatMulInteger {adt.__name__}x{bdt.__name__} {ash}x{bsh} zp={azp is not None},{bzp is not None}")
+    # prepacked B + fused cast*scale (MatMulIntegerToFloat), per-column and scalar scales
+    a = r.u8((4, 128, 768))
+    b = r.i8((768, 256))
+    pk = rt.MatMulInteger().prepack(ctx, 1, b)
+    az, bz = np.uint8(131), r.i8((256,))
+    assert_bit_exact(rt.MatMulInteger().run(ctx, a, b, az, bz, packed_b=pk).numpy(), oracle.matmul_integer(a, b, az, bz), "MatMulInteger prepacked")
+    for sc in (r.uniform((256,), 0.001, 0.1), np.float32(0.02), np.array([0.5], np.float32)):
+        got = rt.MatMulIntegerToFloat().run(ctx, a, b, az, bz, sc, packed_b=pk).numpy()
+        assert_bit_exact(got, oracle.matmul_integer_to_float(a, b, az, bz, sc), f"MatMulIntegerToFloat scale{np.shape(sc)}")
+    for args, kind, msg in [((A, B, np.array([1, 2, 4], np.uint8), np.array([3, 4], np.int8)), "InvalidValue", "Zero point has incorrect size"),
+                            ((A, B, np.full((2, 2), 2, np.uint8), None), "UnsupportedValue", "Only scalar or vector zero points are supported"),
+                            ((np.zeros((1, 2), np.uint8), np.zeros((3, 1), np.int8)), "IncompatibleInputShapes", "Columns of first matrix does not match rows of second matrix"),
+                            ((np.zeros((2, 2, 2), np.uint8), np.zeros((3, 2, 2), np.int8)), "IncompatibleInputShapes", "Cannot broadcast shapes")]:
+        try:
+            rt.MatMulInteger().run(ctx, *args)
+            raise AssertionError("expected error")
+        except rt.OpError as e:
+            assert e.kind == kind and e.msg == msg, str(e)
+    try:
+        rt.MatMulIntegerToFloat().run(ctx, A, B, None, None, np.array([2., 3., 4.], np.float32))
+        raise AssertionError("expected error")
+    except rt.OpError as e:
+        assert e.msg == "Scale length does not match tensor columns", str(e)
+    return "ok"
+
+
+# ------------------------------------------------------------------------------------------
+def _conv_exact(x, w, bias, pads, groups, strides, dil):
+    import torch
+    import torch.nn.functional as F
+    xt = F.pad(torch.from_numpy(x).double(), (pads[1], pads[3], pads[0], pads[2]))
+    wt = torch.from_numpy(w).double()
+    y = F.conv2d(xt, wt, None if bias is None else torch.from_numpy(bias).double(), stride=strides, dilation=dil, groups=groups)
+    ya = F.conv2d(xt.abs(), wt.abs(), None, stride=strides, dilation=dil, groups=groups)
+    return y.numpy(), ya.numpy()
+
+
+def _conv_case(rt, oracle, ctx, xs, ws, pads=(0, 0, 0, 0), groups=1, strides=(1, 1), dil=(1, 1), bias=True, cl=False, prepack=False,
+               residual=False, act=0, seed=1234):
+    r = oracle.XorShiftRng(seed)
+    x = r.uniform(xs)
+    w = r.uniform(ws, -1, 1) / np.float32(np.sqrt(ws[1] * ws[2] * ws[3]))
+    b = r.uniform((ws[0],)) if bias else None
+    op = rt.Conv(groups, dil, pads, strides, activation=act)
+    xd = ctx.to_device(x, channels_last=cl)
+    kw = {}
+    if prepack:
+        kw["packed_w"] = op.prepack(ctx, 1, w)
+    exact, absum = _conv_exact(x, w, b, pads, groups, strides, dil)
+    if residual:
+        res = r.uniform(exact.shape)
+        kw["residual"] = ctx.to_device(res, channels_last=cl)
+        exact = exact + res
+    y = op.run(ctx, xd, w, b, **kw)
+    got = y.numpy()
+    if act == 1:
+        exact = np.maximum(exact, 0)
+    what = f"Conv x{xs} w{ws} pads={pads} g={groups} s={strides} d={dil} cl={cl}"
+    assert got.shape == exact.shape, f"{what}: shape {got.shape} != {exact.shape}"
+    if cl:
+        assert y.strides[1] == 1, f"{what}: channels-last input must give channels-last output, got {y.strides}"
+    return assert_tf32_close(got, exact, absum, what)
+
+
+def check_conv_basic(rt, oracle):
+    ctx = rt.Context(0)
+    # reference goldens (src/ops/conv.rs:783-839); 1-channel 3x3 goes through the explicit-im2col path
+    K = np.array([0.3230, 0.7632, 0.4616, 0.8837, 0.5898, 0.3424, 0.2101, 0.7821, 0.6861], np.float32).reshape(1, 1, 3, 3)
+    X = np.array([0.5946, 0.8249, 0.0448, 0.9552, 0.2041, 0.2501, 0.2693, 0.1007, 0.8862], np.float32).reshape(1, 1, 3, 3)
+    same = np.array([1.5202, 1.5592, 0.9939, 1.7475, 2.6358, 1.3428, 1.0165, 1.1806, 0.8685], np.float32).reshape(1, 1, 3, 3)
+    assert np.abs(rt.Conv(padding=(1, 1, 1, 1)).run(ctx, X, K).numpy() - same).max() < 2e-3
+    assert np.abs(rt.Conv(padding="same").run(ctx, X, K).numpy() - same).max() < 2e-3
+    assert abs(rt.Conv().run(ctx, X, K, np.array([1.0], np.float32)).numpy().item() - 3.6358) < 2e-3
+    w = 0.0
+    w = max(w, _conv_case(rt, oracle, ctx, (2, 32, 8, 8), (16, 32, 3, 3), pads=(1, 1, 1, 1), cl=True))     # implicit, direct NHWC
+    w = max(w, _conv_case(rt, oracle, ctx, (2, 32, 8, 8), (16, 32, 3, 3), pads=(1, 1, 1, 1), cl=False))    # implicit via NHWC copy, NCHW out
+    w = max(w, _conv_case(rt, oracle, ctx, (2, 64, 9, 7), (40, 64, 1, 1), cl=True))                        # pointwise
+    w = max(w, _conv_case(rt, oracle, ctx, (1, 3, 16, 16), (8, 3, 7, 7), pads=(3, 3, 3, 3), strides=(2, 2)))  # explicit (C=3 stem)
+    return f"worst err/bound {w:.3f}"
+
+
+def check_conv_stride(rt, oracle):
+    ctx = rt.Context(0)
+    w = _conv_case(rt, oracle, ctx, (2, 32, 12, 12), (24, 32, 3, 3), pads=(1, 1, 1, 1), strides=(2, 2), cl=True)
+    w = max(w, _conv_case(rt, oracle, ctx, (2, 64, 14, 14), (32, 64, 1, 1), strides=(2, 2), cl=True))
+    w = max(w, _conv_case(rt, oracle, ctx, (1, 32, 13, 11), (8, 32, 3, 2), pads=(0, 1, 2, 0), strides=(2, 1), cl=True))
+    w = max(w, _conv_case(rt, oracle, ctx, (1, 32, 10, 10), (8, 32, 3, 3), pads=(2, 2, 2, 2), strides=(2, 3), dil=(2, 2), cl=True))
+    return f"worst err/bound {w:.3f}"
+
+
+def check_conv_more(rt, oracle):
+    ctx = rt.Context(0)
+    w = 0.0
+    w = max(w, _conv_case(rt, oracle, ctx, (2, 8, 9, 7), (6, 4, 3, 2), pads=(0, 1, 2, 0), strides=(2, 1), groups=2))           # grouped, explicit
+    w = max(w, _conv_case(rt, oracle, ctx, (2, 64, 9, 7), (12, 32, 3, 3), pads=(1, 1, 1, 1), groups=2, cl=True))                # grouped, implicit
+    w = max(w, _conv_case(rt, oracle, ctx, (3, 64, 7, 7), (128, 64, 3, 3), pads=(1, 1, 1, 1), cl=True, prepack=True, residual=True, act=1))
+    w = max(w, _conv_case(rt, oracle, ctx, (4, 96, 14, 14), (80, 96, 3, 3), pads=(1, 1, 1, 1), cl=True, bias=False))            # C tail (96 = 3*32), odd N
+    w = max(w, _conv_case(rt, oracle, ctx, (2, 40, 6, 6), (16, 40, 3, 3), pads=(1, 1, 1, 1), cl=True))                          # C=40: K tail inside a block
+    w = max(w, _conv_case(rt, oracle, ctx, (2, 16, 5, 5), (8, 16, 1, 1), cl=False, residual=True, act=1))
+    # 1-D conv (conv.rs:142-185)
+    r = oracle.XorShiftRng(5)
+    x, k = r.uniform((2, 3, 11)), r.uniform((4, 3, 3))
+    got = rt.Conv(1, (1,), (1, 1), (2,)).run(ctx, x, k).numpy()
+    exp = oracle.conv(x, k, None, [1, 1], 1, (2,), (1,))
+    assert got.shape == exp.shape and np.abs(got - exp).max() < 5e-3, "Conv 1-D"
+    z = lambda *s: np.zeros(s, np.float32)
+    for args, kwargs, kind, msg in [((z(1, 3, 5, 5), z(2, 2, 3, 3)), {}, "IncompatibleInputShapes", "Input channels (per group) does not match kernel input channels"),
+                                    ((z(1, 2, 5, 5), z(2, 2, 3, 3)), {"groups": 0}, "InvalidValue", "Group count must be > 0"),
+                                    ((z(1, 3, 5, 5), z(2, 1, 3, 3)), {"groups": 2}, "InvalidValue", "Input channel count not divisible by groups"),
+                                    ((z(1, 4, 5, 5), z(3, 2, 3, 3)), {"groups": 2}, "InvalidValue", "Output channel count not divisible by groups"),
+                                    ((z(1, 1, 2, 2), z(1, 1, 3, 3)), {}, "InvalidValue", "Input too small for kernel size"),
+                                    ((z(1, 1, 5, 5), z(1, 1, 3, 3)), {"strides": (0, 1)}, "InvalidValue", "Strides must be > 0"),
+                                    ((z(1, 1, 5, 5), z(1, 1, 3, 3)), {"strides": (1,)}, "InvalidValue", "expected 2 stride values")]:
+        try:
+            rt.Conv(**kwargs).run(ctx, *args)
+            raise AssertionError("expected error")
+        except rt.OpError as e:
+            assert e.kind == kind and e.msg == msg, str(e)
+    return f"worst err/bound {w:.3f}"
+
+
+def check_conv_integer(rt, oracle):
+    ctx = rt.Context(0)
+    rng = oracle.XorShiftRng(1234)
+    krng = oracle.XorShiftRng(5678)
+    mk = lambda r, s, dt: (r.u8(s).view(np.int8) if dt == np.int8 else r.u8(s))
+    # the reference's case table (src/ops/conv.rs:1429-1497), all four signedness combos
+    for xdt in (np.uint8, np.int8):
+        for wdt in (np.uint8, np.int8):
+            for xs, ws, xz, wz, g in [((1, 2, 5, 5), (1, 2, 3, 3), 12, [1], 1), ((1, 2, 5, 5), (3, 2, 3, 3), 12, [1, 2, 3], 1),
+                                      ((1, 4, 5, 5), (4, 2, 3, 3), 12, [1, 2, 3, 4], 2), ((1, 2, 5, 5), (1, 2, 3, 3), None, None, 1),
+                                      ((1, 2, 5, 5), (1, 2, 1, 1), 12, [1], 1), ((1, 2, 1, 1), (1, 2, 1, 1), 12, [1], 1)]:
+                x, w = mk(rng, xs, xdt), mk(krng, ws, wdt)
+                xzp = None if xz is None else np.array(xz, xdt)
+                wzp = None if wz is None else np.array(wz, wdt)
+                got = rt.ConvInteger(groups=g).run(ctx, x, w, xzp, wzp).numpy()
+                assert_bit_exact(got, oracle.conv_integer(x, w, xzp, wzp, groups=g), f"ConvInteger {xdt.__name__}/{wdt.__name__} x{xs} w{ws}")
+    # tensor-core path: 16-byte channel groups, padding (production path: G3), stride, zero points, channels-last
+    for xdt in (np.uint8, np.int8):
+        for xs, ws, pads, st, cl in [((2, 32, 9, 9), (24, 32, 3, 3), (1, 1, 1, 1), (1, 1), True), ((2, 64, 12, 10), (16, 64, 3, 3), (1, 1, 1, 1), (2, 2), True),
+                                     ((2, 128, 7, 7), (40, 128, 1, 1), (0, 0, 0, 0), (1, 1), True), ((1, 16, 8, 8), (8, 16, 3, 3), (1, 0, 1, 0), (1, 1), False)]:
+            x, w = mk(rng, xs, xdt), krng.i8(ws)
+            xzp, wzp = np.array(77 if xdt == np.uint8 else -3, xdt), krng.i8((ws[0],))
+            for zx, zw in [(xzp, wzp), (xzp, None), (None, wzp), (None, None)]:
+                op = rt.ConvInteger(padding=pads, strides=st)
+                got = op.run(ctx, ctx.to_device(x, channels_last=cl), w, zx, zw).numpy()
+                assert_bit_exact(got, oracle.conv_integer(x, w, zx, zw, padding=list(pads), strides=st),
+                                 f"ConvInteger tc {xdt.__name__} x{xs} w{ws} pads={pads} s={st} zp={zx is not None},{zw is not None}")
+    x, w = rng.u8((2, 32, 9, 9)), krng.i8((24, 32, 3, 3))
+    op = rt.ConvIntegerToFloat(padding=(1, 1, 1, 1))
+    pk = op.prepack(ctx, 1, w)
+    got = op.run(ctx, ctx.to_device(x, True), w, np.uint8(12), None, np.float32(0.1), packed_w=pk).numpy()
+    assert_bit_exact(got, oracle.conv_integer_to_float(x, w, np.uint8(12), None, np.float32(0.1), padding=[1, 1, 1, 1]), "ConvIntegerToFloat")
+    try:
+        op.run(ctx, x, w, np.uint8(12), None, np.array([0.1, 0.2, 0.3], np.float32))
+        raise AssertionError("expected error")
+    except rt.OpError as e:
+        assert e.msg == "scale should be a scalar", str(e)
+    return "ok"
+
+
+ALL_CHECKS = [
+    ("context", check_context), ("unary", check_unary), ("softmax", check_softmax), ("layer_norm", check_layer_norm),
+    ("dql", check_dql), ("glue", check_glue), ("matmul_small", check_matmul_small), ("matmul_shapes", check_matmul_shapes),
+    ("matmul_bert", check_matmul_bert), ("gemm_op", check_gemm_op), ("matmul_integer", check_matmul_integer),
+    ("conv_basic", check_conv_basic), ("conv_stride", check_conv_stride), ("conv_more", check_conv_more),
+    ("conv_integer", check_conv_integer),
+]
