@@ -81,30 +81,30 @@ rten_status to_kmajor(rten_ctx* ctx, int esize, const Mat& m, OperandDesc* od) {
     return RTEN_OK;
 }
 
-// Collapse broadcast prefix dims of a matmul into at most 2 batch dims (z0 inner, z1 outer).
+// Collapse broadcast prefix dims of a matmul into at most 2 batch dims (z0 inner, z1 outer).  Dims are merged
+// only when A, B and the output all advance uniformly across them.
 struct BatchDims {
     int64_t z0 = 1, z1 = 1;
-    int64_t a0 = 0, a1 = 0, b0 = 0, b1 = 0;
+    int64_t a0 = 0, a1 = 0, b0 = 0, b1 = 0, o0 = 0, o1 = 0;
     bool ok = true;
 };
 
-BatchDims collapse_batch(const std::vector<int64_t>& size, const std::vector<int64_t>& as, const std::vector<int64_t>& bs) {
-    std::vector<int64_t> s, a, b;
+BatchDims collapse_batch(const std::vector<int64_t>& size, const std::vector<int64_t>& as, const std::vector<int64_t>& bs,
+                         const std::vector<int64_t>& os) {
+    std::vector<int64_t> s, a, b, o;
     for (size_t i = 0; i < size.size(); i++) {
         if (size[i] == 1) continue;
-        if (!s.empty()) {
-            // merge with previous (outer) dim when both operands advance uniformly
-            const int64_t ps = s.back();
-            if (a.back() == as[i] * size[i] && b.back() == bs[i] * size[i]) {
-                s.back() = ps * size[i];
-                a.back() = as[i];
-                b.back() = bs[i];
-                continue;
-            }
+        if (!s.empty() && a.back() == as[i] * size[i] && b.back() == bs[i] * size[i] && o.back() == os[i] * size[i]) {
+            s.back() *= size[i];
+            a.back() = as[i];
+            b.back() = bs[i];
+            o.back() = os[i];
+            continue;
         }
         s.push_back(size[i]);
         a.push_back(as[i]);
         b.push_back(bs[i]);
+        o.push_back(os[i]);
     }
     BatchDims r;
     if (s.size() > 2) {
@@ -115,13 +115,16 @@ BatchDims collapse_batch(const std::vector<int64_t>& size, const std::vector<int
         r.z0 = s[0];
         r.a0 = a[0];
         r.b0 = b[0];
+        r.o0 = o[0];
     } else if (s.size() == 2) {
         r.z1 = s[0];
         r.a1 = a[0];
         r.b1 = b[0];
+        r.o1 = o[0];
         r.z0 = s[1];
         r.a0 = a[1];
         r.b0 = b[1];
+        r.o0 = o[1];
     }
     return r;
 }
@@ -186,16 +189,17 @@ rten_status matmul_core(OpScope& sc, MatMulArgs& A, rten_tensor* out) {
     int64_t total = 1;
     for (int i = 0; i < on; i++) total *= oshape[i];
     if (total == 0) return RTEN_OK;
-    // user supplied non-contiguous output -> compute into a temp and copy
+    // output strides of the prefix dims / row / col in the (vector-expanded) [prefix.., M, N] view
+    std::vector<int64_t> pos(pn, 0);
+    int64_t o_rs = 0, o_cs = 0;
+    {
+        int k = 0;
+        for (int i = 0; i < pn; i++) pos[i] = ov.strides[k++];
+        if (!a_vec) o_rs = ov.strides[k++];
+        if (!b_vec) o_cs = ov.strides[k++];
+    }
     rten_tensor dv = ov;
     bool copy_out = false;
-    if (!is_contiguous(&ov)) {
-        set_contiguous(&dv);
-        void* t = nullptr;
-        RTB_TRY(temp_alloc(ctx, (size_t)total * 4, &t));
-        dv.data = t;
-        copy_out = true;
-    }
     const int esize = A.kind == 0 ? 4 : 1;
     int64_t nbatch = 1;
     for (int i = 0; i < pn; i++) nbatch *= psize[i];
@@ -209,13 +213,17 @@ rten_status matmul_core(OpScope& sc, MatMulArgs& A, rten_tensor* out) {
     L.N = (int)N;
     L.K = (int)K;
     L.epi = A.epi;
-    L.epi.d = dv.data;
     L.epi.d_is_i32 = A.out_dtype == RTEN_I32;
-    L.epi.s_col = 1;
-    L.epi.s_row = N;
 
     if (K == 0) {
         // lib.rs:843-873: product term vanishes; out = bias (f32) / 0 (int).  Reuse Add machinery: fill.
+        if (!is_contiguous(&ov)) {
+            set_contiguous(&dv);
+            void* t = nullptr;
+            RTB_TRY(temp_alloc(ctx, (size_t)total * 4, &t));
+            dv.data = t;
+            copy_out = true;
+        }
         RTB_CUDA(ctx, cudaMemsetAsync(dv.data, 0, (size_t)total * 4, ctx->stream));
         if (A.kind == 0 && L.epi.bias) {
             long long shp[2] = {total / N, N}, s0[2] = {N, 1}, sb[2] = {0, 1};
@@ -251,27 +259,50 @@ rten_status matmul_core(OpScope& sc, MatMulArgs& A, rten_tensor* out) {
         // uniformly strided; otherwise keep (up to two) batch dims.
         bool flat = false;
         BatchDims bd;
-        if (nb_mats == 1) {
-            std::vector<int64_t> sz = psize, as = pas, zs(pn, 0);
-            sz.push_back(M);
-            as.push_back(ma.rs);
-            zs.push_back(0);
-            BatchDims c = collapse_batch(sz, as, zs);
-            if (c.ok && c.z1 == 1) {
-                flat = true;
-                ma.rows = c.z0;
-                ma.rs = c.z0 > 1 ? c.a0 : ma.rs;
+        const std::vector<int64_t> b_eff = A.pb ? std::vector<int64_t>(pn, 0) : pbs;
+        for (int attempt = 0; attempt < 2; attempt++) {
+            // attempt 0: write straight into the caller's (possibly strided) output; attempt 1: contiguous temp
+            if (attempt == 1) {
+                set_contiguous(&dv);
+                void* t = nullptr;
+                RTB_TRY(temp_alloc(ctx, (size_t)total * 4, &t));
+                dv.data = t;
+                copy_out = true;
+                int k = 0;
+                for (int i = 0; i < pn; i++) pos[i] = dv.strides[k++];
+                if (!a_vec) o_rs = dv.strides[k++];
+                if (!b_vec) o_cs = dv.strides[k++];
             }
+            flat = false;
+            if (nb_mats == 1) {
+                std::vector<int64_t> sz = psize, as = pas, zs(pn, 0), os = pos;
+                sz.push_back(M);
+                as.push_back(ma.rs);
+                zs.push_back(0);
+                os.push_back(o_rs);
+                BatchDims c = collapse_batch(sz, as, zs, os);
+                if (c.ok && c.z1 == 1) {
+                    flat = true;
+                    ma.rows = c.z0;
+                    if (c.z0 > 1) {
+                        ma.rs = c.a0;
+                        o_rs = c.o0;
+                    }
+                    break;
+                }
+            }
+            bd = collapse_batch(psize, pas, b_eff, pos);
+            if (bd.ok) break;
+            if (attempt == 1)
+                return fail(ctx, RTEN_ERR_UNSUPPORTED_VALUE, "matmul batch dims do not collapse to 2 strided dims");
         }
+        L.epi.d = dv.data;
+        L.epi.s_row = o_rs;
+        L.epi.s_col = b_vec ? 1 : o_cs;
         if (flat) {
             L.M = (int)ma.rows;
             L.z0 = L.z1 = 1;
         } else {
-            bd = collapse_batch(psize, pas, A.pb ? std::vector<int64_t>(pn, 0) : pbs);
-            if (!bd.ok) {
-                // materialise contiguous broadcast copies of both operands: [nbatch, M, K], [nbatch, N, K]
-                return fail(ctx, RTEN_ERR_UNSUPPORTED_VALUE, "matmul batch dims do not collapse to 2 strided dims");
-            }
             L.M = (int)M;
             L.z0 = (int)bd.z0;
             L.z1 = (int)bd.z1;
@@ -283,8 +314,8 @@ rten_status matmul_core(OpScope& sc, MatMulArgs& A, rten_tensor* out) {
             mb.z1 = bd.z1;
             mb.zs0 = bd.b0;
             mb.zs1 = bd.b1;
-            L.epi.s_z0 = M * N;
-            L.epi.s_z1 = bd.z0 * M * N;
+            L.epi.s_z0 = bd.o0;
+            L.epi.s_z1 = bd.o1;
         }
         if (A.kind == 1 && !flat && (A.a_zp || A.b_zp) && nbatch > 1)
             return fail(ctx, RTEN_ERR_UNSUPPORTED_VALUE, "MatMulInteger with a batched RHS and zero points is not supported");
@@ -305,8 +336,8 @@ rten_status matmul_core(OpScope& sc, MatMulArgs& A, rten_tensor* out) {
             L.epi.r_scale = 1.0f;
             L.epi.r_col = 1;
             L.epi.r_row = N;
-            L.epi.r_z0 = L.epi.s_z0;
-            L.epi.r_z1 = L.epi.s_z1;
+            L.epi.r_z0 = flat ? 0 : M * N;
+            L.epi.r_z1 = flat ? 0 : bd.z0 * M * N;
         }
 
         // integer zero points

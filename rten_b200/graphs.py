@@ -1,0 +1,284 @@
+"""Post-fusion operator lists of the BASELINE configs, written the way RTen's graph
+executor would hand them to the operators after its load-time fusions (src/optimize.rs:582-650):
+ResNet-50 (Conv with folded BN bias, Add, Relu, MaxPool, GlobalAveragePool, Gemm) and BERT-base
+(FusedMatMul, AddSoftmax, LayerNormalization, Gelu).  Synthetic, seeded weights: no model files exist
+in this environment.
+
+`spec` objects are plain data (numpy weights) so that the same op list can be executed by this
+backend (`*Runner`, HBM-resident, through the C ABI) and -- in tests / bench cpu_baseline -- by the CPU
+oracle, which lives outside this package.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Callable, List, Optional
+
+import numpy as np
+
+from . import ops as O
+
+# ---------------------------------------------------------------------------------------------
+# ResNet-50 (torchvision v1.5 layout: stride on the 3x3 conv), BatchNorm folded into conv bias
+# ---------------------------------------------------------------------------------------------
+
+
+@dataclass
+class ConvSpec:
+    w: np.ndarray
+    b: np.ndarray
+    stride: int
+    pad: int
+
+
+@dataclass
+class Bottleneck:
+    c1: ConvSpec
+    c2: ConvSpec
+    c3: ConvSpec
+    down: Optional[ConvSpec]
+
+
+@dataclass
+class ResNet50Spec:
+    stem: ConvSpec
+    blocks: List[Bottleneck]
+    fc_w: np.ndarray  # [1000, 2048] (Gemm transB = 1)
+    fc_b: np.ndarray
+    conv_flops_per_image: float = 0.0
+
+
+def make_resnet50(uniform: Callable, num_classes: int = 1000, width_mult: float = 1.0) -> ResNet50Spec:
+    """`uniform(shape)` -> U(-1,1) float32 from the caller's seeded RNG (XorShift 5678 in tests/bench)."""
+
+    def conv(o, i, k, stride, pad):
+        w = (uniform((o, i, k, k)) / np.float32(math.sqrt(i * k * k))).astype(np.float32)
+        b = (uniform((o,)) * np.float32(0.1)).astype(np.float32)
+        return ConvSpec(w, b, stride, pad)
+
+    W = lambda c: max(8, int(c * width_mult) // 8 * 8)
+    stem = conv(W(64), 3, 7, 2, 3)
+    blocks = []
+    inp = W(64)
+    for width, n, stride in [(64, 3, 1), (128, 4, 2), (256, 6, 2), (512, 3, 2)]:
+        wd = W(width)
+        for bi in range(n):
+            s = stride if bi == 0 else 1
+            down = conv(wd * 4, inp, 1, s, 0) if bi == 0 else None
+            blocks.append(Bottleneck(conv(wd, inp, 1, 1, 0), conv(wd, wd, 3, s, 1), conv(wd * 4, wd, 1, 1, 0), down))
+            inp = wd * 4
+    fc_w = (uniform((num_classes, inp)) / np.float32(math.sqrt(inp))).astype(np.float32)
+    fc_b = (uniform((num_classes,)) * np.float32(0.1)).astype(np.float32)
+    return ResNet50Spec(stem, blocks, fc_w, fc_b)
+
+
+def resnet50_flops(spec: ResNet50Spec, hw: int = 224) -> float:
+    """Algorithmic flops per image: 2 * out_c * oh * ow * in_c * kh * kw per conv + the FC."""
+
+    def out(h, k, s, p):
+        return (h + 2 * p - k) // s + 1
+
+    total = 0.0
+    h = out(hw, 7, 2, 3)
+    total += 2.0 * spec.stem.w.shape[0] * h * h * 3 * 49
+    h = out(h, 3, 2, 1)
+    for b in spec.blocks:
+        for c, hin in ((b.c1, h), (b.c2, h)):
+            o, i, k, _ = c.w.shape
+            ho = out(hin, k, c.stride, c.pad)
+            total += 2.0 * o * ho * ho * i * k * k
+        h2 = out(h, 3, b.c2.stride, 1)
+        o, i, _, _ = b.c3.w.shape
+        total += 2.0 * o * h2 * h2 * i
+        if b.down is not None:
+            o, i, _, _ = b.down.w.shape
+            total += 2.0 * o * h2 * h2 * i
+        h = h2
+    total += 2.0 * spec.fc_w.shape[0] * spec.fc_w.shape[1]
+    return total
+
+
+class ResNet50Runner:
+    """Executes the op list on one GPU with activations resident in HBM (channels-last strides;
+    logical shapes stay NCHW at the ABI).  `fuse=True` uses the epilogue fusions (bias + residual +
+    Relu inside the conv kernel); `fuse=False` issues the reference's separate Conv / Add / Relu ops."""
+
+    def __init__(self, ctx: O.Context, spec: ResNet50Spec, fuse: bool = True):
+        self.ctx, self.spec, self.fuse = ctx, spec, fuse
+        self._convs = {}
+
+        def prep(c: ConvSpec):
+            op = O.Conv(1, (1, 1), (c.pad, c.pad, c.pad, c.pad), (c.stride, c.stride))
+            w = ctx.to_device(c.w)
+            self._convs[id(c)] = (op, w, ctx.to_device(c.b), op.prepack(ctx, 1, w))
+
+        prep(spec.stem)
+        for b in spec.blocks:
+            for c in (b.c1, b.c2, b.c3, b.down):
+                if c is not None:
+                    prep(c)
+        self.fc_w = ctx.to_device(spec.fc_w)
+        self.fc_b = ctx.to_device(spec.fc_b)
+        self.maxpool = O.MaxPool((3, 3), (1, 1, 1, 1), (2, 2))
+        self.gap = O.GlobalAveragePool()
+        self.fc = O.Gemm(1.0, 1.0, False, True)
+        self.relu, self.add = O.Relu(), O.Add()
+
+    def _conv(self, c: ConvSpec, x, relu: bool, residual=None):
+        op, w, b, pk = self._convs[id(c)]
+        if self.fuse:
+            op.activation = O.ACT_RELU if relu else O.ACT_NONE
+            return op.run(self.ctx, x, w, b, packed_w=pk, residual=residual)
+        op.activation = O.ACT_NONE
+        y = op.run(self.ctx, x, w, b, packed_w=pk)
+        if residual is not None:
+            y = self.add.run(self.ctx, y, residual)
+        if relu:
+            y = self.relu.run(self.ctx, y, in_place=True)
+        return y
+
+    def run(self, x: O.DeviceTensor) -> O.DeviceTensor:
+        """x: [B,3,224,224] f32 (any strides) -> logits [B,1000]."""
+        s = self.spec
+        y = self._conv(s.stem, x, True)
+        y = self.maxpool.run(self.ctx, y)
+        for b in s.blocks:
+            ident = y if b.down is None else self._conv(b.down, y, False)
+            t = self._conv(b.c1, y, True)
+            t = self._conv(b.c2, t, True)
+            y = self._conv(b.c3, t, True, residual=ident)
+        p = self.gap.run(self.ctx, y)
+        return self.fc.run(self.ctx, p.reshape(p.shape[0], p.shape[1]), self.fc_w, self.fc_b)
+
+
+# ---------------------------------------------------------------------------------------------
+# BERT-base (HF layout, post-fusion): 12 layers, H=768, 12 heads x 64, FFN 3072, eps 1e-12
+# ---------------------------------------------------------------------------------------------
+
+
+@dataclass
+class BertLayer:
+    wq: np.ndarray
+    bq: np.ndarray
+    wk: np.ndarray
+    bk: np.ndarray
+    wv: np.ndarray
+    bv: np.ndarray
+    wo: np.ndarray
+    bo: np.ndarray
+    ln1_g: np.ndarray
+    ln1_b: np.ndarray
+    w1: np.ndarray
+    b1: np.ndarray
+    w2: np.ndarray
+    b2: np.ndarray
+    ln2_g: np.ndarray
+    ln2_b: np.ndarray
+
+
+@dataclass
+class BertSpec:
+    hidden: int
+    heads: int
+    ffn: int
+    word_emb: np.ndarray
+    pos_emb: np.ndarray
+    type_emb: np.ndarray
+    emb_g: np.ndarray
+    emb_b: np.ndarray
+    layers: List[BertLayer] = field(default_factory=list)
+    eps: float = 1e-12
+
+
+def make_bert(uniform: Callable, layers: int = 12, hidden: int = 768, heads: int = 12, ffn: int = 3072, vocab: int = 30522,
+              max_pos: int = 512) -> BertSpec:
+    def lin(i, o):
+        return (uniform((i, o)) / np.float32(math.sqrt(i))).astype(np.float32), (uniform((o,)) * np.float32(0.1)).astype(np.float32)
+
+    def ln():
+        return (np.float32(1.0) + np.float32(0.1) * uniform((hidden,))).astype(np.float32), (np.float32(0.1) * uniform((hidden,))).astype(np.float32)
+
+    spec = BertSpec(hidden, heads, ffn, (uniform((vocab, hidden)) * np.float32(0.5)).astype(np.float32),
+                    (uniform((max_pos, hidden)) * np.float32(0.5)).astype(np.float32), (uniform((2, hidden)) * np.float32(0.5)).astype(np.float32),
+                    *ln())
+    for _ in range(layers):
+        wq, bq = lin(hidden, hidden)
+        wk, bk = lin(hidden, hidden)
+        wv, bv = lin(hidden, hidden)
+        wo, bo = lin(hidden, hidden)
+        g1, b1n = ln()
+        w1, b1 = lin(hidden, ffn)
+        w2, b2 = lin(ffn, hidden)
+        g2, b2n = ln()
+        spec.layers.append(BertLayer(wq, bq, wk, bk, wv, bv, wo, bo, g1, b1n, w1, b1, w2, b2, g2, b2n))
+    return spec
+
+
+def bert_flops(spec: BertSpec, batch: int, seq: int) -> float:
+    t, h, f = batch * seq, spec.hidden, spec.ffn
+    per_layer = 2.0 * t * (4 * h * h + 2 * h * f) + 2.0 * batch * spec.heads * 2 * seq * seq * (h // spec.heads)
+    return per_layer * len(spec.layers)
+
+
+class BertRunner:
+    """Post-fusion BERT encoder on one GPU.  Head split / K^T reach MatMul as permuted views
+    (TransposeFusion); the context is written straight into [B,S,heads,d] memory."""
+
+    def __init__(self, ctx: O.Context, spec: BertSpec, fuse: bool = True):
+        self.ctx, self.spec, self.fuse = ctx, spec, fuse
+        dev = ctx.to_device
+        self.word, self.pos, self.typ = dev(spec.word_emb), dev(spec.pos_emb), dev(spec.type_emb)
+        self.emb_g, self.emb_b = dev(spec.emb_g), dev(spec.emb_b)
+        mm = O.FusedMatMul()
+        self.layers = []
+        for L in spec.layers:
+            d = {}
+            for name in ("wq", "wk", "wv", "wo", "w1", "w2"):
+                w = dev(getattr(L, name))
+                d[name] = (w, mm.prepack(ctx, 1, w))
+            for name in ("bq", "bk", "bv", "bo", "b1", "b2", "ln1_g", "ln1_b", "ln2_g", "ln2_b"):
+                d[name] = dev(getattr(L, name))
+            self.layers.append(d)
+        self.gather, self.add, self.gelu = O.GatherRows(), O.Add(), O.Gelu()
+        self.ln = O.LayerNormalization(-1, spec.eps)
+        self.addsoftmax = O.AddSoftmax()
+
+    def _linear(self, x, wp, b, act=O.ACT_NONE, residual=None):
+        w, pk = wp
+        if self.fuse:
+            return O.FusedMatMul(None, act).run(self.ctx, x, w, b, packed_b=pk, residual=residual)
+        y = O.FusedMatMul(None).run(self.ctx, x, w, b, packed_b=pk)
+        if act == O.ACT_GELU:
+            y = self.gelu.run(self.ctx, y, in_place=True)
+        if residual is not None:
+            y = self.add.run(self.ctx, y, residual)
+        return y
+
+    def run(self, input_ids: O.DeviceTensor, token_type_ids: O.DeviceTensor, add_mask: O.DeviceTensor) -> O.DeviceTensor:
+        """input_ids/token_type_ids: [B,S] i32; add_mask: additive attention mask [B,1,1,S] f32."""
+        ctx, s = self.ctx, self.spec
+        B, S = input_ids.shape
+        H, nh = s.hidden, s.heads
+        dh = H // nh
+        x = self.gather.run(ctx, self.word, input_ids)                      # [B,S,H]
+        x = self.add.run(ctx, x, self.pos.view((S, H), (H, 1)))
+        x = self.add.run(ctx, x, self.gather.run(ctx, self.typ, token_type_ids))
+        x = self.ln.run(ctx, x, self.emb_g, self.emb_b)
+        x = x.reshape(B * S, H)
+        scale = 1.0 / math.sqrt(dh)
+        for d in self.layers:
+            q = self._linear(x, d["wq"], d["bq"])
+            k = self._linear(x, d["wk"], d["bk"])
+            v = self._linear(x, d["wv"], d["bv"])
+            heads = lambda t: t.view((B, nh, S, dh), (S * H, dh, H, 1))      # [B,S,nh,dh] memory seen as [B,nh,S,dh]
+            kt = k.view((B, nh, dh, S), (S * H, dh, 1, H))                   # K^T view
+            scores = O.FusedMatMul(scale).run(ctx, heads(q), kt)             # [B,nh,S,S]
+            probs = self.addsoftmax.run(ctx, scores, add_mask, in_place=True)
+            att = ctx.empty((B * S, H))
+            O.MatMul().run(ctx, probs, heads(v), out=att.view((B, nh, S, dh), (S * H, dh, H, 1)))
+            y = self._linear(att, d["wo"], d["bo"], residual=x)
+            x = self.ln.run(ctx, y, d["ln1_g"], d["ln1_b"])
+            h = self._linear(x, d["w1"], d["b1"], act=O.ACT_GELU)
+            y = self._linear(h, d["w2"], d["b2"], residual=x)
+            x = self.ln.run(ctx, y, d["ln2_g"], d["ln2_b"])
+        return x.reshape(B, S, H)

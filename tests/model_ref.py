@@ -1,0 +1,40 @@
+"""The same post-fusion op lists as rten_b200/graphs.py, executed by the CPU oracle (NCHW, separate
+Conv / Add / Relu ops, the reference's own arithmetic).  Used for whole-model parity and as the
+bench's cpu_baseline / reference arm."""
+import math
+
+import numpy as np
+
+
+def resnet50_oracle(oracle, spec, x):
+    def conv(c, t):
+        return oracle.conv(t, c.w, c.b, [c.pad] * 4, 1, (c.stride, c.stride), (1, 1))
+
+    y = oracle.relu(conv(spec.stem, x))
+    y = oracle.max_pool(y, (3, 3), [1, 1, 1, 1], (2, 2))
+    for b in spec.blocks:
+        ident = y if b.down is None else conv(b.down, y)
+        t = oracle.relu(conv(b.c1, y))
+        t = oracle.relu(conv(b.c2, t))
+        y = oracle.relu(oracle.add(conv(b.c3, t), ident))
+    p = oracle.global_average_pool(y)
+    return oracle.gemm_op(p.reshape(p.shape[0], p.shape[1]), spec.fc_w, spec.fc_b, 1.0, 1.0, False, True)
+
+
+def bert_oracle(oracle, spec, input_ids, token_type_ids, add_mask):
+    B, S = input_ids.shape
+    H, nh = spec.hidden, spec.heads
+    dh = H // nh
+    x = oracle.add(oracle.add(spec.word_emb[input_ids], spec.pos_emb[:S]), spec.type_emb[token_type_ids])
+    x = oracle.layer_norm(x, spec.emb_g, spec.emb_b, -1, spec.eps).reshape(B * S, H)
+    scale = 1.0 / math.sqrt(dh)
+    for L in spec.layers:
+        q = oracle.matmul(x, L.wq, L.bq).reshape(B, S, nh, dh).transpose(0, 2, 1, 3)
+        k = oracle.matmul(x, L.wk, L.bk).reshape(B, S, nh, dh).transpose(0, 2, 3, 1)
+        v = oracle.matmul(x, L.wv, L.bv).reshape(B, S, nh, dh).transpose(0, 2, 1, 3)
+        probs = oracle.add_softmax(oracle.matmul(q, k, None, scale), add_mask)
+        att = oracle.matmul(probs, v).transpose(0, 2, 1, 3).reshape(B * S, H)
+        x = oracle.layer_norm(oracle.add(oracle.matmul(att, L.wo, L.bo), x), L.ln1_g, L.ln1_b, -1, spec.eps)
+        h = oracle.gelu(oracle.matmul(x, L.w1, L.b1))
+        x = oracle.layer_norm(oracle.add(oracle.matmul(h, L.w2, L.b2), x), L.ln2_g, L.ln2_b, -1, spec.eps)
+    return x.reshape(B, S, H)
