@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""bench.py -- one "step" = one pass of the hot path (the post-fusion ResNet-50 fp32 op list, batch 32 per
+GPU: BASELINE.json configs[1]) over one batch of synthetic input.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--model resnet50|bert]
+
+Prints ONE JSON line (rank 0).  `value` = whole-job images/s with inputs resident in HBM; `e2e` = the same
+metric through the public operator API with HOST (pinned) input and output buffers, host<->device copies
+inside the timed region.  `roofline` describes the dominant kernel (the tcgen05 implicit-GEMM conv),
+`cpu_baseline` the CPU restatement of the reference path (oracle/) on a bounded sample.
+`--impl reference` times that CPU restatement alone (the Rust reference cannot be built here: no cargo).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_burst": d["bf16_tflops"], "bf16_sustained": d["bf16_tflops_sustained"], "src": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip().split(", "))
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[4:8]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def make_inputs(oracle, model, batch):
+    rng = oracle.XorShiftRng(1234)
+    if model == "resnet50":
+        return {"x": rng.uniform((batch, 3, 224, 224))}
+    ids = (rng.u64(batch * 128) % 30522).astype(np.int32).reshape(batch, 128)
+    return {"ids": ids, "tt": np.zeros((batch, 128), np.int32), "mask": np.zeros((batch, 1, 1, 128), np.float32)}
+
+
+def make_spec(oracle, model):
+    from rten_b200 import graphs
+    rng = oracle.XorShiftRng(5678)
+    if model == "resnet50":
+        return graphs.make_resnet50(lambda s: rng.uniform(s))
+    return graphs.make_bert(lambda s: rng.uniform(s))
+
+
+def run_reference_arm(args, model, batch):
+    """CPU restatement of the reference path on all host threads, bounded sample per step."""
+    from oracle import oracle
+    import model_ref
+    spec = make_spec(oracle, model)
+    sample = 4 if model == "resnet50" else 2
+    inp = make_inputs(oracle, model, sample)
+    run = (lambda: model_ref.resnet50_oracle(oracle, spec, inp["x"])) if model == "resnet50" else \
+        (lambda: model_ref.bert_oracle(oracle, spec, inp["ids"], inp["tt"], inp["mask"]))
+    for _ in range(max(1, min(args.warmup, 1))):
+        run()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        run()
+    dt = time.perf_counter() - t0
+    val = sample * args.steps / dt
+    unit = "img/s" if model == "resnet50" else "seq/s"
+    cores = oracle.num_threads()
+    return {
+        "impl": "reference", "metric": metric_name(model), "value": val, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": config_of(model, batch, args.gpus),
+        "cpu_baseline": {"value": val, "unit": unit, "cores": cores, "kind": "port",
+                         "sample": f"{sample} of {batch} inputs per step; CPU restatement of the rten path (oracle/), the Rust reference cannot be built here"},
+        "e2e": {"value": val, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+
+
+def metric_name(model):
+    return "resnet50_fp32_inferences_per_sec" if model == "resnet50" else "bert_base_fp32_seq128_inferences_per_sec"
+
+
+def config_of(model, batch, n):
+    if model == "resnet50":
+        return {"workload": "ResNet-50 fp32 (post-fusion op list, BN folded), batch 32 per GPU, 224x224, synthetic weights XorShift(5678)",
+                "global_batch": batch * n, "per_gpu_batch": batch, "parallelism": f"dp{n} (batch shard, all-gather of logits)",
+                "f32_mode": "tf32 single pass", "l2": "256 MiB memset between timed steps"}
+    return {"workload": "BERT-base fp32 (post-fusion op list), batch 16 x seq 128 per GPU, synthetic weights XorShift(5678)",
+            "global_batch": batch * n, "per_gpu_batch": batch, "seq_len": 128, "parallelism": f"dp{n} (batch shard, all-gather of hidden states)",
+            "f32_mode": "tf32 single pass", "l2": "256 MiB memset between timed steps"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="resnet50", choices=["resnet50", "bert"])
+    ap.add_argument("--no-graph", action="store_true", help="issue ops one by one instead of replaying a CUDA graph")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    model = args.model
+    batch = 32 if model == "resnet50" else 16
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        if rank == 0:
+            print(json.dumps(run_reference_arm(args, model, batch)), flush=True)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import rten_b200 as rt
+    from rten_b200 import graphs
+    from oracle import oracle  # inputs/weights RNG + cpu_baseline leg only
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: rten_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    ctx = rt.Context(local_rank, stream=stream.cuda_stream)
+
+    spec = make_spec(oracle, model)
+    inp = make_inputs(oracle, model, batch)
+    if model == "resnet50":
+        runner = graphs.ResNet50Runner(ctx, spec, fuse=True)
+        x_dev = ctx.to_device(inp["x"], channels_last=True)
+        dev_inputs = [x_dev]
+        step_fn = lambda: runner.run(x_dev)
+        flops = graphs.resnet50_flops(spec) * batch
+        unit = "img/s"
+    else:
+        runner = graphs.BertRunner(ctx, spec, fuse=True)
+        ids, tt, mask = ctx.to_device(inp["ids"]), ctx.to_device(inp["tt"]), ctx.to_device(inp["mask"])
+        dev_inputs = [ids, tt, mask]
+        step_fn = lambda: runner.run(ids, tt, mask)
+        flops = graphs.bert_flops(spec, batch, 128)
+        unit = "seq/s"
+
+    # ---- eager run (also warms the buffer pool so that graph capture never allocates)
+    out = step_fn()
+    ctx.sync()
+    out_shape = out.shape
+    gather_buf = torch.empty((world,) + tuple(out_shape), dtype=torch.float32, device="cuda") if world > 1 else None
+    out_t = torch.empty(tuple(out_shape), dtype=torch.float32, device="cuda")
+    out_dst = rt.from_torch(ctx, out_t)
+
+    def copy_out(o):
+        import ctypes as C
+        src, dst = o.desc(), out_dst.desc()
+        ctx.check(ctx.lib.rten_b200_copy(ctx.handle, C.byref(src), C.byref(dst)))
+
+    launches_per_step = None
+    graph = None
+    if not args.no_graph:
+        l0 = ctx.launches
+        ctx.graph_begin()
+        o = step_fn()
+        copy_out(o)
+        graph = ctx.graph_end()
+        del o
+
+    def device_step():
+        if graph is not None:
+            graph.launch()
+        else:
+            copy_out(step_fn())
+        if world > 1:
+            dist.all_gather_into_tensor(gather_buf, out_t)
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def timed(fn, steps, warmup, sampler=None):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        if sampler:
+            sampler.start()
+        evs = []
+        l0 = ctx.launches
+        for _ in range(steps):
+            flush.zero_()  # L2 flush, outside the timed events
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(stream)
+            fn()
+            e.record(stream)
+            evs.append((s, e))
+        torch.cuda.synchronize()
+        clocks = sampler.stop() if sampler else None
+        if world > 1:
+            dist.barrier()
+        ms = sum(s.elapsed_time(e) for s, e in evs)
+        launches = ctx.launches - l0
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, launches, clocks
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms, launches, clocks = timed(device_step, args.steps, args.warmup, sampler)
+    value = batch * world * args.steps / (ms / 1e3)
+
+    # ---- e2e: host (pinned) inputs -> H2D -> op list -> D2H of the result, all inside the timed region
+    import ctypes as C
+    pinned = []
+    order = ["x"] if model == "resnet50" else ["ids", "tt", "mask"]
+    for name, d in zip(order, dev_inputs):
+        h = ctx.pinned_empty(inp[name].shape, inp[name].dtype)
+        h[...] = inp[name]
+        pinned.append((h, d))
+    host_out = ctx.pinned_empty(out_shape, np.float32)
+    h2d = sum(h.nbytes for h, _ in pinned)
+    d2h = host_out.nbytes
+
+    def h2d_copy(h, d):
+        # host arrays are NCHW-contiguous; the device tensor keeps its (channels-last) strides
+        src = rt.ops._desc(h.ctypes.data, h.dtype, h.shape, rt.ops._contig(h.shape), -1)
+        dst = d.desc()
+        ctx.check(ctx.lib.rten_b200_copy(ctx.handle, C.byref(src), C.byref(dst)))
+
+    def e2e_step():
+        for h, d in pinned:
+            h2d_copy(h, d)
+        device_step()
+        src = out_dst.desc()
+        dst = rt.ops._desc(host_out.ctypes.data, host_out.dtype, host_out.shape, rt.ops._contig(host_out.shape), -1)
+        ctx.check(ctx.lib.rten_b200_copy(ctx.handle, C.byref(src), C.byref(dst)))
+
+    ms_e2e, _, _ = timed(e2e_step, args.steps, 3)
+    e2e_value = batch * world * args.steps / (ms_e2e / 1e3)
+
+    # ---- roofline of the dominant kernel: per-launch CUDA-event timing of every GEMM/conv op of one pass
+    roof = None
+    if rank == 0:
+        roof = roofline_pass(ctx, rt, runner, model, spec, dev_inputs, batch, stream, torch)
+
+    if rank == 0:
+        peaks = load_peaks()
+        line = {
+            "metric": metric_name(model), "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32(tf32 mma)",
+            "data": "synthetic", "config": config_of(model, batch, world), "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches),
+            "cuda_graph": graph is not None,
+            "model_tflops": flops * world * args.steps / (ms / 1e3) / 1e12,
+        }
+        if roof:
+            tf32_peak = 0.5 * peaks["bf16_sustained"]
+            roof_line = {"bound": "tensor", "kernel": "rtb::umma_gemm_kernel<0> (tcgen05 kind::tf32 implicit-GEMM conv / GEMM)",
+                         "achieved": roof["tflops"], "peak": tf32_peak, "unit": "TFLOP/s", "frac": roof["tflops"] / tf32_peak,
+                         "traffic": None, "launches_timed": roof["launches"], "share_of_step": roof["share"],
+                         "peak_source": f"0.5 x {peaks['src']} bf16 sustained ({peaks['bf16_sustained']} TF/s): kind::tf32 issues at half the bf16 rate"}
+            line["roofline"] = roof_line
+        if not args.no_cpu_baseline:
+            a2 = argparse.Namespace(**vars(args))
+            a2.steps, a2.warmup = 1, 1
+            ref = run_reference_arm(a2, model, batch)
+            line["cpu_baseline"] = ref["cpu_baseline"]
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def roofline_pass(ctx, rt, runner, model, spec, dev_inputs, batch, stream, torch):
+    """Time each tensor-core op of one eager pass with CUDA events on the launching stream (3 repetitions, after
+    warm-up) and divide the algorithmic flops by the summed durations."""
+    import rten_b200.ops as O
+    records = []
+    orig_conv, orig_mm, orig_mm0 = O.Conv.run, O.FusedMatMul.run, O.MatMul.run
+
+    def wrap(orig, flops_fn):
+        def run(self, c, *a, **k):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(stream)
+            y = orig(self, c, *a, **k)
+            e.record(stream)
+            records.append((s, e, flops_fn(a, y)))
+            return y
+        return run
+
+    def conv_flops(a, y):
+        w = a[1]
+        b, o, oh, ow = y.shape
+        return 2.0 * b * o * oh * ow * w.shape[1] * w.shape[2] * w.shape[3]
+
+    def mm_flops(a, y):
+        k = a[0].shape[-1]
+        return 2.0 * float(np.prod(y.shape)) * k
+
+    O.Conv.run = wrap(orig_conv, conv_flops)
+    O.FusedMatMul.run = wrap(orig_mm, mm_flops)
+    O.MatMul.run = wrap(orig_mm0, mm_flops)
+    try:
+        tot_ms, tot_fl, n = 0.0, 0.0, 0
+        for rep in range(4):
+            records.clear()
+            s0, e0 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record(stream)
+            if model == "resnet50":
+                runner.run(dev_inputs[0])
+            else:
+                runner.run(*dev_inputs)
+            e0.record(stream)
+            torch.cuda.synchronize()
+            if rep == 0:
+                continue
+            tot_ms += sum(s.elapsed_time(e) for s, e, _ in records)
+            tot_fl += sum(f for _, _, f in records)
+            n += len(records)
+            step_ms = s0.elapsed_time(e0)
+            share = sum(s.elapsed_time(e) for s, e, _ in records) / step_ms
+    finally:
+        O.Conv.run, O.FusedMatMul.run, O.MatMul.run = orig_conv, orig_mm, orig_mm0
+    return {"tflops": tot_fl / (tot_ms / 1e3) / 1e12, "launches": n, "share": share}
+
+
+if __name__ == "__main__":
+    main()

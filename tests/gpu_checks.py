@@ -455,10 +455,58 @@ def check_conv_integer(rt, oracle):
     return "ok"
 
 
+def check_resnet50_model(rt, oracle):
+    """Whole-model parity (ResNet-50 fp32, full 224x224 images, batch 2): every conv runs single-pass TF32,
+    so the logits carry ~53 layers of 2^-11-relative operand rounding.  Stated tolerance: max |d| <= 1e-2 * max |ref|."""
+    from rten_b200 import graphs
+    import model_ref
+    ctx = rt.Context(0)
+    rng = oracle.XorShiftRng(5678)
+    spec = graphs.make_resnet50(lambda s: rng.uniform(s))
+    x = oracle.XorShiftRng(1234).uniform((2, 3, 224, 224))
+    ref = model_ref.resnet50_oracle(oracle, spec, x)
+    outs = {}
+    for fuse in (True, False):
+        runner = graphs.ResNet50Runner(ctx, spec, fuse=fuse)
+        outs[fuse] = runner.run(ctx.to_device(x, channels_last=True)).numpy()
+        rel = float(np.abs(outs[fuse] - ref).max() / np.abs(ref).max())
+        assert outs[fuse].shape == ref.shape and rel <= 1e-2, f"ResNet-50 logits (fuse={fuse}): rel err {rel:.3e}"
+        assert (outs[fuse].argmax(1) == ref.argmax(1)).all()
+    # NCHW-contiguous input (the reference's native layout) must give the same answer as channels-last
+    y_nchw = graphs.ResNet50Runner(ctx, spec, fuse=True).run(ctx.to_device(x)).numpy()
+    rel2 = float(np.abs(y_nchw - ref).max() / np.abs(ref).max())
+    assert rel2 <= 1e-2, f"ResNet-50 NCHW input rel err {rel2:.3e}"
+    return f"rel err fused {float(np.abs(outs[True] - ref).max() / np.abs(ref).max()):.2e} unfused {float(np.abs(outs[False] - ref).max() / np.abs(ref).max()):.2e} nchw {rel2:.2e}"
+
+
+def check_bert_model(rt, oracle):
+    """BERT-base encoder, 3 layers, batch 2 x seq 128 (full width 768/3072).  Tolerance: max |d| <= 1e-2 (LayerNorm
+    keeps activations O(1))."""
+    from rten_b200 import graphs
+    import model_ref
+    ctx = rt.Context(0)
+    rng = oracle.XorShiftRng(5678)
+    spec = graphs.make_bert(lambda s: rng.uniform(s), layers=3)
+    ids = (oracle.XorShiftRng(1234).u64(2 * 128) % 30522).astype(np.int32).reshape(2, 128)
+    tt = np.zeros((2, 128), np.int32)
+    tt[:, 64:] = 1
+    mask = np.zeros((2, 1, 1, 128), np.float32)
+    mask[1, :, :, 100:] = -10000.0
+    ref = model_ref.bert_oracle(oracle, spec, ids, tt, mask)
+    res = []
+    for fuse in (True, False):
+        runner = graphs.BertRunner(ctx, spec, fuse=fuse)
+        got = runner.run(ctx.to_device(ids), ctx.to_device(tt), ctx.to_device(mask)).numpy()
+        err = float(np.abs(got - ref).max())
+        assert got.shape == ref.shape and err <= 1e-2, f"BERT hidden states (fuse={fuse}): max abs err {err:.3e}"
+        res.append(err)
+    return f"max abs err fused {res[0]:.2e} unfused {res[1]:.2e} (|ref| max {float(np.abs(ref).max()):.2f})"
+
+
 ALL_CHECKS = [
     ("context", check_context), ("unary", check_unary), ("softmax", check_softmax), ("layer_norm", check_layer_norm),
     ("dql", check_dql), ("glue", check_glue), ("matmul_small", check_matmul_small), ("matmul_shapes", check_matmul_shapes),
     ("matmul_bert", check_matmul_bert), ("gemm_op", check_gemm_op), ("matmul_integer", check_matmul_integer),
     ("conv_basic", check_conv_basic), ("conv_stride", check_conv_stride), ("conv_more", check_conv_more),
-    ("conv_integer", check_conv_integer),
+    ("conv_integer", check_conv_integer), ("resnet50_model", check_resnet50_model), ("bert_model", check_bert_model),
 ]
