@@ -196,6 +196,7 @@ def main():
     out = step_fn()
     ctx.sync()
     out_shape = out.shape
+    del out
     gather_buf = torch.empty((world,) + tuple(out_shape), dtype=torch.float32, device="cuda") if world > 1 else None
     out_t = torch.empty(tuple(out_shape), dtype=torch.float32, device="cuda")
     out_dst = rt.from_torch(ctx, out_t)

@@ -18,8 +18,7 @@ rten_status pool_alloc(rten_ctx* ctx, size_t bytes, void** out) {
         ctx->pool.live[*out] = b;
         return RTEN_OK;
     }
-    if (ctx->capturing)
-        return fail(ctx, RTEN_ERR_CUDA, "buffer pool miss during graph capture (run the op list once eagerly first)");
+    // During graph capture (relaxed mode) growing the pool is still legal: cudaMalloc is not a stream operation.
     void* p = nullptr;
     cudaError_t e = cudaMalloc(&p, b);
     if (e != cudaSuccess) return fail_cuda(ctx, e, "cudaMalloc");
@@ -294,7 +293,7 @@ rten_status rten_b200_graph_begin(rten_ctx* ctx) {
     if (!ctx) return RTEN_ERR_INVALID_VALUE;
     if (ctx->capturing) return fail(ctx, RTEN_ERR_INVALID_VALUE, "graph capture already active");
     cudaSetDevice(ctx->device);
-    RTB_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    RTB_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
     ctx->capturing = true;
     ctx->capture_start_launches = ctx->launches;
     return RTEN_OK;

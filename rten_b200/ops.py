@@ -170,7 +170,7 @@ class DeviceTensor:
 
     def view(self, shape, strides, offset_elems: int = 0) -> "DeviceTensor":
         return DeviceTensor(self.ctx, self.ptr + offset_elems * self.dtype.itemsize, shape, strides, self.dtype, False,
-                            base=self.base or self)
+                            base=self.base if self.base is not None else self)
 
     def permute(self, *axes) -> "DeviceTensor":
         return self.view([self.shape[a] for a in axes], [self.strides[a] for a in axes])
