@@ -10,10 +10,13 @@
 //   warp 1   : MMA issuer     -- one elected thread issues tcgen05.mma (kind::tf32 or kind::i8),
 //                                4 instructions per 128-byte K block, accumulating in TMEM
 //   warp 2   : TMEM allocator -- 512 columns = 2 accumulator stages of up to 256 columns
-//   warps 4-7: epilogue       -- tcgen05.ld accumulator rows -> registers -> fused epilogue
-//                                (alpha, residual/beta*C, bias, activation; or the integer zero-point
-//                                correction and cast*scale) -> global memory.  Runs concurrently with
-//                                the next tile's main loop thanks to the second TMEM stage.
+//   warps 4-11: epilogue      -- two groups of 4 warps, each taking every other 32-column chunk of the tile:
+//                                tcgen05.ld accumulator rows -> registers -> fused epilogue (alpha, residual /
+//                                beta*C, bias, activation; or the integer zero-point correction and cast*scale)
+//                                -> 128B-swizzled smem staging -> cp.async.bulk.tensor store (full-line writes;
+//                                TMA clips rows/columns outside the output).  Outputs whose rows are not
+//                                contiguous fall back to direct register->global stores.  Runs concurrently
+//                                with the next tile's main loop thanks to the second TMEM stage.
 // For Conv the A tile is a TMA box over the NHWC activation tensor at (c0, ox0*sx - pad + kx*dx,
 // oy0*sy - pad + ky*dy, b0): padding comes from TMA out-of-bounds zero fill, the stride from the
 // tensor map's element strides; the im2col matrix is never materialised.
@@ -22,6 +25,7 @@
 
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 
 #include "math.cuh"
 #include "ptx.cuh"
@@ -34,7 +38,8 @@ constexpr int KBYTES = 128;        // bytes of K per stage row = one 128B swizzl
 constexpr int A_STAGE_BYTES = BM * KBYTES;
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_STRIDE = 256;    // TMEM columns per accumulator stage
-constexpr int NUM_THREADS = 256;
+constexpr int NUM_THREADS = 384;   // 4 control warps + 8 epilogue warps (two groups of 4)
+constexpr int STG_BYTES = 128 * 128;  // one 128-row x 128-byte output staging buffer per epilogue group
 constexpr int MAX_STAGES = 8;
 
 struct KParams {
@@ -49,6 +54,7 @@ struct KParams {
     int OH, OW, Bn;
     int sy, sx, dy, dx, pt, pl, kw, c_blocks;
     int a_bcast0, a_bcast1, b_bcast0, b_bcast1;
+    int tma_store;  // 1: epilogue stages 128x32 chunks in smem and writes them with TMA (output rows contiguous)
     EpilogueDesc epi;
 };
 
@@ -85,11 +91,12 @@ __device__ __forceinline__ TileCoord decode_tile(const KParams& p, int t) {
 template <int KIND>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                 const KParams p) {
+                 const __grid_constant__ CUtensorMap tma_d, const KParams p) {
     extern __shared__ uint8_t smem_raw[];
     // 1024-B alignment required by the 128B swizzle atoms / UMMA descriptors (base_offset = 0).
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * p.stage_bytes);
+    uint8_t* stg_base = smem + (size_t)p.stages * p.stage_bytes;  // 2 x STG_BYTES, 1024-B aligned
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg_base + 2 * STG_BYTES);
     uint64_t* empty_bar = full_bar + MAX_STAGES;
     uint64_t* tmem_full = empty_bar + MAX_STAGES;
     uint64_t* tmem_empty = tmem_full + 2;
@@ -101,6 +108,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tma_a);
         tma_prefetch_desc(&tma_b);
+        if (p.tma_store) tma_prefetch_desc(&tma_d);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.stages; s++) {
@@ -109,7 +117,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         }
         for (int s = 0; s < 2; s++) {
             mbar_init(&tmem_full[s], 1);
-            mbar_init(&tmem_empty[s], 4);  // one arrival per epilogue warp
+            mbar_init(&tmem_empty[s], 8);  // one arrival per epilogue warp
         }
         fence_mbar_init();
     }
@@ -194,8 +202,11 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     } else if (warp >= 4) {
         // ===================== epilogue =====================
         const EpilogueDesc& e = p.epi;
-        const int q = warp & 3;  // TMEM lane quadrant this warp may access
+        const int q = warp & 3;          // TMEM lane quadrant this warp may access
+        const int grp = (warp - 4) >> 2;  // epilogue group: chunks grp, grp+2, ...
         const int r = q * 32 + lane;
+        uint8_t* stg = stg_base + grp * STG_BYTES;
+        const bool issuer = (q == 0 && lane == 0);
         int it = 0;
         for (int t = blockIdx.x; t < p.tiles_total; t += gridDim.x, it++) {
             const int acc = it & 1;
@@ -235,7 +246,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_STRIDE;
-            for (int c0 = 0; c0 < p.bn; c0 += 32) {
+            for (int c0 = grp * 32; c0 < p.bn; c0 += 64) {
                 uint32_t v[32];
                 const int ncols = (p.bn - c0) >= 32 ? 32 : 16;
                 if (ncols == 32) {
@@ -250,64 +261,90 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                 }
                 tmem_ld_wait();
                 const int nbase = tc.n0 + c0;
-                if (!row_ok) {
-                    // nothing to store for this row; stay converged for the next aligned tcgen05.ld
-                } else if (KIND == 0) {
-                    float* dptr = reinterpret_cast<float*>(e.d) + d_off;
-                    const bool vec = (e.s_col == 1) && (nbase + ncols <= p.N) &&
-                                     ((reinterpret_cast<uintptr_t>(dptr + nbase) & 15) == 0) &&
-                                     (e.r == nullptr || (e.r_col == 1 && ((reinterpret_cast<uintptr_t>(e.r + r_off + nbase) & 15) == 0)));
-                    if (vec) {
+                // ---- fused epilogue arithmetic on this thread's 32 columns (in place in v[])
+                if (row_ok) {
+                    if (KIND == 0) {
+                        const bool rvec = e.r && e.r_col == 1 && (nbase + 32 <= p.N) &&
+                                          ((reinterpret_cast<uintptr_t>(e.r + r_off + nbase) & 15) == 0);
+                        const bool bvec = e.bias_kind == 1 && (nbase + 32 <= p.N) &&
+                                          ((reinterpret_cast<uintptr_t>(e.bias + nbase) & 15) == 0);
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
-                            if (j < ncols) {
-                                float o[4];
-                                float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
-                                if (e.r) rv = *reinterpret_cast<const float4*>(e.r + r_off + nbase + j);
-                                const float rr[4] = {rv.x, rv.y, rv.z, rv.w};
+                            float rr[4] = {0.f, 0.f, 0.f, 0.f}, bb[4] = {0.f, 0.f, 0.f, 0.f};
+                            if (rvec) {
+                                const float4 t4 = *reinterpret_cast<const float4*>(e.r + r_off + nbase + j);
+                                rr[0] = t4.x, rr[1] = t4.y, rr[2] = t4.z, rr[3] = t4.w;
+                            } else if (e.r) {
 #pragma unroll
-                                for (int u = 0; u < 4; u++) {
-                                    float x = __uint_as_float(v[j + u]) * e.alpha;
-                                    if (e.r) x = fmaf(e.r_scale, rr[u], x);
-                                    if (e.bias_kind == 1) x += e.bias[nbase + j + u];
-                                    x += row_bias;
-                                    o[u] = apply_act(x, e.act);
-                                }
-                                *reinterpret_cast<float4*>(dptr + nbase + j) = make_float4(o[0], o[1], o[2], o[3]);
+                                for (int u = 0; u < 4; u++)
+                                    if (nbase + j + u < p.N) rr[u] = e.r[r_off + (long long)(nbase + j + u) * e.r_col];
+                            }
+                            if (bvec) {
+                                const float4 t4 = __ldg(reinterpret_cast<const float4*>(e.bias + nbase + j));
+                                bb[0] = t4.x, bb[1] = t4.y, bb[2] = t4.z, bb[3] = t4.w;
+                            } else if (e.bias_kind == 1) {
+#pragma unroll
+                                for (int u = 0; u < 4; u++)
+                                    if (nbase + j + u < p.N) bb[u] = e.bias[nbase + j + u];
+                            }
+#pragma unroll
+                            for (int u = 0; u < 4; u++) {
+                                float x = __uint_as_float(v[j + u]) * e.alpha;
+                                if (e.r) x = fmaf(e.r_scale, rr[u], x);
+                                x += bb[u];
+                                x += row_bias;
+                                v[j + u] = __float_as_uint(apply_act(x, e.act));
                             }
                         }
                     } else {
 #pragma unroll
                         for (int j = 0; j < 32; j++) {
                             const int n = nbase + j;
-                            if (j < ncols && n < p.N) {
-                                float x = __uint_as_float(v[j]) * e.alpha;
-                                if (e.r) x = fmaf(e.r_scale, e.r[r_off + (long long)n * e.r_col], x);
-                                if (e.bias_kind == 1) x += e.bias[n];
-                                x += row_bias;
-                                dptr[(long long)n * e.s_col] = apply_act(x, e.act);
+                            if (n < p.N) {
+                                // exact i32 arithmetic with wrap-around (unsigned ops)
+                                unsigned c = v[j];
+                                if (e.za) c -= (unsigned)za_v * (unsigned)e.colsum[n];
+                                if (e.zb) {
+                                    const unsigned zbv = (unsigned)e.zb[n % e.zb_len];
+                                    c -= zbv * (unsigned)rs_v;
+                                    if (e.za) c += (unsigned)p.K * (unsigned)za_v * zbv;
+                                }
+                                v[j] = e.scale ? __float_as_uint(__int2float_rn((int)c) * e.scale[n % e.scale_len]) : c;
                             }
                         }
                     }
-                } else {
+                }
+                if (p.tma_store) {
+                    // previous TMA store of this group must have finished READING the staging buffer
+                    if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+                    // row r -> 128 bytes at r*128, 16-byte chunks XOR-swizzled by (r & 7)  (== SWIZZLE_128B)
+                    uint8_t* rowp = stg + r * 128;
 #pragma unroll
-                    for (int j = 0; j < 32; j++) {
-                        const int n = nbase + j;
-                        if (j < ncols && n < p.N) {
-                            // exact i32 arithmetic with wrap-around (unsigned ops)
-                            unsigned c = v[j];
-                            if (e.za) c -= (unsigned)za_v * (unsigned)e.colsum[n];
-                            if (e.zb) {
-                                const unsigned zbv = (unsigned)e.zb[n % e.zb_len];
-                                c -= zbv * (unsigned)rs_v;
-                                if (e.za) c += (unsigned)p.K * (unsigned)za_v * zbv;
-                            }
-                            const long long off = d_off + (long long)n * e.s_col;
-                            if (e.scale) {
-                                reinterpret_cast<float*>(e.d)[off] = __int2float_rn((int)c) * e.scale[n % e.scale_len];
-                            } else {
-                                reinterpret_cast<int*>(e.d)[off] = (int)c;
-                            }
+                    for (int j = 0; j < 8; j++) {
+                        *reinterpret_cast<uint4*>(rowp + ((j ^ (r & 7)) << 4)) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    }
+                    fence_proxy_async();
+                    asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+                    if (issuer) {
+                        if (p.conv)
+                            tma_store_4d(&tma_d, stg, nbase, tc.ox0, tc.oy0, tc.b0);
+                        else
+                            tma_store_4d(&tma_d, stg, nbase, tc.m0, tc.z0, tc.z1);
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                } else if (row_ok) {
+                    uint32_t* dptr = reinterpret_cast<uint32_t*>(e.d) + d_off;
+                    const bool vec = (e.s_col == 1) && (nbase + ncols <= p.N) && ((reinterpret_cast<uintptr_t>(dptr + nbase) & 15) == 0);
+                    if (vec) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            if (j < ncols) *reinterpret_cast<uint4*>(dptr + nbase + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) {
+                            const int n = nbase + j;
+                            if (j < ncols && n < p.N) dptr[(long long)n * e.s_col] = v[j];
                         }
                     }
                 }
@@ -317,6 +354,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         }
+        // smem must stay valid until the last bulk store has read it
+        if (p.tma_store && issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
 
     tc_fence_before();
@@ -408,13 +447,13 @@ static void pick_conv_tile(const ConvGeom& g, int& tw, int& th, int& tb) {
     }
 }
 
-static int pick_bn(int N, long long tiles_m_total, int num_sms) {
-    // minimise (waves) x (per-tile cost ~ bn + fixed overhead)
-    int best_bn = 16;
+static int pick_bn(int N, long long tiles_m_total, int num_sms, int step) {
+    // minimise (waves) x (per-tile cost ~ bn + fixed overhead); `step` = 32 when the epilogue stores 32-column chunks
+    int best_bn = step;
     double best_cost = 1e30;
-    int n16 = (N + 15) / 16 * 16;
-    for (int bn = 16; bn <= 256; bn += 16) {
-        if (bn > n16 && bn != 16) break;
+    int n16 = (N + step - 1) / step * step;
+    for (int bn = step; bn <= 256; bn += step) {
+        if (bn > n16 && bn != step) break;
         long long tiles = tiles_m_total * ((N + bn - 1) / bn);
         long long waves = (tiles + num_sms - 1) / num_sms;
         double cost = (double)waves * (bn + 24.0);
@@ -487,7 +526,37 @@ rten_status launch_umma_gemm(rten_ctx* ctx, const GemmLaunch& L) {
         p.b_bcast0 = (L.b.dims[2] == 1 && L.z0 > 1) ? 1 : 0;
         p.b_bcast1 = (L.b.dims[3] == 1 && L.z1 > 1) ? 1 : 0;
     }
-    p.bn = pick_bn(L.N, tiles_m_total, ctx->num_sms);
+    // ---- output path: TMA store needs contiguous 4-byte rows at 16-byte aligned pitches
+    OperandDesc od;
+    uint32_t dbox[4] = {32, 1, 1, 1}, des[4] = {1, 1, 1, 1};
+    {
+        const EpilogueDesc& e = L.epi;
+        od.base = e.d;
+        od.dims[0] = L.N;
+        od.strides[0] = 1;
+        if (L.conv) {
+            od.dims[1] = L.g.OW;
+            od.dims[2] = L.g.OH;
+            od.dims[3] = L.g.B;
+            od.strides[1] = e.s_z1;
+            od.strides[2] = e.s_row;
+            od.strides[3] = e.s_z0;
+            dbox[1] = p.tw;
+            dbox[2] = p.th;
+            dbox[3] = p.tb;
+        } else {
+            od.dims[1] = L.M;
+            od.dims[2] = L.z0;
+            od.dims[3] = L.z1;
+            od.strides[1] = e.s_row;
+            od.strides[2] = e.s_z0;
+            od.strides[3] = e.s_z1;
+            dbox[1] = BM;
+        }
+        p.tma_store = (e.s_col == 1 && L.N >= 4 && tma_compatible(od, 4, 4)) ? 1 : 0;
+        if (getenv("RTEN_B200_NO_TMA_STORE")) p.tma_store = 0;
+    }
+    p.bn = pick_bn(L.N, tiles_m_total, ctx->num_sms, p.tma_store ? 32 : 16);
     p.tiles_n = (L.N + p.bn - 1) / p.bn;
     long long tt = tiles_m_total * p.tiles_n;
     if (tt > 0x7FFFFFFFll) return RTEN_ERR_UNSUPPORTED_VALUE;
@@ -498,7 +567,7 @@ rten_status launch_umma_gemm(rten_ctx* ctx, const GemmLaunch& L) {
     bbox[3] = 1;
     p.stage_bytes = A_STAGE_BYTES + p.bn * KBYTES;
     p.tx_bytes = a_rows * KBYTES + p.bn * KBYTES;
-    const int smem_budget = 227 * 1024 - 2048;
+    const int smem_budget = 227 * 1024 - 2048 - 2 * STG_BYTES;
     p.stages = std::min(MAX_STAGES, smem_budget / (int)p.stage_bytes);
     if (p.stages < 2) return RTEN_ERR_UNSUPPORTED_VALUE;
     if (L.kind == 0)
@@ -509,18 +578,23 @@ rten_status launch_umma_gemm(rten_ctx* ctx, const GemmLaunch& L) {
     CUtensorMap map_a, map_b;
     if (!encode_map(ctx, &map_a, L.a, esize, L.kind == 0, abox, aes)) return RTEN_ERR_UNSUPPORTED_VALUE;
     if (!encode_map(ctx, &map_b, L.b, esize, L.kind == 0, bbox, bes)) return RTEN_ERR_UNSUPPORTED_VALUE;
+    CUtensorMap map_d = map_a;
+    if (p.tma_store && !encode_map(ctx, &map_d, od, 4, true, dbox, des)) {
+        p.tma_store = 0;  // direct stores still work for any bn that is a multiple of 16
+        map_d = map_a;
+    }
 
-    const size_t smem_bytes = (size_t)p.stages * p.stage_bytes + 1024 /*align*/ + 256 /*barriers*/;
+    const size_t smem_bytes = (size_t)p.stages * p.stage_bytes + 2 * STG_BYTES + 1024 /*align*/ + 256 /*barriers*/;
     const int grid = std::min(p.tiles_total, ctx->num_sms);
     cudaError_t e;
     if (L.kind == 0) {
         e = cudaFuncSetAttribute(umma_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return fail_cuda(ctx, e, "cudaFuncSetAttribute(umma_gemm<tf32>)");
-        umma_gemm_kernel<0><<<grid, NUM_THREADS, smem_bytes, ctx->stream>>>(map_a, map_b, p);
+        umma_gemm_kernel<0><<<grid, NUM_THREADS, smem_bytes, ctx->stream>>>(map_a, map_b, map_d, p);
     } else {
         e = cudaFuncSetAttribute(umma_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return fail_cuda(ctx, e, "cudaFuncSetAttribute(umma_gemm<i8>)");
-        umma_gemm_kernel<1><<<grid, NUM_THREADS, smem_bytes, ctx->stream>>>(map_a, map_b, p);
+        umma_gemm_kernel<1><<<grid, NUM_THREADS, smem_bytes, ctx->stream>>>(map_a, map_b, map_d, p);
     }
     e = cudaGetLastError();
     if (e != cudaSuccess) return fail_cuda(ctx, e, "umma_gemm launch");

@@ -185,7 +185,7 @@ class DeviceTensor:
         return all(s == 1 or st == c for s, st, c in zip(self.shape, self.strides, _contig(self.shape)))
 
     def copy_from(self, arr: np.ndarray):
-        arr = np.ascontiguousarray(arr, dtype=self.dtype)
+        arr = np.ascontiguousarray(arr, dtype=self.dtype).reshape(np.shape(arr))  # (ascontiguousarray turns 0-d into 1-d)
         assert arr.shape == self.shape
         src = _desc(arr.ctypes.data, arr.dtype, arr.shape, _contig(arr.shape), RTEN_DEVICE_HOST)
         dst = self.desc()

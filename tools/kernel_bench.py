@@ -15,7 +15,18 @@ import torch  # noqa: E402
 import rten_b200 as rt  # noqa: E402
 
 
-def time_fn(fn, stream, flush, iters=10, warm=3):
+CTX = None
+
+
+def time_fn(fn, stream, flush, iters=10, warm=3, graph=True):
+    """Median / best device time of one call.  Our ops are replayed from a CUDA graph so that the Python/ctypes
+    launch path (tens of microseconds) does not sit between the two events."""
+    if graph and CTX is not None:
+        fn()  # warm the pool
+        CTX.graph_begin()
+        fn()
+        g = CTX.graph_end()
+        fn = g.launch
     for _ in range(warm):
         fn()
     ts = []
@@ -35,6 +46,7 @@ def main():
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     ctx = rt.Context(0, stream=stream.cuda_stream)
+    global CTX
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     rows = []
 
@@ -49,25 +61,30 @@ def main():
     for n in (4096, 8192):
         a = torch.randn(n, n, device="cuda", dtype=torch.bfloat16)
         b = torch.randn(n, n, device="cuda", dtype=torch.bfloat16)
-        rec(f"cublas bf16 {n}^3", 2.0 * n ** 3, *time_fn(lambda: torch.matmul(a, b), stream, flush))
+        rec(f"cublas bf16 {n}^3", 2.0 * n ** 3, *time_fn(lambda: torch.matmul(a, b), stream, flush, graph=False))
         a32, b32 = a.float(), b.float()
         torch.backends.cuda.matmul.allow_tf32 = True
-        rec(f"cublas tf32 {n}^3", 2.0 * n ** 3, *time_fn(lambda: torch.matmul(a32, b32), stream, flush))
+        rec(f"cublas tf32 {n}^3", 2.0 * n ** 3, *time_fn(lambda: torch.matmul(a32, b32), stream, flush, graph=False))
         torch.backends.cuda.matmul.allow_tf32 = False
-        rec(f"cublas fp32 {n}^3", 2.0 * n ** 3, *time_fn(lambda: torch.matmul(a32, b32), stream, flush, iters=3, warm=1))
+        rec(f"cublas fp32 {n}^3", 2.0 * n ** 3, *time_fn(lambda: torch.matmul(a32, b32), stream, flush, iters=3, warm=1, graph=False))
         ai = torch.randint(-128, 127, (n, n), device="cuda", dtype=torch.int8)
         bi = torch.randint(-128, 127, (n, n), device="cuda", dtype=torch.int8)
         try:
-            rec(f"cublas int8 {n}^3", 2.0 * n ** 3, *time_fn(lambda: torch._int_mm(ai, bi), stream, flush))
+            rec(f"cublas int8 {n}^3", 2.0 * n ** 3, *time_fn(lambda: torch._int_mm(ai, bi), stream, flush, graph=False))
         except Exception as ex:  # noqa: BLE001
             print("torch._int_mm unavailable:", ex)
         del a, b, a32, b32, ai, bi
 
+    CTX = ctx
     # ---- our GEMM: plain shapes
     mm = rt.MatMul()
     for (m, n, k) in [(8192, 8192, 8192), (4096, 4096, 4096), (2048, 768, 768), (2048, 3072, 768), (2048, 768, 3072), (32, 1000, 2048)]:
-        a = rt.from_torch(ctx, torch.randn(m, k, device="cuda"))
+        at_ = torch.randn(m, k, device="cuda")
+        a = rt.from_torch(ctx, at_)
         bt = torch.randn(n, k, device="cuda")
+        torch.backends.cuda.matmul.allow_tf32 = True
+        rec(f"cublas tf32 gemm {m}x{n}x{k}", 2.0 * m * n * k, *time_fn(lambda: torch.matmul(at_, bt.T), stream, flush, graph=False))
+        torch.backends.cuda.matmul.allow_tf32 = False
         b = rt.from_torch(ctx, bt).permute(1, 0)  # [K, N] view of K-major storage: no packing
         out = ctx.empty((m, n))
         rec(f"ours tf32 gemm {m}x{n}x{k}", 2.0 * m * n * k, *time_fn(lambda: mm.run(ctx, a, b, out=out), stream, flush))
