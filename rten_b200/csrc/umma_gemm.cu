@@ -261,69 +261,71 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                 }
                 tmem_ld_wait();
                 const int nbase = tc.n0 + c0;
-                // ---- fused epilogue arithmetic on this thread's 32 columns (in place in v[])
-                if (row_ok) {
-                    if (KIND == 0) {
-                        const bool rvec = e.r && e.r_col == 1 && (nbase + 32 <= p.N) &&
-                                          ((reinterpret_cast<uintptr_t>(e.r + r_off + nbase) & 15) == 0);
-                        const bool bvec = e.bias_kind == 1 && (nbase + 32 <= p.N) &&
-                                          ((reinterpret_cast<uintptr_t>(e.bias + nbase) & 15) == 0);
+                // ---- fast path (registers, fully unrolled): f32, act in {none, relu}, residual / bias absent or
+                //      128-bit loadable.  Everything else (gelu, strided residual, N tails, the integer zero-point
+                //      math) runs as a ROLLED loop over the staged row: keeps the unrolled code small enough for
+                //      the instruction cache.
+                const bool full = nbase + 32 <= p.N;
+                bool fast = (KIND == 0) && e.act <= 1 && full;
+                if (fast && e.r)
+                    fast = e.r_col == 1 && ((reinterpret_cast<uintptr_t>(e.r + r_off + nbase) & 15) == 0);
+                if (fast && e.bias_kind == 1) fast = (reinterpret_cast<uintptr_t>(e.bias + nbase) & 15) == 0;
+                fast = __all_sync(0xffffffffu, fast || !row_ok);
+                if (fast && row_ok) {
+                    const float relu_floor = e.act == 1 ? 0.0f : -__int_as_float(0x7f800000);
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            float rr[4] = {0.f, 0.f, 0.f, 0.f}, bb[4] = {0.f, 0.f, 0.f, 0.f};
-                            if (rvec) {
-                                const float4 t4 = *reinterpret_cast<const float4*>(e.r + r_off + nbase + j);
-                                rr[0] = t4.x, rr[1] = t4.y, rr[2] = t4.z, rr[3] = t4.w;
-                            } else if (e.r) {
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 rr = make_float4(0.f, 0.f, 0.f, 0.f), bb = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (e.r) rr = *reinterpret_cast<const float4*>(e.r + r_off + nbase + j);
+                        if (e.bias_kind == 1) bb = __ldg(reinterpret_cast<const float4*>(e.bias + nbase + j));
+                        const float r4[4] = {rr.x, rr.y, rr.z, rr.w}, b4[4] = {bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
-                                for (int u = 0; u < 4; u++)
-                                    if (nbase + j + u < p.N) rr[u] = e.r[r_off + (long long)(nbase + j + u) * e.r_col];
-                            }
-                            if (bvec) {
-                                const float4 t4 = __ldg(reinterpret_cast<const float4*>(e.bias + nbase + j));
-                                bb[0] = t4.x, bb[1] = t4.y, bb[2] = t4.z, bb[3] = t4.w;
-                            } else if (e.bias_kind == 1) {
-#pragma unroll
-                                for (int u = 0; u < 4; u++)
-                                    if (nbase + j + u < p.N) bb[u] = e.bias[nbase + j + u];
-                            }
-#pragma unroll
-                            for (int u = 0; u < 4; u++) {
-                                float x = __uint_as_float(v[j + u]) * e.alpha;
-                                if (e.r) x = fmaf(e.r_scale, rr[u], x);
-                                x += bb[u];
-                                x += row_bias;
-                                v[j + u] = __float_as_uint(apply_act(x, e.act));
-                            }
+                        for (int u = 0; u < 4; u++) {
+                            float x = __uint_as_float(v[j + u]) * e.alpha;
+                            x = fmaf(e.r_scale, r4[u], x);
+                            x = x + b4[u] + row_bias;
+                            v[j + u] = __float_as_uint(fmaxf(x, relu_floor));
                         }
-                    } else {
+                    }
+                }
+                // ---- stage the row chunk in shared memory (128 B per row, 16-byte chunks XOR-swizzled by r & 7)
+                if (p.tma_store) {
+                    // the previous TMA store of this group must have finished READING the staging buffer
+                    if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+                }
+                uint8_t* rowp = stg + r * 128;
+                const int sw = r & 7;
 #pragma unroll
-                        for (int j = 0; j < 32; j++) {
-                            const int n = nbase + j;
-                            if (n < p.N) {
-                                // exact i32 arithmetic with wrap-around (unsigned ops)
-                                unsigned c = v[j];
-                                if (e.za) c -= (unsigned)za_v * (unsigned)e.colsum[n];
-                                if (e.zb) {
-                                    const unsigned zbv = (unsigned)e.zb[n % e.zb_len];
-                                    c -= zbv * (unsigned)rs_v;
-                                    if (e.za) c += (unsigned)p.K * (unsigned)za_v * zbv;
-                                }
-                                v[j] = e.scale ? __float_as_uint(__int2float_rn((int)c) * e.scale[n % e.scale_len]) : c;
+                for (int j = 0; j < 8; j++)
+                    *reinterpret_cast<uint4*>(rowp + ((j ^ sw) << 4)) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                if (!fast && row_ok) {
+                    // rolled slow path on this thread's own staged row
+#pragma unroll 1
+                    for (int j = 0; j < ncols; j++) {
+                        const int n = nbase + j;
+                        if (n >= p.N) break;
+                        uint32_t* sp = reinterpret_cast<uint32_t*>(rowp + (((j >> 2) ^ sw) << 4)) + (j & 3);
+                        if (KIND == 0) {
+                            float x = __uint_as_float(*sp) * e.alpha;
+                            if (e.r) x = fmaf(e.r_scale, e.r[r_off + (long long)n * e.r_col], x);
+                            if (e.bias_kind == 1) x += e.bias[n];
+                            x += row_bias;
+                            *sp = __float_as_uint(apply_act(x, e.act));
+                        } else {
+                            // exact i32 arithmetic with wrap-around (unsigned ops)
+                            unsigned c = *sp;
+                            if (e.za) c -= (unsigned)za_v * (unsigned)e.colsum[n];
+                            if (e.zb) {
+                                const unsigned zbv = (unsigned)e.zb[n % e.zb_len];
+                                c -= zbv * (unsigned)rs_v;
+                                if (e.za) c += (unsigned)p.K * (unsigned)za_v * zbv;
                             }
+                            *sp = e.scale ? __float_as_uint(__int2float_rn((int)c) * e.scale[n % e.scale_len]) : c;
                         }
                     }
                 }
                 if (p.tma_store) {
-                    // previous TMA store of this group must have finished READING the staging buffer
-                    if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                    asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
-                    // row r -> 128 bytes at r*128, 16-byte chunks XOR-swizzled by (r & 7)  (== SWIZZLE_128B)
-                    uint8_t* rowp = stg + r * 128;
-#pragma unroll
-                    for (int j = 0; j < 8; j++) {
-                        *reinterpret_cast<uint4*>(rowp + ((j ^ (r & 7)) << 4)) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                    }
                     fence_proxy_async();
                     asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
                     if (issuer) {
@@ -334,18 +336,13 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
                 } else if (row_ok) {
+                    // direct stores from the staged row (any output strides); consecutive lanes = consecutive rows
                     uint32_t* dptr = reinterpret_cast<uint32_t*>(e.d) + d_off;
-                    const bool vec = (e.s_col == 1) && (nbase + ncols <= p.N) && ((reinterpret_cast<uintptr_t>(dptr + nbase) & 15) == 0);
-                    if (vec) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4)
-                            if (j < ncols) *reinterpret_cast<uint4*>(dptr + nbase + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; j++) {
-                            const int n = nbase + j;
-                            if (j < ncols && n < p.N) dptr[(long long)n * e.s_col] = v[j];
-                        }
+#pragma unroll 1
+                    for (int j = 0; j < ncols; j++) {
+                        const int n = nbase + j;
+                        if (n >= p.N) break;
+                        dptr[(long long)n * e.s_col] = *(reinterpret_cast<const uint32_t*>(rowp + (((j >> 2) ^ sw) << 4)) + (j & 3));
                     }
                 }
                 __syncwarp();
