@@ -288,6 +288,25 @@ rten_status rten_b200_copy(rten_ctx* ctx, const rten_tensor* src, rten_tensor* d
     return sc.finish(st);
 }
 
+// ---- debug: in-kernel pipeline trace of CTA 0 of the GEMM kernel (clock64 at stage hand-offs)
+rten_status rten_b200_debug_trace(rten_ctx* ctx, int enable, int64_t* host_out_8192_or_null) {
+    if (!ctx) return RTEN_ERR_INVALID_VALUE;
+    cudaSetDevice(ctx->device);
+    const size_t bytes = 4 * 2048 * sizeof(int64_t);
+    if (ctx->trace && host_out_8192_or_null) {
+        RTB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        RTB_CUDA(ctx, cudaMemcpy(host_out_8192_or_null, ctx->trace, bytes, cudaMemcpyDeviceToHost));
+    }
+    if (enable) {
+        if (!ctx->trace) RTB_CUDA(ctx, cudaMalloc(&ctx->trace, bytes));
+        RTB_CUDA(ctx, cudaMemsetAsync(ctx->trace, 0, bytes, ctx->stream));
+    } else if (ctx->trace) {
+        cudaFree(ctx->trace);
+        ctx->trace = nullptr;
+    }
+    return RTEN_OK;
+}
+
 // ---- CUDA graphs --------------------------------------------------------------------------
 rten_status rten_b200_graph_begin(rten_ctx* ctx) {
     if (!ctx) return RTEN_ERR_INVALID_VALUE;

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -650,6 +651,85 @@ rten_status conv_core(OpScope& sc, ConvArgs& A, rten_tensor* out) {
                 pl_s = 0;
             }
         }
+    }
+
+    // ---- small-channel path (C <= 4, e.g. the RGB stem): NHWC4 zero-padded copy, one 128-byte K block per filter
+    //      row holding kw pixels x 4 channels; vertical padding / stride stay in the TMA tile addressing.
+    const bool smallc_ok = !implicit_ok && A.kind == 0 && groups == 1 && Cg <= 4 && kw * 4 <= 32 && dil[1] == 1 &&
+                           (int64_t)B * OH * OW > 0 && !getenv("RTEN_B200_NO_SMALLC");
+    if (smallc_ok) {
+        const int64_t Wp = (OW - 1) * strides[1] + 8;  // every window of 8 pixels stays inside the padded row
+        float* xp = nullptr;
+        RTB_TRY(temp_alloc(ctx, (size_t)(B * H * Wp * 4) * 4, (void**)&xp));
+        RTB_TRY(launch_smallc_pad(ctx, (const float*)x.data, xp, (int)B, (int)C, (int)H, (int)W, (int)Wp, (int)pl, x.strides[0],
+                                  x.strides[1], x.strides[2], x.strides[3]));
+        float* wsm = nullptr;
+        RTB_TRY(temp_alloc(ctx, (size_t)(O * kh * 32) * 4, (void**)&wsm));
+        RTB_TRY(launch_smallc_pack_w(ctx, (const float*)w.data, wsm, (int)O, (int)C, (int)kh, (int)kw, w.strides[0], w.strides[1],
+                                     w.strides[2], w.strides[3]));
+        GemmLaunch L;
+        L.kind = 0;
+        L.conv = 1;
+        L.N = (int)O;
+        L.K = (int)(kh * 32);
+        L.M = (int)(B * OH * OW);
+        L.g.B = (int)B;
+        L.g.H = (int)H;
+        L.g.W = (int)OW;  // dim 1 of the A map indexes output columns directly
+        L.g.C = 32;
+        L.g.OH = (int)OH;
+        L.g.OW = (int)OW;
+        L.g.kh = (int)kh;
+        L.g.kw = 1;
+        L.g.sy = (int)strides[0];
+        L.g.sx = 1;
+        L.g.dy = (int)dil[0];
+        L.g.dx = 1;
+        L.g.pt = (int)pt;
+        L.g.pl = 0;
+        L.a.base = xp;
+        L.a.dims[0] = 32;
+        L.a.dims[1] = OW;
+        L.a.dims[2] = H;
+        L.a.dims[3] = B;
+        L.a.strides[0] = 1;
+        L.a.strides[1] = strides[1] * 4;
+        L.a.strides[2] = Wp * 4;
+        L.a.strides[3] = H * Wp * 4;
+        L.b.base = wsm;
+        L.b.dims[0] = 32;
+        L.b.dims[1] = O;
+        L.b.dims[2] = kh;
+        L.b.dims[3] = 1;
+        L.b.strides[0] = 1;
+        L.b.strides[1] = kh * 32;
+        L.b.strides[2] = 32;
+        L.b.strides[3] = 0;
+        EpilogueDesc& e = L.epi;
+        e.d = ov.data;
+        e.s_z0 = ov.strides[0];
+        e.s_row = ov.strides[2];
+        e.s_z1 = ov.strides[3];
+        e.s_col = ov.strides[1];
+        e.act = A.act;
+        if (A.bias) {
+            rten_tensor bc;
+            RTB_TRY(sc.contiguous(&bias_v, &bc));
+            e.bias = (const float*)bc.data;
+            e.bias_kind = 1;
+        }
+        if (A.residual) {
+            e.r = (const float*)res_v.data;
+            e.r_scale = 1.0f;
+            e.r_z0 = res_v.strides[0];
+            e.r_row = res_v.strides[2];
+            e.r_z1 = res_v.strides[3];
+            e.r_col = res_v.strides[1];
+        }
+        rten_status st = launch_umma_gemm(ctx, L);
+        if (st == RTEN_OK) return RTEN_OK;
+        if (st != RTEN_ERR_UNSUPPORTED_VALUE) return st;
+        // otherwise fall through to the generic explicit path
     }
 
     for (int g = 0; g < groups; g++) {

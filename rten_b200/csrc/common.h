@@ -52,6 +52,7 @@ struct rten_ctx {
     DevicePool pool;
     // scratch released at the end of each op call
     std::vector<void*> temps;
+    void* trace = nullptr;         // device buffer of 4 x 2048 int64 timestamps (debug), or null
     void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled (driver entry point)
 };
 

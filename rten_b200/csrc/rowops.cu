@@ -678,8 +678,100 @@ rten_status launch_im2col(rten_ctx* ctx, int esize, const void* x, void* out, co
 }
 
 // =========================================================================================
+// Small-channel convolution support (C <= 4, e.g. the 3-channel ResNet stem): the image is copied once into a
+// zero-padded NHWC4 buffer so that the kw pixels x 4 channels under a filter row are 4*kw CONTIGUOUS floats; the
+// implicit-GEMM kernel then reads them as one 128-byte K block per filter row (ky).
+// =========================================================================================
+__global__ void __launch_bounds__(256)
+smallc_pad_kernel(const float* __restrict__ x, float* __restrict__ xp, int B, int C, int H, int W, int Wp, int pl,
+                  long long xs_b, long long xs_c, long long xs_h, long long xs_w) {
+    const long long total = (long long)B * H * Wp;  // one thread per padded pixel (4 channels = one float4)
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int xw = (int)(i % Wp);
+        const long long r = i / Wp;
+        const int y = (int)(r % H);
+        const int b = (int)(r / H);
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        const int ix = xw - pl;
+        if (ix >= 0 && ix < W) {
+            const float* src = x + (long long)b * xs_b + (long long)y * xs_h + (long long)ix * xs_w;
+            for (int c = 0; c < C; c++) v[c] = src[(long long)c * xs_c];
+        }
+        reinterpret_cast<float4*>(xp)[i] = make_float4(v[0], v[1], v[2], v[3]);
+    }
+}
+
+// w [O, C, kh, kw] (strides) -> wp [O, kh, 32]: element (kx*4 + c) of filter row ky, zero elsewhere
+__global__ void smallc_pack_w_kernel(const float* __restrict__ w, float* __restrict__ wp, int O, int C, int kh, int kw,
+                                     long long ws_o, long long ws_c, long long ws_h, long long ws_w) {
+    const int total = O * kh * 32;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int j = i % 32;
+        const int ky = (i / 32) % kh;
+        const int o = i / (32 * kh);
+        const int kx = j >> 2, c = j & 3;
+        wp[i] = (kx < kw && c < C) ? w[o * ws_o + c * ws_c + ky * ws_h + kx * ws_w] : 0.0f;
+    }
+}
+
+rten_status launch_smallc_pad(rten_ctx* ctx, const float* x, float* xp, int B, int C, int H, int W, int Wp, int pl,
+                              long long xs_b, long long xs_c, long long xs_h, long long xs_w) {
+    const long long total = (long long)B * H * Wp;
+    if (total == 0) return RTEN_OK;
+    smallc_pad_kernel<<<ew_grid(ctx, total), 256, 0, ctx->stream>>>(x, xp, B, C, H, W, Wp, pl, xs_b, xs_c, xs_h, xs_w);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "smallc_pad launch");
+    count_launch(ctx);
+    return RTEN_OK;
+}
+
+rten_status launch_smallc_pack_w(rten_ctx* ctx, const float* w, float* wp, int O, int C, int kh, int kw, long long ws_o,
+                                 long long ws_c, long long ws_h, long long ws_w) {
+    const int total = O * kh * 32;
+    if (total == 0) return RTEN_OK;
+    smallc_pack_w_kernel<<<(total + 255) / 256, 256, 0, ctx->stream>>>(w, wp, O, C, kh, kw, ws_o, ws_c, ws_h, ws_w);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "smallc_pack_w launch");
+    count_launch(ctx);
+    return RTEN_OK;
+}
+
+// =========================================================================================
 // Pooling / gather
 // =========================================================================================
+// channels-last fast path: one thread per (pixel, 4 channels), 128-bit loads/stores
+__global__ void __launch_bounds__(256) maxpool_cl4_kernel(const float* __restrict__ x, float* __restrict__ y, PoolParams p) {
+    const int C4 = p.C >> 2;
+    const long long total = (long long)p.B * p.OH * p.OW * C4;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        long long rem = i;
+        const int c = (int)(rem % C4) << 2;
+        rem /= C4;
+        const int ox = (int)(rem % p.OW);
+        rem /= p.OW;
+        const int oy = (int)(rem % p.OH);
+        const int b = (int)(rem / p.OH);
+        const float ninf = __int_as_float(0xff800000);
+        float4 m = make_float4(ninf, ninf, ninf, ninf);
+        for (int ky = 0; ky < p.kh; ky++) {
+            const int iy = oy * p.sy - p.pt + ky;
+            if (iy < 0 || iy >= p.H) continue;
+            for (int kx = 0; kx < p.kw; kx++) {
+                const int ix = ox * p.sx - p.pl + kx;
+                if (ix < 0 || ix >= p.W) continue;
+                const float4 v = *reinterpret_cast<const float4*>(x + (long long)b * p.xs_b + (long long)iy * p.xs_h + (long long)ix * p.xs_w + c);
+                m.x = v.x > m.x ? v.x : m.x;
+                m.y = v.y > m.y ? v.y : m.y;
+                m.z = v.z > m.z ? v.z : m.z;
+                m.w = v.w > m.w ? v.w : m.w;
+            }
+        }
+        *reinterpret_cast<float4*>(y + (long long)b * p.ys_b + (long long)oy * p.ys_h + (long long)ox * p.ys_w + c) = m;
+    }
+}
+
 __global__ void __launch_bounds__(256) maxpool_kernel(const float* __restrict__ x, float* __restrict__ y, PoolParams p) {
     const long long total = (long long)p.B * p.C * p.OH * p.OW;
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -719,7 +811,13 @@ __global__ void __launch_bounds__(256) maxpool_kernel(const float* __restrict__ 
 rten_status launch_maxpool(rten_ctx* ctx, const float* x, float* y, const PoolParams& p) {
     const long long total = (long long)p.B * p.C * p.OH * p.OW;
     if (total == 0) return RTEN_OK;
-    maxpool_kernel<<<ew_grid(ctx, total), 256, 0, ctx->stream>>>(x, y, p);
+    const bool cl4 = p.xs_c == 1 && p.ys_c == 1 && (p.C % 4) == 0 && (p.xs_b % 4) == 0 && (p.xs_h % 4) == 0 &&
+                     (p.xs_w % 4) == 0 && (p.ys_b % 4) == 0 && (p.ys_h % 4) == 0 && (p.ys_w % 4) == 0 &&
+                     ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+    if (cl4)
+        maxpool_cl4_kernel<<<ew_grid(ctx, total / 4), 256, 0, ctx->stream>>>(x, y, p);
+    else
+        maxpool_kernel<<<ew_grid(ctx, total), 256, 0, ctx->stream>>>(x, y, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail_cuda(ctx, e, "maxpool launch");
     count_launch(ctx);

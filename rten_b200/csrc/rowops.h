@@ -44,6 +44,11 @@ struct Im2ColParams {
 };
 rten_status launch_im2col(rten_ctx* ctx, int esize, const void* x, void* out, const Im2ColParams& p, int pad_value);
 
+rten_status launch_smallc_pad(rten_ctx* ctx, const float* x, float* xp, int B, int C, int H, int W, int Wp, int pl,
+                              long long xs_b, long long xs_c, long long xs_h, long long xs_w);
+rten_status launch_smallc_pack_w(rten_ctx* ctx, const float* w, float* wp, int O, int C, int kh, int kw, long long ws_o,
+                                 long long ws_c, long long ws_h, long long ws_w);
+
 struct PoolParams {
     int B, C, H, W, OH, OW, kh, kw, sy, sx, pt, pl;
     long long xs_b, xs_c, xs_h, xs_w, ys_b, ys_c, ys_h, ys_w;

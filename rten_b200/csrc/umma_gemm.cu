@@ -54,6 +54,9 @@ struct KParams {
     int OH, OW, Bn;
     int sy, sx, dy, dx, pt, pl, kw, c_blocks;
     int a_bcast0, a_bcast1, b_bcast0, b_bcast1;
+    long long* trace;  // debug: per-event clock64 timestamps of CTA 0 (4 rows x 2048), or null
+    int pair;       // 1: each CTA iteration computes TWO 128-row tiles sharing one B tile (interleaved MMAs on two
+                    //    accumulators hide the dependent-accumulate latency when bn <= 128)
     int tma_store;  // 1: epilogue stages 128x32 chunks in smem and writes them with TMA (output rows contiguous)
     EpilogueDesc epi;
 };
@@ -65,12 +68,15 @@ struct TileCoord {
     int ox0, oy0, b0;  // conv
 };
 
-__device__ __forceinline__ TileCoord decode_tile(const KParams& p, int t) {
+// t indexes work units: (n tile, m tile or PAIR of m tiles, batch); `sub` selects the tile inside a pair.
+__device__ __forceinline__ TileCoord decode_tile(const KParams& p, int t, int sub) {
     TileCoord c;
     int n_blk = t % p.tiles_n;
     int rest = t / p.tiles_n;
-    int m_blk = rest % p.tiles_m;
-    int z = rest / p.tiles_m;
+    const int units_m = p.pair ? (p.tiles_m + 1) / 2 : p.tiles_m;
+    int m_blk = rest % units_m;
+    int z = rest / units_m;
+    if (p.pair) m_blk = 2 * m_blk + sub;  // may be == tiles_m for the odd tail: every row is then out of range
     c.n0 = n_blk * p.bn;
     c.m0 = m_blk * BM;
     c.z0 = z % p.z0;
@@ -80,7 +86,7 @@ __device__ __forceinline__ TileCoord decode_tile(const KParams& p, int t) {
         int xt = m_blk % p.tiles_x;
         int r2 = m_blk / p.tiles_x;
         int yt = r2 % p.tiles_y;
-        int bt = r2 / p.tiles_y;
+        int bt = r2 / p.tiles_y;  // >= number of batch tiles for the odd tail of a pair -> b0 >= B
         c.ox0 = xt * p.tw;
         c.oy0 = yt * p.th;
         c.b0 = bt * p.tb;
@@ -135,12 +141,15 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
+            int tr_p = 0;
             for (int t = blockIdx.x; t < p.tiles_total; t += gridDim.x) {
-                const TileCoord tc = decode_tile(p, t);
+                const TileCoord tc = decode_tile(p, t, 0);
+                const TileCoord tc1 = decode_tile(p, t, 1);
                 for (int kb = 0; kb < p.k_blocks; kb++) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if (p.trace && blockIdx.x == 0 && tr_p < 2048) p.trace[tr_p++] = clock64();
                     uint8_t* sa = smem + (size_t)stage * p.stage_bytes;
-                    uint8_t* sb = sa + A_STAGE_BYTES;
+                    uint8_t* sb = sa + (p.pair ? 2 : 1) * A_STAGE_BYTES;
                     mbar_expect_tx(&full_bar[stage], p.tx_bytes);
                     if (p.conv) {
                         const int tap = kb / p.c_blocks;
@@ -149,10 +158,16 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                         const int kx = tap - ky * p.kw;
                         tma_load_4d(sa, &tma_a, &full_bar[stage], cb * p.kelems, tc.ox0 * p.sx - p.pl + kx * p.dx,
                                     tc.oy0 * p.sy - p.pt + ky * p.dy, tc.b0);
+                        if (p.pair)
+                            tma_load_4d(sa + A_STAGE_BYTES, &tma_a, &full_bar[stage], cb * p.kelems,
+                                        tc1.ox0 * p.sx - p.pl + kx * p.dx, tc1.oy0 * p.sy - p.pt + ky * p.dy, tc1.b0);
                         tma_load_4d(sb, &tma_b, &full_bar[stage], cb * p.kelems, tc.n0, tap, 0);
                     } else {
                         tma_load_4d(sa, &tma_a, &full_bar[stage], kb * p.kelems, tc.m0, p.a_bcast0 ? 0 : tc.z0,
                                     p.a_bcast1 ? 0 : tc.z1);
+                        if (p.pair)
+                            tma_load_4d(sa + A_STAGE_BYTES, &tma_a, &full_bar[stage], kb * p.kelems, tc1.m0,
+                                        p.a_bcast0 ? 0 : tc.z0, p.a_bcast1 ? 0 : tc.z1);
                         tma_load_4d(sb, &tma_b, &full_bar[stage], kb * p.kelems, tc.n0, p.b_bcast0 ? 0 : tc.z0,
                                     p.b_bcast1 ? 0 : tc.z1);
                     }
@@ -169,6 +184,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
+            int tr_m = 0;
             for (int t = blockIdx.x; t < p.tiles_total; t += gridDim.x, it++) {
                 const int acc = it & 1;
                 const uint32_t acc_phase = (it >> 1) & 1;
@@ -177,10 +193,12 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                 const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
                 for (int kb = 0; kb < p.k_blocks; kb++) {
                     mbar_wait(&full_bar[stage], phase);
+                    if (p.trace && blockIdx.x == 0 && tr_m < 2048) p.trace[2048 + tr_m++] = clock64();
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + (size_t)stage * p.stage_bytes);
                     const uint64_t adesc = make_kmajor_sw128_desc(sa);
-                    const uint64_t bdesc = make_kmajor_sw128_desc(sa + A_STAGE_BYTES);
+                    const uint64_t adesc1 = make_kmajor_sw128_desc(sa + A_STAGE_BYTES);
+                    const uint64_t bdesc = make_kmajor_sw128_desc(sa + (p.pair ? 2 : 1) * A_STAGE_BYTES);
 #pragma unroll
                     for (int k = 0; k < 4; k++) {
                         // advance 32 B along K inside the swizzle atom: +2 in the (addr >> 4) field
@@ -189,6 +207,12 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                             umma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, accum);
                         else
                             umma_i8(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, accum);
+                        if (p.pair) {  // second tile of the pair: independent accumulator, same B operand
+                            if (KIND == 0)
+                                umma_tf32(d_tmem + p.bn, adesc1 + 2 * k, bdesc + 2 * k, p.idesc, accum);
+                            else
+                                umma_i8(d_tmem + p.bn, adesc1 + 2 * k, bdesc + 2 * k, p.idesc, accum);
+                        }
                     }
                     umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
                     if (++stage == p.stages) {
@@ -211,7 +235,11 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         for (int t = blockIdx.x; t < p.tiles_total; t += gridDim.x, it++) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
-            const TileCoord tc = decode_tile(p, t);
+            mbar_wait(&tmem_full[acc], acc_phase);
+            if (p.trace && blockIdx.x == 0 && warp == 4 && lane == 0 && it < 2048) p.trace[4096 + it] = clock64();
+            tc_fence_after();
+            for (int sub = 0; sub <= p.pair; sub++) {
+            const TileCoord tc = decode_tile(p, t, sub);
             // ---- row bookkeeping
             bool row_ok;
             long long d_off, r_off;
@@ -243,9 +271,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                     if (e.zb) rs_v = e.rowsum[m_idx];
                 }
             }
-            mbar_wait(&tmem_full[acc], acc_phase);
-            tc_fence_after();
-            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_STRIDE;
+            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_STRIDE + sub * p.bn;
             for (int c0 = grp * 32; c0 < p.bn; c0 += 64) {
                 uint32_t v[32];
                 const int ncols = (p.bn - c0) >= 32 ? 32 : 16;
@@ -266,12 +292,12 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                 //      math) runs as a ROLLED loop over the staged row: keeps the unrolled code small enough for
                 //      the instruction cache.
                 const bool full = nbase + 32 <= p.N;
-                bool fast = (KIND == 0) && e.act <= 1 && full;
+                bool fast = (KIND == 0) ? (e.act <= 1 && full) : !(e.za || e.zb || e.scale);  // raw i32: nothing to do
                 if (fast && e.r)
                     fast = e.r_col == 1 && ((reinterpret_cast<uintptr_t>(e.r + r_off + nbase) & 15) == 0);
                 if (fast && e.bias_kind == 1) fast = (reinterpret_cast<uintptr_t>(e.bias + nbase) & 15) == 0;
                 fast = __all_sync(0xffffffffu, fast || !row_ok);
-                if (fast && row_ok) {
+                if (KIND == 0 && fast && row_ok) {
                     const float relu_floor = e.act == 1 ? 0.0f : -__int_as_float(0x7f800000);
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
@@ -347,8 +373,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                 }
                 __syncwarp();
             }
+            }  // sub
             tc_fence_before();
             __syncwarp();
+            if (p.trace && blockIdx.x == 0 && warp == 4 && lane == 0 && it < 2048) p.trace[6144 + it] = clock64();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         }
         // smem must stay valid until the last bulk store has read it
@@ -444,22 +472,38 @@ static void pick_conv_tile(const ConvGeom& g, int& tw, int& th, int& tb) {
     }
 }
 
-static int pick_bn(int N, long long tiles_m_total, int num_sms, int step) {
-    // minimise (waves) x (per-tile cost ~ bn + fixed overhead); `step` = 32 when the epilogue stores 32-column chunks
-    int best_bn = step;
-    double best_cost = 1e30;
-    int n16 = (N + step - 1) / step * step;
-    for (int bn = step; bn <= 256; bn += step) {
-        if (bn > n16 && bn != step) break;
-        long long tiles = tiles_m_total * ((N + bn - 1) / bn);
-        long long waves = (tiles + num_sms - 1) / num_sms;
-        double cost = (double)waves * (bn + 24.0);
-        if (cost < best_cost - 1e-9) {
-            best_cost = cost;
-            best_bn = bn;
+// Tile-shape choice.  Cost model (clocks per CTA, measured constants from the in-kernel trace, profiles/):
+//   a tcgen05.mma on one accumulator cannot retire faster than ~130 clk (dependent accumulate), its floor is bn/2 clk;
+//   in PAIR mode two tiles alternate on two accumulators, so each instruction effectively costs max(bn/2, 65);
+//   the epilogue costs ~350 clk per 32-column chunk per tile, split over two warp groups, and overlaps the next
+//   main loop (double-buffered TMEM), so a unit costs max(mainloop, epilogue) + a fixed hand-off.
+struct TileChoice {
+    int bn, pair;
+};
+static TileChoice pick_tile(int N, long long tiles_m, long long batch, int k_blocks, int num_sms, int step) {
+    TileChoice best{step, 0};
+    double best_cost = 1e300;
+    const int nmax = (N + step - 1) / step * step;
+    for (int pair = 0; pair <= 1; pair++) {
+        for (int bn = step; bn <= (pair ? 128 : 256); bn += step) {
+            if (bn > nmax && bn != step) break;
+            const long long tiles_n = (N + bn - 1) / bn;
+            const long long units_m = pair ? (tiles_m + 1) / 2 : tiles_m;
+            if (pair && tiles_m < 2) continue;
+            const long long units = units_m * tiles_n * batch;
+            const long long waves = (units + num_sms - 1) / num_sms;
+            const double instr = pair ? std::max(bn / 2.0, 65.0) : std::max(bn / 2.0, 130.0);
+            const double mainloop = (double)k_blocks * 4.0 * instr * (pair ? 2 : 1);
+            const double epi = (pair ? 2 : 1) * (bn / 32.0) * 350.0 / 2.0 + 600.0;
+            const double unit = std::max(mainloop, epi) + 900.0;
+            const double cost = (double)waves * unit;
+            if (cost < best_cost * 0.999) {
+                best_cost = cost;
+                best = {bn, pair};
+            }
         }
     }
-    return best_bn;
+    return best;
 }
 
 rten_status launch_umma_gemm(rten_ctx* ctx, const GemmLaunch& L) {
@@ -478,6 +522,7 @@ rten_status launch_umma_gemm(rten_ctx* ctx, const GemmLaunch& L) {
     p.kelems = kelems;
     p.conv = L.conv;
     p.epi = L.epi;
+    p.trace = reinterpret_cast<long long*>(ctx->trace);
     uint32_t abox[4], aes[4] = {1, 1, 1, 1}, bbox[4], bes[4] = {1, 1, 1, 1};
     long long tiles_m_total;
     uint32_t a_rows;
@@ -553,7 +598,15 @@ rten_status launch_umma_gemm(rten_ctx* ctx, const GemmLaunch& L) {
         p.tma_store = (e.s_col == 1 && L.N >= 4 && tma_compatible(od, 4, 4)) ? 1 : 0;
         if (getenv("RTEN_B200_NO_TMA_STORE")) p.tma_store = 0;
     }
-    p.bn = pick_bn(L.N, tiles_m_total, ctx->num_sms, p.tma_store ? 32 : 16);
+    {
+        const long long batch = L.conv ? 1 : (long long)L.z0 * L.z1;
+        TileChoice tcz = pick_tile(L.N, p.tiles_m, batch, p.k_blocks, ctx->num_sms, p.tma_store ? 32 : 16);
+        if (const char* f = getenv("RTEN_B200_FORCE_BN")) tcz.bn = atoi(f);
+        if (const char* f = getenv("RTEN_B200_FORCE_PAIR")) tcz.pair = atoi(f) && tcz.bn <= 128 && p.tiles_m >= 2;
+        p.bn = tcz.bn;
+        p.pair = tcz.pair;
+        tiles_m_total = (p.pair ? (p.tiles_m + 1) / 2 : p.tiles_m) * batch;
+    }
     p.tiles_n = (L.N + p.bn - 1) / p.bn;
     long long tt = tiles_m_total * p.tiles_n;
     if (tt > 0x7FFFFFFFll) return RTEN_ERR_UNSUPPORTED_VALUE;
@@ -562,8 +615,8 @@ rten_status launch_umma_gemm(rten_ctx* ctx, const GemmLaunch& L) {
     bbox[1] = p.bn;
     bbox[2] = 1;
     bbox[3] = 1;
-    p.stage_bytes = A_STAGE_BYTES + p.bn * KBYTES;
-    p.tx_bytes = a_rows * KBYTES + p.bn * KBYTES;
+    p.stage_bytes = (p.pair ? 2 : 1) * A_STAGE_BYTES + p.bn * KBYTES;
+    p.tx_bytes = (p.pair ? 2 : 1) * a_rows * KBYTES + p.bn * KBYTES;
     const int smem_budget = 227 * 1024 - 2048 - 2 * STG_BYTES;
     p.stages = std::min(MAX_STAGES, smem_budget / (int)p.stage_bytes);
     if (p.stages < 2) return RTEN_ERR_UNSUPPORTED_VALUE;

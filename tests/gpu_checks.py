@@ -219,6 +219,10 @@ def check_matmul_shapes(rt, oracle):
     worst = max(worst, _matmul_case(rt, oracle, ctx, (2, 5, 12), (12, 7), bias=True, alpha=0.125))
     worst = max(worst, _matmul_case(rt, oracle, ctx, (200, 96), (96, 80), bias=True, prepack=True))
     worst = max(worst, _matmul_case(rt, oracle, ctx, (4, 3, 128, 64), (4, 3, 64, 128), alpha=0.125, b_kmajor=True))
+    # many row tiles with a narrow N (pair mode), odd tile counts, N / K tails
+    worst = max(worst, _matmul_case(rt, oracle, ctx, (128 * 301 + 5, 72), (72, 64), bias=True, prepack=True))
+    worst = max(worst, _matmul_case(rt, oracle, ctx, (40000, 40), (40, 100), b_kmajor=True))
+    worst = max(worst, _matmul_case(rt, oracle, ctx, (3, 128 * 151, 33), (33, 36)))
     # zero sized dims (src/ops/matmul.rs:1344-1361)
     for ash, bsh in [((2, 0, 10), (10, 8)), ((3, 10), (10, 0)), ((3, 0), (0, 4))]:
         got = rt.MatMul().run(ctx, np.zeros(ash, np.float32), np.zeros(bsh, np.float32)).numpy()
@@ -393,6 +397,15 @@ def check_conv_more(rt, oracle):
     w = max(w, _conv_case(rt, oracle, ctx, (4, 96, 14, 14), (80, 96, 3, 3), pads=(1, 1, 1, 1), cl=True, bias=False))            # C tail (96 = 3*32), odd N
     w = max(w, _conv_case(rt, oracle, ctx, (2, 40, 6, 6), (16, 40, 3, 3), pads=(1, 1, 1, 1), cl=True))                          # C=40: K tail inside a block
     w = max(w, _conv_case(rt, oracle, ctx, (2, 16, 5, 5), (8, 16, 1, 1), cl=False, residual=True, act=1))
+    # small-channel path (C <= 4): stem-like shapes, both layouts, asymmetric pads, stride, vertical dilation
+    w = max(w, _conv_case(rt, oracle, ctx, (2, 3, 33, 29), (16, 3, 7, 7), pads=(3, 3, 3, 3), strides=(2, 2), cl=True))
+    w = max(w, _conv_case(rt, oracle, ctx, (2, 3, 33, 29), (16, 3, 7, 7), pads=(3, 3, 3, 3), strides=(2, 2), cl=False, act=1))
+    w = max(w, _conv_case(rt, oracle, ctx, (1, 4, 12, 12), (8, 4, 5, 5), pads=(2, 2, 2, 2), cl=True))
+    w = max(w, _conv_case(rt, oracle, ctx, (3, 2, 9, 14), (5, 2, 3, 4), pads=(0, 2, 1, 0), strides=(1, 3), dil=(2, 1)))
+    w = max(w, _conv_case(rt, oracle, ctx, (2, 1, 10, 10), (6, 1, 3, 8), pads=(1, 4, 1, 3), residual=True))
+    # pair mode / odd tile counts / N tails through the TMA-store epilogue
+    w = max(w, _conv_case(rt, oracle, ctx, (5, 32, 20, 20), (72, 32, 3, 3), pads=(1, 1, 1, 1), cl=True))
+    w = max(w, _conv_case(rt, oracle, ctx, (3, 64, 28, 28), (100, 64, 1, 1), cl=True, residual=True, act=1))
     # 1-D conv (conv.rs:142-185)
     r = oracle.XorShiftRng(5)
     x, k = r.uniform((2, 3, 11)), r.uniform((4, 3, 3))
