@@ -472,11 +472,14 @@ static void pick_conv_tile(const ConvGeom& g, int& tw, int& th, int& tb) {
     }
 }
 
-// Tile-shape choice.  Cost model (clocks per CTA, measured constants from the in-kernel trace, profiles/):
-//   a tcgen05.mma on one accumulator cannot retire faster than ~130 clk (dependent accumulate), its floor is bn/2 clk;
-//   in PAIR mode two tiles alternate on two accumulators, so each instruction effectively costs max(bn/2, 65);
-//   the epilogue costs ~350 clk per 32-column chunk per tile, split over two warp groups, and overlaps the next
-//   main loop (double-buffered TMEM), so a unit costs max(mainloop, epilogue) + a fixed hand-off.
+// Tile-shape choice.  Cost model in clocks per CTA, constants measured with the in-kernel trace (tools/trace_probe.py,
+// profiles/r01_trace_*.txt):
+//   * a tcgen05.mma (SS operands) is bound by operand fetch from shared memory at ~64 B/clk: A (128 rows x 32 B) + B
+//     (bn rows x 32 B) -> 64 + bn/2 clk per instruction, 4 instructions per 128-byte K block;
+//   * consecutive MMAs on ONE accumulator cannot retire faster than ~140 clk each (dependent accumulate); PAIR mode
+//     alternates two tiles on two accumulators and removes that floor (and loads B once for both tiles);
+//   * a K block cannot complete faster than TMA latency / stages in flight (~2200 clk under load);
+//   * the epilogue (~350 clk per 32-column chunk, two warp groups) overlaps the next main loop.
 struct TileChoice {
     int bn, pair;
 };
@@ -487,15 +490,19 @@ static TileChoice pick_tile(int N, long long tiles_m, long long batch, int k_blo
     for (int pair = 0; pair <= 1; pair++) {
         for (int bn = step; bn <= (pair ? 128 : 256); bn += step) {
             if (bn > nmax && bn != step) break;
+            if (pair && tiles_m < 2) continue;
             const long long tiles_n = (N + bn - 1) / bn;
             const long long units_m = pair ? (tiles_m + 1) / 2 : tiles_m;
-            if (pair && tiles_m < 2) continue;
             const long long units = units_m * tiles_n * batch;
             const long long waves = (units + num_sms - 1) / num_sms;
-            const double instr = pair ? std::max(bn / 2.0, 65.0) : std::max(bn / 2.0, 130.0);
-            const double mainloop = (double)k_blocks * 4.0 * instr * (pair ? 2 : 1);
+            const double fetch = 64.0 + bn / 2.0;
+            const double instr = pair ? fetch : std::max(fetch, 140.0);
+            const int stage_bytes = (pair ? 2 : 1) * A_STAGE_BYTES + bn * KBYTES;
+            const int stages = std::min(MAX_STAGES, (227 * 1024 - 2048 - 2 * STG_BYTES) / stage_bytes);
+            const double t_kb = std::max(4.0 * instr * (pair ? 2 : 1), 2200.0 / stages);
+            const double mainloop = (double)k_blocks * t_kb;
             const double epi = (pair ? 2 : 1) * (bn / 32.0) * 350.0 / 2.0 + 600.0;
-            const double unit = std::max(mainloop, epi) + 900.0;
+            const double unit = std::max(mainloop, epi) + 1500.0;
             const double cost = (double)waves * unit;
             if (cost < best_cost * 0.999) {
                 best_cost = cost;
