@@ -234,9 +234,52 @@ row_mean_kernel(const float* x, float* y, long long rows, int n, long long rows_
     if (lane == 0) y[row] = __fdiv_rn(s, (float)n);
 }
 
+// Same reduction order, one THREAD per row: for channels-last tensors consecutive rows (channels) are adjacent in
+// memory, so a warp reads 32 consecutive floats per element index (coalesced) instead of one strided row per warp.
+__global__ void __launch_bounds__(128)
+row_mean_thread_kernel(const float* x, float* y, long long rows, int n, long long rows_inner, long long s_outer,
+                       long long s_inner, long long kstride) {
+    const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= rows) return;
+    const float* xr = x + (row / rows_inner) * s_outer + (row % rows_inner) * s_inner;
+    float acc[4][VL];
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+#pragma unroll
+        for (int l = 0; l < VL; l++) acc[u][l] = 0.0f;
+    int i = 0;
+    for (; i + 64 <= n; i += 64) {
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+#pragma unroll
+            for (int l = 0; l < VL; l++) acc[u][l] = __fadd_rn(acc[u][l], xr[(long long)(i + u * VL + l) * kstride]);
+    }
+#pragma unroll
+    for (int l = 0; l < VL; l++) acc[0][l] = __fadd_rn(__fadd_rn(__fadd_rn(acc[0][l], acc[1][l]), acc[2][l]), acc[3][l]);
+    for (; i + VL <= n; i += VL) {
+#pragma unroll
+        for (int l = 0; l < VL; l++) acc[0][l] = __fadd_rn(acc[0][l], xr[(long long)(i + l) * kstride]);
+    }
+#pragma unroll
+    for (int l = 0; l < VL; l++)
+        if (i + l < n) acc[0][l] = __fadd_rn(acc[0][l], xr[(long long)(i + l) * kstride]);
+    float s = 0.0f;
+#pragma unroll
+    for (int l = 0; l < VL; l++) s = __fadd_rn(s, acc[0][l]);
+    y[row] = __fdiv_rn(s, (float)n);
+}
+
 rten_status launch_row_mean(rten_ctx* ctx, const float* x, float* y, long long rows, int n, long long rows_inner,
                             long long s_outer, long long s_inner, long long kstride) {
     if (rows == 0) return RTEN_OK;
+    if (s_inner == 1 && kstride != 1) {
+        row_mean_thread_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, ctx->stream>>>(x, y, rows, n, rows_inner, s_outer,
+                                                                                        s_inner, kstride);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return fail_cuda(ctx, e, "row_mean launch");
+        count_launch(ctx);
+        return RTEN_OK;
+    }
     const int wpb = 8;
     row_mean_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, ctx->stream>>>(x, y, rows, n, rows_inner,
                                                                                        s_outer, s_inner, kstride);

@@ -25,6 +25,7 @@
 
 #include <algorithm>
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 
 #include "math.cuh"
@@ -57,6 +58,8 @@ struct KParams {
     long long* trace;  // debug: per-event clock64 timestamps of CTA 0 (4 rows x 2048), or null
     int pair;       // 1: each CTA iteration computes TWO 128-row tiles sharing one B tile (interleaved MMAs on two
                     //    accumulators hide the dependent-accumulate latency when bn <= 128)
+    int res_tma;    // 1: the residual tile is prefetched by TMA into the staging buffer (needs tma_store)
+    uint32_t res_tx_bytes;
     int tma_store;  // 1: epilogue stages 128x32 chunks in smem and writes them with TMA (output rows contiguous)
     EpilogueDesc epi;
 };
@@ -97,16 +100,20 @@ __device__ __forceinline__ TileCoord decode_tile(const KParams& p, int t, int su
 template <int KIND>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                 const __grid_constant__ CUtensorMap tma_d, const KParams p) {
+                 const __grid_constant__ CUtensorMap tma_d, const __grid_constant__ CUtensorMap tma_r,
+                 const KParams p) {
     extern __shared__ uint8_t smem_raw[];
     // 1024-B alignment required by the 128B swizzle atoms / UMMA descriptors (base_offset = 0).
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* stg_base = smem + (size_t)p.stages * p.stage_bytes;  // 2 x STG_BYTES, 1024-B aligned
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg_base + 2 * STG_BYTES);
+    // staging: 1 buffer per epilogue group, 2 per group when the residual is prefetched (1024-B aligned)
+    uint8_t* stg_base = smem + (size_t)p.stages * p.stage_bytes;
+    const int nbuf = p.res_tma ? 2 : 1;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg_base + 2 * nbuf * STG_BYTES);
     uint64_t* empty_bar = full_bar + MAX_STAGES;
     uint64_t* tmem_full = empty_bar + MAX_STAGES;
     uint64_t* tmem_empty = tmem_full + 2;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    uint64_t* res_bar = tmem_empty + 2;  // [group][buffer]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_bar + 4);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -115,6 +122,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         tma_prefetch_desc(&tma_a);
         tma_prefetch_desc(&tma_b);
         if (p.tma_store) tma_prefetch_desc(&tma_d);
+        if (p.res_tma) tma_prefetch_desc(&tma_r);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.stages; s++) {
@@ -125,6 +133,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             mbar_init(&tmem_full[s], 1);
             mbar_init(&tmem_empty[s], 8);  // one arrival per epilogue warp
         }
+        for (int s = 0; s < 4; s++) mbar_init(&res_bar[s], 1);
         fence_mbar_init();
     }
     if (warp == 2) {
@@ -229,12 +238,25 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         const int q = warp & 3;          // TMEM lane quadrant this warp may access
         const int grp = (warp - 4) >> 2;  // epilogue group: chunks grp, grp+2, ...
         const int r = q * 32 + lane;
-        uint8_t* stg = stg_base + grp * STG_BYTES;
+        uint8_t* stg0 = stg_base + grp * nbuf * STG_BYTES;
         const bool issuer = (q == 0 && lane == 0);
+        uint32_t ci = 0;            // chunks processed by this group so far (selects the staging buffer)
+        uint32_t rphase = 0;        // bit b = phase of res_bar[grp][b]
         int it = 0;
         for (int t = blockIdx.x; t < p.tiles_total; t += gridDim.x, it++) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
+            if (p.res_tma && issuer && grp * 32 < p.bn) {
+                // residual of this tile's first chunk: independent of the accumulator -> request it before waiting
+                const TileCoord tc0 = decode_tile(p, t, 0);
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                uint64_t* rb = &res_bar[grp * 2 + (ci & 1)];
+                mbar_expect_tx(rb, p.res_tx_bytes);
+                if (p.conv)
+                    tma_load_4d(stg0 + (ci & 1) * STG_BYTES, &tma_r, rb, tc0.n0 + grp * 32, tc0.ox0, tc0.oy0, tc0.b0);
+                else
+                    tma_load_4d(stg0 + (ci & 1) * STG_BYTES, &tma_r, rb, tc0.n0 + grp * 32, tc0.m0, tc0.z0, tc0.z1);
+            }
             mbar_wait(&tmem_full[acc], acc_phase);
             if (p.trace && blockIdx.x == 0 && warp == 4 && lane == 0 && it < 2048) p.trace[4096 + it] = clock64();
             tc_fence_after();
@@ -287,22 +309,52 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                 }
                 tmem_ld_wait();
                 const int nbase = tc.n0 + c0;
+                uint8_t* stg = stg0 + (p.res_tma ? (ci & 1) : 0) * STG_BYTES;
+                uint8_t* rowp = stg + r * 128;
+                const int sw = r & 7;
+                if (p.res_tma) {
+                    // request the next chunk's residual of this tile (other buffer) once the store that last used that
+                    // buffer has been read, then wait for this chunk's residual to land
+                    if (issuer) {
+                        int nsub = sub, nc0 = c0 + 64;
+                        if (nc0 >= p.bn) {
+                            nsub = sub + 1;
+                            nc0 = grp * 32;
+                        }
+                        if (nsub <= p.pair && nc0 < p.bn) {
+                            const TileCoord tn = decode_tile(p, t, nsub);
+                            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                            uint64_t* rb = &res_bar[grp * 2 + ((ci + 1) & 1)];
+                            mbar_expect_tx(rb, p.res_tx_bytes);
+                            uint8_t* dst = stg0 + ((ci + 1) & 1) * STG_BYTES;
+                            if (p.conv)
+                                tma_load_4d(dst, &tma_r, rb, tn.n0 + nc0, tn.ox0, tn.oy0, tn.b0);
+                            else
+                                tma_load_4d(dst, &tma_r, rb, tn.n0 + nc0, tn.m0, tn.z0, tn.z1);
+                        }
+                    }
+                    mbar_wait(&res_bar[grp * 2 + (ci & 1)], (rphase >> (ci & 1)) & 1);
+                    rphase ^= 1u << (ci & 1);
+                }
                 // ---- fast path (registers, fully unrolled): f32, act in {none, relu}, residual / bias absent or
                 //      128-bit loadable.  Everything else (gelu, strided residual, N tails, the integer zero-point
                 //      math) runs as a ROLLED loop over the staged row: keeps the unrolled code small enough for
                 //      the instruction cache.
                 const bool full = nbase + 32 <= p.N;
                 bool fast = (KIND == 0) ? (e.act <= 1 && full) : !(e.za || e.zb || e.scale);  // raw i32: nothing to do
-                if (fast && e.r)
+                if (fast && e.r && !p.res_tma)
                     fast = e.r_col == 1 && ((reinterpret_cast<uintptr_t>(e.r + r_off + nbase) & 15) == 0);
                 if (fast && e.bias_kind == 1) fast = (reinterpret_cast<uintptr_t>(e.bias + nbase) & 15) == 0;
-                fast = __all_sync(0xffffffffu, fast || !row_ok);
+                fast = __all_sync(0xffffffffu, fast || !row_ok) || p.res_tma;  // (res_tma launches are fast-path only)
                 if (KIND == 0 && fast && row_ok) {
                     const float relu_floor = e.act == 1 ? 0.0f : -__int_as_float(0x7f800000);
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
                         float4 rr = make_float4(0.f, 0.f, 0.f, 0.f), bb = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (e.r) rr = *reinterpret_cast<const float4*>(e.r + r_off + nbase + j);
+                        if (p.res_tma)
+                            rr = *reinterpret_cast<const float4*>(rowp + (((j >> 2) ^ sw) << 4));
+                        else if (e.r)
+                            rr = *reinterpret_cast<const float4*>(e.r + r_off + nbase + j);
                         if (e.bias_kind == 1) bb = __ldg(reinterpret_cast<const float4*>(e.bias + nbase + j));
                         const float r4[4] = {rr.x, rr.y, rr.z, rr.w}, b4[4] = {bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
@@ -315,13 +367,12 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                     }
                 }
                 // ---- stage the row chunk in shared memory (128 B per row, 16-byte chunks XOR-swizzled by r & 7)
-                if (p.tma_store) {
+                if (p.tma_store && !p.res_tma) {
                     // the previous TMA store of this group must have finished READING the staging buffer
+                    // (with res_tma the residual mbarrier already orders buffer reuse)
                     if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                     asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
                 }
-                uint8_t* rowp = stg + r * 128;
-                const int sw = r & 7;
 #pragma unroll
                 for (int j = 0; j < 8; j++)
                     *reinterpret_cast<uint4*>(rowp + ((j ^ sw) << 4)) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
@@ -361,6 +412,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                             tma_store_4d(&tma_d, stg, nbase, tc.m0, tc.z0, tc.z1);
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
+                    ci++;
                 } else if (row_ok) {
                     // direct stores from the staged row (any output strides); consecutive lanes = consecutive rows
                     uint32_t* dptr = reinterpret_cast<uint32_t*>(e.d) + d_off;
@@ -483,7 +535,7 @@ static void pick_conv_tile(const ConvGeom& g, int& tw, int& th, int& tb) {
 struct TileChoice {
     int bn, pair;
 };
-static TileChoice pick_tile(int N, long long tiles_m, long long batch, int k_blocks, int num_sms, int step) {
+static TileChoice pick_tile(int N, long long tiles_m, long long batch, int k_blocks, int num_sms, int step, int n_stg) {
     TileChoice best{step, 0};
     double best_cost = 1e300;
     const int nmax = (N + step - 1) / step * step;
@@ -498,7 +550,8 @@ static TileChoice pick_tile(int N, long long tiles_m, long long batch, int k_blo
             const double fetch = 64.0 + bn / 2.0;
             const double instr = pair ? fetch : std::max(fetch, 140.0);
             const int stage_bytes = (pair ? 2 : 1) * A_STAGE_BYTES + bn * KBYTES;
-            const int stages = std::min(MAX_STAGES, (227 * 1024 - 2048 - 2 * STG_BYTES) / stage_bytes);
+            const int stages = std::min(MAX_STAGES, (227 * 1024 - 2048 - n_stg * STG_BYTES) / stage_bytes);
+            if (stages < 2) continue;
             const double t_kb = std::max(4.0 * instr * (pair ? 2 : 1), 2200.0 / stages);
             const double mainloop = (double)k_blocks * t_kb;
             const double epi = (pair ? 2 : 1) * (bn / 32.0) * 350.0 / 2.0 + 600.0;
@@ -576,7 +629,7 @@ rten_status launch_umma_gemm(rten_ctx* ctx, const GemmLaunch& L) {
         p.b_bcast1 = (L.b.dims[3] == 1 && L.z1 > 1) ? 1 : 0;
     }
     // ---- output path: TMA store needs contiguous 4-byte rows at 16-byte aligned pitches
-    OperandDesc od;
+    OperandDesc od, ord;
     uint32_t dbox[4] = {32, 1, 1, 1}, des[4] = {1, 1, 1, 1};
     {
         const EpilogueDesc& e = L.epi;
@@ -604,10 +657,32 @@ rten_status launch_umma_gemm(rten_ctx* ctx, const GemmLaunch& L) {
         }
         p.tma_store = (e.s_col == 1 && L.N >= 4 && tma_compatible(od, 4, 4)) ? 1 : 0;
         if (getenv("RTEN_B200_NO_TMA_STORE")) p.tma_store = 0;
+        // residual prefetched by TMA: same geometry as the output, own strides (fast-path epilogue only)
+        ord = od;
+        ord.base = e.r;
+        if (L.conv) {
+            ord.strides[1] = e.r_z1;
+            ord.strides[2] = e.r_row;
+            ord.strides[3] = e.r_z0;
+        } else {
+            ord.strides[1] = e.r_row;
+            ord.strides[2] = e.r_z0;
+            ord.strides[3] = e.r_z1;
+        }
+        p.res_tma = (p.tma_store && L.kind == 0 && e.r && e.r_col == 1 && e.act <= 1 && (L.N % 32) == 0 &&
+                     (e.bias_kind != 1 || (reinterpret_cast<uintptr_t>(e.bias) & 15) == 0) && tma_compatible(ord, 4, 4))
+                        ? 1
+                        : 0;
+        // a broadcast residual (Gemm's C) has zero strides on real dims: keep the register path for it
+        for (int i = 1; i < 4; i++)
+            if (ord.dims[i] > 1 && ord.strides[i] == 0) p.res_tma = 0;
+        if (getenv("RTEN_B200_NO_RES_TMA")) p.res_tma = 0;
+        p.res_tx_bytes = a_rows * KBYTES;
     }
+    const int n_stg = p.res_tma ? 4 : 2;
     {
         const long long batch = L.conv ? 1 : (long long)L.z0 * L.z1;
-        TileChoice tcz = pick_tile(L.N, p.tiles_m, batch, p.k_blocks, ctx->num_sms, p.tma_store ? 32 : 16);
+        TileChoice tcz = pick_tile(L.N, p.tiles_m, batch, p.k_blocks, ctx->num_sms, p.tma_store ? 32 : 16, n_stg);
         if (const char* f = getenv("RTEN_B200_FORCE_BN")) tcz.bn = atoi(f);
         if (const char* f = getenv("RTEN_B200_FORCE_PAIR")) tcz.pair = atoi(f) && tcz.bn <= 128 && p.tiles_m >= 2;
         p.bn = tcz.bn;
@@ -624,7 +699,7 @@ rten_status launch_umma_gemm(rten_ctx* ctx, const GemmLaunch& L) {
     bbox[3] = 1;
     p.stage_bytes = (p.pair ? 2 : 1) * A_STAGE_BYTES + p.bn * KBYTES;
     p.tx_bytes = (p.pair ? 2 : 1) * a_rows * KBYTES + p.bn * KBYTES;
-    const int smem_budget = 227 * 1024 - 2048 - 2 * STG_BYTES;
+    const int smem_budget = 227 * 1024 - 2048 - n_stg * STG_BYTES;
     p.stages = std::min(MAX_STAGES, smem_budget / (int)p.stage_bytes);
     if (p.stages < 2) return RTEN_ERR_UNSUPPORTED_VALUE;
     if (L.kind == 0)
@@ -635,23 +710,31 @@ rten_status launch_umma_gemm(rten_ctx* ctx, const GemmLaunch& L) {
     CUtensorMap map_a, map_b;
     if (!encode_map(ctx, &map_a, L.a, esize, L.kind == 0, abox, aes)) return RTEN_ERR_UNSUPPORTED_VALUE;
     if (!encode_map(ctx, &map_b, L.b, esize, L.kind == 0, bbox, bes)) return RTEN_ERR_UNSUPPORTED_VALUE;
-    CUtensorMap map_d = map_a;
+    CUtensorMap map_d = map_a, map_r = map_a;
     if (p.tma_store && !encode_map(ctx, &map_d, od, 4, true, dbox, des)) {
         p.tma_store = 0;  // direct stores still work for any bn that is a multiple of 16
+        p.res_tma = 0;
         map_d = map_a;
     }
+    if (p.res_tma && !encode_map(ctx, &map_r, ord, 4, true, dbox, des)) {
+        p.res_tma = 0;
+        map_r = map_a;
+    }
 
-    const size_t smem_bytes = (size_t)p.stages * p.stage_bytes + 2 * STG_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    if (getenv("RTEN_B200_VERBOSE"))
+        fprintf(stderr, "[umma_gemm] kind=%d conv=%d M=%d N=%d K=%d kb=%d tiles_m=%d bn=%d pair=%d units=%d stages=%d tma_store=%d res_tma=%d box=%dx%dx%d\n",
+                L.kind, L.conv, L.M, L.N, L.K, p.k_blocks, p.tiles_m, p.bn, p.pair, p.tiles_total, p.stages, p.tma_store, p.res_tma, p.tw, p.th, p.tb);
+    const size_t smem_bytes = (size_t)p.stages * p.stage_bytes + n_stg * STG_BYTES + 1024 /*align*/ + 256 /*barriers*/;
     const int grid = std::min(p.tiles_total, ctx->num_sms);
     cudaError_t e;
     if (L.kind == 0) {
         e = cudaFuncSetAttribute(umma_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return fail_cuda(ctx, e, "cudaFuncSetAttribute(umma_gemm<tf32>)");
-        umma_gemm_kernel<0><<<grid, NUM_THREADS, smem_bytes, ctx->stream>>>(map_a, map_b, map_d, p);
+        umma_gemm_kernel<0><<<grid, NUM_THREADS, smem_bytes, ctx->stream>>>(map_a, map_b, map_d, map_r, p);
     } else {
         e = cudaFuncSetAttribute(umma_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return fail_cuda(ctx, e, "cudaFuncSetAttribute(umma_gemm<i8>)");
-        umma_gemm_kernel<1><<<grid, NUM_THREADS, smem_bytes, ctx->stream>>>(map_a, map_b, map_d, p);
+        umma_gemm_kernel<1><<<grid, NUM_THREADS, smem_bytes, ctx->stream>>>(map_a, map_b, map_d, map_r, p);
     }
     e = cudaGetLastError();
     if (e != cudaSuccess) return fail_cuda(ctx, e, "umma_gemm launch");
