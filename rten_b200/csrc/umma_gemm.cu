@@ -58,6 +58,8 @@ struct KParams {
     long long* trace;  // debug: per-event clock64 timestamps of CTA 0 (4 rows x 2048), or null
     int pair;       // 1: each CTA iteration computes TWO 128-row tiles sharing one B tile (interleaved MMAs on two
                     //    accumulators hide the dependent-accumulate latency when bn <= 128)
+    int ksplit;     // 1: (single-tile mode, bn <= 128) even / odd K blocks accumulate into two TMEM accumulators that the
+                    //    epilogue adds: consecutive MMAs never depend on each other (no dependent-accumulate stall)
     int res_tma;    // 1: the residual tile is prefetched by TMA into the staging buffer (needs tma_store)
     uint32_t res_tx_bytes;
     int tma_store;  // 1: epilogue stages 128x32 chunks in smem and writes them with TMA (output rows contiguous)
@@ -144,6 +146,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps
+    // the tail of the previous kernel in the stream; global memory is only touched after this point.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -211,11 +217,16 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 #pragma unroll
                     for (int k = 0; k < 4; k++) {
                         // advance 32 B along K inside the swizzle atom: +2 in the (addr >> 4) field
-                        const uint32_t accum = (kb | k) != 0 ? 1u : 0u;
+                        uint32_t accum = (kb | k) != 0 ? 1u : 0u;
+                        uint32_t d0 = d_tmem;
+                        if (p.ksplit) {  // alternate accumulators per instruction (k even -> acc 0, k odd -> acc 1)
+                            d0 = d_tmem + (k & 1) * p.bn;
+                            accum = (kb != 0 || k >= 2) ? 1u : 0u;
+                        }
                         if (KIND == 0)
-                            umma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, accum);
+                            umma_tf32(d0, adesc + 2 * k, bdesc + 2 * k, p.idesc, accum);
                         else
-                            umma_i8(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, accum);
+                            umma_i8(d0, adesc + 2 * k, bdesc + 2 * k, p.idesc, accum);
                         if (p.pair) {  // second tile of the pair: independent accumulator, same B operand
                             if (KIND == 0)
                                 umma_tf32(d_tmem + p.bn, adesc1 + 2 * k, bdesc + 2 * k, p.idesc, accum);
@@ -308,6 +319,24 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                     for (int j = 16; j < 32; j++) v[j] = 0;
                 }
                 tmem_ld_wait();
+                if (p.ksplit) {
+                    // add the second partial accumulator (columns + bn), 16 columns at a time to bound registers
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        if (h * 16 < ncols) {
+                            uint32_t w[16];
+                            tmem_ld_32x16(t_row + p.bn + c0 + h * 16, w);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int j = 0; j < 16; j++) {
+                                if (KIND == 0)
+                                    v[h * 16 + j] = __float_as_uint(__fadd_rn(__uint_as_float(v[h * 16 + j]), __uint_as_float(w[j])));
+                                else
+                                    v[h * 16 + j] += w[j];
+                            }
+                        }
+                    }
+                }
                 const int nbase = tc.n0 + c0;
                 uint8_t* stg = stg0 + (p.res_tma ? (ci & 1) : 0) * STG_BYTES;
                 uint8_t* rowp = stg + r * 128;
@@ -548,7 +577,8 @@ static TileChoice pick_tile(int N, long long tiles_m, long long batch, int k_blo
             const long long units = units_m * tiles_n * batch;
             const long long waves = (units + num_sms - 1) / num_sms;
             const double fetch = 64.0 + bn / 2.0;
-            const double instr = pair ? fetch : std::max(fetch, 140.0);
+            const bool ksplit = !pair && bn <= 128;  // alternating accumulators remove the dependent-accumulate floor
+            const double instr = (pair || ksplit) ? fetch : std::max(fetch, 140.0);
             const int stage_bytes = (pair ? 2 : 1) * A_STAGE_BYTES + bn * KBYTES;
             const int stages = std::min(MAX_STAGES, (227 * 1024 - 2048 - n_stg * STG_BYTES) / stage_bytes);
             if (stages < 2) continue;
@@ -687,6 +717,7 @@ rten_status launch_umma_gemm(rten_ctx* ctx, const GemmLaunch& L) {
         if (const char* f = getenv("RTEN_B200_FORCE_PAIR")) tcz.pair = atoi(f) && tcz.bn <= 128 && p.tiles_m >= 2;
         p.bn = tcz.bn;
         p.pair = tcz.pair;
+        p.ksplit = (!p.pair && p.bn <= 128 && !getenv("RTEN_B200_NO_KSPLIT")) ? 1 : 0;
         tiles_m_total = (p.pair ? (p.tiles_m + 1) / 2 : p.tiles_m) * batch;
     }
     p.tiles_n = (L.N + p.bn - 1) / p.bn;
@@ -722,20 +753,32 @@ rten_status launch_umma_gemm(rten_ctx* ctx, const GemmLaunch& L) {
     }
 
     if (getenv("RTEN_B200_VERBOSE"))
-        fprintf(stderr, "[umma_gemm] kind=%d conv=%d M=%d N=%d K=%d kb=%d tiles_m=%d bn=%d pair=%d units=%d stages=%d tma_store=%d res_tma=%d box=%dx%dx%d\n",
-                L.kind, L.conv, L.M, L.N, L.K, p.k_blocks, p.tiles_m, p.bn, p.pair, p.tiles_total, p.stages, p.tma_store, p.res_tma, p.tw, p.th, p.tb);
+        fprintf(stderr, "[umma_gemm] kind=%d conv=%d M=%d N=%d K=%d kb=%d tiles_m=%d bn=%d pair=%d ksplit=%d units=%d stages=%d tma_store=%d res_tma=%d box=%dx%dx%d\n",
+                L.kind, L.conv, L.M, L.N, L.K, p.k_blocks, p.tiles_m, p.bn, p.pair, p.ksplit, p.tiles_total, p.stages, p.tma_store, p.res_tma, p.tw, p.th, p.tb);
     const size_t smem_bytes = (size_t)p.stages * p.stage_bytes + n_stg * STG_BYTES + 1024 /*align*/ + 256 /*barriers*/;
     const int grid = std::min(p.tiles_total, ctx->num_sms);
     cudaError_t e;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = getenv("RTEN_B200_NO_PDL") ? 0 : 1;
     if (L.kind == 0) {
         e = cudaFuncSetAttribute(umma_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return fail_cuda(ctx, e, "cudaFuncSetAttribute(umma_gemm<tf32>)");
-        umma_gemm_kernel<0><<<grid, NUM_THREADS, smem_bytes, ctx->stream>>>(map_a, map_b, map_d, map_r, p);
+        e = cudaLaunchKernelEx(&cfg, umma_gemm_kernel<0>, map_a, map_b, map_d, map_r, p);
     } else {
         e = cudaFuncSetAttribute(umma_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return fail_cuda(ctx, e, "cudaFuncSetAttribute(umma_gemm<i8>)");
-        umma_gemm_kernel<1><<<grid, NUM_THREADS, smem_bytes, ctx->stream>>>(map_a, map_b, map_d, map_r, p);
+        e = cudaLaunchKernelEx(&cfg, umma_gemm_kernel<1>, map_a, map_b, map_d, map_r, p);
     }
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "umma_gemm launch");
     e = cudaGetLastError();
     if (e != cudaSuccess) return fail_cuda(ctx, e, "umma_gemm launch");
     count_launch(ctx);
