@@ -151,96 +151,108 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
+    // Control warps run their loops WARP-UNIFORMLY (all 32 lanes wait on the barriers, one elected lane issues the
+    // TMA / MMA instructions): addresses and descriptors then live in uniform registers instead of being moved
+    // there (R2UR) for every instruction, which is what bounds a single issuing thread.
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            int tr_p = 0;
-            for (int t = blockIdx.x; t < p.tiles_total; t += gridDim.x) {
-                const TileCoord tc = decode_tile(p, t, 0);
-                const TileCoord tc1 = decode_tile(p, t, 1);
-                for (int kb = 0; kb < p.k_blocks; kb++) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
+        int stage = 0;
+        uint32_t phase = 0;
+        int tr_p = 0;
+        const uint32_t smem0 = smem_u32(smem);
+        const uint32_t full0 = smem_u32(full_bar);
+        const uint32_t a_bytes = (p.pair ? 2 : 1) * A_STAGE_BYTES;
+        for (int t = blockIdx.x; t < p.tiles_total; t += gridDim.x) {
+            const TileCoord tc = decode_tile(p, t, 0);
+            const TileCoord tc1 = decode_tile(p, t, 1);
+            int tap = 0, cb = 0, ky = 0, kx = 0;  // conv: K block -> (filter tap, channel block), kept incrementally
+            for (int kb = 0; kb < p.k_blocks; kb++) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                if (elect_one()) {
                     if (p.trace && blockIdx.x == 0 && tr_p < 2048) p.trace[tr_p++] = clock64();
-                    uint8_t* sa = smem + (size_t)stage * p.stage_bytes;
-                    uint8_t* sb = sa + (p.pair ? 2 : 1) * A_STAGE_BYTES;
-                    mbar_expect_tx(&full_bar[stage], p.tx_bytes);
+                    const uint32_t sa = smem0 + stage * p.stage_bytes;
+                    const uint32_t sb = sa + a_bytes;
+                    const uint32_t fb = full0 + stage * 8;
+                    mbar_expect_tx_u32(fb, p.tx_bytes);
                     if (p.conv) {
-                        const int tap = kb / p.c_blocks;
-                        const int cb = kb - tap * p.c_blocks;
-                        const int ky = tap / p.kw;
-                        const int kx = tap - ky * p.kw;
-                        tma_load_4d(sa, &tma_a, &full_bar[stage], cb * p.kelems, tc.ox0 * p.sx - p.pl + kx * p.dx,
-                                    tc.oy0 * p.sy - p.pt + ky * p.dy, tc.b0);
+                        const int c0 = cb * p.kelems;
+                        tma_load_4d_u32(sa, &tma_a, fb, c0, tc.ox0 * p.sx - p.pl + kx * p.dx, tc.oy0 * p.sy - p.pt + ky * p.dy,
+                                        tc.b0);
                         if (p.pair)
-                            tma_load_4d(sa + A_STAGE_BYTES, &tma_a, &full_bar[stage], cb * p.kelems,
-                                        tc1.ox0 * p.sx - p.pl + kx * p.dx, tc1.oy0 * p.sy - p.pt + ky * p.dy, tc1.b0);
-                        tma_load_4d(sb, &tma_b, &full_bar[stage], cb * p.kelems, tc.n0, tap, 0);
+                            tma_load_4d_u32(sa + A_STAGE_BYTES, &tma_a, fb, c0, tc1.ox0 * p.sx - p.pl + kx * p.dx,
+                                            tc1.oy0 * p.sy - p.pt + ky * p.dy, tc1.b0);
+                        tma_load_4d_u32(sb, &tma_b, fb, c0, tc.n0, tap, 0);
                     } else {
-                        tma_load_4d(sa, &tma_a, &full_bar[stage], kb * p.kelems, tc.m0, p.a_bcast0 ? 0 : tc.z0,
-                                    p.a_bcast1 ? 0 : tc.z1);
-                        if (p.pair)
-                            tma_load_4d(sa + A_STAGE_BYTES, &tma_a, &full_bar[stage], kb * p.kelems, tc1.m0,
-                                        p.a_bcast0 ? 0 : tc.z0, p.a_bcast1 ? 0 : tc.z1);
-                        tma_load_4d(sb, &tma_b, &full_bar[stage], kb * p.kelems, tc.n0, p.b_bcast0 ? 0 : tc.z0,
-                                    p.b_bcast1 ? 0 : tc.z1);
+                        const int k0 = kb * p.kelems;
+                        const int az0 = p.a_bcast0 ? 0 : tc.z0, az1 = p.a_bcast1 ? 0 : tc.z1;
+                        tma_load_4d_u32(sa, &tma_a, fb, k0, tc.m0, az0, az1);
+                        if (p.pair) tma_load_4d_u32(sa + A_STAGE_BYTES, &tma_a, fb, k0, tc1.m0, az0, az1);
+                        tma_load_4d_u32(sb, &tma_b, fb, k0, tc.n0, p.b_bcast0 ? 0 : tc.z0, p.b_bcast1 ? 0 : tc.z1);
                     }
-                    if (++stage == p.stages) {
-                        stage = 0;
-                        phase ^= 1;
+                }
+                __syncwarp();
+                if (++cb == p.c_blocks) {
+                    cb = 0;
+                    tap++;
+                    if (++kx == p.kw) {
+                        kx = 0;
+                        ky++;
                     }
+                }
+                if (++stage == p.stages) {
+                    stage = 0;
+                    phase ^= 1;
                 }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            int it = 0;
-            int tr_m = 0;
-            for (int t = blockIdx.x; t < p.tiles_total; t += gridDim.x, it++) {
-                const int acc = it & 1;
-                const uint32_t acc_phase = (it >> 1) & 1;
-                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        int tr_m = 0;
+        const uint32_t smem0 = smem_u32(smem);
+        const uint32_t empty0 = smem_u32(empty_bar);
+        const uint32_t b_off = (p.pair ? 2 : 1) * A_STAGE_BYTES;
+        const uint32_t d1_off = (p.pair || p.ksplit) ? p.bn : 0;
+        for (int t = blockIdx.x; t < p.tiles_total; t += gridDim.x, it++) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
+            for (int kb = 0; kb < p.k_blocks; kb++) {
+                mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
-                for (int kb = 0; kb < p.k_blocks; kb++) {
-                    mbar_wait(&full_bar[stage], phase);
+                if (elect_one()) {
                     if (p.trace && blockIdx.x == 0 && tr_m < 2048) p.trace[2048 + tr_m++] = clock64();
-                    tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + (size_t)stage * p.stage_bytes);
+                    const uint32_t sa = smem0 + stage * p.stage_bytes;
                     const uint64_t adesc = make_kmajor_sw128_desc(sa);
-                    const uint64_t adesc1 = make_kmajor_sw128_desc(sa + A_STAGE_BYTES);
-                    const uint64_t bdesc = make_kmajor_sw128_desc(sa + (p.pair ? 2 : 1) * A_STAGE_BYTES);
+                    const uint64_t bdesc = make_kmajor_sw128_desc(sa + b_off);
+                    const uint32_t first = kb == 0 ? 0u : 1u;
+                    if (p.pair) {
+                        const uint64_t adesc1 = make_kmajor_sw128_desc(sa + A_STAGE_BYTES);
 #pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        // advance 32 B along K inside the swizzle atom: +2 in the (addr >> 4) field
-                        uint32_t accum = (kb | k) != 0 ? 1u : 0u;
-                        uint32_t d0 = d_tmem;
-                        if (p.ksplit) {  // alternate accumulators per instruction (k even -> acc 0, k odd -> acc 1)
-                            d0 = d_tmem + (k & 1) * p.bn;
-                            accum = (kb != 0 || k >= 2) ? 1u : 0u;
+                        for (int k = 0; k < 4; k++) {  // +2 in the (addr >> 4) field = 32 B along K inside the swizzle atom
+                            umma<KIND>(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, k == 0 ? first : 1u);
+                            umma<KIND>(d_tmem + d1_off, adesc1 + 2 * k, bdesc + 2 * k, p.idesc, k == 0 ? first : 1u);
                         }
-                        if (KIND == 0)
-                            umma_tf32(d0, adesc + 2 * k, bdesc + 2 * k, p.idesc, accum);
-                        else
-                            umma_i8(d0, adesc + 2 * k, bdesc + 2 * k, p.idesc, accum);
-                        if (p.pair) {  // second tile of the pair: independent accumulator, same B operand
-                            if (KIND == 0)
-                                umma_tf32(d_tmem + p.bn, adesc1 + 2 * k, bdesc + 2 * k, p.idesc, accum);
-                            else
-                                umma_i8(d_tmem + p.bn, adesc1 + 2 * k, bdesc + 2 * k, p.idesc, accum);
-                        }
+                    } else if (p.ksplit) {
+#pragma unroll
+                        for (int k = 0; k < 4; k++)  // k even -> accumulator 0, k odd -> accumulator 1
+                            umma<KIND>(d_tmem + (k & 1) * d1_off, adesc + 2 * k, bdesc + 2 * k, p.idesc, k < 2 ? first : 1u);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; k++) umma<KIND>(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, k == 0 ? first : 1u);
                     }
-                    umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
-                    if (++stage == p.stages) {
-                        stage = 0;
-                        phase ^= 1;
-                    }
+                    umma_commit_u32(empty0 + stage * 8);  // smem slot reusable once these MMAs retire
+                    if (kb == p.k_blocks - 1) umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
                 }
-                umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+                __syncwarp();
+                if (++stage == p.stages) {
+                    stage = 0;
+                    phase ^= 1;
+                }
             }
         }
     } else if (warp >= 4) {

@@ -26,7 +26,13 @@ def trace(fn, name):
     buf = (C.c_int64 * 8192)()
     ctx.check(ctx.lib.rten_b200_debug_trace(ctx.handle, 0, buf))
     t = np.frombuffer(buf, dtype=np.int64).reshape(4, 2048)
+    issue_cost = t[3][680:1360]
+    commit_cost = t[3][1364:2044]
+    t[3][680:] = 0
     prod, mma, e0, e1 = (r[r > 0] for r in t)
+    ic, cc = issue_cost[issue_cost > 0], commit_cost[commit_cost > 0]
+    if len(ic):
+        print(f"   MMA thread: wait-done->4(8) MMAs issued median {np.median(ic):.0f} clk; commit issue median {np.median(cc):.0f} clk")
     t0 = min(prod.min(), mma.min())
     print(f"== {name}: {len(prod)} k-blocks, {len(e0)} tiles on CTA 0; total {(max(e1.max(), mma.max()) - t0)} clk")
     if len(prod) > 1:
