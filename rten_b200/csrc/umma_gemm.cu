@@ -24,6 +24,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -58,6 +59,9 @@ struct KParams {
     long long* trace;  // debug: per-event clock64 timestamps of CTA 0 (4 rows x 2048), or null
     int pair;       // 1: each CTA iteration computes TWO 128-row tiles sharing one B tile (interleaved MMAs on two
                     //    accumulators hide the dependent-accumulate latency when bn <= 128)
+    int katoms;     // consecutive 128-byte K blocks loaded / multiplied per pipeline stage (1 or 2): amortises the fixed
+                    // per-stage barrier round trip of the issuing threads when tiles are small
+    uint32_t atom_bytes;
     int ksplit;     // 1: (single-tile mode, bn <= 128) even / odd K blocks accumulate into two TMEM accumulators that the
                     //    epilogue adds: consecutive MMAs never depend on each other (no dependent-accumulate stall)
     int res_tma;    // 1: the residual tile is prefetched by TMA into the staging buffer (needs tma_store)
@@ -166,39 +170,45 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             const TileCoord tc = decode_tile(p, t, 0);
             const TileCoord tc1 = decode_tile(p, t, 1);
             int tap = 0, cb = 0, ky = 0, kx = 0;  // conv: K block -> (filter tap, channel block), kept incrementally
-            for (int kb = 0; kb < p.k_blocks; kb++) {
+            for (int kb = 0; kb < p.k_blocks; kb += p.katoms) {
+                const int natoms = min(p.katoms, p.k_blocks - kb);
                 mbar_wait(&empty_bar[stage], phase ^ 1);
-                if (elect_one()) {
+                const bool leader = elect_one();
+                const uint32_t fb = full0 + stage * 8;
+                if (leader) {
                     if (p.trace && blockIdx.x == 0 && tr_p < 2048) p.trace[tr_p++] = clock64();
-                    const uint32_t sa = smem0 + stage * p.stage_bytes;
-                    const uint32_t sb = sa + a_bytes;
-                    const uint32_t fb = full0 + stage * 8;
-                    mbar_expect_tx_u32(fb, p.tx_bytes);
-                    if (p.conv) {
-                        const int c0 = cb * p.kelems;
-                        tma_load_4d_u32(sa, &tma_a, fb, c0, tc.ox0 * p.sx - p.pl + kx * p.dx, tc.oy0 * p.sy - p.pt + ky * p.dy,
-                                        tc.b0);
-                        if (p.pair)
-                            tma_load_4d_u32(sa + A_STAGE_BYTES, &tma_a, fb, c0, tc1.ox0 * p.sx - p.pl + kx * p.dx,
-                                            tc1.oy0 * p.sy - p.pt + ky * p.dy, tc1.b0);
-                        tma_load_4d_u32(sb, &tma_b, fb, c0, tc.n0, tap, 0);
-                    } else {
-                        const int k0 = kb * p.kelems;
-                        const int az0 = p.a_bcast0 ? 0 : tc.z0, az1 = p.a_bcast1 ? 0 : tc.z1;
-                        tma_load_4d_u32(sa, &tma_a, fb, k0, tc.m0, az0, az1);
-                        if (p.pair) tma_load_4d_u32(sa + A_STAGE_BYTES, &tma_a, fb, k0, tc1.m0, az0, az1);
-                        tma_load_4d_u32(sb, &tma_b, fb, k0, tc.n0, p.b_bcast0 ? 0 : tc.z0, p.b_bcast1 ? 0 : tc.z1);
+                    mbar_expect_tx_u32(fb, p.tx_bytes * natoms);
+                }
+                for (int a = 0; a < natoms; a++) {
+                    if (leader) {
+                        const uint32_t sa = smem0 + stage * p.stage_bytes + a * p.atom_bytes;
+                        const uint32_t sb = sa + a_bytes;
+                        if (p.conv) {
+                            const int c0 = cb * p.kelems;
+                            tma_load_4d_u32(sa, &tma_a, fb, c0, tc.ox0 * p.sx - p.pl + kx * p.dx,
+                                            tc.oy0 * p.sy - p.pt + ky * p.dy, tc.b0);
+                            if (p.pair)
+                                tma_load_4d_u32(sa + A_STAGE_BYTES, &tma_a, fb, c0, tc1.ox0 * p.sx - p.pl + kx * p.dx,
+                                                tc1.oy0 * p.sy - p.pt + ky * p.dy, tc1.b0);
+                            tma_load_4d_u32(sb, &tma_b, fb, c0, tc.n0, tap, 0);
+                        } else {
+                            const int k0 = (kb + a) * p.kelems;
+                            const int az0 = p.a_bcast0 ? 0 : tc.z0, az1 = p.a_bcast1 ? 0 : tc.z1;
+                            tma_load_4d_u32(sa, &tma_a, fb, k0, tc.m0, az0, az1);
+                            if (p.pair) tma_load_4d_u32(sa + A_STAGE_BYTES, &tma_a, fb, k0, tc1.m0, az0, az1);
+                            tma_load_4d_u32(sb, &tma_b, fb, k0, tc.n0, p.b_bcast0 ? 0 : tc.z0, p.b_bcast1 ? 0 : tc.z1);
+                        }
+                    }
+                    if (++cb == p.c_blocks) {
+                        cb = 0;
+                        tap++;
+                        if (++kx == p.kw) {
+                            kx = 0;
+                            ky++;
+                        }
                     }
                 }
                 __syncwarp();
-                if (++cb == p.c_blocks) {
-                    cb = 0;
-                    tap++;
-                    if (++kx == p.kw) {
-                        kx = 0;
-                        ky++;
-                    }
-                }
                 if (++stage == p.stages) {
                     stage = 0;
                     phase ^= 1;
@@ -221,32 +231,36 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
-            for (int kb = 0; kb < p.k_blocks; kb++) {
+            for (int kb = 0; kb < p.k_blocks; kb += p.katoms) {
+                const int natoms = min(p.katoms, p.k_blocks - kb);
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
                 if (elect_one()) {
                     if (p.trace && blockIdx.x == 0 && tr_m < 2048) p.trace[2048 + tr_m++] = clock64();
-                    const uint32_t sa = smem0 + stage * p.stage_bytes;
-                    const uint64_t adesc = make_kmajor_sw128_desc(sa);
-                    const uint64_t bdesc = make_kmajor_sw128_desc(sa + b_off);
-                    const uint32_t first = kb == 0 ? 0u : 1u;
-                    if (p.pair) {
-                        const uint64_t adesc1 = make_kmajor_sw128_desc(sa + A_STAGE_BYTES);
+                    for (int a = 0; a < natoms; a++) {
+                        const uint32_t sa = smem0 + stage * p.stage_bytes + a * p.atom_bytes;
+                        const uint64_t adesc = make_kmajor_sw128_desc(sa);
+                        const uint64_t bdesc = make_kmajor_sw128_desc(sa + b_off);
+                        const uint32_t first = (kb + a) == 0 ? 0u : 1u;
+                        if (p.pair) {
+                            const uint64_t adesc1 = make_kmajor_sw128_desc(sa + A_STAGE_BYTES);
 #pragma unroll
-                        for (int k = 0; k < 4; k++) {  // +2 in the (addr >> 4) field = 32 B along K inside the swizzle atom
-                            umma<KIND>(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, k == 0 ? first : 1u);
-                            umma<KIND>(d_tmem + d1_off, adesc1 + 2 * k, bdesc + 2 * k, p.idesc, k == 0 ? first : 1u);
+                            for (int k = 0; k < 4; k++) {  // +2 in the (addr >> 4) field = 32 B along K in the swizzle atom
+                                umma<KIND>(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, k == 0 ? first : 1u);
+                                umma<KIND>(d_tmem + d1_off, adesc1 + 2 * k, bdesc + 2 * k, p.idesc, k == 0 ? first : 1u);
+                            }
+                        } else if (p.ksplit) {
+#pragma unroll
+                            for (int k = 0; k < 4; k++)  // k even -> accumulator 0, k odd -> accumulator 1
+                                umma<KIND>(d_tmem + (k & 1) * d1_off, adesc + 2 * k, bdesc + 2 * k, p.idesc, k < 2 ? first : 1u);
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 4; k++)
+                                umma<KIND>(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, k == 0 ? first : 1u);
                         }
-                    } else if (p.ksplit) {
-#pragma unroll
-                        for (int k = 0; k < 4; k++)  // k even -> accumulator 0, k odd -> accumulator 1
-                            umma<KIND>(d_tmem + (k & 1) * d1_off, adesc + 2 * k, bdesc + 2 * k, p.idesc, k < 2 ? first : 1u);
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < 4; k++) umma<KIND>(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, k == 0 ? first : 1u);
                     }
                     umma_commit_u32(empty0 + stage * 8);  // smem slot reusable once these MMAs retire
-                    if (kb == p.k_blocks - 1) umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+                    if (kb + natoms >= p.k_blocks) umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
                 }
                 __syncwarp();
                 if (++stage == p.stages) {
@@ -574,12 +588,21 @@ static void pick_conv_tile(const ConvGeom& g, int& tw, int& th, int& tb) {
 //   * a K block cannot complete faster than TMA latency / stages in flight (~2200 clk under load);
 //   * the epilogue (~350 clk per 32-column chunk, two warp groups) overlaps the next main loop.
 struct TileChoice {
-    int bn, pair;
+    int bn, pair, katoms;
 };
+static int smem_budget_for(int n_stg) { return 227 * 1024 - 2048 - n_stg * STG_BYTES; }
+
+// Measured with the in-kernel trace (profiles/r01_trace_*.txt), clocks:
+//   issuing one tcgen05.mma costs the elected thread ~42 clk; executing it is bound by operand fetch from shared
+//   memory at ~110 B/clk (A: 128 rows x 32 B, B: bn rows x 32 B); consecutive MMAs on ONE accumulator serialise at
+//   ~140 clk unless they alternate between two accumulators (pair / ksplit modes); every pipeline stage costs the
+//   issuing warp a fixed ~320 clk (barrier wait, fence, descriptors, commit) -> small tiles put TWO 128-byte K blocks
+//   in a stage; a stage cannot complete faster than TMA latency (~2200 clk under load) / stages in flight.
 static TileChoice pick_tile(int N, long long tiles_m, long long batch, int k_blocks, int num_sms, int step, int n_stg) {
-    TileChoice best{step, 0};
+    TileChoice best{step, 0, 1};
     double best_cost = 1e300;
     const int nmax = (N + step - 1) / step * step;
+    const int budget = smem_budget_for(n_stg);
     for (int pair = 0; pair <= 1; pair++) {
         for (int bn = step; bn <= (pair ? 128 : 256); bn += step) {
             if (bn > nmax && bn != step) break;
@@ -588,20 +611,23 @@ static TileChoice pick_tile(int N, long long tiles_m, long long batch, int k_blo
             const long long units_m = pair ? (tiles_m + 1) / 2 : tiles_m;
             const long long units = units_m * tiles_n * batch;
             const long long waves = (units + num_sms - 1) / num_sms;
-            const double fetch = 64.0 + bn / 2.0;
-            const bool ksplit = !pair && bn <= 128;  // alternating accumulators remove the dependent-accumulate floor
-            const double instr = (pair || ksplit) ? fetch : std::max(fetch, 140.0);
-            const int stage_bytes = (pair ? 2 : 1) * A_STAGE_BYTES + bn * KBYTES;
-            const int stages = std::min(MAX_STAGES, (227 * 1024 - 2048 - n_stg * STG_BYTES) / stage_bytes);
-            if (stages < 2) continue;
-            const double t_kb = std::max(4.0 * instr * (pair ? 2 : 1), 2200.0 / stages);
-            const double mainloop = (double)k_blocks * t_kb;
-            const double epi = (pair ? 2 : 1) * (bn / 32.0) * 350.0 / 2.0 + 600.0;
-            const double unit = std::max(mainloop, epi) + 1500.0;
-            const double cost = (double)waves * unit;
-            if (cost < best_cost * 0.999) {
-                best_cost = cost;
-                best = {bn, pair};
+            const bool two_acc = pair || bn <= 128;
+            const double exec = std::max(42.0, (4096.0 + bn * 32.0) / 110.0);
+            const double instr = two_acc ? exec : std::max(exec, 140.0);
+            const int atom_bytes = (pair ? 2 : 1) * A_STAGE_BYTES + bn * KBYTES;
+            for (int katoms = 1; katoms <= 2; katoms++) {
+                if (katoms == 2 && k_blocks < 2) continue;
+                const int stages = std::min(MAX_STAGES, budget / (atom_bytes * katoms));
+                if (stages < 3 && !(katoms == 1 && stages == 2)) continue;
+                const double t_stage = std::max(katoms * 4.0 * (pair ? 2 : 1) * instr + 320.0, 2200.0 / stages);
+                const double mainloop = std::ceil((double)k_blocks / katoms) * t_stage;
+                const double epi = (pair ? 2 : 1) * (bn / 32.0) * 350.0 / 2.0 + 600.0;
+                const double unit = std::max(mainloop, epi) + 1500.0;
+                const double cost = (double)waves * unit;
+                if (cost < best_cost * 0.999) {
+                    best_cost = cost;
+                    best = {bn, pair, katoms};
+                }
             }
         }
     }
@@ -727,8 +753,10 @@ rten_status launch_umma_gemm(rten_ctx* ctx, const GemmLaunch& L) {
         TileChoice tcz = pick_tile(L.N, p.tiles_m, batch, p.k_blocks, ctx->num_sms, p.tma_store ? 32 : 16, n_stg);
         if (const char* f = getenv("RTEN_B200_FORCE_BN")) tcz.bn = atoi(f);
         if (const char* f = getenv("RTEN_B200_FORCE_PAIR")) tcz.pair = atoi(f) && tcz.bn <= 128 && p.tiles_m >= 2;
+        if (const char* f = getenv("RTEN_B200_FORCE_KATOMS")) tcz.katoms = atoi(f) == 2 ? 2 : 1;
         p.bn = tcz.bn;
         p.pair = tcz.pair;
+        p.katoms = tcz.katoms;
         p.ksplit = (!p.pair && p.bn <= 128 && !getenv("RTEN_B200_NO_KSPLIT")) ? 1 : 0;
         tiles_m_total = (p.pair ? (p.tiles_m + 1) / 2 : p.tiles_m) * batch;
     }
@@ -740,9 +768,11 @@ rten_status launch_umma_gemm(rten_ctx* ctx, const GemmLaunch& L) {
     bbox[1] = p.bn;
     bbox[2] = 1;
     bbox[3] = 1;
-    p.stage_bytes = (p.pair ? 2 : 1) * A_STAGE_BYTES + p.bn * KBYTES;
-    p.tx_bytes = (p.pair ? 2 : 1) * a_rows * KBYTES + p.bn * KBYTES;
-    const int smem_budget = 227 * 1024 - 2048 - n_stg * STG_BYTES;
+    p.atom_bytes = (p.pair ? 2 : 1) * A_STAGE_BYTES + p.bn * KBYTES;
+    if (p.katoms == 2 && (smem_budget_for(n_stg) / (int)(2 * p.atom_bytes) < 2 || p.k_blocks < 2)) p.katoms = 1;
+    p.stage_bytes = p.atom_bytes * p.katoms;
+    p.tx_bytes = (p.pair ? 2 : 1) * a_rows * KBYTES + p.bn * KBYTES;  // per 128-byte K block
+    const int smem_budget = smem_budget_for(n_stg);
     p.stages = std::min(MAX_STAGES, smem_budget / (int)p.stage_bytes);
     if (p.stages < 2) return RTEN_ERR_UNSUPPORTED_VALUE;
     if (L.kind == 0)
@@ -765,8 +795,8 @@ rten_status launch_umma_gemm(rten_ctx* ctx, const GemmLaunch& L) {
     }
 
     if (getenv("RTEN_B200_VERBOSE"))
-        fprintf(stderr, "[umma_gemm] kind=%d conv=%d M=%d N=%d K=%d kb=%d tiles_m=%d bn=%d pair=%d ksplit=%d units=%d stages=%d tma_store=%d res_tma=%d box=%dx%dx%d\n",
-                L.kind, L.conv, L.M, L.N, L.K, p.k_blocks, p.tiles_m, p.bn, p.pair, p.ksplit, p.tiles_total, p.stages, p.tma_store, p.res_tma, p.tw, p.th, p.tb);
+        fprintf(stderr, "[umma_gemm] kind=%d conv=%d M=%d N=%d K=%d kb=%d tiles_m=%d bn=%d pair=%d ksplit=%d katoms=%d units=%d stages=%d tma_store=%d res_tma=%d box=%dx%dx%d\n",
+                L.kind, L.conv, L.M, L.N, L.K, p.k_blocks, p.tiles_m, p.bn, p.pair, p.ksplit, p.katoms, p.tiles_total, p.stages, p.tma_store, p.res_tma, p.tw, p.th, p.tb);
     const size_t smem_bytes = (size_t)p.stages * p.stage_bytes + n_stg * STG_BYTES + 1024 /*align*/ + 256 /*barriers*/;
     const int grid = std::min(p.tiles_total, ctx->num_sms);
     cudaError_t e;
