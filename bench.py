@@ -147,6 +147,7 @@ def main():
     ap.add_argument("--model", default="resnet50", choices=["resnet50", "bert"])
     ap.add_argument("--no-graph", action="store_true", help="issue ops one by one instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary numbers (BERT-base pass, 8192^3 GEMM TFLOP/s)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     model = args.model
@@ -163,7 +164,7 @@ def main():
     import torch
     import torch.distributed as dist
     import rten_b200 as rt
-    from rten_b200 import graphs
+    from rten_b200 import graphs, shard
     from oracle import oracle  # inputs/weights RNG + cpu_baseline leg only
 
     if not torch.cuda.is_available():
@@ -197,7 +198,7 @@ def main():
     ctx.sync()
     out_shape = out.shape
     del out
-    gather_buf = torch.empty((world,) + tuple(out_shape), dtype=torch.float32, device="cuda") if world > 1 else None
+    gather_buf = torch.empty(shard.gather_layout(world, tuple(out_shape)), dtype=torch.float32, device="cuda") if world > 1 else None
     out_t = torch.empty(tuple(out_shape), dtype=torch.float32, device="cuda")
     out_dst = rt.from_torch(ctx, out_t)
 
@@ -222,7 +223,7 @@ def main():
         else:
             copy_out(step_fn())
         if world > 1:
-            dist.all_gather_into_tensor(gather_buf, out_t)
+            shard.all_gather_outputs(dist, out_t, gather_buf)
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
@@ -294,6 +295,10 @@ def main():
     if rank == 0:
         roof = roofline_pass(ctx, rt, runner, model, spec, dev_inputs, batch, stream, torch)
 
+    extras = None
+    if rank == 0 and not args.no_extras:
+        extras = secondary_numbers(ctx, rt, graphs, oracle, model, stream, torch, flush)
+
     if rank == 0:
         peaks = load_peaks()
         line = {
@@ -310,9 +315,15 @@ def main():
             tf32_peak = 0.5 * peaks["bf16_sustained"]
             roof_line = {"bound": "tensor", "kernel": "rtb::umma_gemm_kernel<0> (tcgen05 kind::tf32 implicit-GEMM conv / GEMM)",
                          "achieved": roof["tflops"], "peak": tf32_peak, "unit": "TFLOP/s", "frac": roof["tflops"] / tf32_peak,
-                         "traffic": None, "launches_timed": roof["launches"], "share_of_step": roof["share"],
+                         "traffic": ncu_traffic(), "launches_timed": roof["launches"], "share_of_step": roof["share"],
                          "peak_source": f"0.5 x {peaks['src']} bf16 sustained ({peaks['bf16_sustained']} TF/s): kind::tf32 issues at half the bf16 rate"}
             line["roofline"] = roof_line
+        if extras:
+            tf32_peak = 0.5 * peaks["bf16_burst"]
+            extras["gemm_tf32_8192_frac_of_peak"] = extras["gemm_tf32_8192_tflops"] / tf32_peak
+            extras["gemm_int8_8192_frac_of_peak"] = extras["gemm_int8_8192_tops"] / (2.0 * peaks["bf16_burst"])
+            extras["peaks"] = f"tf32 = 0.5 x, int8 = 2 x {peaks['src']} bf16 burst ({peaks['bf16_burst']} TF/s): kernels timed alone"
+            line["also"] = extras
         if not args.no_cpu_baseline:
             a2 = argparse.Namespace(**vars(args))
             a2.steps, a2.warmup = 1, 1
@@ -322,6 +333,67 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu capture of
+    this same command (profiles/r01_ncu_resnet50.json); None if that summary is absent."""
+    p = os.path.join(ROOT, "profiles", "r01_ncu_resnet50.json")
+    try:
+        return json.load(open(p))["umma_avg_dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
+def secondary_numbers(ctx, rt, graphs, oracle, model, stream, torch, flush):
+    """Secondary numbers the BASELINE metric names (BERT-base pass, GEMM TFLOP/s); same timing hygiene, few steps."""
+    out = {}
+
+    def timed(fn, iters=5, warm=2):
+        fn()
+        ctx.graph_begin()
+        fn()
+        g = ctx.graph_end()
+        for _ in range(warm):
+            g.launch()
+        ms = []
+        for _ in range(iters):
+            flush.zero_()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(stream)
+            g.launch()
+            e.record(stream)
+            torch.cuda.synchronize()
+            ms.append(s.elapsed_time(e))
+        return float(np.median(ms))
+
+    n = 8192
+    a = rt.from_torch(ctx, torch.randn(n, n, device="cuda"))
+    b = rt.from_torch(ctx, torch.randn(n, n, device="cuda")).permute(1, 0)
+    o = ctx.empty((n, n))
+    ms = timed(lambda: rt.MatMul().run(ctx, a, b, out=o))
+    out["gemm_tf32_8192_tflops"] = 2.0 * n ** 3 / ms / 1e9
+    ai = rt.from_torch(ctx, torch.randint(0, 255, (n, n), device="cuda", dtype=torch.uint8))
+    bi = rt.from_torch(ctx, torch.randint(-128, 127, (n, n), device="cuda", dtype=torch.int8)).permute(1, 0)
+    oi = ctx.empty((n, n), np.int32)
+    ms = timed(lambda: rt.MatMulInteger().run(ctx, ai, bi, out=oi))
+    out["gemm_int8_8192_tops"] = 2.0 * n ** 3 / ms / 1e9
+    del a, b, o, ai, bi, oi
+    other = "bert" if model == "resnet50" else "resnet50"
+    spec = make_spec(oracle, other)
+    inp = make_inputs(oracle, other, 16 if other == "bert" else 32)
+    if other == "bert":
+        runner = graphs.BertRunner(ctx, spec)
+        ids, tt, mask = ctx.to_device(inp["ids"]), ctx.to_device(inp["tt"]), ctx.to_device(inp["mask"])
+        ms = timed(lambda: runner.run(ids, tt, mask))
+        out["bert_base_fp32_b16_s128_seq_per_sec"] = 16 / (ms / 1e3)
+        out["bert_base_model_tflops"] = graphs.bert_flops(spec, 16, 128) / ms / 1e9
+    else:
+        runner = graphs.ResNet50Runner(ctx, spec)
+        x = ctx.to_device(inp["x"], channels_last=True)
+        ms = timed(lambda: runner.run(x))
+        out["resnet50_fp32_b32_img_per_sec"] = 32 / (ms / 1e3)
+    return out
 
 
 def roofline_pass(ctx, rt, runner, model, spec, dev_inputs, batch, stream, torch):
