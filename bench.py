@@ -101,7 +101,7 @@ def run_reference_arm(args, model, batch):
     from oracle import oracle
     import model_ref
     spec = make_spec(oracle, model)
-    sample = 4 if model == "resnet50" else 2
+    sample = 8 if model == "resnet50" else 4
     inp = make_inputs(oracle, model, sample)
     run = (lambda: model_ref.resnet50_oracle(oracle, spec, inp["x"])) if model == "resnet50" else \
         (lambda: model_ref.bert_oracle(oracle, spec, inp["ids"], inp["tt"], inp["mask"]))

@@ -553,6 +553,11 @@ static void im2col_f32(const float *x, size_t C, size_t H, size_t W, size_t kh, 
                        size_t oh, size_t ow, int pt, int pl, int sy, int sx, int dy, int dx,
                        float *col) {
     size_t Ncol = oh * ow;
+    int par = 0;
+#ifdef _OPENMP
+    par = !omp_in_parallel();
+#endif
+#pragma omp parallel for collapse(3) schedule(static) if (par)
     for (size_t c = 0; c < C; c++)
         for (size_t ky = 0; ky < kh; ky++)
             for (size_t kx = 0; kx < kw; kx++) {
@@ -570,6 +575,23 @@ static void im2col_f32(const float *x, size_t C, size_t H, size_t W, size_t kh, 
             }
 }
 
+static void conv_f32_one(const float *xi, const float *wg, const float *bg, float *yo, size_t cg, size_t og,
+                         size_t H, size_t W, size_t kh, size_t kw, size_t oh, size_t ow, const int *pads,
+                         const int *strides, const int *dil, int pointwise) {
+    size_t Kd = cg * kh * kw, Ncol = oh * ow;
+    if (pointwise) {
+        rto_gemm_f32(og, Ncol, Kd, wg, (ptrdiff_t)Kd, 1, xi, (ptrdiff_t)Ncol, 1, yo, 1.0f, 0.0f, bg, bg ? 2 : 0);
+    } else {
+        float *col = (float *)malloc(Kd * Ncol * sizeof(float));
+        im2col_f32(xi, cg, H, W, kh, kw, oh, ow, pads[0], pads[1], strides[0], strides[1], dil[0], dil[1], col);
+        rto_gemm_f32(og, Ncol, Kd, wg, (ptrdiff_t)Kd, 1, col, (ptrdiff_t)Ncol, 1, yo, 1.0f, 0.0f, bg, bg ? 2 : 0);
+        free(col);
+    }
+}
+
+/* The reference parallelises over batch items with rayon (conv.rs:317-321) AND inside each GEMM (lib.rs:943-1018,
+ * work stealing).  Here: over (image, group) when there are at least as many as threads, otherwise images run one
+ * after the other and the GEMM inside parallelises over its column tiles -- same arithmetic either way. */
 void rto_conv_f32(const float *x, const float *w, const float *bias, float *y, size_t B,
                   size_t C, size_t H, size_t W, size_t O, size_t kh, size_t kw, size_t oh,
                   size_t ow, const int *pads, const int *strides, const int *dil,
@@ -578,25 +600,22 @@ void rto_conv_f32(const float *x, const float *w, const float *bias, float *y, s
     size_t Kd = cg * kh * kw, Ncol = oh * ow;
     int pointwise = (kh == 1 && kw == 1 && pads[0] == 0 && pads[1] == 0 && pads[2] == 0 &&
                      pads[3] == 0 && strides[0] == 1 && strides[1] == 1);
+    int nthreads = 1;
+#ifdef _OPENMP
+    nthreads = omp_get_max_threads();
+#endif
+    if ((size_t)nthreads <= B * groups || Ncol < 4 * NR) {
 #pragma omp parallel for schedule(dynamic, 1) collapse(2)
-    for (size_t n = 0; n < B; n++)
-        for (size_t g = 0; g < groups; g++) {
-            const float *xi = x + (n * C + g * cg) * H * W;
-            const float *wg = w + g * og * Kd;
-            float *yo = y + (n * O + g * og) * Ncol;
-            const float *bg = bias ? bias + g * og : NULL;
-            if (pointwise) {
-                rto_gemm_f32(og, Ncol, Kd, wg, (ptrdiff_t)Kd, 1, xi, (ptrdiff_t)Ncol, 1, yo, 1.0f,
-                             0.0f, bg, bg ? 2 : 0);
-            } else {
-                float *col = (float *)malloc(Kd * Ncol * sizeof(float));
-                im2col_f32(xi, cg, H, W, kh, kw, oh, ow, pads[0], pads[1], strides[0], strides[1],
-                           dil[0], dil[1], col);
-                rto_gemm_f32(og, Ncol, Kd, wg, (ptrdiff_t)Kd, 1, col, (ptrdiff_t)Ncol, 1, yo, 1.0f,
-                             0.0f, bg, bg ? 2 : 0);
-                free(col);
-            }
-        }
+        for (size_t n = 0; n < B; n++)
+            for (size_t g = 0; g < groups; g++)
+                conv_f32_one(x + (n * C + g * cg) * H * W, w + g * og * Kd, bias ? bias + g * og : NULL,
+                             y + (n * O + g * og) * Ncol, cg, og, H, W, kh, kw, oh, ow, pads, strides, dil, pointwise);
+    } else {
+        for (size_t n = 0; n < B; n++)
+            for (size_t g = 0; g < groups; g++)
+                conv_f32_one(x + (n * C + g * cg) * H * W, w + g * og * Kd, bias ? bias + g * og : NULL,
+                             y + (n * O + g * og) * Ncol, cg, og, H, W, kh, kw, oh, ow, pads, strides, dil, pointwise);
+    }
 }
 
 /* ConvInteger -- src/ops/conv.rs:421-475: kernel is the GEMM LHS (u8 after shift-cast),
