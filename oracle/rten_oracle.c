@@ -408,6 +408,10 @@ void rto_gemm_f32(size_t M, size_t N, size_t K, const float *a, ptrdiff_t a_rs, 
         return;
     }
     size_t n_col_tiles = (N + NR - 1) / NR;
+    /* row blocks of mc = 66 rows (row_block_size: 64 rounded up to a multiple of MR, lib.rs:660-663); column tiles x
+     * row blocks are distributed over threads like the reference's nested rayon loops (lib.rs:943-1018). */
+    const size_t MC = 66;
+    size_t n_row_blocks = (M + MC - 1) / MC;
     int par = 1;
 #ifdef _OPENMP
     par = !omp_in_parallel() && (M * N * K > 262144);
@@ -415,59 +419,61 @@ void rto_gemm_f32(size_t M, size_t N, size_t K, const float *a, ptrdiff_t a_rs, 
 #pragma omp parallel if (par)
     {
         float *bp = (float *)aligned_alloc(64, (size_t)KC * NR * sizeof(float));
-#pragma omp for schedule(dynamic, 1)
-        for (size_t jt = 0; jt < n_col_tiles; jt++) {
-            size_t j0 = jt * NR;
-            size_t nj = (N - j0 < NR) ? N - j0 : NR;
-            for (size_t k0 = 0; k0 < K; k0 += KC) {
-                size_t kc = (K - k0 < KC) ? K - k0 : KC;
-                /* pack B panel (zero padded lanes are computed but never stored) */
-                for (size_t k = 0; k < kc; k++) {
-                    const float *brow = b + (k0 + k) * b_rs + j0 * b_cs;
-                    float *dst = bp + k * NR;
-                    if (b_cs == 1) {
-                        memcpy(dst, brow, nj * sizeof(float));
-                    } else {
-                        for (size_t j = 0; j < nj; j++) dst[j] = brow[j * b_cs];
-                    }
-                    for (size_t j = nj; j < NR; j++) dst[j] = 0.0f;
-                }
-                float eff_beta = (k0 == 0) ? beta : 1.0f;
-                for (size_t i0 = 0; i0 < M; i0 += MR) {
-                    size_t mi = (M - i0 < MR) ? M - i0 : MR;
-                    float acc[MR][NR];
-                    for (size_t i = 0; i < MR; i++)
-                        for (size_t j = 0; j < NR; j++) acc[i][j] = 0.0f;
+#pragma omp for schedule(dynamic, 1) collapse(2)
+        for (size_t jt = 0; jt < n_col_tiles; jt++)
+            for (size_t ib = 0; ib < n_row_blocks; ib++) {
+                size_t j0 = jt * NR;
+                size_t nj = (N - j0 < NR) ? N - j0 : NR;
+                size_t r0 = ib * MC, r1 = (r0 + MC < M) ? r0 + MC : M;
+                for (size_t k0 = 0; k0 < K; k0 += KC) {
+                    size_t kc = (K - k0 < KC) ? K - k0 : KC;
+                    /* pack B panel (zero padded lanes are computed but never stored) */
                     for (size_t k = 0; k < kc; k++) {
-                        const float *bk = bp + k * NR;
-                        for (size_t i = 0; i < mi; i++) {
-                            float av = a[(i0 + i) * a_rs + (k0 + k) * a_cs];
-#pragma omp simd
-                            for (size_t j = 0; j < NR; j++) acc[i][j] = fmaf(av, bk[j], acc[i][j]);
+                        const float *brow = b + (k0 + k) * b_rs + j0 * b_cs;
+                        float *dst = bp + k * NR;
+                        if (b_cs == 1) {
+                            memcpy(dst, brow, nj * sizeof(float));
+                        } else {
+                            for (size_t j = 0; j < nj; j++) dst[j] = brow[j * b_cs];
                         }
+                        for (size_t j = nj; j < NR; j++) dst[j] = 0.0f;
                     }
-                    for (size_t i = 0; i < mi; i++) {
-                        float *crow = c + (i0 + i) * N + j0;
-                        for (size_t j = 0; j < nj; j++) {
-                            float t = acc[i][j], o;
-                            if (eff_beta == 0.0f && alpha == 1.0f)
-                                o = t;
-                            else if (eff_beta == 1.0f && alpha == 1.0f)
-                                o = crow[j] + t;
-                            else if (eff_beta == 0.0f)
-                                o = t * alpha;
-                            else
-                                o = fmaf(t, alpha, crow[j] * eff_beta);
-                            if (k0 == 0) {
-                                if (bias_kind == 1) o = o + bias[j0 + j];
-                                if (bias_kind == 2) o = o + bias[i0 + i];
+                    float eff_beta = (k0 == 0) ? beta : 1.0f;
+                    for (size_t i0 = r0; i0 < r1; i0 += MR) {
+                        size_t mi = (r1 - i0 < MR) ? r1 - i0 : MR;
+                        float acc[MR][NR];
+                        for (size_t i = 0; i < MR; i++)
+                            for (size_t j = 0; j < NR; j++) acc[i][j] = 0.0f;
+                        for (size_t k = 0; k < kc; k++) {
+                            const float *bk = bp + k * NR;
+                            for (size_t i = 0; i < mi; i++) {
+                                float av = a[(i0 + i) * a_rs + (k0 + k) * a_cs];
+#pragma omp simd
+                                for (size_t j = 0; j < NR; j++) acc[i][j] = fmaf(av, bk[j], acc[i][j]);
                             }
-                            crow[j] = o;
+                        }
+                        for (size_t i = 0; i < mi; i++) {
+                            float *crow = c + (i0 + i) * N + j0;
+                            for (size_t j = 0; j < nj; j++) {
+                                float t = acc[i][j], o;
+                                if (eff_beta == 0.0f && alpha == 1.0f)
+                                    o = t;
+                                else if (eff_beta == 1.0f && alpha == 1.0f)
+                                    o = crow[j] + t;
+                                else if (eff_beta == 0.0f)
+                                    o = t * alpha;
+                                else
+                                    o = fmaf(t, alpha, crow[j] * eff_beta);
+                                if (k0 == 0) {
+                                    if (bias_kind == 1) o = o + bias[j0 + j];
+                                    if (bias_kind == 2) o = o + bias[i0 + i];
+                                }
+                                crow[j] = o;
+                            }
                         }
                     }
                 }
             }
-        }
         free(bp);
     }
 }
@@ -604,7 +610,7 @@ void rto_conv_f32(const float *x, const float *w, const float *bias, float *y, s
 #ifdef _OPENMP
     nthreads = omp_get_max_threads();
 #endif
-    if ((size_t)nthreads <= B * groups || Ncol < 4 * NR) {
+    if ((size_t)nthreads <= B * groups) {
 #pragma omp parallel for schedule(dynamic, 1) collapse(2)
         for (size_t n = 0; n < B; n++)
             for (size_t g = 0; g < groups; g++)
