@@ -64,6 +64,7 @@ struct KParams {
     uint32_t atom_bytes;
     int ksplit;     // 1: (single-tile mode, bn <= 128) even / odd K blocks accumulate into two TMEM accumulators that the
                     //    epilogue adds: consecutive MMAs never depend on each other (no dependent-accumulate stall)
+    int nbuf;       // staging buffers per epilogue group (ring): nbuf-1 (nbuf-2 with res_tma) bulk stores stay in flight
     int res_tma;    // 1: the residual tile is prefetched by TMA into the staging buffer (needs tma_store)
     uint32_t res_tx_bytes;
     int tma_store;  // 1: epilogue stages 128x32 chunks in smem and writes them with TMA (output rows contiguous)
@@ -103,6 +104,16 @@ __device__ __forceinline__ TileCoord decode_tile(const KParams& p, int t, int su
     return c;
 }
 
+// cp.async.bulk.wait_group.read takes an immediate: leave at most `n` of this thread's bulk stores un-read
+__device__ __forceinline__ void bulk_wait_read(int n) {
+    switch (n) {
+        case 0: asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); break;
+        case 1: asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); break;
+        case 2: asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory"); break;
+        default: asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory"); break;
+    }
+}
+
 template <int KIND>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
@@ -113,13 +124,13 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     // staging: 1 buffer per epilogue group, 2 per group when the residual is prefetched (1024-B aligned)
     uint8_t* stg_base = smem + (size_t)p.stages * p.stage_bytes;
-    const int nbuf = p.res_tma ? 2 : 1;
+    const int nbuf = p.nbuf;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg_base + 2 * nbuf * STG_BYTES);
     uint64_t* empty_bar = full_bar + MAX_STAGES;
     uint64_t* tmem_full = empty_bar + MAX_STAGES;
     uint64_t* tmem_empty = tmem_full + 2;
-    uint64_t* res_bar = tmem_empty + 2;  // [group][buffer]
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_bar + 4);
+    uint64_t* res_bar = tmem_empty + 2;  // [group][buffer], up to 4 buffers per group
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_bar + 8);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -139,7 +150,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             mbar_init(&tmem_full[s], 1);
             mbar_init(&tmem_empty[s], 8);  // one arrival per epilogue warp
         }
-        for (int s = 0; s < 4; s++) mbar_init(&res_bar[s], 1);
+        for (int s = 0; s < 8; s++) mbar_init(&res_bar[s], 1);
         fence_mbar_init();
     }
     if (warp == 2) {
@@ -286,13 +297,14 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             if (p.res_tma && issuer && grp * 32 < p.bn) {
                 // residual of this tile's first chunk: independent of the accumulator -> request it before waiting
                 const TileCoord tc0 = decode_tile(p, t, 0);
-                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                uint64_t* rb = &res_bar[grp * 2 + (ci & 1)];
+                const int b0 = ci % nbuf;
+                bulk_wait_read(nbuf - 1);  // the store that last used buffer b0 (chunk ci - nbuf) has been read
+                uint64_t* rb = &res_bar[grp * 4 + b0];
                 mbar_expect_tx(rb, p.res_tx_bytes);
                 if (p.conv)
-                    tma_load_4d(stg0 + (ci & 1) * STG_BYTES, &tma_r, rb, tc0.n0 + grp * 32, tc0.ox0, tc0.oy0, tc0.b0);
+                    tma_load_4d(stg0 + b0 * STG_BYTES, &tma_r, rb, tc0.n0 + grp * 32, tc0.ox0, tc0.oy0, tc0.b0);
                 else
-                    tma_load_4d(stg0 + (ci & 1) * STG_BYTES, &tma_r, rb, tc0.n0 + grp * 32, tc0.m0, tc0.z0, tc0.z1);
+                    tma_load_4d(stg0 + b0 * STG_BYTES, &tma_r, rb, tc0.n0 + grp * 32, tc0.m0, tc0.z0, tc0.z1);
             }
             mbar_wait(&tmem_full[acc], acc_phase);
             if (p.trace && blockIdx.x == 0 && warp == 4 && lane == 0 && it < 2048) p.trace[4096 + it] = clock64();
@@ -364,7 +376,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                     }
                 }
                 const int nbase = tc.n0 + c0;
-                uint8_t* stg = stg0 + (p.res_tma ? (ci & 1) : 0) * STG_BYTES;
+                const int bcur = ci % nbuf;
+                uint8_t* stg = stg0 + bcur * STG_BYTES;
                 uint8_t* rowp = stg + r * 128;
                 const int sw = r & 7;
                 if (p.res_tma) {
@@ -378,18 +391,19 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                         }
                         if (nsub <= p.pair && nc0 < p.bn) {
                             const TileCoord tn = decode_tile(p, t, nsub);
-                            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                            uint64_t* rb = &res_bar[grp * 2 + ((ci + 1) & 1)];
+                            const int bnext = (ci + 1) % nbuf;
+                            bulk_wait_read(nbuf - 2);  // chunk ci + 1 - nbuf's store has been read; newer ones stay in flight
+                            uint64_t* rb = &res_bar[grp * 4 + bnext];
                             mbar_expect_tx(rb, p.res_tx_bytes);
-                            uint8_t* dst = stg0 + ((ci + 1) & 1) * STG_BYTES;
+                            uint8_t* dst = stg0 + bnext * STG_BYTES;
                             if (p.conv)
                                 tma_load_4d(dst, &tma_r, rb, tn.n0 + nc0, tn.ox0, tn.oy0, tn.b0);
                             else
                                 tma_load_4d(dst, &tma_r, rb, tn.n0 + nc0, tn.m0, tn.z0, tn.z1);
                         }
                     }
-                    mbar_wait(&res_bar[grp * 2 + (ci & 1)], (rphase >> (ci & 1)) & 1);
-                    rphase ^= 1u << (ci & 1);
+                    mbar_wait(&res_bar[grp * 4 + bcur], (rphase >> bcur) & 1);
+                    rphase ^= 1u << bcur;
                 }
                 // ---- fast path (registers, fully unrolled): f32, act in {none, relu}, residual / bias absent or
                 //      128-bit loadable.  Everything else (gelu, strided residual, N tails, the integer zero-point
@@ -422,12 +436,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                     }
                 }
                 // ---- stage the row chunk in shared memory (128 B per row, 16-byte chunks XOR-swizzled by r & 7)
-                if (p.tma_store && !p.res_tma) {
-                    // the previous TMA store of this group must have finished READING the staging buffer
-                    // (with res_tma the residual mbarrier already orders buffer reuse)
-                    if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                    asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
-                }
+                // Buffer reuse: (no residual) the issuer waited, before the previous chunk's barrier, until the store of
+                // chunk ci - nbuf had been read; (res_tma) the residual mbarrier of this buffer orders it.
 #pragma unroll
                 for (int j = 0; j < 8; j++)
                     *reinterpret_cast<uint4*>(rowp + ((j ^ sw) << 4)) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
@@ -458,6 +468,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                     }
                 }
                 if (p.tma_store) {
+                    // leave nbuf-1 stores in flight minus the one about to be issued: frees the buffer of chunk ci+1
+                    if (issuer && !p.res_tma) bulk_wait_read(nbuf - 2 >= 0 ? nbuf - 2 : 0);
                     fence_proxy_async();
                     asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
                     if (issuer) {
@@ -747,7 +759,11 @@ rten_status launch_umma_gemm(rten_ctx* ctx, const GemmLaunch& L) {
         if (getenv("RTEN_B200_NO_RES_TMA")) p.res_tma = 0;
         p.res_tx_bytes = a_rows * KBYTES;
     }
-    const int n_stg = p.res_tma ? 4 : 2;
+    // staging ring per epilogue group: 2 buffers (1 store in flight), 3 with the residual prefetch (load + compute +
+    // store overlap) when at least 3 pipeline stages of the widest tile still fit
+    p.nbuf = p.res_tma ? 3 : 2;
+    if (const char* f = getenv("RTEN_B200_NBUF")) p.nbuf = std::max(2, std::min(4, atoi(f)));
+    const int n_stg = 2 * p.nbuf;
     {
         const long long batch = L.conv ? 1 : (long long)L.z0 * L.z1;
         TileChoice tcz = pick_tile(L.N, p.tiles_m, batch, p.k_blocks, ctx->num_sms, p.tma_store ? 32 : 16, n_stg);
