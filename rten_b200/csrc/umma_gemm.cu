@@ -114,7 +114,10 @@ __device__ __forceinline__ void bulk_wait_read(int n) {
     }
 }
 
-template <int KIND>
+// FAST = the launch satisfies, for EVERY chunk, the conditions of the register fast path (TMA-store output, N % 32 == 0,
+// f32 with act in {none, relu} and bias / residual absent or vector-addressable [residual via TMA], or raw i32): the
+// epilogue is then a short straight-line loop.  The generic variant (FAST = 0) keeps every edge case.
+template <int KIND, int FAST>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                  const __grid_constant__ CUtensorMap tma_d, const __grid_constant__ CUtensorMap tma_r,
@@ -280,8 +283,121 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                 }
             }
         }
-    } else if (warp >= 4) {
-        // ===================== epilogue =====================
+    } else if (FAST && warp >= 4) {
+        // ===================== epilogue (specialised) =====================
+        const EpilogueDesc& e = p.epi;
+        const int q = warp & 3;
+        const int grp = (warp - 4) >> 2;
+        const int r = q * 32 + lane;
+        const int sw = r & 7;
+        uint8_t* stg0 = stg_base + grp * nbuf * STG_BYTES;
+        const bool issuer = (q == 0 && lane == 0);
+        const bool has_bias = e.bias_kind == 1;
+        const float relu_floor = e.act == 1 ? 0.0f : -__int_as_float(0x7f800000);
+        uint32_t ci = 0, rphase = 0;
+        int it = 0;
+        for (int t = blockIdx.x; t < p.tiles_total; t += gridDim.x, it++) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            if (p.res_tma && issuer && grp * 32 < p.bn) {
+                const TileCoord tc0 = decode_tile(p, t, 0);
+                const int b0 = ci % nbuf;
+                bulk_wait_read(nbuf - 1);
+                uint64_t* rb = &res_bar[grp * 4 + b0];
+                mbar_expect_tx(rb, p.res_tx_bytes);
+                if (p.conv)
+                    tma_load_4d(stg0 + b0 * STG_BYTES, &tma_r, rb, tc0.n0 + grp * 32, tc0.ox0, tc0.oy0, tc0.b0);
+                else
+                    tma_load_4d(stg0 + b0 * STG_BYTES, &tma_r, rb, tc0.n0 + grp * 32, tc0.m0, tc0.z0, tc0.z1);
+            }
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            for (int sub = 0; sub <= p.pair; sub++) {
+                const TileCoord tc = decode_tile(p, t, sub);
+                const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_STRIDE + sub * p.bn;
+                for (int c0 = grp * 32; c0 < p.bn; c0 += 64) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(t_row + c0, v);
+                    const int nbase = tc.n0 + c0;
+                    const int bcur = ci % nbuf;
+                    uint8_t* stg = stg0 + bcur * STG_BYTES;
+                    uint8_t* rowp = stg + r * 128;
+                    if (p.res_tma && issuer) {  // prefetch the next chunk's residual of this tile into the next ring slot
+                        int nsub = sub, nc0 = c0 + 64;
+                        if (nc0 >= p.bn) {
+                            nsub = sub + 1;
+                            nc0 = grp * 32;
+                        }
+                        if (nsub <= p.pair && nc0 < p.bn) {
+                            const TileCoord tn = decode_tile(p, t, nsub);
+                            const int bnext = (ci + 1) % nbuf;
+                            bulk_wait_read(nbuf - 2);
+                            uint64_t* rb = &res_bar[grp * 4 + bnext];
+                            mbar_expect_tx(rb, p.res_tx_bytes);
+                            if (p.conv)
+                                tma_load_4d(stg0 + bnext * STG_BYTES, &tma_r, rb, tn.n0 + nc0, tn.ox0, tn.oy0, tn.b0);
+                            else
+                                tma_load_4d(stg0 + bnext * STG_BYTES, &tma_r, rb, tn.n0 + nc0, tn.m0, tn.z0, tn.z1);
+                        }
+                    }
+                    tmem_ld_wait();
+                    if (p.ksplit) {
+#pragma unroll
+                        for (int h = 0; h < 2; h++) {
+                            uint32_t w[16];
+                            tmem_ld_32x16(t_row + p.bn + c0 + h * 16, w);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int j = 0; j < 16; j++) {
+                                if (KIND == 0)
+                                    v[h * 16 + j] = __float_as_uint(__fadd_rn(__uint_as_float(v[h * 16 + j]), __uint_as_float(w[j])));
+                                else
+                                    v[h * 16 + j] += w[j];
+                            }
+                        }
+                    }
+                    if (p.res_tma) {
+                        mbar_wait(&res_bar[grp * 4 + bcur], (rphase >> bcur) & 1);
+                        rphase ^= 1u << bcur;
+                    }
+                    if (KIND == 0) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            float4 rr = make_float4(0.f, 0.f, 0.f, 0.f), bb = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (p.res_tma) rr = *reinterpret_cast<const float4*>(rowp + (((j >> 2) ^ sw) << 4));
+                            if (has_bias) bb = __ldg(reinterpret_cast<const float4*>(e.bias + nbase + j));
+                            const float r4[4] = {rr.x, rr.y, rr.z, rr.w}, b4[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+                            for (int u = 0; u < 4; u++) {
+                                float x = __uint_as_float(v[j + u]) * e.alpha;
+                                x = fmaf(e.r_scale, r4[u], x);
+                                v[j + u] = __float_as_uint(fmaxf(x + b4[u], relu_floor));
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; j++)
+                        *reinterpret_cast<uint4*>(rowp + ((j ^ sw) << 4)) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    if (issuer && !p.res_tma) bulk_wait_read(nbuf - 2);
+                    fence_proxy_async();
+                    asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+                    if (issuer) {
+                        if (p.conv)
+                            tma_store_4d(&tma_d, stg, nbase, tc.ox0, tc.oy0, tc.b0);
+                        else
+                            tma_store_4d(&tma_d, stg, nbase, tc.m0, tc.z0, tc.z1);
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                    ci++;
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+        if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    } else if (!FAST && warp >= 4) {
+        // ===================== epilogue (generic) =====================
         const EpilogueDesc& e = p.epi;
         const int q = warp & 3;          // TMEM lane quadrant this warp may access
         const int grp = (warp - 4) >> 2;  // epilogue group: chunks grp, grp+2, ...
@@ -344,6 +460,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             }
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_STRIDE + sub * p.bn;
             for (int c0 = grp * 32; c0 < p.bn; c0 += 64) {
+                const bool tr = p.trace && blockIdx.x == 0 && warp == 4 && lane == 0;
+                long long t0 = tr ? clock64() : 0;
                 uint32_t v[32];
                 const int ncols = (p.bn - c0) >= 32 ? 32 : 16;
                 if (ncols == 32) {
@@ -357,6 +475,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                     for (int j = 16; j < 32; j++) v[j] = 0;
                 }
                 tmem_ld_wait();
+                if (tr) { const long long t1 = clock64(); p.trace[6144 + 1024 + 0] += t1 - t0; t0 = t1; }
                 if (p.ksplit) {
                     // add the second partial accumulator (columns + bn), 16 columns at a time to bound registers
 #pragma unroll
@@ -435,6 +554,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                         }
                     }
                 }
+                if (tr) { const long long t1 = clock64(); p.trace[6144 + 1024 + 1] += t1 - t0; t0 = t1; }
                 // ---- stage the row chunk in shared memory (128 B per row, 16-byte chunks XOR-swizzled by r & 7)
                 // Buffer reuse: (no residual) the issuer waited, before the previous chunk's barrier, until the store of
                 // chunk ci - nbuf had been read; (res_tma) the residual mbarrier of this buffer orders it.
@@ -467,11 +587,15 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                         }
                     }
                 }
+                if (tr) { const long long t1 = clock64(); p.trace[6144 + 1024 + 2] += t1 - t0; t0 = t1; }
                 if (p.tma_store) {
                     // leave nbuf-1 stores in flight minus the one about to be issued: frees the buffer of chunk ci+1
                     if (issuer && !p.res_tma) bulk_wait_read(nbuf - 2 >= 0 ? nbuf - 2 : 0);
+                    if (tr) { const long long t1 = clock64(); p.trace[6144 + 1024 + 3] += t1 - t0; t0 = t1; }
                     fence_proxy_async();
+                    if (tr) { const long long t1 = clock64(); p.trace[6144 + 1024 + 4] += t1 - t0; t0 = t1; }
                     asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+                    if (tr) { const long long t1 = clock64(); p.trace[6144 + 1024 + 5] += t1 - t0; t0 = t1; p.trace[6144 + 1024 + 7] += 1; }
                     if (issuer) {
                         if (p.conv)
                             tma_store_4d(&tma_d, stg, nbase, tc.ox0, tc.oy0, tc.b0);
@@ -479,6 +603,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                             tma_store_4d(&tma_d, stg, nbase, tc.m0, tc.z0, tc.z1);
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
+                    if (tr) { const long long t1 = clock64(); p.trace[6144 + 1024 + 6] += t1 - t0; t0 = t1; }
                     ci++;
                 } else if (row_ok) {
                     // direct stores from the staged row (any output strides); consecutive lanes = consecutive rows
@@ -761,7 +886,7 @@ rten_status launch_umma_gemm(rten_ctx* ctx, const GemmLaunch& L) {
     }
     // staging ring per epilogue group: 2 buffers (1 store in flight), 3 with the residual prefetch (load + compute +
     // store overlap) when at least 3 pipeline stages of the widest tile still fit
-    p.nbuf = p.res_tma ? 3 : 2;
+    p.nbuf = 2;
     if (const char* f = getenv("RTEN_B200_NBUF")) p.nbuf = std::max(2, std::min(4, atoi(f)));
     const int n_stg = 2 * p.nbuf;
     {
@@ -811,8 +936,8 @@ rten_status launch_umma_gemm(rten_ctx* ctx, const GemmLaunch& L) {
     }
 
     if (getenv("RTEN_B200_VERBOSE"))
-        fprintf(stderr, "[umma_gemm] kind=%d conv=%d M=%d N=%d K=%d kb=%d tiles_m=%d bn=%d pair=%d ksplit=%d katoms=%d units=%d stages=%d tma_store=%d res_tma=%d box=%dx%dx%d\n",
-                L.kind, L.conv, L.M, L.N, L.K, p.k_blocks, p.tiles_m, p.bn, p.pair, p.ksplit, p.katoms, p.tiles_total, p.stages, p.tma_store, p.res_tma, p.tw, p.th, p.tb);
+        fprintf(stderr, "[umma_gemm] kind=%d conv=%d M=%d N=%d K=%d kb=%d tiles_m=%d bn=%d pair=%d ksplit=%d katoms=%d units=%d stages=%d tma_store=%d res_tma=%d nbuf=%d box=%dx%dx%d\n",
+                L.kind, L.conv, L.M, L.N, L.K, p.k_blocks, p.tiles_m, p.bn, p.pair, p.ksplit, p.katoms, p.tiles_total, p.stages, p.tma_store, p.res_tma, p.nbuf, p.tw, p.th, p.tb);
     const size_t smem_bytes = (size_t)p.stages * p.stage_bytes + n_stg * STG_BYTES + 1024 /*align*/ + 256 /*barriers*/;
     const int grid = std::min(p.tiles_total, ctx->num_sms);
     cudaError_t e;
@@ -827,15 +952,23 @@ rten_status launch_umma_gemm(rten_ctx* ctx, const GemmLaunch& L) {
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = getenv("RTEN_B200_NO_PDL") ? 0 : 1;
-    if (L.kind == 0) {
-        e = cudaFuncSetAttribute(umma_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) return fail_cuda(ctx, e, "cudaFuncSetAttribute(umma_gemm<tf32>)");
-        e = cudaLaunchKernelEx(&cfg, umma_gemm_kernel<0>, map_a, map_b, map_d, map_r, p);
-    } else {
-        e = cudaFuncSetAttribute(umma_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) return fail_cuda(ctx, e, "cudaFuncSetAttribute(umma_gemm<i8>)");
-        e = cudaLaunchKernelEx(&cfg, umma_gemm_kernel<1>, map_a, map_b, map_d, map_r, p);
-    }
+    // specialised epilogue when every chunk qualifies for the register fast path
+    const EpilogueDesc& ee = L.epi;
+    bool fastk = p.tma_store && (L.N % 32) == 0 && !ctx->trace && !getenv("RTEN_B200_NO_FAST");
+    if (L.kind == 0)
+        fastk = fastk && ee.act <= 1 && ee.bias_kind != 2 && (ee.r == nullptr || p.res_tma) &&
+                (ee.bias_kind != 1 || (reinterpret_cast<uintptr_t>(ee.bias) & 15) == 0);
+    else
+        fastk = fastk && !ee.za && !ee.zb && !ee.scale;
+    auto launch = [&](auto kern) -> cudaError_t {
+        cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e2 != cudaSuccess) return e2;
+        return cudaLaunchKernelEx(&cfg, kern, map_a, map_b, map_d, map_r, p);
+    };
+    if (L.kind == 0)
+        e = fastk ? launch(umma_gemm_kernel<0, 1>) : launch(umma_gemm_kernel<0, 0>);
+    else
+        e = fastk ? launch(umma_gemm_kernel<1, 1>) : launch(umma_gemm_kernel<1, 0>);
     if (e != cudaSuccess) return fail_cuda(ctx, e, "umma_gemm launch");
     e = cudaGetLastError();
     if (e != cudaSuccess) return fail_cuda(ctx, e, "umma_gemm launch");

@@ -26,6 +26,8 @@ def trace(fn, name):
     buf = (C.c_int64 * 8192)()
     ctx.check(ctx.lib.rten_b200_debug_trace(ctx.handle, 0, buf))
     t = np.frombuffer(buf, dtype=np.int64).reshape(4, 2048)
+    ph = t[3][1024:1032].copy()
+    t[3][1024:1032] = 0
     issue_cost = t[3][680:1360]
     commit_cost = t[3][1364:2044]
     t[3][680:] = 0
@@ -44,6 +46,9 @@ def trace(fn, name):
         n = min(len(prod), len(mma))
         lat = mma[:n] - prod[:n]
         print(f"   TMA issue->landed latency:      median {np.median(lat):.0f} min {lat.min()} max {lat.max()}  first 12: {lat[:12].tolist()}")
+    if ph[7] > 0:
+        names = ["tmem_ld", "math(+bias/res)", "st.shared(+slow path)", "wait prev store read", "fence.proxy.async", "bar.sync", "store issue"]
+        print("   epilogue phases (warp 4, clk per 32-col chunk): " + ", ".join(f"{n} {ph[i] / ph[7]:.0f}" for i, n in enumerate(names)))
     if len(e0):
         print(f"   epilogue duration per tile:     median {np.median(e1 - e0):.0f}  first 6: {(e1 - e0)[:6].tolist()};  tile start interval {np.diff(e0)[:6].tolist()}")
 
