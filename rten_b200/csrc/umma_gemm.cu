@@ -375,10 +375,14 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                             }
                         }
                     }
+                    if (nbuf == 1) {  // single staging buffer: the previous store must have been read before it is rewritten
+                        if (issuer) bulk_wait_read(0);
+                        asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+                    }
 #pragma unroll
                     for (int j = 0; j < 8; j++)
                         *reinterpret_cast<uint4*>(rowp + ((j ^ sw) << 4)) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                    if (issuer && !p.res_tma) bulk_wait_read(nbuf - 2);
+                    if (issuer && !p.res_tma && nbuf > 1) bulk_wait_read(nbuf - 2);
                     fence_proxy_async();
                     asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
                     if (issuer) {
@@ -558,6 +562,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                 // ---- stage the row chunk in shared memory (128 B per row, 16-byte chunks XOR-swizzled by r & 7)
                 // Buffer reuse: (no residual) the issuer waited, before the previous chunk's barrier, until the store of
                 // chunk ci - nbuf had been read; (res_tma) the residual mbarrier of this buffer orders it.
+                if (p.tma_store && nbuf == 1) {
+                    if (issuer) bulk_wait_read(0);
+                    asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+                }
 #pragma unroll
                 for (int j = 0; j < 8; j++)
                     *reinterpret_cast<uint4*>(rowp + ((j ^ sw) << 4)) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
@@ -590,7 +598,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                 if (tr) { const long long t1 = clock64(); p.trace[6144 + 1024 + 2] += t1 - t0; t0 = t1; }
                 if (p.tma_store) {
                     // leave nbuf-1 stores in flight minus the one about to be issued: frees the buffer of chunk ci+1
-                    if (issuer && !p.res_tma) bulk_wait_read(nbuf - 2 >= 0 ? nbuf - 2 : 0);
+                    if (issuer && !p.res_tma && nbuf > 1) bulk_wait_read(nbuf - 2);
                     if (tr) { const long long t1 = clock64(); p.trace[6144 + 1024 + 3] += t1 - t0; t0 = t1; }
                     fence_proxy_async();
                     if (tr) { const long long t1 = clock64(); p.trace[6144 + 1024 + 4] += t1 - t0; t0 = t1; }
@@ -886,8 +894,9 @@ rten_status launch_umma_gemm(rten_ctx* ctx, const GemmLaunch& L) {
     }
     // staging ring per epilogue group: 2 buffers (1 store in flight), 3 with the residual prefetch (load + compute +
     // store overlap) when at least 3 pipeline stages of the widest tile still fit
-    p.nbuf = 2;
-    if (const char* f = getenv("RTEN_B200_NBUF")) p.nbuf = std::max(2, std::min(4, atoi(f)));
+    // main-loop dominated launches keep shared memory for pipeline stages (one staging buffer per group)
+    p.nbuf = (p.res_tma || p.k_blocks < 24) ? 2 : 1;
+    if (const char* f = getenv("RTEN_B200_NBUF")) p.nbuf = std::max(p.res_tma ? 2 : 1, std::min(4, atoi(f)));
     const int n_stg = 2 * p.nbuf;
     {
         const long long batch = L.conv ? 1 : (long long)L.z0 * L.z1;
