@@ -69,6 +69,7 @@ def lib():
             "rto_global_avgpool": (None, [f32p, f32p, sz, sz]),
             "rto_add": (None, [f32p, f32p, f32p, sz]),
             "rto_num_threads": (C.c_int, []),
+            "rto_set_num_threads": (None, [C.c_int]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)
@@ -665,3 +666,13 @@ def global_average_pool(x):
 
 def num_threads() -> int:
     return int(lib().rto_num_threads())
+
+
+def use_all_cores() -> int:
+    """Use every core this process may run on (torchrun sets OMP_NUM_THREADS=1 for its workers)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    lib().rto_set_num_threads(n)
+    return num_threads()

@@ -759,6 +759,15 @@ void rto_add(const float *a, const float *b, float *y, size_t n) {
     for (size_t i = 0; i < n; i++) y[i] = a[i] + b[i];
 }
 
+/* torchrun exports OMP_NUM_THREADS=1; the CPU baseline legs ask for all host cores explicitly. */
+void rto_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int rto_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();
