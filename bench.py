@@ -111,9 +111,10 @@ def run_reference_arm(args, model, batch):
     """CPU restatement of the reference path on all host threads, bounded sample per step."""
     from oracle import oracle
     import model_ref
-    oracle.use_all_cores()
+    ncores = oracle.use_all_cores()
     spec = make_spec(oracle, model)
-    sample = 8 if model == "resnet50" else 4
+    # images are the outer parallel level: a many-core host needs the whole batch in flight to be busy
+    sample = (batch if ncores >= 32 else 8) if model == "resnet50" else (batch if ncores >= 32 else 4)
     inp = make_inputs(oracle, model, sample)
     run = (lambda: model_ref.resnet50_oracle(oracle, spec, inp["x"])) if model == "resnet50" else \
         (lambda: model_ref.bert_oracle(oracle, spec, inp["ids"], inp["tt"], inp["mask"]))
@@ -159,6 +160,7 @@ def main():
     ap.add_argument("--model", default="resnet50", choices=["resnet50", "bert"])
     ap.add_argument("--no-graph", action="store_true", help="issue ops one by one instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-autotune", action="store_true", help="use the cost model's launch plans instead of timing candidates during warm-up")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary numbers (BERT-base pass, 8192^3 GEMM TFLOP/s)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -187,6 +189,7 @@ def main():
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     ctx = rt.Context(local_rank, stream=stream.cuda_stream)
+    ctx.set_autotune(not args.no_autotune)  # plans are measured during the first (untimed, eager) pass
 
     spec = make_spec(oracle, model)
     inp = make_inputs(oracle, model, batch)

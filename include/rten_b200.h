@@ -82,6 +82,13 @@ void rten_b200_ctx_destroy(rten_ctx* ctx);
 const char* rten_b200_last_error(rten_ctx* ctx);
 rten_status rten_b200_sync(rten_ctx* ctx);
 rten_status rten_b200_set_f32_mode(rten_ctx* ctx, int mode /* rten_f32_mode */);
+/* Plan autotuning (off by default; env RTEN_B200_AUTOTUNE=1 turns it on at context creation).  When on, the FIRST
+ * MatMul / Conv launch of every distinct problem (shape, layout, epilogue) outside graph capture times the cost
+ * model's best launch plans on the device and caches the winner in the context -- the role rten-gemm's per-arch
+ * kernel selection and blocking heuristics play (rten-gemm/src/lib.rs:199-391), decided by measurement.  Integer
+ * results do not depend on the plan; f32 results stay within the TF32 tolerance but may differ in the last bits
+ * between plans (split-K changes the summation order). */
+rten_status rten_b200_set_autotune(rten_ctx* ctx, int enable);
 /* Caching, stream-ordered device allocator = `BufferPool` (src/buffer_pool.rs:1-140). */
 rten_status rten_b200_alloc(rten_ctx* ctx, size_t bytes, void** dev_ptr);
 rten_status rten_b200_free(rten_ctx* ctx, void* dev_ptr);

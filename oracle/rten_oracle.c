@@ -29,6 +29,24 @@
 #include <omp.h>
 #endif
 
+/* Threads a GEMM / im2col may use from where it is called.  Level 0 (not inside a parallel region): every thread
+ * of the runtime; level 1 (inside the per-image team loop of rto_conv_f32): the team size g_team; deeper: 1.
+ * `work` (multiply-adds) bounds the count so tiny problems do not pay the fork/join of 100+ threads. */
+static int g_team = 1;
+static int threads_for(size_t work) {
+#ifdef _OPENMP
+    int level = omp_get_level();
+    int nt = level == 0 ? omp_get_max_threads() : (level == 1 ? g_team : 1);
+    size_t cap = work / 131072;
+    if (cap < 1) cap = 1;
+    if ((size_t)nt > cap) nt = (int)cap;
+    return nt < 1 ? 1 : nt;
+#else
+    (void)work;
+    return 1;
+#endif
+}
+
 #define V 16 /* AVX-512 f32 lanes */
 
 /* ------------------------------------------------------------------------------------
@@ -412,11 +430,8 @@ void rto_gemm_f32(size_t M, size_t N, size_t K, const float *a, ptrdiff_t a_rs, 
      * row blocks are distributed over threads like the reference's nested rayon loops (lib.rs:943-1018). */
     const size_t MC = 66;
     size_t n_row_blocks = (M + MC - 1) / MC;
-    int par = 1;
-#ifdef _OPENMP
-    par = !omp_in_parallel() && (M * N * K > 262144);
-#endif
-#pragma omp parallel if (par)
+    int nt = threads_for(M * N * K);
+#pragma omp parallel if (nt > 1) num_threads(nt)
     {
         float *bp = (float *)aligned_alloc(64, (size_t)KC * NR * sizeof(float));
 #pragma omp for schedule(dynamic, 1) collapse(2)
@@ -506,11 +521,8 @@ void rto_gemm_f64(size_t M, size_t N, size_t K, const float *a, ptrdiff_t a_rs, 
 void rto_gemm_u8i8(size_t M, size_t N, size_t K, const uint8_t *a, ptrdiff_t a_rs,
                    ptrdiff_t a_cs, const int8_t *b, ptrdiff_t b_rs, ptrdiff_t b_cs, int32_t *c,
                    const uint8_t *a_zp, const int8_t *b_zp) {
-    int par = 1;
-#ifdef _OPENMP
-    par = !omp_in_parallel() && (M * N * K > 262144);
-#endif
-#pragma omp parallel if (par)
+    int nt = threads_for(M * N * K);
+#pragma omp parallel if (nt > 1) num_threads(nt)
     {
         int16_t *bcol = (int16_t *)malloc((K ? K : 1) * sizeof(int16_t));
 #pragma omp for schedule(static)
@@ -559,11 +571,8 @@ static void im2col_f32(const float *x, size_t C, size_t H, size_t W, size_t kh, 
                        size_t oh, size_t ow, int pt, int pl, int sy, int sx, int dy, int dx,
                        float *col) {
     size_t Ncol = oh * ow;
-    int par = 0;
-#ifdef _OPENMP
-    par = !omp_in_parallel();
-#endif
-#pragma omp parallel for collapse(3) schedule(static) if (par)
+    int nt = threads_for(C * kh * kw * Ncol * 8);
+#pragma omp parallel for collapse(3) schedule(static) if (nt > 1) num_threads(nt)
     for (size_t c = 0; c < C; c++)
         for (size_t ky = 0; ky < kh; ky++)
             for (size_t kx = 0; kx < kw; kx++) {
@@ -596,8 +605,8 @@ static void conv_f32_one(const float *xi, const float *wg, const float *bg, floa
 }
 
 /* The reference parallelises over batch items with rayon (conv.rs:317-321) AND inside each GEMM (lib.rs:943-1018,
- * work stealing).  Here: over (image, group) when there are at least as many as threads, otherwise images run one
- * after the other and the GEMM inside parallelises over its column tiles -- same arithmetic either way. */
+ * work stealing).  Here: two OpenMP levels -- teams over (image, group), and the column tiles x row blocks of each
+ * GEMM over the threads of a team -- same arithmetic whatever the split. */
 void rto_conv_f32(const float *x, const float *w, const float *bias, float *y, size_t B,
                   size_t C, size_t H, size_t W, size_t O, size_t kh, size_t kw, size_t oh,
                   size_t ow, const int *pads, const int *strides, const int *dil,
@@ -606,16 +615,26 @@ void rto_conv_f32(const float *x, const float *w, const float *bias, float *y, s
     size_t Kd = cg * kh * kw, Ncol = oh * ow;
     int pointwise = (kh == 1 && kw == 1 && pads[0] == 0 && pads[1] == 0 && pads[2] == 0 &&
                      pads[3] == 0 && strides[0] == 1 && strides[1] == 1);
-    int nthreads = 1;
+    size_t units = B * groups;
+    int nthreads = 1, in_par = 0;
 #ifdef _OPENMP
     nthreads = omp_get_max_threads();
+    in_par = omp_in_parallel();
 #endif
-    if ((size_t)nthreads <= B * groups) {
-#pragma omp parallel for schedule(dynamic, 1) collapse(2)
+    if (units > 1 && nthreads > 1 && !in_par) {
+        /* teams: `outer` images in flight, each GEMM / im2col inside uses nthreads / outer threads */
+        int outer = (size_t)nthreads < units ? nthreads : (int)units;
+#ifdef _OPENMP
+        omp_set_max_active_levels(2);
+#endif
+        g_team = nthreads / outer;
+        if (g_team < 1) g_team = 1;
+#pragma omp parallel for schedule(dynamic, 1) collapse(2) num_threads(outer)
         for (size_t n = 0; n < B; n++)
             for (size_t g = 0; g < groups; g++)
                 conv_f32_one(x + (n * C + g * cg) * H * W, w + g * og * Kd, bias ? bias + g * og : NULL,
                              y + (n * O + g * og) * Ncol, cg, og, H, W, kh, kw, oh, ow, pads, strides, dil, pointwise);
+        g_team = 1;
     } else {
         for (size_t n = 0; n < B; n++)
             for (size_t g = 0; g < groups; g++)

@@ -188,6 +188,7 @@ rten_status rten_b200_ctx_create(int device, void* cuda_stream_or_null, size_t w
         }
         ctx->own_stream = true;
     }
+    if (const char* at = getenv("RTEN_B200_AUTOTUNE")) ctx->autotune = atoi(at) != 0;
     const char* mode = getenv("RTEN_B200_F32_MODE");
     if (mode && strcmp(mode, "tf32x3") == 0) ctx->f32_mode = RTEN_F32_TF32X3;
     if (workspace_bytes) {  // pre-reserve one pool bucket so the first ops do not pay cudaMalloc
@@ -205,6 +206,7 @@ void rten_b200_ctx_destroy(rten_ctx* ctx) {
     for (auto& kv : ctx->pool.free_buckets)
         for (void* p : kv.second) cudaFree(p);
     for (auto& kv : ctx->pool.live) cudaFree(kv.first);
+    if (ctx->sk_counters) cudaFree(ctx->sk_counters);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -222,6 +224,12 @@ rten_status rten_b200_set_f32_mode(rten_ctx* ctx, int mode) {
     if (mode != RTEN_F32_TF32 && mode != RTEN_F32_TF32X3) return fail(ctx, RTEN_ERR_INVALID_VALUE, "unknown f32 mode");
     if (mode == RTEN_F32_TF32X3) return fail(ctx, RTEN_ERR_UNSUPPORTED_VALUE, "tf32x3 mode is not implemented yet");
     ctx->f32_mode = mode;
+    return RTEN_OK;
+}
+
+rten_status rten_b200_set_autotune(rten_ctx* ctx, int enable) {
+    if (!ctx) return RTEN_ERR_INVALID_VALUE;
+    ctx->autotune = enable != 0;
     return RTEN_OK;
 }
 

@@ -4,6 +4,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <array>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -54,6 +55,9 @@ struct rten_ctx {
     std::vector<void*> temps;
     void* trace = nullptr;         // device buffer of 4 x 2048 int64 timestamps (debug), or null
     void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled (driver entry point)
+    void* sk_counters = nullptr;   // split-K arrival counters (zero between launches)
+    bool autotune = false;         // time candidate launch plans on first sight of a problem (umma_gemm.cu)
+    std::map<std::vector<long long>, std::array<int, 8>> tune_cache;
 };
 
 namespace rtb {

@@ -24,6 +24,9 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <array>
+#include <cmath>
+#include <vector>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -68,6 +71,15 @@ struct KParams {
     int res_tma;    // 1: the residual tile is prefetched by TMA into the staging buffer (needs tma_store)
     uint32_t res_tx_bytes;
     int tma_store;  // 1: epilogue stages 128x32 chunks in smem and writes them with TMA (output rows contiguous)
+    int acc1;       // 1: ONE accumulator stage of 512 TMEM columns (pair mode with bn = 256: a 256 x 256 tile per CTA halves
+                    //    the L2 -> SM operand traffic per flop; the epilogue no longer overlaps the next main loop)
+    int splitk;     // > 1: `splitk` CTAs share one output tile, each over `kb_per` K blocks; raw partial accumulators go
+                    // to `sk_ws`, the LAST CTA to arrive (per tile and epilogue group, `sk_cnt`) sums them in split order
+                    // (deterministic) and runs the epilogue
+    int kb_per;
+    int units_total;  // tiles_total * splitk
+    uint32_t* sk_ws;
+    int* sk_cnt;
     EpilogueDesc epi;
 };
 
@@ -114,6 +126,59 @@ __device__ __forceinline__ void bulk_wait_read(int n) {
     }
 }
 
+// Split-K hand-off of one epilogue group (128 threads): store this CTA's raw accumulator chunks, then count arrivals.
+// Returns true for the group of the CTA that arrived last: it owns the epilogue of (tile, group).
+// Workspace layout: [tile][sub][split][chunk][column j][row r] so that a warp's 32 rows are contiguous.
+__device__ __forceinline__ bool splitk_publish(const KParams& p, int t, int ks, int grp, int q, int lane, uint32_t t_acc,
+                                               int* flag) {
+    const int r = q * 32 + lane;
+    const int nchunks = p.bn >> 5;
+    for (int sub = 0; sub <= p.pair; sub++) {
+        for (int c0 = grp * 32; c0 < p.bn; c0 += 64) {
+            uint32_t v[32];
+            tmem_ld_32x32(t_acc + sub * p.bn + c0, v);
+            tmem_ld_wait();
+            uint32_t* w = p.sk_ws + ((((size_t)(t * 2 + sub) * p.splitk + ks) * nchunks + (c0 >> 5)) << 12) + r;
+#pragma unroll
+            for (int j = 0; j < 32; j++) __stcg(w + j * 128, v[j]);
+        }
+    }
+    __threadfence();
+    asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+    if (q == 0 && lane == 0) {
+        int* cnt = p.sk_cnt + t * 2 + grp;
+        const int old = atomicAdd(cnt, 1);
+        const int last = old == p.splitk - 1;
+        if (last) *cnt = 0;  // every split has arrived: re-arm for the next launch
+        __threadfence();
+        *flag = last;
+    }
+    asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+    return *reinterpret_cast<volatile int*>(flag) != 0;
+}
+
+// Sum of the `splitk` partial chunks in split order (the same order whichever CTA arrived last).
+template <int KIND>
+__device__ __forceinline__ void splitk_sum(const KParams& p, int t, int sub, int c0, int r, uint32_t (&v)[32]) {
+    const int nchunks = p.bn >> 5;
+    const uint32_t* w = p.sk_ws + ((((size_t)(t * 2 + sub) * p.splitk) * nchunks + (c0 >> 5)) << 12) + r;
+    const size_t stride = (size_t)nchunks << 12;
+#pragma unroll
+    for (int j = 0; j < 32; j++) v[j] = __ldcg(w + j * 128);
+#pragma unroll 1
+    for (int s = 1; s < p.splitk; s++) {
+        w += stride;
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+            const uint32_t x = __ldcg(w + j * 128);
+            if (KIND == 0)
+                v[j] = __float_as_uint(__fadd_rn(__uint_as_float(v[j]), __uint_as_float(x)));
+            else
+                v[j] += x;
+        }
+    }
+}
+
 // FAST = the launch satisfies, for EVERY chunk, the conditions of the register fast path (TMA-store output, N % 32 == 0,
 // f32 with act in {none, relu} and bias / residual absent or vector-addressable [residual via TMA], or raw i32): the
 // epilogue is then a short straight-line loop.  The generic variant (FAST = 0) keeps every edge case.
@@ -134,6 +199,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     uint64_t* tmem_empty = tmem_full + 2;
     uint64_t* res_bar = tmem_empty + 2;  // [group][buffer], up to 4 buffers per group
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_bar + 8);
+    int* sk_flag = reinterpret_cast<int*>(tmem_ptr + 2);  // [group]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -180,12 +246,15 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         const uint32_t smem0 = smem_u32(smem);
         const uint32_t full0 = smem_u32(full_bar);
         const uint32_t a_bytes = (p.pair ? 2 : 1) * A_STAGE_BYTES;
-        for (int t = blockIdx.x; t < p.tiles_total; t += gridDim.x) {
+        for (int u = blockIdx.x; u < p.units_total; u += gridDim.x) {
+            const int t = u % p.tiles_total;
+            const int kb0 = (u / p.tiles_total) * p.kb_per, kb1 = min(p.k_blocks, kb0 + p.kb_per);
             const TileCoord tc = decode_tile(p, t, 0);
             const TileCoord tc1 = decode_tile(p, t, 1);
-            int tap = 0, cb = 0, ky = 0, kx = 0;  // conv: K block -> (filter tap, channel block), kept incrementally
-            for (int kb = 0; kb < p.k_blocks; kb += p.katoms) {
-                const int natoms = min(p.katoms, p.k_blocks - kb);
+            // conv: K block -> (filter tap, channel block), kept incrementally
+            int tap = kb0 / p.c_blocks, cb = kb0 - tap * p.c_blocks, ky = tap / p.kw, kx = tap - ky * p.kw;
+            for (int kb = kb0; kb < kb1; kb += p.katoms) {
+                const int natoms = min(p.katoms, kb1 - kb);
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 const bool leader = elect_one();
                 const uint32_t fb = full0 + stage * 8;
@@ -239,14 +308,15 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         const uint32_t empty0 = smem_u32(empty_bar);
         const uint32_t b_off = (p.pair ? 2 : 1) * A_STAGE_BYTES;
         const uint32_t d1_off = (p.pair || p.ksplit) ? p.bn : 0;
-        for (int t = blockIdx.x; t < p.tiles_total; t += gridDim.x, it++) {
-            const int acc = it & 1;
-            const uint32_t acc_phase = (it >> 1) & 1;
+        for (int u = blockIdx.x; u < p.units_total; u += gridDim.x, it++) {
+            const int kb0 = (u / p.tiles_total) * p.kb_per, kb1 = min(p.k_blocks, kb0 + p.kb_per);
+            const int acc = p.acc1 ? 0 : (it & 1);
+            const uint32_t acc_phase = (p.acc1 ? it : (it >> 1)) & 1;
             mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
-            for (int kb = 0; kb < p.k_blocks; kb += p.katoms) {
-                const int natoms = min(p.katoms, p.k_blocks - kb);
+            for (int kb = kb0; kb < kb1; kb += p.katoms) {
+                const int natoms = min(p.katoms, kb1 - kb);
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
                 if (elect_one()) {
@@ -255,7 +325,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                         const uint32_t sa = smem0 + stage * p.stage_bytes + a * p.atom_bytes;
                         const uint64_t adesc = make_kmajor_sw128_desc(sa);
                         const uint64_t bdesc = make_kmajor_sw128_desc(sa + b_off);
-                        const uint32_t first = (kb + a) == 0 ? 0u : 1u;
+                        const uint32_t first = (kb + a) == kb0 ? 0u : 1u;
                         if (p.pair) {
                             const uint64_t adesc1 = make_kmajor_sw128_desc(sa + A_STAGE_BYTES);
 #pragma unroll
@@ -274,7 +344,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                         }
                     }
                     umma_commit_u32(empty0 + stage * 8);  // smem slot reusable once these MMAs retire
-                    if (kb + natoms >= p.k_blocks) umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+                    if (kb + natoms >= kb1) umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
                 }
                 __syncwarp();
                 if (++stage == p.stages) {
@@ -296,9 +366,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         const float relu_floor = e.act == 1 ? 0.0f : -__int_as_float(0x7f800000);
         uint32_t ci = 0, rphase = 0;
         int it = 0;
-        for (int t = blockIdx.x; t < p.tiles_total; t += gridDim.x, it++) {
-            const int acc = it & 1;
-            const uint32_t acc_phase = (it >> 1) & 1;
+        for (int u = blockIdx.x; u < p.units_total; u += gridDim.x, it++) {
+            const int t = u % p.tiles_total;
+            const int acc = p.acc1 ? 0 : (it & 1);
+            const uint32_t acc_phase = (p.acc1 ? it : (it >> 1)) & 1;
             if (p.res_tma && issuer && grp * 32 < p.bn) {
                 const TileCoord tc0 = decode_tile(p, t, 0);
                 const int b0 = ci % nbuf;
@@ -312,12 +383,19 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             }
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
-            for (int sub = 0; sub <= p.pair; sub++) {
+            bool owner = true;
+            if (p.splitk > 1)
+                owner = splitk_publish(p, t, u / p.tiles_total, grp, q, lane,
+                                       tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_STRIDE, &sk_flag[grp]);
+            for (int sub = 0; owner && sub <= p.pair; sub++) {
                 const TileCoord tc = decode_tile(p, t, sub);
                 const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_STRIDE + sub * p.bn;
                 for (int c0 = grp * 32; c0 < p.bn; c0 += 64) {
                     uint32_t v[32];
-                    tmem_ld_32x32(t_row + c0, v);
+                    if (p.splitk > 1)
+                        splitk_sum<KIND>(p, t, sub, c0, r, v);
+                    else
+                        tmem_ld_32x32(t_row + c0, v);
                     const int nbase = tc.n0 + c0;
                     const int bcur = ci % nbuf;
                     uint8_t* stg = stg0 + bcur * STG_BYTES;
@@ -411,9 +489,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         uint32_t ci = 0;            // chunks processed by this group so far (selects the staging buffer)
         uint32_t rphase = 0;        // bit b = phase of res_bar[grp][b]
         int it = 0;
-        for (int t = blockIdx.x; t < p.tiles_total; t += gridDim.x, it++) {
-            const int acc = it & 1;
-            const uint32_t acc_phase = (it >> 1) & 1;
+        for (int u = blockIdx.x; u < p.units_total; u += gridDim.x, it++) {
+            const int t = u % p.tiles_total;
+            const int acc = p.acc1 ? 0 : (it & 1);
+            const uint32_t acc_phase = (p.acc1 ? it : (it >> 1)) & 1;
             if (p.res_tma && issuer && grp * 32 < p.bn) {
                 // residual of this tile's first chunk: independent of the accumulator -> request it before waiting
                 const TileCoord tc0 = decode_tile(p, t, 0);
@@ -429,7 +508,11 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             mbar_wait(&tmem_full[acc], acc_phase);
             if (p.trace && blockIdx.x == 0 && warp == 4 && lane == 0 && it < 2048) p.trace[4096 + it] = clock64();
             tc_fence_after();
-            for (int sub = 0; sub <= p.pair; sub++) {
+            bool owner = true;
+            if (p.splitk > 1)
+                owner = splitk_publish(p, t, u / p.tiles_total, grp, q, lane,
+                                       tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_STRIDE, &sk_flag[grp]);
+            for (int sub = 0; owner && sub <= p.pair; sub++) {
             const TileCoord tc = decode_tile(p, t, sub);
             // ---- row bookkeeping
             bool row_ok;
@@ -468,7 +551,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                 long long t0 = tr ? clock64() : 0;
                 uint32_t v[32];
                 const int ncols = (p.bn - c0) >= 32 ? 32 : 16;
-                if (ncols == 32) {
+                if (p.splitk > 1) {
+                    splitk_sum<KIND>(p, t, sub, c0, r, v);
+                } else if (ncols == 32) {
                     tmem_ld_32x32(t_row + c0, v);
                 } else {
                     uint32_t w[16];
@@ -724,68 +809,127 @@ static void pick_conv_tile(const ConvGeom& g, int& tw, int& th, int& tb) {
     }
 }
 
-// Tile-shape choice.  Cost model in clocks per CTA, constants measured with the in-kernel trace (tools/trace_probe.py,
-// profiles/r01_trace_*.txt):
-//   * a tcgen05.mma (SS operands) is bound by operand fetch from shared memory at ~64 B/clk: A (128 rows x 32 B) + B
-//     (bn rows x 32 B) -> 64 + bn/2 clk per instruction, 4 instructions per 128-byte K block;
-//   * consecutive MMAs on ONE accumulator cannot retire faster than ~140 clk each (dependent accumulate); PAIR mode
-//     alternates two tiles on two accumulators and removes that floor (and loads B once for both tiles);
-//   * a K block cannot complete faster than TMA latency / stages in flight (~2200 clk under load);
-//   * the epilogue (~350 clk per 32-column chunk, two warp groups) overlaps the next main loop.
-struct TileChoice {
-    int bn, pair, katoms;
+// ------------------------------------------------------------------------------------------
+// Launch plans
+// ------------------------------------------------------------------------------------------
+// A plan fixes the tile shape and the work decomposition of one launch.  Plans come from (a) the cost model below or
+// (b) the per-context autotune cache: with rten_b200_set_autotune(ctx, 1) the first launch of every distinct problem
+// times the model's best candidates on the device (CUDA events on the context stream) and remembers the winner.
+struct Plan {
+    int bn = 32, pair = 0, katoms = 1, ksplit = 0, splitk = 1, nbuf = 1, acc1 = 0;
 };
+
+// Everything about a launch that does not depend on the plan.
+struct Prepared {
+    KParams p;  // geometry filled in; plan-dependent fields zero
+    uint32_t abox[4], aes[4], bbox_k;
+    uint32_t a_rows;
+    long long batch;
+    OperandDesc od, ord;
+    uint32_t dbox[4];
+    int tma_store, res_tma;  // eligibility
+    int step;
+    int esize, kelems;
+};
+
+constexpr int SK_CNT_INTS = 1 << 16;
 static int smem_budget_for(int n_stg) { return 227 * 1024 - 2048 - n_stg * STG_BYTES; }
 
-// Measured with the in-kernel trace (profiles/r01_trace_*.txt), clocks:
-//   issuing one tcgen05.mma costs the elected thread ~42 clk; executing it is bound by operand fetch from shared
-//   memory at ~110 B/clk (A: 128 rows x 32 B, B: bn rows x 32 B); consecutive MMAs on ONE accumulator serialise at
-//   ~140 clk unless they alternate between two accumulators (pair / ksplit modes); every pipeline stage costs the
-//   issuing warp a fixed ~320 clk (barrier wait, fence, descriptors, commit) -> small tiles put TWO 128-byte K blocks
-//   in a stage; a stage cannot complete faster than TMA latency (~2200 clk under load) / stages in flight.
-static TileChoice pick_tile(int N, long long tiles_m, long long batch, int k_blocks, int num_sms, int step, int n_stg) {
-    TileChoice best{step, 0, 1};
-    double best_cost = 1e300;
-    const int nmax = (N + step - 1) / step * step;
-    const int budget = smem_budget_for(n_stg);
-    for (int pair = 0; pair <= 1; pair++) {
-        for (int bn = step; bn <= (pair ? 128 : 256); bn += step) {
-            if (bn > nmax && bn != step) break;
-            if (pair && tiles_m < 2) continue;
-            const long long tiles_n = (N + bn - 1) / bn;
-            const long long units_m = pair ? (tiles_m + 1) / 2 : tiles_m;
-            const long long units = units_m * tiles_n * batch;
-            const long long waves = (units + num_sms - 1) / num_sms;
-            const bool two_acc = pair || bn <= 128;
-            const double exec = std::max(42.0, (4096.0 + bn * 32.0) / 110.0);
-            const double instr = two_acc ? exec : std::max(exec, 140.0);
-            const int atom_bytes = (pair ? 2 : 1) * A_STAGE_BYTES + bn * KBYTES;
-            for (int katoms = 1; katoms <= 2; katoms++) {
-                if (katoms == 2 && k_blocks < 2) continue;
-                const int stages = std::min(MAX_STAGES, budget / (atom_bytes * katoms));
-                if (stages < 3 && !(katoms == 1 && stages == 2)) continue;
-                const double t_stage = std::max(katoms * 4.0 * (pair ? 2 : 1) * instr + 320.0, 2200.0 / stages);
-                const double mainloop = std::ceil((double)k_blocks / katoms) * t_stage;
-                const double epi = (pair ? 2 : 1) * (bn / 32.0) * 350.0 / 2.0 + 600.0;
-                const double unit = std::max(mainloop, epi) + 1500.0;
-                const double cost = (double)waves * unit;
-                if (cost < best_cost * 0.999) {
-                    best_cost = cost;
-                    best = {bn, pair, katoms};
-                }
-            }
-        }
+struct PlanShape {
+    long long tiles_n, units_m, tiles, units;
+    int kb_per, atom_bytes, stage_bytes, stages, n_stg;
+};
+
+// Derived sizes of a plan; false if the plan cannot run (TMEM columns, shared memory, counters).
+static bool plan_shape(const Prepared& q, const Plan& pl, PlanShape& ps) {
+    const KParams& p = q.p;
+    if (pl.bn < 16 || pl.bn > 256 || pl.bn % q.step) return false;
+    if (pl.pair && p.tiles_m < 2) return false;
+    if (pl.acc1 != ((pl.pair && pl.bn > 128) ? 1 : 0)) return false;
+    if (pl.ksplit && (pl.pair || pl.bn > 128 || pl.splitk > 1)) return false;
+    ps.tiles_n = (p.N + pl.bn - 1) / pl.bn;
+    ps.units_m = pl.pair ? (p.tiles_m + 1) / 2 : p.tiles_m;
+    ps.tiles = ps.units_m * ps.tiles_n * q.batch;
+    ps.units = ps.tiles * pl.splitk;
+    if (ps.units > 0x7FFFFFFFll) return false;
+    ps.kb_per = (p.k_blocks + pl.splitk - 1) / pl.splitk;
+    if (pl.splitk > 1) {
+        if (pl.bn % 32 || (long long)(pl.splitk - 1) * ps.kb_per >= p.k_blocks) return false;  // no empty split
+        if (ps.tiles * 2 > SK_CNT_INTS) return false;
     }
-    return best;
+    ps.n_stg = 2 * pl.nbuf;
+    ps.atom_bytes = (pl.pair ? 2 : 1) * A_STAGE_BYTES + pl.bn * KBYTES;
+    if (pl.katoms == 2 && ps.kb_per < 2) return false;
+    ps.stage_bytes = ps.atom_bytes * pl.katoms;
+    ps.stages = std::min(MAX_STAGES, smem_budget_for(ps.n_stg) / ps.stage_bytes);
+    if (ps.stages < 2) return false;
+    return true;
 }
 
-rten_status launch_umma_gemm(rten_ctx* ctx, const GemmLaunch& L) {
+// Cost model in SM clocks.  Constants measured with the in-kernel trace (tools/trace_probe.py,
+// profiles/r01_trace_pipeline.txt) and from whole-layer timings:
+//   * the operand stream L2 -> shared memory is the first limit: ~7400 B/clk for the whole chip (all SMs loading),
+//     at most ~64 B/clk for one SM -> a K block of `atom_bytes` cannot take less than atom_bytes / bw;
+//   * the tensor pipe needs bn/2 clk per 128 x bn x 32-byte MMA, the elected thread ~42 clk to issue it;
+//   * every pipeline stage costs the issuing warp a fixed ~320 clk (barrier wait, fence, descriptors, commit);
+//   * a stage cannot complete faster than TMA latency (~2300 clk under load) / stages in flight;
+//   * the epilogue (~350 clk per 32-column chunk, two warp groups) overlaps the next main loop unless acc1.
+static double plan_cost(const Prepared& q, const Plan& pl, const PlanShape& ps, int num_sms) {
+    const double active = (double)std::min<long long>(ps.units, num_sms);
+    const double waves = std::ceil((double)ps.units / num_sms);
+    const double bw = std::min(64.0, 7400.0 / active);
+    const double mmas = 4.0 * (pl.pair ? 2 : 1);
+    const double t_kb = std::max(mmas * std::max(42.0, pl.bn / 2.0), ps.atom_bytes / bw);
+    double t_stage = std::max(pl.katoms * t_kb, 320.0 + pl.katoms * mmas * 42.0);
+    t_stage = std::max(t_stage, 2300.0 / ps.stages);
+    const double mainloop = std::ceil((double)ps.kb_per / pl.katoms) * t_stage;
+    const double epi = (pl.pair ? 2 : 1) * (pl.bn / 32.0) * 350.0 / 2.0 + 600.0;
+    double unit = pl.acc1 ? mainloop + epi + 1000.0 : std::max(mainloop, epi) + 1500.0;
+    double cost = waves * unit + 2500.0;
+    if (pl.splitk > 1) cost += epi * (1.0 + 0.25 * pl.splitk) + 1500.0;  // publish + the owner's reduction
+    if (pl.splitk > 1 && q.res_tma) cost += 2.0 * epi;                    // residual through the generic epilogue
+    return cost;
+}
+
+static void enumerate_plans(const Prepared& q, int num_sms, std::vector<std::pair<double, Plan>>& out) {
+    const KParams& p = q.p;
+    const int nmax = (p.N + q.step - 1) / q.step * q.step;
+    static const int splits[] = {1, 2, 3, 4, 5, 6, 8, 10, 12, 16};
+    for (int pair = 0; pair <= 1; pair++)
+        for (int bn = q.step; bn <= 256; bn += q.step) {
+            if (bn > nmax && bn != q.step) break;
+            for (int katoms = 1; katoms <= 2; katoms++)
+                for (int sk : splits) {
+                    Plan pl;
+                    pl.bn = bn;
+                    pl.pair = pair;
+                    pl.katoms = katoms;
+                    pl.splitk = sk;
+                    pl.acc1 = (pair && bn > 128) ? 1 : 0;
+                    if (sk > 1 && p.k_blocks / sk < 4) continue;
+                    pl.ksplit = (!pair && bn <= 128 && sk == 1 && !getenv("RTEN_B200_NO_KSPLIT")) ? 1 : 0;
+                    const int kb_per = (p.k_blocks + sk - 1) / sk;
+                    pl.nbuf = pl.acc1 ? 1 : ((q.res_tma || kb_per < 24) ? 2 : 1);
+                    PlanShape ps;
+                    if (!plan_shape(q, pl, ps)) continue;
+                    if (sk > 1 && ps.tiles >= 2 * num_sms) continue;  // enough parallelism without splitting K
+                    if (ps.stages < 3 && !(katoms == 1 && ps.stages == 2)) continue;
+                    out.emplace_back(plan_cost(q, pl, ps, num_sms), pl);
+                }
+        }
+    std::sort(out.begin(), out.end(), [](const std::pair<double, Plan>& x, const std::pair<double, Plan>& y) {
+        return x.first < y.first;
+    });
+}
+
+static rten_status prepare_launch(rten_ctx* ctx, const GemmLaunch& L, Prepared& q) {
     const int esize = L.kind == 0 ? 4 : 1;
     const int kelems = KBYTES / esize;
     if (!tma_compatible(L.a, esize, 4) || !tma_compatible(L.b, esize, 4)) return RTEN_ERR_UNSUPPORTED_VALUE;
     if (L.M <= 0 || L.N <= 0 || L.K <= 0) return RTEN_ERR_UNSUPPORTED_VALUE;
-
-    KParams p;
+    q.esize = esize;
+    q.kelems = kelems;
+    KParams& p = q.p;
     memset(&p, 0, sizeof(p));
     p.M = L.M;
     p.N = L.N;
@@ -796,9 +940,9 @@ rten_status launch_umma_gemm(rten_ctx* ctx, const GemmLaunch& L) {
     p.conv = L.conv;
     p.epi = L.epi;
     p.trace = reinterpret_cast<long long*>(ctx->trace);
-    uint32_t abox[4], aes[4] = {1, 1, 1, 1}, bbox[4], bes[4] = {1, 1, 1, 1};
-    long long tiles_m_total;
-    uint32_t a_rows;
+    p.c_blocks = 1;
+    p.kw = 1;
+    for (int i = 0; i < 4; i++) q.aes[i] = 1;
     if (L.conv) {
         const ConvGeom& g = L.g;
         pick_conv_tile(g, p.tw, p.th, p.tb);
@@ -819,136 +963,147 @@ rten_status launch_umma_gemm(rten_ctx* ctx, const GemmLaunch& L) {
         p.c_blocks = (g.C + kelems - 1) / kelems;
         p.k_blocks = g.kh * g.kw * p.c_blocks;
         p.z0 = p.z1 = 1;
-        abox[0] = kelems;
-        abox[1] = p.tw * g.sx;
-        abox[2] = p.th * g.sy;
-        abox[3] = p.tb;
-        aes[1] = g.sx;
-        aes[2] = g.sy;
-        a_rows = p.tw * p.th * p.tb;
-        tiles_m_total = p.tiles_m;
+        q.abox[0] = kelems;
+        q.abox[1] = p.tw * g.sx;
+        q.abox[2] = p.th * g.sy;
+        q.abox[3] = p.tb;
+        q.aes[1] = g.sx;
+        q.aes[2] = g.sy;
+        q.a_rows = p.tw * p.th * p.tb;
+        q.batch = 1;
     } else {
         p.tiles_m = (L.M + BM - 1) / BM;
         p.k_blocks = (L.K + kelems - 1) / kelems;
-        abox[0] = kelems;
-        abox[1] = BM;
-        abox[2] = 1;
-        abox[3] = 1;
-        a_rows = BM;
-        tiles_m_total = (long long)p.tiles_m * L.z0 * L.z1;
+        q.abox[0] = kelems;
+        q.abox[1] = BM;
+        q.abox[2] = 1;
+        q.abox[3] = 1;
+        q.a_rows = BM;
+        q.batch = (long long)L.z0 * L.z1;
         p.a_bcast0 = (L.a.dims[2] == 1 && L.z0 > 1) ? 1 : 0;
         p.a_bcast1 = (L.a.dims[3] == 1 && L.z1 > 1) ? 1 : 0;
         p.b_bcast0 = (L.b.dims[2] == 1 && L.z0 > 1) ? 1 : 0;
         p.b_bcast1 = (L.b.dims[3] == 1 && L.z1 > 1) ? 1 : 0;
     }
     // ---- output path: TMA store needs contiguous 4-byte rows at 16-byte aligned pitches
-    OperandDesc od, ord;
-    uint32_t dbox[4] = {32, 1, 1, 1}, des[4] = {1, 1, 1, 1};
-    {
-        const EpilogueDesc& e = L.epi;
-        od.base = e.d;
-        od.dims[0] = L.N;
-        od.strides[0] = 1;
-        if (L.conv) {
-            od.dims[1] = L.g.OW;
-            od.dims[2] = L.g.OH;
-            od.dims[3] = L.g.B;
-            od.strides[1] = e.s_z1;
-            od.strides[2] = e.s_row;
-            od.strides[3] = e.s_z0;
-            dbox[1] = p.tw;
-            dbox[2] = p.th;
-            dbox[3] = p.tb;
-        } else {
-            od.dims[1] = L.M;
-            od.dims[2] = L.z0;
-            od.dims[3] = L.z1;
-            od.strides[1] = e.s_row;
-            od.strides[2] = e.s_z0;
-            od.strides[3] = e.s_z1;
-            dbox[1] = BM;
-        }
-        p.tma_store = (e.s_col == 1 && L.N >= 4 && tma_compatible(od, 4, 4)) ? 1 : 0;
-        if (getenv("RTEN_B200_NO_TMA_STORE")) p.tma_store = 0;
-        // residual prefetched by TMA: same geometry as the output, own strides (fast-path epilogue only)
-        ord = od;
-        ord.base = e.r;
-        if (L.conv) {
-            ord.strides[1] = e.r_z1;
-            ord.strides[2] = e.r_row;
-            ord.strides[3] = e.r_z0;
-        } else {
-            ord.strides[1] = e.r_row;
-            ord.strides[2] = e.r_z0;
-            ord.strides[3] = e.r_z1;
-        }
-        p.res_tma = (p.tma_store && L.kind == 0 && e.r && e.r_col == 1 && e.act <= 1 && (L.N % 32) == 0 &&
-                     (e.bias_kind != 1 || (reinterpret_cast<uintptr_t>(e.bias) & 15) == 0) && tma_compatible(ord, 4, 4))
-                        ? 1
-                        : 0;
-        // a broadcast residual (Gemm's C) has zero strides on real dims: keep the register path for it
-        for (int i = 1; i < 4; i++)
-            if (ord.dims[i] > 1 && ord.strides[i] == 0) p.res_tma = 0;
-        if (getenv("RTEN_B200_NO_RES_TMA")) p.res_tma = 0;
-        p.res_tx_bytes = a_rows * KBYTES;
+    OperandDesc& od = q.od;
+    OperandDesc& ord = q.ord;
+    q.dbox[0] = 32;
+    q.dbox[1] = q.dbox[2] = q.dbox[3] = 1;
+    const EpilogueDesc& e = L.epi;
+    od.base = e.d;
+    od.dims[0] = L.N;
+    od.strides[0] = 1;
+    if (L.conv) {
+        od.dims[1] = L.g.OW;
+        od.dims[2] = L.g.OH;
+        od.dims[3] = L.g.B;
+        od.strides[1] = e.s_z1;
+        od.strides[2] = e.s_row;
+        od.strides[3] = e.s_z0;
+        q.dbox[1] = p.tw;
+        q.dbox[2] = p.th;
+        q.dbox[3] = p.tb;
+    } else {
+        od.dims[1] = L.M;
+        od.dims[2] = L.z0;
+        od.dims[3] = L.z1;
+        od.strides[1] = e.s_row;
+        od.strides[2] = e.s_z0;
+        od.strides[3] = e.s_z1;
+        q.dbox[1] = BM;
     }
-    // staging ring per epilogue group: 2 buffers (1 store in flight), 3 with the residual prefetch (load + compute +
-    // store overlap) when at least 3 pipeline stages of the widest tile still fit
-    // main-loop dominated launches keep shared memory for pipeline stages (one staging buffer per group)
-    p.nbuf = (p.res_tma || p.k_blocks < 24) ? 2 : 1;
-    if (const char* f = getenv("RTEN_B200_NBUF")) p.nbuf = std::max(p.res_tma ? 2 : 1, std::min(4, atoi(f)));
+    q.tma_store = (e.s_col == 1 && L.N >= 4 && tma_compatible(od, 4, 4)) ? 1 : 0;
+    if (getenv("RTEN_B200_NO_TMA_STORE")) q.tma_store = 0;
+    // residual prefetched by TMA: same geometry as the output, own strides (fast-path epilogue only)
+    ord = od;
+    ord.base = e.r;
+    if (L.conv) {
+        ord.strides[1] = e.r_z1;
+        ord.strides[2] = e.r_row;
+        ord.strides[3] = e.r_z0;
+    } else {
+        ord.strides[1] = e.r_row;
+        ord.strides[2] = e.r_z0;
+        ord.strides[3] = e.r_z1;
+    }
+    q.res_tma = (q.tma_store && L.kind == 0 && e.r && e.r_col == 1 && e.act <= 1 && (L.N % 32) == 0 &&
+                 (e.bias_kind != 1 || (reinterpret_cast<uintptr_t>(e.bias) & 15) == 0) && tma_compatible(ord, 4, 4))
+                    ? 1
+                    : 0;
+    // a broadcast residual (Gemm's C) has zero strides on real dims: keep the register path for it
+    for (int i = 1; i < 4; i++)
+        if (ord.dims[i] > 1 && ord.strides[i] == 0) q.res_tma = 0;
+    if (getenv("RTEN_B200_NO_RES_TMA")) q.res_tma = 0;
+    p.res_tx_bytes = q.a_rows * KBYTES;
+    q.step = q.tma_store ? 32 : 16;
+    return RTEN_OK;
+}
+
+static rten_status launch_plan(rten_ctx* ctx, const GemmLaunch& L, const Prepared& q, const Plan& pl, bool verbose) {
+    PlanShape ps;
+    if (!plan_shape(q, pl, ps)) return RTEN_ERR_UNSUPPORTED_VALUE;
+    KParams p = q.p;
+    p.bn = pl.bn;
+    p.pair = pl.pair;
+    p.katoms = pl.katoms;
+    p.ksplit = pl.ksplit;
+    p.splitk = pl.splitk;
+    p.acc1 = pl.acc1;
+    p.nbuf = pl.nbuf;
+    p.tma_store = q.tma_store;
+    p.res_tma = (q.res_tma && pl.splitk == 1) ? 1 : 0;
+    if (p.res_tma && p.nbuf < 2) p.nbuf = 2;
+    p.kb_per = ps.kb_per;
+    p.tiles_n = (int)ps.tiles_n;
+    p.tiles_total = (int)ps.tiles;
+    p.units_total = (int)ps.units;
     const int n_stg = 2 * p.nbuf;
-    {
-        const long long batch = L.conv ? 1 : (long long)L.z0 * L.z1;
-        TileChoice tcz = pick_tile(L.N, p.tiles_m, batch, p.k_blocks, ctx->num_sms, p.tma_store ? 32 : 16, n_stg);
-        if (const char* f = getenv("RTEN_B200_FORCE_BN")) tcz.bn = atoi(f);
-        if (const char* f = getenv("RTEN_B200_FORCE_PAIR")) tcz.pair = atoi(f) && tcz.bn <= 128 && p.tiles_m >= 2;
-        if (const char* f = getenv("RTEN_B200_FORCE_KATOMS")) tcz.katoms = atoi(f) == 2 ? 2 : 1;
-        p.bn = tcz.bn;
-        p.pair = tcz.pair;
-        p.katoms = tcz.katoms;
-        p.ksplit = (!p.pair && p.bn <= 128 && !getenv("RTEN_B200_NO_KSPLIT")) ? 1 : 0;
-        tiles_m_total = (p.pair ? (p.tiles_m + 1) / 2 : p.tiles_m) * batch;
-    }
-    p.tiles_n = (L.N + p.bn - 1) / p.bn;
-    long long tt = tiles_m_total * p.tiles_n;
-    if (tt > 0x7FFFFFFFll) return RTEN_ERR_UNSUPPORTED_VALUE;
-    p.tiles_total = (int)tt;
-    bbox[0] = kelems;
-    bbox[1] = p.bn;
-    bbox[2] = 1;
-    bbox[3] = 1;
-    p.atom_bytes = (p.pair ? 2 : 1) * A_STAGE_BYTES + p.bn * KBYTES;
-    if (p.katoms == 2 && (smem_budget_for(n_stg) / (int)(2 * p.atom_bytes) < 2 || p.k_blocks < 2)) p.katoms = 1;
-    p.stage_bytes = p.atom_bytes * p.katoms;
-    p.tx_bytes = (p.pair ? 2 : 1) * a_rows * KBYTES + p.bn * KBYTES;  // per 128-byte K block
-    const int smem_budget = smem_budget_for(n_stg);
-    p.stages = std::min(MAX_STAGES, smem_budget / (int)p.stage_bytes);
+    p.atom_bytes = ps.atom_bytes;
+    p.stage_bytes = ps.stage_bytes;
+    p.tx_bytes = (p.pair ? 2 : 1) * q.a_rows * KBYTES + p.bn * KBYTES;  // per 128-byte K block
+    p.stages = std::min(MAX_STAGES, smem_budget_for(n_stg) / (int)p.stage_bytes);
     if (p.stages < 2) return RTEN_ERR_UNSUPPORTED_VALUE;
     if (L.kind == 0)
         p.idesc = make_idesc(1 /*F32*/, 2 /*TF32*/, 2, BM, p.bn);
     else
         p.idesc = make_idesc(2 /*S32*/, L.a_signed ? 1 : 0, L.b_signed ? 1 : 0, BM, p.bn);
+    if (p.splitk > 1) {
+        if (!ctx->sk_counters) {
+            cudaError_t ce = cudaMalloc(&ctx->sk_counters, SK_CNT_INTS * sizeof(int));
+            if (ce != cudaSuccess) return fail_cuda(ctx, ce, "split-K counters");
+            ce = cudaMemset(ctx->sk_counters, 0, SK_CNT_INTS * sizeof(int));
+            if (ce != cudaSuccess) return fail_cuda(ctx, ce, "split-K counters");
+        }
+        void* ws = nullptr;
+        const size_t ws_bytes = (size_t)ps.tiles * 2 * p.splitk * (p.bn / 32) * 4096 * 4;
+        RTB_TRY(temp_alloc(ctx, ws_bytes, &ws));
+        p.sk_ws = reinterpret_cast<uint32_t*>(ws);
+        p.sk_cnt = reinterpret_cast<int*>(ctx->sk_counters);
+    }
 
+    uint32_t bbox[4] = {(uint32_t)q.kelems, (uint32_t)p.bn, 1, 1}, bes[4] = {1, 1, 1, 1}, des[4] = {1, 1, 1, 1};
     CUtensorMap map_a, map_b;
-    if (!encode_map(ctx, &map_a, L.a, esize, L.kind == 0, abox, aes)) return RTEN_ERR_UNSUPPORTED_VALUE;
-    if (!encode_map(ctx, &map_b, L.b, esize, L.kind == 0, bbox, bes)) return RTEN_ERR_UNSUPPORTED_VALUE;
+    if (!encode_map(ctx, &map_a, L.a, q.esize, L.kind == 0, q.abox, q.aes)) return RTEN_ERR_UNSUPPORTED_VALUE;
+    if (!encode_map(ctx, &map_b, L.b, q.esize, L.kind == 0, bbox, bes)) return RTEN_ERR_UNSUPPORTED_VALUE;
     CUtensorMap map_d = map_a, map_r = map_a;
-    if (p.tma_store && !encode_map(ctx, &map_d, od, 4, true, dbox, des)) {
+    if (p.tma_store && !encode_map(ctx, &map_d, q.od, 4, true, q.dbox, des)) {
+        if (p.bn % 32 == 0 && false) return RTEN_ERR_UNSUPPORTED_VALUE;
         p.tma_store = 0;  // direct stores still work for any bn that is a multiple of 16
         p.res_tma = 0;
         map_d = map_a;
     }
-    if (p.res_tma && !encode_map(ctx, &map_r, ord, 4, true, dbox, des)) {
+    if (p.res_tma && !encode_map(ctx, &map_r, q.ord, 4, true, q.dbox, des)) {
         p.res_tma = 0;
         map_r = map_a;
     }
 
-    if (getenv("RTEN_B200_VERBOSE"))
-        fprintf(stderr, "[umma_gemm] kind=%d conv=%d M=%d N=%d K=%d kb=%d tiles_m=%d bn=%d pair=%d ksplit=%d katoms=%d units=%d stages=%d tma_store=%d res_tma=%d nbuf=%d box=%dx%dx%d\n",
-                L.kind, L.conv, L.M, L.N, L.K, p.k_blocks, p.tiles_m, p.bn, p.pair, p.ksplit, p.katoms, p.tiles_total, p.stages, p.tma_store, p.res_tma, p.nbuf, p.tw, p.th, p.tb);
+    if (verbose)
+        fprintf(stderr, "[umma_gemm] kind=%d conv=%d M=%d N=%d K=%d kb=%d tiles_m=%d bn=%d pair=%d ksplit=%d katoms=%d splitk=%d acc1=%d units=%d stages=%d tma_store=%d res_tma=%d nbuf=%d box=%dx%dx%d\n",
+                L.kind, L.conv, L.M, L.N, L.K, p.k_blocks, p.tiles_m, p.bn, p.pair, p.ksplit, p.katoms, p.splitk, p.acc1,
+                p.units_total, p.stages, p.tma_store, p.res_tma, p.nbuf, p.tw, p.th, p.tb);
     const size_t smem_bytes = (size_t)p.stages * p.stage_bytes + n_stg * STG_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-    const int grid = std::min(p.tiles_total, ctx->num_sms);
+    const int grid = std::min(p.units_total, ctx->num_sms);
     cudaError_t e;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -983,6 +1138,102 @@ rten_status launch_umma_gemm(rten_ctx* ctx, const GemmLaunch& L) {
     if (e != cudaSuccess) return fail_cuda(ctx, e, "umma_gemm launch");
     count_launch(ctx);
     return RTEN_OK;
+}
+
+// Problem signature for the autotune cache: everything that changes which plan is fastest.
+static std::vector<long long> tune_key(const GemmLaunch& L, const Prepared& q) {
+    const EpilogueDesc& e = L.epi;
+    std::vector<long long> k = {L.kind, L.conv, L.M, L.N, L.K, L.z0, L.z1, q.tma_store, q.res_tma, e.act, e.bias_kind,
+                                e.r != nullptr, e.za != nullptr, e.zb != nullptr, e.scale != nullptr,
+                                L.a.strides[1], L.b.strides[1]};
+    if (L.conv) {
+        const ConvGeom& g = L.g;
+        for (long long v : {g.B, g.H, g.W, g.C, g.OH, g.OW, g.kh, g.kw, g.sy, g.sx, g.dy, g.dx, g.pt, g.pl}) k.push_back(v);
+    }
+    return k;
+}
+
+static Plan plan_from_array(const std::array<int, 8>& a) {
+    Plan pl;
+    pl.bn = a[0];
+    pl.pair = a[1];
+    pl.katoms = a[2];
+    pl.ksplit = a[3];
+    pl.splitk = a[4];
+    pl.nbuf = a[5];
+    pl.acc1 = a[6];
+    return pl;
+}
+
+rten_status launch_umma_gemm(rten_ctx* ctx, const GemmLaunch& L) {
+    Prepared q;
+    RTB_TRY(prepare_launch(ctx, L, q));
+    const bool verbose = getenv("RTEN_B200_VERBOSE") != nullptr;
+    std::vector<std::pair<double, Plan>> cands;
+    enumerate_plans(q, ctx->num_sms, cands);
+    if (cands.empty()) return RTEN_ERR_UNSUPPORTED_VALUE;
+    Plan plan = cands[0].second;
+
+    const bool forced = getenv("RTEN_B200_FORCE_BN") || getenv("RTEN_B200_FORCE_PAIR") || getenv("RTEN_B200_FORCE_KATOMS") ||
+                        getenv("RTEN_B200_FORCE_SPLITK");
+    if (forced) {
+        // debugging / sweeps: the best-ranked candidate that matches every forced field
+        const char* fb = getenv("RTEN_B200_FORCE_BN");
+        const char* fp = getenv("RTEN_B200_FORCE_PAIR");
+        const char* fk = getenv("RTEN_B200_FORCE_KATOMS");
+        const char* fs = getenv("RTEN_B200_FORCE_SPLITK");
+        for (const auto& c : cands) {
+            const Plan& x = c.second;
+            if (fb && x.bn != atoi(fb)) continue;
+            if (fp && x.pair != (atoi(fp) ? 1 : 0)) continue;
+            if (fk && x.katoms != atoi(fk)) continue;
+            if (fs && x.splitk != atoi(fs)) continue;
+            plan = x;
+            break;
+        }
+    } else if (ctx->autotune) {
+        const std::vector<long long> key = tune_key(L, q);
+        auto it = ctx->tune_cache.find(key);
+        if (it != ctx->tune_cache.end()) {
+            plan = plan_from_array(it->second);
+        } else {
+            cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+            cudaStreamIsCapturing(ctx->stream, &cs);
+            // re-running the launch must be idempotent: the output may not alias the residual
+            const bool safe = !ctx->capturing && cs == cudaStreamCaptureStatusNone && !ctx->trace &&
+                              (L.epi.r == nullptr || (const void*)L.epi.r != (const void*)L.epi.d);
+            if (safe) {
+                cudaEvent_t e0, e1;
+                cudaEventCreate(&e0);
+                cudaEventCreate(&e1);
+                const size_t ncand = std::min<size_t>(cands.size(), 20);
+                double best_ms = 1e30;
+                const int reps = 3;
+                for (size_t i = 0; i < ncand; i++) {
+                    const Plan& x = cands[i].second;
+                    if (launch_plan(ctx, L, q, x, false) != RTEN_OK) continue;  // warm-up (also validates the plan)
+                    cudaEventRecord(e0, ctx->stream);
+                    bool ok = true;
+                    for (int r = 0; r < reps && ok; r++) ok = launch_plan(ctx, L, q, x, false) == RTEN_OK;
+                    cudaEventRecord(e1, ctx->stream);
+                    if (cudaEventSynchronize(e1) != cudaSuccess || !ok) continue;
+                    float ms = 0.f;
+                    cudaEventElapsedTime(&ms, e0, e1);
+                    if (verbose)
+                        fprintf(stderr, "[autotune] bn=%d pair=%d katoms=%d splitk=%d model=%.0f -> %.2f us\n", x.bn, x.pair,
+                                x.katoms, x.splitk, cands[i].first, ms * 1e3 / reps);
+                    if (ms < best_ms) {
+                        best_ms = ms;
+                        plan = x;
+                    }
+                }
+                cudaEventDestroy(e0);
+                cudaEventDestroy(e1);
+                ctx->tune_cache[key] = {plan.bn, plan.pair, plan.katoms, plan.ksplit, plan.splitk, plan.nbuf, plan.acc1, 0};
+            }
+        }
+    }
+    return launch_plan(ctx, L, q, plan, verbose);
 }
 
 }  // namespace rtb

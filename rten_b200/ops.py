@@ -67,6 +67,10 @@ class Context:
     def sync(self):
         self.check(self.lib.rten_b200_sync(self.handle))
 
+    def set_autotune(self, enable: bool = True):
+        """Time candidate launch plans the first time each MatMul / Conv problem is seen (outside graph capture)."""
+        self.check(self.lib.rten_b200_set_autotune(self.handle, 1 if enable else 0))
+
     @property
     def launches(self) -> int:
         return int(self.lib.rten_b200_launch_count(self.handle))

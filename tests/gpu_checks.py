@@ -325,6 +325,52 @@ def check_matmul_integer(rt, oracle):
 
 
 # ------------------------------------------------------------------------------------------
+def check_plans(rt, oracle):
+    """Every launch-plan family (pair, two K atoms, split-K with the last-arriver reduction, the single 512-column
+    accumulator stage of 256 x 256 tiles) must give the same answers: forced through the debug environment knobs,
+    then chosen by the autotuner."""
+    import os
+    ctx = rt.Context(0)
+    r = oracle.XorShiftRng(99)
+    keys = ("RTEN_B200_FORCE_BN", "RTEN_B200_FORCE_PAIR", "RTEN_B200_FORCE_KATOMS", "RTEN_B200_FORCE_SPLITK")
+    plans = [dict(), dict(BN=64, PAIR=1), dict(BN=128, PAIR=0, KATOMS=2), dict(BN=256, PAIR=1), dict(BN=128, PAIR=1, SPLITK=2),
+             dict(BN=64, PAIR=0, SPLITK=3), dict(BN=256, PAIR=1, SPLITK=2), dict(BN=96, PAIR=0, SPLITK=4, KATOMS=2)]
+    a8 = r.u8((300, 2048))
+    b8 = r.i8((2048, 512))
+    az, bz = r.u8((300,)), r.i8((512,))
+    exp8 = oracle.matmul_integer(a8, b8, az, bz)
+    sc = r.uniform((512,), 0.001, 0.1)
+    exp8f = oracle.matmul_integer_to_float(a8, b8, az, bz, sc)
+    worst = 0.0
+    try:
+        for pl in plans:
+            for k in keys:
+                os.environ.pop(k, None)
+            for k, v in pl.items():
+                os.environ["RTEN_B200_FORCE_" + k] = str(v)
+            tag = f"plan {pl}"
+            worst = max(worst, _matmul_case(rt, oracle, ctx, (384, 1024), (1024, 512), bias=True, prepack=True, seed=5))
+            worst = max(worst, _matmul_case(rt, oracle, ctx, (3, 130, 520), (520, 300), seed=6))
+            assert_bit_exact(rt.MatMulInteger().run(ctx, a8, b8, az, bz).numpy(), exp8, f"MatMulInteger {tag}")
+            assert_bit_exact(rt.MatMulIntegerToFloat().run(ctx, a8, b8, az, bz, sc).numpy(), exp8f, f"MatMulIntegerToFloat {tag}")
+            worst = max(worst, _conv_case(rt, oracle, ctx, (4, 256, 14, 14), (256, 256, 3, 3), pads=(1, 1, 1, 1), cl=True, prepack=True, act=1))
+            worst = max(worst, _conv_case(rt, oracle, ctx, (8, 512, 7, 7), (512, 512, 3, 3), pads=(1, 1, 1, 1), cl=True, residual=True, act=1))
+            worst = max(worst, _conv_case(rt, oracle, ctx, (2, 64, 20, 20), (96, 64, 1, 1), cl=False))
+    finally:
+        for k in keys:
+            os.environ.pop(k, None)
+    # autotuned plans: first call measures, second call replays the cached plan
+    ctx2 = rt.Context(0)
+    ctx2.set_autotune(True)
+    for _ in range(2):
+        worst = max(worst, _matmul_case(rt, oracle, ctx2, (384, 1024), (1024, 512), bias=True, prepack=True, seed=5))
+        assert_bit_exact(rt.MatMulInteger().run(ctx2, a8, b8, az, bz).numpy(), exp8, "MatMulInteger autotuned")
+        worst = max(worst, _conv_case(rt, oracle, ctx2, (8, 512, 7, 7), (512, 512, 3, 3), pads=(1, 1, 1, 1), cl=True, prepack=True, act=1))
+        worst = max(worst, _conv_case(rt, oracle, ctx2, (8, 512, 7, 7), (512, 512, 3, 3), pads=(1, 1, 1, 1), cl=True, residual=True, act=1))
+    return f"worst err/bound {worst:.3f}"
+
+
+# ------------------------------------------------------------------------------------------
 def _conv_exact(x, w, bias, pads, groups, strides, dil):
     import torch
     import torch.nn.functional as F
@@ -521,5 +567,5 @@ ALL_CHECKS = [
     ("dql", check_dql), ("glue", check_glue), ("matmul_small", check_matmul_small), ("matmul_shapes", check_matmul_shapes),
     ("matmul_bert", check_matmul_bert), ("gemm_op", check_gemm_op), ("matmul_integer", check_matmul_integer),
     ("conv_basic", check_conv_basic), ("conv_stride", check_conv_stride), ("conv_more", check_conv_more),
-    ("conv_integer", check_conv_integer), ("resnet50_model", check_resnet50_model), ("bert_model", check_bert_model),
+    ("conv_integer", check_conv_integer), ("plans", check_plans), ("resnet50_model", check_resnet50_model), ("bert_model", check_bert_model),
 ]

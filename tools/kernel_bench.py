@@ -46,6 +46,8 @@ def main():
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     ctx = rt.Context(0, stream=stream.cuda_stream)
+    import os
+    ctx.set_autotune(os.environ.get("KB_AUTOTUNE", "1") != "0")
     global CTX
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     rows = []
