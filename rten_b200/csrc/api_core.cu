@@ -63,7 +63,7 @@ rten_status OpScope::in(const rten_tensor* t, rten_tensor* view) {
     const size_t bytes = (size_t)span * dtype_size(t->dtype);
     void* d = nullptr;
     RTB_TRY(temp_alloc(ctx, bytes ? bytes : 16, &d));
-    if (bytes) RTB_CUDA(ctx, cudaMemcpyAsync(d, t->data, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (bytes) RTB_CUDA(ctx, cudaMemcpyAsync(d, t->data, bytes, cudaMemcpyHostToDevice, rtb::launch_stream(ctx)));
     view->data = d;
     view->device = ctx->device;
     return RTEN_OK;
@@ -138,7 +138,7 @@ rten_status OpScope::finish(rten_status st) {
     if (st == RTEN_OK) {
         for (auto& cb : copybacks) {
             if (cb.bytes) {
-                cudaError_t e = cudaMemcpyAsync(cb.host, cb.dev, cb.bytes, cudaMemcpyDeviceToHost, ctx->stream);
+                cudaError_t e = cudaMemcpyAsync(cb.host, cb.dev, cb.bytes, cudaMemcpyDeviceToHost, rtb::launch_stream(ctx));
                 if (e != cudaSuccess) st = fail_cuda(ctx, e, "cudaMemcpyAsync(D2H)");
             }
         }
@@ -207,6 +207,7 @@ void rten_b200_ctx_destroy(rten_ctx* ctx) {
         for (void* p : kv.second) cudaFree(p);
     for (auto& kv : ctx->pool.live) cudaFree(kv.first);
     if (ctx->sk_counters) cudaFree(ctx->sk_counters);
+    seq_free(ctx);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -269,7 +270,7 @@ rten_status rten_b200_copy(rten_ctx* ctx, const rten_tensor* src, rten_tensor* d
         if (!bytes) return RTEN_OK;
         cudaMemcpyKind kind = src->device < 0 ? (dst->device < 0 ? cudaMemcpyHostToHost : cudaMemcpyHostToDevice)
                                               : (dst->device < 0 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice);
-        RTB_CUDA(ctx, cudaMemcpyAsync(dst->data, src->data, bytes, kind, ctx->stream));
+        RTB_CUDA(ctx, cudaMemcpyAsync(dst->data, src->data, bytes, kind, rtb::launch_stream(ctx)));
         if ((src->device < 0 || dst->device < 0) && !ctx->capturing) RTB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         return RTEN_OK;
     }
@@ -307,7 +308,7 @@ rten_status rten_b200_debug_trace(rten_ctx* ctx, int enable, int64_t* host_out_8
     }
     if (enable) {
         if (!ctx->trace) RTB_CUDA(ctx, cudaMalloc(&ctx->trace, bytes));
-        RTB_CUDA(ctx, cudaMemsetAsync(ctx->trace, 0, bytes, ctx->stream));
+        RTB_CUDA(ctx, cudaMemsetAsync(ctx->trace, 0, bytes, rtb::launch_stream(ctx)));
     } else if (ctx->trace) {
         cudaFree(ctx->trace);
         ctx->trace = nullptr;
@@ -328,6 +329,7 @@ rten_status rten_b200_graph_begin(rten_ctx* ctx) {
 rten_status rten_b200_graph_end(rten_ctx* ctx, rten_graph** out) {
     if (!ctx || !out) return RTEN_ERR_INVALID_VALUE;
     if (!ctx->capturing) return fail(ctx, RTEN_ERR_INVALID_VALUE, "no graph capture active");
+    rten_status fs = seq_flush(ctx);  // tensor-core launches still collected for a sequence kernel
     ctx->capturing = false;
     rten_graph* g = new rten_graph();
     cudaError_t e = cudaStreamEndCapture(ctx->stream, &g->graph);
@@ -336,6 +338,12 @@ rten_status rten_b200_graph_end(rten_ctx* ctx, rten_graph** out) {
         if (g->graph) cudaGraphDestroy(g->graph);
         delete g;
         return fail_cuda(ctx, e, "graph capture/instantiate");
+    }
+    if (fs != RTEN_OK) {
+        cudaGraphExecDestroy(g->exec);
+        cudaGraphDestroy(g->graph);
+        delete g;
+        return fs;
     }
     g->kernels = ctx->launches - ctx->capture_start_launches;
     ctx->launches = ctx->capture_start_launches;  // captured launches did not execute

@@ -225,7 +225,7 @@ rten_status matmul_core(OpScope& sc, MatMulArgs& A, rten_tensor* out) {
             dv.data = t;
             copy_out = true;
         }
-        RTB_CUDA(ctx, cudaMemsetAsync(dv.data, 0, (size_t)total * 4, ctx->stream));
+        RTB_CUDA(ctx, cudaMemsetAsync(dv.data, 0, (size_t)total * 4, rtb::launch_stream(ctx)));
         if (A.kind == 0 && L.epi.bias) {
             long long shp[2] = {total / N, N}, s0[2] = {N, 1}, sb[2] = {0, 1};
             RTB_TRY(launch_nd_add(ctx, (const float*)dv.data, L.epi.bias, (float*)dv.data, 2, shp, s0, sb, s0, 0));
@@ -958,7 +958,7 @@ rten_status rten_b200_prepack_b(rten_ctx* ctx, const rten_tensor* b, rten_packed
         p->ld = round_up(std::max<int64_t>(p->K, 1), 16 / es);
         st = pool_alloc(ctx, (size_t)std::max<int64_t>(p->N * p->ld, 1) * es, &p->data);
         if (st == RTEN_OK) {
-            RTB_CUDA(ctx, cudaMemsetAsync(p->data, 0, (size_t)std::max<int64_t>(p->N * p->ld, 1) * es, ctx->stream));
+            RTB_CUDA(ctx, cudaMemsetAsync(p->data, 0, (size_t)std::max<int64_t>(p->N * p->ld, 1) * es, rtb::launch_stream(ctx)));
             long long shape[2] = {p->N, p->K}, ss[2] = {bv.strides[1], bv.strides[0]}, ds[2] = {p->ld, 1};
             st = launch_nd_copy(ctx, es, bv.data, p->data, 2, shape, ss, ds);
         }
@@ -1402,11 +1402,11 @@ rten_status rten_b200_layer_norm(rten_ctx* ctx, const rten_tensor* x, const rten
         // NOTE: the reference's scalar-scale arm computes rstd = scale / sqrt(var+eps) and uses it directly; to
         // stay bit-identical we read the scalar(s) to the host (a tiny synchronous copy) instead of expanding.
         if (g_scalar) {
-            RTB_CUDA(ctx, cudaMemcpyAsync(&gs, gp, 4, cudaMemcpyDeviceToHost, ctx->stream));
+            RTB_CUDA(ctx, cudaMemcpyAsync(&gs, gp, 4, cudaMemcpyDeviceToHost, rtb::launch_stream(ctx)));
             gp = nullptr;
         }
         if (bias && b_scalar) {
-            RTB_CUDA(ctx, cudaMemcpyAsync(&bs, bp, 4, cudaMemcpyDeviceToHost, ctx->stream));
+            RTB_CUDA(ctx, cudaMemcpyAsync(&bs, bp, 4, cudaMemcpyDeviceToHost, rtb::launch_stream(ctx)));
             bp = nullptr;
         }
         if (g_scalar || (bias && b_scalar)) RTB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1544,8 +1544,8 @@ rten_status rten_b200_dynamic_quantize_linear(rten_ctx* ctx, const rten_tensor* 
         if (n == 0) {
             // quantize.rs:378-386: scale 1, zero point 0
             const float one = 1.0f;
-            RTB_CUDA(ctx, cudaMemcpyAsync(sv.data, &one, 4, cudaMemcpyHostToDevice, ctx->stream));
-            RTB_CUDA(ctx, cudaMemsetAsync(zv.data, 0, 1, ctx->stream));
+            RTB_CUDA(ctx, cudaMemcpyAsync(sv.data, &one, 4, cudaMemcpyHostToDevice, rtb::launch_stream(ctx)));
+            RTB_CUDA(ctx, cudaMemsetAsync(zv.data, 0, 1, rtb::launch_stream(ctx)));
         } else {
             int* mm = nullptr;
             st = temp_alloc(ctx, 8, (void**)&mm);

@@ -57,6 +57,9 @@ struct rten_ctx {
     void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled (driver entry point)
     void* sk_counters = nullptr;   // split-K arrival counters (zero between launches)
     bool autotune = false;         // time candidate launch plans on first sight of a problem (umma_gemm.cu)
+    void* seq_pending = nullptr;   // umma_gemm launches collected during graph capture (std::vector<PendingLaunch>*)
+    int seq_class = -1;            // kernel class (data kind, epilogue variant) of the pending launches
+    void* seq_gbar = nullptr;      // grid-barrier arrival counter of the sequence kernel
     std::map<std::vector<long long>, std::array<int, 8>> tune_cache;
 };
 
@@ -122,5 +125,14 @@ inline int64_t span_elems(const rten_tensor* t) {
 }
 
 inline void count_launch(rten_ctx* ctx, int n = 1) { ctx->launches += (uint64_t)n; }
+
+// Deferred tensor-core launches (graph capture batches them into sequence kernels, umma_gemm.cu) must be issued
+// before anything else is enqueued on the context stream: every other launch site asks for the stream through this.
+rten_status seq_flush(rten_ctx* ctx);
+void seq_free(rten_ctx* ctx);
+inline cudaStream_t launch_stream(rten_ctx* ctx) {
+    if (ctx->seq_pending) seq_flush(ctx);
+    return ctx->stream;
+}
 
 }  // namespace rtb

@@ -112,7 +112,7 @@ rten_status launch_softmax(rten_ctx* ctx, const float* x, float* y, long long ro
     p.mstride_last = mstride_last;
     const int wpb = 8;
     const long long blocks = (rows + wpb - 1) / wpb;
-    softmax_kernel<<<(unsigned)blocks, wpb * 32, 0, ctx->stream>>>(p);
+    softmax_kernel<<<(unsigned)blocks, wpb * 32, 0, launch_stream(ctx)>>>(p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail_cuda(ctx, e, "softmax launch");
     count_launch(ctx);
@@ -198,7 +198,7 @@ rten_status launch_layer_norm(rten_ctx* ctx, const float* x, float* y, long long
     LayerNormParams p{x, y, rows, n, gamma, gamma_scalar, beta, beta_scalar, eps};
     const int wpb = 8;
     const long long blocks = (rows + wpb - 1) / wpb;
-    layer_norm_kernel<<<(unsigned)blocks, wpb * 32, 0, ctx->stream>>>(p);
+    layer_norm_kernel<<<(unsigned)blocks, wpb * 32, 0, launch_stream(ctx)>>>(p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail_cuda(ctx, e, "layer_norm launch");
     count_launch(ctx);
@@ -273,7 +273,7 @@ rten_status launch_row_mean(rten_ctx* ctx, const float* x, float* y, long long r
                             long long s_outer, long long s_inner, long long kstride) {
     if (rows == 0) return RTEN_OK;
     if (s_inner == 1 && kstride != 1) {
-        row_mean_thread_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, ctx->stream>>>(x, y, rows, n, rows_inner, s_outer,
+        row_mean_thread_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, launch_stream(ctx)>>>(x, y, rows, n, rows_inner, s_outer,
                                                                                         s_inner, kstride);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return fail_cuda(ctx, e, "row_mean launch");
@@ -281,7 +281,7 @@ rten_status launch_row_mean(rten_ctx* ctx, const float* x, float* y, long long r
         return RTEN_OK;
     }
     const int wpb = 8;
-    row_mean_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, ctx->stream>>>(x, y, rows, n, rows_inner,
+    row_mean_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, launch_stream(ctx)>>>(x, y, rows, n, rows_inner,
                                                                                        s_outer, s_inner, kstride);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail_cuda(ctx, e, "row_mean launch");
@@ -333,10 +333,10 @@ rten_status launch_unary(rten_ctx* ctx, int op, const float* x, float* y, long l
     const int vec = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0 ? 1 : 0;
     const int grid = ew_grid(ctx, vec ? (n + 3) / 4 : n);
     switch (op) {
-        case UNARY_ERF: unary_kernel<UNARY_ERF><<<grid, 256, 0, ctx->stream>>>(x, y, n, vec); break;
-        case UNARY_GELU: unary_kernel<UNARY_GELU><<<grid, 256, 0, ctx->stream>>>(x, y, n, vec); break;
-        case UNARY_APPROX_GELU: unary_kernel<UNARY_APPROX_GELU><<<grid, 256, 0, ctx->stream>>>(x, y, n, vec); break;
-        case UNARY_RELU: unary_kernel<UNARY_RELU><<<grid, 256, 0, ctx->stream>>>(x, y, n, vec); break;
+        case UNARY_ERF: unary_kernel<UNARY_ERF><<<grid, 256, 0, launch_stream(ctx)>>>(x, y, n, vec); break;
+        case UNARY_GELU: unary_kernel<UNARY_GELU><<<grid, 256, 0, launch_stream(ctx)>>>(x, y, n, vec); break;
+        case UNARY_APPROX_GELU: unary_kernel<UNARY_APPROX_GELU><<<grid, 256, 0, launch_stream(ctx)>>>(x, y, n, vec); break;
+        case UNARY_RELU: unary_kernel<UNARY_RELU><<<grid, 256, 0, launch_stream(ctx)>>>(x, y, n, vec); break;
         default: return fail(ctx, RTEN_ERR_INVALID_VALUE, "unknown unary op");
     }
     cudaError_t e = cudaGetLastError();
@@ -431,9 +431,9 @@ rten_status launch_nd_copy(rten_ctx* ctx, int esize, const void* src, void* dst,
     if (p.n == 0) return RTEN_OK;
     const int grid = ew_grid(ctx, p.n);
     if (esize == 4)
-        nd_copy_kernel<uint32_t><<<grid, 256, 0, ctx->stream>>>((const uint32_t*)src, (uint32_t*)dst, p);
+        nd_copy_kernel<uint32_t><<<grid, 256, 0, launch_stream(ctx)>>>((const uint32_t*)src, (uint32_t*)dst, p);
     else if (esize == 1)
-        nd_copy_kernel<uint8_t><<<grid, 256, 0, ctx->stream>>>((const uint8_t*)src, (uint8_t*)dst, p);
+        nd_copy_kernel<uint8_t><<<grid, 256, 0, launch_stream(ctx)>>>((const uint8_t*)src, (uint8_t*)dst, p);
     else
         return fail(ctx, RTEN_ERR_UNSUPPORTED_TYPE, "unsupported element size");
     cudaError_t e = cudaGetLastError();
@@ -456,7 +456,7 @@ rten_status launch_nd_add(rten_ctx* ctx, const float* a, const float* b, float* 
         p.n *= shape[i];
     }
     if (p.n == 0) return RTEN_OK;
-    nd_add_kernel<<<ew_grid(ctx, p.n), 256, 0, ctx->stream>>>(a, b, d, p, relu);
+    nd_add_kernel<<<ew_grid(ctx, p.n), 256, 0, launch_stream(ctx)>>>(a, b, d, p, relu);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail_cuda(ctx, e, "nd_add launch");
     count_launch(ctx);
@@ -471,7 +471,7 @@ rten_status launch_add_flat(rten_ctx* ctx, const float* a, const float* b, float
         long long shape[1] = {n}, s1[1] = {1};
         return launch_nd_add(ctx, a, b, d, 1, shape, s1, s1, s1, relu);
     }
-    add_flat_kernel<<<ew_grid(ctx, (n + 3) / 4), 256, 0, ctx->stream>>>(a, b, d, n, relu);
+    add_flat_kernel<<<ew_grid(ctx, (n + 3) / 4), 256, 0, launch_stream(ctx)>>>(a, b, d, n, relu);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail_cuda(ctx, e, "add launch");
     count_launch(ctx);
@@ -578,10 +578,10 @@ dql_quantize_kernel(const float* __restrict__ x, uint8_t* __restrict__ y, long l
 }
 
 rten_status launch_minmax(rten_ctx* ctx, const float* x, long long n, int* mm) {
-    minmax_init_kernel<<<1, 1, 0, ctx->stream>>>(mm);
+    minmax_init_kernel<<<1, 1, 0, launch_stream(ctx)>>>(mm);
     count_launch(ctx);
     if (n > 0) {
-        minmax_kernel<<<ew_grid(ctx, (n + 3) / 4), 256, 0, ctx->stream>>>(x, n, mm);
+        minmax_kernel<<<ew_grid(ctx, (n + 3) / 4), 256, 0, launch_stream(ctx)>>>(x, n, mm);
         count_launch(ctx);
     }
     cudaError_t e = cudaGetLastError();
@@ -591,7 +591,7 @@ rten_status launch_minmax(rten_ctx* ctx, const float* x, long long n, int* mm) {
 
 rten_status launch_dql_quantize(rten_ctx* ctx, const float* x, uint8_t* y, long long n, const int* mm, float* scale_out,
                                 uint8_t* zp_out) {
-    dql_quantize_kernel<<<ew_grid(ctx, (n + 3) / 4), 256, 0, ctx->stream>>>(x, y, n, mm, scale_out, zp_out);
+    dql_quantize_kernel<<<ew_grid(ctx, (n + 3) / 4), 256, 0, launch_stream(ctx)>>>(x, y, n, mm, scale_out, zp_out);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail_cuda(ctx, e, "dql launch");
     count_launch(ctx);
@@ -618,7 +618,7 @@ rowsum8_kernel(const uint8_t* __restrict__ a, int is_signed, long long rows, int
 rten_status launch_rowsum8(rten_ctx* ctx, const void* a, int is_signed, long long rows, int K, long long ld, int* out) {
     if (rows == 0) return RTEN_OK;
     const int wpb = 8;
-    rowsum8_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, ctx->stream>>>((const uint8_t*)a, is_signed, rows,
+    rowsum8_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, launch_stream(ctx)>>>((const uint8_t*)a, is_signed, rows,
                                                                                       K, ld, out);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail_cuda(ctx, e, "rowsum launch");
@@ -634,7 +634,7 @@ __global__ void zp_to_i32_kernel(const uint8_t* zp, int is_signed, int n, long l
 
 rten_status launch_zp_to_i32(rten_ctx* ctx, const void* zp, int is_signed, int n, long long zs, int* out) {
     if (n == 0) return RTEN_OK;
-    zp_to_i32_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>((const uint8_t*)zp, is_signed, n, zs, out);
+    zp_to_i32_kernel<<<(n + 127) / 128, 128, 0, launch_stream(ctx)>>>((const uint8_t*)zp, is_signed, n, zs, out);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail_cuda(ctx, e, "zp_to_i32 launch");
     count_launch(ctx);
@@ -647,7 +647,7 @@ __global__ void fill8_kernel(uint8_t* p, long long n, uint8_t v) {
 }
 rten_status launch_fill8(rten_ctx* ctx, void* p, long long n, uint8_t v) {
     if (n == 0) return RTEN_OK;
-    fill8_kernel<<<ew_grid(ctx, n), 256, 0, ctx->stream>>>((uint8_t*)p, n, v);
+    fill8_kernel<<<ew_grid(ctx, n), 256, 0, launch_stream(ctx)>>>((uint8_t*)p, n, v);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail_cuda(ctx, e, "fill launch");
     count_launch(ctx);
@@ -665,7 +665,7 @@ cast_scale_kernel(const int* __restrict__ in, float* __restrict__ out, long long
 rten_status launch_cast_scale(rten_ctx* ctx, const int* in, float* out, long long n, int cols, const float* scale,
                               int scale_len) {
     if (n == 0) return RTEN_OK;
-    cast_scale_kernel<<<ew_grid(ctx, n), 256, 0, ctx->stream>>>(in, out, n, cols, scale, scale_len);
+    cast_scale_kernel<<<ew_grid(ctx, n), 256, 0, launch_stream(ctx)>>>(in, out, n, cols, scale, scale_len);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail_cuda(ctx, e, "cast_scale launch");
     count_launch(ctx);
@@ -709,9 +709,9 @@ rten_status launch_im2col(rten_ctx* ctx, int esize, const void* x, void* out, co
     if (total == 0) return RTEN_OK;
     if (esize == 4) {
         float pv = 0.0f;
-        im2col_kernel<float><<<ew_grid(ctx, total), 256, 0, ctx->stream>>>((const float*)x, (float*)out, p, pv);
+        im2col_kernel<float><<<ew_grid(ctx, total), 256, 0, launch_stream(ctx)>>>((const float*)x, (float*)out, p, pv);
     } else {
-        im2col_kernel<uint8_t><<<ew_grid(ctx, total), 256, 0, ctx->stream>>>((const uint8_t*)x, (uint8_t*)out, p,
+        im2col_kernel<uint8_t><<<ew_grid(ctx, total), 256, 0, launch_stream(ctx)>>>((const uint8_t*)x, (uint8_t*)out, p,
                                                                              (uint8_t)pad_value);
     }
     cudaError_t e = cudaGetLastError();
@@ -762,7 +762,7 @@ rten_status launch_smallc_pad(rten_ctx* ctx, const float* x, float* xp, int B, i
                               long long xs_b, long long xs_c, long long xs_h, long long xs_w) {
     const long long total = (long long)B * H * Wp;
     if (total == 0) return RTEN_OK;
-    smallc_pad_kernel<<<ew_grid(ctx, total), 256, 0, ctx->stream>>>(x, xp, B, C, H, W, Wp, pl, xs_b, xs_c, xs_h, xs_w);
+    smallc_pad_kernel<<<ew_grid(ctx, total), 256, 0, launch_stream(ctx)>>>(x, xp, B, C, H, W, Wp, pl, xs_b, xs_c, xs_h, xs_w);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail_cuda(ctx, e, "smallc_pad launch");
     count_launch(ctx);
@@ -773,7 +773,7 @@ rten_status launch_smallc_pack_w(rten_ctx* ctx, const float* w, float* wp, int O
                                  long long ws_c, long long ws_h, long long ws_w) {
     const int total = O * kh * 32;
     if (total == 0) return RTEN_OK;
-    smallc_pack_w_kernel<<<(total + 255) / 256, 256, 0, ctx->stream>>>(w, wp, O, C, kh, kw, ws_o, ws_c, ws_h, ws_w);
+    smallc_pack_w_kernel<<<(total + 255) / 256, 256, 0, launch_stream(ctx)>>>(w, wp, O, C, kh, kw, ws_o, ws_c, ws_h, ws_w);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail_cuda(ctx, e, "smallc_pack_w launch");
     count_launch(ctx);
@@ -858,9 +858,9 @@ rten_status launch_maxpool(rten_ctx* ctx, const float* x, float* y, const PoolPa
                      (p.xs_w % 4) == 0 && (p.ys_b % 4) == 0 && (p.ys_h % 4) == 0 && (p.ys_w % 4) == 0 &&
                      ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
     if (cl4)
-        maxpool_cl4_kernel<<<ew_grid(ctx, total / 4), 256, 0, ctx->stream>>>(x, y, p);
+        maxpool_cl4_kernel<<<ew_grid(ctx, total / 4), 256, 0, launch_stream(ctx)>>>(x, y, p);
     else
-        maxpool_kernel<<<ew_grid(ctx, total), 256, 0, ctx->stream>>>(x, y, p);
+        maxpool_kernel<<<ew_grid(ctx, total), 256, 0, launch_stream(ctx)>>>(x, y, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail_cuda(ctx, e, "maxpool launch");
     count_launch(ctx);
@@ -884,7 +884,7 @@ gather_rows_kernel(const float* __restrict__ table, const int* __restrict__ idx,
 rten_status launch_gather_rows(rten_ctx* ctx, const float* table, const int* idx, float* out, long long nidx, int width,
                                long long t_rs, long long t_cs, long long rows) {
     if (nidx * width == 0) return RTEN_OK;
-    gather_rows_kernel<<<ew_grid(ctx, nidx * width), 256, 0, ctx->stream>>>(table, idx, out, nidx, width, t_rs, t_cs,
+    gather_rows_kernel<<<ew_grid(ctx, nidx * width), 256, 0, launch_stream(ctx)>>>(table, idx, out, nidx, width, t_rs, t_cs,
                                                                             rows);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail_cuda(ctx, e, "gather launch");

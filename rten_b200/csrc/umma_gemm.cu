@@ -26,6 +26,7 @@
 #include <algorithm>
 #include <array>
 #include <cmath>
+#include <memory>
 #include <vector>
 #include <cmath>
 #include <cstdint>
@@ -77,6 +78,8 @@ struct KParams {
                     // to `sk_ws`, the LAST CTA to arrive (per tile and epilogue group, `sk_cnt`) sums them in split order
                     // (deterministic) and runs the epilogue
     int kb_per;
+    int cta2;       // 1: CTA pairs (cluster 2x1x1) execute 256-row tcgen05.mma.cta_group::2 tiles; each CTA loads its own
+                    //    128 rows of A and HALF of the B tile, so operand bytes entering an SM per flop drop by up to 2x
     int units_total;  // tiles_total * splitk
     uint32_t* sk_ws;
     int* sk_cnt;
@@ -91,14 +94,16 @@ struct TileCoord {
 };
 
 // t indexes work units: (n tile, m tile or PAIR of m tiles, batch); `sub` selects the tile inside a pair.
-__device__ __forceinline__ TileCoord decode_tile(const KParams& p, int t, int sub) {
+__device__ __forceinline__ TileCoord decode_tile(const KParams& p, int t, int sub, int rank = 0) {
     TileCoord c;
     int n_blk = t % p.tiles_n;
     int rest = t / p.tiles_n;
-    const int units_m = p.pair ? (p.tiles_m + 1) / 2 : p.tiles_m;
+    // one unit = (pair + 1) MMA tiles of (cta2 + 1) x 128 rows: `mult` consecutive 128-row blocks
+    const int mult = (p.pair + 1) * (p.cta2 + 1);
+    const int units_m = (p.tiles_m + mult - 1) / mult;
     int m_blk = rest % units_m;
     int z = rest / units_m;
-    if (p.pair) m_blk = 2 * m_blk + sub;  // may be == tiles_m for the odd tail: every row is then out of range
+    m_blk = m_blk * mult + sub * (p.cta2 + 1) + rank;  // may be >= tiles_m in the tail: every row is then out of range
     c.n0 = n_blk * p.bn;
     c.m0 = m_blk * BM;
     c.z0 = z % p.z0;
@@ -130,7 +135,7 @@ __device__ __forceinline__ void bulk_wait_read(int n) {
 // Returns true for the group of the CTA that arrived last: it owns the epilogue of (tile, group).
 // Workspace layout: [tile][sub][split][chunk][column j][row r] so that a warp's 32 rows are contiguous.
 __device__ __forceinline__ bool splitk_publish(const KParams& p, int t, int ks, int grp, int q, int lane, uint32_t t_acc,
-                                               int* flag) {
+                                               int* flag) {  // t = tile slot (tile, or 2 * tile + cluster rank)
     const int r = q * 32 + lane;
     const int nchunks = p.bn >> 5;
     for (int sub = 0; sub <= p.pair; sub++) {
@@ -179,107 +184,93 @@ __device__ __forceinline__ void splitk_sum(const KParams& p, int t, int sub, int
     }
 }
 
-// FAST = the launch satisfies, for EVERY chunk, the conditions of the register fast path (TMA-store output, N % 32 == 0,
-// f32 with act in {none, relu} and bias / residual absent or vector-addressable [residual via TMA], or raw i32): the
-// epilogue is then a short straight-line loop.  The generic variant (FAST = 0) keeps every edge case.
-template <int KIND, int FAST>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
-umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                 const __grid_constant__ CUtensorMap tma_d, const __grid_constant__ CUtensorMap tma_r,
-                 const KParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    // 1024-B alignment required by the 128B swizzle atoms / UMMA descriptors (base_offset = 0).
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    // staging: 1 buffer per epilogue group, 2 per group when the residual is prefetched (1024-B aligned)
+// Per-thread pipeline state that survives from one layer of a sequence kernel to the next: parity bits of the operand
+// ring (bit s = uses of stage s so far, mod 2), of the two accumulator barriers, of the residual barriers, and the
+// running tile count that picks the accumulator stage.  Each role keeps its own copy.
+struct PipeState {
+    uint32_t ring = 0, acc = 0, rphase = 0;
+    int it = 0;
+};
+
+struct SmemLayout {
+    uint8_t* smem;  // operand stages (1024-B aligned), staging buffers behind them
+    uint64_t *full_bar, *empty_bar, *tmem_full, *tmem_empty, *res_bar;
+    int* sk_flag;
+};
+
+// One launch worth of work (all roles).  FAST = the launch satisfies, for EVERY chunk, the conditions of the register
+// fast path (TMA-store output, N % 32 == 0, f32 with act in {none, relu} and bias / residual absent or
+// vector-addressable [residual via TMA], or raw i32): the epilogue is then a short straight-line loop.  The generic
+// variant (FAST = 0) keeps every edge case.
+template <int KIND, int FAST, int CTA2>
+__device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* tma_a, const CUtensorMap* tma_b,
+                                          const CUtensorMap* tma_d, const CUtensorMap* tma_r, const SmemLayout& L,
+                                          uint32_t tmem_base, int cta_rank, int worker, int n_workers, PipeState& st) {
+    uint8_t* smem = L.smem;
     uint8_t* stg_base = smem + (size_t)p.stages * p.stage_bytes;
     const int nbuf = p.nbuf;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg_base + 2 * nbuf * STG_BYTES);
-    uint64_t* empty_bar = full_bar + MAX_STAGES;
-    uint64_t* tmem_full = empty_bar + MAX_STAGES;
-    uint64_t* tmem_empty = tmem_full + 2;
-    uint64_t* res_bar = tmem_empty + 2;  // [group][buffer], up to 4 buffers per group
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_bar + 8);
-    int* sk_flag = reinterpret_cast<int*>(tmem_ptr + 2);  // [group]
-
+    uint64_t* full_bar = L.full_bar;
+    uint64_t* empty_bar = L.empty_bar;
+    uint64_t* tmem_full = L.tmem_full;
+    uint64_t* tmem_empty = L.tmem_empty;
+    uint64_t* res_bar = L.res_bar;
+    int* sk_flag = L.sk_flag;
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-
-    if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tma_a);
-        tma_prefetch_desc(&tma_b);
-        if (p.tma_store) tma_prefetch_desc(&tma_d);
-        if (p.res_tma) tma_prefetch_desc(&tma_r);
-    }
-    if (warp == 1 && lane == 0) {
-        for (int s = 0; s < p.stages; s++) {
-            mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
-        }
-        for (int s = 0; s < 2; s++) {
-            mbar_init(&tmem_full[s], 1);
-            mbar_init(&tmem_empty[s], 8);  // one arrival per epilogue warp
-        }
-        for (int s = 0; s < 8; s++) mbar_init(&res_bar[s], 1);
-        fence_mbar_init();
-    }
-    if (warp == 2) {
-        tmem_alloc(tmem_ptr, TMEM_COLS);
-        tmem_relinquish();
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_ptr;
-    // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps
-    // the tail of the previous kernel in the stream; global memory is only touched after this point.
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-
     // Control warps run their loops WARP-UNIFORMLY (all 32 lanes wait on the barriers, one elected lane issues the
     // TMA / MMA instructions): addresses and descriptors then live in uniform registers instead of being moved
     // there (R2UR) for every instruction, which is what bounds a single issuing thread.
     if (warp == 0) {
         // ===================== TMA producer =====================
         int stage = 0;
-        uint32_t phase = 0;
         int tr_p = 0;
         const uint32_t smem0 = smem_u32(smem);
         const uint32_t full0 = smem_u32(full_bar);
         const uint32_t a_bytes = (p.pair ? 2 : 1) * A_STAGE_BYTES;
-        for (int u = blockIdx.x; u < p.units_total; u += gridDim.x) {
+        const int b_row0 = CTA2 ? cta_rank * (p.bn >> 1) : 0;  // this CTA's half of the B tile
+        for (int u = worker; u < p.units_total; u += n_workers) {
             const int t = u % p.tiles_total;
             const int kb0 = (u / p.tiles_total) * p.kb_per, kb1 = min(p.k_blocks, kb0 + p.kb_per);
-            const TileCoord tc = decode_tile(p, t, 0);
-            const TileCoord tc1 = decode_tile(p, t, 1);
+            const TileCoord tc = decode_tile(p, t, 0, cta_rank);
+            const TileCoord tc1 = decode_tile(p, t, 1, cta_rank);
             // conv: K block -> (filter tap, channel block), kept incrementally
             int tap = kb0 / p.c_blocks, cb = kb0 - tap * p.c_blocks, ky = tap / p.kw, kx = tap - ky * p.kw;
             for (int kb = kb0; kb < kb1; kb += p.katoms) {
                 const int natoms = min(p.katoms, kb1 - kb);
-                mbar_wait(&empty_bar[stage], phase ^ 1);
+                mbar_wait(&empty_bar[stage], ((st.ring >> stage) & 1) ^ 1);
                 const bool leader = elect_one();
-                const uint32_t fb = full0 + stage * 8;
+                // CTA pair: both CTAs' loads complete on the LEADER's barrier, which expects the bytes of both
+                const uint32_t fb = CTA2 ? ((full0 + stage * 8) & PEER_BIT_MASK) : (full0 + stage * 8);
                 if (leader) {
                     if (p.trace && blockIdx.x == 0 && tr_p < 2048) p.trace[tr_p++] = clock64();
-                    mbar_expect_tx_u32(fb, p.tx_bytes * natoms);
+                    if (!CTA2)
+                        mbar_expect_tx_u32(fb, p.tx_bytes * natoms);
+                    else if (cta_rank == 0)
+                        mbar_expect_tx_u32(fb, 2 * p.tx_bytes * natoms);
                 }
                 for (int a = 0; a < natoms; a++) {
                     if (leader) {
                         const uint32_t sa = smem0 + stage * p.stage_bytes + a * p.atom_bytes;
                         const uint32_t sb = sa + a_bytes;
+                        auto load = [&](uint32_t dst, const CUtensorMap* m, int c0, int c1, int c2, int c3) {
+                            if (CTA2)
+                                tma_load_4d_2sm(dst, m, fb, c0, c1, c2, c3);
+                            else
+                                tma_load_4d_u32(dst, m, fb, c0, c1, c2, c3);
+                        };
                         if (p.conv) {
                             const int c0 = cb * p.kelems;
-                            tma_load_4d_u32(sa, &tma_a, fb, c0, tc.ox0 * p.sx - p.pl + kx * p.dx,
-                                            tc.oy0 * p.sy - p.pt + ky * p.dy, tc.b0);
+                            load(sa, tma_a, c0, tc.ox0 * p.sx - p.pl + kx * p.dx, tc.oy0 * p.sy - p.pt + ky * p.dy, tc.b0);
                             if (p.pair)
-                                tma_load_4d_u32(sa + A_STAGE_BYTES, &tma_a, fb, c0, tc1.ox0 * p.sx - p.pl + kx * p.dx,
-                                                tc1.oy0 * p.sy - p.pt + ky * p.dy, tc1.b0);
-                            tma_load_4d_u32(sb, &tma_b, fb, c0, tc.n0, tap, 0);
+                                load(sa + A_STAGE_BYTES, tma_a, c0, tc1.ox0 * p.sx - p.pl + kx * p.dx,
+                                     tc1.oy0 * p.sy - p.pt + ky * p.dy, tc1.b0);
+                            load(sb, tma_b, c0, tc.n0 + b_row0, tap, 0);
                         } else {
                             const int k0 = (kb + a) * p.kelems;
                             const int az0 = p.a_bcast0 ? 0 : tc.z0, az1 = p.a_bcast1 ? 0 : tc.z1;
-                            tma_load_4d_u32(sa, &tma_a, fb, k0, tc.m0, az0, az1);
-                            if (p.pair) tma_load_4d_u32(sa + A_STAGE_BYTES, &tma_a, fb, k0, tc1.m0, az0, az1);
-                            tma_load_4d_u32(sb, &tma_b, fb, k0, tc.n0, p.b_bcast0 ? 0 : tc.z0, p.b_bcast1 ? 0 : tc.z1);
+                            load(sa, tma_a, k0, tc.m0, az0, az1);
+                            if (p.pair) load(sa + A_STAGE_BYTES, tma_a, k0, tc1.m0, az0, az1);
+                            load(sb, tma_b, k0, tc.n0 + b_row0, p.b_bcast0 ? 0 : tc.z0, p.b_bcast1 ? 0 : tc.z1);
                         }
                     }
                     if (++cb == p.c_blocks) {
@@ -292,32 +283,28 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                     }
                 }
                 __syncwarp();
-                if (++stage == p.stages) {
-                    stage = 0;
-                    phase ^= 1;
-                }
+                st.ring ^= 1u << stage;
+                if (++stage == p.stages) stage = 0;
             }
         }
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
+    } else if (warp == 1 && cta_rank == 0) {
+        // ===================== MMA issuer (pair mode: the leader CTA only) =====================
         int stage = 0;
-        uint32_t phase = 0;
-        int it = 0;
         int tr_m = 0;
         const uint32_t smem0 = smem_u32(smem);
         const uint32_t empty0 = smem_u32(empty_bar);
         const uint32_t b_off = (p.pair ? 2 : 1) * A_STAGE_BYTES;
         const uint32_t d1_off = (p.pair || p.ksplit) ? p.bn : 0;
-        for (int u = blockIdx.x; u < p.units_total; u += gridDim.x, it++) {
+        for (int u = worker; u < p.units_total; u += n_workers, st.it++) {
             const int kb0 = (u / p.tiles_total) * p.kb_per, kb1 = min(p.k_blocks, kb0 + p.kb_per);
-            const int acc = p.acc1 ? 0 : (it & 1);
-            const uint32_t acc_phase = (p.acc1 ? it : (it >> 1)) & 1;
-            mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+            const int acc = p.acc1 ? 0 : (st.it & 1);
+            mbar_wait(&tmem_empty[acc], ((st.acc >> acc) & 1) ^ 1);
+            st.acc ^= 1u << acc;
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
             for (int kb = kb0; kb < kb1; kb += p.katoms) {
                 const int natoms = min(p.katoms, kb1 - kb);
-                mbar_wait(&full_bar[stage], phase);
+                mbar_wait(&full_bar[stage], (st.ring >> stage) & 1);
                 tc_fence_after();
                 if (elect_one()) {
                     if (p.trace && blockIdx.x == 0 && tr_m < 2048) p.trace[2048 + tr_m++] = clock64();
@@ -326,31 +313,41 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                         const uint64_t adesc = make_kmajor_sw128_desc(sa);
                         const uint64_t bdesc = make_kmajor_sw128_desc(sa + b_off);
                         const uint32_t first = (kb + a) == kb0 ? 0u : 1u;
+                        auto mma = [&](uint32_t d, uint64_t ad, uint64_t bd, uint32_t accum) {
+                            if (CTA2)
+                                umma2<KIND>(d, ad, bd, p.idesc, accum);
+                            else
+                                umma<KIND>(d, ad, bd, p.idesc, accum);
+                        };
                         if (p.pair) {
                             const uint64_t adesc1 = make_kmajor_sw128_desc(sa + A_STAGE_BYTES);
 #pragma unroll
                             for (int k = 0; k < 4; k++) {  // +2 in the (addr >> 4) field = 32 B along K in the swizzle atom
-                                umma<KIND>(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, k == 0 ? first : 1u);
-                                umma<KIND>(d_tmem + d1_off, adesc1 + 2 * k, bdesc + 2 * k, p.idesc, k == 0 ? first : 1u);
+                                mma(d_tmem, adesc + 2 * k, bdesc + 2 * k, k == 0 ? first : 1u);
+                                mma(d_tmem + d1_off, adesc1 + 2 * k, bdesc + 2 * k, k == 0 ? first : 1u);
                             }
                         } else if (p.ksplit) {
 #pragma unroll
                             for (int k = 0; k < 4; k++)  // k even -> accumulator 0, k odd -> accumulator 1
-                                umma<KIND>(d_tmem + (k & 1) * d1_off, adesc + 2 * k, bdesc + 2 * k, p.idesc, k < 2 ? first : 1u);
+                                mma(d_tmem + (k & 1) * d1_off, adesc + 2 * k, bdesc + 2 * k, k < 2 ? first : 1u);
                         } else {
 #pragma unroll
                             for (int k = 0; k < 4; k++)
-                                umma<KIND>(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, k == 0 ? first : 1u);
+                                mma(d_tmem, adesc + 2 * k, bdesc + 2 * k, k == 0 ? first : 1u);
                         }
                     }
-                    umma_commit_u32(empty0 + stage * 8);  // smem slot reusable once these MMAs retire
-                    if (kb + natoms >= kb1) umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+                    // smem slot reusable once these MMAs retire; accumulator complete -> epilogue (of both CTAs)
+                    if (CTA2) {
+                        umma_commit_mc(empty0 + stage * 8, 3);
+                        if (kb + natoms >= kb1) umma_commit_mc(smem_u32(&tmem_full[acc]), 3);
+                    } else {
+                        umma_commit_u32(empty0 + stage * 8);
+                        if (kb + natoms >= kb1) umma_commit(&tmem_full[acc]);
+                    }
                 }
                 __syncwarp();
-                if (++stage == p.stages) {
-                    stage = 0;
-                    phase ^= 1;
-                }
+                st.ring ^= 1u << stage;
+                if (++stage == p.stages) stage = 0;
             }
         }
     } else if (FAST && warp >= 4) {
@@ -364,36 +361,37 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         const bool issuer = (q == 0 && lane == 0);
         const bool has_bias = e.bias_kind == 1;
         const float relu_floor = e.act == 1 ? 0.0f : -__int_as_float(0x7f800000);
-        uint32_t ci = 0, rphase = 0;
-        int it = 0;
-        for (int u = blockIdx.x; u < p.units_total; u += gridDim.x, it++) {
+        uint32_t ci = 0;
+        uint32_t& rphase = st.rphase;
+        for (int u = worker; u < p.units_total; u += n_workers, st.it++) {
             const int t = u % p.tiles_total;
-            const int acc = p.acc1 ? 0 : (it & 1);
-            const uint32_t acc_phase = (p.acc1 ? it : (it >> 1)) & 1;
+            const int acc = p.acc1 ? 0 : (st.it & 1);
+            const uint32_t acc_phase = (st.acc >> acc) & 1;
+            st.acc ^= 1u << acc;
             if (p.res_tma && issuer && grp * 32 < p.bn) {
-                const TileCoord tc0 = decode_tile(p, t, 0);
+                const TileCoord tc0 = decode_tile(p, t, 0, cta_rank);
                 const int b0 = ci % nbuf;
                 bulk_wait_read(nbuf - 1);
                 uint64_t* rb = &res_bar[grp * 4 + b0];
                 mbar_expect_tx(rb, p.res_tx_bytes);
                 if (p.conv)
-                    tma_load_4d(stg0 + b0 * STG_BYTES, &tma_r, rb, tc0.n0 + grp * 32, tc0.ox0, tc0.oy0, tc0.b0);
+                    tma_load_4d(stg0 + b0 * STG_BYTES, tma_r, rb, tc0.n0 + grp * 32, tc0.ox0, tc0.oy0, tc0.b0);
                 else
-                    tma_load_4d(stg0 + b0 * STG_BYTES, &tma_r, rb, tc0.n0 + grp * 32, tc0.m0, tc0.z0, tc0.z1);
+                    tma_load_4d(stg0 + b0 * STG_BYTES, tma_r, rb, tc0.n0 + grp * 32, tc0.m0, tc0.z0, tc0.z1);
             }
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             bool owner = true;
             if (p.splitk > 1)
-                owner = splitk_publish(p, t, u / p.tiles_total, grp, q, lane,
+                owner = splitk_publish(p, CTA2 ? 2 * t + cta_rank : t, u / p.tiles_total, grp, q, lane,
                                        tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_STRIDE, &sk_flag[grp]);
             for (int sub = 0; owner && sub <= p.pair; sub++) {
-                const TileCoord tc = decode_tile(p, t, sub);
+                const TileCoord tc = decode_tile(p, t, sub, cta_rank);
                 const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_STRIDE + sub * p.bn;
                 for (int c0 = grp * 32; c0 < p.bn; c0 += 64) {
                     uint32_t v[32];
                     if (p.splitk > 1)
-                        splitk_sum<KIND>(p, t, sub, c0, r, v);
+                        splitk_sum<KIND>(p, CTA2 ? 2 * t + cta_rank : t, sub, c0, r, v);
                     else
                         tmem_ld_32x32(t_row + c0, v);
                     const int nbase = tc.n0 + c0;
@@ -407,15 +405,15 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                             nc0 = grp * 32;
                         }
                         if (nsub <= p.pair && nc0 < p.bn) {
-                            const TileCoord tn = decode_tile(p, t, nsub);
+                            const TileCoord tn = decode_tile(p, t, nsub, cta_rank);
                             const int bnext = (ci + 1) % nbuf;
                             bulk_wait_read(nbuf - 2);
                             uint64_t* rb = &res_bar[grp * 4 + bnext];
                             mbar_expect_tx(rb, p.res_tx_bytes);
                             if (p.conv)
-                                tma_load_4d(stg0 + bnext * STG_BYTES, &tma_r, rb, tn.n0 + nc0, tn.ox0, tn.oy0, tn.b0);
+                                tma_load_4d(stg0 + bnext * STG_BYTES, tma_r, rb, tn.n0 + nc0, tn.ox0, tn.oy0, tn.b0);
                             else
-                                tma_load_4d(stg0 + bnext * STG_BYTES, &tma_r, rb, tn.n0 + nc0, tn.m0, tn.z0, tn.z1);
+                                tma_load_4d(stg0 + bnext * STG_BYTES, tma_r, rb, tn.n0 + nc0, tn.m0, tn.z0, tn.z1);
                         }
                     }
                     tmem_ld_wait();
@@ -465,9 +463,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                     asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
                     if (issuer) {
                         if (p.conv)
-                            tma_store_4d(&tma_d, stg, nbase, tc.ox0, tc.oy0, tc.b0);
+                            tma_store_4d(tma_d, stg, nbase, tc.ox0, tc.oy0, tc.b0);
                         else
-                            tma_store_4d(&tma_d, stg, nbase, tc.m0, tc.z0, tc.z1);
+                            tma_store_4d(tma_d, stg, nbase, tc.m0, tc.z0, tc.z1);
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
                     ci++;
@@ -475,7 +473,12 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (lane == 0) {
+                if (CTA2)
+                    mbar_arrive_cluster(smem_u32(&tmem_empty[acc]) & PEER_BIT_MASK);  // the leader's MMA warp waits on it
+                else
+                    mbar_arrive(&tmem_empty[acc]);
+            }
         }
         if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     } else if (!FAST && warp >= 4) {
@@ -487,33 +490,35 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         uint8_t* stg0 = stg_base + grp * nbuf * STG_BYTES;
         const bool issuer = (q == 0 && lane == 0);
         uint32_t ci = 0;            // chunks processed by this group so far (selects the staging buffer)
-        uint32_t rphase = 0;        // bit b = phase of res_bar[grp][b]
-        int it = 0;
-        for (int u = blockIdx.x; u < p.units_total; u += gridDim.x, it++) {
+        uint32_t& rphase = st.rphase;  // bit b = phase of res_bar[grp][b]
+        const int it0 = st.it;
+        for (int u = worker; u < p.units_total; u += n_workers, st.it++) {
+            const int it = st.it - it0;
             const int t = u % p.tiles_total;
-            const int acc = p.acc1 ? 0 : (it & 1);
-            const uint32_t acc_phase = (p.acc1 ? it : (it >> 1)) & 1;
+            const int acc = p.acc1 ? 0 : (st.it & 1);
+            const uint32_t acc_phase = (st.acc >> acc) & 1;
+            st.acc ^= 1u << acc;
             if (p.res_tma && issuer && grp * 32 < p.bn) {
                 // residual of this tile's first chunk: independent of the accumulator -> request it before waiting
-                const TileCoord tc0 = decode_tile(p, t, 0);
+                const TileCoord tc0 = decode_tile(p, t, 0, cta_rank);
                 const int b0 = ci % nbuf;
                 bulk_wait_read(nbuf - 1);  // the store that last used buffer b0 (chunk ci - nbuf) has been read
                 uint64_t* rb = &res_bar[grp * 4 + b0];
                 mbar_expect_tx(rb, p.res_tx_bytes);
                 if (p.conv)
-                    tma_load_4d(stg0 + b0 * STG_BYTES, &tma_r, rb, tc0.n0 + grp * 32, tc0.ox0, tc0.oy0, tc0.b0);
+                    tma_load_4d(stg0 + b0 * STG_BYTES, tma_r, rb, tc0.n0 + grp * 32, tc0.ox0, tc0.oy0, tc0.b0);
                 else
-                    tma_load_4d(stg0 + b0 * STG_BYTES, &tma_r, rb, tc0.n0 + grp * 32, tc0.m0, tc0.z0, tc0.z1);
+                    tma_load_4d(stg0 + b0 * STG_BYTES, tma_r, rb, tc0.n0 + grp * 32, tc0.m0, tc0.z0, tc0.z1);
             }
             mbar_wait(&tmem_full[acc], acc_phase);
             if (p.trace && blockIdx.x == 0 && warp == 4 && lane == 0 && it < 2048) p.trace[4096 + it] = clock64();
             tc_fence_after();
             bool owner = true;
             if (p.splitk > 1)
-                owner = splitk_publish(p, t, u / p.tiles_total, grp, q, lane,
+                owner = splitk_publish(p, CTA2 ? 2 * t + cta_rank : t, u / p.tiles_total, grp, q, lane,
                                        tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_STRIDE, &sk_flag[grp]);
             for (int sub = 0; owner && sub <= p.pair; sub++) {
-            const TileCoord tc = decode_tile(p, t, sub);
+            const TileCoord tc = decode_tile(p, t, sub, cta_rank);
             // ---- row bookkeeping
             bool row_ok;
             long long d_off, r_off;
@@ -552,7 +557,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                 uint32_t v[32];
                 const int ncols = (p.bn - c0) >= 32 ? 32 : 16;
                 if (p.splitk > 1) {
-                    splitk_sum<KIND>(p, t, sub, c0, r, v);
+                    splitk_sum<KIND>(p, CTA2 ? 2 * t + cta_rank : t, sub, c0, r, v);
                 } else if (ncols == 32) {
                     tmem_ld_32x32(t_row + c0, v);
                 } else {
@@ -598,16 +603,16 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                             nc0 = grp * 32;
                         }
                         if (nsub <= p.pair && nc0 < p.bn) {
-                            const TileCoord tn = decode_tile(p, t, nsub);
+                            const TileCoord tn = decode_tile(p, t, nsub, cta_rank);
                             const int bnext = (ci + 1) % nbuf;
                             bulk_wait_read(nbuf - 2);  // chunk ci + 1 - nbuf's store has been read; newer ones stay in flight
                             uint64_t* rb = &res_bar[grp * 4 + bnext];
                             mbar_expect_tx(rb, p.res_tx_bytes);
                             uint8_t* dst = stg0 + bnext * STG_BYTES;
                             if (p.conv)
-                                tma_load_4d(dst, &tma_r, rb, tn.n0 + nc0, tn.ox0, tn.oy0, tn.b0);
+                                tma_load_4d(dst, tma_r, rb, tn.n0 + nc0, tn.ox0, tn.oy0, tn.b0);
                             else
-                                tma_load_4d(dst, &tma_r, rb, tn.n0 + nc0, tn.m0, tn.z0, tn.z1);
+                                tma_load_4d(dst, tma_r, rb, tn.n0 + nc0, tn.m0, tn.z0, tn.z1);
                         }
                     }
                     mbar_wait(&res_bar[grp * 4 + bcur], (rphase >> bcur) & 1);
@@ -631,7 +636,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                         if (p.res_tma)
                             rr = *reinterpret_cast<const float4*>(rowp + (((j >> 2) ^ sw) << 4));
                         else if (e.r)
-                            rr = *reinterpret_cast<const float4*>(e.r + r_off + nbase + j);
+                            rr = __ldcg(reinterpret_cast<const float4*>(e.r + r_off + nbase + j));
                         if (e.bias_kind == 1) bb = __ldg(reinterpret_cast<const float4*>(e.bias + nbase + j));
                         const float r4[4] = {rr.x, rr.y, rr.z, rr.w}, b4[4] = {bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
@@ -663,7 +668,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                         uint32_t* sp = reinterpret_cast<uint32_t*>(rowp + (((j >> 2) ^ sw) << 4)) + (j & 3);
                         if (KIND == 0) {
                             float x = __uint_as_float(*sp) * e.alpha;
-                            if (e.r) x = fmaf(e.r_scale, e.r[r_off + (long long)n * e.r_col], x);
+                            if (e.r) x = fmaf(e.r_scale, __ldcg(e.r + r_off + (long long)n * e.r_col), x);
                             if (e.bias_kind == 1) x += e.bias[n];
                             x += row_bias;
                             *sp = __float_as_uint(apply_act(x, e.act));
@@ -691,9 +696,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                     if (tr) { const long long t1 = clock64(); p.trace[6144 + 1024 + 5] += t1 - t0; t0 = t1; p.trace[6144 + 1024 + 7] += 1; }
                     if (issuer) {
                         if (p.conv)
-                            tma_store_4d(&tma_d, stg, nbase, tc.ox0, tc.oy0, tc.b0);
+                            tma_store_4d(tma_d, stg, nbase, tc.ox0, tc.oy0, tc.b0);
                         else
-                            tma_store_4d(&tma_d, stg, nbase, tc.m0, tc.z0, tc.z1);
+                            tma_store_4d(tma_d, stg, nbase, tc.m0, tc.z0, tc.z1);
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
                     if (tr) { const long long t1 = clock64(); p.trace[6144 + 1024 + 6] += t1 - t0; t0 = t1; }
@@ -714,18 +719,192 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             tc_fence_before();
             __syncwarp();
             if (p.trace && blockIdx.x == 0 && warp == 4 && lane == 0 && it < 2048) p.trace[6144 + it] = clock64();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (lane == 0) {
+                if (CTA2)
+                    mbar_arrive_cluster(smem_u32(&tmem_empty[acc]) & PEER_BIT_MASK);  // the leader's MMA warp waits on it
+                else
+                    mbar_arrive(&tmem_empty[acc]);
+            }
         }
         // smem must stay valid until the last bulk store has read it
         if (p.tma_store && issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
 
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 2) {
-        tc_fence_after();
-        tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// Shared-memory carve-up: a fixed 1 KB block of mbarriers first (so that it does not move when the stage geometry changes
+// from layer to layer of a sequence kernel), operand stages behind it.
+__device__ __forceinline__ SmemLayout carve_smem(uint8_t* smem_raw) {
+    // 1024-B alignment required by the 128B swizzle atoms / UMMA descriptors (base_offset = 0).
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    SmemLayout L;
+    L.full_bar = reinterpret_cast<uint64_t*>(base);
+    L.empty_bar = L.full_bar + MAX_STAGES;
+    L.tmem_full = L.empty_bar + MAX_STAGES;
+    L.tmem_empty = L.tmem_full + 2;
+    L.res_bar = L.tmem_empty + 2;  // [group][buffer], up to 4 buffers per group
+    L.sk_flag = reinterpret_cast<int*>(L.res_bar + 8) + 2;  // [group]; the two ints before it hold the TMEM base
+    L.smem = base + 1024;
+    return L;
+}
+
+template <int CTA2>
+__device__ __forceinline__ uint32_t kernel_setup(const SmemLayout& L) {
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(L.res_bar + 8);
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < MAX_STAGES; s++) {
+            mbar_init(&L.full_bar[s], 1);
+            mbar_init(&L.empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; s++) {
+            mbar_init(&L.tmem_full[s], 1);
+            mbar_init(&L.tmem_empty[s], CTA2 ? 16 : 8);  // one arrival per epilogue warp (of both CTAs of a pair)
+        }
+        for (int s = 0; s < 8; s++) mbar_init(&L.res_bar[s], 1);
+        fence_mbar_init();
     }
+    if (warp == 2) {
+        if (CTA2) {
+            tmem_alloc2(tmem_ptr, TMEM_COLS);
+            tmem_relinquish2();
+        } else {
+            tmem_alloc(tmem_ptr, TMEM_COLS);
+            tmem_relinquish();
+        }
+    }
+    tc_fence_before();
+    if (CTA2)
+        cluster_sync_all();  // the peer's barriers must be initialised before any remote arrive / multicast commit
+    else
+        __syncthreads();
+    tc_fence_after();
+    return *tmem_ptr;
+}
+
+template <int CTA2>
+__device__ __forceinline__ void kernel_teardown(uint32_t tmem_base) {
+    tc_fence_before();
+    if (CTA2)
+        cluster_sync_all();  // neither CTA may exit (or free TMEM) while the pair's MMAs / remote arrives are in flight
+    else
+        __syncthreads();
+    if ((threadIdx.x >> 5) == 2) {
+        tc_fence_after();
+        if (CTA2)
+            tmem_dealloc2(tmem_base, TMEM_COLS);
+        else
+            tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+template <int KIND, int FAST, int CTA2>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                 const __grid_constant__ CUtensorMap tma_d, const __grid_constant__ CUtensorMap tma_r,
+                 const __grid_constant__ KParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const SmemLayout L = carve_smem(smem_raw);
+    if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[6144 + 1100] = clock64();  // kernel entry
+    // CTA pair: cluster rank 0 is the leader (issues the MMAs); work is distributed over clusters
+    const int cta_rank = CTA2 ? (int)cluster_ctarank() : 0;
+    const int worker = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int n_workers = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tma_a);
+        tma_prefetch_desc(&tma_b);
+        if (p.tma_store) tma_prefetch_desc(&tma_d);
+        if (p.res_tma) tma_prefetch_desc(&tma_r);
+    }
+    const uint32_t tmem_base = kernel_setup<CTA2>(L);
+    // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps
+    // the tail of the previous kernel in the stream; global memory is only touched after this point.
+    if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[6144 + 1101] = clock64();  // set-up done
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[6144 + 1102] = clock64();  // predecessor complete
+    PipeState st;
+    run_layer<KIND, FAST, CTA2>(p, &tma_a, &tma_b, &tma_d, &tma_r, L, tmem_base, cta_rank, worker, n_workers, st);
+    if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[6144 + 1103] = clock64();  // control thread done
+    kernel_teardown<CTA2>(tmem_base);
+    if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[6144 + 1104] = clock64();  // exit
+}
+
+// ------------------------------------------------------------------------------------------
+// Sequence kernel: up to SEQ_MAX consecutive launches (layers of a captured op list) run inside ONE persistent
+// kernel.  Between two layers every CTA drains its output stores and meets the others at a grid-wide barrier (an
+// arrival counter in global memory): a layer boundary costs one barrier round trip plus one TMA latency instead of a
+// kernel launch, TMEM allocation, tensor-map fetch and a cold pipeline.  Layer parameters and tensor maps live in the
+// kernel parameter block (constant bank), indexed by the layer number.
+// ------------------------------------------------------------------------------------------
+constexpr int SEQ_MAX = 32;
+struct SeqParams {
+    int n;
+    int pad;
+    unsigned* gbar;  // arrival counter, zero between launches
+    CUtensorMap maps[SEQ_MAX][4];
+    KParams layer[SEQ_MAX];
+};
+static_assert(sizeof(SeqParams) <= 32764, "kernel parameter block too large");
+
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <int KIND, int FAST>
+__global__ void __launch_bounds__(NUM_THREADS, 1) umma_seq_kernel(const __grid_constant__ SeqParams sp) {
+    extern __shared__ uint8_t smem_raw[];
+    const SmemLayout L = carve_smem(smem_raw);
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&sp.maps[0][0]);
+        tma_prefetch_desc(&sp.maps[0][1]);
+    }
+    const uint32_t tmem_base = kernel_setup<0>(L);
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    PipeState st;
+    const int warp = threadIdx.x >> 5;
+    for (int l = 0; l < sp.n; l++) {
+        const KParams& p = sp.layer[l];
+        if (l + 1 == sp.n) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        run_layer<KIND, FAST, 0>(p, &sp.maps[l][0], &sp.maps[l][1], &sp.maps[l][2], &sp.maps[l][3], L, tmem_base, 0,
+                                 (int)blockIdx.x, (int)gridDim.x, st);
+        if (l + 1 < sp.n) {
+            // ---- layer boundary: this CTA's outputs are complete and visible, then wait for every other CTA's
+            if (warp >= 4) {
+                asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // TMA stores performed (issuer threads)
+                asm volatile("fence.proxy.async;" ::: "memory");
+                __threadfence();
+            }
+            if (threadIdx.x == 32) {  // idle until the barrier anyway: fetch the next layer's tensor maps
+                tma_prefetch_desc(&sp.maps[l + 1][0]);
+                tma_prefetch_desc(&sp.maps[l + 1][1]);
+                tma_prefetch_desc(&sp.maps[l + 1][2]);
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                __threadfence();
+                atomicAdd(sp.gbar, 1u);
+                const unsigned target = gridDim.x * (unsigned)(l + 1);
+                uint32_t spins = 0;
+                while (ld_acquire_gpu(sp.gbar) < target) {
+                    __nanosleep(32);
+                    if (++spins > (1u << 25)) __trap();  // > ~1 s: a CTA of the grid never arrived
+                }
+                __threadfence();
+            }
+            __syncthreads();
+            asm volatile("fence.proxy.async;" ::: "memory");
+        }
+    }
+    // re-arm the arrival counter: the last CTA to leave (everyone has passed every barrier by then) zeroes it
+    if (threadIdx.x == 0) {
+        const unsigned old = atomicAdd(sp.gbar, 1u);
+        if (old == gridDim.x * (unsigned)sp.n - 1u) *reinterpret_cast<volatile unsigned*>(sp.gbar) = 0u;
+    }
+    kernel_teardown<0>(tmem_base);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -816,7 +995,7 @@ static void pick_conv_tile(const ConvGeom& g, int& tw, int& th, int& tb) {
 // (b) the per-context autotune cache: with rten_b200_set_autotune(ctx, 1) the first launch of every distinct problem
 // times the model's best candidates on the device (CUDA events on the context stream) and remembers the winner.
 struct Plan {
-    int bn = 32, pair = 0, katoms = 1, ksplit = 0, splitk = 1, nbuf = 1, acc1 = 0;
+    int bn = 32, pair = 0, katoms = 1, ksplit = 0, splitk = 1, nbuf = 1, acc1 = 0, cta2 = 0;
 };
 
 // Everything about a launch that does not depend on the plan.
@@ -845,20 +1024,22 @@ static bool plan_shape(const Prepared& q, const Plan& pl, PlanShape& ps) {
     const KParams& p = q.p;
     if (pl.bn < 16 || pl.bn > 256 || pl.bn % q.step) return false;
     if (pl.pair && p.tiles_m < 2) return false;
+    if (pl.cta2 && (p.tiles_m < 2 || pl.bn % 32)) return false;
     if (pl.acc1 != ((pl.pair && pl.bn > 128) ? 1 : 0)) return false;
     if (pl.ksplit && (pl.pair || pl.bn > 128 || pl.splitk > 1)) return false;
     ps.tiles_n = (p.N + pl.bn - 1) / pl.bn;
-    ps.units_m = pl.pair ? (p.tiles_m + 1) / 2 : p.tiles_m;
+    const int mult = (pl.pair + 1) * (pl.cta2 + 1);
+    ps.units_m = (p.tiles_m + mult - 1) / mult;
     ps.tiles = ps.units_m * ps.tiles_n * q.batch;
     ps.units = ps.tiles * pl.splitk;
     if (ps.units > 0x7FFFFFFFll) return false;
     ps.kb_per = (p.k_blocks + pl.splitk - 1) / pl.splitk;
     if (pl.splitk > 1) {
         if (pl.bn % 32 || (long long)(pl.splitk - 1) * ps.kb_per >= p.k_blocks) return false;  // no empty split
-        if (ps.tiles * 2 > SK_CNT_INTS) return false;
+        if (ps.tiles * 2 * (pl.cta2 + 1) > SK_CNT_INTS) return false;
     }
     ps.n_stg = 2 * pl.nbuf;
-    ps.atom_bytes = (pl.pair ? 2 : 1) * A_STAGE_BYTES + pl.bn * KBYTES;
+    ps.atom_bytes = (pl.pair ? 2 : 1) * A_STAGE_BYTES + (pl.bn >> pl.cta2) * KBYTES;  // pair mode: half of B per CTA
     if (pl.katoms == 2 && ps.kb_per < 2) return false;
     ps.stage_bytes = ps.atom_bytes * pl.katoms;
     ps.stages = std::min(MAX_STAGES, smem_budget_for(ps.n_stg) / ps.stage_bytes);
@@ -875,8 +1056,9 @@ static bool plan_shape(const Prepared& q, const Plan& pl, PlanShape& ps) {
 //   * a stage cannot complete faster than TMA latency (~2300 clk under load) / stages in flight;
 //   * the epilogue (~350 clk per 32-column chunk, two warp groups) overlaps the next main loop unless acc1.
 static double plan_cost(const Prepared& q, const Plan& pl, const PlanShape& ps, int num_sms) {
-    const double active = (double)std::min<long long>(ps.units, num_sms);
-    const double waves = std::ceil((double)ps.units / num_sms);
+    const int workers = pl.cta2 ? num_sms / 2 : num_sms;
+    const double active = (double)std::min<long long>(ps.units, workers) * (pl.cta2 + 1);
+    const double waves = std::ceil((double)ps.units / workers);
     const double bw = std::min(64.0, 7400.0 / active);
     const double mmas = 4.0 * (pl.pair ? 2 : 1);
     const double t_kb = std::max(mmas * std::max(42.0, pl.bn / 2.0), ps.atom_bytes / bw);
@@ -895,12 +1077,15 @@ static void enumerate_plans(const Prepared& q, int num_sms, std::vector<std::pai
     const KParams& p = q.p;
     const int nmax = (p.N + q.step - 1) / q.step * q.step;
     static const int splits[] = {1, 2, 3, 4, 5, 6, 8, 10, 12, 16};
+    const bool allow_cta2 = !getenv("RTEN_B200_NO_CTA2");
+    for (int cta2 = 0; cta2 <= (allow_cta2 ? 1 : 0); cta2++)
     for (int pair = 0; pair <= 1; pair++)
         for (int bn = q.step; bn <= 256; bn += q.step) {
             if (bn > nmax && bn != q.step) break;
             for (int katoms = 1; katoms <= 2; katoms++)
                 for (int sk : splits) {
                     Plan pl;
+                    pl.cta2 = cta2;
                     pl.bn = bn;
                     pl.pair = pair;
                     pl.katoms = katoms;
@@ -912,7 +1097,7 @@ static void enumerate_plans(const Prepared& q, int num_sms, std::vector<std::pai
                     pl.nbuf = pl.acc1 ? 1 : ((q.res_tma || kb_per < 24) ? 2 : 1);
                     PlanShape ps;
                     if (!plan_shape(q, pl, ps)) continue;
-                    if (sk > 1 && ps.tiles >= 2 * num_sms) continue;  // enough parallelism without splitting K
+                    if (sk > 1 && ps.tiles * (cta2 + 1) >= 2 * num_sms) continue;  // enough parallelism without splitting K
                     if (ps.stages < 3 && !(katoms == 1 && ps.stages == 2)) continue;
                     out.emplace_back(plan_cost(q, pl, ps, num_sms), pl);
                 }
@@ -1040,7 +1225,147 @@ static rten_status prepare_launch(rten_ctx* ctx, const GemmLaunch& L, Prepared& 
     return RTEN_OK;
 }
 
-static rten_status launch_plan(rten_ctx* ctx, const GemmLaunch& L, const Prepared& q, const Plan& pl, bool verbose) {
+static size_t splitk_ws_bytes(const PlanShape& ps, const Plan& pl) {
+    return pl.splitk > 1 ? (size_t)ps.tiles * (pl.cta2 + 1) * 2 * pl.splitk * (pl.bn / 32) * 4096 * 4 : 0;
+}
+
+static rten_status ensure_splitk_counters(rten_ctx* ctx) {
+    if (!ctx->sk_counters) {
+        cudaError_t ce = cudaMalloc(&ctx->sk_counters, SK_CNT_INTS * sizeof(int));
+        if (ce != cudaSuccess) return fail_cuda(ctx, ce, "split-K counters");
+        ce = cudaMemset(ctx->sk_counters, 0, SK_CNT_INTS * sizeof(int));
+        if (ce != cudaSuccess) return fail_cuda(ctx, ce, "split-K counters");
+    }
+    return RTEN_OK;
+}
+
+struct PendingLaunch {
+    KParams p;
+    CUtensorMap maps[4];
+    size_t smem_bytes;
+};
+
+static std::vector<PendingLaunch>* pending_of(rten_ctx* ctx) {
+    if (!ctx->seq_pending) ctx->seq_pending = new std::vector<PendingLaunch>();
+    return reinterpret_cast<std::vector<PendingLaunch>*>(ctx->seq_pending);
+}
+
+void seq_free(rten_ctx* ctx) {
+    if (ctx->seq_pending) delete reinterpret_cast<std::vector<PendingLaunch>*>(ctx->seq_pending);
+    ctx->seq_pending = nullptr;
+    if (ctx->seq_gbar) cudaFree(ctx->seq_gbar);
+    ctx->seq_gbar = nullptr;
+}
+
+static void fill_launch_attrs(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, bool cluster2) {
+    int nattr = 0;
+    if (!getenv("RTEN_B200_NO_PDL")) {
+        attr[nattr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[nattr].val.programmaticStreamSerializationAllowed = 1;
+        nattr++;
+    }
+    if (cluster2) {
+        attr[nattr].id = cudaLaunchAttributeClusterDimension;
+        attr[nattr].val.clusterDim.x = 2;
+        attr[nattr].val.clusterDim.y = 1;
+        attr[nattr].val.clusterDim.z = 1;
+        nattr++;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = nattr;
+}
+
+// cls = kind * 2 + fast
+static rten_status launch_single(rten_ctx* ctx, int cls, const PendingLaunch& pl) {
+    const KParams& p = pl.p;
+    const int grid = p.cta2 ? 2 * std::min(p.units_total, ctx->num_sms / 2) : std::min(p.units_total, ctx->num_sms);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = pl.smem_bytes;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[2];
+    fill_launch_attrs(cfg, attr, p.cta2 != 0);
+    auto launch = [&](auto kern) -> cudaError_t {
+        cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e2 != cudaSuccess) return e2;
+        return cudaLaunchKernelEx(&cfg, kern, pl.maps[0], pl.maps[1], pl.maps[2], pl.maps[3], p);
+    };
+    cudaError_t e;
+    switch (cls * 2 + (p.cta2 ? 1 : 0)) {
+        case 0: e = launch(umma_gemm_kernel<0, 0, 0>); break;
+        case 1: e = launch(umma_gemm_kernel<0, 0, 1>); break;
+        case 2: e = launch(umma_gemm_kernel<0, 1, 0>); break;
+        case 3: e = launch(umma_gemm_kernel<0, 1, 1>); break;
+        case 4: e = launch(umma_gemm_kernel<1, 0, 0>); break;
+        case 5: e = launch(umma_gemm_kernel<1, 0, 1>); break;
+        case 6: e = launch(umma_gemm_kernel<1, 1, 0>); break;
+        default: e = launch(umma_gemm_kernel<1, 1, 1>); break;
+    }
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "umma_gemm launch");
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "umma_gemm launch");
+    count_launch(ctx);
+    return RTEN_OK;
+}
+
+// Launch whatever umma_gemm launches are pending on this context (one: the plain kernel; several: the sequence kernel).
+rten_status seq_flush(rten_ctx* ctx) {
+    if (!ctx->seq_pending) return RTEN_OK;
+    auto* q = reinterpret_cast<std::vector<PendingLaunch>*>(ctx->seq_pending);
+    if (q->empty()) return RTEN_OK;
+    std::vector<PendingLaunch> items;
+    items.swap(*q);  // (re-entrancy: launch paths below call seq_flush through launch_stream)
+    const int cls = ctx->seq_class;
+    if (items.size() == 1) return launch_single(ctx, cls, items[0]);
+    if (!ctx->seq_gbar) {
+        cudaError_t ce = cudaMalloc(&ctx->seq_gbar, 256);
+        if (ce != cudaSuccess) return fail_cuda(ctx, ce, "sequence barrier");
+        ce = cudaMemset(ctx->seq_gbar, 0, 256);
+        if (ce != cudaSuccess) return fail_cuda(ctx, ce, "sequence barrier");
+    }
+    std::unique_ptr<SeqParams> sp(new SeqParams());
+    memset(sp.get(), 0, sizeof(SeqParams));
+    sp->n = (int)items.size();
+    sp->gbar = reinterpret_cast<unsigned*>(ctx->seq_gbar);
+    int grid = 1;
+    for (size_t i = 0; i < items.size(); i++) {
+        sp->layer[i] = items[i].p;
+        for (int m = 0; m < 4; m++) sp->maps[i][m] = items[i].maps[m];
+        grid = std::max(grid, std::min(items[i].p.units_total, ctx->num_sms));
+    }
+    if (getenv("RTEN_B200_VERBOSE")) fprintf(stderr, "[umma_seq] %d layers in one kernel, grid %d, class %d\n", sp->n, grid, cls);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = 227 * 1024;  // one CTA per SM by construction: every CTA of the grid is resident (grid barrier)
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[2];
+    fill_launch_attrs(cfg, attr, false);
+    auto launch = [&](auto kern) -> cudaError_t {
+        cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e2 != cudaSuccess) return e2;
+        return cudaLaunchKernelEx(&cfg, kern, *sp);
+    };
+    cudaError_t e;
+    switch (cls) {
+        case 0: e = launch(umma_seq_kernel<0, 0>); break;
+        case 1: e = launch(umma_seq_kernel<0, 1>); break;
+        case 2: e = launch(umma_seq_kernel<1, 0>); break;
+        default: e = launch(umma_seq_kernel<1, 1>); break;
+    }
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "umma_seq launch");
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "umma_seq launch");
+    count_launch(ctx);
+    return RTEN_OK;
+}
+
+// `ws`: split-K workspace of at least splitk_ws_bytes() (null: taken from the op's temporaries)
+static rten_status launch_plan(rten_ctx* ctx, const GemmLaunch& L, const Prepared& q, const Plan& pl, bool verbose,
+                               void* ws = nullptr, bool no_defer = false) {
     PlanShape ps;
     if (!plan_shape(q, pl, ps)) return RTEN_ERR_UNSUPPORTED_VALUE;
     KParams p = q.p;
@@ -1050,6 +1375,7 @@ static rten_status launch_plan(rten_ctx* ctx, const GemmLaunch& L, const Prepare
     p.ksplit = pl.ksplit;
     p.splitk = pl.splitk;
     p.acc1 = pl.acc1;
+    p.cta2 = pl.cta2;
     p.nbuf = pl.nbuf;
     p.tma_store = q.tma_store;
     p.res_tma = (q.res_tma && pl.splitk == 1) ? 1 : 0;
@@ -1061,28 +1387,21 @@ static rten_status launch_plan(rten_ctx* ctx, const GemmLaunch& L, const Prepare
     const int n_stg = 2 * p.nbuf;
     p.atom_bytes = ps.atom_bytes;
     p.stage_bytes = ps.stage_bytes;
-    p.tx_bytes = (p.pair ? 2 : 1) * q.a_rows * KBYTES + p.bn * KBYTES;  // per 128-byte K block
+    p.tx_bytes = (p.pair ? 2 : 1) * q.a_rows * KBYTES + (p.bn >> p.cta2) * KBYTES;  // per 128-byte K block and CTA
     p.stages = std::min(MAX_STAGES, smem_budget_for(n_stg) / (int)p.stage_bytes);
     if (p.stages < 2) return RTEN_ERR_UNSUPPORTED_VALUE;
     if (L.kind == 0)
-        p.idesc = make_idesc(1 /*F32*/, 2 /*TF32*/, 2, BM, p.bn);
+        p.idesc = make_idesc(1 /*F32*/, 2 /*TF32*/, 2, BM << p.cta2, p.bn);
     else
-        p.idesc = make_idesc(2 /*S32*/, L.a_signed ? 1 : 0, L.b_signed ? 1 : 0, BM, p.bn);
+        p.idesc = make_idesc(2 /*S32*/, L.a_signed ? 1 : 0, L.b_signed ? 1 : 0, BM << p.cta2, p.bn);
     if (p.splitk > 1) {
-        if (!ctx->sk_counters) {
-            cudaError_t ce = cudaMalloc(&ctx->sk_counters, SK_CNT_INTS * sizeof(int));
-            if (ce != cudaSuccess) return fail_cuda(ctx, ce, "split-K counters");
-            ce = cudaMemset(ctx->sk_counters, 0, SK_CNT_INTS * sizeof(int));
-            if (ce != cudaSuccess) return fail_cuda(ctx, ce, "split-K counters");
-        }
-        void* ws = nullptr;
-        const size_t ws_bytes = (size_t)ps.tiles * 2 * p.splitk * (p.bn / 32) * 4096 * 4;
-        RTB_TRY(temp_alloc(ctx, ws_bytes, &ws));
+        RTB_TRY(ensure_splitk_counters(ctx));
+        if (!ws) RTB_TRY(temp_alloc(ctx, splitk_ws_bytes(ps, pl), &ws));
         p.sk_ws = reinterpret_cast<uint32_t*>(ws);
         p.sk_cnt = reinterpret_cast<int*>(ctx->sk_counters);
     }
 
-    uint32_t bbox[4] = {(uint32_t)q.kelems, (uint32_t)p.bn, 1, 1}, bes[4] = {1, 1, 1, 1}, des[4] = {1, 1, 1, 1};
+    uint32_t bbox[4] = {(uint32_t)q.kelems, (uint32_t)(p.bn >> p.cta2), 1, 1}, bes[4] = {1, 1, 1, 1}, des[4] = {1, 1, 1, 1};
     CUtensorMap map_a, map_b;
     if (!encode_map(ctx, &map_a, L.a, q.esize, L.kind == 0, q.abox, q.aes)) return RTEN_ERR_UNSUPPORTED_VALUE;
     if (!encode_map(ctx, &map_b, L.b, q.esize, L.kind == 0, bbox, bes)) return RTEN_ERR_UNSUPPORTED_VALUE;
@@ -1099,23 +1418,10 @@ static rten_status launch_plan(rten_ctx* ctx, const GemmLaunch& L, const Prepare
     }
 
     if (verbose)
-        fprintf(stderr, "[umma_gemm] kind=%d conv=%d M=%d N=%d K=%d kb=%d tiles_m=%d bn=%d pair=%d ksplit=%d katoms=%d splitk=%d acc1=%d units=%d stages=%d tma_store=%d res_tma=%d nbuf=%d box=%dx%dx%d\n",
-                L.kind, L.conv, L.M, L.N, L.K, p.k_blocks, p.tiles_m, p.bn, p.pair, p.ksplit, p.katoms, p.splitk, p.acc1,
+        fprintf(stderr, "[umma_gemm] kind=%d conv=%d M=%d N=%d K=%d kb=%d tiles_m=%d bn=%d pair=%d ksplit=%d katoms=%d splitk=%d acc1=%d cta2=%d units=%d stages=%d tma_store=%d res_tma=%d nbuf=%d box=%dx%dx%d\n",
+                L.kind, L.conv, L.M, L.N, L.K, p.k_blocks, p.tiles_m, p.bn, p.pair, p.ksplit, p.katoms, p.splitk, p.acc1, p.cta2,
                 p.units_total, p.stages, p.tma_store, p.res_tma, p.nbuf, p.tw, p.th, p.tb);
-    const size_t smem_bytes = (size_t)p.stages * p.stage_bytes + n_stg * STG_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-    const int grid = std::min(p.units_total, ctx->num_sms);
-    cudaError_t e;
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(NUM_THREADS);
-    cfg.dynamicSmemBytes = smem_bytes;
-    cfg.stream = ctx->stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = getenv("RTEN_B200_NO_PDL") ? 0 : 1;
+    const size_t smem_bytes = (size_t)p.stages * p.stage_bytes + n_stg * STG_BYTES + 1024 /*align*/ + 1024 /*barriers*/;
     // specialised epilogue when every chunk qualifies for the register fast path
     const EpilogueDesc& ee = L.epi;
     bool fastk = p.tma_store && (L.N % 32) == 0 && !ctx->trace && !getenv("RTEN_B200_NO_FAST");
@@ -1124,20 +1430,25 @@ static rten_status launch_plan(rten_ctx* ctx, const GemmLaunch& L, const Prepare
                 (ee.bias_kind != 1 || (reinterpret_cast<uintptr_t>(ee.bias) & 15) == 0);
     else
         fastk = fastk && !ee.za && !ee.zb && !ee.scale;
-    auto launch = [&](auto kern) -> cudaError_t {
-        cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e2 != cudaSuccess) return e2;
-        return cudaLaunchKernelEx(&cfg, kern, map_a, map_b, map_d, map_r, p);
-    };
-    if (L.kind == 0)
-        e = fastk ? launch(umma_gemm_kernel<0, 1>) : launch(umma_gemm_kernel<0, 0>);
-    else
-        e = fastk ? launch(umma_gemm_kernel<1, 1>) : launch(umma_gemm_kernel<1, 0>);
-    if (e != cudaSuccess) return fail_cuda(ctx, e, "umma_gemm launch");
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return fail_cuda(ctx, e, "umma_gemm launch");
-    count_launch(ctx);
-    return RTEN_OK;
+    PendingLaunch pend;
+    pend.p = p;
+    pend.maps[0] = map_a;
+    pend.maps[1] = map_b;
+    pend.maps[2] = map_d;
+    pend.maps[3] = map_r;
+    pend.smem_bytes = smem_bytes;
+    const int cls = L.kind * 2 + (fastk ? 1 : 0);
+    // Inside graph capture consecutive launches are collected and run as ONE sequence kernel (see umma_seq_kernel)
+    if (ctx->capturing && !p.cta2 && !ctx->trace && !no_defer && !getenv("RTEN_B200_NO_SEQ")) {
+        auto* q2 = pending_of(ctx);
+        if (!q2->empty() && ctx->seq_class != cls) RTB_TRY(seq_flush(ctx));
+        ctx->seq_class = cls;
+        q2->push_back(pend);
+        if ((int)q2->size() == SEQ_MAX) RTB_TRY(seq_flush(ctx));
+        return RTEN_OK;
+    }
+    RTB_TRY(seq_flush(ctx));
+    return launch_single(ctx, cls, pend);
 }
 
 // Problem signature for the autotune cache: everything that changes which plan is fastest.
@@ -1162,6 +1473,7 @@ static Plan plan_from_array(const std::array<int, 8>& a) {
     pl.splitk = a[4];
     pl.nbuf = a[5];
     pl.acc1 = a[6];
+    pl.cta2 = a[7];
     return pl;
 }
 
@@ -1175,19 +1487,21 @@ rten_status launch_umma_gemm(rten_ctx* ctx, const GemmLaunch& L) {
     Plan plan = cands[0].second;
 
     const bool forced = getenv("RTEN_B200_FORCE_BN") || getenv("RTEN_B200_FORCE_PAIR") || getenv("RTEN_B200_FORCE_KATOMS") ||
-                        getenv("RTEN_B200_FORCE_SPLITK");
+                        getenv("RTEN_B200_FORCE_SPLITK") || getenv("RTEN_B200_FORCE_CTA2");
     if (forced) {
         // debugging / sweeps: the best-ranked candidate that matches every forced field
         const char* fb = getenv("RTEN_B200_FORCE_BN");
         const char* fp = getenv("RTEN_B200_FORCE_PAIR");
         const char* fk = getenv("RTEN_B200_FORCE_KATOMS");
         const char* fs = getenv("RTEN_B200_FORCE_SPLITK");
+        const char* fc = getenv("RTEN_B200_FORCE_CTA2");
         for (const auto& c : cands) {
             const Plan& x = c.second;
             if (fb && x.bn != atoi(fb)) continue;
             if (fp && x.pair != (atoi(fp) ? 1 : 0)) continue;
             if (fk && x.katoms != atoi(fk)) continue;
             if (fs && x.splitk != atoi(fs)) continue;
+            if (fc && x.cta2 != (atoi(fc) ? 1 : 0)) continue;
             plan = x;
             break;
         }
@@ -1206,30 +1520,44 @@ rten_status launch_umma_gemm(rten_ctx* ctx, const GemmLaunch& L) {
                 cudaEvent_t e0, e1;
                 cudaEventCreate(&e0);
                 cudaEventCreate(&e1);
-                const size_t ncand = std::min<size_t>(cands.size(), 20);
+                const size_t ncand = std::min<size_t>(cands.size(), 24);
+                // one split-K workspace for every candidate (allocating inside the timed launches would time cudaMalloc)
+                size_t ws_max = 0;
+                for (size_t i = 0; i < ncand; i++) {
+                    PlanShape ps;
+                    if (plan_shape(q, cands[i].second, ps)) ws_max = std::max(ws_max, splitk_ws_bytes(ps, cands[i].second));
+                }
+                void* ws = nullptr;
+                if (ws_max) {
+                    RTB_TRY(ensure_splitk_counters(ctx));
+                    RTB_TRY(temp_alloc(ctx, ws_max, &ws));
+                    cudaStreamSynchronize(ctx->stream);
+                }
                 double best_ms = 1e30;
-                const int reps = 3;
+                int reps = 4;  // raised after the first candidate so that every timed window is >= ~150 us (event resolution)
                 for (size_t i = 0; i < ncand; i++) {
                     const Plan& x = cands[i].second;
-                    if (launch_plan(ctx, L, q, x, false) != RTEN_OK) continue;  // warm-up (also validates the plan)
+                    if (launch_plan(ctx, L, q, x, false, ws) != RTEN_OK) continue;  // warm-up (also validates the plan)
                     cudaEventRecord(e0, ctx->stream);
                     bool ok = true;
-                    for (int r = 0; r < reps && ok; r++) ok = launch_plan(ctx, L, q, x, false) == RTEN_OK;
+                    for (int r = 0; r < reps && ok; r++) ok = launch_plan(ctx, L, q, x, false, ws) == RTEN_OK;
                     cudaEventRecord(e1, ctx->stream);
                     if (cudaEventSynchronize(e1) != cudaSuccess || !ok) continue;
                     float ms = 0.f;
                     cudaEventElapsedTime(&ms, e0, e1);
+                    ms /= reps;
                     if (verbose)
-                        fprintf(stderr, "[autotune] bn=%d pair=%d katoms=%d splitk=%d model=%.0f -> %.2f us\n", x.bn, x.pair,
-                                x.katoms, x.splitk, cands[i].first, ms * 1e3 / reps);
+                        fprintf(stderr, "[autotune] bn=%d pair=%d katoms=%d splitk=%d cta2=%d model=%.0f -> %.2f us\n", x.bn, x.pair,
+                                x.katoms, x.splitk, x.cta2, cands[i].first, ms * 1e3);
                     if (ms < best_ms) {
                         best_ms = ms;
                         plan = x;
                     }
+                    reps = std::max(4, std::min(32, (int)(0.15 / std::max(best_ms, 1e-3))));
                 }
                 cudaEventDestroy(e0);
                 cudaEventDestroy(e1);
-                ctx->tune_cache[key] = {plan.bn, plan.pair, plan.katoms, plan.ksplit, plan.splitk, plan.nbuf, plan.acc1, 0};
+                ctx->tune_cache[key] = {plan.bn, plan.pair, plan.katoms, plan.ksplit, plan.splitk, plan.nbuf, plan.acc1, plan.cta2};
             }
         }
     }

@@ -332,9 +332,13 @@ def check_plans(rt, oracle):
     import os
     ctx = rt.Context(0)
     r = oracle.XorShiftRng(99)
-    keys = ("RTEN_B200_FORCE_BN", "RTEN_B200_FORCE_PAIR", "RTEN_B200_FORCE_KATOMS", "RTEN_B200_FORCE_SPLITK")
-    plans = [dict(), dict(BN=64, PAIR=1), dict(BN=128, PAIR=0, KATOMS=2), dict(BN=256, PAIR=1), dict(BN=128, PAIR=1, SPLITK=2),
-             dict(BN=64, PAIR=0, SPLITK=3), dict(BN=256, PAIR=1, SPLITK=2), dict(BN=96, PAIR=0, SPLITK=4, KATOMS=2)]
+    keys = ("RTEN_B200_FORCE_BN", "RTEN_B200_FORCE_PAIR", "RTEN_B200_FORCE_KATOMS", "RTEN_B200_FORCE_SPLITK", "RTEN_B200_FORCE_CTA2")
+    plans = [dict(), dict(BN=64, PAIR=1, CTA2=0), dict(BN=128, PAIR=0, KATOMS=2, CTA2=0), dict(BN=256, PAIR=1, CTA2=0),
+             dict(BN=128, PAIR=1, SPLITK=2, CTA2=0), dict(BN=64, PAIR=0, SPLITK=3, CTA2=0), dict(BN=256, PAIR=1, SPLITK=2, CTA2=0),
+             dict(BN=96, PAIR=0, SPLITK=4, KATOMS=2, CTA2=0),
+             # CTA pairs (tcgen05.mma.cta_group::2, 256-row tiles, half of B per CTA)
+             dict(BN=128, PAIR=0, CTA2=1), dict(BN=256, PAIR=0, CTA2=1), dict(BN=256, PAIR=1, CTA2=1), dict(BN=64, PAIR=1, CTA2=1, KATOMS=2),
+             dict(BN=128, PAIR=0, CTA2=1, SPLITK=2), dict(BN=256, PAIR=1, CTA2=1, SPLITK=2), dict(BN=96, PAIR=0, CTA2=1)]
     a8 = r.u8((300, 2048))
     b8 = r.i8((2048, 512))
     az, bz = r.u8((300,)), r.i8((512,))
@@ -368,6 +372,74 @@ def check_plans(rt, oracle):
         worst = max(worst, _conv_case(rt, oracle, ctx2, (8, 512, 7, 7), (512, 512, 3, 3), pads=(1, 1, 1, 1), cl=True, prepack=True, act=1))
         worst = max(worst, _conv_case(rt, oracle, ctx2, (8, 512, 7, 7), (512, 512, 3, 3), pads=(1, 1, 1, 1), cl=True, residual=True, act=1))
     return f"worst err/bound {worst:.3f}"
+
+
+# ------------------------------------------------------------------------------------------
+def check_sequence(rt, oracle):
+    """Inside graph capture consecutive tensor-core launches are fused into persistent sequence kernels (grid barrier
+    between layers).  Replaying the graph must reproduce the eager results bit for bit (same plans, same arithmetic),
+    for chains shorter and longer than one kernel's layer capacity, with residual links, and more than once."""
+    ctx = rt.Context(0)
+    r = oracle.XorShiftRng(321)
+
+    def conv_layer(ci, co, k, res=None, act=1):
+        w = r.uniform((co, ci, k, k), -1, 1) / np.float32(np.sqrt(ci * k * k))
+        b = r.uniform((co,))
+        op = rt.Conv(1, (1, 1), (k // 2,) * 4, (1, 1), activation=act)
+        return dict(op=op, w=ctx.to_device(w), b=ctx.to_device(b), pk=op.prepack(ctx, 1, w), res=res)
+
+    # a: bottleneck-like chain with residual links (index of the producing layer, -1 = the input)
+    chain_a = [conv_layer(64, 128, 1), conv_layer(128, 128, 3), conv_layer(128, 128, 1, res=0), conv_layer(128, 64, 3),
+               conv_layer(64, 256, 1), conv_layer(256, 64, 1), conv_layer(64, 64, 3, res=5), conv_layer(64, 512, 1, act=0)]
+    # b: longer than SEQ_MAX layers -> split over several sequence kernels
+    chain_b = [conv_layer(64, 64, 1, res=(i - 2 if i >= 2 and i % 3 == 0 else None)) for i in range(45)]
+    x = ctx.to_device(r.uniform((4, 64, 28, 28)), channels_last=True)
+
+    def run_chain(chain, outs):
+        h, produced = x, []
+        for i, l in enumerate(chain):
+            res = None if l["res"] is None else (x if l["res"] < 0 else produced[l["res"]])
+            y = l["op"].run(ctx, h, l["w"], l["b"], packed_w=l["pk"], residual=res, out=(outs[i] if outs else None))
+            produced.append(y)
+            h = y
+        return produced
+
+    worst_layers = 0
+    for name, chain in (("a", chain_a), ("b", chain_b)):
+        eager = run_chain(chain, None)
+        want = [t.numpy() for t in eager]
+        for t in eager:  # poison the buffers: the replay has to recompute everything
+            t.copy_from(np.full(t.shape, np.nan, np.float32))
+        l0 = ctx.launches
+        ctx.graph_begin()
+        run_chain(chain, eager)
+        g = ctx.graph_end()
+        for rep in range(3):
+            if rep:
+                eager[-1].copy_from(np.full(eager[-1].shape, np.nan, np.float32))
+            g.launch()
+            ctx.sync()
+            for i, (t, w) in enumerate(zip(eager, want)):
+                assert_bit_exact(t.numpy(), w, f"sequence chain {name} layer {i} replay {rep}")
+        worst_layers = max(worst_layers, len(chain))
+    # integer launches in one capture (independent problems, one sequence kernel)
+    a8 = [r.u8((200, 512)) for _ in range(3)]
+    b8 = [r.i8((512, 160)) for _ in range(3)]
+    az, bz = r.u8((200,)), r.i8((160,))
+    outs = [rt.MatMulInteger().run(ctx, a, b, az, bz) for a, b in zip(a8, b8)]
+    want = [oracle.matmul_integer(a, b, az, bz) for a, b in zip(a8, b8)]
+    da, db, dz, dbz = [ctx.to_device(a) for a in a8], [ctx.to_device(b) for b in b8], ctx.to_device(az), ctx.to_device(bz)
+    for o in outs:
+        o.copy_from(np.zeros(o.shape, np.int32))
+    ctx.graph_begin()
+    for a, b, o in zip(da, db, outs):
+        rt.MatMulInteger().run(ctx, a, b, dz, dbz, out=o)
+    g = ctx.graph_end()
+    g.launch()
+    ctx.sync()
+    for o, w in zip(outs, want):
+        assert_bit_exact(o.numpy(), w, "sequence MatMulInteger")
+    return f"chains of up to {worst_layers} layers replayed bit-exactly"
 
 
 # ------------------------------------------------------------------------------------------
@@ -567,5 +639,5 @@ ALL_CHECKS = [
     ("dql", check_dql), ("glue", check_glue), ("matmul_small", check_matmul_small), ("matmul_shapes", check_matmul_shapes),
     ("matmul_bert", check_matmul_bert), ("gemm_op", check_gemm_op), ("matmul_integer", check_matmul_integer),
     ("conv_basic", check_conv_basic), ("conv_stride", check_conv_stride), ("conv_more", check_conv_more),
-    ("conv_integer", check_conv_integer), ("plans", check_plans), ("resnet50_model", check_resnet50_model), ("bert_model", check_bert_model),
+    ("conv_integer", check_conv_integer), ("plans", check_plans), ("sequence", check_sequence), ("resnet50_model", check_resnet50_model), ("bert_model", check_bert_model),
 ]

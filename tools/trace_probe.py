@@ -28,6 +28,8 @@ def trace(fn, name):
     t = np.frombuffer(buf, dtype=np.int64).reshape(4, 2048)
     ph = t[3][1024:1032].copy()
     t[3][1024:1032] = 0
+    marks = t[3][1100:1105].copy()
+    t[3][1100:1105] = 0
     issue_cost = t[3][680:1360]
     commit_cost = t[3][1364:2044]
     t[3][680:] = 0
@@ -37,6 +39,11 @@ def trace(fn, name):
         print(f"   MMA thread: wait-done->4(8) MMAs issued median {np.median(ic):.0f} clk; commit issue median {np.median(cc):.0f} clk")
     t0 = min(prod.min(), mma.min())
     print(f"== {name}: {len(prod)} k-blocks, {len(e0)} tiles on CTA 0; total {(max(e1.max(), mma.max()) - t0)} clk")
+    if marks[0] > 0:
+        m0 = marks[0]
+        print(f"   timeline (clk from kernel entry): set-up done {marks[1] - m0}, predecessor done {marks[2] - m0}, first TMA issued {prod.min() - m0}, "
+              f"first operands landed {mma.min() - m0}, first epilogue start {e0.min() - m0 if len(e0) else -1}, last epilogue end {e1.max() - m0 if len(e1) else -1}, "
+              f"thread 0 done {marks[3] - m0}, exit {marks[4] - m0}")
     if len(prod) > 1:
         d = np.diff(prod)
         print(f"   producer slot-acquire interval: median {np.median(d):.0f} mean {d.mean():.0f} max {d.max()}  first 12: {d[:12].tolist()}")
@@ -74,8 +81,10 @@ def gemm_case(m, n, k):
 
 
 trace(gemm_case(4096, 4096, 4096), "gemm 4096^3")
-trace(gemm_case(2048, 768, 3072), "gemm 2048x768x3072")
 trace(conv_case(64, 64, 3, 1, 1, 56), "conv 3x3 64->64 @56")
 trace(conv_case(64, 256, 1, 1, 0, 56), "conv 1x1 64->256 @56")
 trace(conv_case(256, 64, 1, 1, 0, 56), "conv 1x1 256->64 @56")
+trace(conv_case(128, 128, 3, 1, 1, 28), "conv 3x3 128->128 @28")
+trace(conv_case(256, 256, 3, 1, 1, 14), "conv 3x3 256->256 @14")
+trace(conv_case(1024, 256, 1, 1, 0, 14), "conv 1x1 1024->256 @14")
 trace(conv_case(512, 512, 3, 1, 1, 7), "conv 3x3 512->512 @7")
