@@ -171,6 +171,13 @@ rten_status rten_b200_conv_integer(rten_ctx* ctx, const rten_tensor* x, const rt
                                    const rten_packed* packed_w_or_null, const rten_tensor* x_zero_point_or_null,
                                    const rten_tensor* w_zero_point_or_null, const rten_tensor* scale_or_null,
                                    const rten_conv_params* p, rten_tensor* out);
+/* ConvIntegerToFloat followed by the graph's Add(bias [O]), Add(residual, same shape as the output) and Relu
+ * (activation 0 / 1), executed in the kernel epilogue as the same sequence of exactly rounded f32 operations
+ * (mul, add, add, max) -- bit-identical to running the three operators separately.  Requires `scale`. */
+rten_status rten_b200_conv_integer_ex(rten_ctx* ctx, const rten_tensor* x, const rten_tensor* w, const rten_packed* packed_w,
+                                      const rten_tensor* x_zero_point, const rten_tensor* w_zero_point,
+                                      const rten_tensor* scale, const rten_conv_params* params, const rten_tensor* bias,
+                                      const rten_tensor* residual, int activation, rten_tensor* out);
 
 /* Softmax (src/ops/norm.rs:825-899) and AddSoftmax (src/ops/attention.rs:30-165) when mask != NULL
  * (mask broadcast to x, added lane-wise before the softmax over `axis`; AddSoftmax uses axis -1).
@@ -193,6 +200,8 @@ rten_status rten_b200_dynamic_quantize_linear(rten_ctx* ctx, const rten_tensor* 
 rten_status rten_b200_relu(rten_ctx* ctx, const rten_tensor* x, rten_tensor* out);
 /* Add with numpy broadcasting (src/ops/binary_elementwise.rs). */
 rten_status rten_b200_add(rten_ctx* ctx, const rten_tensor* a, const rten_tensor* b, rten_tensor* out);
+/* Mul (src/ops/binary_elementwise.rs), f32, numpy broadcasting. */
+rten_status rten_b200_mul(rten_ctx* ctx, const rten_tensor* a, const rten_tensor* b, rten_tensor* out);
 /* MaxPool 2-D (src/ops/pooling.rs): kernel {kh,kw}; pads/strides as conv; padding never wins. */
 rten_status rten_b200_max_pool(rten_ctx* ctx, const rten_tensor* x, const int32_t kernel[2], const int32_t pads[4],
                                const int32_t strides[2], rten_tensor* out);

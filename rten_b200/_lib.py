@@ -83,6 +83,8 @@ _SIGNATURES = {
     "rten_b200_dynamic_quantize_linear": (C.c_int, [_vp, _TP, _TP, _TP, _TP, _vp]),
     "rten_b200_relu": (C.c_int, [_vp, _TP, _TP]),
     "rten_b200_add": (C.c_int, [_vp, _TP, _TP, _TP]),
+    "rten_b200_mul": (C.c_int, [_vp, _TP, _TP, _TP]),
+    "rten_b200_conv_integer_ex": (C.c_int, [_vp, _TP, _TP, _vp, _TP, _TP, _TP, C.POINTER(RtenConvParams), _TP, _TP, C.c_int, _TP]),
     "rten_b200_max_pool": (C.c_int, [_vp, _TP, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), _TP]),
     "rten_b200_global_average_pool": (C.c_int, [_vp, _TP, _TP]),
     "rten_b200_gather_rows": (C.c_int, [_vp, _TP, _TP, _TP]),

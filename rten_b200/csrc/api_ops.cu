@@ -1218,11 +1218,23 @@ rten_status rten_b200_conv2d(rten_ctx* ctx, const rten_tensor* x, const rten_ten
 rten_status rten_b200_conv_integer(rten_ctx* ctx, const rten_tensor* x, const rten_tensor* w, const rten_packed* pw,
                                    const rten_tensor* x_zp, const rten_tensor* w_zp, const rten_tensor* scale,
                                    const rten_conv_params* p, rten_tensor* out) {
+    return rten_b200_conv_integer_ex(ctx, x, w, pw, x_zp, w_zp, scale, p, nullptr, nullptr, 0, out);
+}
+
+rten_status rten_b200_conv_integer_ex(rten_ctx* ctx, const rten_tensor* x, const rten_tensor* w, const rten_packed* pw,
+                                      const rten_tensor* x_zp, const rten_tensor* w_zp, const rten_tensor* scale,
+                                      const rten_conv_params* p, const rten_tensor* bias, const rten_tensor* residual,
+                                      int activation, rten_tensor* out) {
     RTB_TRY(check_ctx(ctx));
     if (!x || !w || !p || !out) return fail(ctx, RTEN_ERR_MISSING_INPUTS, "missing inputs");
     auto is8 = [](int dt) { return dt == RTEN_U8 || dt == RTEN_I8; };
     if (!is8(x->dtype) || !is8(w->dtype)) return fail(ctx, RTEN_ERR_UNSUPPORTED_TYPE, "unsupported type");
     if (scale && scale->dtype != RTEN_F32) return fail(ctx, RTEN_ERR_CAST_FAILED, "scale must be float");
+    if ((bias || residual || activation) && !scale)
+        return fail(ctx, RTEN_ERR_INVALID_VALUE, "bias / residual / activation follow the float conversion: a scale is required");
+    if ((bias && bias->dtype != RTEN_F32) || (residual && residual->dtype != RTEN_F32))
+        return fail(ctx, RTEN_ERR_UNSUPPORTED_TYPE, "unsupported type");
+    if (activation < 0 || activation > 1) return fail(ctx, RTEN_ERR_UNSUPPORTED_VALUE, "only Relu can follow an integer convolution");
     OpScope sc(ctx);
     ConvArgs A{};
     A.kind = 1;
@@ -1233,6 +1245,9 @@ rten_status rten_b200_conv_integer(rten_ctx* ctx, const rten_tensor* x, const rt
     A.x_zp = x_zp;
     A.w_zp = w_zp;
     A.scale = scale;
+    A.bias = bias;
+    A.residual = residual;
+    A.act = activation;
     return sc.finish(conv_core(sc, A, out));
 }
 
@@ -1482,7 +1497,8 @@ rten_status rten_b200_gelu(rten_ctx* ctx, const rten_tensor* x, int approximate,
 rten_status rten_b200_relu(rten_ctx* ctx, const rten_tensor* x, rten_tensor* out) { return unary_op(ctx, UNARY_RELU, x, out); }
 
 // ---- Add ----------------------------------------------------------------------------------------------
-rten_status rten_b200_add(rten_ctx* ctx, const rten_tensor* a, const rten_tensor* b, rten_tensor* out) {
+// Add / Mul with numpy broadcasting (src/ops/binary_elementwise.rs); flags: 0 = Add, 2 = Mul
+static rten_status binary_f32(rten_ctx* ctx, const rten_tensor* a, const rten_tensor* b, rten_tensor* out, int flags) {
     RTB_TRY(check_ctx(ctx));
     if (!a || !b || !out) return fail(ctx, RTEN_ERR_MISSING_INPUTS, "missing inputs");
     if (a->dtype != RTEN_F32 || b->dtype != RTEN_F32) return fail(ctx, RTEN_ERR_UNSUPPORTED_TYPE, "unsupported type");
@@ -1511,17 +1527,24 @@ rten_status rten_b200_add(rten_ctx* ctx, const rten_tensor* a, const rten_tensor
         for (int i = 0; i < nd && flat; i++)
             if (ov.shape[i] != 1 && ov.strides[i] != av.strides[i]) flat = false;
         if (flat) {
-            st = launch_add_flat(ctx, (const float*)av.data, (const float*)bv.data, (float*)ov.data, numel(&ov), 0);
+            st = launch_add_flat(ctx, (const float*)av.data, (const float*)bv.data, (float*)ov.data, numel(&ov), flags);
         } else {
             long long shp[RTEN_MAX_DIMS], sd[RTEN_MAX_DIMS];
             for (int i = 0; i < nd; i++) {
                 shp[i] = shape[i];
                 sd[i] = ov.strides[i];
             }
-            st = launch_nd_add(ctx, (const float*)av.data, (const float*)bv.data, (float*)ov.data, nd, shp, sa, sb, sd, 0);
+            st = launch_nd_add(ctx, (const float*)av.data, (const float*)bv.data, (float*)ov.data, nd, shp, sa, sb, sd, flags);
         }
     }
     return sc.finish(st);
+}
+
+rten_status rten_b200_add(rten_ctx* ctx, const rten_tensor* a, const rten_tensor* b, rten_tensor* out) {
+    return binary_f32(ctx, a, b, out, 0);
+}
+rten_status rten_b200_mul(rten_ctx* ctx, const rten_tensor* a, const rten_tensor* b, rten_tensor* out) {
+    return binary_f32(ctx, a, b, out, 2);
 }
 
 // ---- DynamicQuantizeLinear ---------------------------------------------------------------------------
@@ -1534,11 +1557,20 @@ rten_status rten_b200_dynamic_quantize_linear(rten_ctx* ctx, const rten_tensor* 
     OpScope sc(ctx);
     rten_tensor xv, xc, yv, sv, zv;
     rten_status st = sc.in(x, &xv);
-    if (st == RTEN_OK) st = sc.contiguous(&xv, &xc);
-    if (st == RTEN_OK) st = sc.out(y, RTEN_U8, xv.ndim, xv.shape, &yv, nullptr);
+    // The op is elementwise plus an order-independent min / max: a DENSE input in any dim order (e.g. channels-last
+    // activations) is processed in memory order and the quantised output keeps the input's strides.
+    bool dense = st == RTEN_OK && span_elems(&xv) == numel(&xv) && y->data == nullptr;
+    for (int i = 0; i < xv.ndim && dense; i++)
+        if (xv.strides[i] <= 0 && xv.shape[i] > 1) dense = false;
+    if (dense) {
+        xc = xv;
+    } else if (st == RTEN_OK) {
+        st = sc.contiguous(&xv, &xc);
+    }
+    if (st == RTEN_OK) st = sc.out(y, RTEN_U8, xv.ndim, xv.shape, &yv, dense ? xv.strides : nullptr);
     if (st == RTEN_OK) st = sc.out(scale, RTEN_F32, 0, nullptr, &sv, nullptr);
     if (st == RTEN_OK) st = sc.out(zero_point, RTEN_U8, 0, nullptr, &zv, nullptr);
-    if (st == RTEN_OK && !is_contiguous(&yv)) st = fail(ctx, RTEN_ERR_UNSUPPORTED_OUTPUT, "quantized output must be contiguous");
+    if (st == RTEN_OK && !dense && !is_contiguous(&yv)) st = fail(ctx, RTEN_ERR_UNSUPPORTED_OUTPUT, "quantized output must be contiguous");
     if (st == RTEN_OK) {
         const long long n = numel(&xv);
         if (n == 0) {

@@ -385,8 +385,8 @@ nd_add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* _
             bo += idx * p.sb[k];
             dof += idx * p.sd[k];
         }
-        float v = __fadd_rn(a[ao], b[bo]);
-        if (relu) v = v > 0.0f ? v : 0.0f;
+        float v = (relu & 2) ? __fmul_rn(a[ao], b[bo]) : __fadd_rn(a[ao], b[bo]);  // flags: 1 = Relu after, 2 = Mul
+        if (relu & 1) v = v > 0.0f ? v : 0.0f;
         d[dof] = v;
     }
 }
@@ -398,8 +398,9 @@ add_flat_kernel(const float* __restrict__ a, const float* __restrict__ b, float*
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
         const float4 x = reinterpret_cast<const float4*>(a)[i];
         const float4 y = reinterpret_cast<const float4*>(b)[i];
-        float4 o = make_float4(__fadd_rn(x.x, y.x), __fadd_rn(x.y, y.y), __fadd_rn(x.z, y.z), __fadd_rn(x.w, y.w));
-        if (relu) {
+        float4 o = (relu & 2) ? make_float4(__fmul_rn(x.x, y.x), __fmul_rn(x.y, y.y), __fmul_rn(x.z, y.z), __fmul_rn(x.w, y.w))
+                              : make_float4(__fadd_rn(x.x, y.x), __fadd_rn(x.y, y.y), __fadd_rn(x.z, y.z), __fadd_rn(x.w, y.w));
+        if (relu & 1) {
             o.x = o.x > 0.f ? o.x : 0.f;
             o.y = o.y > 0.f ? o.y : 0.f;
             o.z = o.z > 0.f ? o.z : 0.f;
@@ -408,8 +409,8 @@ add_flat_kernel(const float* __restrict__ a, const float* __restrict__ b, float*
         reinterpret_cast<float4*>(d)[i] = o;
     }
     for (long long j = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
-        float v = __fadd_rn(a[j], b[j]);
-        if (relu) v = v > 0.f ? v : 0.f;
+        float v = (relu & 2) ? __fmul_rn(a[j], b[j]) : __fadd_rn(a[j], b[j]);
+        if (relu & 1) v = v > 0.f ? v : 0.f;
         d[j] = v;
     }
 }

@@ -360,7 +360,7 @@ __device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* t
         uint8_t* stg0 = stg_base + grp * nbuf * STG_BYTES;
         const bool issuer = (q == 0 && lane == 0);
         const bool has_bias = e.bias_kind == 1;
-        const float relu_floor = e.act == 1 ? 0.0f : -__int_as_float(0x7f800000);
+        const bool do_relu = e.act == 1;  // (no activation: NaNs must pass through, fmaxf would drop them)
         uint32_t ci = 0;
         uint32_t& rphase = st.rphase;
         for (int u = worker; u < p.units_total; u += n_workers, st.it++) {
@@ -388,6 +388,25 @@ __device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* t
             for (int sub = 0; owner && sub <= p.pair; sub++) {
                 const TileCoord tc = decode_tile(p, t, sub, cta_rank);
                 const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_STRIDE + sub * p.bn;
+                // integer zero-point terms of this thread's row:  C = acc - za*colsum[n] - zb[n]*(rowsum - K*za)
+                unsigned za_v = 0, t_m = 0;
+                if (KIND == 1 && (e.za || e.zb)) {
+                    int m_idx;
+                    bool row_ok;
+                    if (p.conv) {
+                        const int xi = r % p.tw, r2 = r / p.tw, yi = r2 % p.th, bi = r2 / p.th;
+                        const int ox = tc.ox0 + xi, oy = tc.oy0 + yi, b = tc.b0 + bi;
+                        row_ok = (bi < p.tb) && (ox < p.OW) && (oy < p.OH) && (b < p.Bn);
+                        m_idx = (b * p.OH + oy) * p.OW + ox;
+                    } else {
+                        m_idx = tc.m0 + r;
+                        row_ok = m_idx < p.M;
+                    }
+                    if (row_ok) {
+                        if (e.za) za_v = (unsigned)e.za[m_idx % e.za_len];
+                        if (e.zb) t_m = (unsigned)e.rowsum[m_idx] - (unsigned)p.K * za_v;
+                    }
+                }
                 for (int c0 = grp * 32; c0 < p.bn; c0 += 64) {
                     uint32_t v[32];
                     if (p.splitk > 1)
@@ -447,7 +466,52 @@ __device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* t
                             for (int u = 0; u < 4; u++) {
                                 float x = __uint_as_float(v[j + u]) * e.alpha;
                                 x = fmaf(e.r_scale, r4[u], x);
-                                v[j + u] = __float_as_uint(fmaxf(x + b4[u], relu_floor));
+                                x = x + b4[u];
+                                v[j + u] = __float_as_uint(do_relu ? fmaxf(x, 0.0f) : x);
+                            }
+                        }
+                    } else if (e.za || e.zb || e.scale) {
+                        // exact i32 arithmetic with wrap-around (unsigned ops), column vectors fetched 128 bits at a time
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            uint4 cs = make_uint4(0u, 0u, 0u, 0u), zb4 = make_uint4(0u, 0u, 0u, 0u);
+                            float4 sc = make_float4(1.f, 1.f, 1.f, 1.f);
+                            if (e.za) cs = __ldg(reinterpret_cast<const uint4*>(e.colsum + nbase + j));
+                            if (e.zb) {
+                                if (e.zb_len == 1) {
+                                    const unsigned z = (unsigned)__ldg(e.zb);
+                                    zb4 = make_uint4(z, z, z, z);
+                                } else {
+                                    zb4 = __ldg(reinterpret_cast<const uint4*>(e.zb + nbase + j));
+                                }
+                            }
+                            if (e.scale) {
+                                if (e.scale_len == 1) {
+                                    const float z = __ldg(e.scale);
+                                    sc = make_float4(z, z, z, z);
+                                } else {
+                                    sc = __ldg(reinterpret_cast<const float4*>(e.scale + nbase + j));
+                                }
+                            }
+                            float4 rr = make_float4(0.f, 0.f, 0.f, 0.f), bb = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (p.res_tma) rr = *reinterpret_cast<const float4*>(rowp + (((j >> 2) ^ sw) << 4));
+                            if (has_bias) bb = __ldg(reinterpret_cast<const float4*>(e.bias + nbase + j));
+                            const unsigned c4[4] = {cs.x, cs.y, cs.z, cs.w}, z4[4] = {zb4.x, zb4.y, zb4.z, zb4.w};
+                            const float s4[4] = {sc.x, sc.y, sc.z, sc.w}, r4[4] = {rr.x, rr.y, rr.z, rr.w},
+                                        b4[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+                            for (int u = 0; u < 4; u++) {
+                                const unsigned c = v[j + u] - za_v * c4[u] - z4[u] * t_m;
+                                if (e.scale) {
+                                    // ConvIntegerToFloat / MatMulIntegerToFloat, then the graph's Add(bias), Add(residual),
+                                    // Relu as separate exactly-rounded f32 operations (no contraction)
+                                    float x = __fmul_rn(__int2float_rn((int)c), s4[u]);
+                                    if (has_bias) x = __fadd_rn(x, b4[u]);
+                                    if (p.res_tma) x = __fadd_rn(x, r4[u]);
+                                    v[j + u] = __float_as_uint(do_relu ? fmaxf(x, 0.0f) : x);
+                                } else {
+                                    v[j + u] = c;
+                                }
                             }
                         }
                     }
@@ -629,7 +693,7 @@ __device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* t
                 if (fast && e.bias_kind == 1) fast = (reinterpret_cast<uintptr_t>(e.bias + nbase) & 15) == 0;
                 fast = __all_sync(0xffffffffu, fast || !row_ok) || p.res_tma;  // (res_tma launches are fast-path only)
                 if (KIND == 0 && fast && row_ok) {
-                    const float relu_floor = e.act == 1 ? 0.0f : -__int_as_float(0x7f800000);
+                    const bool do_relu = e.act == 1;  // (no activation: NaNs must pass through, fmaxf would drop them)
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
                         float4 rr = make_float4(0.f, 0.f, 0.f, 0.f), bb = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -644,7 +708,7 @@ __device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* t
                             float x = __uint_as_float(v[j + u]) * e.alpha;
                             x = fmaf(e.r_scale, r4[u], x);
                             x = x + b4[u] + row_bias;
-                            v[j + u] = __float_as_uint(fmaxf(x, relu_floor));
+                            v[j + u] = __float_as_uint(do_relu ? fmaxf(x, 0.0f) : x);
                         }
                     }
                 }
@@ -681,7 +745,14 @@ __device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* t
                                 c -= zbv * (unsigned)rs_v;
                                 if (e.za) c += (unsigned)p.K * (unsigned)za_v * zbv;
                             }
-                            *sp = e.scale ? __float_as_uint(__int2float_rn((int)c) * e.scale[n % e.scale_len]) : c;
+                            if (e.scale) {
+                                float x = __fmul_rn(__int2float_rn((int)c), e.scale[n % e.scale_len]);
+                                if (e.bias_kind == 1) x = __fadd_rn(x, e.bias[n]);
+                                if (e.r) x = __fadd_rn(x, __ldcg(e.r + r_off + (long long)n * e.r_col));
+                                *sp = __float_as_uint(apply_act(x, e.act));
+                            } else {
+                                *sp = c;
+                            }
                         }
                     }
                 }
@@ -1212,7 +1283,7 @@ static rten_status prepare_launch(rten_ctx* ctx, const GemmLaunch& L, Prepared& 
         ord.strides[2] = e.r_z0;
         ord.strides[3] = e.r_z1;
     }
-    q.res_tma = (q.tma_store && L.kind == 0 && e.r && e.r_col == 1 && e.act <= 1 && (L.N % 32) == 0 &&
+    q.res_tma = (q.tma_store && (L.kind == 0 || e.scale) && e.r && e.r_col == 1 && e.act <= 1 && (L.N % 32) == 0 &&
                  (e.bias_kind != 1 || (reinterpret_cast<uintptr_t>(e.bias) & 15) == 0) && tma_compatible(ord, 4, 4))
                     ? 1
                     : 0;
@@ -1428,8 +1499,13 @@ static rten_status launch_plan(rten_ctx* ctx, const GemmLaunch& L, const Prepare
     if (L.kind == 0)
         fastk = fastk && ee.act <= 1 && ee.bias_kind != 2 && (ee.r == nullptr || p.res_tma) &&
                 (ee.bias_kind != 1 || (reinterpret_cast<uintptr_t>(ee.bias) & 15) == 0);
-    else
-        fastk = fastk && !ee.za && !ee.zb && !ee.scale;
+    else  // integer: column vectors must be 128-bit loadable, zero-point / scale vectors per column or scalar
+        fastk = fastk && ee.act <= 1 && ee.bias_kind != 2 && (ee.r == nullptr || p.res_tma) &&
+                (ee.bias_kind != 1 || (reinterpret_cast<uintptr_t>(ee.bias) & 15) == 0) &&
+                (!ee.za || (reinterpret_cast<uintptr_t>(ee.colsum) & 15) == 0) &&
+                (!ee.zb || ee.zb_len == 1 || (ee.zb_len == L.N && (reinterpret_cast<uintptr_t>(ee.zb) & 15) == 0)) &&
+                (!ee.scale || ee.scale_len == 1 || (ee.scale_len == L.N && (reinterpret_cast<uintptr_t>(ee.scale) & 15) == 0));
+    if (L.kind == 1 && !fastk) p.res_tma = 0;  // the generic integer epilogue reads the residual from global memory
     PendingLaunch pend;
     pend.p = p;
     pend.maps[0] = map_a;
@@ -1438,8 +1514,13 @@ static rten_status launch_plan(rten_ctx* ctx, const GemmLaunch& L, const Prepare
     pend.maps[3] = map_r;
     pend.smem_bytes = smem_bytes;
     const int cls = L.kind * 2 + (fastk ? 1 : 0);
-    // Inside graph capture consecutive launches are collected and run as ONE sequence kernel (see umma_seq_kernel)
-    if (ctx->capturing && !p.cta2 && !ctx->trace && !no_defer && !getenv("RTEN_B200_NO_SEQ")) {
+    // Opt-in (RTEN_B200_SEQ=1): inside graph capture consecutive launches are collected and run as ONE sequence kernel
+    // (umma_seq_kernel).  Measured on B200 (tools/boundary_probe.py): a layer boundary inside the sequence kernel costs
+    // ~2.3 us MORE than a programmatic-dependent-launch kernel boundary (drain + grid barrier + cold operand pipe are not
+    // cheaper than what PDL already overlaps), so separate launches stay the default.
+    const char* seq_env = getenv("RTEN_B200_SEQ");
+    const bool seq_on = seq_env && atoi(seq_env) != 0;
+    if (seq_on && ctx->capturing && !p.cta2 && !ctx->trace && !no_defer) {
         auto* q2 = pending_of(ctx);
         if (!q2->empty() && ctx->seq_class != cls) RTB_TRY(seq_flush(ctx));
         ctx->seq_class = cls;

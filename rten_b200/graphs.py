@@ -152,6 +152,114 @@ class ResNet50Runner:
 
 
 # ---------------------------------------------------------------------------------------------
+# ResNet-50 int8 (BASELINE configs[3]): the graph `tools/ort-quantize.py dynamic --quantize-conv` produces, after
+# RTen's fusions (src/optimize/fusions.rs:966-1058): every Conv becomes
+#     DynamicQuantizeLinear(x) -> Mul(x_scale, w_scale) -> ConvIntegerToFloat(x_q, w_q, x_zp, -, scale) -> Add(bias)
+# followed by the original Add(identity) / Relu; the classifier becomes DynamicQuantizeLinear -> MatMulIntegerToFloat ->
+# Add(bias).  Weights: symmetric int8, 7-bit range (`reduce_range=True`), one scale per tensor for convolutions
+# (ConvIntegerToFloat takes a scalar scale, src/ops/conv.rs:571-577) and per output column for the MatMul
+# (`per_channel=True`); their zero points are 0, so the optional w_zero_point input is omitted.
+# ---------------------------------------------------------------------------------------------
+
+
+@dataclass
+class QConvSpec:
+    wq: np.ndarray      # int8 OIHW
+    w_scale: np.ndarray  # f32 scalar (0-d)
+    b: np.ndarray
+    stride: int
+    pad: int
+
+
+@dataclass
+class ResNet50Int8Spec:
+    stem: QConvSpec
+    blocks: List[Bottleneck]  # of QConvSpec
+    fc_wq: np.ndarray      # int8 [2048, 1000] (K x N)
+    fc_w_scale: np.ndarray  # f32 [1000]
+    fc_b: np.ndarray
+
+
+def _quantize_sym(w: np.ndarray, axis=None):
+    """Symmetric int8 with the reduced 7-bit range; `axis` = dims reduced for the scale (None: whole tensor)."""
+    amax = np.max(np.abs(w), axis=axis, keepdims=axis is not None).astype(np.float32)
+    scale = (np.maximum(amax, np.float32(1e-12)) / np.float32(64.0)).astype(np.float32)
+    q = np.clip(np.rint(w / scale), -64, 64).astype(np.int8)
+    return q, scale
+
+
+def quantize_resnet50(spec: ResNet50Spec) -> ResNet50Int8Spec:
+    def qc(c: ConvSpec):
+        q, s = _quantize_sym(c.w)
+        return QConvSpec(q, np.asarray(s, np.float32).reshape(()), c.b, c.stride, c.pad)
+
+    blocks = [Bottleneck(qc(b.c1), qc(b.c2), qc(b.c3), qc(b.down) if b.down is not None else None) for b in spec.blocks]
+    wq, ws = _quantize_sym(np.ascontiguousarray(spec.fc_w.T), axis=0)
+    return ResNet50Int8Spec(qc(spec.stem), blocks, wq, ws.reshape(-1).astype(np.float32), spec.fc_b)
+
+
+class ResNet50Int8Runner:
+    """configs[3] on one GPU.  `fuse=True` folds Add(bias) / Add(identity) / Relu into the integer convolution's
+    epilogue (same f32 roundings, rten_b200_conv_integer_ex); `fuse=False` issues them as separate operators."""
+
+    def __init__(self, ctx: O.Context, spec: ResNet50Int8Spec, fuse: bool = True):
+        self.ctx, self.spec, self.fuse = ctx, spec, fuse
+        self._convs = {}
+
+        def prep(c: QConvSpec):
+            op = O.ConvIntegerToFloat(1, (1, 1), (c.pad, c.pad, c.pad, c.pad), (c.stride, c.stride))
+            w = ctx.to_device(c.wq)
+            self._convs[id(c)] = (op, w, ctx.to_device(c.b), op.prepack(ctx, 1, w), ctx.to_device(c.w_scale),
+                                  ctx.to_device(c.b.reshape(1, -1, 1, 1)))
+
+        prep(spec.stem)
+        for b in spec.blocks:
+            for c in (b.c1, b.c2, b.c3, b.down):
+                if c is not None:
+                    prep(c)
+        self.fc_w = ctx.to_device(spec.fc_wq)
+        self.fc_pk = O.MatMulInteger().prepack(ctx, 1, self.fc_w)
+        self.fc_scale, self.fc_b = ctx.to_device(spec.fc_w_scale), ctx.to_device(spec.fc_b)
+        self.maxpool = O.MaxPool((3, 3), (1, 1, 1, 1), (2, 2))
+        self.gap = O.GlobalAveragePool()
+        self.dql, self.mul, self.add, self.relu = O.DynamicQuantizeLinear(), O.Mul(), O.Add(), O.Relu()
+        self.fc = O.MatMulIntegerToFloat()
+
+    def _conv(self, c: QConvSpec, x, relu: bool, residual=None):
+        op, w, b, pk, ws, b4 = self._convs[id(c)]
+        ctx = self.ctx
+        xq, xs, xz = self.dql.run(ctx, x)
+        scale = self.mul.run(ctx, xs, ws)
+        if self.fuse:
+            op.activation = O.ACT_RELU if relu else O.ACT_NONE
+            return op.run(ctx, xq, w, xz, None, scale, packed_w=pk, bias=b, residual=residual)
+        op.activation = O.ACT_NONE
+        y = op.run(ctx, xq, w, xz, None, scale, packed_w=pk)
+        y = self.add.run(ctx, y, b4)
+        if residual is not None:
+            y = self.add.run(ctx, y, residual)
+        if relu:
+            y = self.relu.run(ctx, y, in_place=True)
+        return y
+
+    def run(self, x: O.DeviceTensor) -> O.DeviceTensor:
+        s, ctx = self.spec, self.ctx
+        y = self._conv(s.stem, x, True)
+        y = self.maxpool.run(ctx, y)
+        for b in s.blocks:
+            ident = y if b.down is None else self._conv(b.down, y, False)
+            t = self._conv(b.c1, y, True)
+            t = self._conv(b.c2, t, True)
+            y = self._conv(b.c3, t, True, residual=ident)
+        p = self.gap.run(ctx, y)
+        p = p.reshape(p.shape[0], p.shape[1])
+        pq, ps, pz = self.dql.run(ctx, p)
+        scale = self.mul.run(ctx, ps, self.fc_scale)
+        y = self.fc.run(ctx, pq, self.fc_w, pz, None, scale, packed_b=self.fc_pk)
+        return self.add.run(ctx, y, self.fc_b)
+
+
+# ---------------------------------------------------------------------------------------------
 # BERT-base (HF layout, post-fusion): 12 layers, H=768, 12 heads x 64, FFN 3072, eps 1e-12
 # ---------------------------------------------------------------------------------------------
 

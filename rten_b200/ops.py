@@ -418,14 +418,18 @@ class ConvInteger(Conv):
 class ConvIntegerToFloat(Conv):
     """src/ops/conv.rs:535-587"""
 
-    def run(self, ctx, x, w, x_zero_point, w_zero_point, scale, packed_w: Optional[Packed] = None, out=None):
+    def run(self, ctx, x, w, x_zero_point, w_zero_point, scale, packed_w: Optional[Packed] = None, out=None,
+            bias=None, residual=None):
+        """`bias` / `residual` / `self.activation` = the Add(bias), Add(identity), Relu nodes that follow the operator in
+        a quantised ResNet, executed in the epilogue with the same f32 roundings (rten_b200_conv_integer_ex)."""
         if scale is None:
             raise OpError(4, "missing inputs")
         A = _Args(ctx)
         o = A.out(out)
         p = _conv_params(self.padding, self.groups, self.strides, self.dilations)
-        ctx.check(ctx.lib.rten_b200_conv_integer(ctx.handle, A.t(x), A.t(w), _ph(packed_w), A.t(x_zero_point),
-                                                 A.t(w_zero_point), A.t(scale), C.byref(p), C.byref(o)))
+        ctx.check(ctx.lib.rten_b200_conv_integer_ex(ctx.handle, A.t(x), A.t(w), _ph(packed_w), A.t(x_zero_point),
+                                                    A.t(w_zero_point), A.t(scale), C.byref(p), A.t(bias), A.t(residual),
+                                                    self.activation, C.byref(o)))
         return A.wrap(o, out)
 
 
@@ -522,6 +526,16 @@ class Add:
         A = _Args(ctx)
         o = A.out(out)
         ctx.check(ctx.lib.rten_b200_add(ctx.handle, A.t(a), A.t(b), C.byref(o)))
+        return A.wrap(o, out)
+
+
+class Mul:
+    """src/ops/binary_elementwise.rs Mul (f32, broadcasting)."""
+
+    def run(self, ctx, a, b, out=None):
+        A = _Args(ctx)
+        o = A.out(out)
+        ctx.check(ctx.lib.rten_b200_mul(ctx.handle, A.t(a), A.t(b), C.byref(o)))
         return A.wrap(o, out)
 
 

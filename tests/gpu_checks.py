@@ -378,7 +378,17 @@ def check_plans(rt, oracle):
 def check_sequence(rt, oracle):
     """Inside graph capture consecutive tensor-core launches are fused into persistent sequence kernels (grid barrier
     between layers).  Replaying the graph must reproduce the eager results bit for bit (same plans, same arithmetic),
-    for chains shorter and longer than one kernel's layer capacity, with residual links, and more than once."""
+    for chains shorter and longer than one kernel's layer capacity, with residual links, and more than once.
+    (The sequence kernel is opt-in through RTEN_B200_SEQ=1, set here for the duration of the check.)"""
+    import os
+    os.environ["RTEN_B200_SEQ"] = "1"
+    try:
+        return _check_sequence(rt, oracle)
+    finally:
+        os.environ.pop("RTEN_B200_SEQ", None)
+
+
+def _check_sequence(rt, oracle):
     ctx = rt.Context(0)
     r = oracle.XorShiftRng(321)
 
@@ -586,6 +596,62 @@ def check_conv_integer(rt, oracle):
     return "ok"
 
 
+def check_conv_integer_fused(rt, oracle):
+    """ConvIntegerToFloat with the following Add(bias) / Add(identity) / Relu folded into the epilogue must be
+    bit-identical to the separate operators (exact f32 mul, add, add, max), channels-last and NCHW, all plan kinds."""
+    ctx = rt.Context(0)
+    r = oracle.XorShiftRng(77)
+    worst = 0
+    for (xs, ws, pads, strides, cl) in [((2, 64, 14, 14), (128, 64, 1, 1), (0, 0, 0, 0), (1, 1), True),
+                                        ((2, 64, 14, 14), (64, 64, 3, 3), (1, 1, 1, 1), (1, 1), True),
+                                        ((3, 32, 9, 9), (48, 32, 3, 3), (1, 1, 1, 1), (2, 2), False),
+                                        ((2, 128, 7, 7), (96, 128, 1, 1), (0, 0, 0, 0), (1, 1), True)]:
+        x = r.u8(xs)
+        w = r.i8(ws)
+        xz = np.uint8(121)
+        scale = np.float32(0.0173)
+        bias = r.uniform((ws[0],))
+        op = rt.ConvIntegerToFloat(1, (1, 1), pads, strides)
+        base = oracle.conv_integer_to_float(x, w, xz, None, scale, padding=list(pads), groups=1, strides=strides, dilations=(1, 1))
+        res = r.uniform(base.shape)
+        xd = ctx.to_device(x, channels_last=cl)
+        for use_res in (False, True):
+            for act in (0, 1):
+                want = oracle.add(base, bias.reshape(1, -1, 1, 1))
+                if use_res:
+                    want = oracle.add(want, res)
+                if act:
+                    want = oracle.relu(want)
+                op.activation = act
+                got = op.run(ctx, xd, w, xz, None, scale, bias=bias, residual=(ctx.to_device(res, channels_last=cl) if use_res else None)).numpy()
+                assert_bit_exact(got, want, f"ConvIntegerToFloat fused x{xs} w{ws} res={use_res} act={act} cl={cl}")
+                worst += 1
+    # Mul (used for x_scale * w_scale)
+    a, b = r.uniform((5, 1, 7)), r.uniform((3, 1))
+    assert_bit_exact(rt.Mul().run(ctx, a, b).numpy(), (a * b).astype(np.float32), "Mul broadcast")
+    return f"{worst} fused cases bit-exact"
+
+
+def check_resnet50_int8_model(rt, oracle):
+    """configs[3]: dynamically quantised ResNet-50 (DynamicQuantizeLinear -> ConvIntegerToFloat -> Add -> Relu ...), full
+    224x224 images.  Every operator on this path is exact integer or exactly rounded f32 arithmetic, so the logits must
+    be BIT-IDENTICAL to the CPU oracle's, fused or not."""
+    from rten_b200 import graphs
+    import model_ref
+    ctx = rt.Context(0)
+    rng = oracle.XorShiftRng(5678)
+    spec = graphs.make_resnet50(lambda s: rng.uniform(s))
+    q = graphs.quantize_resnet50(spec)
+    x = oracle.XorShiftRng(4321).uniform((2, 3, 224, 224))
+    ref = model_ref.resnet50_int8_oracle(oracle, q, x)
+    for fuse in (True, False):
+        got = graphs.ResNet50Int8Runner(ctx, q, fuse=fuse).run(ctx.to_device(x, channels_last=True)).numpy()
+        assert_bit_exact(got, ref, f"ResNet-50 int8 logits (fuse={fuse})")
+    f32 = model_ref.resnet50_oracle(oracle, spec, x)
+    drift = float(np.abs(ref - f32).max() / np.abs(f32).max())
+    return f"bit-exact; int8 vs fp32 model drift {drift:.3f} of max |logit|"
+
+
 def check_resnet50_model(rt, oracle):
     """Whole-model parity (ResNet-50 fp32, full 224x224 images, batch 2): every conv runs single-pass TF32,
     so the logits carry ~53 layers of 2^-11-relative operand rounding.  Stated tolerance: max |d| <= 1e-2 * max |ref|."""
@@ -639,5 +705,6 @@ ALL_CHECKS = [
     ("dql", check_dql), ("glue", check_glue), ("matmul_small", check_matmul_small), ("matmul_shapes", check_matmul_shapes),
     ("matmul_bert", check_matmul_bert), ("gemm_op", check_gemm_op), ("matmul_integer", check_matmul_integer),
     ("conv_basic", check_conv_basic), ("conv_stride", check_conv_stride), ("conv_more", check_conv_more),
-    ("conv_integer", check_conv_integer), ("plans", check_plans), ("sequence", check_sequence), ("resnet50_model", check_resnet50_model), ("bert_model", check_bert_model),
+    ("conv_integer", check_conv_integer), ("plans", check_plans), ("sequence", check_sequence), ("conv_integer_fused", check_conv_integer_fused),
+    ("resnet50_int8_model", check_resnet50_int8_model), ("resnet50_model", check_resnet50_model), ("bert_model", check_bert_model),
 ]

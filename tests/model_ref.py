@@ -21,6 +21,34 @@ def resnet50_oracle(oracle, spec, x):
     return oracle.gemm_op(p.reshape(p.shape[0], p.shape[1]), spec.fc_w, spec.fc_b, 1.0, 1.0, False, True)
 
 
+def resnet50_int8_oracle(oracle, qspec, x):
+    """configs[3] (rten_b200/graphs.py ResNet50Int8Runner) with the reference's operators, unfused, NCHW."""
+    f32 = np.float32
+
+    def conv(c, t, relu, residual=None):
+        tq, ts, tz = oracle.dynamic_quantize_linear(t)
+        scale = f32(ts) * f32(c.w_scale)
+        y = oracle.conv_integer_to_float(tq, c.wq, tz, None, scale, padding=[c.pad] * 4, groups=1,
+                                         strides=(c.stride, c.stride), dilations=(1, 1))
+        y = oracle.add(y, c.b.reshape(1, -1, 1, 1))
+        if residual is not None:
+            y = oracle.add(y, residual)
+        return oracle.relu(y) if relu else y
+
+    y = conv(qspec.stem, x, True)
+    y = oracle.max_pool(y, (3, 3), [1, 1, 1, 1], (2, 2))
+    for b in qspec.blocks:
+        ident = y if b.down is None else conv(b.down, y, False)
+        t = conv(b.c1, y, True)
+        t = conv(b.c2, t, True)
+        y = conv(b.c3, t, True, residual=ident)
+    p = oracle.global_average_pool(y)
+    p = p.reshape(p.shape[0], p.shape[1])
+    pq, ps, pz = oracle.dynamic_quantize_linear(p)
+    scale = (f32(ps) * qspec.fc_w_scale).astype(f32)
+    return oracle.add(oracle.matmul_integer_to_float(pq, qspec.fc_wq, pz, None, scale), qspec.fc_b)
+
+
 def bert_oracle(oracle, spec, input_ids, token_type_ids, add_mask):
     B, S = input_ids.shape
     H, nh = spec.hidden, spec.heads
