@@ -408,6 +408,13 @@ def secondary_numbers(ctx, rt, graphs, oracle, model, stream, torch, flush):
         x = ctx.to_device(inp["x"], channels_last=True)
         ms = timed(lambda: runner.run(x))
         out["resnet50_fp32_b32_img_per_sec"] = 32 / (ms / 1e3)
+    del runner
+    # configs[3]: dynamically quantised ResNet-50, batch 64 (DynamicQuantizeLinear -> ConvIntegerToFloat(+bias, +identity, Relu))
+    rspec = spec if other == "resnet50" else make_spec(oracle, "resnet50")
+    qrunner = graphs.ResNet50Int8Runner(ctx, graphs.quantize_resnet50(rspec), fuse=True)
+    x64 = ctx.to_device(make_inputs(oracle, "resnet50", 64)["x"], channels_last=True)
+    ms = timed(lambda: qrunner.run(x64))
+    out["resnet50_int8_b64_img_per_sec"] = 64 / (ms / 1e3)
     return out
 
 

@@ -145,6 +145,13 @@ rten_status rten_b200_matmul_integer(rten_ctx* ctx, const rten_tensor* a, const 
                                      const rten_packed* packed_b_or_null, const rten_tensor* a_zero_point_or_null,
                                      const rten_tensor* b_zero_point_or_null, const rten_tensor* scale_or_null,
                                      rten_tensor* out);
+/* MatMulIntegerToFloat followed by the graph's Add(bias [N]), Add(residual, same shape as the output) and activation
+ * (rten_activation) in the epilogue, as separate exactly rounded f32 operations in that order -- bit-identical to the
+ * unfused operators.  Requires `scale`. */
+rten_status rten_b200_matmul_integer_ex(rten_ctx* ctx, const rten_tensor* a, const rten_tensor* b, const rten_packed* packed_b,
+                                        const rten_tensor* a_zero_point, const rten_tensor* b_zero_point,
+                                        const rten_tensor* scale, const rten_tensor* bias, const rten_tensor* residual,
+                                        int activation, rten_tensor* out);
 
 /* Conv (src/ops/conv.rs:124-419).  x NCHW (or NCW), w OIHW, bias [O].  pads = {top,left,bottom,right};
  * auto_pad_same != 0 => `Padding::Same` (pads ignored).  n_spatial = 1 or 2 gives the expected
@@ -190,11 +197,21 @@ rten_status rten_b200_layer_norm(rten_ctx* ctx, const rten_tensor* x, const rten
 /* Erf / Gelu (src/ops/unary_elementwise.rs:384-435); approximate != 0 => tanh form. */
 rten_status rten_b200_erf(rten_ctx* ctx, const rten_tensor* x, rten_tensor* out);
 rten_status rten_b200_gelu(rten_ctx* ctx, const rten_tensor* x, int approximate, rten_tensor* out);
+/* Communicator of a batch-sharded run (one process per GPU).  The reference has no counterpart (single process, rayon
+ * threads); it exists so that DynamicQuantizeLinear can use the range of the WHOLE tensor when the batch is split over
+ * ranks.  NCCL (libnccl.so.2) is resolved with dlopen at the first call; rank 0 creates the 128-byte id, the host
+ * distributes it (any side channel), every rank calls comm_create with the same id. */
+typedef struct rten_comm rten_comm;
+rten_status rten_b200_comm_unique_id(void* id_out_128_bytes);
+rten_status rten_b200_comm_create(rten_ctx* ctx, const void* id_128_bytes, int rank, int world_size, rten_comm** out);
+void rten_b200_comm_destroy(rten_comm* comm);
+
 /* DynamicQuantizeLinear (src/ops/quantize.rs:352-468): y u8, scale f32 scalar, zero_point u8 scalar.
- * nccl_comm_or_null: when the batch is sharded over ranks, all-reduce (min,max) over this
- * ncclComm_t first so every rank picks the unsharded tensor's scale/zero point. */
+ * comm_or_null (a rten_comm*): when the batch is sharded over ranks, the local (min, max) is all-reduced over the ranks
+ * first -- integer min / max on an order-preserving encoding, exact -- so every rank picks the unsharded tensor's scale
+ * and zero point and the sharded outputs stay bit-identical to the unsharded reference's. */
 rten_status rten_b200_dynamic_quantize_linear(rten_ctx* ctx, const rten_tensor* x, rten_tensor* y,
-                                              rten_tensor* scale, rten_tensor* zero_point, void* nccl_comm_or_null);
+                                              rten_tensor* scale, rten_tensor* zero_point, void* comm_or_null);
 
 /* ---- residency glue so whole models stay in HBM ------------------------------ */
 rten_status rten_b200_relu(rten_ctx* ctx, const rten_tensor* x, rten_tensor* out);

@@ -433,7 +433,9 @@ void rto_gemm_f32(size_t M, size_t N, size_t K, const float *a, ptrdiff_t a_rs, 
     int nt = threads_for(M * N * K);
 #pragma omp parallel if (nt > 1) num_threads(nt)
     {
-        float *bp = (float *)aligned_alloc(64, (size_t)KC * NR * sizeof(float));
+        static __thread float *bp_buf = NULL;
+        if (!bp_buf) bp_buf = (float *)aligned_alloc(64, (size_t)KC * NR * sizeof(float));
+        float *bp = bp_buf;
 #pragma omp for schedule(dynamic, 1) collapse(2)
         for (size_t jt = 0; jt < n_col_tiles; jt++)
             for (size_t ib = 0; ib < n_row_blocks; ib++) {
@@ -489,7 +491,6 @@ void rto_gemm_f32(size_t M, size_t N, size_t K, const float *a, ptrdiff_t a_rs, 
                     }
                 }
             }
-        free(bp);
     }
 }
 
@@ -597,10 +598,19 @@ static void conv_f32_one(const float *xi, const float *wg, const float *bg, floa
     if (pointwise) {
         rto_gemm_f32(og, Ncol, Kd, wg, (ptrdiff_t)Kd, 1, xi, (ptrdiff_t)Ncol, 1, yo, 1.0f, 0.0f, bg, bg ? 2 : 0);
     } else {
-        float *col = (float *)malloc(Kd * Ncol * sizeof(float));
+        /* per-thread scratch that only grows: a fresh multi-megabyte malloc per image and layer means mmap + page
+         * faults every time, which serialises many-core hosts on the kernel's address-space lock */
+        static __thread float *col_buf = NULL;
+        static __thread size_t col_cap = 0;
+        size_t need = Kd * Ncol;
+        if (need > col_cap) {
+            free(col_buf);
+            col_buf = (float *)malloc(need * sizeof(float));
+            col_cap = need;
+        }
+        float *col = col_buf;
         im2col_f32(xi, cg, H, W, kh, kw, oh, ow, pads[0], pads[1], strides[0], strides[1], dil[0], dil[1], col);
         rto_gemm_f32(og, Ncol, Kd, wg, (ptrdiff_t)Kd, 1, col, (ptrdiff_t)Ncol, 1, yo, 1.0f, 0.0f, bg, bg ? 2 : 0);
-        free(col);
     }
 }
 
@@ -627,7 +637,9 @@ void rto_conv_f32(const float *x, const float *w, const float *bias, float *y, s
 #ifdef _OPENMP
         omp_set_max_active_levels(2);
 #endif
-        g_team = nthreads / outer;
+        /* threads inside each image's GEMM only when there are few images: nested teams are re-created for every
+         * GEMM call by the OpenMP runtime, which costs more than it gains once >= 8 images run side by side */
+        g_team = units >= 8 ? 1 : nthreads / outer;
         if (g_team < 1) g_team = 1;
 #pragma omp parallel for schedule(dynamic, 1) collapse(2) num_threads(outer)
         for (size_t n = 0; n < B; n++)

@@ -73,6 +73,7 @@ _SIGNATURES = {
     "rten_b200_matmul": (C.c_int, [_vp, _TP, _TP, _vp, _TP, C.c_float, _TP]),
     "rten_b200_matmul_ex": (C.c_int, [_vp, _TP, _TP, _vp, _TP, C.c_float, _TP, C.c_int, _TP]),
     "rten_b200_matmul_integer": (C.c_int, [_vp, _TP, _TP, _vp, _TP, _TP, _TP, _TP]),
+    "rten_b200_matmul_integer_ex": (C.c_int, [_vp, _TP, _TP, _vp, _TP, _TP, _TP, _TP, _TP, C.c_int, _TP]),
     "rten_b200_conv2d": (C.c_int, [_vp, _TP, _TP, _vp, _TP, C.POINTER(RtenConvParams), _TP]),
     "rten_b200_conv2d_ex": (C.c_int, [_vp, _TP, _TP, _vp, _TP, C.POINTER(RtenConvParams), _TP, C.c_int, _TP]),
     "rten_b200_conv_integer": (C.c_int, [_vp, _TP, _TP, _vp, _TP, _TP, _TP, C.POINTER(RtenConvParams), _TP]),
@@ -81,6 +82,9 @@ _SIGNATURES = {
     "rten_b200_erf": (C.c_int, [_vp, _TP, _TP]),
     "rten_b200_gelu": (C.c_int, [_vp, _TP, C.c_int, _TP]),
     "rten_b200_dynamic_quantize_linear": (C.c_int, [_vp, _TP, _TP, _TP, _TP, _vp]),
+    "rten_b200_comm_unique_id": (C.c_int, [_vp]),
+    "rten_b200_comm_create": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.POINTER(_vp)]),
+    "rten_b200_comm_destroy": (None, [_vp]),
     "rten_b200_relu": (C.c_int, [_vp, _TP, _TP]),
     "rten_b200_add": (C.c_int, [_vp, _TP, _TP, _TP]),
     "rten_b200_mul": (C.c_int, [_vp, _TP, _TP, _TP]),

@@ -1141,8 +1141,18 @@ rten_status rten_b200_matmul(rten_ctx* ctx, const rten_tensor* a, const rten_ten
 rten_status rten_b200_matmul_integer(rten_ctx* ctx, const rten_tensor* a, const rten_tensor* b, const rten_packed* pb,
                                      const rten_tensor* a_zp, const rten_tensor* b_zp, const rten_tensor* scale,
                                      rten_tensor* out) {
+    return rten_b200_matmul_integer_ex(ctx, a, b, pb, a_zp, b_zp, scale, nullptr, nullptr, 0, out);
+}
+
+rten_status rten_b200_matmul_integer_ex(rten_ctx* ctx, const rten_tensor* a, const rten_tensor* b, const rten_packed* pb,
+                                        const rten_tensor* a_zp, const rten_tensor* b_zp, const rten_tensor* scale,
+                                        const rten_tensor* bias, const rten_tensor* residual, int activation,
+                                        rten_tensor* out) {
     RTB_TRY(check_ctx(ctx));
     if (!a || !b || !out) return fail(ctx, RTEN_ERR_MISSING_INPUTS, "missing inputs");
+    if ((bias || residual || activation) && !scale)
+        return fail(ctx, RTEN_ERR_INVALID_VALUE, "bias / residual / activation follow the float conversion: a scale is required");
+    if (activation < 0 || activation > 3) return fail(ctx, RTEN_ERR_INVALID_VALUE, "unknown activation");
     auto is8 = [](int dt) { return dt == RTEN_U8 || dt == RTEN_I8; };
     if (!is8(a->dtype) || !is8(b->dtype)) return fail(ctx, RTEN_ERR_UNSUPPORTED_TYPE, "unsupported type");
     const int64_t a_rows = a->ndim > 1 ? a->shape[a->ndim - 2] : 1;
@@ -1185,6 +1195,20 @@ rten_status rten_b200_matmul_integer(rten_ctx* ctx, const rten_tensor* a, const 
             A.epi.scale_len = (int)len;
         }
     }
+    rten_tensor biasv, biasc;
+    if (st == RTEN_OK && bias) {
+        if (bias->dtype != RTEN_F32 || bias->ndim != 1) {
+            st = fail(ctx, RTEN_ERR_CAST_FAILED, "bias must be a float vector");
+        } else {
+            st = sc.in(bias, &biasv);
+            if (st == RTEN_OK) st = sc.contiguous(&biasv, &biasc);
+            if (st == RTEN_OK && biasc.shape[0] != b_cols) st = fail(ctx, RTEN_ERR_INVALID_VALUE, "WrongBiasSize");
+            A.epi.bias = (const float*)biasc.data;
+            A.epi.bias_kind = 1;
+        }
+    }
+    A.epi.act = activation;
+    A.residual = residual;
     if (st == RTEN_OK) st = matmul_core(sc, A, out);
     return sc.finish(st);
 }
@@ -1553,7 +1577,6 @@ rten_status rten_b200_dynamic_quantize_linear(rten_ctx* ctx, const rten_tensor* 
     RTB_TRY(check_ctx(ctx));
     if (!x || !y || !scale || !zero_point) return fail(ctx, RTEN_ERR_MISSING_INPUTS, "missing inputs");
     if (x->dtype != RTEN_F32) return fail(ctx, RTEN_ERR_UNSUPPORTED_TYPE, "unsupported type");
-    if (nccl_comm) return fail(ctx, RTEN_ERR_NCCL, "cross-rank min/max exchange is not built into this library build");
     OpScope sc(ctx);
     rten_tensor xv, xc, yv, sv, zv;
     rten_status st = sc.in(x, &xv);
@@ -1582,6 +1605,8 @@ rten_status rten_b200_dynamic_quantize_linear(rten_ctx* ctx, const rten_tensor* 
             int* mm = nullptr;
             st = temp_alloc(ctx, 8, (void**)&mm);
             if (st == RTEN_OK) st = launch_minmax(ctx, (const float*)xc.data, n, mm);
+            // batch-sharded run: the range is the range of the whole (unsharded) tensor
+            if (st == RTEN_OK && nccl_comm) st = comm_allreduce_minmax(ctx, reinterpret_cast<rten_comm*>(nccl_comm), mm);
             if (st == RTEN_OK)
                 st = launch_dql_quantize(ctx, (const float*)xc.data, (uint8_t*)yv.data, n, mm, (float*)sv.data, (uint8_t*)zv.data);
         }

@@ -126,6 +126,9 @@ inline int64_t span_elems(const rten_tensor* t) {
 
 inline void count_launch(rten_ctx* ctx, int n = 1) { ctx->launches += (uint64_t)n; }
 
+// cross-rank min / max of the DynamicQuantizeLinear range (comm.cu)
+rten_status comm_allreduce_minmax(rten_ctx* ctx, struct ::rten_comm* comm, int* mm);
+
 // Deferred tensor-core launches (graph capture batches them into sequence kernels, umma_gemm.cu) must be issued
 // before anything else is enqueued on the context stream: every other launch site asks for the stream through this.
 rten_status seq_flush(rten_ctx* ctx);

@@ -155,10 +155,12 @@ class ResNet50Runner:
 # ResNet-50 int8 (BASELINE configs[3]): the graph `tools/ort-quantize.py dynamic --quantize-conv` produces, after
 # RTen's fusions (src/optimize/fusions.rs:966-1058): every Conv becomes
 #     DynamicQuantizeLinear(x) -> Mul(x_scale, w_scale) -> ConvIntegerToFloat(x_q, w_q, x_zp, -, scale) -> Add(bias)
-# followed by the original Add(identity) / Relu; the classifier becomes DynamicQuantizeLinear -> MatMulIntegerToFloat ->
-# Add(bias).  Weights: symmetric int8, 7-bit range (`reduce_range=True`), one scale per tensor for convolutions
-# (ConvIntegerToFloat takes a scalar scale, src/ops/conv.rs:571-577) and per output column for the MatMul
-# (`per_channel=True`); their zero points are 0, so the optional w_zero_point input is omitted.
+# followed by the original Add(identity) / Relu; the classifier stays an f32 Gemm (the tool quantises MatMul / Conv only,
+# SURVEY.md 8d C4).  Weights: symmetric int8, 7-bit range (`reduce_range=True`), one scale per tensor
+# (ConvIntegerToFloat takes a scalar scale, src/ops/conv.rs:571-577); the weight zero point is a per-output-channel
+# vector of zeros.  `w_zero_points=True` passes that vector like the exported graph does (the kernel then also runs
+# the window-sum term, multiplied by zero); the default drops the all-zero constant input, which a graph optimiser
+# may do without changing a bit of the result.
 # ---------------------------------------------------------------------------------------------
 
 
@@ -175,8 +177,7 @@ class QConvSpec:
 class ResNet50Int8Spec:
     stem: QConvSpec
     blocks: List[Bottleneck]  # of QConvSpec
-    fc_wq: np.ndarray      # int8 [2048, 1000] (K x N)
-    fc_w_scale: np.ndarray  # f32 [1000]
+    fc_w: np.ndarray  # f32 [1000, 2048] (Gemm transB = 1)
     fc_b: np.ndarray
 
 
@@ -194,47 +195,47 @@ def quantize_resnet50(spec: ResNet50Spec) -> ResNet50Int8Spec:
         return QConvSpec(q, np.asarray(s, np.float32).reshape(()), c.b, c.stride, c.pad)
 
     blocks = [Bottleneck(qc(b.c1), qc(b.c2), qc(b.c3), qc(b.down) if b.down is not None else None) for b in spec.blocks]
-    wq, ws = _quantize_sym(np.ascontiguousarray(spec.fc_w.T), axis=0)
-    return ResNet50Int8Spec(qc(spec.stem), blocks, wq, ws.reshape(-1).astype(np.float32), spec.fc_b)
+    return ResNet50Int8Spec(qc(spec.stem), blocks, spec.fc_w, spec.fc_b)
 
 
 class ResNet50Int8Runner:
     """configs[3] on one GPU.  `fuse=True` folds Add(bias) / Add(identity) / Relu into the integer convolution's
     epilogue (same f32 roundings, rten_b200_conv_integer_ex); `fuse=False` issues them as separate operators."""
 
-    def __init__(self, ctx: O.Context, spec: ResNet50Int8Spec, fuse: bool = True):
-        self.ctx, self.spec, self.fuse = ctx, spec, fuse
+    def __init__(self, ctx: O.Context, spec: ResNet50Int8Spec, fuse: bool = True, comm: Optional[O.Comm] = None,
+                 w_zero_points: bool = False):
+        """`comm`: this rank holds a shard of the batch; quantisation ranges are all-reduced."""
+        self.ctx, self.spec, self.fuse, self.comm, self.w_zero_points = ctx, spec, fuse, comm, w_zero_points
         self._convs = {}
 
         def prep(c: QConvSpec):
             op = O.ConvIntegerToFloat(1, (1, 1), (c.pad, c.pad, c.pad, c.pad), (c.stride, c.stride))
             w = ctx.to_device(c.wq)
             self._convs[id(c)] = (op, w, ctx.to_device(c.b), op.prepack(ctx, 1, w), ctx.to_device(c.w_scale),
-                                  ctx.to_device(c.b.reshape(1, -1, 1, 1)))
+                                  ctx.to_device(c.b.reshape(1, -1, 1, 1)),
+                                  ctx.to_device(np.zeros(c.wq.shape[0], np.int8)) if w_zero_points else None)
 
         prep(spec.stem)
         for b in spec.blocks:
             for c in (b.c1, b.c2, b.c3, b.down):
                 if c is not None:
                     prep(c)
-        self.fc_w = ctx.to_device(spec.fc_wq)
-        self.fc_pk = O.MatMulInteger().prepack(ctx, 1, self.fc_w)
-        self.fc_scale, self.fc_b = ctx.to_device(spec.fc_w_scale), ctx.to_device(spec.fc_b)
+        self.fc_w, self.fc_b = ctx.to_device(spec.fc_w), ctx.to_device(spec.fc_b)
         self.maxpool = O.MaxPool((3, 3), (1, 1, 1, 1), (2, 2))
         self.gap = O.GlobalAveragePool()
         self.dql, self.mul, self.add, self.relu = O.DynamicQuantizeLinear(), O.Mul(), O.Add(), O.Relu()
-        self.fc = O.MatMulIntegerToFloat()
+        self.fc = O.Gemm(1.0, 1.0, False, True)
 
     def _conv(self, c: QConvSpec, x, relu: bool, residual=None):
-        op, w, b, pk, ws, b4 = self._convs[id(c)]
+        op, w, b, pk, ws, b4, wz = self._convs[id(c)]
         ctx = self.ctx
-        xq, xs, xz = self.dql.run(ctx, x)
+        xq, xs, xz = self.dql.run(ctx, x, self.comm)
         scale = self.mul.run(ctx, xs, ws)
         if self.fuse:
             op.activation = O.ACT_RELU if relu else O.ACT_NONE
-            return op.run(ctx, xq, w, xz, None, scale, packed_w=pk, bias=b, residual=residual)
+            return op.run(ctx, xq, w, xz, wz, scale, packed_w=pk, bias=b, residual=residual)
         op.activation = O.ACT_NONE
-        y = op.run(ctx, xq, w, xz, None, scale, packed_w=pk)
+        y = op.run(ctx, xq, w, xz, wz, scale, packed_w=pk)
         y = self.add.run(ctx, y, b4)
         if residual is not None:
             y = self.add.run(ctx, y, residual)
@@ -242,7 +243,9 @@ class ResNet50Int8Runner:
             y = self.relu.run(ctx, y, in_place=True)
         return y
 
-    def run(self, x: O.DeviceTensor) -> O.DeviceTensor:
+    def run(self, x: O.DeviceTensor, return_features: bool = False):
+        """-> logits [B,1000]; with `return_features` also the pooled [B,2048] features, the last tensor produced by
+        exact arithmetic only (the f32 classifier runs on the TF32 tensor-core path)."""
         s, ctx = self.spec, self.ctx
         y = self._conv(s.stem, x, True)
         y = self.maxpool.run(ctx, y)
@@ -253,10 +256,8 @@ class ResNet50Int8Runner:
             y = self._conv(b.c3, t, True, residual=ident)
         p = self.gap.run(ctx, y)
         p = p.reshape(p.shape[0], p.shape[1])
-        pq, ps, pz = self.dql.run(ctx, p)
-        scale = self.mul.run(ctx, ps, self.fc_scale)
-        y = self.fc.run(ctx, pq, self.fc_w, pz, None, scale, packed_b=self.fc_pk)
-        return self.add.run(ctx, y, self.fc_b)
+        logits = self.fc.run(ctx, p, self.fc_w, self.fc_b)
+        return (logits, p) if return_features else logits
 
 
 # ---------------------------------------------------------------------------------------------
@@ -390,3 +391,152 @@ class BertRunner:
             y = self._linear(h, d["w2"], d["b2"], residual=x)
             x = self.ln.run(ctx, y, d["ln2_g"], d["ln2_b"])
         return x.reshape(B, S, H)
+
+
+# ---------------------------------------------------------------------------------------------
+# GPT-2 small, dynamically quantised (BASELINE configs[4]): the autoregressive KV-cache path of
+# rten-generate (rten-generate/src/generator.rs:283-316,465-480: `past_key_values.N.{key,value}` inputs,
+# `present.N.*` outputs).  Every linear layer is DynamicQuantizeLinear -> MatMulIntegerToFloat (a_zp scalar, per-column
+# scale, `tools/ort-quantize.py:147`) -> Add(bias); attention products stay f32 MatMuls; Gelu is the tanh form.
+# ---------------------------------------------------------------------------------------------
+
+
+@dataclass
+class QLinear:
+    wq: np.ndarray      # int8 [K, N]
+    w_scale: np.ndarray  # f32 [N]
+    b: Optional[np.ndarray]
+
+
+@dataclass
+class GPT2Layer:
+    ln1_g: np.ndarray
+    ln1_b: np.ndarray
+    attn: QLinear   # 768 -> 2304
+    proj: QLinear   # 768 -> 768
+    ln2_g: np.ndarray
+    ln2_b: np.ndarray
+    fc: QLinear     # 768 -> 3072
+    fc2: QLinear    # 3072 -> 768
+
+
+@dataclass
+class GPT2Int8Spec:
+    hidden: int
+    heads: int
+    wte: np.ndarray
+    wpe: np.ndarray
+    lnf_g: np.ndarray
+    lnf_b: np.ndarray
+    lm_head: QLinear
+    layers: List[GPT2Layer] = field(default_factory=list)
+    eps: float = 1e-5
+
+
+def make_gpt2_int8(uniform: Callable, layers: int = 12, hidden: int = 768, heads: int = 12, vocab: int = 50257,
+                   max_pos: int = 1024) -> GPT2Int8Spec:
+    def qlin(i, o, bias=True):
+        w = (uniform((i, o)) / np.float32(math.sqrt(i))).astype(np.float32)
+        q, sc = _quantize_sym(w, axis=0)
+        return QLinear(q, sc.reshape(-1).astype(np.float32), (uniform((o,)) * np.float32(0.1)).astype(np.float32) if bias else None)
+
+    def ln():
+        return (np.float32(1.0) + np.float32(0.1) * uniform((hidden,))).astype(np.float32), (np.float32(0.1) * uniform((hidden,))).astype(np.float32)
+
+    spec = GPT2Int8Spec(hidden, heads, (uniform((vocab, hidden)) * np.float32(0.5)).astype(np.float32),
+                        (uniform((max_pos, hidden)) * np.float32(0.5)).astype(np.float32), *ln(), qlin(hidden, vocab, bias=False))
+    for _ in range(layers):
+        g1, b1 = ln()
+        attn, proj = qlin(hidden, 3 * hidden), qlin(hidden, hidden)
+        g2, b2 = ln()
+        spec.layers.append(GPT2Layer(g1, b1, attn, proj, g2, b2, qlin(hidden, 4 * hidden), qlin(4 * hidden, hidden)))
+    return spec
+
+
+class GPT2Int8Runner:
+    """Prefill + decode with a device-resident KV cache.  Keys are cached as [B,heads,max_seq,d] (K-major for Q.K^T as
+    it is), values TRANSPOSED as [B,heads,d,max_seq] so that probs.V also finds its reduction dimension contiguous:
+    neither product re-packs the cache, however long it grows."""
+
+    def __init__(self, ctx: O.Context, spec: GPT2Int8Spec, batch: int, max_seq: int, fuse: bool = True):
+        self.ctx, self.spec, self.B, self.max_seq, self.fuse = ctx, spec, batch, max_seq, fuse
+        dev = ctx.to_device
+        self.wte, self.wpe = dev(spec.wte), dev(spec.wpe)
+        self.lnf = (dev(spec.lnf_g), dev(spec.lnf_b))
+        mm = O.MatMulInteger()
+
+        def prep(l: QLinear):
+            w = dev(l.wq)
+            return (w, mm.prepack(ctx, 1, w), dev(l.w_scale), dev(l.b) if l.b is not None else None)
+
+        self.lm_head = prep(spec.lm_head)
+        self.layers = []
+        nh, dh = spec.heads, spec.hidden // spec.heads
+        for L in spec.layers:
+            self.layers.append(dict(ln1=(dev(L.ln1_g), dev(L.ln1_b)), ln2=(dev(L.ln2_g), dev(L.ln2_b)), attn=prep(L.attn),
+                                    proj=prep(L.proj), fc=prep(L.fc), fc2=prep(L.fc2),
+                                    k=dev(np.zeros((batch, nh, max_seq, dh), np.float32)),
+                                    vt=dev(np.zeros((batch, nh, dh, max_seq), np.float32))))
+        self.past = 0
+        self.gather, self.add, self.mul, self.dql = O.GatherRows(), O.Add(), O.Mul(), O.DynamicQuantizeLinear()
+        self.ln = O.LayerNormalization(-1, spec.eps)
+        self.addsoftmax, self.gelu = O.AddSoftmax(), O.Gelu(approximate=True)
+
+    def reset(self):
+        self.past = 0
+
+    def _linear(self, x, lin, act=O.ACT_NONE, residual=None):
+        w, pk, ws, b = lin
+        ctx = self.ctx
+        xq, xs, xz = self.dql.run(ctx, x)
+        scale = self.mul.run(ctx, xs, ws)
+        if self.fuse:
+            return O.MatMulIntegerToFloat(act).run(ctx, xq, w, xz, None, scale, packed_b=pk, bias=b, residual=residual)
+        y = O.MatMulIntegerToFloat().run(ctx, xq, w, xz, None, scale, packed_b=pk)
+        if b is not None:
+            y = self.add.run(ctx, y, b)
+        if residual is not None:
+            y = self.add.run(ctx, y, residual)
+        if act == O.ACT_GELU_TANH:
+            y = self.gelu.run(ctx, y, in_place=True)
+        return y
+
+    def forward(self, input_ids: np.ndarray) -> O.DeviceTensor:
+        """input_ids: host int32 [B,T] -- the T tokens that follow the `self.past` cached positions (prefill: the whole
+        prompt; decode: T = 1).  Returns the logits of the LAST position, [B, vocab]."""
+        ctx, s = self.ctx, self.spec
+        B, T = input_ids.shape
+        assert B == self.B and self.past + T <= self.max_seq
+        P, Ltot = self.past, self.past + T
+        H, nh = s.hidden, s.heads
+        dh = H // nh
+        ids = ctx.to_device(np.ascontiguousarray(input_ids, np.int32))
+        x = self.gather.run(ctx, self.wte, ids)                                   # [B,T,H]
+        x = self.add.run(ctx, x, self.wpe.view((T, H), (H, 1), P * H))
+        x = x.reshape(B * T, H)
+        # causal mask for the new rows: position P+i attends to 0..P+i
+        mask = np.where(np.arange(Ltot)[None, :] <= (P + np.arange(T))[:, None], 0.0, -np.inf).astype(np.float32)
+        mask = ctx.to_device(mask.reshape(1, 1, T, Ltot))
+        scale = 1.0 / math.sqrt(dh)
+        M = self.max_seq
+        for d in self.layers:
+            h = self.ln.run(ctx, x, *d["ln1"])
+            qkv = self._linear(h, d["attn"])                                      # [B*T, 3H]
+            part = lambda i: qkv.view((B, nh, T, dh), (T * 3 * H, dh, 3 * H, 1), i * H)   # [B,T,3,nh,dh] memory
+            q = part(0)
+            d["k"].view((B, nh, T, dh), (nh * M * dh, M * dh, dh, 1), P * dh).assign(part(1))
+            d["vt"].view((B, nh, T, dh), (nh * dh * M, dh * M, 1, M), P).assign(part(2))
+            kt = d["k"].view((B, nh, dh, Ltot), (nh * M * dh, M * dh, 1, dh))    # K^T over the cached positions
+            scores = O.FusedMatMul(scale).run(ctx, q, kt)                          # [B,nh,T,Ltot]
+            probs = self.addsoftmax.run(ctx, scores, mask, in_place=True)
+            v = d["vt"].view((B, nh, Ltot, dh), (nh * dh * M, dh * M, 1, M))      # V as [.., L, d] with L contiguous
+            att = ctx.empty((B * T, H))
+            O.MatMul().run(ctx, probs, v, out=att.view((B, nh, T, dh), (T * H, dh, H, 1)))
+            x = self._linear(att, d["proj"], residual=x)
+            h = self.ln.run(ctx, x, *d["ln2"])
+            f = self._linear(h, d["fc"], act=O.ACT_GELU_TANH)
+            x = self._linear(f, d["fc2"], residual=x)
+        last = x.view((B, H), (T * H, 1), (T - 1) * H)
+        last = self.ln.run(ctx, last, *self.lnf)
+        self.past = Ltot
+        return self._linear(last, self.lm_head)

@@ -195,6 +195,12 @@ class DeviceTensor:
         dst = self.desc()
         self.ctx.check(self.ctx.lib.rten_b200_copy(self.ctx.handle, C.byref(src), C.byref(dst)))
 
+    def assign(self, src: "DeviceTensor"):
+        """Strided device-to-device copy of `src` (same shape) into this view (e.g. appending to a KV cache)."""
+        assert tuple(src.shape) == tuple(self.shape) and src.dtype == self.dtype
+        a, b = src.desc(), self.desc()
+        self.ctx.check(self.ctx.lib.rten_b200_copy(self.ctx.handle, C.byref(a), C.byref(b)))
+
     def numpy(self) -> np.ndarray:
         out = np.empty(self.shape, self.dtype)
         dst = _desc(out.ctypes.data, out.dtype, out.shape, _contig(out.shape), RTEN_DEVICE_HOST)
@@ -345,13 +351,20 @@ class MatMulInteger(MatMul):
 class MatMulIntegerToFloat(MatMul):
     """src/ops/matmul.rs:776-811 (inputs: a, b, a_zero_point, b_zero_point, scale)"""
 
-    def run(self, ctx, a, b, a_zero_point, b_zero_point, scale, packed_b: Optional[Packed] = None, out=None):
+    def __init__(self, activation: int = ACT_NONE):
+        self.activation = activation
+
+    def run(self, ctx, a, b, a_zero_point, b_zero_point, scale, packed_b: Optional[Packed] = None, out=None, bias=None,
+            residual=None):
+        """`bias` / `residual` / `self.activation`: the Add / Add / Gelu nodes that follow the operator in a quantised
+        transformer, folded into the epilogue with the same f32 roundings (rten_b200_matmul_integer_ex)."""
         if scale is None:
             raise OpError(4, "missing inputs")
         A = _Args(ctx)
         o = A.out(out)
-        ctx.check(ctx.lib.rten_b200_matmul_integer(ctx.handle, A.t(a), A.t(b), _ph(packed_b), A.t(a_zero_point),
-                                                   A.t(b_zero_point), A.t(scale), C.byref(o)))
+        ctx.check(ctx.lib.rten_b200_matmul_integer_ex(ctx.handle, A.t(a), A.t(b), _ph(packed_b), A.t(a_zero_point),
+                                                      A.t(b_zero_point), A.t(scale), A.t(bias), A.t(residual),
+                                                      self.activation, C.byref(o)))
         return A.wrap(o, out)
 
 
@@ -514,11 +527,38 @@ class Relu(_Unary):
 class DynamicQuantizeLinear:
     """src/ops/quantize.rs:436-468 -> (y u8, y_scale f32 scalar, y_zero_point u8 scalar)"""
 
-    def run(self, ctx, x):
+    def run(self, ctx, x, comm: Optional["Comm"] = None):
+        """`comm`: batch-sharded run -- the quantisation range is all-reduced over the ranks (min, max) first."""
         A = _Args(ctx)
         y, s, z = A.out(), A.out(), A.out()
-        ctx.check(ctx.lib.rten_b200_dynamic_quantize_linear(ctx.handle, A.t(x), C.byref(y), C.byref(s), C.byref(z), None))
+        ctx.check(ctx.lib.rten_b200_dynamic_quantize_linear(ctx.handle, A.t(x), C.byref(y), C.byref(s), C.byref(z),
+                                                            comm.handle if comm is not None else None))
         return A.wrap(y, None), A.wrap(s, None), A.wrap(z, None)
+
+
+class Comm:
+    """Cross-rank communicator of a batch-sharded run (rten_b200_comm_*; NCCL resolved at run time)."""
+
+    def __init__(self, ctx: Context, unique_id: bytes, rank: int, world: int):
+        assert len(unique_id) == 128
+        self.ctx, self.rank, self.world = ctx, rank, world
+        h = C.c_void_p()
+        buf = C.create_string_buffer(unique_id, 128)
+        ctx.check(ctx.lib.rten_b200_comm_create(ctx.handle, buf, rank, world, C.byref(h)))
+        self.handle = h
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        st = _lib.load().rten_b200_comm_unique_id(buf)
+        if st != 0:
+            raise OpError(st, "libnccl.so.2 could not be loaded")
+        return buf.raw
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.ctx.lib.rten_b200_comm_destroy(self.handle)
+            self.handle = None
 
 
 class Add:

@@ -21,14 +21,16 @@ def resnet50_oracle(oracle, spec, x):
     return oracle.gemm_op(p.reshape(p.shape[0], p.shape[1]), spec.fc_w, spec.fc_b, 1.0, 1.0, False, True)
 
 
-def resnet50_int8_oracle(oracle, qspec, x):
-    """configs[3] (rten_b200/graphs.py ResNet50Int8Runner) with the reference's operators, unfused, NCHW."""
+def resnet50_int8_oracle(oracle, qspec, x, w_zero_points=True):
+    """configs[3] (rten_b200/graphs.py ResNet50Int8Runner) with the reference's operators, unfused, NCHW.
+    -> (logits, pooled features)."""
     f32 = np.float32
 
     def conv(c, t, relu, residual=None):
         tq, ts, tz = oracle.dynamic_quantize_linear(t)
         scale = f32(ts) * f32(c.w_scale)
-        y = oracle.conv_integer_to_float(tq, c.wq, tz, None, scale, padding=[c.pad] * 4, groups=1,
+        wz = np.zeros(c.wq.shape[0], np.int8) if w_zero_points else None
+        y = oracle.conv_integer_to_float(tq, c.wq, tz, wz, scale, padding=[c.pad] * 4, groups=1,
                                          strides=(c.stride, c.stride), dilations=(1, 1))
         y = oracle.add(y, c.b.reshape(1, -1, 1, 1))
         if residual is not None:
@@ -44,9 +46,7 @@ def resnet50_int8_oracle(oracle, qspec, x):
         y = conv(b.c3, t, True, residual=ident)
     p = oracle.global_average_pool(y)
     p = p.reshape(p.shape[0], p.shape[1])
-    pq, ps, pz = oracle.dynamic_quantize_linear(p)
-    scale = (f32(ps) * qspec.fc_w_scale).astype(f32)
-    return oracle.add(oracle.matmul_integer_to_float(pq, qspec.fc_wq, pz, None, scale), qspec.fc_b)
+    return oracle.gemm_op(p, qspec.fc_w, qspec.fc_b, 1.0, 1.0, False, True), p
 
 
 def bert_oracle(oracle, spec, input_ids, token_type_ids, add_mask):
@@ -66,3 +66,45 @@ def bert_oracle(oracle, spec, input_ids, token_type_ids, add_mask):
         h = oracle.gelu(oracle.matmul(x, L.w1, L.b1))
         x = oracle.layer_norm(oracle.add(oracle.matmul(h, L.w2, L.b2), x), L.ln2_g, L.ln2_b, -1, spec.eps)
     return x.reshape(B, S, H)
+
+
+def gpt2_int8_oracle(oracle, spec, steps):
+    """configs[4] with the reference's operators: `steps` = list of int32 [B,T] token blocks (prefill, then decode
+    steps); K/V of earlier blocks are kept as `past_key_values`.  -> list of last-position logits [B,vocab]."""
+    f32 = np.float32
+    H, nh = spec.hidden, spec.heads
+    dh = H // nh
+
+    def linear(x, l, gelu=False, residual=None):
+        xq, xs, xz = oracle.dynamic_quantize_linear(x)
+        y = oracle.matmul_integer_to_float(xq, l.wq, xz, None, (f32(xs) * l.w_scale).astype(f32))
+        if l.b is not None:
+            y = oracle.add(y, l.b)
+        if residual is not None:
+            y = oracle.add(y, residual)
+        return oracle.gelu(y, True) if gelu else y
+
+    past = [None] * len(spec.layers)
+    P, outs = 0, []
+    for ids in steps:
+        B, T = ids.shape
+        L = P + T
+        x = oracle.add(spec.wte[ids], spec.wpe[P:L]).reshape(B * T, H)
+        mask = np.where(np.arange(L)[None, :] <= (P + np.arange(T))[:, None], 0.0, -np.inf).astype(f32).reshape(1, 1, T, L)
+        for li, ly in enumerate(spec.layers):
+            h = oracle.layer_norm(x, ly.ln1_g, ly.ln1_b, -1, spec.eps)
+            qkv = linear(h, ly.attn).reshape(B, T, 3, nh, dh)
+            q, k, v = (qkv[:, :, i].transpose(0, 2, 1, 3) for i in range(3))
+            if past[li] is not None:
+                k = np.concatenate([past[li][0], k], 2)
+                v = np.concatenate([past[li][1], v], 2)
+            past[li] = (k, v)
+            probs = oracle.add_softmax(oracle.matmul(q, k.transpose(0, 1, 3, 2), None, 1.0 / math.sqrt(dh)), mask)
+            att = oracle.matmul(probs, v).transpose(0, 2, 1, 3).reshape(B * T, H)
+            x = linear(att, ly.proj, residual=x)
+            h = oracle.layer_norm(x, ly.ln2_g, ly.ln2_b, -1, spec.eps)
+            x = linear(linear(h, ly.fc, gelu=True), ly.fc2, residual=x)
+        last = oracle.layer_norm(x.reshape(B, T, H)[:, -1], spec.lnf_g, spec.lnf_b, -1, spec.eps)
+        outs.append(linear(last, spec.lm_head))
+        P = L
+    return outs
