@@ -116,7 +116,8 @@ def run_reference_arm(args, model, batch):
     # images are the outer parallel level: a many-core host needs the whole batch in flight to be busy
     sample = (batch if ncores >= 32 else 8) if model == "resnet50" else (batch if ncores >= 32 else 4)
     inp = make_inputs(oracle, model, sample)
-    run = (lambda: model_ref.resnet50_oracle(oracle, spec, inp["x"])) if model == "resnet50" else \
+    arena = oracle.Arena()  # = the reference's BufferPool: operator outputs are recycled from pass to pass
+    run = (lambda: model_ref.resnet50_oracle(oracle, spec, inp["x"], arena)) if model == "resnet50" else \
         (lambda: model_ref.bert_oracle(oracle, spec, inp["ids"], inp["tt"], inp["mask"]))
     for _ in range(max(1, min(args.warmup, 1))):
         run()
@@ -161,6 +162,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="issue ops one by one instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-autotune", action="store_true", help="use the cost model's launch plans instead of timing candidates during warm-up")
+    ap.add_argument("--plans", default=None, help="file of measured launch plans: loaded if it exists, (re)written after the warm-up pass")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary numbers (BERT-base pass, 8192^3 GEMM TFLOP/s)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -190,6 +192,8 @@ def main():
     torch.cuda.set_stream(stream)
     ctx = rt.Context(local_rank, stream=stream.cuda_stream)
     ctx.set_autotune(not args.no_autotune)  # plans are measured during the first (untimed, eager) pass
+    if args.plans and os.path.exists(args.plans):
+        ctx.load_plans(args.plans)
 
     spec = make_spec(oracle, model)
     inp = make_inputs(oracle, model, batch)
@@ -211,6 +215,8 @@ def main():
     # ---- eager run (also warms the buffer pool so that graph capture never allocates)
     out = step_fn()
     ctx.sync()
+    if args.plans and rank == 0:
+        ctx.save_plans(args.plans)
     out_shape = out.shape
     del out
     gather_buf = torch.empty(shard.gather_layout(world, tuple(out_shape)), dtype=torch.float32, device="cuda") if world > 1 else None
@@ -415,6 +421,29 @@ def secondary_numbers(ctx, rt, graphs, oracle, model, stream, torch, flush):
     x64 = ctx.to_device(make_inputs(oracle, "resnet50", 64)["x"], channels_last=True)
     ms = timed(lambda: qrunner.run(x64))
     out["resnet50_int8_b64_img_per_sec"] = 64 / (ms / 1e3)
+    del qrunner, x64
+    # configs[4]: GPT-2 small int8, batch 8: prefill of 512 tokens, then decode steps against the KV cache (eager
+    # launches: the cache length changes every step)
+    grng = oracle.XorShiftRng(5678)
+    gspec = graphs.make_gpt2_int8(lambda s: grng.uniform(s))
+    grun = graphs.GPT2Int8Runner(ctx, gspec, 8, 576)
+    gids = (oracle.XorShiftRng(1).u64(8 * 576) % 50257).astype(np.int32).reshape(8, 576)
+    grun.forward(gids[:, :512])  # warm-up (autotune, pool)
+    grun.forward(gids[:, 512:513])
+    grun.reset()
+    ctx.set_autotune(False)  # keep the measured plans, stop measuring: the attention shapes change every decode step
+    torch.cuda.synchronize()
+    s0, e0, e1 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    s0.record(stream)
+    grun.forward(gids[:, :512])
+    e0.record(stream)
+    ndec = 32
+    for i in range(ndec):
+        grun.forward(gids[:, 512 + i:513 + i])
+    e1.record(stream)
+    torch.cuda.synchronize()
+    out["gpt2_int8_b8_prefill512_tokens_per_sec"] = 8 * 512 / (s0.elapsed_time(e0) / 1e3)
+    out["gpt2_int8_b8_decode_tokens_per_sec"] = 8 * ndec / (e0.elapsed_time(e1) / 1e3)
     return out
 
 

@@ -87,8 +87,12 @@ rten_status rten_b200_set_f32_mode(rten_ctx* ctx, int mode /* rten_f32_mode */);
  * model's best launch plans on the device and caches the winner in the context -- the role rten-gemm's per-arch
  * kernel selection and blocking heuristics play (rten-gemm/src/lib.rs:199-391), decided by measurement.  Integer
  * results do not depend on the plan; f32 results stay within the TF32 tolerance but may differ in the last bits
- * between plans (split-K changes the summation order). */
+ * between plans (split-K changes the summation order).  Measured plans are used for the rest of the context's life
+ * even after autotuning is switched off again, and env RTEN_B200_TUNE_FILE=<path> keeps them across processes
+ * (read at context creation, rewritten at destruction when new problems were measured). */
 rten_status rten_b200_set_autotune(rten_ctx* ctx, int enable);
+rten_status rten_b200_save_plans(rten_ctx* ctx, const char* path);
+rten_status rten_b200_load_plans(rten_ctx* ctx, const char* path);
 /* Caching, stream-ordered device allocator = `BufferPool` (src/buffer_pool.rs:1-140). */
 rten_status rten_b200_alloc(rten_ctx* ctx, size_t bytes, void** dev_ptr);
 rten_status rten_b200_free(rten_ctx* ctx, void* dev_ptr);

@@ -150,9 +150,11 @@ def expect_equal(a, b, atol=1e-8, rtol=1e-5) -> bool:
 # --------------------------------------------------------------------------------------
 # Elementwise
 # --------------------------------------------------------------------------------------
-def _unary(fn, x):
+def _unary(fn, x, out=None):
+    """`out` (may be `x` itself): run into an existing buffer, as the reference's in-place operators do."""
     x = np.ascontiguousarray(x, dtype=np.float32)
-    y = np.empty_like(x)
+    y = out if out is not None else np.empty_like(x)
+    assert y.shape == x.shape and y.dtype == np.float32 and y.flags.c_contiguous
     fn(_p(x, C.c_float), _p(y, C.c_float), x.size)
     return y
 
@@ -177,19 +179,36 @@ def tanh(x):
     return _unary(lib().rto_tanh, x)
 
 
-def relu(x):
-    return _unary(lib().rto_relu, x)
+def relu(x, out=None):
+    return _unary(lib().rto_relu, x, out)
 
 
-def add(a, b):
+def add(a, b, out=None):
     a = np.asarray(a, dtype=np.float32)
     b = np.asarray(b, dtype=np.float32)
     shape = np.broadcast_shapes(a.shape, b.shape)
     a = np.ascontiguousarray(np.broadcast_to(a, shape))
     b = np.ascontiguousarray(np.broadcast_to(b, shape))
-    y = np.empty(shape, dtype=np.float32)
+    y = out if out is not None else np.empty(shape, dtype=np.float32)
+    assert y.shape == tuple(shape) and y.dtype == np.float32 and y.flags.c_contiguous
     lib().rto_add(_p(a, C.c_float), _p(b, C.c_float), _p(y, C.c_float), y.size)
     return y
+
+
+class Arena:
+    """Output buffers recycled from one model pass to the next, the role `BufferPool` (src/buffer_pool.rs) plays in
+    the reference: without it every operator output is a fresh multi-megabyte allocation whose first-touch page
+    faults dominate a many-core CPU run."""
+
+    def __init__(self):
+        self.bufs = {}
+
+    def get(self, key, shape, dtype=np.float32):
+        a = self.bufs.get(key)
+        if a is None or a.shape != tuple(shape) or a.dtype != dtype:
+            a = np.empty(shape, dtype)
+            self.bufs[key] = a
+        return a
 
 
 # --------------------------------------------------------------------------------------
@@ -554,7 +573,7 @@ def _conv_checks(x, w, groups, strides, dilations):
         raise OpError("InvalidValue", "Output channel count not divisible by groups")
 
 
-def conv(x, w, bias=None, padding=(0, 0, 0, 0), groups=1, strides=(1, 1), dilations=(1, 1)):
+def conv(x, w, bias=None, padding=(0, 0, 0, 0), groups=1, strides=(1, 1), dilations=(1, 1), out=None):
     """src/ops/conv.rs:124-365 (f32, NCHW x OIHW -> NCHW, column bias over out channels)."""
     x = np.ascontiguousarray(x, np.float32)
     w = np.ascontiguousarray(w, np.float32)
@@ -576,7 +595,8 @@ def conv(x, w, bias=None, padding=(0, 0, 0, 0), groups=1, strides=(1, 1), dilati
         if bias.shape != (O,):
             raise OpError("IncompatibleInputShapes", "bias.size(0) != out_channels")
     oh, ow, pads = conv_output_size((H, W), (kh, kw), strides, padding, dilations)
-    y = np.empty((B, O, oh, ow), np.float32)
+    y = out if out is not None else np.empty((B, O, oh, ow), np.float32)
+    assert y.shape == (B, O, oh, ow) and y.dtype == np.float32 and y.flags.c_contiguous
     if y.size:
         lib().rto_conv_f32(_p(x, C.c_float), _p(w, C.c_float), _p(bias, C.c_float), _p(y, C.c_float),
                            B, Cin, H, W, O, kh, kw, oh, ow, _ints(pads), _ints(strides), _ints(dilations), groups)

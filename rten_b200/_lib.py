@@ -55,6 +55,8 @@ _SIGNATURES = {
     "rten_b200_sync": (C.c_int, [_vp]),
     "rten_b200_set_f32_mode": (C.c_int, [_vp, C.c_int]),
     "rten_b200_set_autotune": (C.c_int, [_vp, C.c_int]),
+    "rten_b200_save_plans": (C.c_int, [_vp, C.c_char_p]),
+    "rten_b200_load_plans": (C.c_int, [_vp, C.c_char_p]),
     "rten_b200_alloc": (C.c_int, [_vp, C.c_size_t, C.POINTER(_vp)]),
     "rten_b200_free": (C.c_int, [_vp, _vp]),
     "rten_b200_host_alloc": (C.c_int, [_vp, C.c_size_t, C.POINTER(_vp)]),

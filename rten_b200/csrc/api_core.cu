@@ -166,6 +166,54 @@ extern "C" {
 
 const char* rten_b200_version(void) { return "rten-b200 0.1 (sm_100a)"; }
 
+// Measured launch plans can be kept across processes: RTEN_B200_TUNE_FILE names a text file that is read when a
+// context is created and rewritten when a context that measured new plans is destroyed (one line per problem:
+// key integers, '|', plan integers).
+static void tune_cache_load(rten_ctx* ctx, const char* path) {
+    FILE* f = fopen(path, "r");
+    if (!f) return;
+    char line[2048];
+    while (fgets(line, sizeof(line), f)) {
+        std::vector<long long> key;
+        std::array<int, 8> plan{};
+        char* p = line;
+        bool in_plan = false;
+        int np = 0;
+        while (*p) {
+            while (*p == ' ') p++;
+            if (*p == '|') {
+                in_plan = true;
+                p++;
+                continue;
+            }
+            if (*p == '\n' || *p == 0) break;
+            char* end = nullptr;
+            const long long v = strtoll(p, &end, 10);
+            if (end == p) break;
+            if (in_plan) {
+                if (np < 8) plan[np++] = (int)v;
+            } else {
+                key.push_back(v);
+            }
+            p = end;
+        }
+        if (np == 8 && !key.empty()) ctx->tune_cache[key] = plan;
+    }
+    fclose(f);
+}
+
+static void tune_cache_save(rten_ctx* ctx, const char* path) {
+    FILE* f = fopen(path, "w");
+    if (!f) return;
+    for (const auto& kv : ctx->tune_cache) {
+        for (long long v : kv.first) fprintf(f, "%lld ", v);
+        fprintf(f, "|");
+        for (int v : kv.second) fprintf(f, " %d", v);
+        fprintf(f, "\n");
+    }
+    fclose(f);
+}
+
 rten_status rten_b200_ctx_create(int device, void* cuda_stream_or_null, size_t workspace_bytes, rten_ctx** out) {
     if (!out) return RTEN_ERR_INVALID_VALUE;
     *out = nullptr;
@@ -189,6 +237,10 @@ rten_status rten_b200_ctx_create(int device, void* cuda_stream_or_null, size_t w
         ctx->own_stream = true;
     }
     if (const char* at = getenv("RTEN_B200_AUTOTUNE")) ctx->autotune = atoi(at) != 0;
+    if (const char* tf = getenv("RTEN_B200_TUNE_FILE")) {
+        tune_cache_load(ctx, tf);
+        ctx->tune_loaded = ctx->tune_cache.size();
+    }
     const char* mode = getenv("RTEN_B200_F32_MODE");
     if (mode && strcmp(mode, "tf32x3") == 0) ctx->f32_mode = RTEN_F32_TF32X3;
     if (workspace_bytes) {  // pre-reserve one pool bucket so the first ops do not pay cudaMalloc
@@ -206,6 +258,8 @@ void rten_b200_ctx_destroy(rten_ctx* ctx) {
     for (auto& kv : ctx->pool.free_buckets)
         for (void* p : kv.second) cudaFree(p);
     for (auto& kv : ctx->pool.live) cudaFree(kv.first);
+    if (const char* tf = getenv("RTEN_B200_TUNE_FILE"))
+        if (ctx->tune_cache.size() > ctx->tune_loaded) tune_cache_save(ctx, tf);
     if (ctx->sk_counters) cudaFree(ctx->sk_counters);
     seq_free(ctx);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -225,6 +279,17 @@ rten_status rten_b200_set_f32_mode(rten_ctx* ctx, int mode) {
     if (mode != RTEN_F32_TF32 && mode != RTEN_F32_TF32X3) return fail(ctx, RTEN_ERR_INVALID_VALUE, "unknown f32 mode");
     if (mode == RTEN_F32_TF32X3) return fail(ctx, RTEN_ERR_UNSUPPORTED_VALUE, "tf32x3 mode is not implemented yet");
     ctx->f32_mode = mode;
+    return RTEN_OK;
+}
+
+rten_status rten_b200_save_plans(rten_ctx* ctx, const char* path) {
+    if (!ctx || !path) return RTEN_ERR_INVALID_VALUE;
+    tune_cache_save(ctx, path);
+    return RTEN_OK;
+}
+rten_status rten_b200_load_plans(rten_ctx* ctx, const char* path) {
+    if (!ctx || !path) return RTEN_ERR_INVALID_VALUE;
+    tune_cache_load(ctx, path);
     return RTEN_OK;
 }
 

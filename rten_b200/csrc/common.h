@@ -61,6 +61,7 @@ struct rten_ctx {
     int seq_class = -1;            // kernel class (data kind, epilogue variant) of the pending launches
     void* seq_gbar = nullptr;      // grid-barrier arrival counter of the sequence kernel
     std::map<std::vector<long long>, std::array<int, 8>> tune_cache;
+    size_t tune_loaded = 0;        // entries read from RTEN_B200_TUNE_FILE (the file is rewritten when more exist at destroy)
 };
 
 namespace rtb {

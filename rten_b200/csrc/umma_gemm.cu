@@ -1586,12 +1586,13 @@ rten_status launch_umma_gemm(rten_ctx* ctx, const GemmLaunch& L) {
             plan = x;
             break;
         }
-    } else if (ctx->autotune) {
+    } else if (ctx->autotune || !ctx->tune_cache.empty()) {
+        // measured plans are used whenever they exist; new measurements are only taken while autotuning is on
         const std::vector<long long> key = tune_key(L, q);
         auto it = ctx->tune_cache.find(key);
         if (it != ctx->tune_cache.end()) {
             plan = plan_from_array(it->second);
-        } else {
+        } else if (ctx->autotune) {
             cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
             cudaStreamIsCapturing(ctx->stream, &cs);
             // re-running the launch must be idempotent: the output may not alias the residual

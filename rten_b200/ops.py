@@ -71,6 +71,12 @@ class Context:
         """Time candidate launch plans the first time each MatMul / Conv problem is seen (outside graph capture)."""
         self.check(self.lib.rten_b200_set_autotune(self.handle, 1 if enable else 0))
 
+    def save_plans(self, path: str):
+        self.check(self.lib.rten_b200_save_plans(self.handle, path.encode()))
+
+    def load_plans(self, path: str):
+        self.check(self.lib.rten_b200_load_plans(self.handle, path.encode()))
+
     @property
     def launches(self) -> int:
         return int(self.lib.rten_b200_launch_count(self.handle))

@@ -6,17 +6,35 @@ import math
 import numpy as np
 
 
-def resnet50_oracle(oracle, spec, x):
-    def conv(c, t):
-        return oracle.conv(t, c.w, c.b, [c.pad] * 4, 1, (c.stride, c.stride), (1, 1))
+def resnet50_oracle(oracle, spec, x, arena=None):
+    """`arena` (oracle.Arena): recycle operator outputs from the previous pass and run Relu / Add in place, as the
+    reference's BufferPool and in-place operators do (same arithmetic)."""
+    n = [0]
 
-    y = oracle.relu(conv(spec.stem, x))
+    def conv(c, t):
+        n[0] += 1
+        out = None
+        if arena is not None:
+            B, _, H, W = t.shape
+            O, _, kh, kw = c.w.shape
+            oh = (H + 2 * c.pad - kh) // c.stride + 1
+            ow = (W + 2 * c.pad - kw) // c.stride + 1
+            out = arena.get(("conv", n[0]), (B, O, oh, ow))
+        return oracle.conv(t, c.w, c.b, [c.pad] * 4, 1, (c.stride, c.stride), (1, 1), out=out)
+
+    def relu(t):
+        return oracle.relu(t, out=t if arena is not None else None)
+
+    def add(a, b):
+        return oracle.add(a, b, out=a if arena is not None else None)
+
+    y = relu(conv(spec.stem, x))
     y = oracle.max_pool(y, (3, 3), [1, 1, 1, 1], (2, 2))
     for b in spec.blocks:
         ident = y if b.down is None else conv(b.down, y)
-        t = oracle.relu(conv(b.c1, y))
-        t = oracle.relu(conv(b.c2, t))
-        y = oracle.relu(oracle.add(conv(b.c3, t), ident))
+        t = relu(conv(b.c1, y))
+        t = relu(conv(b.c2, t))
+        y = relu(add(conv(b.c3, t), ident))
     p = oracle.global_average_pool(y)
     return oracle.gemm_op(p.reshape(p.shape[0], p.shape[1]), spec.fc_w, spec.fc_b, 1.0, 1.0, False, True)
 

@@ -60,9 +60,9 @@ def time_graph(ctx, run, n, reps=30):
 cases = [(64, 64, 3, 56), (128, 128, 3, 28), (256, 256, 3, 14), (512, 512, 3, 7), (64, 64, 1, 56), (256, 256, 1, 14)]
 for mode in ("single", "seq"):
     if mode == "single":
-        os.environ["RTEN_B200_NO_SEQ"] = "1"
+        os.environ.pop("RTEN_B200_SEQ", None)
     else:
-        os.environ.pop("RTEN_B200_NO_SEQ", None)
+        os.environ["RTEN_B200_SEQ"] = "1"  # opt-in persistent sequence kernel (grid barrier between layers)
     os.environ["RTEN_B200_NO_CTA2"] = "1"
     ctx = rt.Context(0, stream=stream.cuda_stream)
     ctx.set_autotune(True)

@@ -1,5 +1,5 @@
 """Merge an ncu launch list (gpu__time_duration per launch) of ONE model pass with the host's per-launch tile
-configuration (RTEN_B200_VERBOSE lines, same order).  Usage: merge_launches.py launches.csv verbose.log"""
+configuration (RTEN_B200_VERBOSE lines, same order).  Usage: merge_launches.py launches.csv verbose.log [last_n]"""
 import csv
 import sys
 
@@ -7,6 +7,8 @@ lines = [l for l in open(sys.argv[1]) if not l.startswith("==")]
 rows = [r for r in csv.DictReader(lines) if "umma_gemm" in r["Kernel Name"]]
 cfg = [l.strip()[12:] for l in open(sys.argv[2]) if l.startswith("[umma_gemm]")]
 n = min(len(rows), len(cfg))
+if len(sys.argv) > 3:  # only the last N launches (one model pass)
+    n = min(n, int(sys.argv[3]))
 rows, cfg = rows[-n:], cfg[-n:]
 tot = 0.0
 out = []
