@@ -114,7 +114,7 @@ def run_reference_arm(args, model, batch):
     ncores = oracle.use_all_cores()
     spec = make_spec(oracle, model)
     # images are the outer parallel level: a many-core host needs the whole batch in flight to be busy
-    sample = (batch if ncores >= 32 else 8) if model == "resnet50" else (batch if ncores >= 32 else 4)
+    sample = (batch if ncores >= 16 else 8) if model == "resnet50" else (batch if ncores >= 16 else 4)
     inp = make_inputs(oracle, model, sample)
     arena = oracle.Arena()  # = the reference's BufferPool: operator outputs are recycled from pass to pass
     run = (lambda: model_ref.resnet50_oracle(oracle, spec, inp["x"], arena)) if model == "resnet50" else \
@@ -294,21 +294,76 @@ def main():
     h2d = sum(h.nbytes for h, _ in pinned)
     d2h = host_out.nbytes
 
-    def h2d_copy(h, d):
-        # host arrays are NCHW-contiguous; the device tensor keeps its (channels-last) strides
-        src = rt.ops._desc(h.ctypes.data, h.dtype, h.shape, rt.ops._contig(h.shape), -1)
-        dst = d.desc()
-        ctx.check(ctx.lib.rten_b200_copy(ctx.handle, C.byref(src), C.byref(dst)))
+    # Double-buffered pipeline through the public API: a second context bound to a copy stream moves step i+1's input
+    # from pinned host memory into a raw device buffer while step i computes; the compute stream re-lays it out into the
+    # model's input tensor (channels-last for ResNet-50), replays the step and copies the result back to the host.
+    # EVERY step's H2D and D2H are inside the timed region; nothing is reused across steps.
+    copy_stream = torch.cuda.Stream()
+    cctx = rt.Context(local_rank, stream=copy_stream.cuda_stream)
+    raw = [[cctx.empty(h.shape, h.dtype) for h, _ in pinned] for _ in range(2)]
+    ev_copied = [torch.cuda.Event() for _ in range(2)]
+    ev_consumed = [torch.cuda.Event() for _ in range(2)]
+    host_outs = [host_out, ctx.pinned_empty(out_shape, np.float32)]
 
-    def e2e_step():
-        for h, d in pinned:
-            h2d_copy(h, d)
-        device_step()
-        src = out_dst.desc()
-        dst = rt.ops._desc(host_out.ctypes.data, host_out.dtype, host_out.shape, rt.ops._contig(host_out.shape), -1)
-        ctx.check(ctx.lib.rten_b200_copy(ctx.handle, C.byref(src), C.byref(dst)))
+    def issue_h2d(i):
+        b = i % 2
+        if i >= 2:
+            copy_stream.wait_event(ev_consumed[b])
+        for (h, _), r in zip(pinned, raw[b]):
+            src = rt.ops._desc(h.ctypes.data, h.dtype, h.shape, rt.ops._contig(h.shape), -1)
+            dst = r.desc()
+            cctx.check(cctx.lib.rten_b200_copy(cctx.handle, C.byref(src), C.byref(dst)))
+        ev_copied[b].record(copy_stream)
 
-    ms_e2e, _, _ = timed(e2e_step, args.steps, 3)
+    out_bufs = [ctx.empty(out_shape, np.float32) for _ in range(2)]
+    ev_done = [torch.cuda.Event() for _ in range(2)]
+
+    def issue_d2h(i):
+        # result of step i: device copy made by the compute stream -> pinned host buffer, on the copy stream
+        b = i % 2
+        copy_stream.wait_event(ev_done[b])
+        src = out_bufs[b].desc()
+        ho = host_outs[b]
+        dst = rt.ops._desc(ho.ctypes.data, ho.dtype, ho.shape, rt.ops._contig(ho.shape), -1)
+        cctx.check(cctx.lib.rten_b200_copy(cctx.handle, C.byref(src), C.byref(dst)))
+
+    def e2e_run(steps):
+        """-> device milliseconds from the first H2D to the last D2H of `steps` pipelined steps"""
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record(copy_stream)
+        issue_h2d(0)
+        for i in range(steps):
+            b = i % 2
+            stream.wait_event(ev_copied[b])
+            for (_, d), r in zip(pinned, raw[b]):
+                a_, b_ = r.desc(), d.desc()
+                ctx.check(ctx.lib.rten_b200_copy(ctx.handle, C.byref(a_), C.byref(b_)))  # layout change, device to device
+            ev_consumed[b].record(stream)
+            flush.zero_()  # L2 flush between steps (inside the timed region here)
+            device_step()
+            a_, b_ = out_dst.desc(), out_bufs[b].desc()
+            ctx.check(ctx.lib.rten_b200_copy(ctx.handle, C.byref(a_), C.byref(b_)))
+            ev_done[b].record(stream)
+            # the host now feeds the NEXT step and collects the PREVIOUS result while this step runs
+            if i + 1 < steps:
+                issue_h2d(i + 1)
+            if i >= 1:
+                issue_d2h(i - 1)
+        issue_d2h(steps - 1)
+        t1.record(copy_stream)
+        torch.cuda.synchronize()
+        ms = t0.elapsed_time(t1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    e2e_run(3)
+    ms_e2e = e2e_run(args.steps)
     e2e_value = batch * world * args.steps / (ms_e2e / 1e3)
 
     # ---- roofline of the dominant kernel: per-launch CUDA-event timing of every GEMM/conv op of one pass
@@ -327,7 +382,8 @@ def main():
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32(tf32 mma)",
             "data": "synthetic", "config": config_of(model, batch, world), "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": ms_e2e / args.steps},
+                    "ms_per_step": ms_e2e / args.steps,
+                    "how": "double-buffered: the copy stream moves step i+1's input H2D and step i-1's result D2H while step i computes; every step's H2D + D2H and the L2 flush are inside the timed region"},
             "gpu_launches": int(launches),
             "cuda_graph": graph is not None,
             "model_tflops": flops * world * args.steps / (ms / 1e3) / 1e12,

@@ -688,11 +688,32 @@ def num_threads() -> int:
     return int(lib().rto_num_threads())
 
 
-def use_all_cores() -> int:
-    """Use every core this process may run on (torchrun sets OMP_NUM_THREADS=1 for its workers)."""
+def usable_cores() -> int:
+    """Cores this process may actually use: its affinity mask, capped by the cgroup CPU quota (a container can see 128
+    CPUs and be throttled to 16 -- running 128 spinning threads there is 10x slower than running 16)."""
     try:
         n = len(os.sched_getaffinity(0))
     except AttributeError:
         n = os.cpu_count() or 1
-    lib().rto_set_num_threads(n)
+    quota = None
+    try:
+        q, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            quota = float(q) / float(period)
+    except Exception:
+        try:
+            q = float(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            period = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                quota = q / period
+        except Exception:
+            pass
+    if quota is not None:
+        n = max(1, min(n, int(quota + 0.5)))
+    return n
+
+
+def use_all_cores() -> int:
+    """Use every core this process may run on (torchrun sets OMP_NUM_THREADS=1 for its workers)."""
+    lib().rto_set_num_threads(usable_cores())
     return num_threads()
