@@ -48,6 +48,31 @@ constexpr int NUM_THREADS = 384;   // 4 control warps + 8 epilogue warps (two gr
 constexpr int STG_BYTES = 128 * 128;  // one 128-row x 128-byte output staging buffer per epilogue group
 constexpr int MAX_STAGES = 8;
 
+// Division by a launch-time constant as multiply-high + shift (exact for 0 <= n < 2^31): the tile decode sits on the
+// critical path at the start of every kernel and of every tile, and a hardware-emulated 32-bit division costs ~100
+// instructions.
+struct FastDiv {
+    uint32_t d = 1, mul = 0, shr = 0;
+    __host__ void set(int div) {
+        d = (uint32_t)(div < 1 ? 1 : div);
+        if (d == 1) {
+            mul = 0;
+            shr = 0;
+            return;
+        }
+        uint32_t lg = 0;
+        while ((1ull << lg) < d) lg++;  // ceil(log2(d))
+        const uint32_t p = 31 + lg;
+        mul = (uint32_t)(((1ull << p) + d - 1) / d);
+        shr = p - 32;
+    }
+    __device__ __forceinline__ int div(int n) const { return d == 1 ? n : (int)(__umulhi((uint32_t)n, mul) >> shr); }
+    __device__ __forceinline__ void divmod(int n, int& q, int& r) const {
+        q = div(n);
+        r = n - q * (int)d;
+    }
+};
+
 struct KParams {
     int M, N, K, z0, z1;
     int tiles_m, tiles_n, tiles_total;
@@ -81,6 +106,7 @@ struct KParams {
     int cta2;       // 1: CTA pairs (cluster 2x1x1) execute 256-row tcgen05.mma.cta_group::2 tiles; each CTA loads its own
                     //    128 rows of A and HALF of the B tile, so operand bytes entering an SM per flop drop by up to 2x
     int units_total;  // tiles_total * splitk
+    FastDiv d_tiles_n, d_units_m, d_z0, d_tiles_x, d_tiles_y, d_tiles_total, d_c_blocks, d_kw, d_tw, d_th;
     uint32_t* sk_ws;
     int* sk_cnt;
     EpilogueDesc epi;
@@ -96,24 +122,20 @@ struct TileCoord {
 // t indexes work units: (n tile, m tile or PAIR of m tiles, batch); `sub` selects the tile inside a pair.
 __device__ __forceinline__ TileCoord decode_tile(const KParams& p, int t, int sub, int rank = 0) {
     TileCoord c;
-    int n_blk = t % p.tiles_n;
-    int rest = t / p.tiles_n;
+    int n_blk, rest, m_blk, z;
+    p.d_tiles_n.divmod(t, rest, n_blk);
     // one unit = (pair + 1) MMA tiles of (cta2 + 1) x 128 rows: `mult` consecutive 128-row blocks
     const int mult = (p.pair + 1) * (p.cta2 + 1);
-    const int units_m = (p.tiles_m + mult - 1) / mult;
-    int m_blk = rest % units_m;
-    int z = rest / units_m;
+    p.d_units_m.divmod(rest, z, m_blk);
     m_blk = m_blk * mult + sub * (p.cta2 + 1) + rank;  // may be >= tiles_m in the tail: every row is then out of range
     c.n0 = n_blk * p.bn;
     c.m0 = m_blk * BM;
-    c.z0 = z % p.z0;
-    c.z1 = z / p.z0;
+    p.d_z0.divmod(z, c.z1, c.z0);
     c.ox0 = c.oy0 = c.b0 = 0;
     if (p.conv) {
-        int xt = m_blk % p.tiles_x;
-        int r2 = m_blk / p.tiles_x;
-        int yt = r2 % p.tiles_y;
-        int bt = r2 / p.tiles_y;  // >= number of batch tiles for the odd tail of a pair -> b0 >= B
+        int xt, r2, yt, bt;
+        p.d_tiles_x.divmod(m_blk, r2, xt);
+        p.d_tiles_y.divmod(r2, bt, yt);  // bt >= number of batch tiles for the odd tail of a pair -> b0 >= B
         c.ox0 = xt * p.tw;
         c.oy0 = yt * p.th;
         c.b0 = bt * p.tb;
@@ -229,12 +251,15 @@ __device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* t
         const uint32_t a_bytes = (p.pair ? 2 : 1) * A_STAGE_BYTES;
         const int b_row0 = CTA2 ? cta_rank * (p.bn >> 1) : 0;  // this CTA's half of the B tile
         for (int u = worker; u < p.units_total; u += n_workers) {
-            const int t = u % p.tiles_total;
-            const int kb0 = (u / p.tiles_total) * p.kb_per, kb1 = min(p.k_blocks, kb0 + p.kb_per);
+            int t, ks;
+            p.d_tiles_total.divmod(u, ks, t);
+            const int kb0 = ks * p.kb_per, kb1 = min(p.k_blocks, kb0 + p.kb_per);
             const TileCoord tc = decode_tile(p, t, 0, cta_rank);
-            const TileCoord tc1 = decode_tile(p, t, 1, cta_rank);
+            const TileCoord tc1 = p.pair ? decode_tile(p, t, 1, cta_rank) : tc;
             // conv: K block -> (filter tap, channel block), kept incrementally
-            int tap = kb0 / p.c_blocks, cb = kb0 - tap * p.c_blocks, ky = tap / p.kw, kx = tap - ky * p.kw;
+            int tap, cb, ky, kx;
+            p.d_c_blocks.divmod(kb0, tap, cb);
+            p.d_kw.divmod(tap, ky, kx);
             for (int kb = kb0; kb < kb1; kb += p.katoms) {
                 const int natoms = min(p.katoms, kb1 - kb);
                 mbar_wait(&empty_bar[stage], ((st.ring >> stage) & 1) ^ 1);
@@ -296,7 +321,7 @@ __device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* t
         const uint32_t b_off = (p.pair ? 2 : 1) * A_STAGE_BYTES;
         const uint32_t d1_off = (p.pair || p.ksplit) ? p.bn : 0;
         for (int u = worker; u < p.units_total; u += n_workers, st.it++) {
-            const int kb0 = (u / p.tiles_total) * p.kb_per, kb1 = min(p.k_blocks, kb0 + p.kb_per);
+            const int kb0 = p.d_tiles_total.div(u) * p.kb_per, kb1 = min(p.k_blocks, kb0 + p.kb_per);
             const int acc = p.acc1 ? 0 : (st.it & 1);
             mbar_wait(&tmem_empty[acc], ((st.acc >> acc) & 1) ^ 1);
             st.acc ^= 1u << acc;
@@ -364,7 +389,8 @@ __device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* t
         uint32_t ci = 0;
         uint32_t& rphase = st.rphase;
         for (int u = worker; u < p.units_total; u += n_workers, st.it++) {
-            const int t = u % p.tiles_total;
+            int t, ks_u;
+            p.d_tiles_total.divmod(u, ks_u, t);
             const int acc = p.acc1 ? 0 : (st.it & 1);
             const uint32_t acc_phase = (st.acc >> acc) & 1;
             st.acc ^= 1u << acc;
@@ -383,7 +409,7 @@ __device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* t
             tc_fence_after();
             bool owner = true;
             if (p.splitk > 1)
-                owner = splitk_publish(p, CTA2 ? 2 * t + cta_rank : t, u / p.tiles_total, grp, q, lane,
+                owner = splitk_publish(p, CTA2 ? 2 * t + cta_rank : t, ks_u, grp, q, lane,
                                        tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_STRIDE, &sk_flag[grp]);
             for (int sub = 0; owner && sub <= p.pair; sub++) {
                 const TileCoord tc = decode_tile(p, t, sub, cta_rank);
@@ -394,7 +420,9 @@ __device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* t
                     int m_idx;
                     bool row_ok;
                     if (p.conv) {
-                        const int xi = r % p.tw, r2 = r / p.tw, yi = r2 % p.th, bi = r2 / p.th;
+                        int xi, r2, yi, bi;
+                        p.d_tw.divmod(r, r2, xi);
+                        p.d_th.divmod(r2, bi, yi);
                         const int ox = tc.ox0 + xi, oy = tc.oy0 + yi, b = tc.b0 + bi;
                         row_ok = (bi < p.tb) && (ox < p.OW) && (oy < p.OH) && (b < p.Bn);
                         m_idx = (b * p.OH + oy) * p.OW + ox;
@@ -544,7 +572,9 @@ __device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* t
                     mbar_arrive(&tmem_empty[acc]);
             }
         }
-        if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        // shared memory must stay valid until the last bulk store has READ it; the global writes complete on their own
+        // before the grid is considered finished (a sequence kernel waits for them at its layer boundary)
+        if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     } else if (!FAST && warp >= 4) {
         // ===================== epilogue (generic) =====================
         const EpilogueDesc& e = p.epi;
@@ -558,7 +588,8 @@ __device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* t
         const int it0 = st.it;
         for (int u = worker; u < p.units_total; u += n_workers, st.it++) {
             const int it = st.it - it0;
-            const int t = u % p.tiles_total;
+            int t, ks_u;
+            p.d_tiles_total.divmod(u, ks_u, t);
             const int acc = p.acc1 ? 0 : (st.it & 1);
             const uint32_t acc_phase = (st.acc >> acc) & 1;
             st.acc ^= 1u << acc;
@@ -579,7 +610,7 @@ __device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* t
             tc_fence_after();
             bool owner = true;
             if (p.splitk > 1)
-                owner = splitk_publish(p, CTA2 ? 2 * t + cta_rank : t, u / p.tiles_total, grp, q, lane,
+                owner = splitk_publish(p, CTA2 ? 2 * t + cta_rank : t, ks_u, grp, q, lane,
                                        tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_STRIDE, &sk_flag[grp]);
             for (int sub = 0; owner && sub <= p.pair; sub++) {
             const TileCoord tc = decode_tile(p, t, sub, cta_rank);
@@ -588,10 +619,9 @@ __device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* t
             long long d_off, r_off;
             int m_idx;
             if (p.conv) {
-                const int xi = r % p.tw;
-                const int r2 = r / p.tw;
-                const int yi = r2 % p.th;
-                const int bi = r2 / p.th;
+                int xi, r2, yi, bi;
+                p.d_tw.divmod(r, r2, xi);
+                p.d_th.divmod(r2, bi, yi);
                 const int ox = tc.ox0 + xi, oy = tc.oy0 + yi, b = tc.b0 + bi;
                 row_ok = (bi < p.tb) && (ox < p.OW) && (oy < p.OH) && (b < p.Bn);
                 d_off = (long long)b * e.s_z0 + (long long)oy * e.s_row + (long long)ox * e.s_z1;
@@ -798,7 +828,7 @@ __device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* t
             }
         }
         // smem must stay valid until the last bulk store has read it
-        if (p.tma_store && issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        if (p.tma_store && issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
 
 }
@@ -824,16 +854,18 @@ __device__ __forceinline__ uint32_t kernel_setup(const SmemLayout& L) {
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(L.res_bar + 8);
-    if (warp == 1 && lane == 0) {
-        for (int s = 0; s < MAX_STAGES; s++) {
-            mbar_init(&L.full_bar[s], 1);
-            mbar_init(&L.empty_bar[s], 1);
+    if (warp == 1) {
+        // 28 barriers, one per lane (a single thread initialising them serially sat on the start-up critical path):
+        // lanes 0-15 ring full / empty, 16-17 accumulator full, 18-19 accumulator empty, 20-27 residual
+        if (lane < 2 * MAX_STAGES) {
+            mbar_init(&L.full_bar[lane], 1);  // full_bar and empty_bar are contiguous
+        } else if (lane < 2 * MAX_STAGES + 2) {
+            mbar_init(&L.tmem_full[lane - 2 * MAX_STAGES], 1);
+        } else if (lane < 2 * MAX_STAGES + 4) {
+            mbar_init(&L.tmem_empty[lane - 2 * MAX_STAGES - 2], CTA2 ? 16 : 8);  // one arrival per epilogue warp (of both CTAs of a pair)
+        } else if (lane < 2 * MAX_STAGES + 12) {
+            mbar_init(&L.res_bar[lane - 2 * MAX_STAGES - 4], 1);
         }
-        for (int s = 0; s < 2; s++) {
-            mbar_init(&L.tmem_full[s], 1);
-            mbar_init(&L.tmem_empty[s], CTA2 ? 16 : 8);  // one arrival per epilogue warp (of both CTAs of a pair)
-        }
-        for (int s = 0; s < 8; s++) mbar_init(&L.res_bar[s], 1);
         fence_mbar_init();
     }
     if (warp == 2) {
@@ -909,7 +941,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 // kernel launch, TMEM allocation, tensor-map fetch and a cold pipeline.  Layer parameters and tensor maps live in the
 // kernel parameter block (constant bank), indexed by the layer number.
 // ------------------------------------------------------------------------------------------
-constexpr int SEQ_MAX = 32;
+constexpr int SEQ_MAX = 28;
 struct SeqParams {
     int n;
     int pad;
@@ -1455,6 +1487,16 @@ static rten_status launch_plan(rten_ctx* ctx, const GemmLaunch& L, const Prepare
     p.tiles_n = (int)ps.tiles_n;
     p.tiles_total = (int)ps.tiles;
     p.units_total = (int)ps.units;
+    p.d_tiles_n.set(p.tiles_n);
+    p.d_units_m.set((int)ps.units_m);
+    p.d_z0.set(p.z0);
+    p.d_tiles_x.set(p.conv ? p.tiles_x : 1);
+    p.d_tiles_y.set(p.conv ? p.tiles_y : 1);
+    p.d_tiles_total.set(p.tiles_total);
+    p.d_c_blocks.set(p.c_blocks);
+    p.d_kw.set(p.kw);
+    p.d_tw.set(p.conv ? p.tw : 1);
+    p.d_th.set(p.conv ? p.th : 1);
     const int n_stg = 2 * p.nbuf;
     p.atom_bytes = ps.atom_bytes;
     p.stage_bytes = ps.stage_bytes;
