@@ -277,7 +277,6 @@ rten_status rten_b200_sync(rten_ctx* ctx) {
 rten_status rten_b200_set_f32_mode(rten_ctx* ctx, int mode) {
     if (!ctx) return RTEN_ERR_INVALID_VALUE;
     if (mode != RTEN_F32_TF32 && mode != RTEN_F32_TF32X3) return fail(ctx, RTEN_ERR_INVALID_VALUE, "unknown f32 mode");
-    if (mode == RTEN_F32_TF32X3) return fail(ctx, RTEN_ERR_UNSUPPORTED_VALUE, "tf32x3 mode is not implemented yet");
     ctx->f32_mode = mode;
     return RTEN_OK;
 }

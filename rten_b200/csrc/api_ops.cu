@@ -655,7 +655,7 @@ rten_status conv_core(OpScope& sc, ConvArgs& A, rten_tensor* out) {
 
     // ---- small-channel path (C <= 4, e.g. the RGB stem): NHWC4 zero-padded copy, one 128-byte K block per filter
     //      row holding kw pixels x 4 channels; vertical padding / stride stay in the TMA tile addressing.
-    const bool smallc_ok = !implicit_ok && A.kind == 0 && groups == 1 && Cg <= 4 && kw * 4 <= 32 && dil[1] == 1 &&
+    const bool smallc_ok = !implicit_ok && A.kind == 0 && ctx->f32_mode != RTEN_F32_TF32X3 && groups == 1 && Cg <= 4 && kw * 4 <= 32 && dil[1] == 1 &&
                            (int64_t)B * OH * OW > 0 && !getenv("RTEN_B200_NO_SMALLC");
     if (smallc_ok) {
         const int64_t Wp = (OW - 1) * strides[1] + 8;  // every window of 8 pixels stays inside the padded row

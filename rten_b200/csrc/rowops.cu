@@ -893,4 +893,60 @@ rten_status launch_gather_rows(rten_ctx* ctx, const float* table, const int* idx
     return RTEN_OK;
 }
 
+
+// =========================================================================================
+// 3xTF32 operand split (RTEN_F32_TF32X3): x = hi + lo with hi = x truncated to TF32 (low 13 mantissa bits cleared,
+// exactly what kind::tf32 reads) and lo = x - hi (exact in f32).  The tensor-core product over a reduction dimension
+// that holds [lo | hi | hi] for one operand and [hi | lo | hi] for the other is
+//     sum a_lo*b_hi + a_hi*b_lo + a_hi*b_hi      (a_lo*b_lo ~ 2^-22 |ab| dropped)
+// i.e. an f32-accurate product from three TF32 passes, small terms first.  Source: rank-4 tensor with inner stride 1;
+// destination: contiguous [d3][d2][d1][3 * d0p], each third zero-padded from d0 to d0p elements.
+// =========================================================================================
+struct SplitParams {
+    long long d0, d0p, d1, d2, d3;
+    long long s1, s2, s3;  // source strides (elements) of dims 1..3
+    long long n;           // d3 * d2 * d1 * d0p
+    int role;              // 0: [lo | hi | hi] (A operand), 1: [hi | lo | hi] (B operand)
+};
+
+__global__ void __launch_bounds__(256) tf32x3_split_kernel(const float* __restrict__ x, float* __restrict__ y, const SplitParams p) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += stride) {
+        const long long c = i % p.d0p;
+        long long r = i / p.d0p;
+        const long long i1 = r % p.d1;
+        r /= p.d1;
+        const long long i2 = r % p.d2, i3 = r / p.d2;
+        float v = 0.0f;
+        if (c < p.d0) v = x[i3 * p.s3 + i2 * p.s2 + i1 * p.s1 + c];
+        const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+        const float lo = __fsub_rn(v, hi);
+        float* row = y + ((i3 * p.d2 + i2) * p.d1 + i1) * (3 * p.d0p);
+        row[c] = p.role == 0 ? lo : hi;
+        row[p.d0p + c] = p.role == 0 ? hi : lo;
+        row[2 * p.d0p + c] = hi;
+    }
+}
+
+rten_status launch_tf32x3_split(rten_ctx* ctx, const float* x, float* y, const long long dims[4], const long long strides[4],
+                                long long d0p, int role) {
+    SplitParams p;
+    p.d0 = dims[0];
+    p.d0p = d0p;
+    p.d1 = dims[1];
+    p.d2 = dims[2];
+    p.d3 = dims[3];
+    p.s1 = strides[1];
+    p.s2 = strides[2];
+    p.s3 = strides[3];
+    p.n = p.d3 * p.d2 * p.d1 * p.d0p;
+    p.role = role;
+    if (p.n == 0) return RTEN_OK;
+    tf32x3_split_kernel<<<ew_grid(ctx, p.n), 256, 0, launch_stream(ctx)>>>(x, y, p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "tf32x3 split launch");
+    count_launch(ctx);
+    return RTEN_OK;
+}
+
 }  // namespace rtb

@@ -58,4 +58,8 @@ rten_status launch_maxpool(rten_ctx* ctx, const float* x, float* y, const PoolPa
 rten_status launch_gather_rows(rten_ctx* ctx, const float* table, const int* idx, float* out, long long nidx,
                                int width, long long t_rs, long long t_cs, long long rows);
 
+// 3xTF32 operand split: dst contiguous [d3][d2][d1][3 * d0p]; role 0 = [lo|hi|hi], 1 = [hi|lo|hi]
+rten_status launch_tf32x3_split(rten_ctx* ctx, const float* x, float* y, const long long dims[4], const long long strides[4],
+                                long long d0p, int role);
+
 }  // namespace rtb

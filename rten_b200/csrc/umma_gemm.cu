@@ -35,6 +35,7 @@
 
 #include "math.cuh"
 #include "ptx.cuh"
+#include "rowops.h"
 #include "umma_gemm.h"
 
 namespace rtb {
@@ -1600,7 +1601,47 @@ static Plan plan_from_array(const std::array<int, 8>& a) {
     return pl;
 }
 
+// RTEN_F32_TF32X3: run the same kernel over split operands -- K (plain) or C (conv; K order is (ky, kx, c)) tripled.
+static rten_status launch_tf32x3(rten_ctx* ctx, const GemmLaunch& L0) {
+    GemmLaunch L = L0;
+    const long long d0 = L0.a.dims[0];               // K, or channels per group
+    const long long d0p = (d0 + 3) / 4 * 4;          // thirds stay 16-byte aligned for TMA
+    auto split = [&](const OperandDesc& src, OperandDesc& dst, int role) -> rten_status {
+        long long dims[4], strides[4], n = 3 * d0p;
+        for (int i = 0; i < 4; i++) {
+            // broadcast dims (stride 0) are split once and stay broadcast
+            dims[i] = (i > 0 && src.strides[i] == 0) ? 1 : src.dims[i];
+            strides[i] = src.strides[i];
+        }
+        for (int i = 1; i < 4; i++) n *= dims[i];
+        void* buf = nullptr;
+        RTB_TRY(temp_alloc(ctx, (size_t)n * 4, &buf));
+        RTB_TRY(launch_tf32x3_split(ctx, (const float*)src.base, (float*)buf, dims, strides, d0p, role));
+        dst = src;
+        dst.base = buf;
+        dst.dims[0] = 3 * d0p;
+        long long st = 3 * d0p;
+        for (int i = 1; i < 4; i++) {
+            dst.strides[i] = (src.strides[i] == 0 && src.dims[i] > 1) ? 0 : st;
+            st *= dims[i];
+        }
+        return RTEN_OK;
+    };
+    if (L0.b.dims[0] != d0) return RTEN_ERR_UNSUPPORTED_VALUE;
+    RTB_TRY(split(L0.a, L.a, 0));
+    RTB_TRY(split(L0.b, L.b, 1));
+    if (L.conv)
+        L.g.C = (int)(3 * d0p);
+    L.K = L.conv ? (int)(L0.K / d0 * 3 * d0p) : (int)(3 * d0p);
+    const int saved = ctx->f32_mode;
+    ctx->f32_mode = RTEN_F32_TF32;
+    const rten_status st = launch_umma_gemm(ctx, L);
+    ctx->f32_mode = saved;
+    return st;
+}
+
 rten_status launch_umma_gemm(rten_ctx* ctx, const GemmLaunch& L) {
+    if (L.kind == 0 && ctx->f32_mode == RTEN_F32_TF32X3) return launch_tf32x3(ctx, L);
     Prepared q;
     RTB_TRY(prepare_launch(ctx, L, q));
     const bool verbose = getenv("RTEN_B200_VERBOSE") != nullptr;

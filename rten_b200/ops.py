@@ -67,6 +67,10 @@ class Context:
     def sync(self):
         self.check(self.lib.rten_b200_sync(self.handle))
 
+    def set_f32_mode(self, tf32x3: bool):
+        """False: single-pass TF32 (default).  True: 3xTF32 error-compensated products, ~f32 accuracy at 1/3 of the rate."""
+        self.check(self.lib.rten_b200_set_f32_mode(self.handle, 1 if tf32x3 else 0))
+
     def set_autotune(self, enable: bool = True):
         """Time candidate launch plans the first time each MatMul / Conv problem is seen (outside graph capture)."""
         self.check(self.lib.rten_b200_set_autotune(self.handle, 1 if enable else 0))

@@ -686,6 +686,38 @@ def check_gpt2_int8_kvcache(rt, oracle):
     return f"prefill {T0} + 3 decode steps, worst rel err {worst:.2e}"
 
 
+def check_tf32x3(rt, oracle):
+    """RTEN_F32_TF32X3: three TF32 passes over split operands (hi*hi + hi*lo + lo*hi).  Stated tolerance:
+    |got - exact| <= 2^-18 * sum_k |a_k b_k| + 1e-6 -- 500x tighter than the single-pass bound and of the order of the
+    reference's own f32 accumulation error; whole ResNet-50 logits within 1e-4 of max |ref| (single pass: ~1e-3)."""
+    global TF32_REL
+    from rten_b200 import graphs
+    import model_ref
+    ctx = rt.Context(0)
+    ctx.set_f32_mode(True)
+    saved = TF32_REL
+    TF32_REL = 2.0 ** -18
+    try:
+        w = _matmul_case(rt, oracle, ctx, (128, 64), (64, 128))
+        w = max(w, _matmul_case(rt, oracle, ctx, (3, 130, 520), (520, 300), seed=6))
+        w = max(w, _matmul_case(rt, oracle, ctx, (2, 4, 64, 33), (2, 4, 33, 70), seed=9))            # batched B, K % 4 != 0
+        w = max(w, _matmul_case(rt, oracle, ctx, (384, 1024), (1024, 512), bias=True, prepack=True, seed=5))
+        w = max(w, _conv_case(rt, oracle, ctx, (2, 64, 20, 20), (96, 64, 1, 1), cl=True))
+        w = max(w, _conv_case(rt, oracle, ctx, (2, 32, 14, 14), (64, 32, 3, 3), pads=(1, 1, 1, 1), cl=True, residual=True, act=1))
+        w = max(w, _conv_case(rt, oracle, ctx, (2, 16, 9, 9), (32, 8, 3, 3), pads=(1, 1, 1, 1), groups=2, strides=(2, 2), cl=False))
+        w = max(w, _conv_case(rt, oracle, ctx, (2, 3, 32, 32), (16, 3, 7, 7), pads=(3, 3, 3, 3), strides=(2, 2), cl=True))   # stem-like
+    finally:
+        TF32_REL = saved
+    rng = oracle.XorShiftRng(5678)
+    spec = graphs.make_resnet50(lambda s: rng.uniform(s))
+    x = oracle.XorShiftRng(1234).uniform((2, 3, 224, 224))
+    ref = model_ref.resnet50_oracle(oracle, spec, x)
+    got = graphs.ResNet50Runner(ctx, spec, fuse=True).run(ctx.to_device(x, channels_last=True)).numpy()
+    rel = float(np.abs(got - ref).max() / np.abs(ref).max())
+    assert rel <= 1e-4, f"ResNet-50 logits in 3xTF32 mode: rel err {rel:.3e}"
+    return f"worst err/bound {w:.3f} (bound 2^-18); ResNet-50 logits rel err {rel:.2e}"
+
+
 def check_resnet50_model(rt, oracle):
     """Whole-model parity (ResNet-50 fp32, full 224x224 images, batch 2): every conv runs single-pass TF32,
     so the logits carry ~53 layers of 2^-11-relative operand rounding.  Stated tolerance: max |d| <= 1e-2 * max |ref|."""
@@ -739,6 +771,6 @@ ALL_CHECKS = [
     ("dql", check_dql), ("glue", check_glue), ("matmul_small", check_matmul_small), ("matmul_shapes", check_matmul_shapes),
     ("matmul_bert", check_matmul_bert), ("gemm_op", check_gemm_op), ("matmul_integer", check_matmul_integer),
     ("conv_basic", check_conv_basic), ("conv_stride", check_conv_stride), ("conv_more", check_conv_more),
-    ("conv_integer", check_conv_integer), ("plans", check_plans), ("sequence", check_sequence), ("conv_integer_fused", check_conv_integer_fused),
+    ("conv_integer", check_conv_integer), ("plans", check_plans), ("tf32x3", check_tf32x3), ("sequence", check_sequence), ("conv_integer_fused", check_conv_integer_fused),
     ("resnet50_int8_model", check_resnet50_int8_model), ("gpt2_int8_kvcache", check_gpt2_int8_kvcache), ("resnet50_model", check_resnet50_model), ("bert_model", check_bert_model),
 ]
