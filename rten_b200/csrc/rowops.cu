@@ -44,11 +44,22 @@ __global__ void __launch_bounds__(256) softmax_kernel(const SoftmaxParams p) {
     float* y = p.y + row * p.n;
     const float* m = nullptr;
     if (p.mask) {
-        long long rem = row, off = 0;
-        for (int d = p.nlead - 1; d >= 0; d--) {
-            const long long idx = rem % p.lead[d];
-            rem /= p.lead[d];
-            off += idx * p.mstride[d];
+        long long off = 0;
+        if (p.rows < 0x7fffffffLL) {  // 32-bit division: a 64-bit one costs ~10x the instructions, per row
+            unsigned rem = (unsigned)row;
+            for (int d = p.nlead - 1; d >= 0; d--) {
+                const unsigned ld = (unsigned)p.lead[d];
+                const unsigned q = rem / ld;
+                off += (long long)(rem - q * ld) * p.mstride[d];
+                rem = q;
+            }
+        } else {
+            long long rem = row;
+            for (int d = p.nlead - 1; d >= 0; d--) {
+                const long long idx = rem % p.lead[d];
+                rem /= p.lead[d];
+                off += idx * p.mstride[d];
+            }
         }
         m = p.mask + off;
     }

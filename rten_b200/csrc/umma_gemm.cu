@@ -154,6 +154,17 @@ __device__ __forceinline__ void bulk_wait_read(int n) {
     }
 }
 
+// Gelu (erf / tanh form) of four values as an out-of-line call: the specialised epilogue stays short straight-line
+// code (an unrolled polynomial per element would multiply its size and thrash the instruction cache), yet Gelu no
+// longer forces a launch into the generic epilogue.
+__device__ __noinline__ float4 act4(float4 x, int act) {
+    x.x = apply_act(x.x, act);
+    x.y = apply_act(x.y, act);
+    x.z = apply_act(x.z, act);
+    x.w = apply_act(x.w, act);
+    return x;
+}
+
 // Split-K hand-off of one epilogue group (128 threads): store this CTA's raw accumulator chunks, then count arrivals.
 // Returns true for the group of the CTA that arrived last: it owns the epilogue of (tile, group).
 // Workspace layout: [tile][sub][split][chunk][column j][row r] so that a warp's 32 rows are contiguous.
@@ -498,6 +509,14 @@ __device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* t
                                 x = x + b4[u];
                                 v[j + u] = __float_as_uint(do_relu ? fmaxf(x, 0.0f) : x);
                             }
+                            if (FAST == 2 && e.act > 1) {  // (own instantiation: a possible call changes the whole loop's code)
+                                const float4 t = act4(make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                  __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])), e.act);
+                                v[j] = __float_as_uint(t.x);
+                                v[j + 1] = __float_as_uint(t.y);
+                                v[j + 2] = __float_as_uint(t.z);
+                                v[j + 3] = __float_as_uint(t.w);
+                            }
                         }
                     } else if (e.za || e.zb || e.scale) {
                         // exact i32 arithmetic with wrap-around (unsigned ops), column vectors fetched 128 bits at a time
@@ -541,6 +560,14 @@ __device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* t
                                 } else {
                                     v[j + u] = c;
                                 }
+                            }
+                            if (FAST == 2 && e.scale && e.act > 1) {
+                                const float4 t = act4(make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                  __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])), e.act);
+                                v[j] = __float_as_uint(t.x);
+                                v[j + 1] = __float_as_uint(t.y);
+                                v[j + 2] = __float_as_uint(t.z);
+                                v[j + 3] = __float_as_uint(t.w);
                             }
                         }
                     }
@@ -1316,7 +1343,7 @@ static rten_status prepare_launch(rten_ctx* ctx, const GemmLaunch& L, Prepared& 
         ord.strides[2] = e.r_z0;
         ord.strides[3] = e.r_z1;
     }
-    q.res_tma = (q.tma_store && (L.kind == 0 || e.scale) && e.r && e.r_col == 1 && e.act <= 1 && (L.N % 32) == 0 &&
+    q.res_tma = (q.tma_store && (L.kind == 0 || e.scale) && e.r && e.r_col == 1 && (L.N % 32) == 0 &&
                  (e.bias_kind != 1 || (reinterpret_cast<uintptr_t>(e.bias) & 15) == 0) && tma_compatible(ord, 4, 4))
                     ? 1
                     : 0;
@@ -1379,7 +1406,7 @@ static void fill_launch_attrs(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr
     cfg.numAttrs = nattr;
 }
 
-// cls = kind * 2 + fast
+// cls = kind * 3 + epilogue variant
 static rten_status launch_single(rten_ctx* ctx, int cls, const PendingLaunch& pl) {
     const KParams& p = pl.p;
     const int grid = p.cta2 ? 2 * std::min(p.units_total, ctx->num_sms / 2) : std::min(p.units_total, ctx->num_sms);
@@ -1402,10 +1429,14 @@ static rten_status launch_single(rten_ctx* ctx, int cls, const PendingLaunch& pl
         case 1: e = launch(umma_gemm_kernel<0, 0, 1>); break;
         case 2: e = launch(umma_gemm_kernel<0, 1, 0>); break;
         case 3: e = launch(umma_gemm_kernel<0, 1, 1>); break;
-        case 4: e = launch(umma_gemm_kernel<1, 0, 0>); break;
-        case 5: e = launch(umma_gemm_kernel<1, 0, 1>); break;
-        case 6: e = launch(umma_gemm_kernel<1, 1, 0>); break;
-        default: e = launch(umma_gemm_kernel<1, 1, 1>); break;
+        case 4: e = launch(umma_gemm_kernel<0, 2, 0>); break;
+        case 5: e = launch(umma_gemm_kernel<0, 2, 1>); break;
+        case 6: e = launch(umma_gemm_kernel<1, 0, 0>); break;
+        case 7: e = launch(umma_gemm_kernel<1, 0, 1>); break;
+        case 8: e = launch(umma_gemm_kernel<1, 1, 0>); break;
+        case 9: e = launch(umma_gemm_kernel<1, 1, 1>); break;
+        case 10: e = launch(umma_gemm_kernel<1, 2, 0>); break;
+        default: e = launch(umma_gemm_kernel<1, 2, 1>); break;
     }
     if (e != cudaSuccess) return fail_cuda(ctx, e, "umma_gemm launch");
     e = cudaGetLastError();
@@ -1457,7 +1488,7 @@ rten_status seq_flush(rten_ctx* ctx) {
     switch (cls) {
         case 0: e = launch(umma_seq_kernel<0, 0>); break;
         case 1: e = launch(umma_seq_kernel<0, 1>); break;
-        case 2: e = launch(umma_seq_kernel<1, 0>); break;
+        case 3: e = launch(umma_seq_kernel<1, 0>); break;
         default: e = launch(umma_seq_kernel<1, 1>); break;
     }
     if (e != cudaSuccess) return fail_cuda(ctx, e, "umma_seq launch");
@@ -1540,15 +1571,16 @@ static rten_status launch_plan(rten_ctx* ctx, const GemmLaunch& L, const Prepare
     const EpilogueDesc& ee = L.epi;
     bool fastk = p.tma_store && (L.N % 32) == 0 && !ctx->trace && !getenv("RTEN_B200_NO_FAST");
     if (L.kind == 0)
-        fastk = fastk && ee.act <= 1 && ee.bias_kind != 2 && (ee.r == nullptr || p.res_tma) &&
+        fastk = fastk && ee.bias_kind != 2 && (ee.r == nullptr || p.res_tma) &&
                 (ee.bias_kind != 1 || (reinterpret_cast<uintptr_t>(ee.bias) & 15) == 0);
     else  // integer: column vectors must be 128-bit loadable, zero-point / scale vectors per column or scalar
-        fastk = fastk && ee.act <= 1 && ee.bias_kind != 2 && (ee.r == nullptr || p.res_tma) &&
+        fastk = fastk && ee.bias_kind != 2 && (ee.r == nullptr || p.res_tma) &&
                 (ee.bias_kind != 1 || (reinterpret_cast<uintptr_t>(ee.bias) & 15) == 0) &&
                 (!ee.za || (reinterpret_cast<uintptr_t>(ee.colsum) & 15) == 0) &&
                 (!ee.zb || ee.zb_len == 1 || (ee.zb_len == L.N && (reinterpret_cast<uintptr_t>(ee.zb) & 15) == 0)) &&
                 (!ee.scale || ee.scale_len == 1 || (ee.scale_len == L.N && (reinterpret_cast<uintptr_t>(ee.scale) & 15) == 0));
-    if (L.kind == 1 && !fastk) p.res_tma = 0;  // the generic integer epilogue reads the residual from global memory
+    // the generic epilogue takes a TMA-staged residual only on its register path (f32, act <= Relu)
+    if (!fastk && (L.kind == 1 || ee.act > 1)) p.res_tma = 0;
     PendingLaunch pend;
     pend.p = p;
     pend.maps[0] = map_a;
@@ -1556,14 +1588,15 @@ static rten_status launch_plan(rten_ctx* ctx, const GemmLaunch& L, const Prepare
     pend.maps[2] = map_d;
     pend.maps[3] = map_r;
     pend.smem_bytes = smem_bytes;
-    const int cls = L.kind * 2 + (fastk ? 1 : 0);
+    // kernel class = data kind x epilogue variant (0 generic, 1 specialised, 2 specialised + out-of-line Gelu)
+    const int cls = L.kind * 3 + (fastk ? (ee.act > 1 ? 2 : 1) : 0);
     // Opt-in (RTEN_B200_SEQ=1): inside graph capture consecutive launches are collected and run as ONE sequence kernel
     // (umma_seq_kernel).  Measured on B200 (tools/boundary_probe.py): a layer boundary inside the sequence kernel costs
     // ~2.3 us MORE than a programmatic-dependent-launch kernel boundary (drain + grid barrier + cold operand pipe are not
     // cheaper than what PDL already overlaps), so separate launches stay the default.
     const char* seq_env = getenv("RTEN_B200_SEQ");
     const bool seq_on = seq_env && atoi(seq_env) != 0;
-    if (seq_on && ctx->capturing && !p.cta2 && !ctx->trace && !no_defer) {
+    if (seq_on && ctx->capturing && !p.cta2 && !ctx->trace && !no_defer && cls % 3 != 2) {
         auto* q2 = pending_of(ctx);
         if (!q2->empty() && ctx->seq_class != cls) RTB_TRY(seq_flush(ctx));
         ctx->seq_class = cls;

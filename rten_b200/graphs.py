@@ -375,16 +375,25 @@ class BertRunner:
         x = self.ln.run(ctx, x, self.emb_g, self.emb_b)
         x = x.reshape(B * S, H)
         scale = 1.0 / math.sqrt(dh)
+        x3 = lambda t: t.view((B, S, H), (S * H, H, 1))
         for d in self.layers:
             q = self._linear(x, d["wq"], d["bq"])
             k = self._linear(x, d["wk"], d["bk"])
-            v = self._linear(x, d["wv"], d["bv"])
             heads = lambda t: t.view((B, nh, S, dh), (S * H, dh, H, 1))      # [B,S,nh,dh] memory seen as [B,nh,S,dh]
             kt = k.view((B, nh, dh, S), (S * H, dh, 1, H))                   # K^T view
+            if self.fuse:
+                # V is written TRANSPOSED per batch ([B, H, S] memory: the MatMul output is a strided view), so that
+                # probs.V finds its reduction dimension (the sequence) contiguous and needs no re-layout
+                vt = ctx.empty((B, H, S))
+                w, pk = d["wv"]
+                O.FusedMatMul(None).run(ctx, x3(x), w, d["bv"], packed_b=pk, out=vt.view((B, S, H), (H * S, 1, S)))
+                v_heads = vt.view((B, nh, S, dh), (H * S, dh * S, 1, S))
+            else:
+                v_heads = heads(self._linear(x, d["wv"], d["bv"]))
             scores = O.FusedMatMul(scale).run(ctx, heads(q), kt)             # [B,nh,S,S]
             probs = self.addsoftmax.run(ctx, scores, add_mask, in_place=True)
             att = ctx.empty((B * S, H))
-            O.MatMul().run(ctx, probs, heads(v), out=att.view((B, nh, S, dh), (S * H, dh, H, 1)))
+            O.MatMul().run(ctx, probs, v_heads, out=att.view((B, nh, S, dh), (S * H, dh, H, 1)))
             y = self._linear(att, d["wo"], d["bo"], residual=x)
             x = self.ln.run(ctx, y, d["ln1_g"], d["ln1_b"])
             h = self._linear(x, d["w1"], d["b1"], act=O.ACT_GELU)
