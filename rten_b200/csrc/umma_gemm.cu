@@ -272,6 +272,9 @@ __device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* t
             int tap, cb, ky, kx;
             p.d_c_blocks.divmod(kb0, tap, cb);
             p.d_kw.divmod(tap, ky, kx);
+            // programmatic dependent launch: the producer is the first to touch the predecessor's output; everything
+            // above (tile decode) ran while the predecessor grid was still draining
+            if (u == worker) asm volatile("griddepcontrol.wait;" ::: "memory");
             for (int kb = kb0; kb < kb1; kb += p.katoms) {
                 const int natoms = min(p.katoms, kb1 - kb);
                 mbar_wait(&empty_bar[stage], ((st.ring >> stage) & 1) ^ 1);
@@ -882,11 +885,21 @@ __device__ __forceinline__ uint32_t kernel_setup(const SmemLayout& L) {
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(L.res_bar + 8);
+    if (warp == 0 && !CTA2) {
+        // the producer initialises its own ring barriers and does NOT wait for the rest of the set-up (TMEM allocation,
+        // the CTA-wide barrier): it only arrives on a named barrier, so its first TMA is issued that much earlier
+        if (lane < 2 * MAX_STAGES) mbar_init(&L.full_bar[lane], 1);  // full_bar and empty_bar are contiguous
+        fence_mbar_init();
+        __syncwarp();
+        asm volatile("bar.arrive 15, %0;" ::"r"(NUM_THREADS) : "memory");
+        return 0;  // (the producer never touches TMEM)
+    }
     if (warp == 1) {
-        // 28 barriers, one per lane (a single thread initialising them serially sat on the start-up critical path):
-        // lanes 0-15 ring full / empty, 16-17 accumulator full, 18-19 accumulator empty, 20-27 residual
+        // one barrier per lane (a single thread initialising them serially sat on the start-up critical path):
+        // lanes 0-15 ring full / empty (pair mode only, else the producer's), 16-17 accumulator full, 18-19 accumulator
+        // empty, 20-27 residual
         if (lane < 2 * MAX_STAGES) {
-            mbar_init(&L.full_bar[lane], 1);  // full_bar and empty_bar are contiguous
+            if (CTA2) mbar_init(&L.full_bar[lane], 1);
         } else if (lane < 2 * MAX_STAGES + 2) {
             mbar_init(&L.tmem_full[lane - 2 * MAX_STAGES], 1);
         } else if (lane < 2 * MAX_STAGES + 4) {
@@ -909,7 +922,7 @@ __device__ __forceinline__ uint32_t kernel_setup(const SmemLayout& L) {
     if (CTA2)
         cluster_sync_all();  // the peer's barriers must be initialised before any remote arrive / multicast commit
     else
-        __syncthreads();
+        asm volatile("bar.sync 15, %0;" ::"r"(NUM_THREADS) : "memory");  // 11 warps wait, the producer warp only arrives
     tc_fence_after();
     return *tmem_ptr;
 }
@@ -952,7 +965,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps
     // the tail of the previous kernel in the stream; global memory is only touched after this point.
     if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[6144 + 1101] = clock64();  // set-up done
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (threadIdx.x >= 32) asm volatile("griddepcontrol.wait;" ::: "memory");  // (the producer warp waits after its tile decode)
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[6144 + 1102] = clock64();  // predecessor complete
     PipeState st;
@@ -994,7 +1007,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_seq_kernel(const __grid_c
         tma_prefetch_desc(&sp.maps[0][1]);
     }
     const uint32_t tmem_base = kernel_setup<0>(L);
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (threadIdx.x >= 32) asm volatile("griddepcontrol.wait;" ::: "memory");
     PipeState st;
     const int warp = threadIdx.x >> 5;
     for (int l = 0; l < sp.n; l++) {
