@@ -67,3 +67,29 @@ def test_product_never_imports_the_oracle():
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, re.M), f"{f} imports the oracle"
                 assert "librten_oracle" not in txt and "rten_oracle.c" not in txt, f"{f} links the oracle"
+
+
+def test_fastdiv_magic_numbers():
+    """The tile decode of umma_gemm.cu divides by launch-time constants with multiply-high + shift (FastDiv::set).
+    Same arithmetic restated here: exact for every 0 <= n < 2^31 -- checked on boundary values and random samples."""
+    import random
+
+    def magic(d):
+        if d == 1:
+            return 0, 0
+        lg = (d - 1).bit_length()  # ceil(log2(d))
+        p = 31 + lg
+        return ((1 << p) + d - 1) // d, p - 32
+
+    def fdiv(n, d, mul, shr):
+        return n if d == 1 else ((n * mul) >> 32) >> shr
+
+    rnd = random.Random(1234)
+    divisors = list(range(1, 300)) + [392, 784, 1568, 3136, 4095, 4096, 4097, 65535, 65536, 100352, 401408, (1 << 31) - 1]
+    for d in divisors:
+        mul, shr = magic(d)
+        assert mul < (1 << 32)
+        samples = [0, 1, d - 1, d, d + 1, 2 * d - 1, 2 * d, (1 << 31) - 1, (1 << 31) - d] + [rnd.randrange(1 << 31) for _ in range(200)]
+        for n in samples:
+            if 0 <= n < (1 << 31):
+                assert fdiv(n, d, mul, shr) == n // d, (n, d)
