@@ -1601,6 +1601,8 @@ rten_status rten_b200_dynamic_quantize_linear(rten_ctx* ctx, const rten_tensor* 
             const float one = 1.0f;
             RTB_CUDA(ctx, cudaMemcpyAsync(sv.data, &one, 4, cudaMemcpyHostToDevice, rtb::launch_stream(ctx)));
             RTB_CUDA(ctx, cudaMemsetAsync(zv.data, 0, 1, rtb::launch_stream(ctx)));
+        } else if (!nccl_comm && n <= 16384) {
+            st = launch_dql_small(ctx, (const float*)xc.data, (uint8_t*)yv.data, (int)n, (float*)sv.data, (uint8_t*)zv.data);
         } else {
             int* mm = nullptr;
             st = temp_alloc(ctx, 8, (void**)&mm);

@@ -589,6 +589,55 @@ dql_quantize_kernel(const float* __restrict__ x, uint8_t* __restrict__ y, long l
         y[j] = quant1(x[j], inv, zp);
 }
 
+// Small tensors (decode-time activations): range and quantisation in ONE single-CTA kernel instead of three launches.
+// min / max are order independent and the quantisation is the same per-element code, so results are identical.
+__global__ void __launch_bounds__(1024)
+dql_small_kernel(const float* __restrict__ x, uint8_t* __restrict__ y, int n, float* scale_out, uint8_t* zp_out) {
+    __shared__ float slo[32], shi[32];
+    __shared__ int mm[2];
+    float lo = __int_as_float(0x7f800000), hi = __int_as_float(0xff800000);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const float v = x[i];
+        lo = fminf(lo, v);
+        hi = fmaxf(hi, v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        slo[threadIdx.x >> 5] = lo;
+        shi[threadIdx.x >> 5] = hi;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < (int)(blockDim.x >> 5); k++) {
+            lo = fminf(lo, slo[k]);
+            hi = fmaxf(hi, shi[k]);
+        }
+        mm[0] = float_to_ordered(lo);
+        mm[1] = float_to_ordered(hi);
+    }
+    __syncthreads();
+    float scale, inv;
+    int zp;
+    dql_params(mm, scale, inv, zp);
+    if (threadIdx.x == 0) {
+        *scale_out = scale;
+        *zp_out = (uint8_t)zp;
+    }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) y[i] = quant1(x[i], inv, zp);
+}
+
+rten_status launch_dql_small(rten_ctx* ctx, const float* x, uint8_t* y, int n, float* scale_out, uint8_t* zp_out) {
+    dql_small_kernel<<<1, 1024, 0, launch_stream(ctx)>>>(x, y, n, scale_out, zp_out);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "dql launch");
+    count_launch(ctx);
+    return RTEN_OK;
+}
+
 rten_status launch_minmax(rten_ctx* ctx, const float* x, long long n, int* mm) {
     minmax_init_kernel<<<1, 1, 0, launch_stream(ctx)>>>(mm);
     count_launch(ctx);

@@ -62,4 +62,6 @@ rten_status launch_gather_rows(rten_ctx* ctx, const float* table, const int* idx
 rten_status launch_tf32x3_split(rten_ctx* ctx, const float* x, float* y, const long long dims[4], const long long strides[4],
                                 long long d0p, int role);
 
+rten_status launch_dql_small(rten_ctx* ctx, const float* x, uint8_t* y, int n, float* scale_out, uint8_t* zp_out);
+
 }  // namespace rtb

@@ -138,7 +138,8 @@ def check_layer_norm(rt, oracle):
 def check_dql(rt, oracle):
     ctx = rt.Context(0)
     r = oracle.XorShiftRng(1234)
-    for shape, lo, hi in [((5, 1000), -1.2, 2.8), ((4096, 768), -3, 3), ((3, 7, 11), 0.5, 2.0), ((17,), -5, -1), ((0, 3), 0, 1)]:
+    for shape, lo, hi in [((5, 1000), -1.2, 2.8), ((4096, 768), -3, 3), ((3, 7, 11), 0.5, 2.0), ((17,), -5, -1), ((0, 3), 0, 1),
+                          ((128, 128), -7, 0.25), ((16385,), -0.5, 9.0)]:  # single-kernel path up to 16384 elements, three kernels above
         x = r.uniform(shape, lo, hi)
         y, s, z = rt.DynamicQuantizeLinear().run(ctx, x)
         ey, es, ez = oracle.dynamic_quantize_linear(x)
