@@ -230,6 +230,10 @@ rten_status rten_b200_global_average_pool(rten_ctx* ctx, const rten_tensor* x, r
 /* Gather along axis 0 of a 2-D table with i32 indices (embedding lookups, src/ops/gather.rs). */
 rten_status rten_b200_gather_rows(rten_ctx* ctx, const rten_tensor* table, const rten_tensor* indices_i32,
                                   rten_tensor* out);
+/* table[indices[r], :] = updates[r, :] in place (ScatterElements / ScatterND restricted to whole rows of a 2-D f32 table,
+ * distinct indices): the KV-cache append when the write position is a device-resident value, so that a decode step is
+ * a fixed list of launches and can be replayed as a CUDA graph. */
+rten_status rten_b200_scatter_rows(rten_ctx* ctx, rten_tensor* table, const rten_tensor* indices, const rten_tensor* updates);
 
 #ifdef __cplusplus
 }

@@ -7,5 +7,5 @@ from . import _lib  # noqa: F401
 from .ops import (  # noqa: F401
     ACT_GELU, ACT_GELU_TANH, ACT_NONE, ACT_RELU, Add, AddSoftmax, Comm, Context, Conv, ConvInteger, ConvIntegerToFloat,
     DeviceTensor, DynamicQuantizeLinear, Erf, FusedMatMul, GatherRows, Gelu, Gemm, GlobalAveragePool,
-    LayerNormalization, MatMul, MatMulInteger, MatMulIntegerToFloat, MaxPool, Mul, OpError, Packed, Relu, Softmax, from_torch,
+    LayerNormalization, MatMul, MatMulInteger, MatMulIntegerToFloat, MaxPool, Mul, OpError, Packed, Relu, ScatterRows, Softmax, from_torch,
 )

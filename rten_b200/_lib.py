@@ -94,6 +94,7 @@ _SIGNATURES = {
     "rten_b200_max_pool": (C.c_int, [_vp, _TP, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), _TP]),
     "rten_b200_global_average_pool": (C.c_int, [_vp, _TP, _TP]),
     "rten_b200_gather_rows": (C.c_int, [_vp, _TP, _TP, _TP]),
+    "rten_b200_scatter_rows": (C.c_int, [_vp, _TP, _TP, _TP]),
 }
 
 _lib = None

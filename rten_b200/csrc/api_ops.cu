@@ -1720,4 +1720,25 @@ rten_status rten_b200_gather_rows(rten_ctx* ctx, const rten_tensor* table, const
     return sc.finish(st);
 }
 
+rten_status rten_b200_scatter_rows(rten_ctx* ctx, rten_tensor* table, const rten_tensor* idx, const rten_tensor* src) {
+    RTB_TRY(check_ctx(ctx));
+    if (!table || !idx || !src) return fail(ctx, RTEN_ERR_MISSING_INPUTS, "missing inputs");
+    if (table->dtype != RTEN_F32 || src->dtype != RTEN_F32 || idx->dtype != RTEN_I32)
+        return fail(ctx, RTEN_ERR_UNSUPPORTED_TYPE, "unsupported type");
+    if (table->ndim != 2 || src->ndim != 2 || idx->ndim != 1) return fail(ctx, RTEN_ERR_INVALID_VALUE, "scatter_rows expects 2-D table / updates and 1-D indices");
+    if (src->shape[0] != idx->shape[0] || src->shape[1] != table->shape[1])
+        return fail(ctx, RTEN_ERR_INCOMPATIBLE_SHAPES, "updates do not match the indices / table width");
+    if (table->device < 0) return fail(ctx, RTEN_ERR_UNSUPPORTED_OUTPUT, "the table must be device resident (updated in place)");
+    OpScope sc(ctx);
+    rten_tensor iv, ic, sv;
+    rten_status st = sc.in(idx, &iv);
+    if (st == RTEN_OK) st = sc.contiguous(&iv, &ic);
+    if (st == RTEN_OK) st = sc.in(src, &sv);
+    if (st == RTEN_OK)
+        st = launch_scatter_rows(ctx, (float*)table->data, (const int*)ic.data, (const float*)sv.data, iv.shape[0],
+                                 (int)table->shape[1], table->strides[0], table->strides[1], sv.strides[0], sv.strides[1],
+                                 table->shape[0]);
+    return sc.finish(st);
+}
+
 }  // extern "C"

@@ -954,6 +954,33 @@ rten_status launch_gather_rows(rten_ctx* ctx, const float* table, const int* idx
 }
 
 
+// ScatterElements-style row update (the KV-cache append of rten-generate when the write position lives on the device):
+// table[idx[r], c] = src[r, c].  Rows named by `idx` must be distinct.
+__global__ void __launch_bounds__(256)
+scatter_rows_kernel(float* __restrict__ table, const int* __restrict__ idx, const float* __restrict__ src, long long nidx,
+                    int width, long long t_rs, long long t_cs, long long s_rs, long long s_cs, long long rows) {
+    const long long total = nidx * width;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const long long r = i / width;
+        const int c = (int)(i % width);
+        long long id = idx[r];
+        if (id < 0) id += rows;
+        if (id >= 0 && id < rows) table[id * t_rs + c * t_cs] = src[r * s_rs + c * s_cs];
+    }
+}
+
+rten_status launch_scatter_rows(rten_ctx* ctx, float* table, const int* idx, const float* src, long long nidx, int width,
+                                long long t_rs, long long t_cs, long long s_rs, long long s_cs, long long rows) {
+    if (nidx * width == 0) return RTEN_OK;
+    scatter_rows_kernel<<<ew_grid(ctx, nidx * width), 256, 0, launch_stream(ctx)>>>(table, idx, src, nidx, width, t_rs, t_cs,
+                                                                             s_rs, s_cs, rows);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "scatter launch");
+    count_launch(ctx);
+    return RTEN_OK;
+}
+
 // =========================================================================================
 // 3xTF32 operand split (RTEN_F32_TF32X3): x = hi + lo with hi = x truncated to TF32 (low 13 mantissa bits cleared,
 // exactly what kind::tf32 reads) and lo = x - hi (exact in f32).  The tensor-core product over a reduction dimension

@@ -64,4 +64,7 @@ rten_status launch_tf32x3_split(rten_ctx* ctx, const float* x, float* y, const l
 
 rten_status launch_dql_small(rten_ctx* ctx, const float* x, uint8_t* y, int n, float* scale_out, uint8_t* zp_out);
 
+rten_status launch_scatter_rows(rten_ctx* ctx, float* table, const int* idx, const float* src, long long nidx, int width,
+                                long long t_rs, long long t_cs, long long s_rs, long long s_cs, long long rows);
+
 }  // namespace rtb

@@ -549,3 +549,80 @@ class GPT2Int8Runner:
         last = self.ln.run(ctx, last, *self.lnf)
         self.past = Ltot
         return self._linear(last, self.lm_head)
+
+    # ---- decode steps as ONE replayed CUDA graph ---------------------------------------------------------------
+    # Everything that depends on the position lives in small device buffers (token ids, position index, cache rows to
+    # write, additive mask); attention always runs over the whole cache length with the not-yet-written positions
+    # masked to -inf (their probabilities are exactly 0, so the result equals the exact-length computation), and the
+    # K / V append is a ScatterRows whose row indices are data.  A step is then a fixed launch list.
+    def build_decode_graph(self):
+        ctx, s, B, M = self.ctx, self.spec, self.B, self.max_seq
+        H, nh = s.hidden, s.heads
+        dh = H // nh
+        n_ids, n_k, n_v = B, B * nh, B * nh * dh
+        self._g_ints = ctx.to_device(np.zeros((n_ids + 1 + n_k + n_v,), np.int32))
+        self._g_ids = self._g_ints.view((B, 1), (1, 1), 0)
+        self._g_pos = self._g_ints.view((1,), (1,), n_ids)
+        self._g_kidx = self._g_ints.view((n_k,), (1,), n_ids + 1)
+        self._g_vidx = self._g_ints.view((n_v,), (1,), n_ids + 1 + n_k)
+        mask = np.full((1, 1, 1, M), -np.inf, np.float32)
+        mask[..., :self.past] = 0.0
+        self._g_mask = ctx.to_device(mask)
+        self._g_logits = ctx.empty((B, s.lm_head.wq.shape[1]))
+        self._scatter = O.ScatterRows()
+        self._host_ints = np.zeros((n_ids + 1 + n_k + n_v,), np.int32)
+        self._write_step_inputs(np.zeros((B, 1), np.int32))
+        self._decode_fixed()  # eager pass: buffer pool warm, plans measured
+        ctx.sync()
+        ctx.graph_begin()
+        self._decode_fixed()
+        self._graph = ctx.graph_end()
+
+    def _write_step_inputs(self, ids):
+        B, M, P = self.B, self.max_seq, self.past
+        nh, dh = self.spec.heads, self.spec.hidden // self.spec.heads
+        h = self._host_ints
+        h[:B] = np.asarray(ids, np.int32).reshape(B)
+        h[B] = P
+        h[B + 1:B + 1 + B * nh] = np.arange(B * nh, dtype=np.int32) * M + P          # rows of K viewed [B*nh*M, dh]
+        h[B + 1 + B * nh:] = np.arange(B * nh * dh, dtype=np.int32) * M + P          # rows of V^T viewed [B*nh*dh*M, 1]
+        self._g_ints.copy_from(h)
+        self._g_mask.view((1,), (1,), P).copy_from(np.zeros((1,), np.float32))      # position P becomes visible
+
+    def _decode_fixed(self):
+        ctx, s, B, M = self.ctx, self.spec, self.B, self.max_seq
+        H, nh = s.hidden, s.heads
+        dh = H // nh
+        x = self.gather.run(ctx, self.wte, self._g_ids)                              # [B,1,H]
+        x = self.add.run(ctx, x, self.gather.run(ctx, self.wpe, self._g_pos))        # + wpe[P]
+        x = x.reshape(B, H)
+        scale = 1.0 / math.sqrt(dh)
+        for d in self.layers:
+            h = self.ln.run(ctx, x, *d["ln1"])
+            qkv = self._linear(h, d["attn"])                                          # [B, 3H]
+            q = qkv.view((B, nh, 1, dh), (3 * H, dh, 3 * H, 1), 0)
+            knew, vnew = ctx.empty((B, nh, dh)), ctx.empty((B, nh, dh))
+            knew.assign(qkv.view((B, nh, dh), (3 * H, dh, 1), H))
+            vnew.assign(qkv.view((B, nh, dh), (3 * H, dh, 1), 2 * H))
+            self._scatter.run(ctx, d["k"].view((B * nh * M, dh), (dh, 1)), self._g_kidx, knew.reshape(B * nh, dh))
+            self._scatter.run(ctx, d["vt"].view((B * nh * dh * M, 1), (1, 1)), self._g_vidx, vnew.reshape(B * nh * dh, 1))
+            kt = d["k"].view((B, nh, dh, M), (nh * M * dh, M * dh, 1, dh))
+            scores = O.FusedMatMul(scale).run(ctx, q, kt)                             # [B,nh,1,M]
+            probs = self.addsoftmax.run(ctx, scores, self._g_mask, in_place=True)
+            v = d["vt"].view((B, nh, M, dh), (nh * dh * M, dh * M, 1, M))
+            att = ctx.empty((B, H))
+            O.MatMul().run(ctx, probs, v, out=att.view((B, nh, 1, dh), (H, dh, H, 1)))
+            x = self._linear(att, d["proj"], residual=x)
+            h = self.ln.run(ctx, x, *d["ln2"])
+            f = self._linear(h, d["fc"], act=O.ACT_GELU_TANH)
+            x = self._linear(f, d["fc2"], residual=x)
+        last = self.ln.run(ctx, x, *self.lnf)
+        self._g_logits.assign(self._linear(last, self.lm_head))
+
+    def decode_step(self, ids: np.ndarray) -> O.DeviceTensor:
+        """One token per sequence through the captured graph (build_decode_graph() first).  -> logits [B, vocab]."""
+        assert self.past + 1 <= self.max_seq
+        self._write_step_inputs(ids)
+        self._graph.launch()
+        self.past += 1
+        return self._g_logits

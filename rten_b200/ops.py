@@ -613,6 +613,16 @@ class GlobalAveragePool:
         return A.wrap(o, out)
 
 
+class ScatterRows:
+    """table[indices[r], :] = updates[r, :] in place (2-D f32 table, distinct i32 indices)."""
+
+    def run(self, ctx, table: "DeviceTensor", indices, updates):
+        A = _Args(ctx)
+        t = table.desc()
+        ctx.check(ctx.lib.rten_b200_scatter_rows(ctx.handle, C.byref(t), A.t(indices), A.t(updates)))
+        return table
+
+
 class GatherRows:
     """Gather(axis=0) of a 2-D table with i32 indices (embedding lookup; src/ops/gather.rs)."""
 

@@ -151,6 +151,14 @@ def check_dql(rt, oracle):
 
 def check_glue(rt, oracle):
     ctx = rt.Context(0)
+    rr = oracle.XorShiftRng(55)
+    table, upd = rr.uniform((40, 12)), rr.uniform((5, 12))
+    idx = np.array([3, 39, 0, 17, -2], np.int32)
+    td = ctx.to_device(table)
+    rt.ScatterRows().run(ctx, td, idx, upd)
+    want = table.copy()
+    want[idx] = upd
+    assert_bit_exact(td.numpy(), want, "ScatterRows")
     r = oracle.XorShiftRng(1234)
     a, b = r.uniform((2, 3, 4, 5)), r.uniform((2, 3, 4, 5))
     assert_bit_exact(rt.Add().run(ctx, a, b).numpy(), a + b, "Add")
@@ -684,7 +692,16 @@ def check_gpt2_int8_kvcache(rt, oracle):
         assert a.shape == r.shape and rel <= 2e-2, f"GPT-2 int8 step {i}: rel err {rel:.3e}"
         assert (a.argmax(1) == r.argmax(1)).all(), f"GPT-2 int8 step {i}: greedy token differs"
         worst = max(worst, rel)
-    return f"prefill {T0} + 3 decode steps, worst rel err {worst:.2e}"
+    # decode steps replayed as ONE CUDA graph (fixed-length masked attention, ScatterRows cache append)
+    runner = graphs.GPT2Int8Runner(ctx, spec, B, 64, fuse=True)
+    g_out = [runner.forward(steps[0]).numpy()]
+    runner.build_decode_graph()
+    g_out += [runner.decode_step(st).numpy().copy() for st in steps[1:]]
+    for i, (a, r) in enumerate(zip(g_out, ref)):
+        rel = float(np.abs(a - r).max() / np.abs(r).max())
+        assert rel <= 2e-2 and (a.argmax(1) == r.argmax(1)).all(), f"GPT-2 int8 graph decode step {i}: rel err {rel:.3e}"
+        worst = max(worst, rel)
+    return f"prefill {T0} + 3 decode steps (eager and graph-replayed), worst rel err {worst:.2e}"
 
 
 def check_tf32x3(rt, oracle):
