@@ -154,8 +154,9 @@ rten_status rten_b200_matmul_integer(rten_ctx* ctx, const rten_tensor* a, const 
  * unfused operators.  Requires `scale`. */
 rten_status rten_b200_matmul_integer_ex(rten_ctx* ctx, const rten_tensor* a, const rten_tensor* b, const rten_packed* packed_b,
                                         const rten_tensor* a_zero_point, const rten_tensor* b_zero_point,
-                                        const rten_tensor* scale, const rten_tensor* bias, const rten_tensor* residual,
-                                        int activation, rten_tensor* out);
+                                        const rten_tensor* scale, const rten_tensor* scale_b_or_null /* scalar: effective scale = scale_b * scale */,
+                                        const rten_tensor* bias, const rten_tensor* residual, int activation,
+                                        rten_tensor* out);
 
 /* Conv (src/ops/conv.rs:124-419).  x NCHW (or NCW), w OIHW, bias [O].  pads = {top,left,bottom,right};
  * auto_pad_same != 0 => `Padding::Same` (pads ignored).  n_spatial = 1 or 2 gives the expected
@@ -182,13 +183,15 @@ rten_status rten_b200_conv_integer(rten_ctx* ctx, const rten_tensor* x, const rt
                                    const rten_packed* packed_w_or_null, const rten_tensor* x_zero_point_or_null,
                                    const rten_tensor* w_zero_point_or_null, const rten_tensor* scale_or_null,
                                    const rten_conv_params* p, rten_tensor* out);
-/* ConvIntegerToFloat followed by the graph's Add(bias [O]), Add(residual, same shape as the output) and Relu
- * (activation 0 / 1), executed in the kernel epilogue as the same sequence of exactly rounded f32 operations
- * (mul, add, add, max) -- bit-identical to running the three operators separately.  Requires `scale`. */
+/* ConvIntegerToFloat with the graph nodes around it folded into the kernel epilogue, each as the same exactly rounded
+ * f32 operation the separate operator would perform (bit-identical results): the Mul that forms the scale
+ * (`scale_b_or_null`: scalar, effective scale = scale_b * scale), then Add(bias [O]), Add(residual, same shape as the
+ * output) and Relu (activation 0 / 1).  Requires `scale`. */
 rten_status rten_b200_conv_integer_ex(rten_ctx* ctx, const rten_tensor* x, const rten_tensor* w, const rten_packed* packed_w,
                                       const rten_tensor* x_zero_point, const rten_tensor* w_zero_point,
-                                      const rten_tensor* scale, const rten_conv_params* params, const rten_tensor* bias,
-                                      const rten_tensor* residual, int activation, rten_tensor* out);
+                                      const rten_tensor* scale, const rten_tensor* scale_b_or_null,
+                                      const rten_conv_params* params, const rten_tensor* bias, const rten_tensor* residual,
+                                      int activation, rten_tensor* out);
 
 /* Softmax (src/ops/norm.rs:825-899) and AddSoftmax (src/ops/attention.rs:30-165) when mask != NULL
  * (mask broadcast to x, added lane-wise before the softmax over `axis`; AddSoftmax uses axis -1).

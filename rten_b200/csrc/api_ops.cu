@@ -348,11 +348,16 @@ rten_status matmul_core(OpScope& sc, MatMulArgs& A, rten_tensor* out) {
                 rten_tensor z;
                 RTB_TRY(sc.in(A.a_zp, &z));
                 const int len = z.ndim == 0 ? 1 : (int)z.shape[0];
-                int32_t* za = nullptr;
-                RTB_TRY(temp_alloc(ctx, (size_t)len * 4, (void**)&za));
-                RTB_TRY(launch_zp_to_i32(ctx, z.data, z.dtype == RTEN_I8, len, z.ndim == 0 ? 0 : z.strides[0], za));
-                L.epi.za = za;
-                L.epi.za_len = len;
+                if (len == 1) {  // scalar (DynamicQuantizeLinear's zero point): read in place by the epilogue
+                    L.epi.za8 = (const uint8_t*)z.data;
+                    L.epi.za8_signed = z.dtype == RTEN_I8;
+                } else {
+                    int32_t* za = nullptr;
+                    RTB_TRY(temp_alloc(ctx, (size_t)len * 4, (void**)&za));
+                    RTB_TRY(launch_zp_to_i32(ctx, z.data, z.dtype == RTEN_I8, len, z.ndim == 0 ? 0 : z.strides[0], za));
+                    L.epi.za = za;
+                    L.epi.za_len = len;
+                }
                 if (A.pb && A.pb->colsum) {
                     L.epi.colsum = A.pb->colsum;
                 } else {
@@ -443,6 +448,7 @@ struct ConvArgs {
     const rten_tensor* x_zp = nullptr;
     const rten_tensor* w_zp = nullptr;
     const rten_tensor* scale = nullptr;
+    const rten_tensor* scale_b = nullptr;  // optional second scalar factor (x_scale of a DynamicQuantizeLinear)
 };
 
 rten_status pack_conv_weight(rten_ctx* ctx, const rten_tensor* w, int esize, void* dst) {
@@ -559,7 +565,8 @@ rten_status conv_core(OpScope& sc, ConvArgs& A, rten_tensor* out) {
     }
 
     // ---- integer zero points (x_zp scalar, w_zp per output channel)
-    const int32_t* za = nullptr;   // x zero point (GEMM A operand = activations)
+    const int32_t* za = nullptr;   // x zero point (GEMM A operand = activations), as i32 ...
+    const uint8_t* za8 = nullptr;  // ... or the 8-bit scalar as it is
     const int32_t* zb = nullptr;   // w zero points per column
     int zb_len = 0;
     int pad_value = 0;
@@ -573,10 +580,7 @@ rten_status conv_core(OpScope& sc, ConvArgs& A, rten_tensor* out) {
             RTB_TRY(sc.in(A.x_zp, &z));
             if (numel(&z) != 1) return fail(ctx, RTEN_ERR_INVALID_VALUE, "input zero point must be a scalar");
             if (z.dtype != x.dtype) return fail(ctx, RTEN_ERR_CAST_FAILED, "zero point type does not match its tensor");
-            int32_t* p = nullptr;
-            RTB_TRY(temp_alloc(ctx, 4, (void**)&p));
-            RTB_TRY(launch_zp_to_i32(ctx, z.data, x_signed, 1, 0, p));
-            za = p;
+            za8 = (const uint8_t*)z.data;  // scalar: read in place by the epilogue
             if (!w_colsum) {
                 int32_t* cs = nullptr;
                 RTB_TRY(temp_alloc(ctx, (size_t)O * 4, (void**)&cs));
@@ -595,12 +599,18 @@ rten_status conv_core(OpScope& sc, ConvArgs& A, rten_tensor* out) {
             zb = p;
         }
     }
-    const float* scale_p = nullptr;
+    const float *scale_p = nullptr, *scale2_p = nullptr;
     if (A.scale) {
         rten_tensor s;
         RTB_TRY(sc.in(A.scale, &s));
         if (numel(&s) != 1 || s.ndim > 1) return fail(ctx, RTEN_ERR_INVALID_VALUE, "scale should be a scalar");
         scale_p = (const float*)s.data;
+    }
+    if (A.scale_b) {
+        rten_tensor s;
+        RTB_TRY(sc.in(A.scale_b, &s));
+        if (s.dtype != RTEN_F32 || numel(&s) != 1) return fail(ctx, RTEN_ERR_INVALID_VALUE, "scale should be a scalar");
+        scale2_p = (const float*)s.data;
     }
     rten_tensor res_v;
     if (A.residual) {
@@ -764,6 +774,9 @@ rten_status conv_core(OpScope& sc, ConvArgs& A, rten_tensor* out) {
         if (A.kind == 1) {
             e.za = za;
             e.za_len = za ? 1 : 0;
+            e.za8 = za8;
+            e.za8_signed = x_signed;
+            e.scale2 = scale2_p;
             e.colsum = w_colsum ? w_colsum + g * Og : nullptr;
             e.zb = zb ? (zb_len == 1 ? zb : zb + g * Og) : nullptr;
             e.zb_len = zb ? (zb_len == 1 ? 1 : (int)Og) : 0;
@@ -1141,16 +1154,16 @@ rten_status rten_b200_matmul(rten_ctx* ctx, const rten_tensor* a, const rten_ten
 rten_status rten_b200_matmul_integer(rten_ctx* ctx, const rten_tensor* a, const rten_tensor* b, const rten_packed* pb,
                                      const rten_tensor* a_zp, const rten_tensor* b_zp, const rten_tensor* scale,
                                      rten_tensor* out) {
-    return rten_b200_matmul_integer_ex(ctx, a, b, pb, a_zp, b_zp, scale, nullptr, nullptr, 0, out);
+    return rten_b200_matmul_integer_ex(ctx, a, b, pb, a_zp, b_zp, scale, nullptr, nullptr, nullptr, 0, out);
 }
 
 rten_status rten_b200_matmul_integer_ex(rten_ctx* ctx, const rten_tensor* a, const rten_tensor* b, const rten_packed* pb,
                                         const rten_tensor* a_zp, const rten_tensor* b_zp, const rten_tensor* scale,
-                                        const rten_tensor* bias, const rten_tensor* residual, int activation,
-                                        rten_tensor* out) {
+                                        const rten_tensor* scale_b, const rten_tensor* bias, const rten_tensor* residual,
+                                        int activation, rten_tensor* out) {
     RTB_TRY(check_ctx(ctx));
     if (!a || !b || !out) return fail(ctx, RTEN_ERR_MISSING_INPUTS, "missing inputs");
-    if ((bias || residual || activation) && !scale)
+    if ((bias || residual || activation || scale_b) && !scale)
         return fail(ctx, RTEN_ERR_INVALID_VALUE, "bias / residual / activation follow the float conversion: a scale is required");
     if (activation < 0 || activation > 3) return fail(ctx, RTEN_ERR_INVALID_VALUE, "unknown activation");
     auto is8 = [](int dt) { return dt == RTEN_U8 || dt == RTEN_I8; };
@@ -1195,7 +1208,15 @@ rten_status rten_b200_matmul_integer_ex(rten_ctx* ctx, const rten_tensor* a, con
             A.epi.scale_len = (int)len;
         }
     }
-    rten_tensor biasv, biasc;
+    rten_tensor biasv, biasc, s2v;
+    if (st == RTEN_OK && scale_b) {
+        if (scale_b->dtype != RTEN_F32 || numel(scale_b) != 1) {
+            st = fail(ctx, RTEN_ERR_INVALID_VALUE, "the second scale factor must be a float scalar");
+        } else {
+            st = sc.in(scale_b, &s2v);
+            A.epi.scale2 = (const float*)s2v.data;
+        }
+    }
     if (st == RTEN_OK && bias) {
         if (bias->dtype != RTEN_F32 || bias->ndim != 1) {
             st = fail(ctx, RTEN_ERR_CAST_FAILED, "bias must be a float vector");
@@ -1242,19 +1263,19 @@ rten_status rten_b200_conv2d(rten_ctx* ctx, const rten_tensor* x, const rten_ten
 rten_status rten_b200_conv_integer(rten_ctx* ctx, const rten_tensor* x, const rten_tensor* w, const rten_packed* pw,
                                    const rten_tensor* x_zp, const rten_tensor* w_zp, const rten_tensor* scale,
                                    const rten_conv_params* p, rten_tensor* out) {
-    return rten_b200_conv_integer_ex(ctx, x, w, pw, x_zp, w_zp, scale, p, nullptr, nullptr, 0, out);
+    return rten_b200_conv_integer_ex(ctx, x, w, pw, x_zp, w_zp, scale, nullptr, p, nullptr, nullptr, 0, out);
 }
 
 rten_status rten_b200_conv_integer_ex(rten_ctx* ctx, const rten_tensor* x, const rten_tensor* w, const rten_packed* pw,
                                       const rten_tensor* x_zp, const rten_tensor* w_zp, const rten_tensor* scale,
-                                      const rten_conv_params* p, const rten_tensor* bias, const rten_tensor* residual,
-                                      int activation, rten_tensor* out) {
+                                      const rten_tensor* scale_b, const rten_conv_params* p, const rten_tensor* bias,
+                                      const rten_tensor* residual, int activation, rten_tensor* out) {
     RTB_TRY(check_ctx(ctx));
     if (!x || !w || !p || !out) return fail(ctx, RTEN_ERR_MISSING_INPUTS, "missing inputs");
     auto is8 = [](int dt) { return dt == RTEN_U8 || dt == RTEN_I8; };
     if (!is8(x->dtype) || !is8(w->dtype)) return fail(ctx, RTEN_ERR_UNSUPPORTED_TYPE, "unsupported type");
     if (scale && scale->dtype != RTEN_F32) return fail(ctx, RTEN_ERR_CAST_FAILED, "scale must be float");
-    if ((bias || residual || activation) && !scale)
+    if ((bias || residual || activation || scale_b) && !scale)
         return fail(ctx, RTEN_ERR_INVALID_VALUE, "bias / residual / activation follow the float conversion: a scale is required");
     if ((bias && bias->dtype != RTEN_F32) || (residual && residual->dtype != RTEN_F32))
         return fail(ctx, RTEN_ERR_UNSUPPORTED_TYPE, "unsupported type");
@@ -1269,6 +1290,7 @@ rten_status rten_b200_conv_integer_ex(rten_ctx* ctx, const rten_tensor* x, const
     A.x_zp = x_zp;
     A.w_zp = w_zp;
     A.scale = scale;
+    A.scale_b = scale_b;
     A.bias = bias;
     A.residual = residual;
     A.act = activation;

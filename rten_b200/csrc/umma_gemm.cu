@@ -431,7 +431,7 @@ __device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* t
                 const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_STRIDE + sub * p.bn;
                 // integer zero-point terms of this thread's row:  C = acc - za*colsum[n] - zb[n]*(rowsum - K*za)
                 unsigned za_v = 0, t_m = 0;
-                if (KIND == 1 && (e.za || e.zb)) {
+                if (KIND == 1 && (e.za || e.za8 || e.zb)) {
                     int m_idx;
                     bool row_ok;
                     if (p.conv) {
@@ -447,6 +447,7 @@ __device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* t
                     }
                     if (row_ok) {
                         if (e.za) za_v = (unsigned)e.za[m_idx % e.za_len];
+                        else if (e.za8) za_v = (unsigned)(e.za8_signed ? (int)(int8_t)__ldg(e.za8) : (int)__ldg(e.za8));
                         if (e.zb) t_m = (unsigned)e.rowsum[m_idx] - (unsigned)p.K * za_v;
                     }
                 }
@@ -521,13 +522,13 @@ __device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* t
                                 v[j + 3] = __float_as_uint(t.w);
                             }
                         }
-                    } else if (e.za || e.zb || e.scale) {
+                    } else if (e.za || e.za8 || e.zb || e.scale) {
                         // exact i32 arithmetic with wrap-around (unsigned ops), column vectors fetched 128 bits at a time
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
                             uint4 cs = make_uint4(0u, 0u, 0u, 0u), zb4 = make_uint4(0u, 0u, 0u, 0u);
                             float4 sc = make_float4(1.f, 1.f, 1.f, 1.f);
-                            if (e.za) cs = __ldg(reinterpret_cast<const uint4*>(e.colsum + nbase + j));
+                            if (e.za || e.za8) cs = __ldg(reinterpret_cast<const uint4*>(e.colsum + nbase + j));
                             if (e.zb) {
                                 if (e.zb_len == 1) {
                                     const unsigned z = (unsigned)__ldg(e.zb);
@@ -542,6 +543,10 @@ __device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* t
                                     sc = make_float4(z, z, z, z);
                                 } else {
                                     sc = __ldg(reinterpret_cast<const float4*>(e.scale + nbase + j));
+                                }
+                                if (e.scale2) {
+                                    const float s2 = __ldg(e.scale2);
+                                    sc = make_float4(__fmul_rn(s2, sc.x), __fmul_rn(s2, sc.y), __fmul_rn(s2, sc.z), __fmul_rn(s2, sc.w));
                                 }
                             }
                             float4 rr = make_float4(0.f, 0.f, 0.f, 0.f), bb = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -672,6 +677,7 @@ __device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* t
                     if (e.bias_kind == 2) row_bias = e.bias[m_idx];
                 } else {
                     if (e.za) za_v = e.za[m_idx % e.za_len];
+                    else if (e.za8) za_v = e.za8_signed ? (int)(int8_t)__ldg(e.za8) : (int)__ldg(e.za8);
                     if (e.zb) rs_v = e.rowsum[m_idx];
                 }
             }
@@ -748,7 +754,7 @@ __device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* t
                 //      math) runs as a ROLLED loop over the staged row: keeps the unrolled code small enough for
                 //      the instruction cache.
                 const bool full = nbase + 32 <= p.N;
-                bool fast = (KIND == 0) ? (e.act <= 1 && full) : !(e.za || e.zb || e.scale);  // raw i32: nothing to do
+                bool fast = (KIND == 0) ? (e.act <= 1 && full) : !(e.za || e.za8 || e.zb || e.scale);  // raw i32: nothing to do
                 if (fast && e.r && !p.res_tma)
                     fast = e.r_col == 1 && ((reinterpret_cast<uintptr_t>(e.r + r_off + nbase) & 15) == 0);
                 if (fast && e.bias_kind == 1) fast = (reinterpret_cast<uintptr_t>(e.bias + nbase) & 15) == 0;
@@ -800,14 +806,16 @@ __device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* t
                         } else {
                             // exact i32 arithmetic with wrap-around (unsigned ops)
                             unsigned c = *sp;
-                            if (e.za) c -= (unsigned)za_v * (unsigned)e.colsum[n];
+                            if (e.za || e.za8) c -= (unsigned)za_v * (unsigned)e.colsum[n];
                             if (e.zb) {
                                 const unsigned zbv = (unsigned)e.zb[n % e.zb_len];
                                 c -= zbv * (unsigned)rs_v;
-                                if (e.za) c += (unsigned)p.K * (unsigned)za_v * zbv;
+                                if (e.za || e.za8) c += (unsigned)p.K * (unsigned)za_v * zbv;
                             }
                             if (e.scale) {
-                                float x = __fmul_rn(__int2float_rn((int)c), e.scale[n % e.scale_len]);
+                                float sv = e.scale[n % e.scale_len];
+                                if (e.scale2) sv = __fmul_rn(__ldg(e.scale2), sv);
+                                float x = __fmul_rn(__int2float_rn((int)c), sv);
                                 if (e.bias_kind == 1) x = __fadd_rn(x, e.bias[n]);
                                 if (e.r) x = __fadd_rn(x, __ldcg(e.r + r_off + (long long)n * e.r_col));
                                 *sp = __float_as_uint(apply_act(x, e.act));
@@ -1589,7 +1597,7 @@ static rten_status launch_plan(rten_ctx* ctx, const GemmLaunch& L, const Prepare
     else  // integer: column vectors must be 128-bit loadable, zero-point / scale vectors per column or scalar
         fastk = fastk && ee.bias_kind != 2 && (ee.r == nullptr || p.res_tma) &&
                 (ee.bias_kind != 1 || (reinterpret_cast<uintptr_t>(ee.bias) & 15) == 0) &&
-                (!ee.za || (reinterpret_cast<uintptr_t>(ee.colsum) & 15) == 0) &&
+                (!(ee.za || ee.za8) || (reinterpret_cast<uintptr_t>(ee.colsum) & 15) == 0) &&
                 (!ee.zb || ee.zb_len == 1 || (ee.zb_len == L.N && (reinterpret_cast<uintptr_t>(ee.zb) & 15) == 0)) &&
                 (!ee.scale || ee.scale_len == 1 || (ee.scale_len == L.N && (reinterpret_cast<uintptr_t>(ee.scale) & 15) == 0));
     // the generic epilogue takes a TMA-staged residual only on its register path (f32, act <= Relu)
@@ -1625,7 +1633,7 @@ static rten_status launch_plan(rten_ctx* ctx, const GemmLaunch& L, const Prepare
 static std::vector<long long> tune_key(const GemmLaunch& L, const Prepared& q) {
     const EpilogueDesc& e = L.epi;
     std::vector<long long> k = {L.kind, L.conv, L.M, L.N, L.K, L.z0, L.z1, q.tma_store, q.res_tma, e.act, e.bias_kind,
-                                e.r != nullptr, e.za != nullptr, e.zb != nullptr, e.scale != nullptr,
+                                e.r != nullptr, (e.za != nullptr || e.za8 != nullptr), e.zb != nullptr, e.scale != nullptr,
                                 L.a.strides[1], L.b.strides[1]};
     if (L.conv) {
         const ConvGeom& g = L.g;

@@ -38,12 +38,17 @@ struct EpilogueDesc {
     // integer path: C = acc - za[m % za_len]*colsum[n] - zb[n % zb_len]*rowsum[m] + K*za*zb
     const int32_t* za = nullptr;
     int za_len = 0;
+    // ... or ONE 8-bit zero point read in place (a DynamicQuantizeLinear output used as it is: no conversion launch)
+    const uint8_t* za8 = nullptr;
+    int za8_signed = 0;
     const int32_t* zb = nullptr;
     int zb_len = 0;
     const int32_t* rowsum = nullptr;  // sum_k A[m,k]   (needed iff zb != null)
     const int32_t* colsum = nullptr;  // sum_k B[n,k]   (needed iff za != null)
     const float* scale = nullptr;     // cast_scale fused: f32 out = f32(C) * scale[n % scale_len]
     int scale_len = 0;
+    const float* scale2 = nullptr;    // optional scalar factor: the effective scale is fmul(scale2[0], scale[n]) -- the
+                                      // graph's Mul(x_scale, w_scale) node folded into the epilogue, same rounding
 };
 
 struct ConvGeom {

@@ -229,11 +229,16 @@ class ResNet50Int8Runner:
     def _conv(self, c: QConvSpec, x, relu: bool, residual=None):
         op, w, b, pk, ws, b4, wz = self._convs[id(c)]
         ctx = self.ctx
+        if self.fuse:
+            # one DynamicQuantizeLinear per distinct input (a block's conv1 and its downsample conv share theirs), and
+            # the Mul(x_scale, w_scale) node is folded into the epilogue
+            if self._dql_of is not x:
+                self._dql_of, self._dql_val = x, self.dql.run(ctx, x, self.comm)
+            xq, xs, xz = self._dql_val
+            op.activation = O.ACT_RELU if relu else O.ACT_NONE
+            return op.run(ctx, xq, w, xz, wz, ws, packed_w=pk, bias=b, residual=residual, scale_b=xs)
         xq, xs, xz = self.dql.run(ctx, x, self.comm)
         scale = self.mul.run(ctx, xs, ws)
-        if self.fuse:
-            op.activation = O.ACT_RELU if relu else O.ACT_NONE
-            return op.run(ctx, xq, w, xz, wz, scale, packed_w=pk, bias=b, residual=residual)
         op.activation = O.ACT_NONE
         y = op.run(ctx, xq, w, xz, wz, scale, packed_w=pk)
         y = self.add.run(ctx, y, b4)
@@ -247,6 +252,7 @@ class ResNet50Int8Runner:
         """-> logits [B,1000]; with `return_features` also the pooled [B,2048] features, the last tensor produced by
         exact arithmetic only (the f32 classifier runs on the TF32 tensor-core path)."""
         s, ctx = self.spec, self.ctx
+        self._dql_of = self._dql_val = None
         y = self._conv(s.stem, x, True)
         y = self.maxpool.run(ctx, y)
         for b in s.blocks:
@@ -254,6 +260,7 @@ class ResNet50Int8Runner:
             t = self._conv(b.c1, y, True)
             t = self._conv(b.c2, t, True)
             y = self._conv(b.c3, t, True, residual=ident)
+        self._dql_of = self._dql_val = None
         p = self.gap.run(ctx, y)
         p = p.reshape(p.shape[0], p.shape[1])
         logits = self.fc.run(ctx, p, self.fc_w, self.fc_b)
@@ -498,9 +505,9 @@ class GPT2Int8Runner:
         w, pk, ws, b = lin
         ctx = self.ctx
         xq, xs, xz = self.dql.run(ctx, x)
+        if self.fuse:  # Mul(x_scale, w_scale), Add(bias), Add(residual) and Gelu folded into the epilogue
+            return O.MatMulIntegerToFloat(act).run(ctx, xq, w, xz, None, ws, packed_b=pk, bias=b, residual=residual, scale_b=xs)
         scale = self.mul.run(ctx, xs, ws)
-        if self.fuse:
-            return O.MatMulIntegerToFloat(act).run(ctx, xq, w, xz, None, scale, packed_b=pk, bias=b, residual=residual)
         y = O.MatMulIntegerToFloat().run(ctx, xq, w, xz, None, scale, packed_b=pk)
         if b is not None:
             y = self.add.run(ctx, y, b)

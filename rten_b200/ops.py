@@ -365,7 +365,7 @@ class MatMulIntegerToFloat(MatMul):
         self.activation = activation
 
     def run(self, ctx, a, b, a_zero_point, b_zero_point, scale, packed_b: Optional[Packed] = None, out=None, bias=None,
-            residual=None):
+            residual=None, scale_b=None):
         """`bias` / `residual` / `self.activation`: the Add / Add / Gelu nodes that follow the operator in a quantised
         transformer, folded into the epilogue with the same f32 roundings (rten_b200_matmul_integer_ex)."""
         if scale is None:
@@ -373,7 +373,7 @@ class MatMulIntegerToFloat(MatMul):
         A = _Args(ctx)
         o = A.out(out)
         ctx.check(ctx.lib.rten_b200_matmul_integer_ex(ctx.handle, A.t(a), A.t(b), _ph(packed_b), A.t(a_zero_point),
-                                                      A.t(b_zero_point), A.t(scale), A.t(bias), A.t(residual),
+                                                      A.t(b_zero_point), A.t(scale), A.t(scale_b), A.t(bias), A.t(residual),
                                                       self.activation, C.byref(o)))
         return A.wrap(o, out)
 
@@ -442,7 +442,7 @@ class ConvIntegerToFloat(Conv):
     """src/ops/conv.rs:535-587"""
 
     def run(self, ctx, x, w, x_zero_point, w_zero_point, scale, packed_w: Optional[Packed] = None, out=None,
-            bias=None, residual=None):
+            bias=None, residual=None, scale_b=None):
         """`bias` / `residual` / `self.activation` = the Add(bias), Add(identity), Relu nodes that follow the operator in
         a quantised ResNet, executed in the epilogue with the same f32 roundings (rten_b200_conv_integer_ex)."""
         if scale is None:
@@ -451,8 +451,8 @@ class ConvIntegerToFloat(Conv):
         o = A.out(out)
         p = _conv_params(self.padding, self.groups, self.strides, self.dilations)
         ctx.check(ctx.lib.rten_b200_conv_integer_ex(ctx.handle, A.t(x), A.t(w), _ph(packed_w), A.t(x_zero_point),
-                                                    A.t(w_zero_point), A.t(scale), C.byref(p), A.t(bias), A.t(residual),
-                                                    self.activation, C.byref(o)))
+                                                    A.t(w_zero_point), A.t(scale), A.t(scale_b), C.byref(p), A.t(bias),
+                                                    A.t(residual), self.activation, C.byref(o)))
         return A.wrap(o, out)
 
 

@@ -635,6 +635,18 @@ def check_conv_integer_fused(rt, oracle):
                 got = op.run(ctx, xd, w, xz, None, scale, bias=bias, residual=(ctx.to_device(res, channels_last=cl) if use_res else None)).numpy()
                 assert_bit_exact(got, want, f"ConvIntegerToFloat fused x{xs} w{ws} res={use_res} act={act} cl={cl}")
                 worst += 1
+    # the Mul(x_scale, w_scale) node folded into the epilogue (scale_b) and an 8-bit scalar zero point read in place
+    x, w = r.u8((2, 64, 12, 12)), r.i8((96, 64, 3, 3))
+    xs_, ws_, xz = np.float32(0.0371), np.float32(0.0042), np.uint8(97)
+    op = rt.ConvIntegerToFloat(1, (1, 1), (1, 1, 1, 1), (1, 1))
+    want = oracle.conv_integer_to_float(x, w, xz, None, np.float32(xs_ * ws_), padding=[1, 1, 1, 1], groups=1, strides=(1, 1), dilations=(1, 1))
+    got = op.run(ctx, ctx.to_device(x, channels_last=True), w, xz, None, ws_, scale_b=xs_).numpy()
+    assert_bit_exact(got, want, "ConvIntegerToFloat with folded scale product")
+    a8, b8 = r.u8((70, 256)), r.i8((256, 96))
+    wsv = r.uniform((96,), 0.001, 0.01)
+    want = oracle.matmul_integer_to_float(a8, b8, xz, None, (xs_ * wsv).astype(np.float32))
+    got = rt.MatMulIntegerToFloat().run(ctx, a8, b8, xz, None, wsv, scale_b=xs_).numpy()
+    assert_bit_exact(got, want, "MatMulIntegerToFloat with folded scale product")
     # Mul (used for x_scale * w_scale)
     a, b = r.uniform((5, 1, 7)), r.uniform((3, 1))
     assert_bit_exact(rt.Mul().run(ctx, a, b).numpy(), (a * b).astype(np.float32), "Mul broadcast")
