@@ -370,6 +370,23 @@ struct NdParams {
 template <typename T>
 __global__ void __launch_bounds__(256) nd_copy_kernel(const T* __restrict__ src, T* __restrict__ dst, const NdParams p) {
     const long long stride = (long long)gridDim.x * blockDim.x;
+    if (p.n <= 0x7fffffffLL) {  // 32-bit index arithmetic: the emulated 64-bit division is ~10x the instructions
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += stride) {
+            unsigned rem = (unsigned)i;
+            long long so = 0, dof = 0;
+#pragma unroll 1
+            for (int d = p.ndim - 1; d >= 0; d--) {
+                const unsigned sh = (unsigned)p.shape[d];
+                const unsigned q = rem / sh;
+                const unsigned idx = rem - q * sh;
+                rem = q;
+                so += (long long)idx * p.sa[d];
+                dof += (long long)idx * p.sd[d];
+            }
+            dst[dof] = src[so];
+        }
+        return;
+    }
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += stride) {
         long long rem = i, so = 0, dof = 0;
 #pragma unroll 1
@@ -441,13 +458,35 @@ rten_status launch_nd_copy(rten_ctx* ctx, int esize, const void* src, void* dst,
         p.n *= shape[i];
     }
     if (p.n == 0) return RTEN_OK;
+    if (esize != 4 && esize != 1) return fail(ctx, RTEN_ERR_UNSUPPORTED_TYPE, "unsupported element size");
+    // Wider elements when both sides are contiguous along the innermost visited dim: a padded copy of a channels-last
+    // u8 tensor moves 16 bytes per thread instead of one.
+    int es = esize;
+    if (ndim >= 1 && p.sa[ndim - 1] == 1 && p.sd[ndim - 1] == 1) {
+        while (es < 16) {
+            const long long inner_bytes = p.shape[ndim - 1] * es;
+            bool ok = inner_bytes % (2 * es) == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) % (2 * es)) == 0;
+            for (int i = 0; i < ndim - 1 && ok; i++)
+                if ((p.sa[i] * es) % (2 * es) != 0 || (p.sd[i] * es) % (2 * es) != 0) ok = false;
+            if (!ok) break;
+            // strides are in units of the CURRENT element size: halve them together with the inner extent
+            p.shape[ndim - 1] /= 2;
+            for (int i = 0; i < ndim - 1; i++) {
+                p.sa[i] /= 2;
+                p.sd[i] /= 2;
+            }
+            p.n /= 2;
+            es *= 2;
+        }
+    }
     const int grid = ew_grid(ctx, p.n);
-    if (esize == 4)
-        nd_copy_kernel<uint32_t><<<grid, 256, 0, launch_stream(ctx)>>>((const uint32_t*)src, (uint32_t*)dst, p);
-    else if (esize == 1)
-        nd_copy_kernel<uint8_t><<<grid, 256, 0, launch_stream(ctx)>>>((const uint8_t*)src, (uint8_t*)dst, p);
-    else
-        return fail(ctx, RTEN_ERR_UNSUPPORTED_TYPE, "unsupported element size");
+    switch (es) {
+        case 1: nd_copy_kernel<uint8_t><<<grid, 256, 0, launch_stream(ctx)>>>((const uint8_t*)src, (uint8_t*)dst, p); break;
+        case 2: nd_copy_kernel<uint16_t><<<grid, 256, 0, launch_stream(ctx)>>>((const uint16_t*)src, (uint16_t*)dst, p); break;
+        case 4: nd_copy_kernel<uint32_t><<<grid, 256, 0, launch_stream(ctx)>>>((const uint32_t*)src, (uint32_t*)dst, p); break;
+        case 8: nd_copy_kernel<uint2><<<grid, 256, 0, launch_stream(ctx)>>>((const uint2*)src, (uint2*)dst, p); break;
+        default: nd_copy_kernel<uint4><<<grid, 256, 0, launch_stream(ctx)>>>((const uint4*)src, (uint4*)dst, p); break;
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail_cuda(ctx, e, "nd_copy launch");
     count_launch(ctx);
@@ -740,33 +779,52 @@ rten_status launch_cast_scale(rten_ctx* ctx, const int* in, float* out, long lon
 template <typename T>
 __global__ void __launch_bounds__(256)
 im2col_kernel(const T* __restrict__ x, T* __restrict__ out, Im2ColParams p, T pad_value) {
-    const long long total = (long long)p.B * p.OH * p.OW * p.kpad;
+    // one thread = 16 bytes of one im2col row (kpad is a multiple of 16 bytes): the pixel decode is shared by the
+    // group and the store is one 128-bit transaction
+    constexpr int VEC = 16 / (int)sizeof(T);
+    const int groups = p.kpad / VEC;
+    const long long total = (long long)p.B * p.OH * p.OW * groups;
     const long long stride = (long long)gridDim.x * blockDim.x;
+    const int kreal = p.kh * p.kw * p.C;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-        const int k = (int)(i % p.kpad);
-        const long long pix = i / p.kpad;
-        T v = 0;
-        if (k < p.kh * p.kw * p.C) {
-            const int c = k % p.C;
-            const int tap = k / p.C;
-            const int kx = tap % p.kw, ky = tap / p.kw;
-            const int ox = (int)(pix % p.OW);
-            const long long r2 = pix / p.OW;
-            const int oy = (int)(r2 % p.OH);
-            const int b = (int)(r2 / p.OH);
-            const int iy = oy * p.sy - p.pt + ky * p.dy;
-            const int ix = ox * p.sx - p.pl + kx * p.dx;
-            if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W)
-                v = x[(long long)b * p.xs_b + (long long)(c + p.c0) * p.xs_c + (long long)iy * p.xs_h + (long long)ix * p.xs_w];
-            else
-                v = pad_value;
+        const int g = (int)(i % groups);
+        const long long pix = i / groups;
+        const int ox = (int)(pix % p.OW);
+        const long long r2 = pix / p.OW;
+        const int oy = (int)(r2 % p.OH);
+        const int b = (int)(r2 / p.OH);
+        const T* xb = x + (long long)b * p.xs_b + (long long)p.c0 * p.xs_c;
+        const int iy0 = oy * p.sy - p.pt, ix0 = ox * p.sx - p.pl;
+        int k = g * VEC;
+        int c = k % p.C, tap = k / p.C;
+        int kx = tap % p.kw, ky = tap / p.kw;
+        alignas(16) T v[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; j++, k++) {
+            T val = 0;
+            if (k < kreal) {
+                const int iy = iy0 + ky * p.dy, ix = ix0 + kx * p.dx;
+                val = (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W)
+                          ? xb[(long long)c * p.xs_c + (long long)iy * p.xs_h + (long long)ix * p.xs_w]
+                          : pad_value;
+            }
+            v[j] = val;
+            if (++c == p.C) {
+                c = 0;
+                if (++kx == p.kw) {
+                    kx = 0;
+                    ky++;
+                }
+            }
         }
-        out[i] = v;
+        *reinterpret_cast<uint4*>(out + pix * p.kpad + (long long)g * VEC) = *reinterpret_cast<const uint4*>(v);
     }
 }
 
 rten_status launch_im2col(rten_ctx* ctx, int esize, const void* x, void* out, const Im2ColParams& p, int pad_value) {
-    const long long total = (long long)p.B * p.OH * p.OW * p.kpad;
+    if (((long long)p.kpad * esize) % 16 != 0 || (reinterpret_cast<uintptr_t>(out) & 15) != 0)
+        return fail(ctx, RTEN_ERR_INVALID_VALUE, "im2col rows must be multiples of 16 bytes");
+    const long long total = (long long)p.B * p.OH * p.OW * (p.kpad * esize / 16);
     if (total == 0) return RTEN_OK;
     if (esize == 4) {
         float pv = 0.0f;
