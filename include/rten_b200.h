@@ -156,7 +156,7 @@ rten_status rten_b200_matmul_integer_ex(rten_ctx* ctx, const rten_tensor* a, con
                                         const rten_tensor* a_zero_point, const rten_tensor* b_zero_point,
                                         const rten_tensor* scale, const rten_tensor* scale_b_or_null /* scalar: effective scale = scale_b * scale */,
                                         const rten_tensor* bias, const rten_tensor* residual, int activation,
-                                        rten_tensor* out);
+                                        rten_tensor* out_range_or_null, rten_tensor* out);
 
 /* Conv (src/ops/conv.rs:124-419).  x NCHW (or NCW), w OIHW, bias [O].  pads = {top,left,bottom,right};
  * auto_pad_same != 0 => `Padding::Same` (pads ignored).  n_spatial = 1 or 2 gives the expected
@@ -191,7 +191,7 @@ rten_status rten_b200_conv_integer_ex(rten_ctx* ctx, const rten_tensor* x, const
                                       const rten_tensor* x_zero_point, const rten_tensor* w_zero_point,
                                       const rten_tensor* scale, const rten_tensor* scale_b_or_null,
                                       const rten_conv_params* params, const rten_tensor* bias, const rten_tensor* residual,
-                                      int activation, rten_tensor* out);
+                                      int activation, rten_tensor* out_range_or_null, rten_tensor* out);
 
 /* Softmax (src/ops/norm.rs:825-899) and AddSoftmax (src/ops/attention.rs:30-165) when mask != NULL
  * (mask broadcast to x, added lane-wise before the softmax over `axis`; AddSoftmax uses axis -1).
@@ -219,6 +219,14 @@ void rten_b200_comm_destroy(rten_comm* comm);
  * and zero point and the sharded outputs stay bit-identical to the unsharded reference's. */
 rten_status rten_b200_dynamic_quantize_linear(rten_ctx* ctx, const rten_tensor* x, rten_tensor* y,
                                               rten_tensor* scale, rten_tensor* zero_point, void* comm_or_null);
+/* Producer-computed ranges.  `out_range_or_null` of the *_integer_ex functions is a device i32[2] in which the kernel
+ * epilogue accumulates (min, max) of the f32 output it writes (order-preserving integer encoding, atomicMin / atomicMax:
+ * exact, order independent); `rten_b200_range_reset` re-arms any number of such pairs in one launch; the ranged
+ * DynamicQuantizeLinear then skips its own pass over x.  Same bits as the plain operator (NaN inputs excepted). */
+rten_status rten_b200_range_reset(rten_ctx* ctx, rten_tensor* ranges_i32_n_by_2);
+rten_status rten_b200_dynamic_quantize_linear_ranged(rten_ctx* ctx, const rten_tensor* x, const rten_tensor* range_or_null,
+                                                     rten_tensor* y, rten_tensor* scale, rten_tensor* zero_point,
+                                                     void* comm_or_null);
 
 /* ---- residency glue so whole models stay in HBM ------------------------------ */
 rten_status rten_b200_relu(rten_ctx* ctx, const rten_tensor* x, rten_tensor* out);

@@ -75,7 +75,7 @@ _SIGNATURES = {
     "rten_b200_matmul": (C.c_int, [_vp, _TP, _TP, _vp, _TP, C.c_float, _TP]),
     "rten_b200_matmul_ex": (C.c_int, [_vp, _TP, _TP, _vp, _TP, C.c_float, _TP, C.c_int, _TP]),
     "rten_b200_matmul_integer": (C.c_int, [_vp, _TP, _TP, _vp, _TP, _TP, _TP, _TP]),
-    "rten_b200_matmul_integer_ex": (C.c_int, [_vp, _TP, _TP, _vp, _TP, _TP, _TP, _TP, _TP, _TP, C.c_int, _TP]),
+    "rten_b200_matmul_integer_ex": (C.c_int, [_vp, _TP, _TP, _vp, _TP, _TP, _TP, _TP, _TP, _TP, C.c_int, _TP, _TP]),
     "rten_b200_conv2d": (C.c_int, [_vp, _TP, _TP, _vp, _TP, C.POINTER(RtenConvParams), _TP]),
     "rten_b200_conv2d_ex": (C.c_int, [_vp, _TP, _TP, _vp, _TP, C.POINTER(RtenConvParams), _TP, C.c_int, _TP]),
     "rten_b200_conv_integer": (C.c_int, [_vp, _TP, _TP, _vp, _TP, _TP, _TP, C.POINTER(RtenConvParams), _TP]),
@@ -90,7 +90,9 @@ _SIGNATURES = {
     "rten_b200_relu": (C.c_int, [_vp, _TP, _TP]),
     "rten_b200_add": (C.c_int, [_vp, _TP, _TP, _TP]),
     "rten_b200_mul": (C.c_int, [_vp, _TP, _TP, _TP]),
-    "rten_b200_conv_integer_ex": (C.c_int, [_vp, _TP, _TP, _vp, _TP, _TP, _TP, _TP, C.POINTER(RtenConvParams), _TP, _TP, C.c_int, _TP]),
+    "rten_b200_conv_integer_ex": (C.c_int, [_vp, _TP, _TP, _vp, _TP, _TP, _TP, _TP, C.POINTER(RtenConvParams), _TP, _TP, C.c_int, _TP, _TP]),
+    "rten_b200_range_reset": (C.c_int, [_vp, _TP]),
+    "rten_b200_dynamic_quantize_linear_ranged": (C.c_int, [_vp, _TP, _TP, _TP, _TP, _TP, _vp]),
     "rten_b200_max_pool": (C.c_int, [_vp, _TP, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), _TP]),
     "rten_b200_global_average_pool": (C.c_int, [_vp, _TP, _TP]),
     "rten_b200_gather_rows": (C.c_int, [_vp, _TP, _TP, _TP]),

@@ -449,6 +449,7 @@ struct ConvArgs {
     const rten_tensor* w_zp = nullptr;
     const rten_tensor* scale = nullptr;
     const rten_tensor* scale_b = nullptr;  // optional second scalar factor (x_scale of a DynamicQuantizeLinear)
+    const rten_tensor* out_range = nullptr;  // optional i32[2] device tensor: (min, max) of the output, ordered-int encoded
 };
 
 rten_status pack_conv_weight(rten_ctx* ctx, const rten_tensor* w, int esize, void* dst) {
@@ -611,6 +612,12 @@ rten_status conv_core(OpScope& sc, ConvArgs& A, rten_tensor* out) {
         RTB_TRY(sc.in(A.scale_b, &s));
         if (s.dtype != RTEN_F32 || numel(&s) != 1) return fail(ctx, RTEN_ERR_INVALID_VALUE, "scale should be a scalar");
         scale2_p = (const float*)s.data;
+    }
+    int* range_p = nullptr;
+    if (A.out_range) {
+        if (A.out_range->dtype != RTEN_I32 || numel(A.out_range) != 2 || A.out_range->device < 0 || !is_contiguous(A.out_range))
+            return fail(ctx, RTEN_ERR_INVALID_VALUE, "the output range must be a device-resident i32[2]");
+        range_p = (int*)A.out_range->data;
     }
     rten_tensor res_v;
     if (A.residual) {
@@ -777,6 +784,7 @@ rten_status conv_core(OpScope& sc, ConvArgs& A, rten_tensor* out) {
             e.za8 = za8;
             e.za8_signed = x_signed;
             e.scale2 = scale2_p;
+            e.range = range_p;
             e.colsum = w_colsum ? w_colsum + g * Og : nullptr;
             e.zb = zb ? (zb_len == 1 ? zb : zb + g * Og) : nullptr;
             e.zb_len = zb ? (zb_len == 1 ? 1 : (int)Og) : 0;
@@ -1154,13 +1162,13 @@ rten_status rten_b200_matmul(rten_ctx* ctx, const rten_tensor* a, const rten_ten
 rten_status rten_b200_matmul_integer(rten_ctx* ctx, const rten_tensor* a, const rten_tensor* b, const rten_packed* pb,
                                      const rten_tensor* a_zp, const rten_tensor* b_zp, const rten_tensor* scale,
                                      rten_tensor* out) {
-    return rten_b200_matmul_integer_ex(ctx, a, b, pb, a_zp, b_zp, scale, nullptr, nullptr, nullptr, 0, out);
+    return rten_b200_matmul_integer_ex(ctx, a, b, pb, a_zp, b_zp, scale, nullptr, nullptr, nullptr, 0, nullptr, out);
 }
 
 rten_status rten_b200_matmul_integer_ex(rten_ctx* ctx, const rten_tensor* a, const rten_tensor* b, const rten_packed* pb,
                                         const rten_tensor* a_zp, const rten_tensor* b_zp, const rten_tensor* scale,
                                         const rten_tensor* scale_b, const rten_tensor* bias, const rten_tensor* residual,
-                                        int activation, rten_tensor* out) {
+                                        int activation, rten_tensor* out_range, rten_tensor* out) {
     RTB_TRY(check_ctx(ctx));
     if (!a || !b || !out) return fail(ctx, RTEN_ERR_MISSING_INPUTS, "missing inputs");
     if ((bias || residual || activation || scale_b) && !scale)
@@ -1230,6 +1238,12 @@ rten_status rten_b200_matmul_integer_ex(rten_ctx* ctx, const rten_tensor* a, con
     }
     A.epi.act = activation;
     A.residual = residual;
+    if (st == RTEN_OK && out_range) {
+        if (!scale || out_range->dtype != RTEN_I32 || numel(out_range) != 2 || out_range->device < 0 || !is_contiguous(out_range))
+            st = fail(ctx, RTEN_ERR_INVALID_VALUE, "the output range must be a device-resident i32[2] (float outputs only)");
+        else
+            A.epi.range = (int*)out_range->data;
+    }
     if (st == RTEN_OK) st = matmul_core(sc, A, out);
     return sc.finish(st);
 }
@@ -1263,13 +1277,14 @@ rten_status rten_b200_conv2d(rten_ctx* ctx, const rten_tensor* x, const rten_ten
 rten_status rten_b200_conv_integer(rten_ctx* ctx, const rten_tensor* x, const rten_tensor* w, const rten_packed* pw,
                                    const rten_tensor* x_zp, const rten_tensor* w_zp, const rten_tensor* scale,
                                    const rten_conv_params* p, rten_tensor* out) {
-    return rten_b200_conv_integer_ex(ctx, x, w, pw, x_zp, w_zp, scale, nullptr, p, nullptr, nullptr, 0, out);
+    return rten_b200_conv_integer_ex(ctx, x, w, pw, x_zp, w_zp, scale, nullptr, p, nullptr, nullptr, 0, nullptr, out);
 }
 
 rten_status rten_b200_conv_integer_ex(rten_ctx* ctx, const rten_tensor* x, const rten_tensor* w, const rten_packed* pw,
                                       const rten_tensor* x_zp, const rten_tensor* w_zp, const rten_tensor* scale,
                                       const rten_tensor* scale_b, const rten_conv_params* p, const rten_tensor* bias,
-                                      const rten_tensor* residual, int activation, rten_tensor* out) {
+                                      const rten_tensor* residual, int activation, rten_tensor* out_range,
+                                      rten_tensor* out) {
     RTB_TRY(check_ctx(ctx));
     if (!x || !w || !p || !out) return fail(ctx, RTEN_ERR_MISSING_INPUTS, "missing inputs");
     auto is8 = [](int dt) { return dt == RTEN_U8 || dt == RTEN_I8; };
@@ -1294,6 +1309,8 @@ rten_status rten_b200_conv_integer_ex(rten_ctx* ctx, const rten_tensor* x, const
     A.bias = bias;
     A.residual = residual;
     A.act = activation;
+    A.out_range = out_range;
+    if (out_range && !scale) return fail(ctx, RTEN_ERR_INVALID_VALUE, "the output range is defined for float outputs: a scale is required");
     return sc.finish(conv_core(sc, A, out));
 }
 
@@ -1594,11 +1611,28 @@ rten_status rten_b200_mul(rten_ctx* ctx, const rten_tensor* a, const rten_tensor
 }
 
 // ---- DynamicQuantizeLinear ---------------------------------------------------------------------------
+rten_status rten_b200_range_reset(rten_ctx* ctx, rten_tensor* ranges) {
+    RTB_TRY(check_ctx(ctx));
+    if (!ranges) return fail(ctx, RTEN_ERR_MISSING_INPUTS, "missing inputs");
+    if (ranges->dtype != RTEN_I32 || ranges->device < 0 || !is_contiguous(ranges) || numel(ranges) % 2)
+        return fail(ctx, RTEN_ERR_INVALID_VALUE, "ranges must be a contiguous device-resident i32[n, 2]");
+    cudaSetDevice(ctx->device);
+    return launch_range_reset(ctx, (int*)ranges->data, (int)(numel(ranges) / 2));
+}
+
 rten_status rten_b200_dynamic_quantize_linear(rten_ctx* ctx, const rten_tensor* x, rten_tensor* y, rten_tensor* scale,
                                               rten_tensor* zero_point, void* nccl_comm) {
+    return rten_b200_dynamic_quantize_linear_ranged(ctx, x, nullptr, y, scale, zero_point, nccl_comm);
+}
+
+rten_status rten_b200_dynamic_quantize_linear_ranged(rten_ctx* ctx, const rten_tensor* x, const rten_tensor* range,
+                                                     rten_tensor* y, rten_tensor* scale, rten_tensor* zero_point,
+                                                     void* nccl_comm) {
     RTB_TRY(check_ctx(ctx));
     if (!x || !y || !scale || !zero_point) return fail(ctx, RTEN_ERR_MISSING_INPUTS, "missing inputs");
     if (x->dtype != RTEN_F32) return fail(ctx, RTEN_ERR_UNSUPPORTED_TYPE, "unsupported type");
+    if (range && (range->dtype != RTEN_I32 || numel(range) != 2 || range->device < 0 || !is_contiguous(range)))
+        return fail(ctx, RTEN_ERR_INVALID_VALUE, "the range must be a device-resident i32[2]");
     OpScope sc(ctx);
     rten_tensor xv, xc, yv, sv, zv;
     rten_status st = sc.in(x, &xv);
@@ -1623,12 +1657,15 @@ rten_status rten_b200_dynamic_quantize_linear(rten_ctx* ctx, const rten_tensor* 
             const float one = 1.0f;
             RTB_CUDA(ctx, cudaMemcpyAsync(sv.data, &one, 4, cudaMemcpyHostToDevice, rtb::launch_stream(ctx)));
             RTB_CUDA(ctx, cudaMemsetAsync(zv.data, 0, 1, rtb::launch_stream(ctx)));
-        } else if (!nccl_comm && n <= 16384) {
+        } else if (!nccl_comm && !range && n <= 16384) {
             st = launch_dql_small(ctx, (const float*)xc.data, (uint8_t*)yv.data, (int)n, (float*)sv.data, (uint8_t*)zv.data);
         } else {
-            int* mm = nullptr;
-            st = temp_alloc(ctx, 8, (void**)&mm);
-            if (st == RTEN_OK) st = launch_minmax(ctx, (const float*)xc.data, n, mm);
+            // `range`: the producer of x already accumulated (min, max) in its epilogue -- no pass over x for it
+            int* mm = range ? (int*)range->data : nullptr;
+            if (!mm) {
+                st = temp_alloc(ctx, 8, (void**)&mm);
+                if (st == RTEN_OK) st = launch_minmax(ctx, (const float*)xc.data, n, mm);
+            }
             // batch-sharded run: the range is the range of the whole (unsharded) tensor
             if (st == RTEN_OK && nccl_comm) st = comm_allreduce_minmax(ctx, reinterpret_cast<rten_comm*>(nccl_comm), mm);
             if (st == RTEN_OK)

@@ -677,6 +677,23 @@ rten_status launch_dql_small(rten_ctx* ctx, const float* x, uint8_t* y, int n, f
     return RTEN_OK;
 }
 
+__global__ void range_reset_kernel(int* mm, int pairs) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < pairs) {
+        mm[2 * i] = float_to_ordered(__int_as_float(0x7f800000));      // +inf
+        mm[2 * i + 1] = float_to_ordered(__int_as_float(0xff800000));  // -inf
+    }
+}
+
+rten_status launch_range_reset(rten_ctx* ctx, int* mm, int pairs) {
+    if (pairs == 0) return RTEN_OK;
+    range_reset_kernel<<<(pairs + 127) / 128, 128, 0, launch_stream(ctx)>>>(mm, pairs);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "range reset launch");
+    count_launch(ctx);
+    return RTEN_OK;
+}
+
 rten_status launch_minmax(rten_ctx* ctx, const float* x, long long n, int* mm) {
     minmax_init_kernel<<<1, 1, 0, launch_stream(ctx)>>>(mm);
     count_launch(ctx);

@@ -67,4 +67,6 @@ rten_status launch_dql_small(rten_ctx* ctx, const float* x, uint8_t* y, int n, f
 rten_status launch_scatter_rows(rten_ctx* ctx, float* table, const int* idx, const float* src, long long nidx, int width,
                                 long long t_rs, long long t_cs, long long s_rs, long long s_cs, long long rows);
 
+rten_status launch_range_reset(rten_ctx* ctx, int* mm, int pairs);
+
 }  // namespace rtb

@@ -154,6 +154,23 @@ __device__ __forceinline__ void bulk_wait_read(int n) {
     }
 }
 
+__device__ __forceinline__ int f32_to_ordered(float f) {  // same encoding as rowops.cu's min / max kernels
+    const int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+// fold a warp's running (min, max) into the launch-wide range (EpilogueDesc::range)
+__device__ __forceinline__ void range_commit(int* range, float lo, float hi) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0 && lo <= hi) {
+        atomicMin(&range[0], f32_to_ordered(lo));
+        atomicMax(&range[1], f32_to_ordered(hi));
+    }
+}
+
 // Gelu (erf / tanh form) of four values as an out-of-line call: the specialised epilogue stays short straight-line
 // code (an unrolled polynomial per element would multiply its size and thrash the instruction cache), yet Gelu no
 // longer forces a launch into the generic epilogue.
@@ -403,6 +420,7 @@ __device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* t
         const bool do_relu = e.act == 1;  // (no activation: NaNs must pass through, fmaxf would drop them)
         uint32_t ci = 0;
         uint32_t& rphase = st.rphase;
+        float rg_lo = __int_as_float(0x7f800000), rg_hi = __int_as_float(0xff800000);  // output range (e.range)
         for (int u = worker; u < p.units_total; u += n_workers, st.it++) {
             int t, ks_u;
             p.d_tiles_total.divmod(u, ks_u, t);
@@ -431,9 +449,9 @@ __device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* t
                 const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_STRIDE + sub * p.bn;
                 // integer zero-point terms of this thread's row:  C = acc - za*colsum[n] - zb[n]*(rowsum - K*za)
                 unsigned za_v = 0, t_m = 0;
-                if (KIND == 1 && (e.za || e.za8 || e.zb)) {
+                bool row_ok = true;
+                if ((KIND == 1 && (e.za || e.za8 || e.zb)) || e.range) {
                     int m_idx;
-                    bool row_ok;
                     if (p.conv) {
                         int xi, r2, yi, bi;
                         p.d_tw.divmod(r, r2, xi);
@@ -499,6 +517,11 @@ __device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* t
                         mbar_wait(&res_bar[grp * 4 + bcur], (rphase >> bcur) & 1);
                         rphase ^= 1u << bcur;
                     }
+                    // a tile may overhang N (N % bn != 0): its last 32-column chunks are then entirely out of range -- the
+                    // TMA store clips them, and neither the column vectors (bias, sums, scales) nor the range may touch them
+                    const bool col_ok = nbase < p.N;
+                    if (!col_ok) {
+                    } else
                     if (KIND == 0) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
@@ -579,6 +602,13 @@ __device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* t
                             }
                         }
                     }
+                    if (e.range && row_ok && col_ok) {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) {
+                            rg_lo = fminf(rg_lo, __uint_as_float(v[j]));
+                            rg_hi = fmaxf(rg_hi, __uint_as_float(v[j]));
+                        }
+                    }
                     if (nbuf == 1) {  // single staging buffer: the previous store must have been read before it is rewritten
                         if (issuer) bulk_wait_read(0);
                         asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
@@ -608,6 +638,7 @@ __device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* t
                     mbar_arrive(&tmem_empty[acc]);
             }
         }
+        if (e.range) range_commit(e.range, rg_lo, rg_hi);
         // shared memory must stay valid until the last bulk store has READ it; the global writes complete on their own
         // before the grid is considered finished (a sequence kernel waits for them at its layer boundary)
         if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -621,6 +652,7 @@ __device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* t
         const bool issuer = (q == 0 && lane == 0);
         uint32_t ci = 0;            // chunks processed by this group so far (selects the staging buffer)
         uint32_t& rphase = st.rphase;  // bit b = phase of res_bar[grp][b]
+        float rg_lo = __int_as_float(0x7f800000), rg_hi = __int_as_float(0xff800000);  // output range (e.range)
         const int it0 = st.it;
         for (int u = worker; u < p.units_total; u += n_workers, st.it++) {
             const int it = st.it - it0;
@@ -825,6 +857,15 @@ __device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* t
                         }
                     }
                 }
+                if (e.range && row_ok) {  // (rolled: the generic epilogue trades speed for size)
+#pragma unroll 1
+                    for (int j = 0; j < ncols; j++) {
+                        if (nbase + j >= p.N) break;
+                        const float xv = *(reinterpret_cast<const float*>(rowp + (((j >> 2) ^ sw) << 4)) + (j & 3));
+                        rg_lo = fminf(rg_lo, xv);
+                        rg_hi = fmaxf(rg_hi, xv);
+                    }
+                }
                 if (tr) { const long long t1 = clock64(); p.trace[6144 + 1024 + 2] += t1 - t0; t0 = t1; }
                 if (p.tma_store) {
                     // leave nbuf-1 stores in flight minus the one about to be issued: frees the buffer of chunk ci+1
@@ -867,6 +908,7 @@ __device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* t
             }
         }
         // smem must stay valid until the last bulk store has read it
+        if (e.range) range_commit(e.range, rg_lo, rg_hi);
         if (p.tma_store && issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
 

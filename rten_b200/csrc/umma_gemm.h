@@ -47,6 +47,9 @@ struct EpilogueDesc {
     const int32_t* colsum = nullptr;  // sum_k B[n,k]   (needed iff za != null)
     const float* scale = nullptr;     // cast_scale fused: f32 out = f32(C) * scale[n % scale_len]
     int scale_len = 0;
+    // optional: running (min, max) of the f32 OUTPUT of this launch, as two order-preserving int encodings updated with
+    // atomicMin / atomicMax -- the range the next DynamicQuantizeLinear needs, computed while the data is in registers
+    int* range = nullptr;
     const float* scale2 = nullptr;    // optional scalar factor: the effective scale is fmul(scale2[0], scale[n]) -- the
                                       // graph's Mul(x_scale, w_scale) node folded into the epilogue, same rounding
 };

@@ -230,13 +230,19 @@ class ResNet50Int8Runner:
         op, w, b, pk, ws, b4, wz = self._convs[id(c)]
         ctx = self.ctx
         if self.fuse:
-            # one DynamicQuantizeLinear per distinct input (a block's conv1 and its downsample conv share theirs), and
-            # the Mul(x_scale, w_scale) node is folded into the epilogue
+            # one DynamicQuantizeLinear per distinct input (a block's conv1 and its downsample conv share theirs); its
+            # min / max pass is skipped when the producer of x accumulated the range in its epilogue; the
+            # Mul(x_scale, w_scale) node is folded into this convolution's epilogue
             if self._dql_of is not x:
-                self._dql_of, self._dql_val = x, self.dql.run(ctx, x, self.comm)
+                self._dql_of = x
+                self._dql_val = self.dql.run(ctx, x, self.comm, value_range=getattr(x, "value_range", None))
             xq, xs, xz = self._dql_val
             op.activation = O.ACT_RELU if relu else O.ACT_NONE
-            return op.run(ctx, xq, w, xz, wz, ws, packed_w=pk, bias=b, residual=residual, scale_b=xs)
+            rng = self._ranges.view((2,), (1,), 2 * self._n_conv)
+            self._n_conv += 1
+            y = op.run(ctx, xq, w, xz, wz, ws, packed_w=pk, bias=b, residual=residual, scale_b=xs, out_range=rng)
+            y.value_range = rng
+            return y
         xq, xs, xz = self.dql.run(ctx, x, self.comm)
         scale = self.mul.run(ctx, xs, ws)
         op.activation = O.ACT_NONE
@@ -253,6 +259,11 @@ class ResNet50Int8Runner:
         exact arithmetic only (the f32 classifier runs on the TF32 tensor-core path)."""
         s, ctx = self.spec, self.ctx
         self._dql_of = self._dql_val = None
+        if self.fuse:
+            if getattr(self, "_ranges", None) is None:
+                self._ranges = ctx.to_device(np.zeros((2 + 4 * len(s.blocks), 2), np.int32))
+            O.DynamicQuantizeLinear.reset_ranges(ctx, self._ranges)  # one launch re-arms every producer-computed range
+            self._n_conv = 0
         y = self._conv(s.stem, x, True)
         y = self.maxpool.run(ctx, y)
         for b in s.blocks:

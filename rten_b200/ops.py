@@ -365,7 +365,7 @@ class MatMulIntegerToFloat(MatMul):
         self.activation = activation
 
     def run(self, ctx, a, b, a_zero_point, b_zero_point, scale, packed_b: Optional[Packed] = None, out=None, bias=None,
-            residual=None, scale_b=None):
+            residual=None, scale_b=None, out_range=None):
         """`bias` / `residual` / `self.activation`: the Add / Add / Gelu nodes that follow the operator in a quantised
         transformer, folded into the epilogue with the same f32 roundings (rten_b200_matmul_integer_ex)."""
         if scale is None:
@@ -374,7 +374,7 @@ class MatMulIntegerToFloat(MatMul):
         o = A.out(out)
         ctx.check(ctx.lib.rten_b200_matmul_integer_ex(ctx.handle, A.t(a), A.t(b), _ph(packed_b), A.t(a_zero_point),
                                                       A.t(b_zero_point), A.t(scale), A.t(scale_b), A.t(bias), A.t(residual),
-                                                      self.activation, C.byref(o)))
+                                                      self.activation, A.t(out_range), C.byref(o)))
         return A.wrap(o, out)
 
 
@@ -442,7 +442,7 @@ class ConvIntegerToFloat(Conv):
     """src/ops/conv.rs:535-587"""
 
     def run(self, ctx, x, w, x_zero_point, w_zero_point, scale, packed_w: Optional[Packed] = None, out=None,
-            bias=None, residual=None, scale_b=None):
+            bias=None, residual=None, scale_b=None, out_range=None):
         """`bias` / `residual` / `self.activation` = the Add(bias), Add(identity), Relu nodes that follow the operator in
         a quantised ResNet, executed in the epilogue with the same f32 roundings (rten_b200_conv_integer_ex)."""
         if scale is None:
@@ -452,7 +452,7 @@ class ConvIntegerToFloat(Conv):
         p = _conv_params(self.padding, self.groups, self.strides, self.dilations)
         ctx.check(ctx.lib.rten_b200_conv_integer_ex(ctx.handle, A.t(x), A.t(w), _ph(packed_w), A.t(x_zero_point),
                                                     A.t(w_zero_point), A.t(scale), A.t(scale_b), C.byref(p), A.t(bias),
-                                                    A.t(residual), self.activation, C.byref(o)))
+                                                    A.t(residual), self.activation, A.t(out_range), C.byref(o)))
         return A.wrap(o, out)
 
 
@@ -537,13 +537,21 @@ class Relu(_Unary):
 class DynamicQuantizeLinear:
     """src/ops/quantize.rs:436-468 -> (y u8, y_scale f32 scalar, y_zero_point u8 scalar)"""
 
-    def run(self, ctx, x, comm: Optional["Comm"] = None):
-        """`comm`: batch-sharded run -- the quantisation range is all-reduced over the ranks (min, max) first."""
+    def run(self, ctx, x, comm: Optional["Comm"] = None, value_range=None):
+        """`comm`: batch-sharded run -- the quantisation range is all-reduced over the ranks (min, max) first.
+        `value_range`: i32[2] device tensor filled by the producer of x (`out_range=` of the *IntegerToFloat operators):
+        the operator then skips its own min / max pass."""
         A = _Args(ctx)
         y, s, z = A.out(), A.out(), A.out()
-        ctx.check(ctx.lib.rten_b200_dynamic_quantize_linear(ctx.handle, A.t(x), C.byref(y), C.byref(s), C.byref(z),
-                                                            comm.handle if comm is not None else None))
+        ctx.check(ctx.lib.rten_b200_dynamic_quantize_linear_ranged(ctx.handle, A.t(x), A.t(value_range), C.byref(y), C.byref(s),
+                                                                   C.byref(z), comm.handle if comm is not None else None))
         return A.wrap(y, None), A.wrap(s, None), A.wrap(z, None)
+
+    @staticmethod
+    def reset_ranges(ctx, ranges: "DeviceTensor"):
+        """Re-arm a [n, 2] i32 tensor of producer-computed ranges (one launch) before the producers run."""
+        d = ranges.desc()
+        ctx.check(ctx.lib.rten_b200_range_reset(ctx.handle, C.byref(d)))
 
 
 class Comm:
