@@ -1741,13 +1741,17 @@ rten_status launch_umma_gemm(rten_ctx* ctx, const GemmLaunch& L) {
     Prepared q;
     RTB_TRY(prepare_launch(ctx, L, q));
     const bool verbose = getenv("RTEN_B200_VERBOSE") != nullptr;
+    const bool forced = getenv("RTEN_B200_FORCE_BN") || getenv("RTEN_B200_FORCE_PAIR") || getenv("RTEN_B200_FORCE_KATOMS") ||
+                        getenv("RTEN_B200_FORCE_SPLITK") || getenv("RTEN_B200_FORCE_CTA2");
+    if (!forced && !ctx->tune_cache.empty()) {  // measured plan on record: no need to enumerate and rank candidates
+        auto hit = ctx->tune_cache.find(tune_key(L, q));
+        if (hit != ctx->tune_cache.end()) return launch_plan(ctx, L, q, plan_from_array(hit->second), verbose);
+    }
     std::vector<std::pair<double, Plan>> cands;
     enumerate_plans(q, ctx->num_sms, cands);
     if (cands.empty()) return RTEN_ERR_UNSUPPORTED_VALUE;
     Plan plan = cands[0].second;
 
-    const bool forced = getenv("RTEN_B200_FORCE_BN") || getenv("RTEN_B200_FORCE_PAIR") || getenv("RTEN_B200_FORCE_KATOMS") ||
-                        getenv("RTEN_B200_FORCE_SPLITK") || getenv("RTEN_B200_FORCE_CTA2");
     if (forced) {
         // debugging / sweeps: the best-ranked candidate that matches every forced field
         const char* fb = getenv("RTEN_B200_FORCE_BN");
