@@ -613,18 +613,21 @@ dql_quantize_kernel(const float* __restrict__ x, uint8_t* __restrict__ y, long l
         *zp_out = (uint8_t)zp;
     }
     const long long stride = (long long)gridDim.x * blockDim.x;
-    const bool al = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((reinterpret_cast<uintptr_t>(y) & 3) == 0);
-    const long long n4 = al ? (n >> 2) : 0;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-        const float4 v = reinterpret_cast<const float4*>(x)[i];
-        uchar4 o;
-        o.x = quant1(v.x, inv, zp);
-        o.y = quant1(v.y, inv, zp);
-        o.z = quant1(v.z, inv, zp);
-        o.w = quant1(v.w, inv, zp);
-        reinterpret_cast<uchar4*>(y)[i] = o;
+    // 16 elements per thread and iteration: four independent 128-bit loads in flight, one 128-bit store
+    const bool al = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
+    const long long n16 = al ? (n >> 4) : 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+        const float4* xp = reinterpret_cast<const float4*>(x) + 4 * i;
+        const float4 v0 = xp[0], v1 = xp[1], v2 = xp[2], v3 = xp[3];
+        const float f[16] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w, v3.x, v3.y, v3.z, v3.w};
+        uint32_t w[4];
+#pragma unroll
+        for (int g = 0; g < 4; g++)
+            w[g] = (uint32_t)quant1(f[4 * g], inv, zp) | ((uint32_t)quant1(f[4 * g + 1], inv, zp) << 8) |
+                   ((uint32_t)quant1(f[4 * g + 2], inv, zp) << 16) | ((uint32_t)quant1(f[4 * g + 3], inv, zp) << 24);
+        reinterpret_cast<uint4*>(y)[i] = make_uint4(w[0], w[1], w[2], w[3]);
     }
-    for (long long j = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride)
+    for (long long j = (n16 << 4) + (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride)
         y[j] = quant1(x[j], inv, zp);
 }
 
@@ -708,7 +711,7 @@ rten_status launch_minmax(rten_ctx* ctx, const float* x, long long n, int* mm) {
 
 rten_status launch_dql_quantize(rten_ctx* ctx, const float* x, uint8_t* y, long long n, const int* mm, float* scale_out,
                                 uint8_t* zp_out) {
-    dql_quantize_kernel<<<ew_grid(ctx, (n + 3) / 4), 256, 0, launch_stream(ctx)>>>(x, y, n, mm, scale_out, zp_out);
+    dql_quantize_kernel<<<ew_grid(ctx, (n + 15) / 16), 256, 0, launch_stream(ctx)>>>(x, y, n, mm, scale_out, zp_out);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail_cuda(ctx, e, "dql launch");
     count_launch(ctx);
