@@ -152,6 +152,46 @@ class ResNet50Runner:
 
 
 # ---------------------------------------------------------------------------------------------
+# MNIST CNN (BASELINE configs[0]; the reference's own test model rten-onnx/test-data/mnist.onnx, exported by
+# tools/train-mnist.py:24-46): Conv(1->32,3x3,p1) Relu MaxPool2 Conv(32->72,3x3,p1) Relu MaxPool2 Conv(72->64,1x1) Relu
+# ReduceMean(H,W) Reshape Gemm(64->10, transB).  Real weights: tests/golden/mnist.npz (tests/golden/make_mnist_fixture.py).
+# ---------------------------------------------------------------------------------------------
+
+
+def load_mnist_weights(path: str) -> dict:
+    z = np.load(path)
+    return {k[2:]: z[k] for k in z.files if k.startswith("w:")}
+
+
+class MnistRunner:
+    def __init__(self, ctx: O.Context, weights: dict, fuse: bool = True):
+        self.ctx, self.fuse = ctx, fuse
+        dev = ctx.to_device
+        self.w = {k: dev(v) for k, v in weights.items()}
+        self.c1 = O.Conv(1, (1, 1), (1, 1, 1, 1), (1, 1))
+        self.c2 = O.Conv(1, (1, 1), (1, 1, 1, 1), (1, 1))
+        self.pw = O.Conv(1, (1, 1), (0, 0, 0, 0), (1, 1))
+        self.pool = O.MaxPool((2, 2), (0, 0, 0, 0), (2, 2))
+        self.relu, self.gap, self.fc = O.Relu(), O.GlobalAveragePool(), O.Gemm(1.0, 1.0, False, True)
+
+    def _conv(self, op, x, name):
+        if self.fuse:
+            op.activation = O.ACT_RELU
+            return op.run(self.ctx, x, self.w[name + ".weight"], self.w[name + ".bias"])
+        op.activation = O.ACT_NONE
+        return self.relu.run(self.ctx, op.run(self.ctx, x, self.w[name + ".weight"], self.w[name + ".bias"]), in_place=True)
+
+    def run(self, x: O.DeviceTensor) -> O.DeviceTensor:
+        """x: [B,1,28,28] -> logits [B,10]."""
+        ctx = self.ctx
+        y = self.pool.run(ctx, self._conv(self.c1, x, "conv1"))
+        y = self.pool.run(ctx, self._conv(self.c2, y, "conv2"))
+        y = self._conv(self.pw, y, "pw")
+        p = self.gap.run(ctx, y)  # ReduceMean over (H, W), keepdims -> [B,64,1,1]
+        return self.fc.run(ctx, p.reshape(p.shape[0], p.shape[1]), self.w["fc.weight"], self.w["fc.bias"])
+
+
+# ---------------------------------------------------------------------------------------------
 # ResNet-50 int8 (BASELINE configs[3]): the graph `tools/ort-quantize.py dynamic --quantize-conv` produces, after
 # RTen's fusions (src/optimize/fusions.rs:966-1058): every Conv becomes
 #     DynamicQuantizeLinear(x) -> Mul(x_scale, w_scale) -> ConvIntegerToFloat(x_q, w_q, x_zp, -, scale) -> Add(bias)

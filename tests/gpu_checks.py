@@ -748,6 +748,32 @@ def check_tf32x3(rt, oracle):
     return f"worst err/bound {w:.3f} (bound 2^-18); ResNet-50 logits rel err {rel:.2e}"
 
 
+def check_mnist_model(rt, oracle):
+    """configs[0]: the reference's MNIST test model with its real weights (tests/golden/mnist.npz): 1-channel stem through
+    the small-C path, 72-channel pointwise conv, 2x2 max pooling, ReduceMean, Gemm.  Single-pass TF32 within 1e-2 of
+    max |logit| (the whole-model bound used for ResNet-50 too), 3xTF32 within 5e-5; fused and unfused epilogues; batch 1 (the reference's test input) and batch 5."""
+    import os
+    from rten_b200 import graphs
+    import model_ref
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mnist.npz")
+    w = graphs.load_mnist_weights(path)
+    x1 = np.full((1, 1, 28, 28), 0.5, np.float32)
+    x5 = np.concatenate([x1, oracle.XorShiftRng(8).uniform((4, 1, 28, 28))], 0)
+    out = []
+    for x in (x1, x5):
+        ref = model_ref.mnist_oracle(oracle, w, x)
+        for x3, tol in ((False, 1e-2), (True, 5e-5)):
+            ctx = rt.Context(0)
+            ctx.set_f32_mode(x3)
+            for fuse in (True, False):
+                got = graphs.MnistRunner(ctx, w, fuse=fuse).run(ctx.to_device(x)).numpy()
+                rel = float(np.abs(got - ref).max() / np.abs(ref).max())
+                assert got.shape == ref.shape and rel <= tol, f"MNIST logits (batch {x.shape[0]}, x3={x3}, fuse={fuse}): rel err {rel:.3e}"
+                assert (got.argmax(1) == ref.argmax(1)).all()
+                out.append(rel)
+    return f"rel err tf32 {max(out[0::4] + out[1::4]):.1e}, 3xtf32 {max(out[2::4] + out[3::4]):.1e}"
+
+
 def check_resnet50_model(rt, oracle):
     """Whole-model parity (ResNet-50 fp32, full 224x224 images, batch 2): every conv runs single-pass TF32,
     so the logits carry ~53 layers of 2^-11-relative operand rounding.  Stated tolerance: max |d| <= 1e-2 * max |ref|."""
@@ -802,5 +828,5 @@ ALL_CHECKS = [
     ("matmul_bert", check_matmul_bert), ("gemm_op", check_gemm_op), ("matmul_integer", check_matmul_integer),
     ("conv_basic", check_conv_basic), ("conv_stride", check_conv_stride), ("conv_more", check_conv_more),
     ("conv_integer", check_conv_integer), ("plans", check_plans), ("tf32x3", check_tf32x3), ("sequence", check_sequence), ("conv_integer_fused", check_conv_integer_fused),
-    ("resnet50_int8_model", check_resnet50_int8_model), ("gpt2_int8_kvcache", check_gpt2_int8_kvcache), ("resnet50_model", check_resnet50_model), ("bert_model", check_bert_model),
+    ("resnet50_int8_model", check_resnet50_int8_model), ("gpt2_int8_kvcache", check_gpt2_int8_kvcache), ("mnist_model", check_mnist_model), ("resnet50_model", check_resnet50_model), ("bert_model", check_bert_model),
 ]

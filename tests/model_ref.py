@@ -39,6 +39,17 @@ def resnet50_oracle(oracle, spec, x, arena=None):
     return oracle.gemm_op(p.reshape(p.shape[0], p.shape[1]), spec.fc_w, spec.fc_b, 1.0, 1.0, False, True)
 
 
+def mnist_oracle(oracle, w, x):
+    """configs[0]: the reference's MNIST CNN (rten-onnx/test-data/mnist.onnx) with the reference's operators."""
+    y = oracle.relu(oracle.conv(x, w["conv1.weight"], w["conv1.bias"], [1, 1, 1, 1], 1, (1, 1), (1, 1)))
+    y = oracle.max_pool(y, (2, 2), [0, 0, 0, 0], (2, 2))
+    y = oracle.relu(oracle.conv(y, w["conv2.weight"], w["conv2.bias"], [1, 1, 1, 1], 1, (1, 1), (1, 1)))
+    y = oracle.max_pool(y, (2, 2), [0, 0, 0, 0], (2, 2))
+    y = oracle.relu(oracle.conv(y, w["pw.weight"], w["pw.bias"], [0, 0, 0, 0], 1, (1, 1), (1, 1)))
+    p = oracle.global_average_pool(y)
+    return oracle.gemm_op(p.reshape(p.shape[0], p.shape[1]), w["fc.weight"], w["fc.bias"], 1.0, 1.0, False, True)
+
+
 def resnet50_int8_oracle(oracle, qspec, x, w_zero_points=True):
     """configs[3] (rten_b200/graphs.py ResNet50Int8Runner) with the reference's operators, unfused, NCHW.
     -> (logits, pooled features)."""

@@ -46,3 +46,18 @@ def test_gpt2_kv_cache_steps_have_the_right_shapes_and_differ_from_scratch_only_
     full = model_ref.gpt2_int8_oracle(oracle, spec, [ids])[0]
     # dynamic quantisation ranges differ between incremental and from-scratch runs: close, not identical
     assert np.abs(full - steps[2]).max() < 0.25 * np.abs(full).max()
+
+
+def test_mnist_oracle_matches_independent_logits(oracle):
+    """configs[0] (CPU plumbing): the reference's own MNIST model and the input of its own test
+    (`full([1,1,28,28], 0.5)`, src/model.rs:1284-1287).  The reference pins only the output shape; the values are
+    pinned here by PyTorch float64 logits stored in the fixture, to the reference's default tolerance
+    (expect_equal: atol 1e-8 + rtol 1e-5 -- loosened to 1e-5 absolute for f32 accumulation over 288 terms)."""
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mnist.npz")
+    w = graphs.load_mnist_weights(path)
+    want = np.load(path)["logits_f64"]
+    got = model_ref.mnist_oracle(oracle, w, np.full((1, 1, 28, 28), 0.5, np.float32))
+    assert got.shape == (1, 10)
+    assert np.abs(got - want).max() <= 1e-5, np.abs(got - want).max()
+    assert int(got.argmax()) == int(want.argmax())
