@@ -393,7 +393,10 @@ def main():
             roof_line = {"bound": "tensor", "kernel": "rtb::umma_gemm_kernel<0> (tcgen05 kind::tf32 implicit-GEMM conv / GEMM)",
                          "achieved": roof["tflops"], "peak": tf32_peak, "unit": "TFLOP/s", "frac": roof["tflops"] / tf32_peak,
                          "traffic": ncu_traffic(), "launches_timed": roof["launches"], "share_of_step": roof["share"],
-                         "peak_source": f"0.5 x {peaks['src']} bf16 sustained ({peaks['bf16_sustained']} TF/s): kind::tf32 issues at half the bf16 rate"}
+                         "peak_source": f"0.5 x {peaks['src']} bf16 sustained ({peaks['bf16_sustained']} TF/s): kind::tf32 issues at half the bf16 rate",
+                         # the same launches against the other roof: at batch 32 the wide 1x1 layers are nearer to it
+                         "hbm_view": {"achieved": roof["gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                      "frac": roof["gbs"] / peaks["hbm_gbs"], "bytes": "algorithmic: operands + output (+ residual) once"}}
             line["roofline"] = roof_line
         if extras:
             tf32_peak = 0.5 * peaks["bf16_burst"]
@@ -516,13 +519,18 @@ def roofline_pass(ctx, rt, runner, model, spec, dev_inputs, batch, stream, torch
     records = []
     orig_conv, orig_mm, orig_mm0 = O.Conv.run, O.FusedMatMul.run, O.MatMul.run
 
+    def nbytes(t):
+        return float(np.prod(t.shape)) * 4.0 if t is not None and hasattr(t, "shape") else 0.0
+
     def wrap(orig, flops_fn):
         def run(self, c, *a, **k):
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record(stream)
             y = orig(self, c, *a, **k)
             e.record(stream)
-            records.append((s, e, flops_fn(a, y)))
+            # algorithmic bytes: every operand read once, the output written once
+            by = nbytes(a[0]) + nbytes(a[1]) + nbytes(y) + nbytes(k.get("residual")) + (nbytes(a[2]) if len(a) > 2 else 0.0)
+            records.append((s, e, flops_fn(a, y), by))
             return y
         return run
 
@@ -539,7 +547,7 @@ def roofline_pass(ctx, rt, runner, model, spec, dev_inputs, batch, stream, torch
     O.FusedMatMul.run = wrap(orig_mm, mm_flops)
     O.MatMul.run = wrap(orig_mm0, mm_flops)
     try:
-        tot_ms, tot_fl, n = 0.0, 0.0, 0
+        tot_ms, tot_fl, tot_by, n = 0.0, 0.0, 0.0, 0
         for rep in range(4):
             records.clear()
             s0, e0 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -552,14 +560,15 @@ def roofline_pass(ctx, rt, runner, model, spec, dev_inputs, batch, stream, torch
             torch.cuda.synchronize()
             if rep == 0:
                 continue
-            tot_ms += sum(s.elapsed_time(e) for s, e, _ in records)
-            tot_fl += sum(f for _, _, f in records)
+            tot_ms += sum(s.elapsed_time(e) for s, e, _, _ in records)
+            tot_fl += sum(f for _, _, f, _ in records)
+            tot_by += sum(b for _, _, _, b in records)
             n += len(records)
             step_ms = s0.elapsed_time(e0)
-            share = sum(s.elapsed_time(e) for s, e, _ in records) / step_ms
+            share = sum(s.elapsed_time(e) for s, e, _, _ in records) / step_ms
     finally:
         O.Conv.run, O.FusedMatMul.run, O.MatMul.run = orig_conv, orig_mm, orig_mm0
-    return {"tflops": tot_fl / (tot_ms / 1e3) / 1e12, "launches": n, "share": share}
+    return {"tflops": tot_fl / (tot_ms / 1e3) / 1e12, "gbs": tot_by / (tot_ms / 1e3) / 1e9, "launches": n, "share": share}
 
 
 if __name__ == "__main__":
