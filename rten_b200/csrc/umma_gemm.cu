@@ -4,19 +4,23 @@
 // rten-gemm/src/kernels/simd_generic.rs:285,576) and the im2col packing
 // (rten-gemm/src/im2col.rs:110-389) on the MatMul / MatMulInteger / Conv / ConvInteger path.
 //
-// Persistent, warp-specialised kernel, one CTA per SM (256 threads):
-//   warp 0   : TMA producer   -- cp.async.bulk.tensor tiles of A (128 rows x 128 B) and B (bn rows x 128 B)
-//                                into a ring of 128B-swizzled shared-memory stages
-//   warp 1   : MMA issuer     -- one elected thread issues tcgen05.mma (kind::tf32 or kind::i8),
+// Persistent, warp-specialised kernel, one CTA of 384 threads per SM (or one CTA per SM of a CTA pair):
+//   warp 0   : TMA producer   -- cp.async.bulk.tensor tiles of A (128 rows x 128 B, two of them in pair mode) and B
+//                                (bn rows x 128 B; half of them per CTA in CTA-pair mode) into a ring of 128B-swizzled
+//                                shared-memory stages; starts before the rest of the CTA has finished its set-up
+//   warp 1   : MMA issuer     -- one elected thread issues tcgen05.mma (kind::tf32 or kind::i8, cta_group::1 or ::2),
 //                                4 instructions per 128-byte K block, accumulating in TMEM
-//   warp 2   : TMEM allocator -- 512 columns = 2 accumulator stages of up to 256 columns
+//   warp 2   : TMEM allocator -- 512 columns = 2 accumulator stages of up to 256 columns (or one of 512)
 //   warps 4-11: epilogue      -- two groups of 4 warps, each taking every other 32-column chunk of the tile:
 //                                tcgen05.ld accumulator rows -> registers -> fused epilogue (alpha, residual /
-//                                beta*C, bias, activation; or the integer zero-point correction and cast*scale)
-//                                -> 128B-swizzled smem staging -> cp.async.bulk.tensor store (full-line writes;
-//                                TMA clips rows/columns outside the output).  Outputs whose rows are not
-//                                contiguous fall back to direct register->global stores.  Runs concurrently
-//                                with the next tile's main loop thanks to the second TMEM stage.
+//                                beta*C, bias, activation; or the integer zero-point correction, cast*scale, bias,
+//                                residual, activation; optionally the output's min / max) -> 128B-swizzled smem
+//                                staging -> cp.async.bulk.tensor store (full-line writes; TMA clips rows/columns
+//                                outside the output).  Outputs whose rows are not contiguous fall back to direct
+//                                register->global stores.  Runs concurrently with the next tile's main loop thanks
+//                                to the second TMEM stage.
+// Work decomposition (tile width, pair, split-K, CTA pair ...) is a launch `Plan` (see "Launch plans" below), ranked by
+// a cost model and, optionally, measured on the device per problem.
 // For Conv the A tile is a TMA box over the NHWC activation tensor at (c0, ox0*sx - pad + kx*dx,
 // oy0*sy - pad + ky*dy, b0): padding comes from TMA out-of-bounds zero fill, the stride from the
 // tensor map's element strides; the im2col matrix is never materialised.
