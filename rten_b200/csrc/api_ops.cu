@@ -749,6 +749,96 @@ rten_status conv_core(OpScope& sc, ConvArgs& A, rten_tensor* out) {
         // otherwise fall through to the generic explicit path
     }
 
+    // ---- 8-bit small-channel path (the quantised RGB stem): padded [B,Hp,Wp,16] copy, one 128-byte K block per filter row
+    const bool smallc8_ok = !implicit_ok && A.kind == 1 && groups == 1 && Cg <= 16 && kw <= 8 && dil[1] == 1 && !zb &&
+                            (int64_t)B * OH * OW > 0 && !getenv("RTEN_B200_NO_SMALLC");
+    if (smallc8_ok) {
+        const int64_t Hp = H + pt + pb;
+        const int64_t Wp = std::max<int64_t>(W + pl + pr, (OW - 1) * strides[1] + 8);
+        void *xp = nullptr, *wsm = nullptr;
+        RTB_TRY(temp_alloc(ctx, (size_t)(B * Hp * Wp * 16), &xp));
+        RTB_TRY(launch_smallc8_pad(ctx, x.data, xp, (int)B, (int)C, (int)H, (int)W, (int)Hp, (int)Wp, (int)pt, (int)pl,
+                                   x.strides[0], x.strides[1], x.strides[2], x.strides[3], pad_value));
+        RTB_TRY(temp_alloc(ctx, (size_t)(O * kh * 128), &wsm));
+        RTB_TRY(launch_smallc8_pack_w(ctx, w.data, wsm, (int)O, (int)C, (int)kh, (int)kw, w.strides[0], w.strides[1],
+                                      w.strides[2], w.strides[3]));
+        GemmLaunch L;
+        L.kind = 1;
+        L.a_signed = x_signed;
+        L.b_signed = w_signed;
+        L.conv = 1;
+        L.N = (int)O;
+        L.K = (int)(kh * 128);
+        L.M = (int)(B * OH * OW);
+        L.g.B = (int)B;
+        L.g.H = (int)Hp;
+        L.g.W = (int)OW;  // dim 1 of the A map indexes output columns directly
+        L.g.C = 128;
+        L.g.OH = (int)OH;
+        L.g.OW = (int)OW;
+        L.g.kh = (int)kh;
+        L.g.kw = 1;
+        L.g.sy = (int)strides[0];
+        L.g.sx = 1;
+        L.g.dy = (int)dil[0];
+        L.g.dx = 1;
+        L.g.pt = 0;
+        L.g.pl = 0;
+        L.a.base = xp;
+        L.a.dims[0] = 128;
+        L.a.dims[1] = OW;
+        L.a.dims[2] = Hp;
+        L.a.dims[3] = B;
+        L.a.strides[0] = 1;
+        L.a.strides[1] = strides[1] * 16;
+        L.a.strides[2] = Wp * 16;
+        L.a.strides[3] = Hp * Wp * 16;
+        L.b.base = wsm;
+        L.b.dims[0] = 128;
+        L.b.dims[1] = O;
+        L.b.dims[2] = kh;
+        L.b.dims[3] = 1;
+        L.b.strides[0] = 1;
+        L.b.strides[1] = kh * 128;
+        L.b.strides[2] = 128;
+        L.b.strides[3] = 0;
+        EpilogueDesc& e = L.epi;
+        e.d = ov.data;
+        e.d_is_i32 = out_dtype == RTEN_I32;
+        e.s_z0 = ov.strides[0];
+        e.s_row = ov.strides[2];
+        e.s_z1 = ov.strides[3];
+        e.s_col = ov.strides[1];
+        e.act = A.act;
+        if (A.bias) {
+            rten_tensor bc;
+            RTB_TRY(sc.contiguous(&bias_v, &bc));
+            e.bias = (const float*)bc.data;
+            e.bias_kind = 1;
+        }
+        if (A.residual) {
+            e.r = (const float*)res_v.data;
+            e.r_scale = 1.0f;
+            e.r_z0 = res_v.strides[0];
+            e.r_row = res_v.strides[2];
+            e.r_z1 = res_v.strides[3];
+            e.r_col = res_v.strides[1];
+        }
+        e.za = za;
+        e.za_len = za ? 1 : 0;
+        e.za8 = za8;
+        e.za8_signed = x_signed;
+        e.colsum = w_colsum;
+        e.scale = scale_p;
+        e.scale_len = scale_p ? 1 : 0;
+        e.scale2 = scale2_p;
+        e.range = range_p;
+        rten_status st = launch_umma_gemm(ctx, L);
+        if (st == RTEN_OK) return RTEN_OK;
+        if (st != RTEN_ERR_UNSUPPORTED_VALUE) return st;
+        // otherwise fall through to the generic explicit path
+    }
+
     for (int g = 0; g < groups; g++) {
         GemmLaunch L;
         L.kind = A.kind;

@@ -1032,6 +1032,71 @@ rten_status launch_gather_rows(rten_ctx* ctx, const float* table, const int* idx
 }
 
 
+// 8-bit small-channel path (the quantised RGB stem): [B, Hp, Wp, 16] copy with BOTH paddings materialised (the reference
+// pads u8 images with 128, which TMA's zero fill cannot produce) and channels padded to 16 bytes per pixel, so that one
+// 128-byte K block = 8 pixels = one filter row and every TMA stride is a multiple of 16 bytes.
+__global__ void __launch_bounds__(256)
+smallc8_pad_kernel(const uint8_t* __restrict__ x, uint8_t* __restrict__ xp, int B, int C, int H, int W, int Hp, int Wp,
+                   int pt, int pl, long long xs_b, long long xs_c, long long xs_h, long long xs_w, int pad_value) {
+    const long long total = (long long)B * Hp * Wp;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int xw = (int)(i % Wp);
+        const long long r = i / Wp;
+        const int yh = (int)(r % Hp);
+        const int b = (int)(r / Hp);
+        const int iy = yh - pt, ix = xw - pl;
+        alignas(16) uint8_t v[16];
+#pragma unroll
+        for (int c = 0; c < 16; c++) v[c] = 0;
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+            const uint8_t* src = x + (long long)b * xs_b + (long long)iy * xs_h + (long long)ix * xs_w;
+            for (int c = 0; c < C; c++) v[c] = src[(long long)c * xs_c];
+        } else {
+            for (int c = 0; c < C; c++) v[c] = (uint8_t)pad_value;
+        }
+        reinterpret_cast<uint4*>(xp)[i] = *reinterpret_cast<const uint4*>(v);
+    }
+}
+
+// weights OIHW (any strides) -> [O, kh, 8 pixels, 16 channels], zero where kx >= kw or c >= C
+__global__ void smallc8_pack_w_kernel(const uint8_t* __restrict__ w, uint8_t* __restrict__ wp, int O, int C, int kh, int kw,
+                                      long long ws_o, long long ws_c, long long ws_h, long long ws_w) {
+    const int total = O * kh * 128;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c = i & 15, kx = (i >> 4) & 7;
+    const int r = i >> 7;
+    const int ky = r % kh, o = r / kh;
+    uint8_t v = 0;
+    if (c < C && kx < kw) v = w[(long long)o * ws_o + (long long)c * ws_c + (long long)ky * ws_h + (long long)kx * ws_w];
+    wp[i] = v;
+}
+
+rten_status launch_smallc8_pad(rten_ctx* ctx, const void* x, void* xp, int B, int C, int H, int W, int Hp, int Wp, int pt,
+                               int pl, long long xs_b, long long xs_c, long long xs_h, long long xs_w, int pad_value) {
+    const long long total = (long long)B * Hp * Wp;
+    if (total == 0) return RTEN_OK;
+    smallc8_pad_kernel<<<ew_grid(ctx, total), 256, 0, launch_stream(ctx)>>>((const uint8_t*)x, (uint8_t*)xp, B, C, H, W, Hp, Wp,
+                                                                     pt, pl, xs_b, xs_c, xs_h, xs_w, pad_value);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "smallc8 pad launch");
+    count_launch(ctx);
+    return RTEN_OK;
+}
+
+rten_status launch_smallc8_pack_w(rten_ctx* ctx, const void* w, void* wp, int O, int C, int kh, int kw, long long ws_o,
+                                  long long ws_c, long long ws_h, long long ws_w) {
+    const int total = O * kh * 128;
+    if (total == 0) return RTEN_OK;
+    smallc8_pack_w_kernel<<<(total + 255) / 256, 256, 0, launch_stream(ctx)>>>((const uint8_t*)w, (uint8_t*)wp, O, C, kh, kw,
+                                                                         ws_o, ws_c, ws_h, ws_w);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "smallc8 pack launch");
+    count_launch(ctx);
+    return RTEN_OK;
+}
+
 // ScatterElements-style row update (the KV-cache append of rten-generate when the write position lives on the device):
 // table[idx[r], c] = src[r, c].  Rows named by `idx` must be distinct.
 __global__ void __launch_bounds__(256)

@@ -69,4 +69,9 @@ rten_status launch_scatter_rows(rten_ctx* ctx, float* table, const int* idx, con
 
 rten_status launch_range_reset(rten_ctx* ctx, int* mm, int pairs);
 
+rten_status launch_smallc8_pad(rten_ctx* ctx, const void* x, void* xp, int B, int C, int H, int W, int Hp, int Wp, int pt,
+                               int pl, long long xs_b, long long xs_c, long long xs_h, long long xs_w, int pad_value);
+rten_status launch_smallc8_pack_w(rten_ctx* ctx, const void* w, void* wp, int O, int C, int kh, int kw, long long ws_o,
+                                  long long ws_c, long long ws_h, long long ws_w);
+
 }  // namespace rtb

@@ -584,7 +584,10 @@ def check_conv_integer(rt, oracle):
     # tensor-core path: 16-byte channel groups, padding (production path: G3), stride, zero points, channels-last
     for xdt in (np.uint8, np.int8):
         for xs, ws, pads, st, cl in [((2, 32, 9, 9), (24, 32, 3, 3), (1, 1, 1, 1), (1, 1), True), ((2, 64, 12, 10), (16, 64, 3, 3), (1, 1, 1, 1), (2, 2), True),
-                                     ((2, 128, 7, 7), (40, 128, 1, 1), (0, 0, 0, 0), (1, 1), True), ((1, 16, 8, 8), (8, 16, 3, 3), (1, 0, 1, 0), (1, 1), False)]:
+                                     ((2, 128, 7, 7), (40, 128, 1, 1), (0, 0, 0, 0), (1, 1), True), ((1, 16, 8, 8), (8, 16, 3, 3), (1, 0, 1, 0), (1, 1), False),
+                                     # small-channel 8-bit path (quantised RGB stem): padded 16-byte pixels, one K block per filter row
+                                     ((2, 3, 32, 32), (16, 3, 7, 7), (3, 3, 3, 3), (2, 2), True), ((3, 1, 12, 13), (8, 1, 3, 3), (1, 1, 1, 1), (1, 1), False),
+                                     ((2, 4, 9, 9), (32, 4, 5, 5), (2, 1, 0, 2), (1, 2), True)]:
             x, w = mk(rng, xs, xdt), krng.i8(ws)
             xzp, wzp = np.array(77 if xdt == np.uint8 else -3, xdt), krng.i8((ws[0],))
             for zx, zw in [(xzp, wzp), (xzp, None), (None, wzp), (None, None)]:
