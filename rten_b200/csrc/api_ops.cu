@@ -1731,15 +1731,27 @@ rten_status rten_b200_dynamic_quantize_linear_ranged(rten_ctx* ctx, const rten_t
     bool dense = st == RTEN_OK && span_elems(&xv) == numel(&xv) && y->data == nullptr;
     for (int i = 0; i < xv.ndim && dense; i++)
         if (xv.strides[i] <= 0 && xv.shape[i] > 1) dense = false;
-    if (dense) {
+    const bool x_cl_dense = st == RTEN_OK && xv.ndim == 4 && xv.strides[1] == 1 && xv.strides[3] == xv.shape[1] &&
+                            xv.strides[2] == xv.shape[3] * xv.shape[1] && xv.strides[0] == xv.shape[2] * xv.shape[3] * xv.shape[1];
+    if (dense || (x_cl_dense && y->data && y->ndim == 4 && y->strides[1] == 1)) {
         xc = xv;
     } else if (st == RTEN_OK) {
         st = sc.contiguous(&xv, &xc);
     }
+    // A caller-provided channels-last output whose rows (b, h) sit at arbitrary pitches -- the interior of a spatially
+    // pre-padded buffer, so that the consuming ConvInteger needs no padded copy -- is written row by row.
+    bool rows_out = false;
+    if (st == RTEN_OK && y->data && xv.ndim == 4 && y->ndim == 4 && y->device >= 0) {
+        const int64_t Cc = xv.shape[1], Hh = xv.shape[2], Ww = xv.shape[3];
+        rows_out = xv.strides[1] == 1 && xv.strides[3] == Cc && xv.strides[2] == Ww * Cc && xv.strides[0] == Hh * Ww * Cc &&
+                   y->strides[1] == 1 && y->strides[3] == Cc && !is_contiguous(y) &&
+                   !(y->strides[2] == Ww * Cc && y->strides[0] == Hh * Ww * Cc);
+        if (rows_out) xc = xv;
+    }
     if (st == RTEN_OK) st = sc.out(y, RTEN_U8, xv.ndim, xv.shape, &yv, dense ? xv.strides : nullptr);
     if (st == RTEN_OK) st = sc.out(scale, RTEN_F32, 0, nullptr, &sv, nullptr);
     if (st == RTEN_OK) st = sc.out(zero_point, RTEN_U8, 0, nullptr, &zv, nullptr);
-    if (st == RTEN_OK && !dense && !is_contiguous(&yv)) st = fail(ctx, RTEN_ERR_UNSUPPORTED_OUTPUT, "quantized output must be contiguous");
+    if (st == RTEN_OK && !dense && !rows_out && !is_contiguous(&yv)) st = fail(ctx, RTEN_ERR_UNSUPPORTED_OUTPUT, "quantized output must be contiguous");
     if (st == RTEN_OK) {
         const long long n = numel(&xv);
         if (n == 0) {
@@ -1747,7 +1759,7 @@ rten_status rten_b200_dynamic_quantize_linear_ranged(rten_ctx* ctx, const rten_t
             const float one = 1.0f;
             RTB_CUDA(ctx, cudaMemcpyAsync(sv.data, &one, 4, cudaMemcpyHostToDevice, rtb::launch_stream(ctx)));
             RTB_CUDA(ctx, cudaMemsetAsync(zv.data, 0, 1, rtb::launch_stream(ctx)));
-        } else if (!nccl_comm && !range && n <= 16384) {
+        } else if (!nccl_comm && !range && !rows_out && n <= 16384) {
             st = launch_dql_small(ctx, (const float*)xc.data, (uint8_t*)yv.data, (int)n, (float*)sv.data, (uint8_t*)zv.data);
         } else {
             // `range`: the producer of x already accumulated (min, max) in its epilogue -- no pass over x for it
@@ -1758,7 +1770,11 @@ rten_status rten_b200_dynamic_quantize_linear_ranged(rten_ctx* ctx, const rten_t
             }
             // batch-sharded run: the range is the range of the whole (unsharded) tensor
             if (st == RTEN_OK && nccl_comm) st = comm_allreduce_minmax(ctx, reinterpret_cast<rten_comm*>(nccl_comm), mm);
-            if (st == RTEN_OK)
+            if (st == RTEN_OK && rows_out)
+                st = launch_dql_quantize_rows(ctx, (const float*)xc.data, (uint8_t*)yv.data, xv.shape[0] * xv.shape[2],
+                                              (int)(xv.shape[3] * xv.shape[1]), (int)xv.shape[2], yv.strides[2], yv.strides[0], mm,
+                                              (float*)sv.data, (uint8_t*)zv.data);
+            else if (st == RTEN_OK)
                 st = launch_dql_quantize(ctx, (const float*)xc.data, (uint8_t*)yv.data, n, mm, (float*)sv.data, (uint8_t*)zv.data);
         }
     }

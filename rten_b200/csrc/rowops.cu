@@ -672,6 +672,55 @@ dql_small_kernel(const float* __restrict__ x, uint8_t* __restrict__ y, int n, fl
     for (int i = threadIdx.x; i < n; i += blockDim.x) y[i] = quant1(x[i], inv, zp);
 }
 
+// Quantise pass with a ROW-STRIDED destination: x is [rows, row_len] contiguous, row r of y starts at
+// (r / rows_inner) * y_outer + (r % rows_inner) * y_inner -- the interior of a spatially pre-padded channels-last buffer.
+__global__ void __launch_bounds__(256)
+dql_quantize_rows_kernel(const float* __restrict__ x, uint8_t* __restrict__ y, long long rows, int row_len, int rows_inner,
+                         long long y_inner, long long y_outer, const int* mm, float* scale_out, uint8_t* zp_out) {
+    float scale, inv;
+    int zp;
+    dql_params(mm, scale, inv, zp);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        *scale_out = scale;
+        *zp_out = (uint8_t)zp;
+    }
+    const int groups = (row_len + 15) >> 4;
+    const long long total = rows * groups;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const long long r = i / groups;
+        const int g = (int)(i - r * groups);
+        const float* xr = x + r * row_len + g * 16;
+        uint8_t* yr = y + (r / rows_inner) * y_outer + (r % rows_inner) * y_inner + g * 16;
+        const int nrem = row_len - g * 16;
+        if (nrem >= 16 && ((reinterpret_cast<uintptr_t>(xr) | reinterpret_cast<uintptr_t>(yr)) & 15) == 0) {
+            const float4* xp = reinterpret_cast<const float4*>(xr);
+            const float4 v0 = xp[0], v1 = xp[1], v2 = xp[2], v3 = xp[3];
+            const float f[16] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w, v3.x, v3.y, v3.z, v3.w};
+            uint32_t w[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                w[q] = (uint32_t)quant1(f[4 * q], inv, zp) | ((uint32_t)quant1(f[4 * q + 1], inv, zp) << 8) |
+                       ((uint32_t)quant1(f[4 * q + 2], inv, zp) << 16) | ((uint32_t)quant1(f[4 * q + 3], inv, zp) << 24);
+            *reinterpret_cast<uint4*>(yr) = make_uint4(w[0], w[1], w[2], w[3]);
+        } else {
+            for (int j = 0; j < nrem && j < 16; j++) yr[j] = quant1(xr[j], inv, zp);
+        }
+    }
+}
+
+rten_status launch_dql_quantize_rows(rten_ctx* ctx, const float* x, uint8_t* y, long long rows, int row_len, int rows_inner,
+                                     long long y_inner, long long y_outer, const int* mm, float* scale_out, uint8_t* zp_out) {
+    const long long total = rows * ((row_len + 15) / 16);
+    if (total == 0) return RTEN_OK;
+    dql_quantize_rows_kernel<<<ew_grid(ctx, total), 256, 0, launch_stream(ctx)>>>(x, y, rows, row_len, rows_inner, y_inner, y_outer,
+                                                                          mm, scale_out, zp_out);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "dql launch");
+    count_launch(ctx);
+    return RTEN_OK;
+}
+
 rten_status launch_dql_small(rten_ctx* ctx, const float* x, uint8_t* y, int n, float* scale_out, uint8_t* zp_out) {
     dql_small_kernel<<<1, 1024, 0, launch_stream(ctx)>>>(x, y, n, scale_out, zp_out);
     cudaError_t e = cudaGetLastError();

@@ -74,4 +74,7 @@ rten_status launch_smallc8_pad(rten_ctx* ctx, const void* x, void* xp, int B, in
 rten_status launch_smallc8_pack_w(rten_ctx* ctx, const void* w, void* wp, int O, int C, int kh, int kw, long long ws_o,
                                   long long ws_c, long long ws_h, long long ws_w);
 
+rten_status launch_dql_quantize_rows(rten_ctx* ctx, const float* x, uint8_t* y, long long rows, int row_len, int rows_inner,
+                                     long long y_inner, long long y_outer, const int* mm, float* scale_out, uint8_t* zp_out);
+
 }  // namespace rtb

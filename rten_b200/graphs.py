@@ -246,7 +246,7 @@ class ResNet50Int8Runner:
                  w_zero_points: bool = False):
         """`comm`: this rank holds a shard of the batch; quantisation ranges are all-reduced."""
         self.ctx, self.spec, self.fuse, self.comm, self.w_zero_points = ctx, spec, fuse, comm, w_zero_points
-        self._convs = {}
+        self._convs, self._pad_bufs, self._nopad_ops = {}, {}, {}
 
         def prep(c: QConvSpec):
             op = O.ConvIntegerToFloat(1, (1, 1), (c.pad, c.pad, c.pad, c.pad), (c.stride, c.stride))
@@ -266,6 +266,26 @@ class ResNet50Int8Runner:
         self.dql, self.mul, self.add, self.relu = O.DynamicQuantizeLinear(), O.Mul(), O.Add(), O.Relu()
         self.fc = O.Gemm(1.0, 1.0, False, True)
 
+    def _padded_buffer(self, c: QConvSpec, x):
+        """(buffer [B,C,H+2p,W+2p] channels-last filled with 128, its [B,C,H,W] interior view), cached per conv / shape."""
+        B, C, H, W = x.shape
+        p = c.pad
+        key = (id(c), B, C, H, W)
+        hit = self._pad_bufs.get(key)
+        if hit is None:
+            Hp, Wp = H + 2 * p, W + 2 * p
+            buf = self.ctx.to_device(np.full((B, Hp, Wp, C), 128, np.uint8))
+            full = buf.view((B, C, Hp, Wp), (Hp * Wp * C, 1, Wp * C, C))
+            interior = buf.view((B, C, H, W), (Hp * Wp * C, 1, Wp * C, C), (p * Wp + p) * C)
+            hit = self._pad_bufs[key] = (full, interior)
+        return hit
+
+    def _nopad_op(self, c: QConvSpec):
+        op = self._nopad_ops.get(id(c))
+        if op is None:
+            op = self._nopad_ops[id(c)] = O.ConvIntegerToFloat(1, (1, 1), (0, 0, 0, 0), (c.stride, c.stride))
+        return op
+
     def _conv(self, c: QConvSpec, x, relu: bool, residual=None):
         op, w, b, pk, ws, b4, wz = self._convs[id(c)]
         ctx = self.ctx
@@ -273,10 +293,21 @@ class ResNet50Int8Runner:
             # one DynamicQuantizeLinear per distinct input (a block's conv1 and its downsample conv share theirs); its
             # min / max pass is skipped when the producer of x accumulated the range in its epilogue; the
             # Mul(x_scale, w_scale) node is folded into this convolution's epilogue
-            if self._dql_of is not x:
-                self._dql_of = x
-                self._dql_val = self.dql.run(ctx, x, self.comm, value_range=getattr(x, "value_range", None))
-            xq, xs, xz = self._dql_val
+            pad_into = None
+            if c.pad > 0 and c.wq.shape[1] >= 32 and x.strides[1] == 1:
+                # padded convolution of a channels-last tensor: quantise straight into the interior of a buffer whose
+                # border holds the reference's pad value for u8 images (128, rten-gemm/src/im2col.rs:340-358) and run
+                # the convolution un-padded on it -- same arithmetic, no padded copy per call
+                pad_into = self._padded_buffer(c, x)
+            if pad_into is not None:
+                buf, interior = pad_into
+                xq, xs, xz = self.dql.run(ctx, x, self.comm, value_range=getattr(x, "value_range", None), out=interior)
+                xq, op = buf, self._nopad_op(c)
+            else:
+                if self._dql_of is not x:
+                    self._dql_of = x
+                    self._dql_val = self.dql.run(ctx, x, self.comm, value_range=getattr(x, "value_range", None))
+                xq, xs, xz = self._dql_val
             op.activation = O.ACT_RELU if relu else O.ACT_NONE
             rng = self._ranges.view((2,), (1,), 2 * self._n_conv)
             self._n_conv += 1

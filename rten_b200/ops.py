@@ -537,15 +537,16 @@ class Relu(_Unary):
 class DynamicQuantizeLinear:
     """src/ops/quantize.rs:436-468 -> (y u8, y_scale f32 scalar, y_zero_point u8 scalar)"""
 
-    def run(self, ctx, x, comm: Optional["Comm"] = None, value_range=None):
+    def run(self, ctx, x, comm: Optional["Comm"] = None, value_range=None, out=None):
         """`comm`: batch-sharded run -- the quantisation range is all-reduced over the ranks (min, max) first.
         `value_range`: i32[2] device tensor filled by the producer of x (`out_range=` of the *IntegerToFloat operators):
-        the operator then skips its own min / max pass."""
+        the operator then skips its own min / max pass.  `out`: u8 destination view, e.g. the interior of a spatially
+        pre-padded channels-last buffer (rows at arbitrary pitches)."""
         A = _Args(ctx)
-        y, s, z = A.out(), A.out(), A.out()
+        y, s, z = A.out(out), A.out(), A.out()
         ctx.check(ctx.lib.rten_b200_dynamic_quantize_linear_ranged(ctx.handle, A.t(x), A.t(value_range), C.byref(y), C.byref(s),
                                                                    C.byref(z), comm.handle if comm is not None else None))
-        return A.wrap(y, None), A.wrap(s, None), A.wrap(z, None)
+        return A.wrap(y, out), A.wrap(s, None), A.wrap(z, None)
 
     @staticmethod
     def reset_ranges(ctx, ranges: "DeviceTensor"):

@@ -146,6 +146,17 @@ def check_dql(rt, oracle):
         assert_bit_exact(s.numpy(), np.float32(es), f"DQL scale {shape}")
         assert_bit_exact(z.numpy(), np.uint8(ez), f"DQL zero point {shape}")
         assert_bit_exact(y.numpy(), ey, f"DQL y {shape}")
+    # channels-last input quantised straight into the interior of a spatially pre-padded buffer (border = 128), with the
+    # range taken from a caller-provided (min, max) pair
+    x = r.uniform((2, 32, 6, 5), -2, 3)
+    ey, es, ez = oracle.dynamic_quantize_linear(x)
+    buf = ctx.to_device(np.full((2, 8, 7, 32), 128, np.uint8))
+    interior = buf.view((2, 32, 6, 5), (8 * 7 * 32, 1, 7 * 32, 32), (1 * 7 + 1) * 32)
+    y, s, z = rt.DynamicQuantizeLinear().run(ctx, ctx.to_device(x, channels_last=True), out=interior)
+    want = np.full((2, 8, 7, 32), 128, np.uint8)
+    want[:, 1:7, 1:6, :] = ey.transpose(0, 2, 3, 1)
+    assert_bit_exact(buf.numpy(), want, "DQL into a pre-padded buffer")
+    assert_bit_exact(s.numpy(), np.float32(es), "DQL scale (padded destination)")
     return "ok"
 
 
