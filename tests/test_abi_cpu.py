@@ -93,3 +93,17 @@ def test_fastdiv_magic_numbers():
         for n in samples:
             if 0 <= n < (1 << 31):
                 assert fdiv(n, d, mul, shr) == n // d, (n, d)
+
+
+def test_ctypes_signatures_have_the_header_arity():
+    """Every prototype of include/rten_b200.h and its ctypes signature in rten_b200/_lib.py take the same number of
+    parameters (a silently mismatched arity corrupts the call instead of failing)."""
+    from rten_b200 import _lib
+    src = open(os.path.join(ROOT, "include", "rten_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", " ", src, flags=re.S)
+    protos = dict(re.findall(r"\b(rten_b200_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S))
+    assert set(protos) == set(_lib.declared_symbols())
+    for name, params in protos.items():
+        params = params.strip()
+        n = 0 if params in ("", "void") else len([p for p in params.split(",") if p.strip()])
+        assert n == len(_lib._SIGNATURES[name][1]), f"{name}: header has {n} parameters, _lib.py {len(_lib._SIGNATURES[name][1])}"
