@@ -72,7 +72,7 @@ class ClockSampler:
 
     def stop(self):
         if self.nv is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"], "samples": 0}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "note": "NVML binding unavailable: clocks not sampled"}
         self.stop_flag = True
         self.thread.join(timeout=1)
         nv = self.nv
