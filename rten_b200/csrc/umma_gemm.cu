@@ -431,7 +431,9 @@ __device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* t
             const int acc = p.acc1 ? 0 : (st.it & 1);
             const uint32_t acc_phase = (st.acc >> acc) & 1;
             st.acc ^= 1u << acc;
-            if (p.res_tma && issuer && grp * 32 < p.bn) {
+            // residual of this tile's first chunk: independent of the accumulator -> requested before waiting for it
+            // (split-K: only once this CTA knows that it owns the tile's epilogue)
+            auto first_residual = [&]() {
                 const TileCoord tc0 = decode_tile(p, t, 0, cta_rank);
                 const int b0 = ci % nbuf;
                 bulk_wait_read(nbuf - 1);
@@ -441,13 +443,16 @@ __device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* t
                     tma_load_4d(stg0 + b0 * STG_BYTES, tma_r, rb, tc0.n0 + grp * 32, tc0.ox0, tc0.oy0, tc0.b0);
                 else
                     tma_load_4d(stg0 + b0 * STG_BYTES, tma_r, rb, tc0.n0 + grp * 32, tc0.m0, tc0.z0, tc0.z1);
-            }
+            };
+            if (p.res_tma && p.splitk == 1 && issuer && grp * 32 < p.bn) first_residual();
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             bool owner = true;
-            if (p.splitk > 1)
+            if (p.splitk > 1) {
                 owner = splitk_publish(p, CTA2 ? 2 * t + cta_rank : t, ks_u, grp, q, lane,
                                        tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_STRIDE, &sk_flag[grp]);
+                if (owner && p.res_tma && issuer && grp * 32 < p.bn) first_residual();
+            }
             for (int sub = 0; owner && sub <= p.pair; sub++) {
                 const TileCoord tc = decode_tile(p, t, sub, cta_rank);
                 const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_STRIDE + sub * p.bn;
@@ -665,7 +670,7 @@ __device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* t
             const int acc = p.acc1 ? 0 : (st.it & 1);
             const uint32_t acc_phase = (st.acc >> acc) & 1;
             st.acc ^= 1u << acc;
-            if (p.res_tma && issuer && grp * 32 < p.bn) {
+            auto first_residual = [&]() {
                 // residual of this tile's first chunk: independent of the accumulator -> request it before waiting
                 const TileCoord tc0 = decode_tile(p, t, 0, cta_rank);
                 const int b0 = ci % nbuf;
@@ -676,14 +681,17 @@ __device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* t
                     tma_load_4d(stg0 + b0 * STG_BYTES, tma_r, rb, tc0.n0 + grp * 32, tc0.ox0, tc0.oy0, tc0.b0);
                 else
                     tma_load_4d(stg0 + b0 * STG_BYTES, tma_r, rb, tc0.n0 + grp * 32, tc0.m0, tc0.z0, tc0.z1);
-            }
+            };
+            if (p.res_tma && p.splitk == 1 && issuer && grp * 32 < p.bn) first_residual();
             mbar_wait(&tmem_full[acc], acc_phase);
             if (p.trace && blockIdx.x == 0 && warp == 4 && lane == 0 && it < 2048) p.trace[4096 + it] = clock64();
             tc_fence_after();
             bool owner = true;
-            if (p.splitk > 1)
+            if (p.splitk > 1) {
                 owner = splitk_publish(p, CTA2 ? 2 * t + cta_rank : t, ks_u, grp, q, lane,
                                        tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_STRIDE, &sk_flag[grp]);
+                if (owner && p.res_tma && issuer && grp * 32 < p.bn) first_residual();
+            }
             for (int sub = 0; owner && sub <= p.pair; sub++) {
             const TileCoord tc = decode_tile(p, t, sub, cta_rank);
             // ---- row bookkeeping
@@ -1267,7 +1275,7 @@ static double plan_cost(const Prepared& q, const Plan& pl, const PlanShape& ps, 
     double unit = pl.acc1 ? mainloop + epi + 1000.0 : std::max(mainloop, epi) + 1500.0;
     double cost = waves * unit + 2500.0;
     if (pl.splitk > 1) cost += epi * (1.0 + 0.25 * pl.splitk) + 1500.0;  // publish + the owner's reduction
-    if (pl.splitk > 1 && q.res_tma) cost += 2.0 * epi;                    // residual through the generic epilogue
+
     return cost;
 }
 
@@ -1580,7 +1588,7 @@ static rten_status launch_plan(rten_ctx* ctx, const GemmLaunch& L, const Prepare
     p.cta2 = pl.cta2;
     p.nbuf = pl.nbuf;
     p.tma_store = q.tma_store;
-    p.res_tma = (q.res_tma && pl.splitk == 1) ? 1 : 0;
+    p.res_tma = q.res_tma ? 1 : 0;
     if (p.res_tma && p.nbuf < 2) p.nbuf = 2;
     p.kb_per = ps.kb_per;
     p.tiles_n = (int)ps.tiles_n;
