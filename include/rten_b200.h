@@ -72,8 +72,10 @@ typedef struct rten_packed rten_packed;
 
 /* fp32 GEMM/Conv arithmetic mode (SURVEY.md hard part A). */
 typedef enum {
-    RTEN_F32_TF32 = 0,  /* single tcgen05 kind::tf32 pass (default; tolerance in DESIGN.md) */
-    RTEN_F32_TF32X3 = 1 /* 3-pass error-compensated split: ~fp32 accuracy at 1/3 tensor rate */
+    RTEN_F32_TF32 = 0,  /* single tcgen05 kind::tf32 pass: operands rounded to 10 mantissa bits.  EXPLICIT OPT-IN
+                           (rten_b200_set_f32_mode or env RTEN_B200_F32_MODE=tf32); tolerance in DESIGN.md */
+    RTEN_F32_TF32X3 = 1 /* DEFAULT: 3-pass error-compensated split (hi*hi + hi*lo + lo*hi, f32 accumulation): meets the
+                           reference's own f32 tolerance (rten-tensor/src/test_util.rs:47-92) at 1/3 of the tensor rate */
 } rten_f32_mode;
 
 /* ---- context, memory, diagnostics ----------------------------------------------------------- */
@@ -104,6 +106,10 @@ rten_status rten_b200_copy(rten_ctx* ctx, const rten_tensor* src, rten_tensor* d
 /* Number of CUDA kernels this context has launched so far (bench.py `gpu_launches`). */
 uint64_t rten_b200_launch_count(rten_ctx* ctx);
 const char* rten_b200_version(void);
+/* Debug aid for plan sweeps (env RTEN_B200_FORCE_BN / _PAIR / _KATOMS / _SPLITK / _CTA2): how many tensor-core launches
+ * found a valid plan matching every forced field, and how many fell back to the cost model's choice because none did.
+ * With env RTEN_B200_FORCE_STRICT=1 such a launch fails with RTEN_ERR_INVALID_VALUE instead. */
+rten_status rten_b200_debug_forced_plans(rten_ctx* ctx, uint64_t* matched, uint64_t* unmatched);
 /* Debug aid: when enabled, CTA 0 of every GEMM/conv launch records clock64() at its pipeline hand-offs into a
  * 4 x 2048 int64 buffer (rows: producer slot acquired, MMA operands landed, epilogue start, epilogue end).
  * `host_out_8192_or_null` receives the current contents before the state change. */

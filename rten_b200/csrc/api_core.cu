@@ -1,8 +1,10 @@
 // Context, allocator, staging and copy entry points of the C ABI (include/rten_b200.h).
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <iterator>
 
 #include "api_util.h"
 #include "rowops.h"
@@ -11,11 +13,21 @@ namespace rtb {
 
 rten_status pool_alloc(rten_ctx* ctx, size_t bytes, void** out) {
     const size_t b = DevicePool::bucket(bytes);
+    if (ctx->capturing) {  // buffers released earlier in this capture first (they stay private to the graph)
+        auto ci = ctx->pool.cap_free.find(b);
+        if (ci != ctx->pool.cap_free.end() && !ci->second.empty()) {
+            *out = ci->second.back();
+            ci->second.pop_back();
+            ctx->pool.live[*out] = b;
+            return RTEN_OK;
+        }
+    }
     auto it = ctx->pool.free_buckets.find(b);
     if (it != ctx->pool.free_buckets.end() && !it->second.empty()) {
         *out = it->second.back();
         it->second.pop_back();
         ctx->pool.live[*out] = b;
+        if (ctx->capturing) ctx->pool.cap_touched[*out] = b;
         return RTEN_OK;
     }
     // During graph capture (relaxed mode) growing the pool is still legal: cudaMalloc is not a stream operation.
@@ -24,6 +36,7 @@ rten_status pool_alloc(rten_ctx* ctx, size_t bytes, void** out) {
     if (e != cudaSuccess) return fail_cuda(ctx, e, "cudaMalloc");
     ctx->pool.bytes_reserved += b;
     ctx->pool.live[p] = b;
+    if (ctx->capturing) ctx->pool.cap_touched[p] = b;
     *out = p;
     return RTEN_OK;
 }
@@ -32,9 +45,40 @@ rten_status pool_free(rten_ctx* ctx, void* p) {
     if (!p) return RTEN_OK;
     auto it = ctx->pool.live.find(p);
     if (it == ctx->pool.live.end()) return fail(ctx, RTEN_ERR_INVALID_VALUE, "pointer was not allocated by this context");
-    ctx->pool.free_buckets[it->second].push_back(p);
+    const size_t b = it->second;
     ctx->pool.live.erase(it);
+    if (ctx->capturing) {
+        // the captured nodes keep this pointer: reusable by later nodes of the SAME capture only
+        ctx->pool.cap_touched[p] = b;
+        ctx->pool.cap_free[b].push_back(p);
+        return RTEN_OK;
+    }
+    auto pin = ctx->pool.pinned.find(p);
+    if (pin != ctx->pool.pinned.end()) {  // referenced by an instantiated graph: parked there until it is destroyed
+        pin->second->held.emplace_back(p, b);
+        ctx->pool.pinned.erase(pin);
+        return RTEN_OK;
+    }
+    ctx->pool.free_buckets[b].push_back(p);
     return RTEN_OK;
+}
+
+// End of a capture: buffers released during it go to the graph (or back to the pool when the capture failed), buffers
+// handed out during it that the caller still holds are pinned to the graph.
+static void capture_settle(rten_ctx* ctx, rten_graph* g) {
+    DevicePool& pool = ctx->pool;
+    for (auto& kv : pool.cap_free)
+        for (void* p : kv.second) {
+            if (g)
+                g->held.emplace_back(p, kv.first);
+            else
+                pool.free_buckets[kv.first].push_back(p);
+        }
+    if (g)
+        for (auto& kv : pool.cap_touched)
+            if (pool.live.count(kv.first)) pool.pinned[kv.first] = g;
+    pool.cap_free.clear();
+    pool.cap_touched.clear();
 }
 
 rten_status temp_alloc(rten_ctx* ctx, size_t bytes, void** out) {
@@ -241,8 +285,9 @@ rten_status rten_b200_ctx_create(int device, void* cuda_stream_or_null, size_t w
         tune_cache_load(ctx, tf);
         ctx->tune_loaded = ctx->tune_cache.size();
     }
-    const char* mode = getenv("RTEN_B200_F32_MODE");
+    const char* mode = getenv("RTEN_B200_F32_MODE");  // default: tf32x3 (fp32-grade); "tf32" opts in to the single pass
     if (mode && strcmp(mode, "tf32x3") == 0) ctx->f32_mode = RTEN_F32_TF32X3;
+    if (mode && strcmp(mode, "tf32") == 0) ctx->f32_mode = RTEN_F32_TF32;
     if (workspace_bytes) {  // pre-reserve one pool bucket so the first ops do not pay cudaMalloc
         void* p = nullptr;
         if (pool_alloc(ctx, workspace_bytes, &p) == RTEN_OK) pool_free(ctx, p);
@@ -258,6 +303,13 @@ void rten_b200_ctx_destroy(rten_ctx* ctx) {
     for (auto& kv : ctx->pool.free_buckets)
         for (void* p : kv.second) cudaFree(p);
     for (auto& kv : ctx->pool.live) cudaFree(kv.first);
+    for (auto& kv : ctx->pool.cap_free)
+        for (void* p : kv.second) cudaFree(p);
+    for (rten_graph* g : ctx->graphs) {  // graphs that outlive the context keep nothing of it
+        for (auto& pb : g->held) cudaFree(pb.first);
+        g->held.clear();
+        g->ctx = nullptr;
+    }
     if (const char* tf = getenv("RTEN_B200_TUNE_FILE"))
         if (ctx->tune_cache.size() > ctx->tune_loaded) tune_cache_save(ctx, tf);
     if (ctx->sk_counters) cudaFree(ctx->sk_counters);
@@ -319,6 +371,13 @@ rten_status rten_b200_host_free(rten_ctx* ctx, void* host_ptr) {
 }
 
 uint64_t rten_b200_launch_count(rten_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+rten_status rten_b200_debug_forced_plans(rten_ctx* ctx, uint64_t* matched, uint64_t* unmatched) {
+    if (!ctx) return RTEN_ERR_INVALID_VALUE;
+    if (matched) *matched = ctx->forced_hits;
+    if (unmatched) *unmatched = ctx->forced_misses;
+    return RTEN_OK;
+}
 
 rten_status rten_b200_copy(rten_ctx* ctx, const rten_tensor* src, rten_tensor* dst) {
     if (!ctx || !src || !dst) return RTEN_ERR_INVALID_VALUE;
@@ -401,14 +460,19 @@ rten_status rten_b200_graph_end(rten_ctx* ctx, rten_graph** out) {
     if (e != cudaSuccess) {
         if (g->graph) cudaGraphDestroy(g->graph);
         delete g;
+        capture_settle(ctx, nullptr);
         return fail_cuda(ctx, e, "graph capture/instantiate");
     }
     if (fs != RTEN_OK) {
         cudaGraphExecDestroy(g->exec);
         cudaGraphDestroy(g->graph);
         delete g;
+        capture_settle(ctx, nullptr);
         return fs;
     }
+    g->ctx = ctx;
+    ctx->graphs.push_back(g);
+    capture_settle(ctx, g);
     g->kernels = ctx->launches - ctx->capture_start_launches;
     ctx->launches = ctx->capture_start_launches;  // captured launches did not execute
     *out = g;
@@ -424,6 +488,14 @@ void rten_b200_graph_destroy(rten_graph* g) {
     if (!g) return;
     if (g->exec) cudaGraphExecDestroy(g->exec);
     if (g->graph) cudaGraphDestroy(g->graph);
+    if (rten_ctx* ctx = g->ctx) {
+        // no replay can touch them any more: the parked buffers return to the pool, pinned ones become ordinary again.
+        // (Replays still in flight are ordered before any later use: the pool is stream-ordered on the same stream.)
+        for (auto& pb : g->held) ctx->pool.free_buckets[pb.second].push_back(pb.first);
+        for (auto it = ctx->pool.pinned.begin(); it != ctx->pool.pinned.end();)
+            it = it->second == g ? ctx->pool.pinned.erase(it) : std::next(it);
+        ctx->graphs.erase(std::remove(ctx->graphs.begin(), ctx->graphs.end(), g), ctx->graphs.end());
+    }
     delete g;
 }
 

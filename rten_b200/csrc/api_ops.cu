@@ -1565,19 +1565,17 @@ rten_status rten_b200_layer_norm(rten_ctx* ctx, const rten_tensor* x, const rten
         long long n = 1;
         for (int i = ax; i < nd; i++) n *= xv.shape[i];
         const long long rows = numel(&xv) / n;
-        // scalar gamma / beta live on the device: expand to a per-element vector so that the kernel needs no
-        // host read (keeps the call asynchronous); arithmetic is identical (gamma[i]*rstd == 1*rstd*gamma ... see below)
-        // NOTE: the reference's scalar-scale arm computes rstd = scale / sqrt(var+eps) and uses it directly; to
-        // stay bit-identical we read the scalar(s) to the host (a tiny synchronous copy) instead of expanding.
+        // scalar gamma / beta stay on the device and are read by the kernel (the reference's scalar-scale arm computes
+        // rstd = scale / sqrt(var + eps), src/ops/norm.rs:456-529): no host read, no synchronisation, capturable
+        const float *gsp = nullptr, *bsp = nullptr;
         if (g_scalar) {
-            RTB_CUDA(ctx, cudaMemcpyAsync(&gs, gp, 4, cudaMemcpyDeviceToHost, rtb::launch_stream(ctx)));
+            gsp = gp;
             gp = nullptr;
         }
         if (bias && b_scalar) {
-            RTB_CUDA(ctx, cudaMemcpyAsync(&bs, bp, 4, cudaMemcpyDeviceToHost, rtb::launch_stream(ctx)));
+            bsp = bp;
             bp = nullptr;
         }
-        if (g_scalar || (bias && b_scalar)) RTB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         rten_tensor yc = ov;
         const bool direct = is_contiguous(&ov);
         if (!direct) {
@@ -1587,7 +1585,7 @@ rten_status rten_b200_layer_norm(rten_ctx* ctx, const rten_tensor* x, const rten
             yc.data = t;
         }
         if (st == RTEN_OK)
-            st = launch_layer_norm(ctx, (const float*)xc.data, (float*)yc.data, rows, (int)n, gp, gs, bp, bs, eps);
+            st = launch_layer_norm(ctx, (const float*)xc.data, (float*)yc.data, rows, (int)n, gp, gs, bp, bs, eps, gsp, bsp);
         if (st == RTEN_OK && !direct) {
             long long shape[RTEN_MAX_DIMS], ss[RTEN_MAX_DIMS], ds[RTEN_MAX_DIMS];
             for (int i = 0; i < nd; i++) {

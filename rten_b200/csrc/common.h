@@ -11,14 +11,21 @@
 #include <map>
 #include <string>
 #include <unordered_map>
+#include <utility>
 #include <vector>
 
 #include "../../include/rten_b200.h"
 
+struct rten_ctx;
 struct rten_graph {
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
     uint64_t kernels = 0;  // kernels captured (added to the launch counter on every replay)
+    // Pool buffers whose raw pointers are baked into the instantiated graph (temporaries and intermediate outputs
+    // allocated or released while capturing).  They stay out of the context's pool until the graph is destroyed:
+    // a later allocation can never alias memory that a replay reads or writes.
+    rten_ctx* ctx = nullptr;  // null once the owning context is gone
+    std::vector<std::pair<void*, size_t>> held;
 };
 
 // Device-side caching allocator, stream-ordered on the context stream
@@ -27,6 +34,12 @@ struct DevicePool {
     std::unordered_map<void*, size_t> live;             // ptr -> bucket size
     std::map<size_t, std::vector<void*>> free_buckets;  // bucket size -> free buffers
     size_t bytes_reserved = 0;
+    // Graph capture: buffers released while capturing are recycled only INSIDE that capture (stream order inside the
+    // graph keeps that safe) and are handed to the rten_graph at graph_end; buffers handed out while capturing that are
+    // still live at graph_end are pinned to the graph and join its `held` list when the caller frees them.
+    std::map<size_t, std::vector<void*>> cap_free;
+    std::unordered_map<void*, size_t> cap_touched;      // every buffer handed out or released during the capture
+    std::unordered_map<void*, rten_graph*> pinned;      // live buffer -> graph whose nodes reference it
 
     static size_t bucket(size_t bytes) {
         if (bytes < 512) bytes = 512;
@@ -45,7 +58,7 @@ struct rten_ctx {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     int num_sms = 148;
-    int f32_mode = RTEN_F32_TF32;
+    int f32_mode = RTEN_F32_TF32X3;  // fp32-grade by default; single-pass TF32 is an explicit opt-in
     uint64_t launches = 0;
     bool capturing = false;
     uint64_t capture_start_launches = 0;
@@ -62,6 +75,8 @@ struct rten_ctx {
     void* seq_gbar = nullptr;      // grid-barrier arrival counter of the sequence kernel
     std::map<std::vector<long long>, std::array<int, 8>> tune_cache;
     size_t tune_loaded = 0;        // entries read from RTEN_B200_TUNE_FILE (the file is rewritten when more exist at destroy)
+    std::vector<rten_graph*> graphs;  // graphs captured on this context that still exist
+    uint64_t forced_hits = 0, forced_misses = 0;  // RTEN_B200_FORCE_* launches that found / did not find a matching plan
 };
 
 namespace rtb {

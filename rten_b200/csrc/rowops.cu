@@ -10,6 +10,7 @@
 
 #include <cfloat>
 #include <cstdint>
+#include <cstdlib>
 
 #include "common.h"
 #include "math.cuh"
@@ -104,6 +105,126 @@ __global__ void __launch_bounds__(256) softmax_kernel(const SoftmaxParams p) {
     }
 }
 
+// -----------------------------------------------------------------------------------------
+// Vectorised softmax: the row lives in registers, ONE pass over global memory (128-bit loads and stores).
+// The reference accumulates the exponentials in 16 SIMD-lane partial sums, lane l owning the elements i = l (mod 16)
+// in ascending i (rten-vecmath/src/softmax.rs:192-228).  A float4 at float4-index f holds lanes 4 (f mod 4) .. + 3, so
+// thread (t0 = f mod 4) owns FOUR of the sixteen chains outright: a row is handled by 4 * S threads, thread (t0, s)
+// holding the float4s f = t0 + 4 (s F + k), k < F -- its own contiguous-in-i piece of its four chains.  Adds inside a
+// thread are sequential in i; segment s starts from segment s - 1's sums (shuffle), which keeps the exact order.
+// Requires n % (16 S) == 0, F = n / (16 S) <= 16, 16-byte aligned rows.
+// -----------------------------------------------------------------------------------------
+template <int S>
+__global__ void __launch_bounds__(256) softmax_vec_kernel(const SoftmaxParams p) {
+    constexpr int LPR = 4 * S;        // threads per row
+    constexpr int RPW = 32 / LPR;     // rows per warp
+    const int lane = threadIdx.x & 31;
+    const int t0 = lane & 3, seg = (lane >> 2) & (S - 1), rw = lane / LPR;
+    const long long warp_id = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long row = warp_id * RPW + rw;
+    const bool live = row < p.rows;
+    const int n = p.n;
+    const int F = n / (16 * S);
+    const long long rr = live ? row : 0;
+    const float4* x4 = reinterpret_cast<const float4*>(p.x + rr * n);
+    float4* y4 = reinterpret_cast<float4*>(p.y + rr * n);
+    const float* m = nullptr;
+    if (p.mask) {
+        long long off = 0;
+        unsigned rem = (unsigned)rr;  // (the launcher keeps rows < 2^31 on this path)
+        for (int d = p.nlead - 1; d >= 0; d--) {
+            const unsigned ld = (unsigned)p.lead[d];
+            const unsigned q = rem / ld;
+            off += (long long)(rem - q * ld) * p.mstride[d];
+            rem = q;
+        }
+        m = p.mask + off;
+    }
+    float4 v[16];
+    float mx = -FLT_MAX;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        if (k < F) {
+            const int f = t0 + 4 * (seg * F + k);
+            float4 a = live ? __ldg(x4 + f) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m) {
+                float4 b;
+                if (p.mstride_last == 1) {
+                    b = __ldg(reinterpret_cast<const float4*>(m) + f);
+                } else {
+                    const long long ms = p.mstride_last;
+                    b = make_float4(__ldg(m + (4LL * f) * ms), __ldg(m + (4LL * f + 1) * ms), __ldg(m + (4LL * f + 2) * ms),
+                                    __ldg(m + (4LL * f + 3) * ms));
+                }
+                a.x = __fadd_rn(a.x, b.x);
+                a.y = __fadd_rn(a.y, b.y);
+                a.z = __fadd_rn(a.z, b.z);
+                a.w = __fadd_rn(a.w, b.w);
+            }
+            v[k] = a;
+            mx = fmaxf(mx, fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w)));
+        }
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        if (k < F) {
+            v[k].x = reduced_range_exp(__fsub_rn(v[k].x, mx));
+            v[k].y = reduced_range_exp(__fsub_rn(v[k].y, mx));
+            v[k].z = reduced_range_exp(__fsub_rn(v[k].z, mx));
+            v[k].w = reduced_range_exp(__fsub_rn(v[k].w, mx));
+        }
+    }
+    // the four chains of this thread, segment after segment
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int sg = 0; sg < S; sg++) {
+        if (sg > 0) {  // continue from the previous segment's running sums
+            const float4 in = make_float4(__shfl_up_sync(0xffffffffu, acc.x, 4), __shfl_up_sync(0xffffffffu, acc.y, 4),
+                                          __shfl_up_sync(0xffffffffu, acc.z, 4), __shfl_up_sync(0xffffffffu, acc.w, 4));
+            if (seg == sg) acc = in;
+        }
+        if (seg == sg) {
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                if (k < F) {
+                    acc.x = __fadd_rn(acc.x, v[k].x);
+                    acc.y = __fadd_rn(acc.y, v[k].y);
+                    acc.z = __fadd_rn(acc.z, v[k].z);
+                    acc.w = __fadd_rn(acc.w, v[k].w);
+                }
+            }
+        }
+    }
+    // lanes summed in order l = 0 .. 15: thread t0 of the LAST segment holds l = 4 t0 .. 4 t0 + 3
+    float s = 0.0f;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const float in = __shfl_up_sync(0xffffffffu, s, 1);
+        if (t0 == q) {
+            if (q > 0) s = in;
+            s = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(s, acc.x), acc.y), acc.z), acc.w);
+        }
+    }
+    s = __shfl_sync(0xffffffffu, s, rw * LPR + (S - 1) * 4 + 3);
+    const float inv = __fdiv_rn(1.0f, s);
+    if (!live) return;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        if (k < F) {
+            float4 o = make_float4(__fmul_rn(v[k].x, inv), __fmul_rn(v[k].y, inv), __fmul_rn(v[k].z, inv), __fmul_rn(v[k].w, inv));
+            if (p.flush_nan) {
+                if (o.x != o.x) o.x = 0.0f;
+                if (o.y != o.y) o.y = 0.0f;
+                if (o.z != o.z) o.z = 0.0f;
+                if (o.w != o.w) o.w = 0.0f;
+            }
+            y4[t0 + 4 * (seg * F + k)] = o;
+        }
+    }
+}
+
 rten_status launch_softmax(rten_ctx* ctx, const float* x, float* y, long long rows, int n, int flush_nan,
                            const float* mask, int nlead, const long long* lead, const long long* mstride,
                            long long mstride_last) {
@@ -122,6 +243,31 @@ rten_status launch_softmax(rten_ctx* ctx, const float* x, float* y, long long ro
     }
     p.mstride_last = mstride_last;
     const int wpb = 8;
+    // register-resident rows, 128-bit accesses: n a multiple of 16 S with n / (16 S) <= 16 float4s per thread
+    int S = 0;
+    for (int c = 1; c <= 8 && !S; c *= 2)
+        if (n % (16 * c) == 0 && n / (16 * c) <= 16) S = c;
+    const bool aligned = (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
+                         (!mask || mstride_last != 1 || (reinterpret_cast<uintptr_t>(mask) & 15) == 0);
+    bool mask_vec_ok = true;  // vector mask loads need every row's mask base 16-byte aligned
+    if (mask && mstride_last == 1)
+        for (int i = 0; i < nlead; i++)
+            if (mstride[i] % 4) mask_vec_ok = false;
+    if (S && aligned && mask_vec_ok && rows < 0x7fffffffLL && !getenv("RTEN_B200_NO_VEC_ROWS")) {
+        const int rpw = 32 / (4 * S);
+        const long long warps = (rows + rpw - 1) / rpw;
+        const unsigned blocks = (unsigned)((warps + wpb - 1) / wpb);
+        switch (S) {
+            case 1: softmax_vec_kernel<1><<<blocks, wpb * 32, 0, launch_stream(ctx)>>>(p); break;
+            case 2: softmax_vec_kernel<2><<<blocks, wpb * 32, 0, launch_stream(ctx)>>>(p); break;
+            case 4: softmax_vec_kernel<4><<<blocks, wpb * 32, 0, launch_stream(ctx)>>>(p); break;
+            default: softmax_vec_kernel<8><<<blocks, wpb * 32, 0, launch_stream(ctx)>>>(p); break;
+        }
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return fail_cuda(ctx, e, "softmax launch");
+        count_launch(ctx);
+        return RTEN_OK;
+    }
     const long long blocks = (rows + wpb - 1) / wpb;
     softmax_kernel<<<(unsigned)blocks, wpb * 32, 0, launch_stream(ctx)>>>(p);
     cudaError_t e = cudaGetLastError();
@@ -178,6 +324,9 @@ struct LayerNormParams {
     const float* beta;  // per element or null
     float beta_scalar;
     float eps;
+    // scalar scale / bias that live on the device (read by the kernel: the call stays asynchronous and capturable)
+    const float* gamma_sp;
+    const float* beta_sp;
 };
 
 __global__ void __launch_bounds__(256) layer_norm_kernel(const LayerNormParams p) {
@@ -187,29 +336,153 @@ __global__ void __launch_bounds__(256) layer_norm_kernel(const LayerNormParams p
     const float* x = p.x + row * p.n;
     float* y = p.y + row * p.n;
     const int n = p.n;
+    const float gamma_scalar = p.gamma_sp ? __ldg(p.gamma_sp) : p.gamma_scalar;
+    const float beta_scalar = p.beta_sp ? __ldg(p.beta_sp) : p.beta_scalar;
     const float mean = __fdiv_rn(simd_fold_unroll4<false>(x, n, 0.0f, lane), (float)n);
     const float var = __fdiv_rn(simd_fold_unroll4<true>(x, n, mean, lane), (float)n);
-    const float rstd = __fdiv_rn(p.gamma_scalar, __fsqrt_rn(__fadd_rn(var, p.eps)));
+    const float rstd = __fdiv_rn(gamma_scalar, __fsqrt_rn(__fadd_rn(var, p.eps)));
     if (!p.gamma && !p.beta) {
-        for (int i = lane; i < n; i += 32) y[i] = __fmaf_rn(__fsub_rn(x[i], mean), rstd, p.beta_scalar);
-    } else if (p.gamma && !p.beta && p.beta_scalar == 0.0f) {
+        for (int i = lane; i < n; i += 32) y[i] = __fmaf_rn(__fsub_rn(x[i], mean), rstd, beta_scalar);
+    } else if (p.gamma && !p.beta && beta_scalar == 0.0f) {
         for (int i = lane; i < n; i += 32) y[i] = __fmul_rn(__fsub_rn(x[i], mean), __fmul_rn(p.gamma[i], rstd));
     } else {
         for (int i = lane; i < n; i += 32) {
             const float sv = __fmul_rn(p.gamma ? p.gamma[i] : 1.0f, rstd);
-            const float bv = __fadd_rn(p.beta ? p.beta[i] : 0.0f, p.beta_scalar);
+            const float bv = __fadd_rn(p.beta ? p.beta[i] : 0.0f, beta_scalar);
             y[i] = __fmaf_rn(__fsub_rn(x[i], mean), sv, bv);
         }
     }
 }
 
+// -----------------------------------------------------------------------------------------
+// Vectorised LayerNormalization: row in registers, one pass over global memory, 128-bit accesses.
+// fold_unroll<4> over 16 lanes = 64 independent chains, chain p owning the elements i = p (mod 64) in ascending i
+// (only full 64-element chunks exist here: n % 64 == 0).  The float4 at index f holds chains 4 (f mod 16) .. + 3:
+// thread (c = f mod 16, segment s) keeps f = c + 16 (s F + k), k < F, and so owns its four chains outright; segment
+// s continues from segment s - 1's sums.  Then acc[0][l] = ((acc[0][l] + acc[1][l]) + acc[2][l]) + acc[3][l] with
+// chain p = 16 u + l, and the 16 lanes are summed in order (rten-vecmath/src/sum.rs:22-35, rten-simd/src/iter.rs:70-120).
+// -----------------------------------------------------------------------------------------
+template <int S, bool SQSUB>
+__device__ __forceinline__ float ln_vec_fold(const float4 (&v)[16], int F, float off, int c, int seg) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int sg = 0; sg < S; sg++) {
+        if (sg > 0) {
+            const float4 in = make_float4(__shfl_up_sync(0xffffffffu, acc.x, 16), __shfl_up_sync(0xffffffffu, acc.y, 16),
+                                          __shfl_up_sync(0xffffffffu, acc.z, 16), __shfl_up_sync(0xffffffffu, acc.w, 16));
+            if (seg == sg) acc = in;
+        }
+        if (seg == sg) {
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                if (k < F) {
+                    acc.x = fold_step<SQSUB>(acc.x, v[k].x, off);
+                    acc.y = fold_step<SQSUB>(acc.y, v[k].y, off);
+                    acc.z = fold_step<SQSUB>(acc.z, v[k].z, off);
+                    acc.w = fold_step<SQSUB>(acc.w, v[k].w, off);
+                }
+            }
+        }
+    }
+    // u = c >> 2 selects the unrolled accumulator, l = 4 (c & 3) + j the lane: threads c, c + 4, c + 8, c + 12 -> thread c (< 4)
+    float4 r = acc;
+#pragma unroll
+    for (int u = 1; u < 4; u++) {
+        r.x = __fadd_rn(r.x, __shfl_down_sync(0xffffffffu, acc.x, 4 * u));
+        r.y = __fadd_rn(r.y, __shfl_down_sync(0xffffffffu, acc.y, 4 * u));
+        r.z = __fadd_rn(r.z, __shfl_down_sync(0xffffffffu, acc.z, 4 * u));
+        r.w = __fadd_rn(r.w, __shfl_down_sync(0xffffffffu, acc.w, 4 * u));
+    }
+    float s = 0.0f;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const float in = __shfl_up_sync(0xffffffffu, s, 1);
+        if (c == q) {
+            if (q > 0) s = in;
+            s = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(s, r.x), r.y), r.z), r.w);
+        }
+    }
+    // thread c = 3 of the row's LAST segment holds the total
+    const int lane = threadIdx.x & 31;
+    const int base = (lane / (16 * S)) * (16 * S);
+    return __shfl_sync(0xffffffffu, s, base + (S - 1) * 16 + 3);
+}
+
+template <int S>
+__global__ void __launch_bounds__(256) layer_norm_vec_kernel(const LayerNormParams p) {
+    constexpr int LPR = 16 * S;
+    constexpr int RPW = 32 / LPR;
+    const int lane = threadIdx.x & 31;
+    const int c = lane & 15, seg = (lane >> 4) & (S - 1), rw = lane / LPR;
+    const long long warp_id = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long row = warp_id * RPW + rw;
+    const bool live = row < p.rows;
+    const int n = p.n;
+    const int F = n / (64 * S);
+    const long long rr = live ? row : 0;
+    const float4* x4 = reinterpret_cast<const float4*>(p.x + rr * n);
+    float4 v[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++)
+        if (k < F) v[k] = __ldg(x4 + c + 16 * (seg * F + k));
+    const float gamma_scalar = p.gamma_sp ? __ldg(p.gamma_sp) : p.gamma_scalar;
+    const float beta_scalar = p.beta_sp ? __ldg(p.beta_sp) : p.beta_scalar;
+    const float mean = __fdiv_rn(ln_vec_fold<S, false>(v, F, 0.0f, c, seg), (float)n);
+    const float var = __fdiv_rn(ln_vec_fold<S, true>(v, F, mean, c, seg), (float)n);
+    const float rstd = __fdiv_rn(gamma_scalar, __fsqrt_rn(__fadd_rn(var, p.eps)));
+    if (!live) return;
+    float4* y4 = reinterpret_cast<float4*>(p.y + rr * n);
+    const float4* g4 = reinterpret_cast<const float4*>(p.gamma);
+    const float4* b4 = reinterpret_cast<const float4*>(p.beta);
+    const int mode = (!p.gamma && !p.beta) ? 0 : ((p.gamma && !p.beta && beta_scalar == 0.0f) ? 1 : 2);
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        if (k < F) {
+            const int f = c + 16 * (seg * F + k);
+            const float4 a = v[k];
+            float4 o;
+            if (mode == 0) {
+                o = make_float4(__fmaf_rn(__fsub_rn(a.x, mean), rstd, beta_scalar), __fmaf_rn(__fsub_rn(a.y, mean), rstd, beta_scalar),
+                                __fmaf_rn(__fsub_rn(a.z, mean), rstd, beta_scalar), __fmaf_rn(__fsub_rn(a.w, mean), rstd, beta_scalar));
+            } else if (mode == 1) {
+                const float4 g = __ldg(g4 + f);
+                o = make_float4(__fmul_rn(__fsub_rn(a.x, mean), __fmul_rn(g.x, rstd)), __fmul_rn(__fsub_rn(a.y, mean), __fmul_rn(g.y, rstd)),
+                                __fmul_rn(__fsub_rn(a.z, mean), __fmul_rn(g.z, rstd)), __fmul_rn(__fsub_rn(a.w, mean), __fmul_rn(g.w, rstd)));
+            } else {
+                const float4 g = p.gamma ? __ldg(g4 + f) : make_float4(1.f, 1.f, 1.f, 1.f);
+                const float4 b = p.beta ? __ldg(b4 + f) : make_float4(0.f, 0.f, 0.f, 0.f);
+                o = make_float4(__fmaf_rn(__fsub_rn(a.x, mean), __fmul_rn(g.x, rstd), __fadd_rn(b.x, beta_scalar)),
+                                __fmaf_rn(__fsub_rn(a.y, mean), __fmul_rn(g.y, rstd), __fadd_rn(b.y, beta_scalar)),
+                                __fmaf_rn(__fsub_rn(a.z, mean), __fmul_rn(g.z, rstd), __fadd_rn(b.z, beta_scalar)),
+                                __fmaf_rn(__fsub_rn(a.w, mean), __fmul_rn(g.w, rstd), __fadd_rn(b.w, beta_scalar)));
+            }
+            y4[f] = o;
+        }
+    }
+}
+
 rten_status launch_layer_norm(rten_ctx* ctx, const float* x, float* y, long long rows, int n, const float* gamma,
-                              float gamma_scalar, const float* beta, float beta_scalar, float eps) {
+                              float gamma_scalar, const float* beta, float beta_scalar, float eps, const float* gamma_sp,
+                              const float* beta_sp) {
     if (rows == 0 || n == 0) return RTEN_OK;
-    LayerNormParams p{x, y, rows, n, gamma, gamma_scalar, beta, beta_scalar, eps};
+    LayerNormParams p{x, y, rows, n, gamma, gamma_scalar, beta, beta_scalar, eps, gamma_sp, beta_sp};
     const int wpb = 8;
-    const long long blocks = (rows + wpb - 1) / wpb;
-    layer_norm_kernel<<<(unsigned)blocks, wpb * 32, 0, launch_stream(ctx)>>>(p);
+    int S = 0;
+    for (int c = 1; c <= 2 && !S; c *= 2)
+        if (n % (64 * c) == 0 && n / (64 * c) <= 16) S = c;
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    if (S && al16(x) && al16(y) && al16(gamma) && al16(beta) && !getenv("RTEN_B200_NO_VEC_ROWS")) {
+        const int rpw = 2 / S;
+        const long long warps = (rows + rpw - 1) / rpw;
+        const unsigned blocks = (unsigned)((warps + wpb - 1) / wpb);
+        if (S == 1)
+            layer_norm_vec_kernel<1><<<blocks, wpb * 32, 0, launch_stream(ctx)>>>(p);
+        else
+            layer_norm_vec_kernel<2><<<blocks, wpb * 32, 0, launch_stream(ctx)>>>(p);
+    } else {
+        const long long blocks = (rows + wpb - 1) / wpb;
+        layer_norm_kernel<<<(unsigned)blocks, wpb * 32, 0, launch_stream(ctx)>>>(p);
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail_cuda(ctx, e, "layer_norm launch");
     count_launch(ctx);

@@ -15,8 +15,10 @@ enum { UNARY_ERF = 0, UNARY_GELU = 1, UNARY_APPROX_GELU = 2, UNARY_RELU = 3 };
 rten_status launch_softmax(rten_ctx* ctx, const float* x, float* y, long long rows, int n, int flush_nan,
                            const float* mask, int nlead, const long long* lead, const long long* mstride,
                            long long mstride_last);
+// gamma_sp / beta_sp: scalar scale / bias resident on the device (then gamma / beta are null and the host scalars unused)
 rten_status launch_layer_norm(rten_ctx* ctx, const float* x, float* y, long long rows, int n, const float* gamma,
-                              float gamma_scalar, const float* beta, float beta_scalar, float eps);
+                              float gamma_scalar, const float* beta, float beta_scalar, float eps,
+                              const float* gamma_sp = nullptr, const float* beta_sp = nullptr);
 // y[row] = Sum(x_row) / n in the reference's Sum order; row r starts at
 // x + (r / rows_inner) * s_outer + (r % rows_inner) * s_inner, elements kstride apart.
 rten_status launch_row_mean(rten_ctx* ctx, const float* x, float* y, long long rows, int n, long long rows_inner,

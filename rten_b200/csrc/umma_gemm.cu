@@ -1757,7 +1757,13 @@ rten_status launch_umma_gemm(rten_ctx* ctx, const GemmLaunch& L) {
                         getenv("RTEN_B200_FORCE_SPLITK") || getenv("RTEN_B200_FORCE_CTA2");
     if (!forced && !ctx->tune_cache.empty()) {  // measured plan on record: no need to enumerate and rank candidates
         auto hit = ctx->tune_cache.find(tune_key(L, q));
-        if (hit != ctx->tune_cache.end()) return launch_plan(ctx, L, q, plan_from_array(hit->second), verbose);
+        if (hit != ctx->tune_cache.end()) {
+            PlanShape ps;
+            if (plan_shape(q, plan_from_array(hit->second), ps)) return launch_plan(ctx, L, q, plan_from_array(hit->second), verbose);
+            // a stale entry (plans file written by another build / geometry): drop it and plan afresh
+            if (verbose) fprintf(stderr, "[umma_gemm] recorded plan no longer valid for this problem: re-planning\n");
+            ctx->tune_cache.erase(hit);
+        }
     }
     std::vector<std::pair<double, Plan>> cands;
     enumerate_plans(q, ctx->num_sms, cands);
@@ -1771,6 +1777,7 @@ rten_status launch_umma_gemm(rten_ctx* ctx, const GemmLaunch& L) {
         const char* fk = getenv("RTEN_B200_FORCE_KATOMS");
         const char* fs = getenv("RTEN_B200_FORCE_SPLITK");
         const char* fc = getenv("RTEN_B200_FORCE_CTA2");
+        bool found = false;
         for (const auto& c : cands) {
             const Plan& x = c.second;
             if (fb && x.bn != atoi(fb)) continue;
@@ -1779,13 +1786,25 @@ rten_status launch_umma_gemm(rten_ctx* ctx, const GemmLaunch& L) {
             if (fs && x.splitk != atoi(fs)) continue;
             if (fc && x.cta2 != (atoi(fc) ? 1 : 0)) continue;
             plan = x;
+            found = true;
             break;
+        }
+        // RTEN_B200_FORCE_STRICT=1 (tests): a forced combination that no valid plan satisfies is an error instead of a
+        // silent fall-back to the model's choice -- a sweep must exercise what it names
+        if (!found) {
+            ctx->forced_misses++;
+            if (verbose) fprintf(stderr, "[umma_gemm] no valid plan matches the forced fields: using the model's choice\n");
+            if (getenv("RTEN_B200_FORCE_STRICT"))
+                return fail(ctx, RTEN_ERR_INVALID_VALUE, "no launch plan matches the forced RTEN_B200_FORCE_* fields");
+        } else {
+            ctx->forced_hits++;
         }
     } else if (ctx->autotune || !ctx->tune_cache.empty()) {
         // measured plans are used whenever they exist; new measurements are only taken while autotuning is on
         const std::vector<long long> key = tune_key(L, q);
         auto it = ctx->tune_cache.find(key);
-        if (it != ctx->tune_cache.end()) {
+        PlanShape ps_hit;
+        if (it != ctx->tune_cache.end() && plan_shape(q, plan_from_array(it->second), ps_hit)) {
             plan = plan_from_array(it->second);
         } else if (ctx->autotune) {
             cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;

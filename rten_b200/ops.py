@@ -68,8 +68,15 @@ class Context:
         self.check(self.lib.rten_b200_sync(self.handle))
 
     def set_f32_mode(self, tf32x3: bool):
-        """False: single-pass TF32 (default).  True: 3xTF32 error-compensated products, ~f32 accuracy at 1/3 of the rate."""
+        """True (the library default): 3xTF32 error-compensated products, f32-grade accuracy at 1/3 of the tensor rate.
+        False: single-pass TF32 -- an explicit opt-in to 10-bit operand mantissas."""
         self.check(self.lib.rten_b200_set_f32_mode(self.handle, 1 if tf32x3 else 0))
+
+    def forced_plan_counts(self):
+        """(matched, unmatched) launches under the RTEN_B200_FORCE_* sweep knobs."""
+        a, b = C.c_uint64(), C.c_uint64()
+        self.check(self.lib.rten_b200_debug_forced_plans(self.handle, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
 
     def set_autotune(self, enable: bool = True):
         """Time candidate launch plans the first time each MatMul / Conv problem is seen (outside graph capture)."""

@@ -12,6 +12,23 @@ import numpy as np
 TF32_REL = 2.0 ** -9
 
 
+def new_ctx(rt, tf32=True):
+    """The library defaults to the fp32-grade 3xTF32 mode; the kernel-variant checks below opt in to the single TF32 pass
+    explicitly (their bound is the TF32 one) unless they test the 3x mode."""
+    ctx = rt.Context(0)
+    ctx.set_f32_mode(not tf32)
+    return ctx
+
+
+def assert_reference_rule(got, want, what):
+    """The reference's own float comparison (rten-tensor/src/test_util.rs:47-92): |a - b| <= 1e-8 + 1e-5 * |b|."""
+    got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+    assert got.shape == want.shape, f"{what}: shape {got.shape} != {want.shape}"
+    bad = np.abs(got - want) > 1e-8 + 1e-5 * np.abs(want)
+    assert not bad.any(), (f"{what}: {int(bad.sum())} of {bad.size} elements outside 1e-8 + 1e-5*|ref| "
+                           f"(worst rel {float((np.abs(got - want) / np.maximum(np.abs(want), 1e-30)).max()):.2e})")
+
+
 def _ulp_diff(a, b):
     a = np.ascontiguousarray(a, np.float32).view(np.int32).astype(np.int64)
     b = np.ascontiguousarray(b, np.float32).view(np.int32).astype(np.int64)
@@ -40,7 +57,7 @@ def assert_tf32_close(got, exact, absum, what, extra_abs=0.0):
 
 # ------------------------------------------------------------------------------------------
 def check_context(rt, oracle):
-    ctx = rt.Context(0)
+    ctx = new_ctx(rt)
     x = oracle.XorShiftRng(1234).f32((3, 5, 7))
     t = ctx.to_device(x)
     assert_bit_exact(t.numpy(), x, "copy roundtrip")
@@ -51,7 +68,7 @@ def check_context(rt, oracle):
 
 
 def check_unary(rt, oracle):
-    ctx = rt.Context(0)
+    ctx = new_ctx(rt)
     x = np.concatenate([np.arange(-6, 6, 0.001, dtype=np.float32), oracle.XorShiftRng(7).uniform((100003,), -10, 10),
                         np.array([0.0, -0.0, np.inf, -np.inf, 1e-30, -88.0, 104.0], np.float32)])
     assert_bit_exact(rt.Erf().run(ctx, x).numpy(), oracle.erf(x), "Erf")
@@ -70,7 +87,7 @@ def check_unary(rt, oracle):
 
 
 def check_softmax(rt, oracle):
-    ctx = rt.Context(0)
+    ctx = new_ctx(rt)
     r = oracle.XorShiftRng(1234)
     for shape, axis in [((6,), 0), ((2, 3), 1), ((2, 3), 0), ((4, 4), 1), ((5, 17), -1), ((3, 4, 130), -1),
                         ((2, 12, 128, 128), -1), ((7, 1000), 1), ((3, 5, 9), 1), ((0, 4), 1), ((2, 2050), -1)]:
@@ -105,7 +122,7 @@ def check_softmax(rt, oracle):
 
 
 def check_layer_norm(rt, oracle):
-    ctx = rt.Context(0)
+    ctx = new_ctx(rt)
     r = oracle.XorShiftRng(1234)
     for shape, axis in [((1, 5, 2), -1), ((1, 5, 2), -2), ((7, 768), -1), ((3, 4, 100), -1), ((2, 3, 64), -1),
                         ((5, 1000), -1), ((4, 15), -1), ((2, 16, 17), 1)]:
@@ -136,7 +153,7 @@ def check_layer_norm(rt, oracle):
 
 
 def check_dql(rt, oracle):
-    ctx = rt.Context(0)
+    ctx = new_ctx(rt)
     r = oracle.XorShiftRng(1234)
     for shape, lo, hi in [((5, 1000), -1.2, 2.8), ((4096, 768), -3, 3), ((3, 7, 11), 0.5, 2.0), ((17,), -5, -1), ((0, 3), 0, 1),
                           ((128, 128), -7, 0.25), ((16385,), -0.5, 9.0)]:  # single-kernel path up to 16384 elements, three kernels above
@@ -161,7 +178,7 @@ def check_dql(rt, oracle):
 
 
 def check_glue(rt, oracle):
-    ctx = rt.Context(0)
+    ctx = new_ctx(rt)
     rr = oracle.XorShiftRng(55)
     table, upd = rr.uniform((40, 12)), rr.uniform((5, 12))
     idx = np.array([3, 39, 0, 17, -2], np.int32)
@@ -218,7 +235,7 @@ def _matmul_case(rt, oracle, ctx, ashape, bshape, bias=False, alpha=None, b_kmaj
 
 
 def check_matmul_small(rt, oracle):
-    ctx = rt.Context(0)
+    ctx = new_ctx(rt)
     a = np.array([[1, 2], [3, 4]], np.float32)
     b = np.array([[5, 6], [7, 8]], np.float32)
     assert_bit_exact(rt.MatMul().run(ctx, a, b).numpy(), np.array([[19, 22], [43, 50]], np.float32), "2x2 f32 (exact in tf32)")
@@ -228,7 +245,7 @@ def check_matmul_small(rt, oracle):
 
 
 def check_matmul_shapes(rt, oracle):
-    ctx = rt.Context(0)
+    ctx = new_ctx(rt)
     worst = 0.0
     cases = [((3, 10), (10, 8)), ((2, 3, 10), (10, 8)), ((3, 10), (2, 10, 8)), ((2, 3, 10), (2, 10, 8)),
              ((2, 1, 3, 10), (1, 4, 10, 8)), ((10,), (10, 8)), ((3, 10), (10,)), ((10,), (10,)),
@@ -260,7 +277,7 @@ def check_matmul_shapes(rt, oracle):
 
 
 def check_matmul_bert(rt, oracle):
-    ctx = rt.Context(0)
+    ctx = new_ctx(rt)
     w = _matmul_case(rt, oracle, ctx, (4, 128, 768), (768, 768), bias=True, prepack=True)
     w = max(w, _matmul_case(rt, oracle, ctx, (512, 768), (768, 3072), bias=True))
     w = max(w, _matmul_case(rt, oracle, ctx, (256, 3072), (3072, 768), prepack=True))
@@ -268,7 +285,7 @@ def check_matmul_bert(rt, oracle):
 
 
 def check_gemm_op(rt, oracle):
-    ctx = rt.Context(0)
+    ctx = new_ctx(rt)
     r = oracle.XorShiftRng(1234)
     worst = 0.0
     for (m, n, k), ta, tb, alpha, beta, cshape in [((3, 8, 10), False, False, 1.0, 1.0, (8,)), ((32, 1000, 2048), False, True, 1.0, 1.0, (1000,)),
@@ -296,7 +313,7 @@ def check_gemm_op(rt, oracle):
 
 # ------------------------------------------------------------------------------------------
 def check_matmul_integer(rt, oracle):
-    ctx = rt.Context(0)
+    ctx = new_ctx(rt)
     A = np.array([[1, 2], [3, 4]], np.uint8)
     B = np.array([[5, 6], [7, 8]], np.int8)
     lit = [(A, B, None, None), (A, B, np.uint8(127), np.int8(-50)), (A, B, np.array([1, 2], np.uint8), np.array([3, 4], np.int8)),
@@ -350,7 +367,7 @@ def check_plans(rt, oracle):
     accumulator stage of 256 x 256 tiles) must give the same answers: forced through the debug environment knobs,
     then chosen by the autotuner."""
     import os
-    ctx = rt.Context(0)
+    ctx = new_ctx(rt)
     r = oracle.XorShiftRng(99)
     keys = ("RTEN_B200_FORCE_BN", "RTEN_B200_FORCE_PAIR", "RTEN_B200_FORCE_KATOMS", "RTEN_B200_FORCE_SPLITK", "RTEN_B200_FORCE_CTA2")
     plans = [dict(), dict(BN=64, PAIR=1, CTA2=0), dict(BN=128, PAIR=0, KATOMS=2, CTA2=0), dict(BN=256, PAIR=1, CTA2=0),
@@ -366,6 +383,7 @@ def check_plans(rt, oracle):
     sc = r.uniform((512,), 0.001, 0.1)
     exp8f = oracle.matmul_integer_to_float(a8, b8, az, bz, sc)
     worst = 0.0
+    hits_before = 0
     try:
         for pl in plans:
             for k in keys:
@@ -380,11 +398,16 @@ def check_plans(rt, oracle):
             worst = max(worst, _conv_case(rt, oracle, ctx, (4, 256, 14, 14), (256, 256, 3, 3), pads=(1, 1, 1, 1), cl=True, prepack=True, act=1))
             worst = max(worst, _conv_case(rt, oracle, ctx, (8, 512, 7, 7), (512, 512, 3, 3), pads=(1, 1, 1, 1), cl=True, residual=True, act=1))
             worst = max(worst, _conv_case(rt, oracle, ctx, (2, 64, 20, 20), (96, 64, 1, 1), cl=False))
+            worst = max(worst, _conv_case(rt, oracle, ctx, (4, 512, 14, 14), (256, 512, 1, 1), cl=True, residual=True, act=1))  # 16 K blocks: split-K / CTA-pair plans exist
+            hit, miss = ctx.forced_plan_counts()
+            if pl:
+                assert hit > hits_before, f"{tag}: no launch of this sweep ran the forced plan ({miss} fell back to the model's choice)"
+            hits_before = hit
     finally:
         for k in keys:
             os.environ.pop(k, None)
     # autotuned plans: first call measures, second call replays the cached plan
-    ctx2 = rt.Context(0)
+    ctx2 = new_ctx(rt)
     ctx2.set_autotune(True)
     for _ in range(2):
         worst = max(worst, _matmul_case(rt, oracle, ctx2, (384, 1024), (1024, 512), bias=True, prepack=True, seed=5))
@@ -409,7 +432,7 @@ def check_sequence(rt, oracle):
 
 
 def _check_sequence(rt, oracle):
-    ctx = rt.Context(0)
+    ctx = new_ctx(rt)
     r = oracle.XorShiftRng(321)
 
     def conv_layer(ci, co, k, res=None, act=1):
@@ -511,7 +534,7 @@ def _conv_case(rt, oracle, ctx, xs, ws, pads=(0, 0, 0, 0), groups=1, strides=(1,
 
 
 def check_conv_basic(rt, oracle):
-    ctx = rt.Context(0)
+    ctx = new_ctx(rt)
     # reference goldens (src/ops/conv.rs:783-839); 1-channel 3x3 goes through the explicit-im2col path
     K = np.array([0.3230, 0.7632, 0.4616, 0.8837, 0.5898, 0.3424, 0.2101, 0.7821, 0.6861], np.float32).reshape(1, 1, 3, 3)
     X = np.array([0.5946, 0.8249, 0.0448, 0.9552, 0.2041, 0.2501, 0.2693, 0.1007, 0.8862], np.float32).reshape(1, 1, 3, 3)
@@ -528,7 +551,7 @@ def check_conv_basic(rt, oracle):
 
 
 def check_conv_stride(rt, oracle):
-    ctx = rt.Context(0)
+    ctx = new_ctx(rt)
     w = _conv_case(rt, oracle, ctx, (2, 32, 12, 12), (24, 32, 3, 3), pads=(1, 1, 1, 1), strides=(2, 2), cl=True)
     w = max(w, _conv_case(rt, oracle, ctx, (2, 64, 14, 14), (32, 64, 1, 1), strides=(2, 2), cl=True))
     w = max(w, _conv_case(rt, oracle, ctx, (1, 32, 13, 11), (8, 32, 3, 2), pads=(0, 1, 2, 0), strides=(2, 1), cl=True))
@@ -537,7 +560,7 @@ def check_conv_stride(rt, oracle):
 
 
 def check_conv_more(rt, oracle):
-    ctx = rt.Context(0)
+    ctx = new_ctx(rt)
     w = 0.0
     w = max(w, _conv_case(rt, oracle, ctx, (2, 8, 9, 7), (6, 4, 3, 2), pads=(0, 1, 2, 0), strides=(2, 1), groups=2))           # grouped, explicit
     w = max(w, _conv_case(rt, oracle, ctx, (2, 64, 9, 7), (12, 32, 3, 3), pads=(1, 1, 1, 1), groups=2, cl=True))                # grouped, implicit
@@ -577,7 +600,7 @@ def check_conv_more(rt, oracle):
 
 
 def check_conv_integer(rt, oracle):
-    ctx = rt.Context(0)
+    ctx = new_ctx(rt)
     rng = oracle.XorShiftRng(1234)
     krng = oracle.XorShiftRng(5678)
     mk = lambda r, s, dt: (r.u8(s).view(np.int8) if dt == np.int8 else r.u8(s))
@@ -622,7 +645,7 @@ def check_conv_integer(rt, oracle):
 def check_conv_integer_fused(rt, oracle):
     """ConvIntegerToFloat with the following Add(bias) / Add(identity) / Relu folded into the epilogue must be
     bit-identical to the separate operators (exact f32 mul, add, add, max), channels-last and NCHW, all plan kinds."""
-    ctx = rt.Context(0)
+    ctx = new_ctx(rt)
     r = oracle.XorShiftRng(77)
     worst = 0
     for (xs, ws, pads, strides, cl) in [((2, 64, 14, 14), (128, 64, 1, 1), (0, 0, 0, 0), (1, 1), True),
@@ -674,7 +697,7 @@ def check_resnet50_int8_model(rt, oracle):
     zero points or with that constant dropped; the f32 classifier on top carries the TF32 tolerance."""
     from rten_b200 import graphs
     import model_ref
-    ctx = rt.Context(0)
+    ctx = new_ctx(rt)
     rng = oracle.XorShiftRng(5678)
     spec = graphs.make_resnet50(lambda s: rng.uniform(s))
     q = graphs.quantize_resnet50(spec)
@@ -700,7 +723,7 @@ def check_gpt2_int8_kvcache(rt, oracle):
     must agree with each other bit for bit."""
     from rten_b200 import graphs
     import model_ref
-    ctx = rt.Context(0)
+    ctx = new_ctx(rt)
     rng = oracle.XorShiftRng(5678)
     spec = graphs.make_gpt2_int8(lambda s: rng.uniform(s), layers=3, vocab=5000, max_pos=128)
     B, T0 = 2, 40
@@ -737,8 +760,7 @@ def check_tf32x3(rt, oracle):
     global TF32_REL
     from rten_b200 import graphs
     import model_ref
-    ctx = rt.Context(0)
-    ctx.set_f32_mode(True)
+    ctx = new_ctx(rt, tf32=False)
     saved = TF32_REL
     TF32_REL = 2.0 ** -18
     try:
@@ -777,8 +799,7 @@ def check_mnist_model(rt, oracle):
     for x in (x1, x5):
         ref = model_ref.mnist_oracle(oracle, w, x)
         for x3, tol in ((False, 1e-2), (True, 5e-5)):
-            ctx = rt.Context(0)
-            ctx.set_f32_mode(x3)
+            ctx = new_ctx(rt, tf32=not x3)
             for fuse in (True, False):
                 got = graphs.MnistRunner(ctx, w, fuse=fuse).run(ctx.to_device(x)).numpy()
                 rel = float(np.abs(got - ref).max() / np.abs(ref).max())
@@ -793,7 +814,7 @@ def check_resnet50_model(rt, oracle):
     so the logits carry ~53 layers of 2^-11-relative operand rounding.  Stated tolerance: max |d| <= 1e-2 * max |ref|."""
     from rten_b200 import graphs
     import model_ref
-    ctx = rt.Context(0)
+    ctx = new_ctx(rt)
     rng = oracle.XorShiftRng(5678)
     spec = graphs.make_resnet50(lambda s: rng.uniform(s))
     x = oracle.XorShiftRng(1234).uniform((2, 3, 224, 224))
@@ -817,7 +838,7 @@ def check_bert_model(rt, oracle):
     keeps activations O(1))."""
     from rten_b200 import graphs
     import model_ref
-    ctx = rt.Context(0)
+    ctx = new_ctx(rt)
     rng = oracle.XorShiftRng(5678)
     spec = graphs.make_bert(lambda s: rng.uniform(s), layers=3)
     ids = (oracle.XorShiftRng(1234).u64(2 * 128) % 30522).astype(np.int32).reshape(2, 128)
@@ -836,6 +857,196 @@ def check_bert_model(rt, oracle):
     return f"max abs err fused {res[0]:.2e} unfused {res[1]:.2e} (|ref| max {float(np.abs(ref).max()):.2f})"
 
 
+# ------------------------------------------------------------------------------------------
+# The reference's own float rule on the reference's own kind of test data
+# ------------------------------------------------------------------------------------------
+def check_reference_rule_f32(rt, oracle):
+    """Library default (3xTF32): MatMul / Gemm / Conv outputs obey the reference's comparison rule
+    |got - oracle| <= 1e-8 + 1e-5 * |oracle| (rten-tensor/src/test_util.rs:47-92) element by element, on the kind of
+    data the reference's tests draw -- XorShiftRng f32 in [0, 1) (rten-gemm/src/tests.rs:336-362, src/ops/conv.rs:1131-1319) --
+    at the reference's sweep sizes and at the BASELINE layer sizes.  (Signed data with cancellation is covered by the
+    sum |a b| bounds of check_tf32x3: no two f32 summation orders agree to 1e-5 of a result that cancels to ~0.)"""
+    ctx = rt.Context(0)  # untouched default mode
+    r = oracle.XorShiftRng(1234)
+    n = 0
+    for (m, k, nn) in [(1, 1, 1), (2, 2, 2), (5, 7, 10), (17, 33, 9), (64, 64, 64), (130, 520, 300), (2048, 768, 768), (32, 2048, 1000)]:
+        a, b = r.f32((m, k)), r.f32((k, nn))
+        assert_reference_rule(rt.MatMul().run(ctx, a, b).numpy(), oracle.matmul(a, b), f"MatMul {m}x{k}x{nn} (reference rule)")
+        n += 1
+    a, b, c = r.f32((40, 96)), r.f32((50, 96)), r.f32((50,))
+    assert_reference_rule(rt.Gemm(0.5, 2.0, False, True).run(ctx, a, b, c).numpy(), oracle.gemm_op(a, b, c, 0.5, 2.0, False, True),
+                          "Gemm alpha/beta/transB (reference rule)")
+    q, kt = r.f32((2, 12, 128, 64)), r.f32((2, 12, 64, 128))
+    assert_reference_rule(rt.FusedMatMul(0.125).run(ctx, q, kt).numpy(), oracle.matmul(q, kt, None, 0.125), "batched QK^T (reference rule)")
+    for xs, ws, pads, st in [((2, 3, 20, 20), (8, 3, 3, 3), (1, 1, 1, 1), (1, 1)), ((2, 64, 56, 56), (64, 64, 3, 3), (1, 1, 1, 1), (1, 1)),
+                             ((2, 256, 14, 14), (1024, 256, 1, 1), (0, 0, 0, 0), (1, 1)), ((2, 128, 28, 28), (128, 128, 3, 3), (1, 1, 1, 1), (2, 2)),
+                             ((1, 3, 64, 64), (16, 3, 7, 7), (3, 3, 3, 3), (2, 2))]:
+        x, w, b = r.f32(xs), r.f32(ws), r.f32((ws[0],))
+        want = oracle.conv(x, w, b, list(pads), 1, st, (1, 1))
+        for cl in (False, True):
+            got = rt.Conv(1, (1, 1), pads, st).run(ctx, ctx.to_device(x, channels_last=cl), w, b).numpy()
+            assert_reference_rule(got, want, f"Conv {xs} * {ws} cl={cl} (reference rule)")
+            n += 1
+    return f"{n} MatMul / Conv cases inside 1e-8 + 1e-5*|ref|"
+
+
+# ------------------------------------------------------------------------------------------
+# Parity at the exact BASELINE sizes, on the graphs bench.py times (autotuned plans, CUDA-graph replay)
+# ------------------------------------------------------------------------------------------
+def _replayed(ctx, fn):
+    """Eager pass (autotunes, warms the pool), then capture + replay: the output of the REPLAY is what is compared."""
+    ctx.set_autotune(True)
+    first = fn()
+    ctx.sync()
+    ctx.set_autotune(False)
+    del first
+    ctx.graph_begin()
+    out = fn()
+    g = ctx.graph_end()
+    if out.dtype == np.float32:
+        out.copy_from(np.full(out.shape, np.nan, np.float32))
+    g.launch()
+    ctx.sync()
+    return out, g
+
+
+def check_resnet50_b32_baseline(rt, oracle):
+    """configs[1] exactly as benched: ResNet-50 fp32, batch 32, autotuned launch plans (split-K, CTA pairs ...), the step
+    replayed from a CUDA graph.  TF32 single pass: logits within 1e-2 * max |ref|; 3xTF32 (library default): within
+    1e-4 * max |ref| and the same arg-max on every image."""
+    from rten_b200 import graphs
+    import model_ref
+    rng = oracle.XorShiftRng(5678)
+    spec = graphs.make_resnet50(lambda s: rng.uniform(s))
+    x = oracle.XorShiftRng(1234).uniform((32, 3, 224, 224))
+    oracle.use_all_cores()
+    ref = model_ref.resnet50_oracle(oracle, spec, x)
+    res = {}
+    for name, tf32, tol in (("tf32", True, 1e-2), ("tf32x3", False, 1e-4)):
+        ctx = new_ctx(rt, tf32=tf32)
+        runner = graphs.ResNet50Runner(ctx, spec, fuse=True)
+        xd = ctx.to_device(x, channels_last=True)
+        out, g = _replayed(ctx, lambda: runner.run(xd))
+        got = out.numpy()
+        rel = float(np.abs(got - ref).max() / np.abs(ref).max())
+        assert got.shape == ref.shape and rel <= tol, f"ResNet-50 b32 ({name}): rel err {rel:.3e} > {tol}"
+        assert (got.argmax(1) == ref.argmax(1)).all(), f"ResNet-50 b32 ({name}): arg-max differs"
+        res[name] = rel
+        del g
+    return f"b32 graph replay: rel err tf32 {res['tf32']:.2e}, tf32x3 {res['tf32x3']:.2e}"
+
+
+def check_bert_b16_baseline(rt, oracle):
+    """configs[2] exactly as benched: BERT-base, 12 layers, batch 16 x seq 128, graph replay.  TF32: hidden states within
+    1e-2 absolute (LayerNorm keeps them O(1)); 3xTF32: within 2e-4."""
+    from rten_b200 import graphs
+    import model_ref
+    rng = oracle.XorShiftRng(5678)
+    spec = graphs.make_bert(lambda s: rng.uniform(s))
+    ids = (oracle.XorShiftRng(1234).u64(16 * 128) % 30522).astype(np.int32).reshape(16, 128)
+    tt = np.zeros((16, 128), np.int32)
+    mask = np.zeros((16, 1, 1, 128), np.float32)
+    oracle.use_all_cores()
+    ref = model_ref.bert_oracle(oracle, spec, ids, tt, mask)
+    res = {}
+    for name, tf32, tol in (("tf32", True, 1e-2), ("tf32x3", False, 2e-4)):
+        ctx = new_ctx(rt, tf32=tf32)
+        runner = graphs.BertRunner(ctx, spec, fuse=True)
+        di, dt, dm = ctx.to_device(ids), ctx.to_device(tt), ctx.to_device(mask)
+        out, g = _replayed(ctx, lambda: runner.run(di, dt, dm))
+        got = out.numpy()
+        err = float(np.abs(got - ref).max())
+        assert got.shape == ref.shape and err <= tol, f"BERT-base b16 x s128 ({name}): max abs err {err:.3e} > {tol}"
+        res[name] = err
+        del g
+    return f"12 layers b16 x s128 graph replay: max abs err tf32 {res['tf32']:.2e}, tf32x3 {res['tf32x3']:.2e}"
+
+
+def check_resnet50_int8_b64_baseline(rt, oracle):
+    """configs[3] exactly as benched: dynamically quantised ResNet-50, batch 64, fused epilogues, graph replay: pooled
+    features BIT-IDENTICAL to the oracle."""
+    from rten_b200 import graphs
+    import model_ref
+    rng = oracle.XorShiftRng(5678)
+    spec = graphs.make_resnet50(lambda s: rng.uniform(s))
+    q = graphs.quantize_resnet50(spec)
+    x = oracle.XorShiftRng(1234).uniform((64, 3, 224, 224))
+    oracle.use_all_cores()
+    ref, ref_feat = model_ref.resnet50_int8_oracle(oracle, q, x)
+    ctx = new_ctx(rt)
+    runner = graphs.ResNet50Int8Runner(ctx, q, fuse=True)
+    xd = ctx.to_device(x, channels_last=True)
+    ctx.set_autotune(True)
+    runner.run(xd, True)
+    ctx.sync()
+    ctx.set_autotune(False)
+    ctx.graph_begin()
+    logits, feat = runner.run(xd, True)
+    g = ctx.graph_end()
+    feat.copy_from(np.zeros(feat.shape, np.float32))
+    g.launch()
+    ctx.sync()
+    assert_bit_exact(feat.numpy(), ref_feat, "ResNet-50 int8 b64 pooled features (graph replay)")
+    rel = float(np.abs(logits.numpy() - ref).max() / np.abs(ref).max())
+    assert rel <= 2e-3, f"ResNet-50 int8 b64 logits: rel err {rel:.3e}"
+    return f"b64 features bit-exact; classifier rel err {rel:.1e}"
+
+
+def check_gpt2_b8_baseline(rt, oracle):
+    """configs[4] exactly as benched: GPT-2 small int8, 12 layers, vocabulary 50257, batch 8: prefill of 512 tokens, then
+    8 decode steps replayed from ONE CUDA graph against the 576-position KV cache.  Last-position logits within
+    2e-2 * max |ref| of the oracle's at every step, greedy tokens equal."""
+    from rten_b200 import graphs
+    import model_ref
+    rng = oracle.XorShiftRng(5678)
+    spec = graphs.make_gpt2_int8(lambda s: rng.uniform(s))
+    B, T0, nd = 8, 512, 8
+    ids = (oracle.XorShiftRng(1).u64(B * (T0 + nd)) % 50257).astype(np.int32).reshape(B, T0 + nd)
+    steps = [ids[:, :T0]] + [ids[:, T0 + i:T0 + i + 1] for i in range(nd)]
+    oracle.use_all_cores()
+    ref = model_ref.gpt2_int8_oracle(oracle, spec, steps)
+    ctx = new_ctx(rt)
+    ctx.set_autotune(True)
+    runner = graphs.GPT2Int8Runner(ctx, spec, B, 576, fuse=True)
+    outs = [runner.forward(steps[0]).numpy()]
+    runner.build_decode_graph()
+    ctx.set_autotune(False)
+    outs += [runner.decode_step(st).numpy().copy() for st in steps[1:]]
+    worst = 0.0
+    for i, (a, r) in enumerate(zip(outs, ref)):
+        rel = float(np.abs(a - r).max() / np.abs(r).max())
+        assert a.shape == r.shape and rel <= 2e-2, f"GPT-2 int8 b8 step {i}: rel err {rel:.3e}"
+        assert (a.argmax(1) == r.argmax(1)).all(), f"GPT-2 int8 b8 step {i}: greedy token differs"
+        worst = max(worst, rel)
+    return f"prefill 512 + {nd} graph-replayed decode steps, worst rel err {worst:.2e}"
+
+
+def check_graph_pool_isolation(rt, oracle):
+    """Buffers a captured graph references (temporaries, intermediate outputs freed after capture) never return to the
+    pool while the graph exists: allocations made AFTER graph_end cannot alias them, so replays stay correct."""
+    ctx = new_ctx(rt)
+    r = oracle.XorShiftRng(77)
+    a, b = r.uniform((256, 384)), r.uniform((384, 320))
+    bias = r.uniform((320,))
+    da, db, dbias = ctx.to_device(a), ctx.to_device(b.T.copy()).permute(1, 0), ctx.to_device(bias)
+    eager = rt.Gelu().run(ctx, rt.FusedMatMul(None).run(ctx, da, db, dbias)).numpy()
+    ctx.graph_begin()
+    mid = rt.FusedMatMul(None).run(ctx, da, db, dbias)   # intermediate: freed right after the capture
+    out = rt.Gelu().run(ctx, mid)
+    g = ctx.graph_end()
+    del mid
+    # grab (and scribble over) everything the pool would hand out in the sizes the graph uses
+    junk = [ctx.to_device(np.full((256, 320), np.nan, np.float32)) for _ in range(6)]
+    junk += [ctx.to_device(np.full((n,), 255, np.uint8)) for n in (512, 4096, 65536, 1 << 20)]
+    for rep in range(2):
+        g.launch()
+        ctx.sync()
+        assert_bit_exact(out.numpy(), eager, f"graph replay {rep} after post-capture allocations")
+        for j in junk[:6]:
+            assert np.isnan(j.numpy()).all(), "a post-capture allocation aliases a buffer the graph writes"
+    return "replays unaffected by post-capture allocations"
+
+
 ALL_CHECKS = [
     ("context", check_context), ("unary", check_unary), ("softmax", check_softmax), ("layer_norm", check_layer_norm),
     ("dql", check_dql), ("glue", check_glue), ("matmul_small", check_matmul_small), ("matmul_shapes", check_matmul_shapes),
@@ -843,4 +1054,7 @@ ALL_CHECKS = [
     ("conv_basic", check_conv_basic), ("conv_stride", check_conv_stride), ("conv_more", check_conv_more),
     ("conv_integer", check_conv_integer), ("plans", check_plans), ("tf32x3", check_tf32x3), ("sequence", check_sequence), ("conv_integer_fused", check_conv_integer_fused),
     ("resnet50_int8_model", check_resnet50_int8_model), ("gpt2_int8_kvcache", check_gpt2_int8_kvcache), ("mnist_model", check_mnist_model), ("resnet50_model", check_resnet50_model), ("bert_model", check_bert_model),
+    ("reference_rule_f32", check_reference_rule_f32), ("graph_pool_isolation", check_graph_pool_isolation),
+    ("resnet50_b32_baseline", check_resnet50_b32_baseline), ("bert_b16_baseline", check_bert_b16_baseline),
+    ("resnet50_int8_b64_baseline", check_resnet50_int8_b64_baseline), ("gpt2_b8_baseline", check_gpt2_b8_baseline),
 ]

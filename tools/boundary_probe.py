@@ -2,6 +2,8 @@
 layer (chained: copy i reads the output of copy i-1 when shapes allow, else the same input), with the sequence kernel on
 and off.  Slope = steady-state time per layer, intercept = graph launch overhead."""
 import os
+
+os.environ.setdefault("RTEN_B200_F32_MODE", "tf32")  # these tools measure the single-pass TF32 kernels unless told otherwise
 import sys
 
 import numpy as np

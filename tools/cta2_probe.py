@@ -1,5 +1,7 @@
 # quick standalone probe of the CTA-pair path (run under `timeout`): small GEMM, forced plan, compare with numpy
 import os, sys, numpy as np
+
+os.environ.setdefault("RTEN_B200_F32_MODE", "tf32")  # these tools measure the single-pass TF32 kernels unless told otherwise
 sys.path.insert(0, os.getcwd())
 os.environ["RTEN_B200_FORCE_CTA2"] = "1"
 os.environ["RTEN_B200_FORCE_BN"] = "128"

@@ -1,5 +1,7 @@
 """One eager pass of the int8 ResNet-50 runner (batch 64) for `ncu --metrics gpu__time_duration.sum` launch lists."""
 import os, sys
+
+os.environ.setdefault("RTEN_B200_F32_MODE", "tf32")  # these tools measure the single-pass TF32 kernels unless told otherwise
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch

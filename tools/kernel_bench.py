@@ -3,6 +3,8 @@ GEMM TFLOP/s (tf32 and int8) and the ResNet-50 / BERT layer shapes.  Also measur
 throughput of the same box as a yardstick.  Output: gpurun_out/kernel_bench.json + a table on stdout."""
 import json
 import os
+
+os.environ.setdefault("RTEN_B200_F32_MODE", "tf32")  # these tools measure the single-pass TF32 kernels unless told otherwise
 import sys
 
 import numpy as np

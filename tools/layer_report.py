@@ -1,6 +1,8 @@
 """Per-launch report of one ResNet-50 (or BERT) pass: tile configuration chosen by the host (RTEN_B200_VERBOSE) next to
 the CUDA-event time of each tensor-core op (graph-less, so tiny ops include launch gaps; use for relative ranking)."""
 import os
+
+os.environ.setdefault("RTEN_B200_F32_MODE", "tf32")  # these tools measure the single-pass TF32 kernels unless told otherwise
 import subprocess
 import sys
 

@@ -1,5 +1,7 @@
 """A few representative tensor-core launches for `ncu --set full` (no CUDA graph, 2 launches each)."""
 import os
+
+os.environ.setdefault("RTEN_B200_F32_MODE", "tf32")  # these tools measure the single-pass TF32 kernels unless told otherwise
 import sys
 
 import numpy as np

@@ -2,6 +2,8 @@
 with the DynamicQuantizeLinear range all-reduced over the ranks (rten_b200.Comm) the gathered pooled features (everything below the f32 classifier) must be
 BIT-IDENTICAL to the unsharded CPU oracle's; without the exchange they are not (each shard would pick its own range)."""
 import os
+
+os.environ.setdefault("RTEN_B200_F32_MODE", "tf32")  # these tools measure the single-pass TF32 kernels unless told otherwise
 import sys
 
 import numpy as np

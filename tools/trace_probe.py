@@ -2,6 +2,8 @@
 epilogue times, to see which hand-off bounds the kernel."""
 import ctypes as C
 import os
+
+os.environ.setdefault("RTEN_B200_F32_MODE", "tf32")  # these tools measure the single-pass TF32 kernels unless told otherwise
 import sys
 
 import numpy as np
