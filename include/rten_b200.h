@@ -199,6 +199,42 @@ rten_status rten_b200_conv_integer_ex(rten_ctx* ctx, const rten_tensor* x, const
                                       const rten_conv_params* params, const rten_tensor* bias, const rten_tensor* residual,
                                       int activation, rten_tensor* out_range_or_null, rten_tensor* out);
 
+/* ---- autoregressive decode path (rten-generate's loop: one token per sequence and step) -------------------------- */
+/* The per-token linear layer of a dynamically quantised transformer as ONE call:
+ *   [LayerNormalization(x, ln_scale, ln_bias, axis -1)] -> DynamicQuantizeLinear -> Mul(x_scale, w_scale) ->
+ *   MatMulIntegerToFloat(x_q, w, x_zp, w_zero_point, scale) -> Add(bias) -> Add(residual) -> activation
+ * -- the node chain `tools/ort-quantize.py` + RTen's fusions (src/optimize/fusions.rs:966-1058) leave around every
+ * MatMul of GPT-2.  x [.., K] f32, w [K, N] i8 | u8 (packed_w = its rten_b200_prepack_b handle), w_scale scalar or [N].
+ * For M = prod(leading dims) <= 16 this is the skinny-M kernel that plays rten-gemm's gemv path
+ * (rten-gemm/src/lib.rs:668-747, kernels simd_generic.rs:795-1129): the weights stream from HBM exactly once, the
+ * quantised activations live in shared memory, nothing else is launched.  Larger M runs the separate operators.  Either
+ * way every stage performs the operators' exactly rounded arithmetic: results are bit-identical to the unfused graph. */
+rten_status rten_b200_quantized_linear(rten_ctx* ctx, const rten_tensor* x, const rten_tensor* ln_scale_or_null,
+                                       const rten_tensor* ln_bias_or_null, float ln_epsilon, const rten_tensor* w,
+                                       const rten_packed* packed_w_or_null, const rten_tensor* w_zero_point_or_null,
+                                       const rten_tensor* w_scale, const rten_tensor* bias_or_null,
+                                       const rten_tensor* residual_or_null, int activation, rten_tensor* out);
+/* Attention (src/ops/attention.rs:645-905, the ONNX `Attention` operator) on 4-D inputs: query [batch, q_heads, q_seq,
+ * head], key / value [batch, kv_heads, total_seq, head] with any strides (a transposed value cache is just a view),
+ * attn_mask float broadcastable to [batch, q_heads, q_seq, total_seq], nonpad_kv_seqlen i32 [batch] = number of valid
+ * key / value positions when the caller manages a right-padded KV cache (`:817-832`; read on the device, so a decode
+ * step stays a fixed launch list).  out [batch, q_heads, q_seq, head]; fully masked rows give zeros (sdpa_head :548-552).
+ * q_seq = 1 (decode) with head size 64 / 128 is ONE kernel: scores, softmax and the value product stream the cache once,
+ * split over the sequence to fill the SMs.  `new_key` / `new_value` [batch, kv_heads, 1, head] (optional) are written
+ * into the caches at position nonpad_kv_seqlen[b] - 1 by the same kernel first (the cache append of rten-generate,
+ * rten-generate/src/generator.rs:858-886, without a separate launch).  Other shapes compose MatMul / Softmax / MatMul. */
+typedef struct {
+    int32_t is_causal;
+    int32_t q_num_heads;  /* informative for 4-D inputs */
+    int32_t kv_num_heads;
+    float scale;          /* <= 0: 1 / sqrt(head size) */
+    float softcap;        /* > 0 unsupported */
+} rten_attention_params;
+rten_status rten_b200_attention(rten_ctx* ctx, const rten_tensor* query, const rten_tensor* key, const rten_tensor* value,
+                                const rten_tensor* attn_mask_or_null, const rten_tensor* nonpad_kv_seqlen_or_null,
+                                const rten_attention_params* params, const rten_tensor* new_key_or_null,
+                                const rten_tensor* new_value_or_null, rten_tensor* out);
+
 /* Softmax (src/ops/norm.rs:825-899) and AddSoftmax (src/ops/attention.rs:30-165) when mask != NULL
  * (mask broadcast to x, added lane-wise before the softmax over `axis`; AddSoftmax uses axis -1).
  * `out` may alias `x` (= run_in_place). */

@@ -5,7 +5,7 @@ The product is `librten_b200.so` (hand-written CUDA behind the C ABI in include/
 runners and bench.py.  There is no CPU implementation in this package."""
 from . import _lib  # noqa: F401
 from .ops import (  # noqa: F401
-    ACT_GELU, ACT_GELU_TANH, ACT_NONE, ACT_RELU, Add, AddSoftmax, Comm, Context, Conv, ConvInteger, ConvIntegerToFloat,
+    ACT_GELU, ACT_GELU_TANH, ACT_NONE, ACT_RELU, Add, AddSoftmax, Attention, Comm, Context, Conv, ConvInteger, ConvIntegerToFloat,
     DeviceTensor, DynamicQuantizeLinear, Erf, FusedMatMul, GatherRows, Gelu, Gemm, GlobalAveragePool,
-    LayerNormalization, MatMul, MatMulInteger, MatMulIntegerToFloat, MaxPool, Mul, OpError, Packed, Relu, ScatterRows, Softmax, from_torch,
+    LayerNormalization, MatMul, MatMulInteger, MatMulIntegerToFloat, MaxPool, Mul, OpError, Packed, QuantizedLinear, Relu, ScatterRows, Softmax, from_torch,
 )

@@ -44,6 +44,11 @@ class RtenConvParams(C.Structure):
     ]
 
 
+class RtenAttentionParams(C.Structure):
+    _fields_ = [("is_causal", C.c_int32), ("q_num_heads", C.c_int32), ("kv_num_heads", C.c_int32), ("scale", C.c_float),
+                ("softcap", C.c_float)]
+
+
 _TP = C.POINTER(RtenTensor)
 _vp = C.c_void_p
 
@@ -80,6 +85,8 @@ _SIGNATURES = {
     "rten_b200_conv2d": (C.c_int, [_vp, _TP, _TP, _vp, _TP, C.POINTER(RtenConvParams), _TP]),
     "rten_b200_conv2d_ex": (C.c_int, [_vp, _TP, _TP, _vp, _TP, C.POINTER(RtenConvParams), _TP, C.c_int, _TP]),
     "rten_b200_conv_integer": (C.c_int, [_vp, _TP, _TP, _vp, _TP, _TP, _TP, C.POINTER(RtenConvParams), _TP]),
+    "rten_b200_quantized_linear": (C.c_int, [_vp, _TP, _TP, _TP, C.c_float, _TP, _vp, _TP, _TP, _TP, _TP, C.c_int, _TP]),
+    "rten_b200_attention": (C.c_int, [_vp, _TP, _TP, _TP, _TP, _TP, C.POINTER(RtenAttentionParams), _TP, _TP, _TP]),
     "rten_b200_softmax": (C.c_int, [_vp, _TP, _TP, C.c_int, C.c_int, _TP]),
     "rten_b200_layer_norm": (C.c_int, [_vp, _TP, _TP, _TP, C.c_int, C.c_float, _TP]),
     "rten_b200_erf": (C.c_int, [_vp, _TP, _TP]),

@@ -313,6 +313,7 @@ void rten_b200_ctx_destroy(rten_ctx* ctx) {
     if (const char* tf = getenv("RTEN_B200_TUNE_FILE"))
         if (ctx->tune_cache.size() > ctx->tune_loaded) tune_cache_save(ctx, tf);
     if (ctx->sk_counters) cudaFree(ctx->sk_counters);
+    if (ctx->attn_cnt) cudaFree(ctx->attn_cnt);
     seq_free(ctx);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;

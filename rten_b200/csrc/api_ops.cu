@@ -10,21 +10,10 @@
 
 #include "api_util.h"
 #include "rowops.h"
+#include "skinny.h"
 #include "umma_gemm.h"
 
 using namespace rtb;
-
-struct rten_packed {
-    int kind = 0;   // 0: MatMul B, 1: Conv weight
-    int dtype = RTEN_F32;
-    // matmul: B [K, N] stored K-major as [N, ld]
-    int64_t K = 0, N = 0, ld = 0;
-    // conv: [O, kh*kw, Cg] (K-major, pitch per tap = Cg)
-    int64_t O = 0, Cg = 0, kh = 0, kw = 0;
-    int groups = 1;
-    void* data = nullptr;
-    int32_t* colsum = nullptr;  // int8: sum over K per output column / channel
-};
 
 namespace {
 
@@ -382,9 +371,37 @@ rten_status matmul_core(OpScope& sc, MatMulArgs& A, rten_tensor* out) {
                 L.epi.rowsum = rs;
             }
         }
+        // M <= 32 f32 rows: the HBM-streaming skinny kernel (exact f32 FMA arithmetic) instead of a 128-row MMA tile
+        // (rten-gemm's gemv path, rten-gemm/src/lib.rs:668-747)
+        if (A.kind == 0 && L.z0 == 1 && L.z1 == 1 && L.M <= 32 && L.epi.s_col == 1 && L.epi.bias_kind != 2 &&
+            (!L.epi.r || L.epi.r_col == 1) && !L.epi.range && L.a.strides[0] == 1 && L.b.strides[0] == 1) {
+            SkinnyF32Launch S;
+            S.a = (const float*)L.a.base;
+            S.as = L.a.strides[1];
+            S.b = (const float*)L.b.base;
+            S.bs = L.b.strides[1];
+            S.M = L.M;
+            S.N = L.N;
+            S.K = L.K;
+            S.alpha = L.epi.alpha;
+            S.bias = L.epi.bias_kind == 1 ? L.epi.bias : nullptr;
+            S.residual = L.epi.r;
+            S.rs = L.epi.r_row;
+            S.r_scale = L.epi.r_scale;
+            S.act = L.epi.act;
+            S.out = (float*)L.epi.d;
+            S.os = L.epi.s_row;
+            if (skinny_f32_supported(S)) {
+                RTB_TRY(launch_skinny_f32(ctx, S));
+                goto launched;
+            }
+        }
+        {
         rten_status st = launch_umma_gemm(ctx, L);
         if (st == RTEN_ERR_UNSUPPORTED_VALUE) return fail(ctx, st, "GEMM operands are not addressable by TMA after packing");
         RTB_TRY(st);
+        }
+    launched:;
     }
     if (copy_out) {
         long long shape[RTEN_MAX_DIMS], ss[RTEN_MAX_DIMS], ds[RTEN_MAX_DIMS];

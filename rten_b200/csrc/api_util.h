@@ -5,6 +5,18 @@
 
 #include "common.h"
 
+struct rten_packed {
+    int kind = 0;   // 0: MatMul B, 1: Conv weight
+    int dtype = RTEN_F32;
+    // matmul: B [K, N] stored K-major as [N, ld]
+    int64_t K = 0, N = 0, ld = 0;
+    // conv: [O, kh*kw, Cg] (K-major, pitch per tap = Cg)
+    int64_t O = 0, Cg = 0, kh = 0, kw = 0;
+    int groups = 1;
+    void* data = nullptr;
+    int32_t* colsum = nullptr;  // int8: sum over K per output column / channel
+};
+
 namespace rtb {
 
 struct OpScope {

@@ -76,6 +76,8 @@ struct rten_ctx {
     std::map<std::vector<long long>, std::array<int, 8>> tune_cache;
     size_t tune_loaded = 0;        // entries read from RTEN_B200_TUNE_FILE (the file is rewritten when more exist at destroy)
     std::vector<rten_graph*> graphs;  // graphs captured on this context that still exist
+    void* attn_cnt = nullptr;      // arrival counters of the split single-query attention kernel (zero between launches)
+    int attn_cnt_len = 0;
     uint64_t forced_hits = 0, forced_misses = 0;  // RTEN_B200_FORCE_* launches that found / did not find a matching plan
 };
 

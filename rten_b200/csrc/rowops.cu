@@ -14,6 +14,7 @@
 
 #include "common.h"
 #include "math.cuh"
+#include "rowmath.cuh"
 #include "rowops.h"
 
 namespace rtb {
@@ -114,8 +115,8 @@ __global__ void __launch_bounds__(256) softmax_kernel(const SoftmaxParams p) {
 // thread are sequential in i; segment s starts from segment s - 1's sums (shuffle), which keeps the exact order.
 // Requires n % (16 S) == 0, F = n / (16 S) <= 16, 16-byte aligned rows.
 // -----------------------------------------------------------------------------------------
-template <int S>
-__global__ void __launch_bounds__(256) softmax_vec_kernel(const SoftmaxParams p) {
+template <int S, int FMAX>
+__global__ void __launch_bounds__(128) softmax_vec_kernel(const SoftmaxParams p) {
     constexpr int LPR = 4 * S;        // threads per row
     constexpr int RPW = 32 / LPR;     // rows per warp
     const int lane = threadIdx.x & 31;
@@ -132,18 +133,21 @@ __global__ void __launch_bounds__(256) softmax_vec_kernel(const SoftmaxParams p)
     if (p.mask) {
         long long off = 0;
         unsigned rem = (unsigned)rr;  // (the launcher keeps rows < 2^31 on this path)
-        for (int d = p.nlead - 1; d >= 0; d--) {
-            const unsigned ld = (unsigned)p.lead[d];
-            const unsigned q = rem / ld;
-            off += (long long)(rem - q * ld) * p.mstride[d];
-            rem = q;
+#pragma unroll
+        for (int d = 3; d >= 0; d--) {  // (static indices: the parameter arrays stay in the constant bank)
+            if (d < p.nlead) {
+                const unsigned ld = (unsigned)p.lead[d];
+                const unsigned q = rem / ld;
+                off += (long long)(rem - q * ld) * p.mstride[d];
+                rem = q;
+            }
         }
         m = p.mask + off;
     }
-    float4 v[16];
+    float4 v[FMAX];
     float mx = -FLT_MAX;
 #pragma unroll
-    for (int k = 0; k < 16; k++) {
+    for (int k = 0; k < FMAX; k++) {
         if (k < F) {
             const int f = t0 + 4 * (seg * F + k);
             float4 a = live ? __ldg(x4 + f) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -168,7 +172,7 @@ __global__ void __launch_bounds__(256) softmax_vec_kernel(const SoftmaxParams p)
 #pragma unroll
     for (int o = LPR / 2; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
 #pragma unroll
-    for (int k = 0; k < 16; k++) {
+    for (int k = 0; k < FMAX; k++) {
         if (k < F) {
             v[k].x = reduced_range_exp(__fsub_rn(v[k].x, mx));
             v[k].y = reduced_range_exp(__fsub_rn(v[k].y, mx));
@@ -187,7 +191,7 @@ __global__ void __launch_bounds__(256) softmax_vec_kernel(const SoftmaxParams p)
         }
         if (seg == sg) {
 #pragma unroll
-            for (int k = 0; k < 16; k++) {
+            for (int k = 0; k < FMAX; k++) {
                 if (k < F) {
                     acc.x = __fadd_rn(acc.x, v[k].x);
                     acc.y = __fadd_rn(acc.y, v[k].y);
@@ -211,7 +215,7 @@ __global__ void __launch_bounds__(256) softmax_vec_kernel(const SoftmaxParams p)
     const float inv = __fdiv_rn(1.0f, s);
     if (!live) return;
 #pragma unroll
-    for (int k = 0; k < 16; k++) {
+    for (int k = 0; k < FMAX; k++) {
         if (k < F) {
             float4 o = make_float4(__fmul_rn(v[k].x, inv), __fmul_rn(v[k].y, inv), __fmul_rn(v[k].z, inv), __fmul_rn(v[k].w, inv));
             if (p.flush_nan) {
@@ -243,10 +247,16 @@ rten_status launch_softmax(rten_ctx* ctx, const float* x, float* y, long long ro
     }
     p.mstride_last = mstride_last;
     const int wpb = 8;
-    // register-resident rows, 128-bit accesses: n a multiple of 16 S with n / (16 S) <= 16 float4s per thread
+    // register-resident rows, 128-bit accesses: n a multiple of 16 S with F = n / (16 S) <= 16 float4s per thread.
+    // More segments (threads per row) when the rows alone would not give every SM enough warps to hide the latency
+    // of its one burst of loads.
     int S = 0;
-    for (int c = 1; c <= 8 && !S; c *= 2)
-        if (n % (16 * c) == 0 && n / (16 * c) <= 16) S = c;
+    for (int c = 1; c <= 8; c *= 2) {
+        if (n % (16 * c) != 0 || n / (16 * c) > 16) continue;
+        S = c;
+        const long long warps = (rows * 4 * c + 31) / 32;
+        if (warps >= 32LL * ctx->num_sms || n / (16 * c) <= 2) break;
+    }
     const bool aligned = (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
                          (!mask || mstride_last != 1 || (reinterpret_cast<uintptr_t>(mask) & 15) == 0);
     bool mask_vec_ok = true;  // vector mask loads need every row's mask base 16-byte aligned
@@ -255,14 +265,21 @@ rten_status launch_softmax(rten_ctx* ctx, const float* x, float* y, long long ro
             if (mstride[i] % 4) mask_vec_ok = false;
     if (S && aligned && mask_vec_ok && rows < 0x7fffffffLL && !getenv("RTEN_B200_NO_VEC_ROWS")) {
         const int rpw = 32 / (4 * S);
+        const int vwpb = 4;
         const long long warps = (rows + rpw - 1) / rpw;
-        const unsigned blocks = (unsigned)((warps + wpb - 1) / wpb);
-        switch (S) {
-            case 1: softmax_vec_kernel<1><<<blocks, wpb * 32, 0, launch_stream(ctx)>>>(p); break;
-            case 2: softmax_vec_kernel<2><<<blocks, wpb * 32, 0, launch_stream(ctx)>>>(p); break;
-            case 4: softmax_vec_kernel<4><<<blocks, wpb * 32, 0, launch_stream(ctx)>>>(p); break;
-            default: softmax_vec_kernel<8><<<blocks, wpb * 32, 0, launch_stream(ctx)>>>(p); break;
+        const unsigned blocks = (unsigned)((warps + vwpb - 1) / vwpb);
+        const int F = n / (16 * S);
+        const int fm = F <= 2 ? 2 : (F <= 4 ? 4 : (F <= 8 ? 8 : 16));
+        cudaStream_t st = launch_stream(ctx);
+#define RTB_SOFTMAX_CASE(SS, FF) \
+    case SS * 100 + FF: softmax_vec_kernel<SS, FF><<<blocks, vwpb * 32, 0, st>>>(p); break;
+        switch (S * 100 + fm) {
+            RTB_SOFTMAX_CASE(1, 2) RTB_SOFTMAX_CASE(1, 4) RTB_SOFTMAX_CASE(1, 8) RTB_SOFTMAX_CASE(1, 16)
+            RTB_SOFTMAX_CASE(2, 2) RTB_SOFTMAX_CASE(2, 4) RTB_SOFTMAX_CASE(2, 8) RTB_SOFTMAX_CASE(2, 16)
+            RTB_SOFTMAX_CASE(4, 2) RTB_SOFTMAX_CASE(4, 4) RTB_SOFTMAX_CASE(4, 8) RTB_SOFTMAX_CASE(4, 16)
+            RTB_SOFTMAX_CASE(8, 2) RTB_SOFTMAX_CASE(8, 4) RTB_SOFTMAX_CASE(8, 8) RTB_SOFTMAX_CASE(8, 16)
         }
+#undef RTB_SOFTMAX_CASE
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return fail_cuda(ctx, e, "softmax launch");
         count_launch(ctx);
@@ -281,15 +298,6 @@ rten_status launch_softmax(rten_ctx* ctx, const float* x, float* y, long long ro
 // fold_unroll<4> with V=16: position p = i % 64 owns accumulator (u = p / 16, l = p % 16) for the
 // full 64-element chunks; thread t owns p = t and p = t + 32.
 // =========================================================================================
-template <bool SQSUB>
-__device__ __forceinline__ float fold_step(float acc, float x, float off) {
-    if (SQSUB) {
-        const float d = __fsub_rn(x, off);
-        return __fmaf_rn(d, d, acc);
-    }
-    return __fadd_rn(acc, x);
-}
-
 template <bool SQSUB>
 __device__ __forceinline__ float simd_fold_unroll4(const float* x, int n, float off, int lane) {
     float a0 = 0.0f, a1 = 0.0f;
@@ -362,54 +370,8 @@ __global__ void __launch_bounds__(256) layer_norm_kernel(const LayerNormParams p
 // s continues from segment s - 1's sums.  Then acc[0][l] = ((acc[0][l] + acc[1][l]) + acc[2][l]) + acc[3][l] with
 // chain p = 16 u + l, and the 16 lanes are summed in order (rten-vecmath/src/sum.rs:22-35, rten-simd/src/iter.rs:70-120).
 // -----------------------------------------------------------------------------------------
-template <int S, bool SQSUB>
-__device__ __forceinline__ float ln_vec_fold(const float4 (&v)[16], int F, float off, int c, int seg) {
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int sg = 0; sg < S; sg++) {
-        if (sg > 0) {
-            const float4 in = make_float4(__shfl_up_sync(0xffffffffu, acc.x, 16), __shfl_up_sync(0xffffffffu, acc.y, 16),
-                                          __shfl_up_sync(0xffffffffu, acc.z, 16), __shfl_up_sync(0xffffffffu, acc.w, 16));
-            if (seg == sg) acc = in;
-        }
-        if (seg == sg) {
-#pragma unroll
-            for (int k = 0; k < 16; k++) {
-                if (k < F) {
-                    acc.x = fold_step<SQSUB>(acc.x, v[k].x, off);
-                    acc.y = fold_step<SQSUB>(acc.y, v[k].y, off);
-                    acc.z = fold_step<SQSUB>(acc.z, v[k].z, off);
-                    acc.w = fold_step<SQSUB>(acc.w, v[k].w, off);
-                }
-            }
-        }
-    }
-    // u = c >> 2 selects the unrolled accumulator, l = 4 (c & 3) + j the lane: threads c, c + 4, c + 8, c + 12 -> thread c (< 4)
-    float4 r = acc;
-#pragma unroll
-    for (int u = 1; u < 4; u++) {
-        r.x = __fadd_rn(r.x, __shfl_down_sync(0xffffffffu, acc.x, 4 * u));
-        r.y = __fadd_rn(r.y, __shfl_down_sync(0xffffffffu, acc.y, 4 * u));
-        r.z = __fadd_rn(r.z, __shfl_down_sync(0xffffffffu, acc.z, 4 * u));
-        r.w = __fadd_rn(r.w, __shfl_down_sync(0xffffffffu, acc.w, 4 * u));
-    }
-    float s = 0.0f;
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-        const float in = __shfl_up_sync(0xffffffffu, s, 1);
-        if (c == q) {
-            if (q > 0) s = in;
-            s = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(s, r.x), r.y), r.z), r.w);
-        }
-    }
-    // thread c = 3 of the row's LAST segment holds the total
-    const int lane = threadIdx.x & 31;
-    const int base = (lane / (16 * S)) * (16 * S);
-    return __shfl_sync(0xffffffffu, s, base + (S - 1) * 16 + 3);
-}
-
-template <int S>
-__global__ void __launch_bounds__(256) layer_norm_vec_kernel(const LayerNormParams p) {
+template <int S, int FMAX>
+__global__ void __launch_bounds__(128) layer_norm_vec_kernel(const LayerNormParams p) {
     constexpr int LPR = 16 * S;
     constexpr int RPW = 32 / LPR;
     const int lane = threadIdx.x & 31;
@@ -421,14 +383,14 @@ __global__ void __launch_bounds__(256) layer_norm_vec_kernel(const LayerNormPara
     const int F = n / (64 * S);
     const long long rr = live ? row : 0;
     const float4* x4 = reinterpret_cast<const float4*>(p.x + rr * n);
-    float4 v[16];
+    float4 v[FMAX];
 #pragma unroll
-    for (int k = 0; k < 16; k++)
+    for (int k = 0; k < FMAX; k++)
         if (k < F) v[k] = __ldg(x4 + c + 16 * (seg * F + k));
     const float gamma_scalar = p.gamma_sp ? __ldg(p.gamma_sp) : p.gamma_scalar;
     const float beta_scalar = p.beta_sp ? __ldg(p.beta_sp) : p.beta_scalar;
-    const float mean = __fdiv_rn(ln_vec_fold<S, false>(v, F, 0.0f, c, seg), (float)n);
-    const float var = __fdiv_rn(ln_vec_fold<S, true>(v, F, mean, c, seg), (float)n);
+    const float mean = __fdiv_rn(ln_vec_fold<S, false, FMAX>(v, F, 0.0f, c, seg), (float)n);
+    const float var = __fdiv_rn(ln_vec_fold<S, true, FMAX>(v, F, mean, c, seg), (float)n);
     const float rstd = __fdiv_rn(gamma_scalar, __fsqrt_rn(__fadd_rn(var, p.eps)));
     if (!live) return;
     float4* y4 = reinterpret_cast<float4*>(p.y + rr * n);
@@ -436,7 +398,7 @@ __global__ void __launch_bounds__(256) layer_norm_vec_kernel(const LayerNormPara
     const float4* b4 = reinterpret_cast<const float4*>(p.beta);
     const int mode = (!p.gamma && !p.beta) ? 0 : ((p.gamma && !p.beta && beta_scalar == 0.0f) ? 1 : 2);
 #pragma unroll
-    for (int k = 0; k < 16; k++) {
+    for (int k = 0; k < FMAX; k++) {
         if (k < F) {
             const int f = c + 16 * (seg * F + k);
             const float4 a = v[k];
@@ -467,18 +429,31 @@ rten_status launch_layer_norm(rten_ctx* ctx, const float* x, float* y, long long
     if (rows == 0 || n == 0) return RTEN_OK;
     LayerNormParams p{x, y, rows, n, gamma, gamma_scalar, beta, beta_scalar, eps, gamma_sp, beta_sp};
     const int wpb = 8;
+    // 16 S lanes per row, F = n / (64 S) <= 16 float4s per thread; two segments per row when that is possible and the
+    // rows alone would leave the SMs short of warps
     int S = 0;
-    for (int c = 1; c <= 2 && !S; c *= 2)
-        if (n % (64 * c) == 0 && n / (64 * c) <= 16) S = c;
+    for (int c = 1; c <= 2; c *= 2) {
+        if (n % (64 * c) != 0 || n / (64 * c) > 16) continue;
+        S = c;
+        const long long warps = (rows * 16 * c + 31) / 32;
+        if (warps >= 32LL * ctx->num_sms) break;
+    }
     auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
     if (S && al16(x) && al16(y) && al16(gamma) && al16(beta) && !getenv("RTEN_B200_NO_VEC_ROWS")) {
         const int rpw = 2 / S;
+        const int vwpb = 4;
         const long long warps = (rows + rpw - 1) / rpw;
-        const unsigned blocks = (unsigned)((warps + wpb - 1) / wpb);
-        if (S == 1)
-            layer_norm_vec_kernel<1><<<blocks, wpb * 32, 0, launch_stream(ctx)>>>(p);
-        else
-            layer_norm_vec_kernel<2><<<blocks, wpb * 32, 0, launch_stream(ctx)>>>(p);
+        const unsigned blocks = (unsigned)((warps + vwpb - 1) / vwpb);
+        const int F = n / (64 * S);
+        const int fm = F <= 4 ? 4 : (F <= 8 ? 8 : (F <= 12 ? 12 : 16));
+        cudaStream_t st = launch_stream(ctx);
+#define RTB_LN_CASE(SS, FF) \
+    case SS * 100 + FF: layer_norm_vec_kernel<SS, FF><<<blocks, vwpb * 32, 0, st>>>(p); break;
+        switch (S * 100 + fm) {
+            RTB_LN_CASE(1, 4) RTB_LN_CASE(1, 8) RTB_LN_CASE(1, 12) RTB_LN_CASE(1, 16)
+            RTB_LN_CASE(2, 4) RTB_LN_CASE(2, 8) RTB_LN_CASE(2, 12) RTB_LN_CASE(2, 16)
+        }
+#undef RTB_LN_CASE
     } else {
         const long long blocks = (rows + wpb - 1) / wpb;
         layer_norm_kernel<<<(unsigned)blocks, wpb * 32, 0, launch_stream(ctx)>>>(p);
@@ -807,12 +782,6 @@ rten_status launch_add_flat(rten_ctx* ctx, const float* a, const float* b, float
 //   pass 1: min / max  (order independent) -> 2 floats (ordered-int atomics)
 //   pass 2: scale, zero point (every thread recomputes the 6 scalar ops) + quantise
 // =========================================================================================
-__device__ __forceinline__ int float_to_ordered(float f) {
-    int i = __float_as_int(f);
-    return i >= 0 ? i : i ^ 0x7fffffff;
-}
-__device__ __forceinline__ float ordered_to_float(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
-
 __global__ void minmax_init_kernel(int* mm) {
     mm[0] = float_to_ordered(__int_as_float(0x7f800000));  // +inf
     mm[1] = float_to_ordered(__int_as_float(0xff800000));  // -inf
@@ -851,28 +820,6 @@ __global__ void __launch_bounds__(256) minmax_kernel(const float* __restrict__ x
         atomicMin(&mm[0], float_to_ordered(lo));
         atomicMax(&mm[1], float_to_ordered(hi));
     }
-}
-
-__device__ __forceinline__ void dql_params(const int* mm, float& scale, float& inv_scale, int& zp) {
-    const float x_min = ordered_to_float(mm[0]), x_max = ordered_to_float(mm[1]);
-    const float lo = fminf(x_min, 0.0f), hi = fmaxf(x_max, 0.0f);
-    scale = __fdiv_rn(__fsub_rn(hi, lo), 255.0f);
-    const float min_scaled = __fdiv_rn(lo, scale);
-    float z = __fsub_rn(0.0f, min_scaled);
-    z = fminf(fmaxf(z, 0.0f), 255.0f);  // clamp (NaN -> 0 after the cast below)
-    z = rintf(z);                       // round_ties_even
-    zp = (z != z) ? 0 : (int)z;
-    inv_scale = __fdiv_rn(1.0f, scale);
-}
-
-__device__ __forceinline__ int rne_i32_x86(float v) {
-    if (!(v >= -2147483648.0f && v < 2147483648.0f)) return (int)0x80000000;
-    return __float2int_rn(v);
-}
-__device__ __forceinline__ uint8_t quant1(float x, float inv_scale, int zp) {
-    long long q = (long long)rne_i32_x86(__fmul_rn(x, inv_scale)) + zp;
-    q = q < 0 ? 0 : (q > 255 ? 255 : q);
-    return (uint8_t)q;
 }
 
 __global__ void __launch_bounds__(256)

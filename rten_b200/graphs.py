@@ -644,7 +644,12 @@ class GPT2Int8Runner:
     # write, additive mask); attention always runs over the whole cache length with the not-yet-written positions
     # masked to -inf (their probabilities are exactly 0, so the result equals the exact-length computation), and the
     # K / V append is a ScatterRows whose row indices are data.  A step is then a fixed launch list.
-    def build_decode_graph(self):
+    def build_decode_graph(self, fused: bool = True):
+        """`fused=True` (default): the decode step is 5 launches per layer -- rten_b200_quantized_linear x 4 (LayerNorm,
+        DynamicQuantizeLinear, the int8 vector-matrix products and their epilogues in the skinny-M kernel) and ONE
+        rten_b200_attention (cache append + single-query attention over the cache, valid length read from the device).
+        `fused=False`: the separate operators (ScatterRows append, fixed-length masked attention through MatMul)."""
+        self._fused_decode = fused
         ctx, s, B, M = self.ctx, self.spec, self.B, self.max_seq
         H, nh = s.hidden, s.heads
         dh = H // nh
@@ -658,6 +663,8 @@ class GPT2Int8Runner:
         mask[..., :self.past] = 0.0
         self._g_mask = ctx.to_device(mask)
         self._g_logits = ctx.empty((B, s.lm_head.wq.shape[1]))
+        self._g_len = ctx.to_device(np.full((B,), self.past + 1, np.int32))  # nonpad_kv_seqlen of the Attention operator
+        self._host_len = np.zeros((B,), np.int32)
         self._scatter = O.ScatterRows()
         self._host_ints = np.zeros((n_ids + 1 + n_k + n_v,), np.int32)
         self._write_step_inputs(np.zeros((B, 1), np.int32))
@@ -676,9 +683,41 @@ class GPT2Int8Runner:
         h[B + 1:B + 1 + B * nh] = np.arange(B * nh, dtype=np.int32) * M + P          # rows of K viewed [B*nh*M, dh]
         h[B + 1 + B * nh:] = np.arange(B * nh * dh, dtype=np.int32) * M + P          # rows of V^T viewed [B*nh*dh*M, 1]
         self._g_ints.copy_from(h)
-        self._g_mask.view((1,), (1,), P).copy_from(np.zeros((1,), np.float32))      # position P becomes visible
+        if getattr(self, "_fused_decode", False):
+            self._host_len[:] = P + 1
+            self._g_len.copy_from(self._host_len)                                     # valid cache length incl. this token
+        else:
+            self._g_mask.view((1,), (1,), P).copy_from(np.zeros((1,), np.float32))  # position P becomes visible
+
+    def _decode_fused(self):
+        ctx, s, B, M = self.ctx, self.spec, self.B, self.max_seq
+        H, nh = s.hidden, s.heads
+        dh = H // nh
+        x = self.gather.run(ctx, self.wte, self._g_ids)
+        x = self.add.run(ctx, x, self.gather.run(ctx, self.wpe, self._g_pos)).reshape(B, H)
+        ql = lambda act=O.ACT_NONE: O.QuantizedLinear(act, s.eps)
+        attention = O.Attention(is_causal=True, q_num_heads=nh, kv_num_heads=nh, scale=1.0 / math.sqrt(dh))
+
+        def lin(x, l, ln=None, act=O.ACT_NONE, residual=None, out=None):
+            w, pk, ws, b = l
+            return ql(act).run(ctx, x, w, ws, packed_w=pk, bias=b, residual=residual, ln_scale=ln[0] if ln else None,
+                               ln_bias=ln[1] if ln else None, out=out)
+
+        for d in self.layers:
+            qkv = lin(x, d["attn"], ln=d["ln1"])                                     # [B, 3H]
+            part = lambda i: qkv.view((B, nh, 1, dh), (3 * H, dh, 3 * H, 1), i * H)
+            att = ctx.empty((B, H))
+            attention.run(ctx, part(0), d["k"], d["vt"].view((B, nh, M, dh), (nh * dh * M, dh * M, 1, M)),
+                          nonpad_kv_seqlen=self._g_len, new_key=part(1), new_value=part(2),
+                          out=att.view((B, nh, 1, dh), (H, dh, H, 1)))
+            x = lin(att, d["proj"], residual=x)
+            f = lin(x, d["fc"], ln=d["ln2"], act=O.ACT_GELU_TANH)
+            x = lin(f, d["fc2"], residual=x)
+        lin(x, self.lm_head, ln=self.lnf, out=self._g_logits)
 
     def _decode_fixed(self):
+        if getattr(self, "_fused_decode", False):
+            return self._decode_fused()
         ctx, s, B, M = self.ctx, self.spec, self.B, self.max_seq
         H, nh = s.hidden, s.heads
         dh = H // nh

@@ -18,7 +18,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 from . import _lib
-from ._lib import RTEN_DEVICE_HOST, RTEN_F32, RTEN_I8, RTEN_I32, RTEN_U8, RtenConvParams, RtenTensor
+from ._lib import RTEN_DEVICE_HOST, RTEN_F32, RTEN_I8, RTEN_I32, RTEN_U8, RtenAttentionParams, RtenConvParams, RtenTensor
 
 _NP2RT = {np.dtype(np.float32): RTEN_F32, np.dtype(np.int32): RTEN_I32, np.dtype(np.int8): RTEN_I8,
           np.dtype(np.uint8): RTEN_U8}
@@ -382,6 +382,42 @@ class MatMulIntegerToFloat(MatMul):
         ctx.check(ctx.lib.rten_b200_matmul_integer_ex(ctx.handle, A.t(a), A.t(b), _ph(packed_b), A.t(a_zero_point),
                                                       A.t(b_zero_point), A.t(scale), A.t(scale_b), A.t(bias), A.t(residual),
                                                       self.activation, A.t(out_range), C.byref(o)))
+        return A.wrap(o, out)
+
+
+class QuantizedLinear:
+    """[LayerNormalization] -> DynamicQuantizeLinear -> Mul -> MatMulIntegerToFloat -> Add(bias) -> Add(residual) -> activation
+    as one call (rten_b200_quantized_linear): the skinny-M decode kernel for <= 16 rows, the operator chain otherwise;
+    bit-identical to the separate operators either way."""
+
+    def __init__(self, activation: int = ACT_NONE, ln_epsilon: Optional[float] = None):
+        self.activation, self.ln_epsilon = activation, ln_epsilon
+
+    def run(self, ctx, x, w, w_scale, packed_w: Optional[Packed] = None, w_zero_point=None, bias=None, residual=None,
+            ln_scale=None, ln_bias=None, out=None):
+        A = _Args(ctx)
+        o = A.out(out)
+        ctx.check(ctx.lib.rten_b200_quantized_linear(ctx.handle, A.t(x), A.t(ln_scale), A.t(ln_bias),
+                                                     -1.0 if self.ln_epsilon is None else float(self.ln_epsilon), A.t(w), _ph(packed_w),
+                                                     A.t(w_zero_point), A.t(w_scale), A.t(bias), A.t(residual), self.activation, C.byref(o)))
+        return A.wrap(o, out)
+
+
+class Attention:
+    """src/ops/attention.rs:645-905 (ONNX `Attention`) on 4-D inputs; attributes as the reference's."""
+
+    def __init__(self, is_causal=False, kv_num_heads=None, q_num_heads=None, scale: Optional[float] = None, softcap: float = 0.0):
+        self.is_causal, self.kv_num_heads, self.q_num_heads, self.scale, self.softcap = is_causal, kv_num_heads, q_num_heads, scale, softcap
+
+    def run(self, ctx, query, key, value, attn_mask=None, nonpad_kv_seqlen=None, new_key=None, new_value=None, out=None):
+        """`new_key` / `new_value`: this step's key / value [batch, kv_heads, 1, head], appended to the caches `key` /
+        `value` at position nonpad_kv_seqlen[b] - 1 by the same kernel (q_seq = 1 only)."""
+        A = _Args(ctx)
+        o = A.out(out)
+        p = RtenAttentionParams(int(bool(self.is_causal)), int(self.q_num_heads or 0), int(self.kv_num_heads or 0),
+                                float(self.scale) if self.scale else 0.0, float(self.softcap))
+        ctx.check(ctx.lib.rten_b200_attention(ctx.handle, A.t(query), A.t(key), A.t(value), A.t(attn_mask), A.t(nonpad_kv_seqlen),
+                                              C.byref(p), A.t(new_key), A.t(new_value), C.byref(o)))
         return A.wrap(o, out)
 
 

@@ -372,7 +372,7 @@ def check_plans(rt, oracle):
     keys = ("RTEN_B200_FORCE_BN", "RTEN_B200_FORCE_PAIR", "RTEN_B200_FORCE_KATOMS", "RTEN_B200_FORCE_SPLITK", "RTEN_B200_FORCE_CTA2")
     plans = [dict(), dict(BN=64, PAIR=1, CTA2=0), dict(BN=128, PAIR=0, KATOMS=2, CTA2=0), dict(BN=256, PAIR=1, CTA2=0),
              dict(BN=128, PAIR=1, SPLITK=2, CTA2=0), dict(BN=64, PAIR=0, SPLITK=3, CTA2=0), dict(BN=256, PAIR=1, SPLITK=2, CTA2=0),
-             dict(BN=96, PAIR=0, SPLITK=4, KATOMS=2, CTA2=0),
+             dict(BN=96, PAIR=0, SPLITK=4, KATOMS=1, CTA2=0),
              # CTA pairs (tcgen05.mma.cta_group::2, 256-row tiles, half of B per CTA)
              dict(BN=128, PAIR=0, CTA2=1), dict(BN=256, PAIR=0, CTA2=1), dict(BN=256, PAIR=1, CTA2=1), dict(BN=64, PAIR=1, CTA2=1, KATOMS=2),
              dict(BN=128, PAIR=0, CTA2=1, SPLITK=2), dict(BN=256, PAIR=1, CTA2=1, SPLITK=2), dict(BN=96, PAIR=0, CTA2=1)]
@@ -741,16 +741,18 @@ def check_gpt2_int8_kvcache(rt, oracle):
         assert a.shape == r.shape and rel <= 2e-2, f"GPT-2 int8 step {i}: rel err {rel:.3e}"
         assert (a.argmax(1) == r.argmax(1)).all(), f"GPT-2 int8 step {i}: greedy token differs"
         worst = max(worst, rel)
-    # decode steps replayed as ONE CUDA graph (fixed-length masked attention, ScatterRows cache append)
-    runner = graphs.GPT2Int8Runner(ctx, spec, B, 64, fuse=True)
-    g_out = [runner.forward(steps[0]).numpy()]
-    runner.build_decode_graph()
-    g_out += [runner.decode_step(st).numpy().copy() for st in steps[1:]]
-    for i, (a, r) in enumerate(zip(g_out, ref)):
-        rel = float(np.abs(a - r).max() / np.abs(r).max())
-        assert rel <= 2e-2 and (a.argmax(1) == r.argmax(1)).all(), f"GPT-2 int8 graph decode step {i}: rel err {rel:.3e}"
-        worst = max(worst, rel)
-    return f"prefill {T0} + 3 decode steps (eager and graph-replayed), worst rel err {worst:.2e}"
+    # decode steps replayed as ONE CUDA graph: the fused path (quantised-linear skinny kernels + single-query attention
+    # with the cache append inside) and the separate operators (ScatterRows append, fixed-length masked attention)
+    for fused in (True, False):
+        runner = graphs.GPT2Int8Runner(ctx, spec, B, 64, fuse=True)
+        g_out = [runner.forward(steps[0]).numpy()]
+        runner.build_decode_graph(fused=fused)
+        g_out += [runner.decode_step(st).numpy().copy() for st in steps[1:]]
+        for i, (a, r) in enumerate(zip(g_out, ref)):
+            rel = float(np.abs(a - r).max() / np.abs(r).max())
+            assert rel <= 2e-2 and (a.argmax(1) == r.argmax(1)).all(), f"GPT-2 int8 graph decode (fused={fused}) step {i}: rel err {rel:.3e}"
+            worst = max(worst, rel)
+    return f"prefill {T0} + 3 decode steps (eager, graph-replayed fused and unfused), worst rel err {worst:.2e}"
 
 
 def check_tf32x3(rt, oracle):
@@ -938,7 +940,7 @@ def check_resnet50_b32_baseline(rt, oracle):
 
 def check_bert_b16_baseline(rt, oracle):
     """configs[2] exactly as benched: BERT-base, 12 layers, batch 16 x seq 128, graph replay.  TF32: hidden states within
-    1e-2 absolute (LayerNorm keeps them O(1)); 3xTF32: within 2e-4."""
+    3e-2 absolute (12 layers of 2^-11-relative operand rounding; LayerNorm keeps activations O(1)); 3xTF32: within 2e-4."""
     from rten_b200 import graphs
     import model_ref
     rng = oracle.XorShiftRng(5678)
@@ -949,7 +951,7 @@ def check_bert_b16_baseline(rt, oracle):
     oracle.use_all_cores()
     ref = model_ref.bert_oracle(oracle, spec, ids, tt, mask)
     res = {}
-    for name, tf32, tol in (("tf32", True, 1e-2), ("tf32x3", False, 2e-4)):
+    for name, tf32, tol in (("tf32", True, 3e-2), ("tf32x3", False, 2e-4)):
         ctx = new_ctx(rt, tf32=tf32)
         runner = graphs.BertRunner(ctx, spec, fuse=True)
         di, dt, dm = ctx.to_device(ids), ctx.to_device(tt), ctx.to_device(mask)
@@ -1005,7 +1007,7 @@ def check_gpt2_b8_baseline(rt, oracle):
     steps = [ids[:, :T0]] + [ids[:, T0 + i:T0 + i + 1] for i in range(nd)]
     oracle.use_all_cores()
     ref = model_ref.gpt2_int8_oracle(oracle, spec, steps)
-    ctx = new_ctx(rt)
+    ctx = new_ctx(rt, tf32=False)  # the f32 attention products of the prefill at fp32 grade (library default)
     ctx.set_autotune(True)
     runner = graphs.GPT2Int8Runner(ctx, spec, B, 576, fuse=True)
     outs = [runner.forward(steps[0]).numpy()]
@@ -1047,6 +1049,183 @@ def check_graph_pool_isolation(rt, oracle):
     return "replays unaffected by post-capture allocations"
 
 
+# ------------------------------------------------------------------------------------------
+# Decode path: fused quantised linear layer, single-query attention, skinny f32 products
+# ------------------------------------------------------------------------------------------
+def _qlinear_oracle(oracle, x, ln, wq, wz, ws, bias, residual, act, eps):
+    f32 = np.float32
+    h = oracle.layer_norm(x, ln[0], ln[1], -1, eps) if ln is not None else x
+    xq, xs, xz = oracle.dynamic_quantize_linear(h)
+    scale = (f32(xs) * np.asarray(ws, f32)).astype(f32)
+    y = oracle.matmul_integer_to_float(xq.reshape(-1, xq.shape[-1]), wq, xz, wz, scale if scale.ndim else scale.reshape(()))
+    if bias is not None:
+        y = oracle.add(y, bias)
+    if residual is not None:
+        y = oracle.add(y, residual.reshape(y.shape))
+    if act == 3:
+        y = oracle.gelu(y, True)
+    elif act == 2:
+        y = oracle.gelu(y)
+    elif act == 1:
+        y = oracle.relu(y)
+    return y.reshape(x.shape[:-1] + (wq.shape[1],))
+
+
+def check_quantized_linear(rt, oracle):
+    """rten_b200_quantized_linear = [LayerNormalization] -> DynamicQuantizeLinear -> Mul -> MatMulIntegerToFloat -> Add -> Add
+    -> activation.  The skinny-M kernel (M <= 16) and the composed path (larger M) must both be BIT-IDENTICAL to the
+    oracle's operator chain: GPT-2 decode shapes, per-column and scalar scales, weight zero points, u8 weights."""
+    ctx = new_ctx(rt)
+    r = oracle.XorShiftRng(4242)
+    n = 0
+    cases = [  # (x shape, N, layer norm, bias, residual, activation, weight zero points, weight dtype, scalar scale)
+        ((8, 768), 2304, True, True, False, 0, None, np.int8, False), ((8, 768), 768, False, True, True, 0, None, np.int8, False),
+        ((8, 768), 3072, True, True, False, 3, None, np.int8, False), ((8, 3072), 768, False, True, True, 0, None, np.int8, False),
+        ((8, 768), 5003, True, False, False, 0, None, np.int8, False), ((1, 768), 777, True, True, True, 2, "vec", np.int8, False),
+        ((3, 5, 256), 130, False, True, False, 1, "vec", np.uint8, True), ((16, 1024), 4100, True, False, True, 0, "scalar", np.int8, False),
+        ((13, 128), 64, True, True, False, 0, None, np.uint8, False), ((40, 768), 300, True, True, True, 3, None, np.int8, False),
+        ((2, 9, 160), 96, False, False, False, 0, "vec", np.int8, True), ((8, 48), 40, False, True, False, 0, None, np.int8, False)]
+    for xs, N, has_ln, has_bias, has_res, act, wzp, wdt, scalar_scale in cases:
+        K = xs[-1]
+        x = r.uniform(xs, -2, 3)
+        ln = (r.uniform((K,), 0.5, 1.5), r.uniform((K,), -0.5, 0.5)) if has_ln else None
+        wq = r.i8((K, N)) if wdt == np.int8 else r.u8((K, N))
+        ws = r.uniform((), 0.001, 0.05) if scalar_scale else r.uniform((N,), 0.001, 0.05)
+        bias = r.uniform((N,)) if has_bias else None
+        M = int(np.prod(xs[:-1]))
+        res = r.uniform(xs[:-1] + (N,)) if has_res else None
+        wz = None
+        if wzp == "vec":
+            wz = r.i8((N,)) if wdt == np.int8 else r.u8((N,))
+        elif wzp == "scalar":
+            wz = np.array(r.i8((1,))[0] if wdt == np.int8 else r.u8((1,))[0])
+        want = _qlinear_oracle(oracle, x, ln, wq, wz, ws, bias, res, act, 1e-5)
+        dw = ctx.to_device(wq)
+        op = rt.QuantizedLinear(act, 1e-5)
+        pk = rt.MatMulInteger().prepack(ctx, 1, dw)
+        dev = lambda a: None if a is None else ctx.to_device(a)
+        got = op.run(ctx, dev(x), dw, dev(ws), packed_w=pk, w_zero_point=dev(wz), bias=dev(bias), residual=dev(res),
+                     ln_scale=dev(ln[0]) if ln else None, ln_bias=dev(ln[1]) if ln else None).numpy()
+        assert_bit_exact(got, want, f"QuantizedLinear x{xs} N={N} ln={has_ln} act={act} wzp={wzp} {np.dtype(wdt).name}")
+        # host tensors / no prepack -> the composed operator chain: same bits
+        got2 = op.run(ctx, x, wq, ws, w_zero_point=wz, bias=bias, residual=res, ln_scale=ln[0] if ln else None,
+                      ln_bias=ln[1] if ln else None).numpy()
+        assert_bit_exact(got2, want, f"QuantizedLinear (composed) x{xs} N={N}")
+        n += 1
+    return f"{n} cases bit-exact (fused kernel and composed chain)"
+
+
+def _attention_ref(q, k, v, lens, mask, scale):
+    """float64 reference of softmax(scale q k^T + mask) v over the first lens[b] positions."""
+    B, qh, _, dh = q.shape
+    kvh = k.shape[1]
+    out = np.zeros((B, qh, 1, dh))
+    for b in range(B):
+        L = int(lens[b])
+        for h in range(qh):
+            hk = h // (qh // kvh)
+            if L == 0:
+                continue
+            s = scale * (k[b, hk, :L].astype(np.float64) @ q[b, h, 0].astype(np.float64))
+            if mask is not None:
+                s = s + np.broadcast_to(mask, (B, qh, 1, k.shape[2]))[b, h, 0, :L]
+            s = s - s.max()
+            p = np.exp(s)
+            out[b, h, 0] = (p / p.sum()) @ v[b, hk, :L].astype(np.float64)
+    return out
+
+
+def check_attention_decode(rt, oracle):
+    """rten_b200_attention with q_seq = 1 against a float64 restatement of sdpa_head (src/ops/attention.rs:518-560) over an
+    externally managed, right-padded cache (nonpad_kv_seqlen): natural and transposed value caches, grouped-query heads,
+    additive masks, head sizes 64 / 128, cache lengths that split over several CTAs, the fused cache append, and the
+    composed path for q_seq > 1.  f32 arithmetic: |d| <= 2e-5 * max |ref| (stated)."""
+    ctx = new_ctx(rt, tf32=False)
+    r = oracle.XorShiftRng(777)
+    worst, n = 0.0, 0
+    for B, qh, kvh, dh, cap, lens, use_mask, vt in [(3, 4, 4, 64, 200, [1, 77, 200], False, False), (8, 12, 12, 64, 576, [513] * 8, False, True),
+                                                    (2, 8, 2, 64, 1000, [1000, 333], True, True), (2, 4, 4, 128, 96, [96, 5], True, False),
+                                                    (1, 2, 1, 64, 5000, [4999], False, False), (2, 3, 3, 64, 64, [0, 64], False, True)]:
+        q = r.uniform((B, qh, 1, dh))
+        k = r.uniform((B, kvh, cap, dh))
+        v = r.uniform((B, kvh, cap, dh))
+        mask = r.uniform((B, 1, 1, cap), -2, 0) if use_mask else None
+        lens_a = np.array(lens, np.int32)
+        scale = 1.0 / np.sqrt(dh)
+        ref = _attention_ref(q, k, v, lens_a, mask, scale)
+        dk = ctx.to_device(k)
+        if vt:  # value cache stored [.., dh, cap]; the operator sees the [.., cap, dh] view
+            dvt = ctx.to_device(np.ascontiguousarray(v.transpose(0, 1, 3, 2)))
+            dv = dvt.view((B, kvh, cap, dh), (kvh * dh * cap, dh * cap, 1, cap))
+        else:
+            dv = ctx.to_device(v)
+        op = rt.Attention(is_causal=True, q_num_heads=qh, kv_num_heads=kvh)
+        got = op.run(ctx, ctx.to_device(q), dk, dv, attn_mask=None if mask is None else ctx.to_device(mask),
+                     nonpad_kv_seqlen=ctx.to_device(lens_a)).numpy()
+        err = float(np.abs(got - ref).max() / max(np.abs(ref).max(), 1e-30))
+        assert got.shape == ref.shape and err <= 2e-5, f"Attention decode B={B} heads={qh}/{kvh} dh={dh} cap={cap} lens={lens}: rel err {err:.2e}"
+        worst = max(worst, err)
+        n += 1
+    # fused cache append: the new key / value land at position len - 1 and take part in the attention
+    B, nh, dh, cap = 4, 6, 64, 160
+    lens_a = np.array([1, 50, 160, 97], np.int32)
+    q, kn, vn = r.uniform((B, nh, 1, dh)), r.uniform((B, nh, 1, dh)), r.uniform((B, nh, 1, dh))
+    k, v = r.uniform((B, nh, cap, dh)), r.uniform((B, nh, cap, dh))
+    k2, v2 = k.copy(), v.copy()
+    for b in range(B):
+        k2[b, :, lens_a[b] - 1] = kn[b, :, 0]
+        v2[b, :, lens_a[b] - 1] = vn[b, :, 0]
+    ref = _attention_ref(q, k2, v2, lens_a, None, 0.125)
+    for vt in (False, True):
+        dk = ctx.to_device(k)
+        if vt:
+            dvt = ctx.to_device(np.ascontiguousarray(v.transpose(0, 1, 3, 2)))
+            dv = dvt.view((B, nh, cap, dh), (nh * dh * cap, dh * cap, 1, cap))
+        else:
+            dv = ctx.to_device(v)
+        got = rt.Attention(is_causal=True, scale=0.125).run(ctx, ctx.to_device(q), dk, dv, nonpad_kv_seqlen=ctx.to_device(lens_a),
+                                                            new_key=ctx.to_device(kn), new_value=ctx.to_device(vn)).numpy()
+        err = float(np.abs(got - ref).max() / np.abs(ref).max())
+        assert err <= 2e-5, f"Attention with fused append (vt={vt}): rel err {err:.2e}"
+        assert_bit_exact(dk.numpy(), k2, "key cache after the fused append")
+        assert_bit_exact(dv.numpy(), v2, "value cache after the fused append")
+        worst = max(worst, err)
+    # q_seq > 1 (composed MatMul / Softmax / MatMul, 3xTF32): BERT-shaped, float mask
+    q, k, v = r.uniform((2, 4, 32, 64)), r.uniform((2, 4, 48, 64)), r.uniform((2, 4, 48, 64))
+    mask = r.uniform((2, 1, 1, 48), -2, 0)
+    got = rt.Attention().run(ctx, q, k, v, attn_mask=mask).numpy()
+    s = 0.125 * np.einsum("bhqd,bhkd->bhqk", q.astype(np.float64), k.astype(np.float64)) + mask
+    p = np.exp(s - s.max(-1, keepdims=True))
+    ref = np.einsum("bhqk,bhkd->bhqd", p / p.sum(-1, keepdims=True), v.astype(np.float64))
+    err = float(np.abs(got - ref).max() / np.abs(ref).max())
+    assert err <= 1e-4, f"Attention q_seq=32 (composed): rel err {err:.2e}"
+    try:
+        rt.Attention().run(ctx, r.uniform((2, 4, 1, 64)), r.uniform((2, 3, 9, 64)), r.uniform((2, 3, 9, 64)))
+        raise AssertionError("expected an error")
+    except rt.OpError as e:
+        assert e.kind == "IncompatibleInputShapes" and e.msg == "q_num_heads must be a positive multiple of kv_num_heads", str(e)
+    return f"{n + 2} decode cases, worst rel err {worst:.1e}; composed q_seq=32 rel err {err:.1e}"
+
+
+def check_skinny_f32(rt, oracle):
+    """MatMul / Gemm / FusedMatMul with M <= 32 rows run the HBM-streaming skinny kernel in exact f32 FMA arithmetic
+    (rten-gemm's gemv path): the reference's float rule against the oracle, in BOTH f32 modes (the mode does not
+    matter here), incl. the ResNet-50 classifier shape, bias, alpha, beta * C and the vector forms."""
+    worst = 0
+    for tf32 in (True, False):
+        ctx = new_ctx(rt, tf32=tf32)
+        r = oracle.XorShiftRng(31)
+        for (m, k, n) in [(32, 2048, 1000), (8, 768, 3072), (1, 768, 50), (16, 3072, 768), (5, 100, 7), (31, 64, 33)]:
+            a, b, bias = r.f32((m, k)), r.f32((k, n)), r.f32((n,))
+            assert_reference_rule(rt.FusedMatMul(0.5).run(ctx, a, b, bias).numpy(), oracle.matmul(a, b, bias, 0.5), f"skinny FusedMatMul {m}x{k}x{n}")
+            worst += 1
+        a, b, c = r.f32((32, 2048)), r.f32((1000, 2048)), r.f32((1000,))
+        assert_reference_rule(rt.Gemm(1.0, 1.0, False, True).run(ctx, a, b, c).numpy(), oracle.gemm_op(a, b, c, 1.0, 1.0, False, True), "skinny Gemm transB + C")
+        v, mtx = r.f32((768,)), r.f32((768, 1000))
+        assert_reference_rule(rt.MatMul().run(ctx, v, mtx).numpy(), oracle.matmul(v, mtx), "skinny vector x matrix")
+    return f"{worst} cases inside 1e-8 + 1e-5*|ref| in both modes"
+
+
 ALL_CHECKS = [
     ("context", check_context), ("unary", check_unary), ("softmax", check_softmax), ("layer_norm", check_layer_norm),
     ("dql", check_dql), ("glue", check_glue), ("matmul_small", check_matmul_small), ("matmul_shapes", check_matmul_shapes),
@@ -1054,6 +1233,7 @@ ALL_CHECKS = [
     ("conv_basic", check_conv_basic), ("conv_stride", check_conv_stride), ("conv_more", check_conv_more),
     ("conv_integer", check_conv_integer), ("plans", check_plans), ("tf32x3", check_tf32x3), ("sequence", check_sequence), ("conv_integer_fused", check_conv_integer_fused),
     ("resnet50_int8_model", check_resnet50_int8_model), ("gpt2_int8_kvcache", check_gpt2_int8_kvcache), ("mnist_model", check_mnist_model), ("resnet50_model", check_resnet50_model), ("bert_model", check_bert_model),
+    ("quantized_linear", check_quantized_linear), ("attention_decode", check_attention_decode), ("skinny_f32", check_skinny_f32),
     ("reference_rule_f32", check_reference_rule_f32), ("graph_pool_isolation", check_graph_pool_isolation),
     ("resnet50_b32_baseline", check_resnet50_b32_baseline), ("bert_b16_baseline", check_bert_b16_baseline),
     ("resnet50_int8_b64_baseline", check_resnet50_int8_b64_baseline), ("gpt2_b8_baseline", check_gpt2_b8_baseline),
