@@ -1,22 +1,33 @@
 #!/usr/bin/env python
-"""bench.py -- one "step" = one pass of the hot path (the post-fusion ResNet-50 fp32 op list, batch 32 per
-GPU: BASELINE.json configs[1]) over one batch of synthetic input.
+"""bench.py -- one "step" = one pass of the hot path over one batch of synthetic input.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--model resnet50|bert]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                  [--model resnet50|bert|resnet50_int8|gpt2]
 
-Prints ONE JSON line (rank 0).  `value` = whole-job images/s with inputs resident in HBM; `e2e` = the same
-metric through the public operator API with HOST (pinned) input and output buffers, host<->device copies
-inside the timed region.  `roofline` describes the dominant kernel (the tcgen05 implicit-GEMM conv),
-`cpu_baseline` the CPU restatement of the reference path (oracle/) on a bounded sample.
-`--impl reference` times that CPU restatement alone (the Rust reference cannot be built here: no cargo).
+Default workload = BASELINE.json configs[1]: the post-fusion ResNet-50 fp32 op list, batch 32 per GPU.  Prints ONE
+JSON line (rank 0).
+
+  value     whole-job throughput, inputs resident in HBM, the step replayed from a CUDA graph, CUDA events on the
+            launching stream, 256 MiB L2 flush between steps (outside the events), max over ranks.
+  e2e       the same metric through the public operator API with HOST (pinned) input and output buffers, host<->device
+            copies inside the timed region.
+  modes     fp32 models are measured in BOTH arithmetic modes of the library: "tf32" (single tcgen05 kind::tf32 pass,
+            an explicit opt-in) and "tf32x3" (the library default: error-compensated, meets the reference's own f32
+            tolerance).  The top-level value / e2e / roofline are the tf32 block (north_star names the TF32 roofline);
+            `modes.tf32x3` carries the same keys for the fp32-grade path.  Algorithmic flops are counted 1x in both.
+  roofline  dominant kernel: algorithmic flops (or bytes) per step / that kernel's time inside the GRAPH replay (CUPTI
+            kernel records through torch.profiler; `lower_bound` = the same work / the whole step time), against the
+            tensor peak measured in this run (cuBLASLt 8192^3 through torch: burst = best of 10, sustained = 3 s).
+  cpu_baseline / --impl reference: the CPU restatement of the reference path (oracle/; the Rust reference cannot be
+            built here: no cargo) on the host cores, bounded sample.
 """
 from __future__ import annotations
 
 import argparse
+import ctypes as C
 import json
 import os
 import statistics
-import subprocess
 import sys
 import threading
 import time
@@ -27,18 +38,25 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import numpy as np  # noqa: E402
 
+MODELS = {
+    "resnet50": dict(batch=32, unit="img/s", metric="resnet50_fp32_inferences_per_sec", modes=["tf32", "tf32x3"]),
+    "bert": dict(batch=16, unit="seq/s", metric="bert_base_fp32_seq128_inferences_per_sec", modes=["tf32", "tf32x3"]),
+    "resnet50_int8": dict(batch=64, unit="img/s", metric="resnet50_int8_inferences_per_sec", modes=["int8"]),
+    "gpt2": dict(batch=8, unit="tokens/s", metric="gpt2_int8_decode_tokens_per_sec", modes=["int8"]),
+}
+GPT2_PREFILL, GPT2_CACHE = 512, 576
+
 
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return {"hbm_gbs": d["hbm_gbs"], "bf16_burst": d["bf16_tflops"], "bf16_sustained": d["bf16_tflops_sustained"], "src": "measured"}
-    return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "src": "fallback"}
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_burst": d["bf16_tflops"], "bf16_sustained": d["bf16_tflops_sustained"], "src": "MEASURED_PEAKS.json"}
+    return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "src": "fallback (B200_PROFILING.md)"}
 
 
 class ClockSampler:
-    """SM clock and throttle reasons sampled every ~5 ms DURING the timed region through NVML (falls back to
-    `nvidia-smi -lms` when the binding is missing)."""
+    """SM clock and throttle reasons sampled every ~4 ms DURING a timed region through NVML."""
 
     def __init__(self, index: int):
         self.index, self.rows, self.stop_flag, self.thread = index, [], False, None
@@ -64,6 +82,7 @@ class ClockSampler:
             time.sleep(0.004)
 
     def start(self):
+        self.rows = []
         if self.nv is None:
             return
         self.stop_flag = False
@@ -91,12 +110,18 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+# ------------------------------------------------------------------------------------------
+# workload definitions shared by both arms
+# ------------------------------------------------------------------------------------------
 def make_inputs(oracle, model, batch):
     rng = oracle.XorShiftRng(1234)
-    if model == "resnet50":
+    if model in ("resnet50", "resnet50_int8"):
         return {"x": rng.uniform((batch, 3, 224, 224))}
-    ids = (rng.u64(batch * 128) % 30522).astype(np.int32).reshape(batch, 128)
-    return {"ids": ids, "tt": np.zeros((batch, 128), np.int32), "mask": np.zeros((batch, 1, 1, 128), np.float32)}
+    if model == "bert":
+        ids = (rng.u64(batch * 128) % 30522).astype(np.int32).reshape(batch, 128)
+        return {"ids": ids, "tt": np.zeros((batch, 128), np.int32), "mask": np.zeros((batch, 1, 1, 128), np.float32)}
+    ids = (oracle.XorShiftRng(1).u64(batch * GPT2_CACHE) % 50257).astype(np.int32).reshape(batch, GPT2_CACHE)
+    return {"ids": ids}
 
 
 def make_spec(oracle, model):
@@ -104,52 +129,163 @@ def make_spec(oracle, model):
     rng = oracle.XorShiftRng(5678)
     if model == "resnet50":
         return graphs.make_resnet50(lambda s: rng.uniform(s))
-    return graphs.make_bert(lambda s: rng.uniform(s))
+    if model == "resnet50_int8":
+        return graphs.quantize_resnet50(graphs.make_resnet50(lambda s: rng.uniform(s)))
+    if model == "bert":
+        return graphs.make_bert(lambda s: rng.uniform(s))
+    return graphs.make_gpt2_int8(lambda s: rng.uniform(s))
+
+
+def metric_name(model):
+    return MODELS[model]["metric"]
+
+
+def config_of(model, batch, n):
+    common = {"global_batch": batch * n, "per_gpu_batch": batch, "l2": "256 MiB memset between timed steps",
+              "f32_modes": "top level = tf32 (explicit opt-in, single kind::tf32 pass); modes.tf32x3 = library default (fp32-grade)"}
+    if model == "resnet50":
+        return {"workload": "ResNet-50 fp32 (post-fusion op list, BN folded), batch 32 per GPU, 224x224, synthetic weights XorShift(5678)",
+                "parallelism": f"dp{n} (batch shard, all-gather of logits)", **common}
+    if model == "bert":
+        return {"workload": "BERT-base fp32 (post-fusion op list), batch 16 x seq 128 per GPU, synthetic weights XorShift(5678)",
+                "seq_len": 128, "parallelism": f"dp{n} (batch shard, all-gather of hidden states)", **common}
+    if model == "resnet50_int8":
+        return {"workload": "ResNet-50 dynamically quantised (DynamicQuantizeLinear -> ConvIntegerToFloat), batch 64 per GPU, 224x224",
+                "parallelism": f"dp{n} (batch shard; quantisation ranges all-reduced over the ranks, all-gather of logits)", **common}
+    return {"workload": f"GPT-2 small int8 (dynamic quantisation), batch 8 per GPU: decode steps against a KV cache holding a {GPT2_PREFILL}-token prefill",
+            "seq_len": GPT2_PREFILL, "parallelism": f"dp{n} (independent replicas per GPU, all-gather of logits)", **common}
 
 
 def run_reference_arm(args, model, batch):
-    """CPU restatement of the reference path on all host threads, bounded sample per step."""
+    """CPU restatement of the reference path on all host threads.  One step processes what ONE step of the GPU arm
+    processes at this N (batch x N inputs), in chunks of one per-GPU batch, so the two arms are like for like."""
     from oracle import oracle
     import model_ref
     ncores = oracle.use_all_cores()
     spec = make_spec(oracle, model)
-    # images are the outer parallel level: a many-core host needs the whole batch in flight to be busy
-    sample = (batch if ncores >= 16 else 8) if model == "resnet50" else (batch if ncores >= 16 else 4)
-    inp = make_inputs(oracle, model, sample)
-    arena = oracle.Arena()  # = the reference's BufferPool: operator outputs are recycled from pass to pass
-    run = (lambda: model_ref.resnet50_oracle(oracle, spec, inp["x"], arena)) if model == "resnet50" else \
-        (lambda: model_ref.bert_oracle(oracle, spec, inp["ids"], inp["tt"], inp["mask"]))
+    n = max(1, args.gpus)
+    unit = MODELS[model]["unit"]
+    if model == "gpt2":
+        # bounded sample: a 128-token prefill (untimed), then decode steps of 8 tokens; each step = N per-GPU batches
+        inp = make_inputs(oracle, model, batch)["ids"]
+        state = {"past": None}
+
+        def prefill():
+            return model_ref.gpt2_int8_decoder(oracle, spec, inp[:, :128])
+
+        dec = prefill()
+        pos = [128]
+
+        def run():
+            for _ in range(n):
+                dec.step(inp[:, pos[0]:pos[0] + 1])
+            pos[0] += 1
+
+        per_step = batch * n
+        sample = f"decode steps of {batch} tokens x {n} after a 128-token prefill (the GPU arm decodes after {GPT2_PREFILL}); oracle port"
+    else:
+        chunk = batch if ncores >= 16 else max(1, batch // 4)
+        inp = make_inputs(oracle, model, chunk)
+        arena = oracle.Arena()  # = the reference's BufferPool: operator outputs are recycled from pass to pass
+        if model == "resnet50":
+            one = lambda: model_ref.resnet50_oracle(oracle, spec, inp["x"], arena)
+        elif model == "resnet50_int8":
+            one = lambda: model_ref.resnet50_int8_oracle(oracle, spec, inp["x"])
+        else:
+            one = lambda: model_ref.bert_oracle(oracle, spec, inp["ids"], inp["tt"], inp["mask"])
+        reps = n * (batch // chunk)
+
+        def run():
+            for _ in range(reps):
+                one()
+
+        per_step = chunk * reps
+        sample = f"{per_step} inputs per step in chunks of {chunk} (= batch {batch} x {n} GPU(s)); CPU restatement of the rten path (oracle/), the Rust reference cannot be built here"
     for _ in range(max(1, min(args.warmup, 1))):
         run()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         run()
     dt = time.perf_counter() - t0
-    val = sample * args.steps / dt
-    unit = "img/s" if model == "resnet50" else "seq/s"
+    val = per_step * args.steps / dt
     cores = oracle.num_threads()
     return {
         "impl": "reference", "metric": metric_name(model), "value": val, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": config_of(model, batch, args.gpus),
-        "cpu_baseline": {"value": val, "unit": unit, "cores": cores, "kind": "port",
-                         "sample": f"{sample} of {batch} inputs per step; CPU restatement of the rten path (oracle/), the Rust reference cannot be built here"},
+        "dtype": "f32" if model in ("resnet50", "bert") else "u8 x i8 -> i32 (f32 between layers)", "data": "synthetic",
+        "config": config_of(model, batch, args.gpus),
+        "cpu_baseline": {"value": val, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
 
 
-def metric_name(model):
-    return "resnet50_fp32_inferences_per_sec" if model == "resnet50" else "bert_base_fp32_seq128_inferences_per_sec"
+# ------------------------------------------------------------------------------------------
+# measurement helpers (GPU arm)
+# ------------------------------------------------------------------------------------------
+def measure_matmul_peaks(torch, n=8192, sustained_s=3.0):
+    """cuBLASLt through torch on this box, in this run: burst (best of 10) and sustained (back to back for 3 s)."""
+    out = {}
+    torch.backends.cuda.matmul.allow_tf32 = True
+    cases = {"tf32": (torch.float32, torch.matmul), "int8": (torch.int8, torch._int_mm), "bf16": (torch.bfloat16, torch.matmul)}
+    for name, (dt, fn) in cases.items():
+        try:
+            if dt == torch.int8:
+                a = torch.randint(-128, 127, (n, n), device="cuda", dtype=dt)
+                b = torch.randint(-128, 127, (n, n), device="cuda", dtype=dt)
+            else:
+                a = torch.randn(n, n, device="cuda", dtype=dt)
+                b = torch.randn(n, n, device="cuda", dtype=dt)
+            for _ in range(3):
+                fn(a, b)
+            torch.cuda.synchronize()
+            best = 1e9
+            for _ in range(10):
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                fn(a, b)
+                e.record()
+                torch.cuda.synchronize()
+                best = min(best, s.elapsed_time(e))
+            t0 = time.time()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            cnt = 0
+            while time.time() - t0 < sustained_s:
+                for _ in range(20):
+                    fn(a, b)
+                cnt += 20
+                torch.cuda.synchronize()
+            e.record()
+            torch.cuda.synchronize()
+            out[name] = {"burst": 2.0 * n ** 3 / best / 1e9, "sustained": 2.0 * n ** 3 * cnt / s.elapsed_time(e) / 1e9}
+            del a, b
+        except Exception as ex:  # noqa: BLE001
+            out[name] = {"error": str(ex)[:200]}
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return out
 
 
-def config_of(model, batch, n):
-    if model == "resnet50":
-        return {"workload": "ResNet-50 fp32 (post-fusion op list, BN folded), batch 32 per GPU, 224x224, synthetic weights XorShift(5678)",
-                "global_batch": batch * n, "per_gpu_batch": batch, "parallelism": f"dp{n} (batch shard, all-gather of logits)",
-                "f32_mode": "tf32 single pass", "l2": "256 MiB memset between timed steps"}
-    return {"workload": "BERT-base fp32 (post-fusion op list), batch 16 x seq 128 per GPU, synthetic weights XorShift(5678)",
-            "global_batch": batch * n, "per_gpu_batch": batch, "seq_len": 128, "parallelism": f"dp{n} (batch shard, all-gather of hidden states)",
-            "f32_mode": "tf32 single pass", "l2": "256 MiB memset between timed steps"}
+def graph_kernel_times(torch, launch, reps=3):
+    """Per-kernel device time of `reps` graph replays from CUPTI kernel records (torch.profiler) -> {name: (count, us)}
+    per replay, or None when the profiler is unavailable."""
+    try:
+        from torch.profiler import ProfilerActivity, profile
+        launch()
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(reps):
+                launch()
+            torch.cuda.synchronize()
+        rows = {}
+        for ev in prof.key_averages():
+            t = getattr(ev, "device_time_total", None)
+            if t is None:
+                t = getattr(ev, "cuda_time_total", 0.0)
+            if t and ev.count:
+                rows[ev.key] = (ev.count / reps, float(t) / reps)
+        return rows or None
+    except Exception:  # noqa: BLE001
+        return None
 
 
 def main():
@@ -158,16 +294,18 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--model", default="resnet50", choices=["resnet50", "bert"])
-    ap.add_argument("--no-graph", action="store_true", help="issue ops one by one instead of replaying a CUDA graph")
+    ap.add_argument("--model", default="resnet50", choices=sorted(MODELS))
+    ap.add_argument("--no-graph", action="store_true", help="issue ops one by one instead of replaying a CUDA graph (profiling aid)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-autotune", action="store_true", help="use the cost model's launch plans instead of timing candidates during warm-up")
     ap.add_argument("--plans", default=None, help="file of measured launch plans: loaded if it exists, (re)written after the warm-up pass")
-    ap.add_argument("--no-extras", action="store_true", help="skip the secondary numbers (BERT-base pass, 8192^3 GEMM TFLOP/s)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary numbers (other configs, 8192^3 GEMM TFLOP/s)")
+    ap.add_argument("--no-peaks", action="store_true", help="skip the on-box cuBLAS peak measurement (uses MEASURED_PEAKS.json ratios)")
+    ap.add_argument("--modes", default=None, help="comma list restricting the f32 modes measured (tf32,tf32x3)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     model = args.model
-    batch = 32 if model == "resnet50" else 16
+    batch = MODELS[model]["batch"]
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -181,7 +319,7 @@ def main():
     import torch.distributed as dist
     import rten_b200 as rt
     from rten_b200 import graphs, shard
-    from oracle import oracle  # inputs/weights RNG + cpu_baseline leg only
+    from oracle import oracle  # inputs / weights RNG + the cpu_baseline leg only
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: rten_b200 has no CPU fallback")
@@ -189,253 +327,444 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     stream = torch.cuda.Stream()
+    comm_stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
-    ctx = rt.Context(local_rank, stream=stream.cuda_stream)
-    ctx.set_autotune(not args.no_autotune)  # plans are measured during the first (untimed, eager) pass
-    if args.plans and os.path.exists(args.plans):
-        ctx.load_plans(args.plans)
-
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     spec = make_spec(oracle, model)
     inp = make_inputs(oracle, model, batch)
-    if model == "resnet50":
-        runner = graphs.ResNet50Runner(ctx, spec, fuse=True)
-        x_dev = ctx.to_device(inp["x"], channels_last=True)
-        dev_inputs = [x_dev]
-        step_fn = lambda: runner.run(x_dev)
-        flops = graphs.resnet50_flops(spec) * batch
-        unit = "img/s"
-    else:
-        runner = graphs.BertRunner(ctx, spec, fuse=True)
-        ids, tt, mask = ctx.to_device(inp["ids"]), ctx.to_device(inp["tt"]), ctx.to_device(inp["mask"])
-        dev_inputs = [ids, tt, mask]
-        step_fn = lambda: runner.run(ids, tt, mask)
-        flops = graphs.bert_flops(spec, batch, 128)
-        unit = "seq/s"
+    unit = MODELS[model]["unit"]
+    modes = MODELS[model]["modes"]
+    if args.modes:
+        modes = [m for m in modes if m in args.modes.split(",")] or modes
 
-    # ---- eager run (also warms the buffer pool so that graph capture never allocates)
-    out = step_fn()
-    ctx.sync()
-    if args.plans and rank == 0:
-        ctx.save_plans(args.plans)
-    out_shape = out.shape
-    del out
-    gather_buf = torch.empty(shard.gather_layout(world, tuple(out_shape)), dtype=torch.float32, device="cuda") if world > 1 else None
-    out_t = torch.empty(tuple(out_shape), dtype=torch.float32, device="cuda")
-    out_dst = rt.from_torch(ctx, out_t)
-
-    def copy_out(o):
-        import ctypes as C
-        src, dst = o.desc(), out_dst.desc()
+    def copy_desc(ctx, src, dst):
         ctx.check(ctx.lib.rten_b200_copy(ctx.handle, C.byref(src), C.byref(dst)))
 
-    launches_per_step = None
-    graph = None
-    if not args.no_graph:
-        l0 = ctx.launches
-        ctx.graph_begin()
-        o = step_fn()
-        copy_out(o)
-        graph = ctx.graph_end()
-        del o
+    def host_desc(h):
+        return rt.ops._desc(h.ctypes.data, h.dtype, h.shape, rt.ops._contig(h.shape), -1)
 
-    def device_step():
-        if graph is not None:
-            graph.launch()
+    def run_mode(mode, want_kernel_times):
+        """One arithmetic mode: build the runner on a fresh context, warm up / autotune, capture, time value and e2e."""
+        ctx = rt.Context(local_rank, stream=stream.cuda_stream)
+        ctx.set_f32_mode(mode != "tf32")  # tf32 = explicit opt-in; everything else keeps the library default
+        ctx.set_autotune(not args.no_autotune)
+        if args.plans and os.path.exists(args.plans):
+            ctx.load_plans(args.plans)
+        comm = None
+        if world > 1 and model == "resnet50_int8":
+            ids = [rt.Comm.unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(ids, src=0)
+            comm = rt.Comm(ctx, ids[0], rank, world)
+        res = {"mode": mode}
+        if model == "gpt2":
+            return run_gpt2(ctx, res)
+        if model == "resnet50":
+            runner = graphs.ResNet50Runner(ctx, spec, fuse=True)
+            dev_inputs = [ctx.to_device(inp["x"], channels_last=True)]
+            order = ["x"]
+            flops = graphs.resnet50_flops(spec) * batch
+        elif model == "resnet50_int8":
+            runner = graphs.ResNet50Int8Runner(ctx, spec, fuse=True, comm=comm)
+            dev_inputs = [ctx.to_device(inp["x"], channels_last=True)]
+            order = ["x"]
+            flops = None  # (the roofline block counts the integer ops of the same convolutions)
         else:
-            copy_out(step_fn())
-        if world > 1:
-            shard.all_gather_outputs(dist, out_t, gather_buf)
+            runner = graphs.BertRunner(ctx, spec, fuse=True)
+            dev_inputs = [ctx.to_device(inp["ids"]), ctx.to_device(inp["tt"]), ctx.to_device(inp["mask"])]
+            order = ["ids", "tt", "mask"]
+            flops = graphs.bert_flops(spec, batch, 128)
+        step_fn = lambda: runner.run(*dev_inputs)
+        out = step_fn()  # eager pass: plans measured, buffer pool warm
+        ctx.sync()
+        if args.plans and rank == 0:
+            ctx.save_plans(args.plans)
+        out_shape = tuple(out.shape)
+        del out
+        out_t = torch.empty(out_shape, dtype=torch.float32, device="cuda")
+        out_dst = rt.from_torch(ctx, out_t)
+        gather_bufs = [torch.empty(shard.gather_layout(world, out_shape), dtype=torch.float32, device="cuda") for _ in range(2)] if world > 1 else None
+        graph, o_fixed = None, None
+        # with a communicator the step contains NCCL calls issued by the library (range all-reduce): not captured
+        use_graph = not args.no_graph and comm is None
+        if use_graph:
+            ctx.graph_begin()
+            o_fixed = step_fn()
+            if world == 1:
+                copy_desc(ctx, o_fixed.desc(), out_dst.desc())
+            graph = ctx.graph_end()
+        ev_copied, ev_gathered = torch.cuda.Event(), [torch.cuda.Event(), torch.cuda.Event()]
+        counter = {"i": 0}
 
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+        def device_step():
+            """One step; at N > 1 the all-gather of step i runs on the comm stream, overlapped with step i + 1."""
+            i = counter["i"]
+            counter["i"] += 1
+            if graph is not None:
+                graph.launch()
+                o = o_fixed
+            else:
+                o = step_fn()
+            if world == 1:
+                if graph is None:
+                    copy_desc(ctx, o.desc(), out_dst.desc())
+                return
+            if i >= 1:
+                stream.wait_event(ev_gathered[(i - 1) % 2])  # out_t is free again (long since)
+            copy_desc(ctx, o.desc(), out_dst.desc())
+            ev_copied.record(stream)
+            comm_stream.wait_event(ev_copied)
+            with torch.cuda.stream(comm_stream):
+                shard.all_gather_outputs(dist, out_t, gather_bufs[i % 2])
+                ev_gathered[i % 2].record(comm_stream)
 
-    def timed(fn, steps, warmup, sampler=None):
-        for _ in range(warmup):
-            fn()
+        def timed(fn, steps, warmup, smp):
+            for _ in range(warmup):
+                fn()
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            if smp:
+                smp.start()
+            evs = []
+            l0 = ctx.launches
+            for _ in range(steps):
+                flush.zero_()  # L2 flush, outside the timed events
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record(stream)
+                fn()
+                e.record(stream)
+                evs.append((s, e))
+            tail = torch.cuda.Event(enable_timing=True)
+            tail.record(comm_stream if world > 1 else stream)  # after the last (overlapped) all-gather
+            torch.cuda.synchronize()
+            clocks = smp.stop() if smp else None
+            if world > 1:
+                dist.barrier()
+            ms = sum(s.elapsed_time(e) for s, e in evs) + max(0.0, evs[-1][1].elapsed_time(tail))
+            launches = ctx.launches - l0
+            if world > 1:
+                t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t.item())
+            return ms, launches, clocks
+
+        ms, launches, clocks = timed(device_step, args.steps, args.warmup, sampler)
+        res.update(value=batch * world * args.steps / (ms / 1e3), ms_per_step=ms / args.steps, gpu_launches=int(launches), clocks=clocks,
+                   cuda_graph=graph is not None, flops_per_step=flops)
+        if flops:
+            res["model_tflops"] = flops * world * args.steps / (ms / 1e3) / 1e12
+        if want_kernel_times and rank == 0 and graph is not None:
+            res["kernel_times"] = graph_kernel_times(torch, graph.launch)
+
+        # ---- e2e: pinned host inputs -> H2D -> step -> D2H of the result, every step, double-buffered on a copy stream
+        pinned = []
+        for name, d in zip(order, dev_inputs):
+            h = ctx.pinned_empty(inp[name].shape, inp[name].dtype)
+            h[...] = inp[name]
+            pinned.append((h, d))
+        h2d = sum(h.nbytes for h, _ in pinned)
+        copy_stream = torch.cuda.Stream()
+        cctx = rt.Context(local_rank, stream=copy_stream.cuda_stream)
+        raw = [[cctx.empty(h.shape, h.dtype) for h, _ in pinned] for _ in range(2)]
+        ev_in, ev_used, ev_done = ([torch.cuda.Event() for _ in range(2)] for _ in range(3))
+        host_outs = [ctx.pinned_empty(out_shape, np.float32) for _ in range(2)]
+        d2h = host_outs[0].nbytes
+        out_bufs = [ctx.empty(out_shape, np.float32) for _ in range(2)]
+
+        def issue_h2d(i):
+            b = i % 2
+            if i >= 2:
+                copy_stream.wait_event(ev_used[b])
+            for (h, _), r in zip(pinned, raw[b]):
+                copy_desc(cctx, host_desc(h), r.desc())
+            ev_in[b].record(copy_stream)
+
+        def issue_d2h(i):
+            b = i % 2
+            copy_stream.wait_event(ev_done[b])
+            copy_desc(cctx, out_bufs[b].desc(), host_desc(host_outs[b]))
+
+        def e2e_run(steps):
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record(copy_stream)
+            issue_h2d(0)
+            for i in range(steps):
+                b = i % 2
+                stream.wait_event(ev_in[b])
+                for (_, d), r in zip(pinned, raw[b]):
+                    copy_desc(ctx, r.desc(), d.desc())  # layout change (channels-last), device to device
+                ev_used[b].record(stream)
+                flush.zero_()  # L2 flush between steps (inside the timed region here)
+                device_step()
+                copy_desc(ctx, out_dst.desc(), out_bufs[b].desc())
+                ev_done[b].record(stream)
+                if i + 1 < steps:
+                    issue_h2d(i + 1)  # the host feeds the NEXT step and collects the PREVIOUS result while this one runs
+                if i >= 1:
+                    issue_d2h(i - 1)
+            issue_d2h(steps - 1)
+            t1.record(copy_stream)
+            torch.cuda.synchronize()
+            ms2 = t0.elapsed_time(t1)
+            if world > 1:
+                t = torch.tensor([ms2], dtype=torch.float64, device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms2 = float(t.item())
+            return ms2
+
+        e2e_run(3)
+        ms_e2e = e2e_run(args.steps)
+        res["e2e"] = {"value": batch * world * args.steps / (ms_e2e / 1e3), "unit": unit, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                      "ms_per_step": ms_e2e / args.steps,
+                      "how": "double-buffered: the copy stream moves step i+1's input H2D and step i-1's result D2H while step i computes; every step's H2D + D2H and the L2 flush are inside the timed region"}
+        if comm is not None:
+            comm.close()
+        return res
+
+    def run_gpt2(ctx, res):
+        """configs[4]: step = one decode step (8 tokens per GPU) replayed from one CUDA graph against a cache that holds a
+        512-token prefill.  e2e = the same step driven the way rten-generate drives it: token ids H2D, graph, logits D2H."""
+        run = graphs.GPT2Int8Runner(ctx, spec, batch, GPT2_CACHE)
+        ids = inp["ids"]
+        run.forward(ids[:, :GPT2_PREFILL])  # warm-up (autotune, pool)
+        run.reset()
+        ctx.set_autotune(False)
+        torch.cuda.synchronize()
+        s0, e0 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(stream)
+        run.forward(ids[:, :GPT2_PREFILL])
+        e0.record(stream)
+        ctx.set_autotune(not args.no_autotune)
+        run.build_decode_graph()
+        ctx.set_autotune(False)
+        torch.cuda.synchronize()
+        res["prefill_tokens_per_sec"] = batch * world * GPT2_PREFILL / (s0.elapsed_time(e0) / 1e3)
+        vocab = run._g_logits.shape[1]
+        host_logits = ctx.pinned_empty((batch, vocab), np.float32)
+        gather_buf = torch.empty((world * batch, vocab), dtype=torch.float32, device="cuda") if world > 1 else None
+        logits_t = torch.empty((batch, vocab), dtype=torch.float32, device="cuda")
+        logits_dst = rt.from_torch(ctx, logits_t)
+        nmax = GPT2_CACHE - GPT2_PREFILL - 1
+
+        def replay_only():
+            run._graph.launch()  # same cache position every time: the work of a step does not depend on it
+            if world > 1:
+                copy_desc(ctx, run._g_logits.desc(), logits_dst.desc())
+                shard.all_gather_outputs(dist, logits_t, gather_buf)
+
+        run._write_step_inputs(ids[:, GPT2_PREFILL:GPT2_PREFILL + 1])
+        for _ in range(args.warmup):
+            replay_only()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        torch.cuda.synchronize()
         if sampler:
             sampler.start()
-        evs = []
-        l0 = ctx.launches
-        for _ in range(steps):
-            flush.zero_()  # L2 flush, outside the timed events
+        evs, l0 = [], ctx.launches
+        for _ in range(args.steps):
+            flush.zero_()
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record(stream)
-            fn()
+            replay_only()
             e.record(stream)
             evs.append((s, e))
         torch.cuda.synchronize()
         clocks = sampler.stop() if sampler else None
-        if world > 1:
-            dist.barrier()
         ms = sum(s.elapsed_time(e) for s, e in evs)
         launches = ctx.launches - l0
         if world > 1:
             t = torch.tensor([ms], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        return ms, launches, clocks
-
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    ms, launches, clocks = timed(device_step, args.steps, args.warmup, sampler)
-    value = batch * world * args.steps / (ms / 1e3)
-
-    # ---- e2e: host (pinned) inputs -> H2D -> op list -> D2H of the result, all inside the timed region
-    import ctypes as C
-    pinned = []
-    order = ["x"] if model == "resnet50" else ["ids", "tt", "mask"]
-    for name, d in zip(order, dev_inputs):
-        h = ctx.pinned_empty(inp[name].shape, inp[name].dtype)
-        h[...] = inp[name]
-        pinned.append((h, d))
-    host_out = ctx.pinned_empty(out_shape, np.float32)
-    h2d = sum(h.nbytes for h, _ in pinned)
-    d2h = host_out.nbytes
-
-    # Double-buffered pipeline through the public API: a second context bound to a copy stream moves step i+1's input
-    # from pinned host memory into a raw device buffer while step i computes; the compute stream re-lays it out into the
-    # model's input tensor (channels-last for ResNet-50), replays the step and copies the result back to the host.
-    # EVERY step's H2D and D2H are inside the timed region; nothing is reused across steps.
-    copy_stream = torch.cuda.Stream()
-    cctx = rt.Context(local_rank, stream=copy_stream.cuda_stream)
-    raw = [[cctx.empty(h.shape, h.dtype) for h, _ in pinned] for _ in range(2)]
-    ev_copied = [torch.cuda.Event() for _ in range(2)]
-    ev_consumed = [torch.cuda.Event() for _ in range(2)]
-    host_outs = [host_out, ctx.pinned_empty(out_shape, np.float32)]
-
-    def issue_h2d(i):
-        b = i % 2
-        if i >= 2:
-            copy_stream.wait_event(ev_consumed[b])
-        for (h, _), r in zip(pinned, raw[b]):
-            src = rt.ops._desc(h.ctypes.data, h.dtype, h.shape, rt.ops._contig(h.shape), -1)
-            dst = r.desc()
-            cctx.check(cctx.lib.rten_b200_copy(cctx.handle, C.byref(src), C.byref(dst)))
-        ev_copied[b].record(copy_stream)
-
-    out_bufs = [ctx.empty(out_shape, np.float32) for _ in range(2)]
-    ev_done = [torch.cuda.Event() for _ in range(2)]
-
-    def issue_d2h(i):
-        # result of step i: device copy made by the compute stream -> pinned host buffer, on the copy stream
-        b = i % 2
-        copy_stream.wait_event(ev_done[b])
-        src = out_bufs[b].desc()
-        ho = host_outs[b]
-        dst = rt.ops._desc(ho.ctypes.data, ho.dtype, ho.shape, rt.ops._contig(ho.shape), -1)
-        cctx.check(cctx.lib.rten_b200_copy(cctx.handle, C.byref(src), C.byref(dst)))
-
-    def e2e_run(steps):
-        """-> device milliseconds from the first H2D to the last D2H of `steps` pipelined steps"""
+        res.update(value=batch * world * args.steps / (ms / 1e3), ms_per_step=ms / args.steps, gpu_launches=int(launches), clocks=clocks, cuda_graph=True,
+                   flops_per_step=None)
+        if rank == 0:
+            res["kernel_times"] = graph_kernel_times(torch, run._graph.launch)
+        # e2e: ids H2D (+ position bookkeeping), replay, logits D2H to pinned host memory, synchronously per step
+        steps = min(args.steps, nmax)
         torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0.record(copy_stream)
-        issue_h2d(0)
+        t0.record(stream)
         for i in range(steps):
-            b = i % 2
-            stream.wait_event(ev_copied[b])
-            for (_, d), r in zip(pinned, raw[b]):
-                a_, b_ = r.desc(), d.desc()
-                ctx.check(ctx.lib.rten_b200_copy(ctx.handle, C.byref(a_), C.byref(b_)))  # layout change, device to device
-            ev_consumed[b].record(stream)
-            flush.zero_()  # L2 flush between steps (inside the timed region here)
-            device_step()
-            a_, b_ = out_dst.desc(), out_bufs[b].desc()
-            ctx.check(ctx.lib.rten_b200_copy(ctx.handle, C.byref(a_), C.byref(b_)))
-            ev_done[b].record(stream)
-            # the host now feeds the NEXT step and collects the PREVIOUS result while this step runs
-            if i + 1 < steps:
-                issue_h2d(i + 1)
-            if i >= 1:
-                issue_d2h(i - 1)
-        issue_d2h(steps - 1)
-        t1.record(copy_stream)
+            lg = run.decode_step(ids[:, GPT2_PREFILL + i:GPT2_PREFILL + i + 1])
+            copy_desc(ctx, lg.desc(), host_desc(host_logits))
+        t1.record(stream)
         torch.cuda.synchronize()
-        ms = t0.elapsed_time(t1)
-        if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
+        ms2 = t0.elapsed_time(t1)
+        res["e2e"] = {"value": batch * world * steps / (ms2 / 1e3), "unit": unit, "h2d_bytes_per_step": int(run._host_ints.nbytes + run._host_len.nbytes),
+                      "d2h_bytes_per_step": int(host_logits.nbytes), "ms_per_step": ms2 / steps,
+                      "how": "per step: token ids / position / cache length H2D, one graph replay, logits D2H to pinned host memory, host-synchronous (the next token depends on the logits)"}
+        # algorithmic HBM bytes of a decode step: int8 weights once + the valid part of the f32 KV cache once
+        wbytes = sum(l.wq.size for L in spec.layers for l in (L.attn, L.proj, L.fc, L.fc2)) + spec.lm_head.wq.size
+        kv = 2 * len(spec.layers) * batch * spec.hidden * 4 * (GPT2_PREFILL + 1)
+        res["algorithmic_bytes_per_step"] = float(wbytes + kv)
+        return res
 
-    e2e_run(3)
-    ms_e2e = e2e_run(args.steps)
-    e2e_value = batch * world * args.steps / (ms_e2e / 1e3)
+    # ---- the measured modes
+    results = {}
+    for k, mode in enumerate(modes):
+        results[mode] = run_mode(mode, want_kernel_times=True)
+    head = results[modes[0]]
 
-    # ---- roofline of the dominant kernel: per-launch CUDA-event timing of every GEMM/conv op of one pass
-    roof = None
-    if rank == 0:
-        roof = roofline_pass(ctx, rt, runner, model, spec, dev_inputs, batch, stream, torch)
-
+    peaks_meas = None
+    if rank == 0 and not args.no_peaks:
+        peaks_meas = measure_matmul_peaks(torch)
     extras = None
-    if rank == 0 and not args.no_extras:
-        extras = secondary_numbers(ctx, rt, graphs, oracle, model, stream, torch, flush)
+    if rank == 0 and not args.no_extras and model == "resnet50":
+        extras = secondary_numbers(rt, graphs, oracle, stream, torch, flush, sampler, local_rank)
 
     if rank == 0:
         peaks = load_peaks()
-        line = {
-            "metric": metric_name(model), "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32(tf32 mma)",
-            "data": "synthetic", "config": config_of(model, batch, world), "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": ms_e2e / args.steps,
-                    "how": "double-buffered: the copy stream moves step i+1's input H2D and step i-1's result D2H while step i computes; every step's H2D + D2H and the L2 flush are inside the timed region"},
-            "gpu_launches": int(launches),
-            "cuda_graph": graph is not None,
-            "model_tflops": flops * world * args.steps / (ms / 1e3) / 1e12,
-        }
-        if roof:
-            tf32_peak = 0.5 * peaks["bf16_sustained"]
-            roof_line = {"bound": "tensor", "kernel": "rtb::umma_gemm_kernel<0> (tcgen05 kind::tf32 implicit-GEMM conv / GEMM)",
-                         "achieved": roof["tflops"], "peak": tf32_peak, "unit": "TFLOP/s", "frac": roof["tflops"] / tf32_peak,
-                         "traffic": ncu_traffic(), "launches_timed": roof["launches"], "share_of_step": roof["share"],
-                         "peak_source": f"0.5 x {peaks['src']} bf16 sustained ({peaks['bf16_sustained']} TF/s): kind::tf32 issues at half the bf16 rate",
-                         # the same launches against the other roof: at batch 32 the wide 1x1 layers are nearer to it
-                         "hbm_view": {"achieved": roof["gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                                      "frac": roof["gbs"] / peaks["hbm_gbs"], "bytes": "algorithmic: operands + output (+ residual) once"}}
-            line["roofline"] = roof_line
+
+        def peak_of(kind):
+            if peaks_meas and kind in peaks_meas and "burst" in peaks_meas[kind]:
+                return peaks_meas[kind]["burst"], peaks_meas[kind]["sustained"], "measured in this run: cuBLASLt 8192^3 through torch (burst = best of 10, sustained = 3 s)"
+            f = 0.5 if kind == "tf32" else 2.0
+            return f * peaks["bf16_burst"], f * peaks["bf16_sustained"], f"{f} x bf16 of {peaks['src']} (no on-box measurement in this run)"
+
+        def roofline_of(r):
+            kt = r.get("kernel_times")
+            step_ms = r["ms_per_step"]
+            if model == "gpt2":
+                ach_lb = r["algorithmic_bytes_per_step"] / (step_ms / 1e3) / 1e9
+                kern_us = sum(t for name, (_, t) in kt.items() if "qlinear" in name or "attn_decode" in name) if kt else None
+                if kern_us:
+                    kern_us = min(kern_us, step_ms * 1e3)  # (durations overlap under programmatic dependent launch)
+                ach = r["algorithmic_bytes_per_step"] / (kern_us / 1e6) / 1e9 if kern_us else ach_lb
+                return {"bound": "hbm", "kernel": "rtb::qlinear_kernel + rtb::attn_decode_kernel (decode step: int8 weights + f32 KV cache streamed once)",
+                        "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None,
+                        "lower_bound": {"achieved": ach_lb, "frac": ach_lb / peaks["hbm_gbs"], "how": "algorithmic bytes / whole step time"},
+                        "kernel_time_us_per_step": kern_us, "source": "CUPTI kernel records of the graph replay" if kern_us else "whole step time",
+                        "peak_source": peaks["src"]}
+            kind = "int8" if model == "resnet50_int8" else "tf32"
+            fl = r.get("flops_per_step")
+            if model == "resnet50_int8":
+                fl = graphs.resnet50_flops(make_spec(oracle, "resnet50")) * batch
+            burst, sust, psrc = peak_of(kind)
+            lb = fl / (step_ms / 1e3) / 1e12
+            kern_us = sum(t for name, (_, t) in kt.items() if "umma_" in name) if kt else None
+            n_kern = sum(c for name, (c, _) in kt.items() if "umma_" in name) if kt else None
+            # With programmatic dependent launch the kernels of a step OVERLAP (kernel n + 1 is resident, waiting in
+            # griddepcontrol.wait, while kernel n drains), so the sum of the CUPTI durations can exceed the step time: the
+            # time the tensor-core kernels occupy the GPU is then bounded by the step itself.
+            busy_us = min(kern_us, step_ms * 1e3) if kern_us else None
+            ach = fl / (busy_us / 1e6) / 1e12 if busy_us else lb
+            return {"bound": "tensor", "kernel": f"rtb::umma_gemm_kernel<{1 if kind == 'int8' else 0}> (tcgen05 kind::{'i8' if kind == 'int8' else 'tf32'} implicit-GEMM conv / GEMM)",
+                    "achieved": ach, "peak": burst, "unit": "TFLOP/s" if kind == "tf32" else "TOP/s", "frac": ach / burst, "frac_of_sustained_peak": ach / sust,
+                    "traffic": ncu_traffic(model),
+                    "lower_bound": {"achieved": lb, "frac": lb / burst, "how": "algorithmic flops / whole step time (kernel time <= step time)"},
+                    "kernel_time_us_per_step": busy_us, "sum_of_kernel_durations_us": kern_us, "launches_per_step": n_kern,
+                    "share_of_step": (busy_us / 1e3 / step_ms) if busy_us else None,
+                    "source": ("CUPTI kernel records of the GRAPH replay (torch.profiler); durations overlap under programmatic dependent launch, "
+                               "so the busy time is min(sum of durations, step time)") if kern_us else "whole step time (profiler unavailable)",
+                    "peak_source": psrc,
+                    "hbm_view": {"achieved": hbm_bytes(model, spec, batch) / (step_ms / 1e3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                 "frac": hbm_bytes(model, spec, batch) / (step_ms / 1e3) / 1e9 / peaks["hbm_gbs"],
+                                 "bytes": "algorithmic: every operand / output / residual of every conv and GEMM once, over the whole step time"}}
+
+        def public(r):
+            keep = {k: r[k] for k in ("value", "ms_per_step", "gpu_launches", "clocks", "e2e", "cuda_graph") if k in r}
+            if r.get("model_tflops"):
+                keep["model_tflops"] = r["model_tflops"]
+            if r.get("prefill_tokens_per_sec"):
+                keep["prefill_tokens_per_sec"] = r["prefill_tokens_per_sec"]
+            keep["roofline"] = roofline_of(r)
+            if r.get("kernel_times"):
+                top = sorted(r["kernel_times"].items(), key=lambda kv: -kv[1][1])[:6]
+                keep["top_kernels_us_per_step"] = {k[:70]: round(v[1], 1) for k, v in top}
+            return keep
+
+        dtype = {"tf32": "f32(tf32 mma, explicit opt-in)", "tf32x3": "f32(3xtf32 mma, fp32-grade)", "int8": "u8 x i8 -> i32 (f32 between layers)"}[modes[0]]
+        line = {"metric": metric_name(model), "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic", "config": config_of(model, batch, world)}
+        line.update(public(head))
+        line["f32_mode"] = modes[0] if modes[0] != "int8" else None
+        if len(modes) > 1:
+            line["modes"] = {m: public(results[m]) for m in modes[1:]}
+            for m in modes[1:]:
+                line["modes"][m]["dtype"] = "f32(3xtf32 mma, fp32-grade: library default)"
+        if peaks_meas:
+            line["peaks_measured"] = peaks_meas
         if extras:
-            tf32_peak = 0.5 * peaks["bf16_burst"]
-            extras["gemm_tf32_8192_frac_of_peak"] = extras["gemm_tf32_8192_tflops"] / tf32_peak
-            extras["gemm_int8_8192_frac_of_peak"] = extras["gemm_int8_8192_tops"] / (2.0 * peaks["bf16_burst"])
-            extras["peaks"] = f"tf32 = 0.5 x, int8 = 2 x {peaks['src']} bf16 burst ({peaks['bf16_burst']} TF/s): kernels timed alone"
+            b_tf32, _, src = peak_of("tf32")
+            b_i8, _, _ = peak_of("int8")
+            extras["gemm_tf32_8192_frac_of_peak"] = extras["gemm_tf32_8192_tflops"] / b_tf32
+            extras["gemm_int8_8192_frac_of_peak"] = extras["gemm_int8_8192_tops"] / b_i8
+            extras["peaks"] = src
             line["also"] = extras
         if not args.no_cpu_baseline:
             a2 = argparse.Namespace(**vars(args))
-            a2.steps, a2.warmup = 1, 1
-            ref = run_reference_arm(a2, model, batch)
-            line["cpu_baseline"] = ref["cpu_baseline"]
+            a2.steps, a2.warmup, a2.gpus = 1, 1, 1
+            line["cpu_baseline"] = run_reference_arm(a2, model, batch)["cpu_baseline"]
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
-def ncu_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu capture of
-    this same command (profiles/r01_ncu_resnet50.json); None if that summary is absent."""
-    p = os.path.join(ROOT, "profiles", "r01_ncu_resnet50.json")
-    try:
-        return json.load(open(p))["umma_avg_dram_bytes_per_launch"]
-    except Exception:
-        return None
+def hbm_bytes(model, spec, batch):
+    """Algorithmic bytes of the tensor-core ops of one step: activations in / out (+ residual) and weights once."""
+    if model == "bert":
+        h, f, t = spec.hidden, spec.ffn, batch * 128
+        per_layer = 4 * (4 * h * h + 2 * h * f) + 4 * t * (h * 8 + 2 * f) + 4 * 2 * batch * spec.heads * 128 * 128
+        return float(per_layer * len(spec.layers))
+    es_in = 1 if model == "resnet50_int8" else 4
+    total, hw = 0.0, 224
+
+    def conv(c, h_in):
+        w = c.wq if hasattr(c, "wq") else c.w
+        o, i, k, _ = w.shape
+        ho = (h_in + 2 * c.pad - k) // c.stride + 1
+        return batch * (i * h_in * h_in * es_in + o * ho * ho * 4) + w.size * es_in, ho
+
+    b0, h = conv(spec.stem, hw)
+    total += b0
+    h = (h + 2 - 3) // 2 + 1
+    for blk in spec.blocks:
+        b1, h1 = conv(blk.c1, h)
+        b2, h2 = conv(blk.c2, h1)
+        b3, h3 = conv(blk.c3, h2)
+        total += b1 + b2 + b3 + batch * blk.c3.b.size * h3 * h3 * 4  # + the residual read
+        if blk.down is not None:
+            total += conv(blk.down, h)[0]
+        h = h3
+    return total
 
 
-def secondary_numbers(ctx, rt, graphs, oracle, model, stream, torch, flush):
-    """Secondary numbers the BASELINE metric names (BERT-base pass, GEMM TFLOP/s); same timing hygiene, few steps."""
+def ncu_traffic(model):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full`
+    capture of this same command (profiles/r02_ncu_<model>.json, falling back to round 1's); None if absent."""
+    for name in (f"r02_ncu_{model}.json", "r01_ncu_resnet50.json" if model == "resnet50" else ""):
+        p = os.path.join(ROOT, "profiles", name)
+        try:
+            return json.load(open(p))["umma_avg_dram_bytes_per_launch"]
+        except Exception:
+            continue
+    return None
+
+
+def secondary_numbers(rt, graphs, oracle, stream, torch, flush, sampler, device):
+    """Secondary numbers the BASELINE metric names, same timing hygiene, few steps, each with its own clock sample."""
     out = {}
+    ctx = rt.Context(device, stream=stream.cuda_stream)
+    ctx.set_f32_mode(False)
+    ctx.set_autotune(True)
 
-    def timed(fn, iters=5, warm=2):
+    def timed(fn, iters=5, warm=2, tag=None):
         fn()
         ctx.graph_begin()
         fn()
         g = ctx.graph_end()
         for _ in range(warm):
             g.launch()
+        torch.cuda.synchronize()
+        if sampler:
+            sampler.start()
         ms = []
         for _ in range(iters):
             flush.zero_()
@@ -445,130 +774,69 @@ def secondary_numbers(ctx, rt, graphs, oracle, model, stream, torch, flush):
             e.record(stream)
             torch.cuda.synchronize()
             ms.append(s.elapsed_time(e))
+        if sampler and tag:
+            out.setdefault("clocks", {})[tag] = sampler.stop()
+        del g
         return float(np.median(ms))
 
     n = 8192
     a = rt.from_torch(ctx, torch.randn(n, n, device="cuda"))
     b = rt.from_torch(ctx, torch.randn(n, n, device="cuda")).permute(1, 0)
     o = ctx.empty((n, n))
-    ms = timed(lambda: rt.MatMul().run(ctx, a, b, out=o))
-    out["gemm_tf32_8192_tflops"] = 2.0 * n ** 3 / ms / 1e9
+    out["gemm_tf32_8192_tflops"] = 2.0 * n ** 3 / timed(lambda: rt.MatMul().run(ctx, a, b, out=o), tag="gemm_tf32_8192") / 1e9
     ai = rt.from_torch(ctx, torch.randint(0, 255, (n, n), device="cuda", dtype=torch.uint8))
     bi = rt.from_torch(ctx, torch.randint(-128, 127, (n, n), device="cuda", dtype=torch.int8)).permute(1, 0)
     oi = ctx.empty((n, n), np.int32)
-    ms = timed(lambda: rt.MatMulInteger().run(ctx, ai, bi, out=oi))
-    out["gemm_int8_8192_tops"] = 2.0 * n ** 3 / ms / 1e9
+    out["gemm_int8_8192_tops"] = 2.0 * n ** 3 / timed(lambda: rt.MatMulInteger().run(ctx, ai, bi, out=oi), tag="gemm_int8_8192") / 1e9
     del a, b, o, ai, bi, oi
-    other = "bert" if model == "resnet50" else "resnet50"
-    spec = make_spec(oracle, other)
-    inp = make_inputs(oracle, other, 16 if other == "bert" else 32)
-    if other == "bert":
+    spec = make_spec(oracle, "bert")
+    inp = make_inputs(oracle, "bert", 16)
+    for mode, x3 in (("tf32", False), ("tf32x3", True)):
+        ctx.set_f32_mode(x3)
         runner = graphs.BertRunner(ctx, spec)
         ids, tt, mask = ctx.to_device(inp["ids"]), ctx.to_device(inp["tt"]), ctx.to_device(inp["mask"])
-        ms = timed(lambda: runner.run(ids, tt, mask))
-        out["bert_base_fp32_b16_s128_seq_per_sec"] = 16 / (ms / 1e3)
-        out["bert_base_model_tflops"] = graphs.bert_flops(spec, 16, 128) / ms / 1e9
-    else:
-        runner = graphs.ResNet50Runner(ctx, spec)
-        x = ctx.to_device(inp["x"], channels_last=True)
-        ms = timed(lambda: runner.run(x))
-        out["resnet50_fp32_b32_img_per_sec"] = 32 / (ms / 1e3)
-    del runner
-    # configs[3]: dynamically quantised ResNet-50, batch 64 (DynamicQuantizeLinear -> ConvIntegerToFloat(+bias, +identity, Relu))
-    rspec = spec if other == "resnet50" else make_spec(oracle, "resnet50")
-    qrunner = graphs.ResNet50Int8Runner(ctx, graphs.quantize_resnet50(rspec), fuse=True)
+        ms = timed(lambda: runner.run(ids, tt, mask), tag=f"bert_{mode}")
+        out[f"bert_base_fp32_b16_s128_seq_per_sec_{mode}"] = 16 / (ms / 1e3)
+        out[f"bert_base_model_tflops_{mode}"] = graphs.bert_flops(spec, 16, 128) / ms / 1e9
+        del runner
+    ctx.set_f32_mode(False)
+    # configs[3]: dynamically quantised ResNet-50, batch 64
+    qrunner = graphs.ResNet50Int8Runner(ctx, make_spec(oracle, "resnet50_int8"), fuse=True)
     x64 = ctx.to_device(make_inputs(oracle, "resnet50", 64)["x"], channels_last=True)
-    ms = timed(lambda: qrunner.run(x64))
+    ms = timed(lambda: qrunner.run(x64), tag="resnet50_int8")
     out["resnet50_int8_b64_img_per_sec"] = 64 / (ms / 1e3)
     del qrunner, x64
-    # configs[4]: GPT-2 small int8, batch 8: prefill of 512 tokens, then decode steps against the KV cache (eager
-    # launches: the cache length changes every step)
-    grng = oracle.XorShiftRng(5678)
-    gspec = graphs.make_gpt2_int8(lambda s: grng.uniform(s))
-    grun = graphs.GPT2Int8Runner(ctx, gspec, 8, 576)
-    gids = (oracle.XorShiftRng(1).u64(8 * 576) % 50257).astype(np.int32).reshape(8, 576)
-    grun.forward(gids[:, :512])  # warm-up (autotune, pool)
-    grun.forward(gids[:, 512:513])
+    # configs[4]: GPT-2 small int8, batch 8: prefill of 512 tokens, then graph-replayed decode steps (fused decode path)
+    ctx.set_f32_mode(True)  # the f32 attention products of the prefill at fp32 grade (library default)
+    gspec = make_spec(oracle, "gpt2")
+    grun = graphs.GPT2Int8Runner(ctx, gspec, 8, GPT2_CACHE)
+    gids = make_inputs(oracle, "gpt2", 8)["ids"]
+    grun.forward(gids[:, :GPT2_PREFILL])
     grun.reset()
-    ctx.set_autotune(False)  # keep the measured plans, stop measuring: the attention shapes change every decode step
+    ctx.set_autotune(False)
     torch.cuda.synchronize()
     s0, e0 = (torch.cuda.Event(enable_timing=True) for _ in range(2))
     s0.record(stream)
-    grun.forward(gids[:, :512])
+    grun.forward(gids[:, :GPT2_PREFILL])
     e0.record(stream)
-    ndec = 32
     ctx.set_autotune(True)
-    grun.build_decode_graph()  # untimed: capture of the fixed-shape decode step
+    grun.build_decode_graph()
     ctx.set_autotune(False)
     torch.cuda.synchronize()
+    ndec = 32
+    if sampler:
+        sampler.start()
     e0b, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0b.record(stream)
     for i in range(ndec):
-        grun.decode_step(gids[:, 512 + i:513 + i])  # per step: two small H2D copies + one graph replay
+        grun.decode_step(gids[:, GPT2_PREFILL + i:GPT2_PREFILL + i + 1])  # per step: small H2D copies + one graph replay
     e1.record(stream)
     torch.cuda.synchronize()
-    out["gpt2_int8_b8_prefill512_tokens_per_sec"] = 8 * 512 / (s0.elapsed_time(e0) / 1e3)
+    if sampler:
+        out.setdefault("clocks", {})["gpt2"] = sampler.stop()
+    out["gpt2_int8_b8_prefill512_tokens_per_sec"] = 8 * GPT2_PREFILL / (s0.elapsed_time(e0) / 1e3)
     out["gpt2_int8_b8_decode_tokens_per_sec"] = 8 * ndec / (e0b.elapsed_time(e1) / 1e3)
     return out
-
-
-def roofline_pass(ctx, rt, runner, model, spec, dev_inputs, batch, stream, torch):
-    """Time each tensor-core op of one eager pass with CUDA events on the launching stream (3 repetitions, after
-    warm-up) and divide the algorithmic flops by the summed durations."""
-    import rten_b200.ops as O
-    records = []
-    orig_conv, orig_mm, orig_mm0 = O.Conv.run, O.FusedMatMul.run, O.MatMul.run
-
-    def nbytes(t):
-        return float(np.prod(t.shape)) * 4.0 if t is not None and hasattr(t, "shape") else 0.0
-
-    def wrap(orig, flops_fn):
-        def run(self, c, *a, **k):
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record(stream)
-            y = orig(self, c, *a, **k)
-            e.record(stream)
-            # algorithmic bytes: every operand read once, the output written once (SURVEY.md 8d)
-            by = nbytes(a[0]) + nbytes(a[1]) + nbytes(y) + nbytes(k.get("residual")) + (nbytes(a[2]) if len(a) > 2 else 0.0)
-            records.append((s, e, flops_fn(a, y), by))
-            return y
-        return run
-
-    def conv_flops(a, y):
-        w = a[1]
-        b, o, oh, ow = y.shape
-        return 2.0 * b * o * oh * ow * w.shape[1] * w.shape[2] * w.shape[3]
-
-    def mm_flops(a, y):
-        k = a[0].shape[-1]
-        return 2.0 * float(np.prod(y.shape)) * k
-
-    O.Conv.run = wrap(orig_conv, conv_flops)
-    O.FusedMatMul.run = wrap(orig_mm, mm_flops)
-    O.MatMul.run = wrap(orig_mm0, mm_flops)
-    try:
-        tot_ms, tot_fl, tot_by, n = 0.0, 0.0, 0.0, 0
-        for rep in range(4):
-            records.clear()
-            s0, e0 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s0.record(stream)
-            if model == "resnet50":
-                runner.run(dev_inputs[0])
-            else:
-                runner.run(*dev_inputs)
-            e0.record(stream)
-            torch.cuda.synchronize()
-            if rep == 0:
-                continue
-            tot_ms += sum(s.elapsed_time(e) for s, e, _, _ in records)
-            tot_fl += sum(f for _, _, f, _ in records)
-            tot_by += sum(b for _, _, _, b in records)
-            n += len(records)
-            step_ms = s0.elapsed_time(e0)
-            share = sum(s.elapsed_time(e) for s, e, _, _ in records) / step_ms
-    finally:
-        O.Conv.run, O.FusedMatMul.run, O.MatMul.run = orig_conv, orig_mm, orig_mm0
-    return {"tflops": tot_fl / (tot_ms / 1e3) / 1e12, "gbs": tot_by / (tot_ms / 1e3) / 1e9, "launches": n, "share": share}
 
 
 if __name__ == "__main__":

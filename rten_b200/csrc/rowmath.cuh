@@ -29,9 +29,11 @@ __device__ __forceinline__ int rne_i32_x86(float v) {
     return __float2int_rn(v);
 }
 __device__ __forceinline__ uint8_t quant1(float x, float inv_scale, int zp) {
-    long long q = (long long)rne_i32_x86(__fmul_rn(x, inv_scale)) + zp;
-    q = q < 0 ? 0 : (q > 255 ? 255 : q);
-    return (uint8_t)q;
+    // saturate_u8(round(x * inv_scale) + zp): the rounded value is clamped to [-256, 511] first -- anything outside
+    // saturates the same way -- so that the sum stays in 32 bits (zp is in [0, 255])
+    int r = rne_i32_x86(__fmul_rn(x, inv_scale));
+    r = max(-256, min(511, r));
+    return (uint8_t)max(0, min(255, r + zp));
 }
 
 template <bool SQSUB>

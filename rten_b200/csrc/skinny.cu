@@ -66,56 +66,185 @@ __device__ __forceinline__ void reduce_scatter_warp(T (&v)[NV], int lane, int& b
 
 // =========================================================================================
 // Fused [LayerNorm] -> DynamicQuantizeLinear -> int8 GEMV -> scale / bias / residual / activation
+//
+// Everything here is latency, not throughput (a decode step moves a few megabytes): the kernel is organised so that
+// every long-latency access is issued as early as its address is known -- the weight tile of a warp (CPW columns x K
+// bytes, <= 16 x 16 bytes per lane) is loaded into REGISTERS before the kernel even waits for its predecessor (the
+// weights do not depend on it), the next tile's weights and epilogue vectors are loaded while the current tile is
+// multiplied, LayerNorm's gamma / beta are requested together with the row.
 // =========================================================================================
 struct QLinearParams {
     QLinearLaunch L;
     int tiles;  // column tiles of 8 * CPW columns
 };
 
-// One row of x, optionally layer-normalised, as float4s in the vector-LayerNorm mapping (32 lanes per row):
-// thread (c = lane & 15, seg = lane >> 4) holds the float4s f = c + 16 (seg F + k), k < F = K / 128.
-__device__ __forceinline__ void qlin_ln_row(const QLinearLaunch& L, int r, int lane, float4 (&v)[16]) {
-    const int c = lane & 15, seg = lane >> 4;
-    const int F = L.K >> 7;
-    const float4* x4 = reinterpret_cast<const float4*>(L.x + (long long)r * L.xs);
-#pragma unroll
-    for (int k = 0; k < 16; k++)
-        if (k < F) v[k] = x4[c + 16 * (seg * F + k)];
-    const float mean = __fdiv_rn(ln_vec_fold<2, false>(v, F, 0.0f, c, seg), (float)L.K);
-    const float var = __fdiv_rn(ln_vec_fold<2, true>(v, F, mean, c, seg), (float)L.K);
-    const float rstd = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(var, L.ln_eps)));
-    const float4* g4 = reinterpret_cast<const float4*>(L.ln_gamma);
-    const float4* b4 = reinterpret_cast<const float4*>(L.ln_beta);
-#pragma unroll
-    for (int k = 0; k < 16; k++) {
-        if (k < F) {
-            const int f = c + 16 * (seg * F + k);
-            const float4 a = v[k];
-            const float4 g = __ldg(g4 + f);
-            if (!L.ln_beta) {  // (same arm as layer_norm_vec_kernel's mode 1)
-                v[k] = make_float4(__fmul_rn(__fsub_rn(a.x, mean), __fmul_rn(g.x, rstd)), __fmul_rn(__fsub_rn(a.y, mean), __fmul_rn(g.y, rstd)),
-                                   __fmul_rn(__fsub_rn(a.z, mean), __fmul_rn(g.z, rstd)), __fmul_rn(__fsub_rn(a.w, mean), __fmul_rn(g.w, rstd)));
-            } else {  // (mode 2: beta + the scalar bias 0.0)
-                const float4 b = __ldg(b4 + f);
-                v[k] = make_float4(__fmaf_rn(__fsub_rn(a.x, mean), __fmul_rn(g.x, rstd), __fadd_rn(b.x, 0.0f)),
-                                   __fmaf_rn(__fsub_rn(a.y, mean), __fmul_rn(g.y, rstd), __fadd_rn(b.y, 0.0f)),
-                                   __fmaf_rn(__fsub_rn(a.z, mean), __fmul_rn(g.z, rstd), __fadd_rn(b.z, 0.0f)),
-                                   __fmaf_rn(__fsub_rn(a.w, mean), __fmul_rn(g.w, rstd), __fadd_rn(b.w, 0.0f)));
-            }
-        }
-    }
-}
-
 __device__ __forceinline__ uint32_t quant4(float4 a, float inv, int zp) {
     return (uint32_t)quant1(a.x, inv, zp) | ((uint32_t)quant1(a.y, inv, zp) << 8) | ((uint32_t)quant1(a.z, inv, zp) << 16) |
            ((uint32_t)quant1(a.w, inv, zp) << 24);
 }
 
-template <int MT, int CPW, bool WSIGNED>
-__global__ void __launch_bounds__(256) qlinear_kernel(const QLinearParams p) {
+// One row of x, layer-normalised, as float4s in the vector-LayerNorm mapping (32 lanes per row): thread
+// (c = lane & 15, seg = lane >> 4) holds the float4s f = c + 16 (seg F + k), k < F = K / 128 <= 8.  Same arithmetic
+// as layer_norm_vec_kernel<2, .> (rowops.cu), so the values equal the LayerNormalization operator's bit for bit.
+template <int FLN>
+__device__ __forceinline__ void qlin_ln_row(const QLinearLaunch& L, int r, int lane, float4 (&v)[FLN]) {
+    const int c = lane & 15, seg = lane >> 4;
+    const int F = L.K >> 7;
+    const float4* x4 = reinterpret_cast<const float4*>(L.x + (long long)r * L.xs);
+    const float4* g4 = reinterpret_cast<const float4*>(L.ln_gamma);
+    const float4* b4 = reinterpret_cast<const float4*>(L.ln_beta);
+    float4 g[FLN], bt[FLN];
+#pragma unroll
+    for (int k = 0; k < FLN; k++)
+        if (k < F) v[k] = x4[c + 16 * (seg * F + k)];
+#pragma unroll
+    for (int k = 0; k < FLN; k++) {  // requested now, needed after the two reductions
+        if (k < F) {
+            g[k] = __ldg(g4 + c + 16 * (seg * F + k));
+            if (L.ln_beta) bt[k] = __ldg(b4 + c + 16 * (seg * F + k));
+        }
+    }
+    const float mean = __fdiv_rn(ln_vec_fold<2, false, FLN>(v, F, 0.0f, c, seg), (float)L.K);
+    const float var = __fdiv_rn(ln_vec_fold<2, true, FLN>(v, F, mean, c, seg), (float)L.K);
+    const float rstd = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(var, L.ln_eps)));
+#pragma unroll
+    for (int k = 0; k < FLN; k++) {
+        if (k < F) {
+            const float4 a = v[k];
+            if (!L.ln_beta) {  // (same arm as layer_norm_vec_kernel's mode 1)
+                v[k] = make_float4(__fmul_rn(__fsub_rn(a.x, mean), __fmul_rn(g[k].x, rstd)), __fmul_rn(__fsub_rn(a.y, mean), __fmul_rn(g[k].y, rstd)),
+                                   __fmul_rn(__fsub_rn(a.z, mean), __fmul_rn(g[k].z, rstd)), __fmul_rn(__fsub_rn(a.w, mean), __fmul_rn(g[k].w, rstd)));
+            } else {  // (mode 2: beta + the scalar bias 0.0)
+                v[k] = make_float4(__fmaf_rn(__fsub_rn(a.x, mean), __fmul_rn(g[k].x, rstd), __fadd_rn(bt[k].x, 0.0f)),
+                                   __fmaf_rn(__fsub_rn(a.y, mean), __fmul_rn(g[k].y, rstd), __fadd_rn(bt[k].y, 0.0f)),
+                                   __fmaf_rn(__fsub_rn(a.z, mean), __fmul_rn(g[k].z, rstd), __fadd_rn(bt[k].z, 0.0f)),
+                                   __fmaf_rn(__fsub_rn(a.w, mean), __fmul_rn(g[k].w, rstd), __fadd_rn(bt[k].w, 0.0f)));
+            }
+        }
+    }
+}
+
+// The (row m, column offset j) whose complete sum lane `lane` holds after reduce_scatter_warp<NV> (a function of the
+// lane number only), so that the epilogue vectors of that output can be requested together with the weights.
+template <int NV>
+__device__ __forceinline__ int scatter_base(int lane) {
+    int base = 0, n = NV;
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        if (n > 1) {
+            n >>= 1;
+            if (lane & o) base += n;
+        }
+    }
+    return base;
+}
+
+// Registers of one column tile of a warp: the weights (KI x CPW 16-byte chunks per lane) and the per-output epilogue
+// operands of the (at most two) outputs this lane will finish.
+template <int MT, int CPW, int KI>
+struct QTile {
+    static constexpr int NV = MT * CPW;
+    static constexpr int NOUT = NV > 32 ? NV / 32 : 1;
+    uint4 w[KI][CPW];
+    int colsum[NOUT];
+    float wscale[NOUT], bias[NOUT], res[NOUT];
+    unsigned zb[NOUT];
+
+    __device__ __forceinline__ void load(const QLinearLaunch& L, int n0, int lane, int base) {
+        const uint8_t* wp = reinterpret_cast<const uint8_t*>(L.w);
+        const int KC = L.K >> 4;
+#pragma unroll
+        for (int it = 0; it < KI; it++) {
+            const int c = lane + 32 * it;
+#pragma unroll
+            for (int j = 0; j < CPW; j++) {
+                const int n = n0 + j < L.N ? n0 + j : L.N - 1;  // (clamped: the duplicate column is never stored)
+                w[it][j] = (c < KC && n0 < L.N) ? __ldg(reinterpret_cast<const uint4*>(wp + (long long)n * L.ldw) + c) : make_uint4(0u, 0u, 0u, 0u);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < NOUT; i++) {
+            const int idx = base + i;
+            const int m = idx / CPW, n = n0 + idx % CPW;
+            const bool ok = m < L.M && n < L.N;
+            colsum[i] = ok ? __ldg(L.colsum + n) : 0;
+            wscale[i] = ok ? __ldg(L.w_scale + (L.w_scale_len == 1 ? 0 : n)) : 0.0f;
+            bias[i] = (ok && L.bias) ? __ldg(L.bias + n) : 0.0f;
+            zb[i] = (ok && L.zb) ? (unsigned)__ldg(L.zb + (L.zb_len == 1 ? 0 : n)) : 0u;
+        }
+    }
+    // the residual is written by the predecessor kernel: only after griddepcontrol.wait
+    __device__ __forceinline__ void load_residual(const QLinearLaunch& L, int n0, int base) {
+#pragma unroll
+        for (int i = 0; i < NOUT; i++) {
+            const int idx = base + i;
+            const int m = idx / CPW, n = n0 + idx % CPW;
+            res[i] = (L.residual && m < L.M && n < L.N) ? L.residual[(long long)m * L.rs + n] : 0.0f;
+        }
+    }
+};
+
+template <int MT, int CPW, int KI, bool WSIGNED>
+__device__ __forceinline__ void qlin_tile(const QLinearLaunch& L, QTile<MT, CPW, KI>& t, const uint4* aq4, const int* s_rowsum,
+                                          int n0, int lane, int base, float x_scale, int zp) {
+    constexpr int NV = MT * CPW;
+    const int KC = L.K >> 4;
+    int acc[NV];
+#pragma unroll
+    for (int i = 0; i < NV; i++) acc[i] = 0;
+#pragma unroll
+    for (int it = 0; it < KI; it++) {
+        const int c = lane + 32 * it;
+        if (c < KC) {
+#pragma unroll
+            for (int m = 0; m < MT; m++) {
+                const uint4 av = aq4[m * KC + c];
+#pragma unroll
+                for (int j = 0; j < CPW; j++) {
+                    int a = acc[m * CPW + j];
+                    const uint4 wv = t.w[it][j];
+                    if (WSIGNED) {
+                        a = dp4a_us(av.x, wv.x, a);
+                        a = dp4a_us(av.y, wv.y, a);
+                        a = dp4a_us(av.z, wv.z, a);
+                        a = dp4a_us(av.w, wv.w, a);
+                    } else {
+                        a = dp4a_uu(av.x, wv.x, a);
+                        a = dp4a_uu(av.y, wv.y, a);
+                        a = dp4a_uu(av.z, wv.z, a);
+                        a = dp4a_uu(av.w, wv.w, a);
+                    }
+                    acc[m * CPW + j] = a;
+                }
+            }
+        }
+    }
+    int b2, nout;
+    reduce_scatter_warp<NV>(acc, lane, b2, nout);
+    // ---- epilogue: lane holds the exact i32 dot products of (m, j) = divmod(base + i, CPW)
+#pragma unroll
+    for (int i = 0; i < QTile<MT, CPW, KI>::NOUT; i++) {
+        const int idx = base + i;
+        const int m = idx / CPW, n = n0 + idx % CPW;
+        if (m < L.M && n < L.N) {
+            // C = acc - za*colsum[n] - zb[n]*(rowsum[m] - K*za), wrapping 32-bit (rten-gemm/src/kernels/simd_generic.rs:676-746)
+            unsigned cval = (unsigned)acc[i] - (unsigned)zp * (unsigned)t.colsum[i];
+            if (L.zb) cval -= t.zb[i] * ((unsigned)s_rowsum[m] - (unsigned)L.K * (unsigned)zp);
+            // Mul(x_scale, w_scale), cast * scale, Add(bias), Add(residual), activation: separate exactly rounded ops
+            const float sc = __fmul_rn(x_scale, t.wscale[i]);
+            float xv = __fmul_rn(__int2float_rn((int)cval), sc);
+            if (L.bias) xv = __fadd_rn(xv, t.bias[i]);
+            if (L.residual) xv = __fadd_rn(xv, t.res[i]);
+            L.out[(long long)m * L.os + n] = apply_act(xv, L.act);
+        }
+    }
+}
+
+template <int MT, int CPW, int KI, bool WSIGNED, int FLN, bool DB>
+__global__ void __launch_bounds__(256, 2) qlinear_kernel(const QLinearParams p) {
     extern __shared__ __align__(16) uint8_t sm_raw[];
     const QLinearLaunch& L = p.L;
-    const int K = L.K, M = L.M, N = L.N;
+    const int K = L.K, M = L.M;
     uint8_t* aq = sm_raw;  // [MT][K]
     int* s_rowsum = reinterpret_cast<int*>(aq + (size_t)MT * K);
     float* s_lo = reinterpret_cast<float*>(s_rowsum + MT);
@@ -123,30 +252,28 @@ __global__ void __launch_bounds__(256) qlinear_kernel(const QLinearParams p) {
     int* s_mm = reinterpret_cast<int*>(s_hi + 8);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     constexpr int NT = 8 * CPW;
-    const uint8_t* w = reinterpret_cast<const uint8_t*>(L.w);
+    const int base = scatter_base<MT * CPW>(lane);
+    const int G = gridDim.x;
 
-    // the weights do not depend on the previous kernel: pull this CTA's first tile towards L2 while it still runs
-    {
-        const long long lines = ((long long)NT * K + 127) >> 7;
-        const int n0 = blockIdx.x * NT;
-        for (long long i = tid; i < lines; i += 256) {
-            const long long byte = i << 7;
-            const int n = n0 + (int)(byte / K);
-            if (n < N) prefetch_l2(w + (long long)n * L.ldw + (byte % K));
-        }
-    }
+    // the weights do not depend on the previous kernel: this warp's first tile is on its way before we wait for it
+    QTile<MT, CPW, KI> t0;
+    int tile = blockIdx.x;
+    t0.load(L, tile * NT + warp * CPW, lane, base);
     pdl_wait();
     pdl_launch_dependents();
+    t0.load_residual(L, tile * NT + warp * CPW, base);
 
-    // ---- pass 1: range of the (normalised) input
+    // ---- range of the (normalised) input, then quantisation into shared memory (rows >= M are zero)
+    uint32_t* aq32 = reinterpret_cast<uint32_t*>(aq);
+    const int k4 = K >> 2;
     float lo = __int_as_float(0x7f800000), hi = __int_as_float(0xff800000);
+    float4 v[FLN];
     if (L.has_ln) {
+        const int F = K >> 7;
         for (int r = warp; r < M; r += 8) {
-            float4 v[16];
-            qlin_ln_row(L, r, lane, v);
-            const int F = K >> 7;
+            qlin_ln_row<FLN>(L, r, lane, v);
 #pragma unroll
-            for (int k = 0; k < 16; k++) {
+            for (int k = 0; k < FLN; k++) {
                 if (k < F) {
                     lo = fminf(fminf(lo, v[k].x), fminf(v[k].y, fminf(v[k].z, v[k].w)));
                     hi = fmaxf(fmaxf(hi, v[k].x), fmaxf(v[k].y, fmaxf(v[k].z, v[k].w)));
@@ -154,7 +281,6 @@ __global__ void __launch_bounds__(256) qlinear_kernel(const QLinearParams p) {
             }
         }
     } else {
-        const int k4 = K >> 2;
         for (int i = tid; i < M * k4; i += 256) {
             const int r = i / k4, f = i - r * k4;
             const float4 a = reinterpret_cast<const float4*>(L.x + (long long)r * L.xs)[f];
@@ -184,17 +310,13 @@ __global__ void __launch_bounds__(256) qlinear_kernel(const QLinearParams p) {
     float x_scale, inv;
     int zp;
     dql_params(s_mm, x_scale, inv, zp);
-
-    // ---- pass 2: quantise into shared memory (rows >= M are zero)
-    uint32_t* aq32 = reinterpret_cast<uint32_t*>(aq);
-    const int k4 = K >> 2;
     if (L.has_ln) {
+        const int c = lane & 15, seg = lane >> 4, F = K >> 7;
         for (int r = warp; r < M; r += 8) {
-            float4 v[16];
-            qlin_ln_row(L, r, lane, v);
-            const int c = lane & 15, seg = lane >> 4, F = K >> 7;
+            // (M <= 8: the row of pass 1 is still in registers; two rows per warp: recompute, same values)
+            if (MT > 8) qlin_ln_row<FLN>(L, r, lane, v);
 #pragma unroll
-            for (int k = 0; k < 16; k++)
+            for (int k = 0; k < FLN; k++)
                 if (k < F) aq32[r * k4 + c + 16 * (seg * F + k)] = quant4(v[k], inv, zp);
         }
     } else {
@@ -216,79 +338,56 @@ __global__ void __launch_bounds__(256) qlinear_kernel(const QLinearParams p) {
         __syncthreads();
     }
 
-    // ---- GEMV: warp `warp` of tile t owns columns t * NT + warp * CPW .. + CPW - 1; lanes split K in 16-byte chunks
+    // ---- GEMV.  DB (wide outputs, several tiles per CTA): tiles double-buffered in registers -- tile t + G is requested
+    // before tile t is multiplied.  Otherwise one tile per CTA (the launcher sizes the grid so) and half the registers,
+    // which lets the CTAs of the NEXT kernel become resident (and fetch their weights) while this one still runs.
     const uint4* aq4 = reinterpret_cast<const uint4*>(aq);
-    const int KC = K >> 4;
-    for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
-        const int n0 = tile * NT + warp * CPW;
-        int acc[MT * CPW];
-#pragma unroll
-        for (int i = 0; i < MT * CPW; i++) acc[i] = 0;
-        if (n0 < N) {
-#pragma unroll 2
-            for (int c = lane; c < KC; c += 32) {
-                uint4 wv[CPW];
-#pragma unroll
-                for (int j = 0; j < CPW; j++) {
-                    const int n = n0 + j < N ? n0 + j : N - 1;  // (clamped: the duplicate column is never stored)
-                    wv[j] = __ldg(reinterpret_cast<const uint4*>(w + (long long)n * L.ldw) + c);
-                }
-#pragma unroll
-                for (int m = 0; m < MT; m++) {
-                    const uint4 av = aq4[m * KC + c];
-#pragma unroll
-                    for (int j = 0; j < CPW; j++) {
-                        int a = acc[m * CPW + j];
-                        if (WSIGNED) {
-                            a = dp4a_us(av.x, wv[j].x, a);
-                            a = dp4a_us(av.y, wv[j].y, a);
-                            a = dp4a_us(av.z, wv[j].z, a);
-                            a = dp4a_us(av.w, wv[j].w, a);
-                        } else {
-                            a = dp4a_uu(av.x, wv[j].x, a);
-                            a = dp4a_uu(av.y, wv[j].y, a);
-                            a = dp4a_uu(av.z, wv[j].z, a);
-                            a = dp4a_uu(av.w, wv[j].w, a);
-                        }
-                        acc[m * CPW + j] = a;
-                    }
-                }
+    if (!DB) {
+        while (tile < p.tiles) {
+            qlin_tile<MT, CPW, KI, WSIGNED>(L, t0, aq4, s_rowsum, tile * NT + warp * CPW, lane, base, x_scale, zp);
+            tile += G;
+            if (tile < p.tiles) {
+                t0.load(L, tile * NT + warp * CPW, lane, base);
+                t0.load_residual(L, tile * NT + warp * CPW, base);
             }
         }
-        int base, nout;
-        reduce_scatter_warp<MT * CPW>(acc, lane, base, nout);
-        // ---- epilogue: lane holds the exact i32 dot products of (m, j) = divmod(base + i, CPW)
-#pragma unroll
-        for (int i = 0; i < (MT * CPW + 31) / 32; i++) {
-            if (i < nout) {
-                const int idx = base + i;
-                const int m = idx / CPW, n = n0 + idx % CPW;
-                if (m < M && n < N) {
-                    // C = acc - za*colsum[n] - zb[n]*(rowsum[m] - K*za), wrapping 32-bit (rten-gemm/src/kernels/simd_generic.rs:676-746)
-                    unsigned cval = (unsigned)acc[i] - (unsigned)zp * (unsigned)__ldg(L.colsum + n);
-                    if (L.zb) {
-                        const unsigned zbv = (unsigned)__ldg(L.zb + (L.zb_len == 1 ? 0 : n));
-                        cval -= zbv * ((unsigned)s_rowsum[m] - (unsigned)K * (unsigned)zp);
-                    }
-                    // Mul(x_scale, w_scale), cast * scale, Add(bias), Add(residual), activation: separate exactly rounded ops
-                    const float sc = __fmul_rn(x_scale, __ldg(L.w_scale + (L.w_scale_len == 1 ? 0 : n)));
-                    float xv = __fmul_rn(__int2float_rn((int)cval), sc);
-                    if (L.bias) xv = __fadd_rn(xv, __ldg(L.bias + n));
-                    if (L.residual) xv = __fadd_rn(xv, L.residual[(long long)m * L.rs + n]);
-                    L.out[(long long)m * L.os + n] = apply_act(xv, L.act);
-                }
-            }
-        }
+        return;
     }
+    QTile<MT, CPW, KI> t1;
+    while (tile < p.tiles) {
+        int nxt = tile + G;
+        if (nxt < p.tiles) {
+            t1.load(L, nxt * NT + warp * CPW, lane, base);
+            t1.load_residual(L, nxt * NT + warp * CPW, base);
+        }
+        qlin_tile<MT, CPW, KI, WSIGNED>(L, t0, aq4, s_rowsum, tile * NT + warp * CPW, lane, base, x_scale, zp);
+        tile = nxt;
+        if (tile >= p.tiles) break;
+        nxt = tile + G;
+        if (nxt < p.tiles) {
+            t0.load(L, nxt * NT + warp * CPW, lane, base);
+            t0.load_residual(L, nxt * NT + warp * CPW, base);
+        }
+        qlin_tile<MT, CPW, KI, WSIGNED>(L, t1, aq4, s_rowsum, tile * NT + warp * CPW, lane, base, x_scale, zp);
+        tile = nxt;
+    }
+}
+
+static void qlinear_shape(const QLinearLaunch& L, int& mt, int& cpw, int& ki) {
+    mt = L.M <= 8 ? 8 : 16;
+    const int kc = L.K >> 4;
+    ki = kc <= 64 ? 2 : 6;
+    // columns per warp: more bytes in flight per SM for wide outputs, fewer for narrow ones so that the tiles cover the SMs
+    cpw = ki == 6 ? 1 : (L.N >= 8192 ? 4 : (L.N >= 2048 ? 2 : 1));
 }
 
 bool qlinear_supported(const QLinearLaunch& L) {
     if (getenv("RTEN_B200_NO_SKINNY")) return false;
     if (L.M < 1 || L.M > 16 || L.N < 1 || L.K < 16 || (L.K & 15)) return false;
-    if ((size_t)16 * L.K + 256 > 200 * 1024) return false;
+    if ((L.K >> 4) > 192) return false;  // weights of a tile live in registers: K <= 3072
     auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
     if (!al16(L.x) || (L.xs & 3) || !al16(L.w) || (L.ldw & 15)) return false;
-    if (L.has_ln && ((L.K & 127) || (L.K >> 7) > 16 || !L.ln_gamma || !al16(L.ln_gamma) || !al16(L.ln_beta))) return false;
+    if (L.has_ln && ((L.K & 127) || (L.K >> 7) > 8 || !L.ln_gamma || !al16(L.ln_gamma) || !al16(L.ln_beta))) return false;
     if (!L.colsum || !L.w_scale) return false;
     return true;
 }
@@ -296,14 +395,11 @@ bool qlinear_supported(const QLinearLaunch& L) {
 rten_status launch_qlinear(rten_ctx* ctx, const QLinearLaunch& L) {
     QLinearParams p;
     p.L = L;
-    // columns per warp: more columns in flight per warp for wide outputs (bytes in flight per SM), fewer for narrow
-    // ones so that the tiles still cover the SMs
-    const int mt = L.M <= 8 ? 8 : 16;
-    int cpw = L.N >= 16384 ? 8 : (L.N >= 2048 ? 2 : 1);
-    if (mt == 16 && cpw == 8) cpw = 4;
+    int mt, cpw, ki;
+    qlinear_shape(L, mt, cpw, ki);
     const int nt = 8 * cpw;
     p.tiles = (L.N + nt - 1) / nt;
-    const int grid = std::min(p.tiles, 2 * ctx->num_sms);
+    const int grid = cpw == 4 ? std::min(p.tiles, 2 * ctx->num_sms) : p.tiles;  // (one tile per CTA unless double-buffered)
     const size_t smem = (size_t)mt * L.K + mt * sizeof(int) + 16 * sizeof(float) + 16;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -317,25 +413,25 @@ rten_status launch_qlinear(rten_ctx* ctx, const QLinearLaunch& L) {
     cfg.attrs = attr;
     cfg.numAttrs = getenv("RTEN_B200_NO_PDL") ? 0 : 1;
     auto go = [&](auto kern) -> cudaError_t {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e != cudaSuccess) return e;
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+        }
         return cudaLaunchKernelEx(&cfg, kern, p);
     };
-    cudaError_t e;
-    const int key = (mt == 16 ? 100 : 0) + cpw * 2 + (L.w_signed ? 1 : 0);
+    cudaError_t e = cudaSuccess;
+    const int fln = (L.has_ln && (L.K >> 7) > 6) ? 8 : 6;
+    const int key = (mt == 16 ? 10000 : 0) + cpw * 1000 + ki * 100 + fln * 10 + (L.w_signed ? 1 : 0);
     switch (key) {
-        case 2: e = go(qlinear_kernel<8, 1, false>); break;
-        case 3: e = go(qlinear_kernel<8, 1, true>); break;
-        case 4: e = go(qlinear_kernel<8, 2, false>); break;
-        case 5: e = go(qlinear_kernel<8, 2, true>); break;
-        case 16: e = go(qlinear_kernel<8, 8, false>); break;
-        case 17: e = go(qlinear_kernel<8, 8, true>); break;
-        case 102: e = go(qlinear_kernel<16, 1, false>); break;
-        case 103: e = go(qlinear_kernel<16, 1, true>); break;
-        case 104: e = go(qlinear_kernel<16, 2, false>); break;
-        case 105: e = go(qlinear_kernel<16, 2, true>); break;
-        case 108: e = go(qlinear_kernel<16, 4, false>); break;
-        default: e = go(qlinear_kernel<16, 4, true>); break;
+#define RTB_QL_CASE(MT_, CPW_, KI_, FLN_)                                                                                          \
+    case (MT_ == 16 ? 10000 : 0) + CPW_ * 1000 + KI_ * 100 + FLN_ * 10 + 0: e = go(qlinear_kernel<MT_, CPW_, KI_, false, FLN_, (CPW_ == 4)>); break; \
+    case (MT_ == 16 ? 10000 : 0) + CPW_ * 1000 + KI_ * 100 + FLN_ * 10 + 1: e = go(qlinear_kernel<MT_, CPW_, KI_, true, FLN_, (CPW_ == 4)>); break;
+        RTB_QL_CASE(8, 1, 2, 6) RTB_QL_CASE(8, 2, 2, 6) RTB_QL_CASE(8, 4, 2, 6) RTB_QL_CASE(8, 1, 6, 6)
+        RTB_QL_CASE(16, 1, 2, 6) RTB_QL_CASE(16, 2, 2, 6) RTB_QL_CASE(16, 4, 2, 6) RTB_QL_CASE(16, 1, 6, 6)
+        RTB_QL_CASE(8, 1, 2, 8) RTB_QL_CASE(8, 2, 2, 8) RTB_QL_CASE(8, 4, 2, 8)
+        RTB_QL_CASE(16, 1, 2, 8) RTB_QL_CASE(16, 2, 2, 8) RTB_QL_CASE(16, 4, 2, 8)
+#undef RTB_QL_CASE
+        default: return fail(ctx, RTEN_ERR_UNSUPPORTED_VALUE, "quantized linear: no kernel variant for this shape");
     }
     if (e != cudaSuccess) return fail_cuda(ctx, e, "qlinear launch");
     e = cudaGetLastError();
@@ -370,6 +466,19 @@ __global__ void __launch_bounds__(256) skinny_f32_kernel(const SkinnyF32Params p
         for (int k0 = 0; k0 < K; k0 += p.kc) {
             const int kn = min(p.kc, K - k0);  // multiple of 4
             const int q4 = kn >> 2, ld4 = p.kc >> 2;
+            // this warp's slice of B for the chunk goes to registers first (kc <= 1024 floats: 8 float4 per lane and
+            // column), so its latency overlaps the staging of A below
+            float4 wreg[8][CPW];
+#pragma unroll
+            for (int it = 0; it < 8; it++) {
+                const int c = lane + 32 * it;
+#pragma unroll
+                for (int j = 0; j < CPW; j++) {
+                    const int n = n0 + j < N ? n0 + j : N - 1;
+                    wreg[it][j] = (c < q4 && n0 < N) ? __ldg(reinterpret_cast<const float4*>(L.b + (long long)n * L.bs + k0) + c)
+                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
             __syncthreads();  // the previous chunk has been consumed
             for (int i = tid; i < MT * q4; i += 256) {
                 const int r = i / q4, f = i - r * q4;
@@ -377,25 +486,22 @@ __global__ void __launch_bounds__(256) skinny_f32_kernel(const SkinnyF32Params p
             }
             __syncthreads();
             if (n0 < N) {
-#pragma unroll 2
-                for (int c = lane; c < q4; c += 32) {
-                    float4 wv[CPW];
 #pragma unroll
-                    for (int j = 0; j < CPW; j++) {
-                        const int n = n0 + j < N ? n0 + j : N - 1;
-                        wv[j] = __ldg(reinterpret_cast<const float4*>(L.b + (long long)n * L.bs + k0) + c);
-                    }
+                for (int it = 0; it < 8; it++) {
+                    const int c = lane + 32 * it;
+                    if (c < q4) {
 #pragma unroll
-                    for (int m = 0; m < MT; m++) {
-                        const float4 av = as4[m * ld4 + c];
+                        for (int m = 0; m < MT; m++) {
+                            const float4 av = as4[m * ld4 + c];
 #pragma unroll
-                        for (int j = 0; j < CPW; j++) {
-                            float a = acc[m * CPW + j];
-                            a = __fmaf_rn(av.x, wv[j].x, a);
-                            a = __fmaf_rn(av.y, wv[j].y, a);
-                            a = __fmaf_rn(av.z, wv[j].z, a);
-                            a = __fmaf_rn(av.w, wv[j].w, a);
-                            acc[m * CPW + j] = a;
+                            for (int j = 0; j < CPW; j++) {
+                                float a = acc[m * CPW + j];
+                                a = __fmaf_rn(av.x, wreg[it][j].x, a);
+                                a = __fmaf_rn(av.y, wreg[it][j].y, a);
+                                a = __fmaf_rn(av.z, wreg[it][j].z, a);
+                                a = __fmaf_rn(av.w, wreg[it][j].w, a);
+                                acc[m * CPW + j] = a;
+                            }
                         }
                     }
                 }
@@ -434,7 +540,7 @@ rten_status launch_skinny_f32(rten_ctx* ctx, const SkinnyF32Launch& L) {
     const int cpw = mt == 32 ? 1 : (L.N >= 4096 ? 2 : 1);
     const int nt = 8 * cpw;
     p.tiles = (L.N + nt - 1) / nt;
-    p.kc = std::min((L.K + 3) / 4 * 4, mt == 32 ? 1024 : 2048);
+    p.kc = std::min((L.K + 3) / 4 * 4, 1024);
     const int grid = std::min(p.tiles, 2 * ctx->num_sms);
     const size_t smem = (size_t)mt * p.kc * sizeof(float);
     cudaLaunchConfig_t cfg;
@@ -469,6 +575,10 @@ rten_status launch_skinny_f32(rten_ctx* ctx, const SkinnyF32Launch& L) {
 
 // =========================================================================================
 // Single-query attention over a KV cache (flash-decoding split over the cached sequence)
+//
+// One CTA = one (batch, query head, split of <= 128 cached positions).  Latency organisation as above: the CTA's K rows
+// (2 x 16 bytes per lane and position, <= 4 positions per lane) and, for a transposed value cache, its V rows are
+// requested in one burst and consumed afterwards.
 // =========================================================================================
 struct AttnDecodeParams {
     AttnDecodeLaunch L;
@@ -477,63 +587,97 @@ struct AttnDecodeParams {
     int* cnt;   // [B * q_heads] arrival counters (zero between launches)
 };
 
-constexpr int ATTN_MAX_CHUNK = 4096;  // positions of one split held in shared memory
+constexpr int ATTN_CHUNK = 128;  // cached positions per CTA
 
 template <int DH>
-__global__ void __launch_bounds__(256) attn_decode_kernel(const AttnDecodeParams p) {
-    __shared__ float s_p[ATTN_MAX_CHUNK];
-    __shared__ float s_q[DH];
-    __shared__ float s_red[8];
+__global__ void __launch_bounds__(256, 2) attn_decode_kernel(const AttnDecodeParams p) {
+    // Every warp owns 16 consecutive cached positions of the CTA's chunk and runs the whole attention on them by itself
+    // (scores, local max, exponentials, local sum, value product): no block barrier until the eight warps' partial
+    // (max, sum, output) triples are merged -- the same merge that later combines the splits of a (batch, head).
+    __shared__ __align__(16) float s_pw[8][16];
+    __shared__ float s_m[8], s_s[8];
     __shared__ float s_o[8][DH];
-    __shared__ float s_bcast[2];
     __shared__ int s_last;
     const AttnDecodeLaunch& L = p.L;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int bh = blockIdx.x / p.nsplit, split = blockIdx.x - bh * p.nsplit;
     const int b = bh / L.q_heads, h = bh - b * L.q_heads;
-    const int hk = h / (L.q_heads / L.kv_heads);
+    const int group = L.q_heads / L.kv_heads;
+    const int hk = h / group;
     pdl_wait();
     pdl_launch_dependents();
     int len = L.len ? L.len[b] : L.kv_cap;
     len = max(0, min(len, L.kv_cap));
-    const int per = (len + p.nsplit - 1) / p.nsplit;
+    const int per = ((len + p.nsplit - 1) / p.nsplit + 3) & ~3;  // multiple of 4: 16-byte aligned rows of a transposed V
     const int l0 = min(len, split * per), l1 = min(len, l0 + per);
-    const int nl = l1 - l0;
+    const int nl = l1 - l0;      // <= ATTN_CHUNK (the launcher picks nsplit accordingly)
+    const int w0 = warp * 16;    // first position of this warp inside the chunk
     float* kc = L.k + (long long)b * L.k_b + (long long)hk * L.k_h;
     float* vc = L.v + (long long)b * L.v_b + (long long)hk * L.v_h;
-    if (tid < DH) s_q[tid] = L.q[(long long)b * L.q_b + (long long)h * L.q_h + tid];
-    // fused cache append: the split that owns position len - 1 writes the new key / value there first (one CTA per
-    // kv head does it: the query heads of a group share the cache row)
-    const bool appends = L.k_new && len > 0 && l1 == len && nl > 0 && (h % (L.q_heads / L.kv_heads)) == 0;
-    if (appends && tid < DH) {
-        kc[(long long)(len - 1) * L.k_l + tid] = L.k_new[(long long)b * L.kn_b + (long long)hk * L.kn_h + tid];
-        vc[(long long)(len - 1) * L.v_l + (long long)tid * L.v_d] = L.v_new[(long long)b * L.vn_b + (long long)hk * L.vn_h + tid];
-    }
-    __syncthreads();
-    // ---- scores: 8 lanes per cached position (DH / 8 floats each), 4 positions per warp and iteration
-    constexpr int PER_LANE = DH / 8;  // 8 (dh 64) or 16 (dh 128) floats
+    const float* knew = L.k_new ? L.k_new + (long long)b * L.kn_b + (long long)hk * L.kn_h : nullptr;
+    const float* vnew = L.v_new ? L.v_new + (long long)b * L.vn_b + (long long)hk * L.vn_h : nullptr;
+    // ---- everything this warp will need is requested here: K rows (8 lanes per position, DH / 8 floats per lane) ...
+    constexpr int PER_LANE = DH / 8;
+    constexpr int NV4 = PER_LANE / 4;
     const int sub = lane >> 3, l8 = lane & 7;
-    float qreg[PER_LANE];
+    float4 kreg[4][NV4], qreg[NV4];
+    const float4* q4 = reinterpret_cast<const float4*>(L.q + (long long)b * L.q_b + (long long)h * L.q_h + l8 * PER_LANE);
 #pragma unroll
-    for (int i = 0; i < PER_LANE; i++) qreg[i] = s_q[l8 * PER_LANE + i];
-    const float* mrow = L.mask ? L.mask + (long long)b * L.m_b + (long long)h * L.m_h : nullptr;
-    const bool new_in_regs = L.k_new != nullptr;  // (other query heads of the group may race with the append: read k_new)
-    float mx = -FLT_MAX;
-    for (int i0 = warp * 4; i0 < nl; i0 += 32) {
-        const int i = i0 + sub;
-        float s = 0.0f;
+    for (int j = 0; j < NV4; j++) qreg[j] = q4[j];
+#pragma unroll
+    for (int it = 0; it < 4; it++) {
+        const int i = w0 + it * 4 + sub;
         if (i < nl) {
             const int l = l0 + i;
-            const float* kr = (new_in_regs && l == len - 1) ? L.k_new + (long long)b * L.kn_b + (long long)hk * L.kn_h
-                                                            : kc + (long long)l * L.k_l;
+            const float* kr = (knew && l == len - 1) ? knew : kc + (long long)l * L.k_l;  // (the new row may not be in the cache yet)
             const float4* k4 = reinterpret_cast<const float4*>(kr + l8 * PER_LANE);
 #pragma unroll
-            for (int j = 0; j < PER_LANE / 4; j++) {
-                const float4 kv = k4[j];
-                s = fmaf(qreg[4 * j], kv.x, s);
-                s = fmaf(qreg[4 * j + 1], kv.y, s);
-                s = fmaf(qreg[4 * j + 2], kv.z, s);
-                s = fmaf(qreg[4 * j + 3], kv.w, s);
+            for (int j = 0; j < NV4; j++) kreg[it][j] = k4[j];
+        }
+    }
+    // ... and its V tile.  Transposed cache [.., dh, cap]: lane = (channel row lane >> 2, float4 lane & 3 of the 16
+    // positions); natural cache [.., cap, dh]: lane owns DH / 32 consecutive channels of every position.
+    constexpr int DPW = DH / 8, CH = DH / 32;
+    const bool vt = L.v_l == 1;
+    const int dq = lane >> 2, f4 = lane & 3;
+    float4 vreg[DPW];
+    float vnat[16][CH];
+    if (vt) {
+#pragma unroll
+        for (int j = 0; j < DPW; j++)
+            vreg[j] = (w0 + 4 * f4 < nl) ? *reinterpret_cast<const float4*>(vc + (long long)(dq + 8 * j) * L.v_d + l0 + w0 + 4 * f4)
+                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            if (w0 + i < nl) {
+                const float* vr = (vnew && l0 + w0 + i == len - 1) ? vnew : vc + (long long)(l0 + w0 + i) * L.v_l;
+#pragma unroll
+                for (int j = 0; j < CH; j++) vnat[i][j] = vr[(long long)(lane * CH + j) * L.v_d];
+            }
+        }
+    }
+    // fused cache append: the split that owns position len - 1 writes the new key / value there (one CTA per kv head:
+    // the query heads of a group share the cache row; every reader of that position takes k_new / v_new instead)
+    if (knew && len > 0 && l1 == len && nl > 0 && (h % group) == 0 && tid < DH) {
+        kc[(long long)(len - 1) * L.k_l + tid] = knew[tid];
+        vc[(long long)(len - 1) * L.v_l + (long long)tid * L.v_d] = vnew[tid];
+    }
+    // ---- scores of the warp's 16 positions
+    const float* mrow = L.mask ? L.mask + (long long)b * L.m_b + (long long)h * L.m_h : nullptr;
+    float sc[4];
+    float mw = -FLT_MAX;
+#pragma unroll
+    for (int it = 0; it < 4; it++) {
+        const int i = w0 + it * 4 + sub;
+        float s = 0.0f;
+        if (i < nl) {
+#pragma unroll
+            for (int j = 0; j < NV4; j++) {
+                s = fmaf(qreg[j].x, kreg[it][j].x, s);
+                s = fmaf(qreg[j].y, kreg[it][j].y, s);
+                s = fmaf(qreg[j].z, kreg[it][j].z, s);
+                s = fmaf(qreg[j].w, kreg[it][j].w, s);
             }
         }
         s += __shfl_xor_sync(0xffffffffu, s, 4);
@@ -542,83 +686,86 @@ __global__ void __launch_bounds__(256) attn_decode_kernel(const AttnDecodeParams
         if (i < nl) {
             s *= L.scale;
             if (mrow) s += mrow[(long long)(l0 + i) * L.m_l];
-            if (l8 == 0) s_p[i] = s;
-            mx = fmaxf(mx, s);
+            mw = fmaxf(mw, s);
         }
+        sc[it] = s;
     }
+    mw = fmaxf(mw, __shfl_xor_sync(0xffffffffu, mw, 8));
+    mw = fmaxf(mw, __shfl_xor_sync(0xffffffffu, mw, 16));
+    // ---- exponentials (the reference's polynomial, rten-vecmath/src/exp.rs:140-191), local sum, p staged per warp
+    float sw = 0.0f;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if (lane == 0) s_red[warp] = mx;
-    __syncthreads();
-    if (tid == 0) {
-        float m = s_red[0];
-        for (int k = 1; k < 8; k++) m = fmaxf(m, s_red[k]);
-        s_bcast[0] = m;
+    for (int it = 0; it < 4; it++) {
+        const int i = w0 + it * 4 + sub;
+        const float e = i < nl ? reduced_range_exp(sc[it] - mw) : 0.0f;
+        sw += e;
+        if (l8 == 0) s_pw[warp][it * 4 + sub] = e;
     }
-    __syncthreads();
-    mx = s_bcast[0];
-    // ---- exponentials (the reference's polynomial, rten-vecmath/src/exp.rs:140-191) and their sum
-    float sum = 0.0f;
-    for (int i = tid; i < nl; i += 256) {
-        const float e = reduced_range_exp(s_p[i] - mx);
-        s_p[i] = e;
-        sum += e;
-    }
+    sw += __shfl_xor_sync(0xffffffffu, sw, 8);
+    sw += __shfl_xor_sync(0xffffffffu, sw, 16);
+    __syncwarp();
+    // ---- the warp's unnormalised output o_w[d] = sum_{its positions} p V
+    if (vt) {
+        const float4 p4 = reinterpret_cast<const float4*>(s_pw[warp])[f4];
+        const int pbase = w0 + 4 * f4;                                                   // chunk position of component .x
+        const int inew = (vnew && l1 == len) ? (len - 1 - l0) - pbase : -1;             // component that is the new position
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    __syncthreads();  // (s_red is reused; every thread has read s_bcast[0])
-    if (lane == 0) s_red[warp] = sum;
-    __syncthreads();
-    if (tid == 0) {
-        float t = 0.0f;
-        for (int k = 0; k < 8; k++) t += s_red[k];
-        s_bcast[1] = t;
-    }
-    __syncthreads();
-    sum = s_bcast[1];
-    // ---- unnormalised output o[d] = sum_l p[l] V[l, d]
-    const float* vnew = L.v_new ? L.v_new + (long long)b * L.vn_b + (long long)hk * L.vn_h : nullptr;
-    float o_mine = 0.0f;  // thread d < DH ends up with o[d]
-    if (L.v_l == 1) {
-        // transposed cache [.., dh, cap]: warp w owns rows d = w, w + 8, ...; lanes stride the cached positions
-        for (int d = warp; d < DH; d += 8) {
-            const float* vr = vc + (long long)d * L.v_d + l0;
-            float a = 0.0f;
-            for (int i = lane; i < nl; i += 32) {
-                const float vv = (vnew && l0 + i == len - 1) ? vnew[d] : vr[i];
-                a = fmaf(s_p[i], vv, a);
+        for (int j = 0; j < DPW; j++) {
+            const int d = dq + 8 * j;
+            float4 vv = vreg[j];
+            if (inew >= 0 && inew < 4) {
+                const float nv = vnew[d];
+                if (inew == 0) vv.x = nv;
+                if (inew == 1) vv.y = nv;
+                if (inew == 2) vv.z = nv;
+                if (inew == 3) vv.w = nv;
             }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-            if (lane == 0) s_o[0][d] = a;
+            // (positions beyond nl hold p = 0 but their V may be uninitialised memory: never multiply it)
+            float a = 0.0f;
+            if (pbase < nl) a = fmaf(p4.x, vv.x, a);
+            if (pbase + 1 < nl) a = fmaf(p4.y, vv.y, a);
+            if (pbase + 2 < nl) a = fmaf(p4.z, vv.z, a);
+            if (pbase + 3 < nl) a = fmaf(p4.w, vv.w, a);
+            a += __shfl_xor_sync(0xffffffffu, a, 1);
+            a += __shfl_xor_sync(0xffffffffu, a, 2);
+            if (f4 == 0) s_o[warp][d] = a;
         }
-        __syncthreads();
-        if (tid < DH) o_mine = s_o[0][tid];
     } else {
-        // natural cache [.., cap, dh]: warp w takes positions w, w + 8, ...; lanes own dh / 32 consecutive channels
-        constexpr int CH = DH / 32;
         float a[CH];
 #pragma unroll
         for (int j = 0; j < CH; j++) a[j] = 0.0f;
-        for (int i = warp; i < nl; i += 8) {
-            const float pw = s_p[i];
-            const float* vr = (vnew && l0 + i == len - 1) ? vnew : vc + (long long)(l0 + i) * L.v_l;
 #pragma unroll
-            for (int j = 0; j < CH; j++) a[j] = fmaf(pw, vr[(long long)(lane * CH + j) * L.v_d], a[j]);
+        for (int i = 0; i < 16; i++) {
+            if (w0 + i < nl) {
+                const float pw = s_pw[warp][i];
+#pragma unroll
+                for (int j = 0; j < CH; j++) a[j] = fmaf(pw, vnat[i][j], a[j]);
+            }
         }
 #pragma unroll
         for (int j = 0; j < CH; j++) s_o[warp][lane * CH + j] = a[j];
-        __syncthreads();
-        if (tid < DH) {
-            float t = 0.0f;
-            for (int k = 0; k < 8; k++) t += s_o[k][tid];
-            o_mine = t;
+    }
+    if (lane == 0) {
+        s_m[warp] = w0 < nl ? mw : -FLT_MAX;
+        s_s[warp] = sw;
+    }
+    __syncthreads();
+    // ---- merge the eight warps
+    float m = -FLT_MAX, num = 0.0f, den = 0.0f;
+    if (tid < DH) {
+#pragma unroll
+        for (int w = 0; w < 8; w++) m = fmaxf(m, s_m[w]);
+#pragma unroll
+        for (int w = 0; w < 8; w++) {
+            const float e = reduced_range_exp(s_m[w] - m);
+            den = fmaf(s_s[w], e, den);
+            num = fmaf(s_o[w][tid], e, num);
         }
     }
     float* outp = L.out + (long long)b * L.o_b + (long long)h * L.o_h;
     if (p.nsplit == 1) {
         if (tid < DH) {
-            float r = o_mine / sum;
+            float r = num / den;
             if (r != r) r = 0.0f;  // fully masked row -> zeros (sdpa_head flushes NaNs)
             outp[tid] = r;
         }
@@ -627,10 +774,10 @@ __global__ void __launch_bounds__(256) attn_decode_kernel(const AttnDecodeParams
     // ---- merge the splits: the last CTA of (b, h) to arrive combines the partial (max, sum, output) triples
     float* wsp = p.ws + ((long long)bh * p.nsplit + split) * (2 + DH);
     if (tid == 0) {
-        wsp[0] = mx;
-        wsp[1] = sum;
+        wsp[0] = m;
+        wsp[1] = den;
     }
-    if (tid < DH) wsp[2 + tid] = o_mine;
+    if (tid < DH) wsp[2 + tid] = num;
     __threadfence();
     __syncthreads();
     if (tid == 0) {
@@ -642,17 +789,17 @@ __global__ void __launch_bounds__(256) attn_decode_kernel(const AttnDecodeParams
     __syncthreads();
     if (!s_last) return;
     if (tid < DH) {
-        const float* w0 = p.ws + (long long)bh * p.nsplit * (2 + DH);
-        float m = -FLT_MAX;
-        for (int s2 = 0; s2 < p.nsplit; s2++) m = fmaxf(m, __ldcg(w0 + s2 * (2 + DH)));
-        float num = 0.0f, den = 0.0f;
+        const float* w0p = p.ws + (long long)bh * p.nsplit * (2 + DH);
+        float mm = -FLT_MAX;
+        for (int s2 = 0; s2 < p.nsplit; s2++) mm = fmaxf(mm, __ldcg(w0p + s2 * (2 + DH)));
+        float nn = 0.0f, dd = 0.0f;
         for (int s2 = 0; s2 < p.nsplit; s2++) {
-            const float* ww = w0 + s2 * (2 + DH);
-            const float sc = reduced_range_exp(__ldcg(ww) - m);
-            den = fmaf(__ldcg(ww + 1), sc, den);
-            num = fmaf(__ldcg(ww + 2 + tid), sc, num);
+            const float* ww = w0p + s2 * (2 + DH);
+            const float e = reduced_range_exp(__ldcg(ww) - mm);
+            dd = fmaf(__ldcg(ww + 1), e, dd);
+            nn = fmaf(__ldcg(ww + 2 + tid), e, nn);
         }
-        float r = num / den;
+        float r = nn / dd;
         if (r != r) r = 0.0f;
         outp[tid] = r;
     }
@@ -662,11 +809,13 @@ bool attn_decode_supported(const AttnDecodeLaunch& L) {
     if (getenv("RTEN_B200_NO_SKINNY")) return false;
     if (L.dh != 64 && L.dh != 128) return false;
     if (L.B < 1 || L.q_heads < 1 || L.kv_heads < 1 || L.q_heads % L.kv_heads) return false;
-    if (L.kv_cap < 1 || L.kv_cap > 8 * ATTN_MAX_CHUNK) return false;
+    if (L.kv_cap < 1 || L.kv_cap > 64 * ATTN_CHUNK) return false;
     auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
     if (!al16(L.k) || (L.k_b & 3) || (L.k_h & 3) || (L.k_l & 3)) return false;
+    if (!al16(L.q) || (L.q_b & 3) || (L.q_h & 3)) return false;
     if (L.k_new && (!al16(L.k_new) || (L.kn_b & 3) || (L.kn_h & 3) || !L.v_new)) return false;
     if (L.v_l != 1 && L.v_d != 1) return false;
+    if (L.v_l == 1 && (!al16(L.v) || (L.v_b & 3) || (L.v_h & 3) || (L.v_d & 3))) return false;  // float4 along the positions
     return true;
 }
 
@@ -674,10 +823,11 @@ rten_status launch_attn_decode(rten_ctx* ctx, const AttnDecodeLaunch& L) {
     AttnDecodeParams p;
     p.L = L;
     const int bh = L.B * L.q_heads;
-    // enough CTAs to cover the SMs about twice, every split at least 64 positions and at most ATTN_MAX_CHUNK
-    int ns = std::max(1, std::min(8, (2 * ctx->num_sms + bh - 1) / bh));
-    ns = std::min(ns, std::max(1, L.kv_cap / 64));
-    ns = std::max(ns, (L.kv_cap + ATTN_MAX_CHUNK - 1) / ATTN_MAX_CHUNK);
+    // a split covers at most ATTN_CHUNK positions (rounded to 4); more splits when (batch x heads) alone leaves SMs idle
+    int ns = (L.kv_cap + ATTN_CHUNK - 4) / (ATTN_CHUNK - 3);
+    ns = std::max(ns, std::min(16, (2 * ctx->num_sms + bh - 1) / bh));
+    ns = std::max(1, std::min(ns, std::max(1, (L.kv_cap + 15) / 16)));
+    while ((((L.kv_cap + ns - 1) / ns + 3) & ~3) > ATTN_CHUNK) ns++;
     p.nsplit = ns;
     p.ws = nullptr;
     p.cnt = nullptr;

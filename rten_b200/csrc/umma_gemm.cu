@@ -1146,8 +1146,8 @@ bool tma_compatible(const OperandDesc& od, int esize, int rank) {
     return true;
 }
 
-static bool encode_map(rten_ctx* ctx, CUtensorMap* map, const OperandDesc& od, int esize, bool is_f32,
-                       const uint32_t box[4], const uint32_t estr[4]) {
+bool encode_map(rten_ctx* ctx, CUtensorMap* map, const OperandDesc& od, int esize, bool is_f32,
+                const uint32_t box[4], const uint32_t estr[4]) {
     EncodeTiledFn enc = get_encode(ctx);
     if (!enc) return false;
     cuuint64_t dims[4];
@@ -1750,6 +1750,12 @@ static rten_status launch_tf32x3(rten_ctx* ctx, const GemmLaunch& L0) {
 
 rten_status launch_umma_gemm(rten_ctx* ctx, const GemmLaunch& L) {
     if (L.kind == 0 && ctx->f32_mode == RTEN_F32_TF32X3) return launch_tf32x3(ctx, L);
+    // stride-1 windows (the 3x3 layers): the halo-reuse kernel moves the activations into shared memory once per channel
+    // block instead of once per filter tap (umma_halo.cu); everything it does not cover falls through
+    if (L.conv && L.kind == 0 && L.g.kh * L.g.kw > 1 && !ctx->trace) {
+        const rten_status hs = launch_umma_halo_conv(ctx, L);
+        if (hs != RTEN_ERR_UNSUPPORTED_VALUE) return hs;
+    }
     Prepared q;
     RTB_TRY(prepare_launch(ctx, L, q));
     const bool verbose = getenv("RTEN_B200_VERBOSE") != nullptr;

@@ -8,6 +8,8 @@
 // The A operand is either a plain (k, m, z0, z1) tensor or an NHWC activation tensor addressed
 // as an implicit im2col matrix: row = output pixel (b, oy, ox), k = (ky, kx, c).
 #pragma once
+#include <cuda.h>
+
 #include <cstdint>
 
 #include "common.h"
@@ -77,6 +79,15 @@ struct GemmLaunch {
 // semantics of the caller) when the operands violate a TMA constraint -- the caller then packs
 // the operand into an aligned K-major workspace and retries.
 rten_status launch_umma_gemm(rten_ctx* ctx, const GemmLaunch& L);
+
+// Tiled, 128B-swizzled rank-4 tensor map over `od` (cuTensorMapEncodeTiled through the runtime's driver entry point).
+bool encode_map(rten_ctx* ctx, CUtensorMap* map, const OperandDesc& od, int esize, bool is_f32, const uint32_t box[4],
+                const uint32_t estr[4]);
+
+// Stride-1 convolutions with a kh x kw > 1 window on the halo-reuse kernel (umma_halo.cu): one activation patch per
+// channel block in shared memory, every filter tap a shifted window of it.  RTEN_ERR_UNSUPPORTED_VALUE = not applicable
+// (the caller then takes the generic implicit-GEMM kernel).
+rten_status launch_umma_halo_conv(rten_ctx* ctx, const GemmLaunch& L);
 
 // true if `od` can be fed to TMA directly (16-B aligned base and strides, inner stride 1).
 bool tma_compatible(const OperandDesc& od, int esize, int rank);

@@ -97,14 +97,18 @@ def bert_oracle(oracle, spec, input_ids, token_type_ids, add_mask):
     return x.reshape(B, S, H)
 
 
-def gpt2_int8_oracle(oracle, spec, steps):
-    """configs[4] with the reference's operators: `steps` = list of int32 [B,T] token blocks (prefill, then decode
-    steps); K/V of earlier blocks are kept as `past_key_values`.  -> list of last-position logits [B,vocab]."""
-    f32 = np.float32
-    H, nh = spec.hidden, spec.heads
-    dh = H // nh
+class gpt2_int8_decoder:
+    """configs[4] with the reference's operators, stateful: the constructor runs the prompt (prefill), `step(ids)` feeds
+    the next [B,T] token block against the `past_key_values` kept so far.  `.logits` = last-position logits [B,vocab]."""
 
-    def linear(x, l, gelu=False, residual=None):
+    def __init__(self, oracle, spec, prompt_ids):
+        self.oracle, self.spec = oracle, spec
+        self.past = [None] * len(spec.layers)
+        self.P = 0
+        self.logits = self.step(prompt_ids)
+
+    def _linear(self, x, l, gelu=False, residual=None):
+        oracle, f32 = self.oracle, np.float32
         xq, xs, xz = oracle.dynamic_quantize_linear(x)
         y = oracle.matmul_integer_to_float(xq, l.wq, xz, None, (f32(xs) * l.w_scale).astype(f32))
         if l.b is not None:
@@ -113,27 +117,38 @@ def gpt2_int8_oracle(oracle, spec, steps):
             y = oracle.add(y, residual)
         return oracle.gelu(y, True) if gelu else y
 
-    past = [None] * len(spec.layers)
-    P, outs = 0, []
-    for ids in steps:
+    def step(self, ids):
+        oracle, spec, f32 = self.oracle, self.spec, np.float32
+        H, nh = spec.hidden, spec.heads
+        dh = H // nh
         B, T = ids.shape
+        P = self.P
         L = P + T
         x = oracle.add(spec.wte[ids], spec.wpe[P:L]).reshape(B * T, H)
         mask = np.where(np.arange(L)[None, :] <= (P + np.arange(T))[:, None], 0.0, -np.inf).astype(f32).reshape(1, 1, T, L)
         for li, ly in enumerate(spec.layers):
             h = oracle.layer_norm(x, ly.ln1_g, ly.ln1_b, -1, spec.eps)
-            qkv = linear(h, ly.attn).reshape(B, T, 3, nh, dh)
+            qkv = self._linear(h, ly.attn).reshape(B, T, 3, nh, dh)
             q, k, v = (qkv[:, :, i].transpose(0, 2, 1, 3) for i in range(3))
-            if past[li] is not None:
-                k = np.concatenate([past[li][0], k], 2)
-                v = np.concatenate([past[li][1], v], 2)
-            past[li] = (k, v)
+            if self.past[li] is not None:
+                k = np.concatenate([self.past[li][0], k], 2)
+                v = np.concatenate([self.past[li][1], v], 2)
+            self.past[li] = (k, v)
             probs = oracle.add_softmax(oracle.matmul(q, k.transpose(0, 1, 3, 2), None, 1.0 / math.sqrt(dh)), mask)
             att = oracle.matmul(probs, v).transpose(0, 2, 1, 3).reshape(B * T, H)
-            x = linear(att, ly.proj, residual=x)
+            x = self._linear(att, ly.proj, residual=x)
             h = oracle.layer_norm(x, ly.ln2_g, ly.ln2_b, -1, spec.eps)
-            x = linear(linear(h, ly.fc, gelu=True), ly.fc2, residual=x)
+            x = self._linear(self._linear(h, ly.fc, gelu=True), ly.fc2, residual=x)
         last = oracle.layer_norm(x.reshape(B, T, H)[:, -1], spec.lnf_g, spec.lnf_b, -1, spec.eps)
-        outs.append(linear(last, spec.lm_head))
-        P = L
+        self.P = L
+        self.logits = self._linear(last, spec.lm_head)
+        return self.logits
+
+
+def gpt2_int8_oracle(oracle, spec, steps):
+    """-> list of last-position logits [B,vocab], one per token block of `steps` (prefill, then decode steps)."""
+    dec = gpt2_int8_decoder(oracle, spec, steps[0])
+    outs = [dec.logits]
+    for ids in steps[1:]:
+        outs.append(dec.step(ids))
     return outs
