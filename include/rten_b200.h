@@ -288,6 +288,38 @@ rten_status rten_b200_gather_rows(rten_ctx* ctx, const rten_tensor* table, const
  * a fixed list of launches and can be replayed as a CUDA graph. */
 rten_status rten_b200_scatter_rows(rten_ctx* ctx, rten_tensor* table, const rten_tensor* indices, const rten_tensor* updates);
 
+/* ---- model loading and graph execution ------------------------------------------------- */
+/* `Model::load` + `Graph::run_plan` (src/model.rs, src/graph.rs:880-1286) for the hot-path operator set: the ONNX file is
+ * decoded by a hand-written wire-format reader (rten-onnx/src/onnx.rs), int64 tensors become i32 as in rten's loader,
+ * constants are uploaded to HBM once, Conv + Relu and MatMul + Add(bias) are fused at load (the subset of
+ * src/optimize.rs these models need), constant weights are prepacked once (`Operator::prepack`, src/graph.rs:488-565).
+ * A run executes the nodes in topological order, one operator call of this library each; temporaries are reference
+ * counted and return to the context pool after their last consumer; Relu / Gelu / Erf / Softmax run in place when the
+ * executor holds the last reference to their input (src/graph.rs:973-1049); Reshape / Flatten / Squeeze / Unsqueeze /
+ * Transpose / Identity are views.  Operators: Conv, ConvInteger, Relu, MaxPool, GlobalAveragePool, ReduceMean (spatial
+ * axes), Gemm, MatMul, MatMulInteger, Add, Mul, Softmax, LayerNormalization, Gelu, Erf, Gather (rows), Cast (i32 -> f32),
+ * DynamicQuantizeLinear, Attention (4-D), Constant and the view operators; anything else fails the LOAD with
+ * RTEN_ERR_UNSUPPORTED_VALUE ("unsupported operator <name>"). */
+typedef struct rten_model rten_model;
+rten_status rten_b200_model_load(rten_ctx* ctx, const void* onnx_bytes, size_t len, rten_model** out);
+void rten_b200_model_free(rten_model* model);
+int32_t rten_b200_model_num_inputs(const rten_model* model);
+int32_t rten_b200_model_num_outputs(const rten_model* model);
+const char* rten_b200_model_input_name(const rten_model* model, int32_t index);
+const char* rten_b200_model_output_name(const rten_model* model, int32_t index);
+int32_t rten_b200_model_num_nodes(const rten_model* model); /* after the load-time fusions */
+const char* rten_b200_model_node_op(const rten_model* model, int32_t index);
+const char* rten_b200_model_summary(const rten_model* model); /* JSON: the decoded file (before fusion) */
+/* Inputs by name (device tensors, or host tensors staged for the run; integer inputs are i32).  Outputs by name: any
+ * value of the graph may be requested (`Model::run` with arbitrary output nodes); each comes back as a contiguous device
+ * tensor the caller owns (rten_b200_free). */
+rten_status rten_b200_model_run(rten_model* model, int32_t n_inputs, const char* const* input_names, const rten_tensor* inputs,
+                                int32_t n_outputs, const char* const* output_names, rten_tensor* outputs);
+/* The reader alone -- no context, no GPU: JSON description (opset, nodes with operator / inputs / outputs / attribute
+ * names, initialisers with type and shape, graph inputs / outputs) of an ONNX file.  `needed` receives the size of the
+ * full text incl. the terminator. */
+rten_status rten_b200_onnx_summary(const void* onnx_bytes, size_t len, char* json_out, size_t capacity, size_t* needed);
+
 #ifdef __cplusplus
 }
 #endif

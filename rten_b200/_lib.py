@@ -105,6 +105,17 @@ _SIGNATURES = {
     "rten_b200_global_average_pool": (C.c_int, [_vp, _TP, _TP]),
     "rten_b200_gather_rows": (C.c_int, [_vp, _TP, _TP, _TP]),
     "rten_b200_scatter_rows": (C.c_int, [_vp, _TP, _TP, _TP]),
+    "rten_b200_model_load": (C.c_int, [_vp, _vp, C.c_size_t, C.POINTER(_vp)]),
+    "rten_b200_model_free": (None, [_vp]),
+    "rten_b200_model_num_inputs": (C.c_int32, [_vp]),
+    "rten_b200_model_num_outputs": (C.c_int32, [_vp]),
+    "rten_b200_model_input_name": (C.c_char_p, [_vp, C.c_int32]),
+    "rten_b200_model_output_name": (C.c_char_p, [_vp, C.c_int32]),
+    "rten_b200_model_num_nodes": (C.c_int32, [_vp]),
+    "rten_b200_model_node_op": (C.c_char_p, [_vp, C.c_int32]),
+    "rten_b200_model_summary": (C.c_char_p, [_vp]),
+    "rten_b200_model_run": (C.c_int, [_vp, C.c_int32, C.POINTER(C.c_char_p), _TP, C.c_int32, C.POINTER(C.c_char_p), _TP]),
+    "rten_b200_onnx_summary": (C.c_int, [_vp, C.c_size_t, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),
 }
 
 _lib = None

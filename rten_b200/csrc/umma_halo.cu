@@ -10,7 +10,7 @@
 // 128B swizzle is a function of the absolute shared-memory address, so TMA's layout and the shifted descriptor agree
 // (measured: tools/desc_probe.cu, profiles/r02_desc_probe.txt).  Slots with x >= OW (and the rows past the strip) are
 // computed and thrown away: 2 / P of the MMA rows for a 3x3 window.  The weights stream through a ring of
-// (bn x 32 channel) tiles, one per tap.
+// stages of `tps` taps x (bn x 32 channel) tiles (one barrier hand-off per stage).
 //
 // Replaces rten-gemm/src/im2col.rs:110-212 (the A-operand gather of the packed GEMM) for these layers.
 #include <cuda.h>
@@ -48,6 +48,7 @@ struct HaloParams {
     int strips, units_n, units_total;
     int acc_stages;     // 1 or 2 TMEM accumulator stages of T * bn columns
     int b_stages;       // weight ring depth
+    int tps;            // filter taps per weight-ring stage (one barrier hand-off per stage: taps, kw or 1)
     uint32_t patch_bytes, patch_tx, b_bytes;
     uint32_t idesc;
     EpilogueDesc epi;
@@ -121,11 +122,11 @@ umma_halo_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                 __syncwarp();
                 pphase ^= 1u << ps;
                 ps ^= 1;
-                for (int tap = 0; tap < p.taps; tap++) {
+                for (int tap = 0; tap < p.taps; tap += p.tps) {
                     mbar_wait(&b_empty[bs], ((bphase >> bs) & 1) ^ 1);
                     if (elect_one()) {
                         mbar_expect_tx(&b_full[bs], p.b_bytes);
-                        tma_load_4d(bring + (size_t)bs * p.b_bytes, &tma_b, &b_full[bs], cb * 32, n0, tap, 0);
+                        tma_load_4d(bring + (size_t)bs * p.b_bytes, &tma_b, &b_full[bs], cb * 32, n0, tap, 0);  // box: tps taps
                     }
                     __syncwarp();
                     bphase ^= 1u << bs;
@@ -145,23 +146,28 @@ umma_halo_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             const uint32_t d_tmem = tmem_base + acc * 256;
             for (int cb = 0; cb < p.c_blocks; cb++) {
                 mbar_wait(&patch_full[ps], (pphase >> ps) & 1);
-                const uint32_t pa = smem_u32(patch0 + (size_t)ps * p.patch_bytes);
-                int ky = 0, kx = 0;
-                for (int tap = 0; tap < p.taps; tap++) {
+                const uint64_t adesc0 = make_kmajor_sw128_desc(smem_u32(patch0 + (size_t)ps * p.patch_bytes));
+                for (int tap0 = 0; tap0 < p.taps; tap0 += p.tps) {
                     mbar_wait(&b_full[bs], (bphase >> bs) & 1);
                     tc_fence_after();
                     if (elect_one()) {
-                        const uint32_t ba = smem_u32(bring + (size_t)bs * p.b_bytes);
-                        const uint32_t shift = (uint32_t)(ky * p.P + kx) * 128u;
-                        for (int t = 0; t < p.T; t++) {
-                            const uint64_t adesc = make_kmajor_sw128_desc(pa + shift + (uint32_t)t * 128u * 128u);
-                            const uint64_t bdesc = make_kmajor_sw128_desc(ba);
+                        const uint64_t bdesc0 = make_kmajor_sw128_desc(smem_u32(bring + (size_t)bs * p.b_bytes));
+                        for (int ti = 0; ti < p.tps; ti++) {
+                            // the tap is the SAME patch seen (ky P + kx) pixel slots of 128 bytes further on; descriptor
+                            // addresses count 16-byte units
+                            const int tap = tap0 + ti;
+                            const int ky = tap / p.kw, kx = tap - ky * p.kw;
+                            const uint64_t adesc = adesc0 + (uint64_t)((ky * p.P + kx) * 8);
+                            const uint64_t bdesc = bdesc0 + (uint64_t)(ti * p.bn * 8);
+                            const uint32_t first = (cb | tap0 | ti) ? 1u : 0u;
+                            for (int t = 0; t < p.T; t++) {
 #pragma unroll
-                            for (int k = 0; k < 4; k++)
-                                umma_tf32(d_tmem + t * p.bn, adesc + 2 * k, bdesc + 2 * k, p.idesc, (cb | tap | k) ? 1u : 0u);
+                                for (int k = 0; k < 4; k++)
+                                    umma_tf32(d_tmem + t * p.bn, adesc + (uint64_t)(t * 1024 + 2 * k), bdesc + 2 * k, p.idesc, (first | (uint32_t)k) ? 1u : 0u);
+                            }
                         }
                         umma_commit(&b_empty[bs]);
-                        if (tap == p.taps - 1) {
+                        if (tap0 + p.tps >= p.taps) {
                             umma_commit(&patch_empty[ps]);
                             if (cb == p.c_blocks - 1) umma_commit(&tmem_full[acc]);
                         }
@@ -169,10 +175,6 @@ umma_halo_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                     __syncwarp();
                     bphase ^= 1u << bs;
                     if (++bs == p.b_stages) bs = 0;
-                    if (++kx == p.kw) {
-                        kx = 0;
-                        ky++;
-                    }
                 }
                 pphase ^= 1u << ps;
                 ps ^= 1;
@@ -278,7 +280,7 @@ rten_status launch_umma_halo_conv(rten_ctx* ctx, const GemmLaunch& L) {
     // slots that are thrown away counted in.
     const int num_sms = ctx->num_sms;
     double best = 1e30;
-    int bbn = 0, bT = 0, bR = 0, btb = 0;
+    int bbn = 0, bT = 0, bR = 0, btb = 0, btps = 1;
     const char* fbn = getenv("RTEN_B200_HALO_BN");
     const char* fT = getenv("RTEN_B200_HALO_T");
     for (int bn = 32; bn <= std::min(L.N, 256); bn += 32) {
@@ -303,16 +305,25 @@ rten_status launch_umma_halo_conv(rten_ctx* ctx, const GemmLaunch& L) {
             const long long alloc_slots = (long long)T * 128 + (g.kh - 1) * p.P + g.kw - 1;
             const long long loaded_slots = (long long)tb * nr * p.P;
             const long long patch_bytes = (std::max(alloc_slots, loaded_slots) * 128 + 1023) / 1024 * 1024;
-            const long long b_bytes = (long long)bn * 128;
+            // taps per weight stage: the whole window, one window row, or one tap -- the most that leaves >= 2 stages
             const long long budget = 227 * 1024 - 2048 - 2 * patch_bytes;
-            if (budget < 3 * b_bytes) continue;
+            int tps = 0;
+            for (int cand : {g.kh * g.kw, g.kw, 1}) {
+                if ((long long)cand * bn * 128 * (cand == 1 ? 3 : 2) <= budget) {
+                    tps = cand;
+                    break;
+                }
+            }
+            if (!tps || tps > 256) continue;
+            const long long b_bytes = (long long)tps * bn * 128;
             const long long strips = (g.OH + R - 1) / R;
             const long long units = strips * ((g.B + tb - 1) / tb) * (L.N / bn);
             const double waves = std::ceil((double)units / num_sms);
             // per unit: MMA clocks (T tiles x taps x c_blocks x 4 instructions of bn / 2 clocks, issue >= 40 clk each) vs the
             // operand bytes entering the SM at ~55 B/clk; epilogue not overlapped when there is a single accumulator stage
-            const double mma = (double)T * p.taps * p.c_blocks * 4.0 * std::max(40.0, bn / 2.0);
-            const double bytes = (double)p.c_blocks * (loaded_slots * 128.0 + (double)p.taps * b_bytes);
+            // (~42 clk to issue an MMA, ~320 clk per barrier hand-off of a weight stage: profiles/r01_trace_pipeline_v2.txt)
+            const double mma = (double)p.c_blocks * ((double)T * p.taps * 4.0 * std::max(42.0, bn / 2.0) + 320.0 * (p.taps / tps));
+            const double bytes = (double)p.c_blocks * (loaded_slots * 128.0 + (double)p.taps * bn * 128.0);
             const double ingest = bytes / 55.0;
             const double epi = (double)T * (bn / 32.0) * 350.0 / 2.0;
             const int acc_stages = (2 * T * bn <= 512) ? 2 : 1;
@@ -324,6 +335,7 @@ rten_status launch_umma_halo_conv(rten_ctx* ctx, const GemmLaunch& L) {
                 bT = T;
                 bR = R;
                 btb = tb;
+                btps = tps;
             }
         }
     }
@@ -341,18 +353,19 @@ rten_status launch_umma_halo_conv(rten_ctx* ctx, const GemmLaunch& L) {
     const long long loaded_slots = (long long)p.tb * p.nr * p.P;
     p.patch_bytes = (uint32_t)((std::max(alloc_slots, loaded_slots) * 128 + 1023) / 1024 * 1024);
     p.patch_tx = (uint32_t)(loaded_slots * 128);
-    p.b_bytes = (uint32_t)p.bn * 128u;
+    p.tps = btps;
+    p.b_bytes = (uint32_t)(p.tps * p.bn) * 128u;
     p.b_stages = (int)std::min<long long>(HB_MAX, (227 * 1024 - 2048 - 2LL * p.patch_bytes) / p.b_bytes);
     p.idesc = make_idesc(1 /*F32*/, 2 /*TF32*/, 2, 128, p.bn);
 
     uint32_t abox[4] = {32u, (uint32_t)p.P, (uint32_t)p.nr, (uint32_t)p.tb}, ones[4] = {1, 1, 1, 1};
-    uint32_t bbox[4] = {32u, (uint32_t)p.bn, 1u, 1u};
+    uint32_t bbox[4] = {32u, (uint32_t)p.bn, (uint32_t)p.tps, 1u};
     CUtensorMap map_a, map_b;
     if (!encode_map(ctx, &map_a, L.a, 4, true, abox, ones)) return RTEN_ERR_UNSUPPORTED_VALUE;
     if (!encode_map(ctx, &map_b, L.b, 4, true, bbox, ones)) return RTEN_ERR_UNSUPPORTED_VALUE;
     if (getenv("RTEN_B200_VERBOSE"))
-        fprintf(stderr, "[umma_halo] B=%d %dx%d C=%d N=%d k=%dx%d: bn=%d T=%d R=%d tb=%d P=%d units=%d acc_stages=%d b_stages=%d patch=%u B\n", g.B,
-                g.OH, g.OW, g.C, L.N, g.kh, g.kw, p.bn, p.T, p.R, p.tb, p.P, p.units_total, p.acc_stages, p.b_stages, p.patch_bytes);
+        fprintf(stderr, "[umma_halo] B=%d %dx%d C=%d N=%d k=%dx%d: bn=%d T=%d R=%d tb=%d P=%d units=%d acc_stages=%d b_stages=%d tps=%d patch=%u B\n", g.B,
+                g.OH, g.OW, g.C, L.N, g.kh, g.kw, p.bn, p.T, p.R, p.tb, p.P, p.units_total, p.acc_stages, p.b_stages, p.tps, p.patch_bytes);
     const size_t smem = 1024 + 1024 + 2 * (size_t)p.patch_bytes + (size_t)p.b_stages * p.b_bytes;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));

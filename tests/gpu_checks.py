@@ -1284,6 +1284,188 @@ def check_halo_conv(rt, oracle):
     return f"{n} cases, worst err/bound {worst:.3f}; halo vs generic max |d| {float(np.abs(halo - generic).max()):.2e}"
 
 
+# ------------------------------------------------------------------------------------------
+# ONNX reader + graph executor (rten_b200_model_*)
+# ------------------------------------------------------------------------------------------
+def _onnx_interpret(oracle, nodes, consts, feeds, want):
+    """Test-side interpreter of the small ONNX graphs built below: every node through the CPU oracle's operator of the
+    same name, unfused -- what rten's executor would compute."""
+    vals = dict(consts)
+    vals.update(feeds)
+    f32 = np.float32
+    for op, ins, outs, attrs in nodes:
+        x = [vals[i] if i else None for i in ins]
+        if op == "MatMul":
+            y = oracle.matmul(x[0], x[1])
+        elif op == "Add":
+            y = oracle.add(x[0], x[1])
+        elif op == "Mul":
+            y = (x[0] * x[1]).astype(f32)
+        elif op == "Softmax":
+            y = oracle.softmax(x[0], attrs.get("axis", -1))
+        elif op == "LayerNormalization":
+            y = oracle.layer_norm(x[0], x[1], x[2] if len(x) > 2 else None, attrs.get("axis", -1), attrs.get("epsilon", 1e-5))
+        elif op == "Gelu":
+            y = oracle.gelu(x[0], attrs.get("approximate") == "tanh")
+        elif op == "Erf":
+            y = oracle.erf(x[0])
+        elif op == "Relu":
+            y = oracle.relu(x[0])
+        elif op == "Reshape":
+            shape = [int(x[0].shape[i]) if d == 0 else int(d) for i, d in enumerate(np.asarray(x[1]).reshape(-1))]
+            y = np.ascontiguousarray(x[0]).reshape(shape)
+        elif op == "Transpose":
+            y = x[0].transpose(attrs["perm"])
+        elif op == "Gather":
+            y = x[0][x[1]]
+        elif op == "DynamicQuantizeLinear":
+            q, sc, zp = oracle.dynamic_quantize_linear(x[0])
+            vals[outs[0]], vals[outs[1]], vals[outs[2]] = q, np.asarray(sc, f32).reshape(()), np.asarray(zp, np.uint8).reshape(())
+            continue
+        elif op == "MatMulInteger":
+            y = oracle.matmul_integer(x[0], x[1], x[2] if len(x) > 2 else None, x[3] if len(x) > 3 else None)
+        elif op == "Cast":
+            y = x[0].astype(f32)
+        else:
+            raise AssertionError(f"interpreter: {op}")
+        vals[outs[0]] = y
+    return [vals[w] for w in want]
+
+
+def _bert_layer_onnx(oracle, W, B, S, H, nh, ffn, seed):
+    """One BERT encoder layer as an exporter writes it (opset 20: LayerNormalization and Gelu are single nodes): MatMul + Add
+    for every linear layer, Reshape / Transpose head split, Mul by 1/sqrt(d), additive mask, Softmax."""
+    r = oracle.XorShiftRng(seed)
+    dh = H // nh
+    lin = lambda i, o: ((r.uniform((i, o)) / np.float32(np.sqrt(i))).astype(np.float32), (r.uniform((o,)) * np.float32(0.1)).astype(np.float32))
+    consts = {}
+    for name, (i, o) in {"q": (H, H), "k": (H, H), "v": (H, H), "o": (H, H), "f1": (H, ffn), "f2": (ffn, H)}.items():
+        consts["w" + name], consts["b" + name] = lin(i, o)
+    for n in ("ln1", "ln2"):
+        consts[n + "g"] = (1 + 0.1 * r.uniform((H,))).astype(np.float32)
+        consts[n + "b"] = (0.1 * r.uniform((H,))).astype(np.float32)
+    consts["shape_heads"] = np.array([0, 0, nh, dh], np.int64)
+    consts["shape_merge"] = np.array([0, 0, H], np.int64)
+    consts["scale"] = np.array(1.0 / np.sqrt(dh), np.float32)
+    nodes = []
+    N = lambda op, ins, outs, **a: nodes.append((op, ins, outs, a))
+    for t in "qkv":
+        N("MatMul", ["x", "w" + t], [t + "0"])
+        N("Add", [t + "0", "b" + t], [t + "1"])
+        N("Reshape", [t + "1", "shape_heads"], [t + "2"])
+        N("Transpose", [t + "2"], [t + "h"], perm=[0, 2, 3, 1] if t == "k" else [0, 2, 1, 3])
+    N("MatMul", ["qh", "kh"], ["s0"])
+    N("Mul", ["s0", "scale"], ["s1"])
+    N("Add", ["s1", "mask"], ["s2"])
+    N("Softmax", ["s2"], ["p"], axis=-1)
+    N("MatMul", ["p", "vh"], ["c0"])
+    N("Transpose", ["c0"], ["c1"], perm=[0, 2, 1, 3])
+    N("Reshape", ["c1", "shape_merge"], ["c2"])
+    N("MatMul", ["c2", "wo"], ["a0"])
+    N("Add", ["a0", "bo"], ["a1"])
+    N("Add", ["a1", "x"], ["a2"])
+    N("LayerNormalization", ["a2", "ln1g", "ln1b"], ["h"], axis=-1, epsilon=1e-12)
+    N("MatMul", ["h", "wf1"], ["f0"])
+    N("Add", ["f0", "bf1"], ["f1"])
+    N("Gelu", ["f1"], ["f2"])
+    N("MatMul", ["f2", "wf2"], ["g0"])
+    N("Add", ["g0", "bf2"], ["g1"])
+    N("Add", ["g1", "h"], ["g2"])
+    N("LayerNormalization", ["g2", "ln2g", "ln2b"], ["out"], axis=-1, epsilon=1e-12)
+    data = W.model([W.node(op, ins, outs, **a) for op, ins, outs, a in nodes], [W.tensor(k, v) for k, v in consts.items()],
+                   [W.value_info("x", W.FLOAT, [B, S, H]), W.value_info("mask", W.FLOAT, [B, 1, 1, S])], [W.value_info("out", W.FLOAT, [B, S, H])], opset=20)
+    return data, nodes, consts
+
+
+def check_model_executor(rt, oracle):
+    """rten_b200_model_load / _run: the ONNX reader and the native graph executor.  (1) The reference's MNIST test model
+    (re-encoded from the golden fixture) gives the oracle's logits, with Conv + Relu fused at load and intermediate values
+    requestable by name.  (2) A BERT encoder layer in exporter form (MatMul + Add, Reshape / Transpose views, Softmax,
+    LayerNormalization, Gelu) matches the oracle interpreting the same graph, in both f32 modes.  (3) A dynamically
+    quantised linear layer (DynamicQuantizeLinear -> MatMulInteger -> Cast -> Mul -> Add) is bit-exact.  (4) Error paths."""
+    import os
+    import onnx_writer as W
+    from rten_b200 import graphs
+    from rten_b200.model import Model
+    import model_ref
+    here = os.path.dirname(os.path.abspath(__file__))
+    # ---- (1) MNIST
+    data = W.mnist_from_fixture(os.path.join(here, "golden", "mnist.npz"))
+    wts = graphs.load_mnist_weights(os.path.join(here, "golden", "mnist.npz"))
+    x1 = np.full((1, 1, 28, 28), 0.5, np.float32)
+    ref = model_ref.mnist_oracle(oracle, wts, x1)
+    res = {}
+    for tf32, tol in ((True, 1e-2), (False, 5e-5)):
+        ctx = new_ctx(rt, tf32=tf32)
+        m = Model(ctx, data)
+        assert m.input_names == ["input"] and m.output_names == ["logits"]
+        assert m.node_ops == ["Conv", "MaxPool", "Conv", "MaxPool", "Conv", "ReduceMean", "Reshape", "Gemm"], m.node_ops  # Relu fused
+        for xin in (x1, ctx.to_device(x1)):  # host tensor staged by the executor, and a resident tensor
+            (logits,) = m.run({"input": xin})
+            got = logits.numpy()
+            rel = float(np.abs(got - ref).max() / np.abs(ref).max())
+            assert got.shape == ref.shape and rel <= tol, f"MNIST through the executor (tf32={tf32}): rel err {rel:.3e}"
+        res[tf32] = rel
+        # any value of the graph can be requested: the pooled activation after the first block, and the logits with it
+        pooled, logits2 = m.run({"input": x1}, ["max_pool2d", "logits"])
+        want = oracle.max_pool(oracle.relu(oracle.conv(x1, wts["conv1.weight"], wts["conv1.bias"], [1, 1, 1, 1], 1, (1, 1), (1, 1))), (2, 2), [0, 0, 0, 0], (2, 2))
+        assert pooled.shape == want.shape and float(np.abs(pooled.numpy() - want).max()) <= (3e-2 if tf32 else 1e-4)
+        assert_bit_exact(logits2.numpy(), got, "same logits when an intermediate is requested too")
+        try:
+            m.run({"input": np.zeros((2, 1, 28, 28), np.float32)})  # the model's Reshape is to [1, 64]
+            raise AssertionError("expected a Reshape error")
+        except rt.OpError as e:
+            assert e.kind == "InvalidValue" and "total elements" in e.msg, str(e)
+        (again,) = m.run({"input": x1})  # the failed run released everything it held
+        assert_bit_exact(again.numpy(), got, "run after a failed run")
+    # ---- (2) transformer layer
+    B, S, H, nh, ffn = 2, 16, 64, 4, 128
+    data, nodes, consts = _bert_layer_onnx(oracle, W, B, S, H, nh, ffn, 2024)
+    r = oracle.XorShiftRng(9)
+    x = r.uniform((B, S, H))
+    mask = np.zeros((B, 1, 1, S), np.float32)
+    mask[1, ..., 11:] = -10000.0
+    (want,) = _onnx_interpret(oracle, nodes, consts, {"x": x, "mask": mask}, ["out"])
+    errs = []
+    for tf32, tol in ((True, 2e-2), (False, 2e-4)):
+        ctx = new_ctx(rt, tf32=tf32)
+        m = Model(ctx, data)
+        assert m.node_ops.count("Add") == 3 and m.node_ops.count("MatMul") == 8, m.node_ops  # six MatMul + Add(bias) pairs fused, residual / mask adds kept
+        (out,) = m.run({"x": ctx.to_device(x), "mask": mask})
+        err = float(np.abs(out.numpy() - want).max())
+        assert out.shape == want.shape and err <= tol, f"BERT layer through the executor (tf32={tf32}): max abs err {err:.3e}"
+        errs.append(err)
+    # ---- (3) dynamically quantised linear layer, unfused exporter form
+    K, N = 96, 80
+    wq, wz = r.i8((K, N)), r.i8((N,))
+    ws, bias = r.uniform((N,), 0.001, 0.05), r.uniform((N,))
+    qnodes = [("DynamicQuantizeLinear", ["x"], ["xq", "xs", "xz"], {}), ("MatMulInteger", ["xq", "w", "xz", "wz"], ["acc"], {}),
+              ("Cast", ["acc"], ["accf"], {"to": 1}), ("Mul", ["xs", "ws"], ["sc"], {}), ("Mul", ["accf", "sc"], ["y0"], {}), ("Add", ["y0", "b"], ["y"], {})]
+    qconsts = {"w": wq, "wz": wz, "ws": ws, "b": bias}
+    qdata = W.model([W.node(op, ins, outs, **a) for op, ins, outs, a in qnodes], [W.tensor(k, v) for k, v in qconsts.items()],
+                    [W.value_info("x", W.FLOAT, [5, K])], [W.value_info("y", W.FLOAT, [5, N])], opset=18)
+    xq = r.uniform((5, K), -2, 3)
+    (want_q,) = _onnx_interpret(oracle, qnodes, qconsts, {"x": xq}, ["y"])
+    ctx = new_ctx(rt)
+    (got_q,) = Model(ctx, qdata).run({"x": xq})
+    assert_bit_exact(got_q.numpy(), want_q, "quantised linear layer through the executor")
+    # ---- (4) errors
+    bad = W.model([W.node("NonMaxSuppression", ["x"], ["y"])], [], [W.value_info("x", W.FLOAT, [1])], [W.value_info("y", W.FLOAT, [1])])
+    try:
+        Model(ctx, bad)
+        raise AssertionError("expected an unsupported-operator error")
+    except rt.OpError as e:
+        assert e.kind == "UnsupportedValue" and e.msg == "unsupported operator NonMaxSuppression", str(e)
+    m = Model(ctx, qdata)
+    for kwargs, kind in (({"inputs": {"nope": xq}}, "InvalidValue"), ({"inputs": {}}, "MissingInputs"), ({"inputs": {"x": xq}, "outputs": ["zzz"]}, "InvalidValue")):
+        try:
+            m.run(**kwargs)
+            raise AssertionError("expected an error")
+        except rt.OpError as e:
+            assert e.kind == kind, str(e)
+    return f"MNIST rel err tf32 {res[True]:.1e} / 3xtf32 {res[False]:.1e}; BERT layer max abs err {errs[0]:.1e} / {errs[1]:.1e}; int8 layer bit-exact"
+
+
 ALL_CHECKS = [
     ("context", check_context), ("unary", check_unary), ("softmax", check_softmax), ("layer_norm", check_layer_norm),
     ("dql", check_dql), ("glue", check_glue), ("matmul_small", check_matmul_small), ("matmul_shapes", check_matmul_shapes),
@@ -1291,7 +1473,7 @@ ALL_CHECKS = [
     ("conv_basic", check_conv_basic), ("conv_stride", check_conv_stride), ("conv_more", check_conv_more),
     ("conv_integer", check_conv_integer), ("plans", check_plans), ("tf32x3", check_tf32x3), ("sequence", check_sequence), ("conv_integer_fused", check_conv_integer_fused),
     ("resnet50_int8_model", check_resnet50_int8_model), ("gpt2_int8_kvcache", check_gpt2_int8_kvcache), ("mnist_model", check_mnist_model), ("resnet50_model", check_resnet50_model), ("bert_model", check_bert_model),
-    ("halo_conv", check_halo_conv), ("quantized_linear", check_quantized_linear), ("attention_decode", check_attention_decode), ("skinny_f32", check_skinny_f32),
+    ("model_executor", check_model_executor), ("halo_conv", check_halo_conv), ("quantized_linear", check_quantized_linear), ("attention_decode", check_attention_decode), ("skinny_f32", check_skinny_f32),
     ("reference_rule_f32", check_reference_rule_f32), ("graph_pool_isolation", check_graph_pool_isolation),
     ("resnet50_b32_baseline", check_resnet50_b32_baseline), ("bert_b16_baseline", check_bert_b16_baseline),
     ("resnet50_int8_b64_baseline", check_resnet50_int8_b64_baseline), ("gpt2_b8_baseline", check_gpt2_b8_baseline),
