@@ -1466,6 +1466,50 @@ def check_model_executor(rt, oracle):
     return f"MNIST rel err tf32 {res[True]:.1e} / 3xtf32 {res[False]:.1e}; BERT layer max abs err {errs[0]:.1e} / {errs[1]:.1e}; int8 layer bit-exact"
 
 
+def check_generator(rt, oracle):
+    """rten-generate's loop (generator.rs:481-1000) over the HBM-resident GPT-2: the model is driven ONLY through the
+    Optimum names (input_ids / attention_mask / position_ids / past_key_values.N.* in, logits / present.N.* out), the
+    present.* handles of one step are the past_key_values.* of the next, and the cache doubles its capacity when full
+    (:878-884) -- here from 16 to 32 positions in the middle of the run, which also re-captures the decode graph.  Every
+    step's logits are compared with the oracle decoding the same tokens (2e-2 of max |logit|, greedy token within it)."""
+    from rten_b200 import graphs
+    from rten_b200.generate import GPT2DecoderModel, Generator, TopKSampler
+    import model_ref
+    ctx = new_ctx(rt, tf32=False)
+    rng = oracle.XorShiftRng(5678)
+    spec = graphs.make_gpt2_int8(lambda s: rng.uniform(s), layers=3, vocab=5000, max_pos=128)
+    B, T0, nsteps = 2, 12, 9
+    prompt = (oracle.XorShiftRng(3).u64(B * T0) % 5000).astype(np.int32).reshape(B, T0)
+    model = GPT2DecoderModel(ctx, spec, B, initial_capacity=16)
+    gen = Generator.from_model(model).with_prompt(prompt)
+    assert len(gen.kv_pairs) == 2 * 3 and gen.kv_cache_len() is None
+    dec = None
+    worst = 0.0
+    caps = []
+    for step in range(nsteps):
+        tok = next(gen)
+        if dec is None:
+            dec = model_ref.gpt2_int8_decoder(oracle, spec, prompt)
+            ref = dec.logits
+        else:
+            ref = dec.step(prev[:, None])
+        rel = float(np.abs(gen.last_logits - ref).max() / np.abs(ref).max())
+        assert gen.last_logits.shape == ref.shape and rel <= 2e-2, f"generator step {step}: rel err {rel:.3e}"
+        assert_same_greedy_token(gen.last_logits, ref, 2e-2, f"generator step {step}")
+        assert (tok == gen.last_logits.argmax(1)).all()
+        worst = max(worst, rel)
+        prev = tok  # teacher forcing: the oracle decodes the tokens the generator actually produced
+        assert gen.kv_cache_len() == T0 + step
+        caps.append(gen.kv_cache["past_key_values.0.key"].capacity)
+    assert caps[0] == 16 and caps[-1] == 32, caps
+    assert gen.prev_tokens().shape == (B, nsteps)
+    # a seeded TopK sampler runs through the same loop
+    g2 = Generator.from_model(GPT2DecoderModel(ctx, spec, B, initial_capacity=32)).with_prompt(prompt).with_sampler(TopKSampler(5, 0.8, seed=1))
+    toks = [next(g2) for _ in range(3)]
+    assert all(t.shape == (B,) for t in toks)
+    return f"{nsteps} steps, cache capacity 16 -> 32, worst rel err {worst:.2e}"
+
+
 ALL_CHECKS = [
     ("context", check_context), ("unary", check_unary), ("softmax", check_softmax), ("layer_norm", check_layer_norm),
     ("dql", check_dql), ("glue", check_glue), ("matmul_small", check_matmul_small), ("matmul_shapes", check_matmul_shapes),
@@ -1473,7 +1517,7 @@ ALL_CHECKS = [
     ("conv_basic", check_conv_basic), ("conv_stride", check_conv_stride), ("conv_more", check_conv_more),
     ("conv_integer", check_conv_integer), ("plans", check_plans), ("tf32x3", check_tf32x3), ("sequence", check_sequence), ("conv_integer_fused", check_conv_integer_fused),
     ("resnet50_int8_model", check_resnet50_int8_model), ("gpt2_int8_kvcache", check_gpt2_int8_kvcache), ("mnist_model", check_mnist_model), ("resnet50_model", check_resnet50_model), ("bert_model", check_bert_model),
-    ("model_executor", check_model_executor), ("halo_conv", check_halo_conv), ("quantized_linear", check_quantized_linear), ("attention_decode", check_attention_decode), ("skinny_f32", check_skinny_f32),
+    ("model_executor", check_model_executor), ("generator", check_generator), ("halo_conv", check_halo_conv), ("quantized_linear", check_quantized_linear), ("attention_decode", check_attention_decode), ("skinny_f32", check_skinny_f32),
     ("reference_rule_f32", check_reference_rule_f32), ("graph_pool_isolation", check_graph_pool_isolation),
     ("resnet50_b32_baseline", check_resnet50_b32_baseline), ("bert_b16_baseline", check_bert_b16_baseline),
     ("resnet50_int8_b64_baseline", check_resnet50_int8_b64_baseline), ("gpt2_b8_baseline", check_gpt2_b8_baseline),

@@ -61,3 +61,29 @@ def test_mnist_oracle_matches_independent_logits(oracle):
     assert got.shape == (1, 10)
     assert np.abs(got - want).max() <= 1e-5, np.abs(got - want).max()
     assert int(got.argmax()) == int(want.argmax())
+
+
+def test_generator_pairs_kv_cache_names_like_the_reference():
+    """rten-generate's input/output name contract (generator.rs:283-316): `past_key_values.N.key|value` pair with
+    `present.N.key|value`; a model without logits or with an unpaired cache input is rejected."""
+    from rten_b200.generate import Generator
+
+    class Fake:
+        input_names = ["input_ids", "attention_mask", "past_key_values.0.key", "past_key_values.0.value", "past_key_values.1.key", "past_key_values.1.value"]
+        output_names = ["logits", "present.0.key", "present.0.value", "present.1.key", "present.1.value"]
+
+    g = Generator.from_model(Fake())
+    assert g.kv_pairs == [("past_key_values.0.key", "present.0.key"), ("past_key_values.1.key", "present.1.key"),
+                          ("past_key_values.0.value", "present.0.value"), ("past_key_values.1.value", "present.1.value")]
+    assert g.kv_cache_len() is None
+
+    class NoLogits(Fake):
+        output_names = ["present.0.key"]
+
+    class Unpaired(Fake):
+        output_names = ["logits", "present.0.key", "present.0.value", "present.1.key"]
+
+    import pytest
+    for bad in (NoLogits, Unpaired):
+        with pytest.raises(ValueError):
+            Generator.from_model(bad())

@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q -rA -k "halo or model_executor or conv_basic or resnet50_model or resnet50_b32 or mnist" > gpurun_out/c6_pytest.log 2>&1; echo "pytest rc=$?"
+timeout 900 python -m pytest tests -m gpu -q -rA -k "halo or model_executor or generator or conv_basic or resnet50_model or resnet50_b32 or mnist" > gpurun_out/c6_pytest.log 2>&1; echo "pytest rc=$?"
 grep -E "PASSED|FAILED|passed|failed" gpurun_out/c6_pytest.log | tail -12
 grep -n "Error" gpurun_out/c6_pytest.log | head
 timeout 900 python tools/halo_sweep.py > gpurun_out/c6_halo_sweep.log 2>&1; echo "sweep rc=$?"; cat gpurun_out/halo_sweep.txt
