@@ -11,6 +11,7 @@
 #include <cstring>
 
 #include "api_util.h"
+#include "attn_fused.h"
 #include "rowops.h"
 #include "skinny.h"
 
@@ -252,6 +253,55 @@ rten_status rten_b200_attention(rten_ctx* ctx, const rten_tensor* query, const r
             }
             return sc.finish(st);
         }
+    }
+    // ---- encoder shapes (128 keys, head size 64, value tensor stored transposed): ONE tcgen05 kernel per layer
+    // (single-pass TF32 products: only when the context opted in to that mode)
+    if (resident && ctx->f32_mode == RTEN_F32_TF32 && !new_key && !nonpad_kv_seqlen && !prm->is_causal && qh == kvh && dv == dh &&
+        query->strides[3] == 1 && key->strides[3] == 1 && value->strides[2] == 1 &&
+        (!attn_mask || (ms[1] == 0 && ms[2] == 0 && (ms[3] == 1 || total == 1)))) {
+        AttnFusedLaunch L;
+        L.B = (int)B;
+        L.heads = (int)qh;
+        L.q_seq = (int)qs;
+        L.kv_seq = (int)total;
+        L.dh = (int)dh;
+        auto od = [&](const rten_tensor* t, bool transposed) {
+            OperandDesc d;
+            d.base = t->data;
+            d.dims[0] = transposed ? t->shape[2] : t->shape[3];
+            d.dims[1] = transposed ? t->shape[3] : t->shape[2];
+            d.dims[2] = t->shape[1];
+            d.dims[3] = t->shape[0];
+            d.strides[0] = 1;
+            d.strides[1] = transposed ? t->strides[3] : t->strides[2];
+            d.strides[2] = t->strides[1];
+            d.strides[3] = t->strides[0];
+            return d;
+        };
+        L.q = od(query, false);
+        L.k = od(key, false);
+        L.vt = od(value, true);
+        L.mask = attn_mask ? (const float*)attn_mask->data : nullptr;
+        L.m_b = ms[0];
+        L.scale = scale;
+        OpScope sc(ctx);
+        rten_tensor ov;
+        const int64_t oshape[4] = {B, qh, qs, dh};
+        rten_status st = sc.out(out, RTEN_F32, 4, oshape, &ov, nullptr);
+        if (st == RTEN_OK) {
+            L.out = (float*)ov.data;
+            L.o_b = ov.strides[0];
+            L.o_h = ov.strides[1];
+            L.o_s = ov.strides[2];
+            if (ov.strides[3] == 1 && attn_fused_supported(L)) return sc.finish(launch_attn_fused(ctx, L));
+            if (out->data == ov.data && sc.allocated.size()) {  // allocated here but not usable: give it back, compose below
+                pool_free(ctx, ov.data);
+                out->data = nullptr;
+                sc.allocated.clear();
+            }
+        }
+        st = sc.finish(st);
+        if (st != RTEN_OK) return st;
     }
     // ---- general path: scale * Q K^T (+ mask) -> Softmax (NaNs flushed) -> . V  with this library's operators.
     // Causal masking / externally managed caches with q_seq > 1 need the mask spelled out by the caller.

@@ -1427,6 +1427,32 @@ __global__ void __launch_bounds__(256) tf32x3_split_kernel(const float* __restri
     }
 }
 
+// 128-bit variant: one float4 of the (padded) inner dimension per thread, 32-bit index arithmetic
+__global__ void __launch_bounds__(256) tf32x3_split_vec_kernel(const float* __restrict__ x, float* __restrict__ y, const SplitParams p) {
+    const unsigned q0 = (unsigned)(p.d0p >> 2), d1 = (unsigned)p.d1, d2 = (unsigned)p.d2;
+    const unsigned n4 = (unsigned)(p.n >> 2);
+    const unsigned stride = gridDim.x * blockDim.x;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const unsigned c4 = i % q0;
+        unsigned r = i / q0;
+        const unsigned i1 = r % d1;
+        r /= d1;
+        const unsigned i2 = r % d2, i3 = r / d2;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if ((long long)c4 * 4 < p.d0) v = *reinterpret_cast<const float4*>(x + (long long)i3 * p.s3 + (long long)i2 * p.s2 + (long long)i1 * p.s1 + c4 * 4);
+        float4 hi, lo;
+        hi.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+        hi.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+        hi.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+        hi.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+        lo = make_float4(__fsub_rn(v.x, hi.x), __fsub_rn(v.y, hi.y), __fsub_rn(v.z, hi.z), __fsub_rn(v.w, hi.w));
+        float4* row = reinterpret_cast<float4*>(y + (long long)(i / q0) * (3 * p.d0p)) + c4;
+        row[0] = p.role == 0 ? lo : hi;
+        row[q0] = p.role == 0 ? hi : lo;
+        row[2 * q0] = hi;
+    }
+}
+
 rten_status launch_tf32x3_split(rten_ctx* ctx, const float* x, float* y, const long long dims[4], const long long strides[4],
                                 long long d0p, int role) {
     SplitParams p;
@@ -1441,7 +1467,12 @@ rten_status launch_tf32x3_split(rten_ctx* ctx, const float* x, float* y, const l
     p.n = p.d3 * p.d2 * p.d1 * p.d0p;
     p.role = role;
     if (p.n == 0) return RTEN_OK;
-    tf32x3_split_kernel<<<ew_grid(ctx, p.n), 256, 0, launch_stream(ctx)>>>(x, y, p);
+    const bool vec = (p.d0 & 3) == 0 && (p.d0p & 3) == 0 && (p.s1 & 3) == 0 && (p.s2 & 3) == 0 && (p.s3 & 3) == 0 &&
+                     (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 && p.n < 0x7fffffffLL;
+    if (vec)
+        tf32x3_split_vec_kernel<<<ew_grid(ctx, p.n / 4), 256, 0, launch_stream(ctx)>>>(x, y, p);
+    else
+        tf32x3_split_kernel<<<ew_grid(ctx, p.n), 256, 0, launch_stream(ctx)>>>(x, y, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail_cuda(ctx, e, "tf32x3 split launch");
     count_launch(ctx);

@@ -440,6 +440,7 @@ class BertRunner:
         self.gather, self.add, self.gelu = O.GatherRows(), O.Add(), O.Gelu()
         self.ln = O.LayerNormalization(-1, spec.eps)
         self.addsoftmax = O.AddSoftmax()
+        self.attention = O.Attention()
 
     def _linear(self, x, wp, b, act=O.ACT_NONE, residual=None):
         w, pk = wp
@@ -479,10 +480,16 @@ class BertRunner:
                 v_heads = vt.view((B, nh, S, dh), (H * S, dh * S, 1, S))
             else:
                 v_heads = heads(self._linear(x, d["wv"], d["bv"]))
-            scores = O.FusedMatMul(scale).run(ctx, heads(q), kt)             # [B,nh,S,S]
-            probs = self.addsoftmax.run(ctx, scores, add_mask, in_place=True)
             att = ctx.empty((B * S, H))
-            O.MatMul().run(ctx, probs, v_heads, out=att.view((B, nh, S, dh), (S * H, dh, H, 1)))
+            if self.fuse:
+                # the Attention operator (src/ops/attention.rs:645-905): for 128 keys / head size 64 one tcgen05 kernel
+                # (scores and probabilities never leave the SM); other shapes / the 3xTF32 mode compose the three operators
+                self.attention.scale = scale
+                self.attention.run(ctx, heads(q), heads(k), v_heads, attn_mask=add_mask, out=att.view((B, nh, S, dh), (S * H, dh, H, 1)))
+            else:
+                scores = O.FusedMatMul(scale).run(ctx, heads(q), kt)         # [B,nh,S,S]
+                probs = self.addsoftmax.run(ctx, scores, add_mask, in_place=True)
+                O.MatMul().run(ctx, probs, v_heads, out=att.view((B, nh, S, dh), (S * H, dh, H, 1)))
             y = self._linear(att, d["wo"], d["bo"], residual=x)
             x = self.ln.run(ctx, y, d["ln1_g"], d["ln1_b"])
             h = self._linear(x, d["w1"], d["b1"], act=O.ACT_GELU)
