@@ -590,7 +590,7 @@ struct AttnDecodeParams {
 constexpr int ATTN_CHUNK = 128;  // cached positions per CTA
 
 template <int DH>
-__global__ void __launch_bounds__(256, 2) attn_decode_kernel(const AttnDecodeParams p) {
+__global__ void __launch_bounds__(256, DH == 64 ? 3 : 1) attn_decode_kernel(const AttnDecodeParams p) {
     // Every warp owns 16 consecutive cached positions of the CTA's chunk and runs the whole attention on them by itself
     // (scores, local max, exponentials, local sum, value product): no block barrier until the eight warps' partial
     // (max, sum, output) triples are merged -- the same merge that later combines the splits of a (batch, head).

@@ -248,7 +248,11 @@ umma_halo_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 }  // namespace
 
 rten_status launch_umma_halo_conv(rten_ctx* ctx, const GemmLaunch& L) {
-    if (getenv("RTEN_B200_NO_HALO")) return RTEN_ERR_UNSUPPORTED_VALUE;
+    // Opt-in (RTEN_B200_HALO=1): measured at parity with the autotuned generic kernel on the 56^2 / 28^2 layers and slower
+    // on 14^2 / 7^2 (profiles/r02_halo_sweep.txt) -- both are paced by the shared-memory operand reads of
+    // SS-mode tcgen05.mma, which the patch does not reduce.
+    const char* on = getenv("RTEN_B200_HALO");
+    if (!on || atoi(on) == 0 || getenv("RTEN_B200_NO_HALO")) return RTEN_ERR_UNSUPPORTED_VALUE;
     if (!L.conv || L.kind != 0) return RTEN_ERR_UNSUPPORTED_VALUE;
     const ConvGeom& g = L.g;
     const EpilogueDesc& e = L.epi;

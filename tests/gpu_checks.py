@@ -1248,6 +1248,15 @@ def check_halo_conv(rt, oracle):
     images per unit, batch tails), 5x5 / 1x3 / 3x1 windows, asymmetric padding, both f32 modes; against float64 within the
     TF32 bound, and the generic implicit-GEMM kernel must agree within the same bound."""
     import os
+    os.environ["RTEN_B200_HALO"] = "1"  # the kernel is opt-in (DESIGN.md 4.2)
+    try:
+        return _check_halo_conv(rt, oracle)
+    finally:
+        os.environ.pop("RTEN_B200_HALO", None)
+
+
+def _check_halo_conv(rt, oracle):
+    import os
     worst, n = 0.0, 0
     cases = [((2, 64, 56, 56), (64, 64, 3, 3), (1, 1, 1, 1)), ((3, 128, 28, 28), (128, 128, 3, 3), (1, 1, 1, 1)),
              ((5, 256, 14, 14), (256, 256, 3, 3), (1, 1, 1, 1)), ((7, 512, 7, 7), (512, 512, 3, 3), (1, 1, 1, 1)),

@@ -6,6 +6,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 os.environ.setdefault("RTEN_B200_F32_MODE", "tf32")
+os.environ["RTEN_B200_HALO"] = "1"
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
