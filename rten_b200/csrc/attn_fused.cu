@@ -40,7 +40,7 @@ struct AttnFusedParams {
     long long o_b, o_h, o_s;
 };
 
-__global__ void __launch_bounds__(AF_THREADS, 1)
+__global__ void __launch_bounds__(AF_THREADS, 2)
 attn_fused_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
                   const __grid_constant__ CUtensorMap tma_v, const __grid_constant__ AttnFusedParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -54,7 +54,8 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
     uint8_t* sq = base + 1024;              // 2 tiles
     uint8_t* sk = sq + 2 * TILE;            // 2 tiles
     uint8_t* sv = sk + 2 * TILE;            // 4 tiles of V^T
-    uint8_t* sp = sv + 4 * VT_TILE;         // 4 tiles of P
+    uint8_t* sp = sq;                       // 4 tiles of P: over Q and K, which are dead once S = Q K^T has completed (bar_s)
+                                            // -> 98 KB per CTA, two CTAs per SM: one CTA's softmax overlaps the other's TMA / MMA
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int u = blockIdx.x;
     const int qt = u % p.q_tiles, h = (u / p.q_tiles) % p.heads, b = u / (p.q_tiles * p.heads);
@@ -224,7 +225,7 @@ rten_status launch_attn_fused(rten_ctx* ctx, const AttnFusedLaunch& L) {
     if (!encode_map(ctx, &mq, L.q, 4, true, qbox, ones) || !encode_map(ctx, &mk, L.k, 4, true, kbox, ones) ||
         !encode_map(ctx, &mv, L.vt, 4, true, vbox, ones))
         return RTEN_ERR_UNSUPPORTED_VALUE;
-    const size_t smem = 1024 + 1024 + 4 * (size_t)TILE + 4 * (size_t)VT_TILE + 4 * (size_t)TILE;
+    const size_t smem = 1024 + 1024 + 4 * (size_t)TILE + 4 * (size_t)VT_TILE;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(L.B * L.heads * p.q_tiles);
