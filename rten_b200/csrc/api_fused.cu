@@ -257,7 +257,7 @@ rten_status rten_b200_attention(rten_ctx* ctx, const rten_tensor* query, const r
     // ---- encoder shapes (128 keys, head size 64, value tensor stored transposed): ONE tcgen05 kernel per layer
     // (single-pass TF32 products: only when the context opted in to that mode)
     if (resident && ctx->f32_mode == RTEN_F32_TF32 && !new_key && !nonpad_kv_seqlen && !prm->is_causal && qh == kvh && dv == dh &&
-        query->strides[3] == 1 && key->strides[3] == 1 && value->strides[2] == 1 &&
+        query->strides[3] == 1 && key->strides[3] == 1 && (value->strides[2] == 1 || value->strides[3] == 1) &&
         (!attn_mask || (ms[1] == 0 && ms[2] == 0 && (ms[3] == 1 || total == 1)))) {
         AttnFusedLaunch L;
         L.B = (int)B;
@@ -280,7 +280,14 @@ rten_status rten_b200_attention(rten_ctx* ctx, const rten_tensor* query, const r
         };
         L.q = od(query, false);
         L.k = od(key, false);
-        L.vt = od(value, true);
+        if (value->strides[3] == 1 && value->strides[2] != 1) {  // natural layout: the kernel transposes the tile itself
+            L.v = (const float*)value->data;
+            L.v_b = value->strides[0];
+            L.v_h = value->strides[1];
+            L.v_s = value->strides[2];
+        } else {
+            L.vt = od(value, true);
+        }
         L.mask = attn_mask ? (const float*)attn_mask->data : nullptr;
         L.m_b = ms[0];
         L.scale = scale;

@@ -33,6 +33,8 @@ constexpr uint32_t VT_TILE = DH * 128;    // a [64 rows x 32 floats] tile of V^T
 
 struct AttnFusedParams {
     int B, heads, q_tiles;
+    const float* v;  // natural value tensor [b][h][s][d] (d contiguous): transposed into the V^T tiles by the kernel; null = TMA from V^T
+    long long v_b, v_h, v_s;
     float scale;
     const float* mask;  // additive [B, keys] (row stride m_b) or null
     long long m_b;
@@ -65,7 +67,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
         tma_prefetch_desc(&tma_k);
         tma_prefetch_desc(&tma_v);
         mbar_init(bar_qk, 1);
-        mbar_init(bar_v, 1);
+        mbar_init(bar_v, p.v ? 4 : 1);
         mbar_init(bar_s, 1);
         mbar_init(bar_p, 4);
         mbar_init(bar_o, 1);
@@ -89,8 +91,10 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
                 tma_load_4d(sq + kb * TILE, &tma_q, bar_qk, kb * 32, qt * SQ, h, b);
                 tma_load_4d(sk + kb * TILE, &tma_k, bar_qk, kb * 32, 0, h, b);
             }
-            mbar_expect_tx(bar_v, 4 * VT_TILE);
-            for (int kb = 0; kb < 4; kb++) tma_load_4d(sv + kb * VT_TILE, &tma_v, bar_v, kb * 32, 0, h, b);
+            if (!p.v) {
+                mbar_expect_tx(bar_v, 4 * VT_TILE);
+                for (int kb = 0; kb < 4; kb++) tma_load_4d(sv + kb * VT_TILE, &tma_v, bar_v, kb * 32, 0, h, b);
+            }
         }
         __syncwarp();
         // ---- S = Q K^T
@@ -125,6 +129,28 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
         const int r = warp * 32 + lane;
         const uint32_t t_row = tmem + ((uint32_t)(warp * 32) << 16);
         const float* mrow = p.mask ? p.mask + (long long)b * p.m_b : nullptr;
+        if (p.v) {
+            // natural V [s][d]: this thread's key row s = r goes into column r of the K-major, 128B-swizzled V^T tiles
+            // (tile r / 32, row d, 16-byte chunk ((r % 32) / 4) ^ (d & 7)) while the tensor core is busy with Q K^T
+            const float4* vrow = reinterpret_cast<const float4*>(p.v + (long long)b * p.v_b + (long long)h * p.v_h + (long long)r * p.v_s);
+            float4 vv[DH / 4];
+#pragma unroll
+            for (int j = 0; j < DH / 4; j++) vv[j] = vrow[j];
+            uint8_t* tile = sv + (r >> 5) * VT_TILE;
+            const int col = r & 31;
+#pragma unroll
+            for (int j = 0; j < DH / 4; j++) {
+                const float e[4] = {vv[j].x, vv[j].y, vv[j].z, vv[j].w};
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    const int d = 4 * j + t;
+                    *reinterpret_cast<float*>(tile + d * 128 + (((col >> 2) ^ (d & 7)) << 4) + ((col & 3) << 2)) = e[t];
+                }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_v);
+        }
         float z[SK];
         mbar_wait(bar_s, 0);
         tc_fence_after();
@@ -202,7 +228,8 @@ bool attn_fused_supported(const AttnFusedLaunch& L) {
     auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
     if (!al16(L.out) || (L.o_b & 3) || (L.o_h & 3) || (L.o_s & 3)) return false;
     // Q, K: head dimension contiguous; V: key dimension contiguous (a transposed value tensor)
-    if (!tma_compatible(L.q, 4, 4) || !tma_compatible(L.k, 4, 4) || !tma_compatible(L.vt, 4, 4)) return false;
+    if (!tma_compatible(L.q, 4, 4) || !tma_compatible(L.k, 4, 4)) return false;
+    if (L.v ? (!al16(L.v) || (L.v_b & 3) || (L.v_h & 3) || (L.v_s & 3)) : !tma_compatible(L.vt, 4, 4)) return false;
     return true;
 }
 
@@ -215,6 +242,10 @@ rten_status launch_attn_fused(rten_ctx* ctx, const AttnFusedLaunch& L) {
     p.scale = L.scale;
     p.mask = L.mask;
     p.m_b = L.m_b;
+    p.v = L.v;
+    p.v_b = L.v_b;
+    p.v_h = L.v_h;
+    p.v_s = L.v_s;
     p.out = L.out;
     p.o_b = L.o_b;
     p.o_h = L.o_h;
@@ -222,9 +253,9 @@ rten_status launch_attn_fused(rten_ctx* ctx, const AttnFusedLaunch& L) {
     uint32_t ones[4] = {1, 1, 1, 1};
     uint32_t qbox[4] = {32u, (uint32_t)SQ, 1u, 1u}, kbox[4] = {32u, (uint32_t)SK, 1u, 1u}, vbox[4] = {32u, (uint32_t)DH, 1u, 1u};
     CUtensorMap mq, mk, mv;
-    if (!encode_map(ctx, &mq, L.q, 4, true, qbox, ones) || !encode_map(ctx, &mk, L.k, 4, true, kbox, ones) ||
-        !encode_map(ctx, &mv, L.vt, 4, true, vbox, ones))
-        return RTEN_ERR_UNSUPPORTED_VALUE;
+    if (!encode_map(ctx, &mq, L.q, 4, true, qbox, ones) || !encode_map(ctx, &mk, L.k, 4, true, kbox, ones)) return RTEN_ERR_UNSUPPORTED_VALUE;
+    mv = mq;  // (unused when the kernel transposes a natural V itself)
+    if (!L.v && !encode_map(ctx, &mv, L.vt, 4, true, vbox, ones)) return RTEN_ERR_UNSUPPORTED_VALUE;
     const size_t smem = 1024 + 1024 + 4 * (size_t)TILE + 4 * (size_t)VT_TILE;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));

@@ -9,7 +9,9 @@ struct AttnFusedLaunch {
     int B = 0, heads = 0, q_seq = 0, kv_seq = 0, dh = 0;
     OperandDesc q;   // (d, s, h, b): head dimension contiguous
     OperandDesc k;   // (d, s, h, b)
-    OperandDesc vt;  // (s, d, h, b): KEY dimension contiguous (the value tensor stored transposed)
+    OperandDesc vt;  // (s, d, h, b): KEY dimension contiguous (the value tensor stored transposed) -- used when v == null
+    const float* v = nullptr;  // natural value tensor, head dimension contiguous, element strides v_b / v_h / v_s
+    long long v_b = 0, v_h = 0, v_s = 0;
     const float* mask = nullptr;  // additive, [B, kv_seq] with row stride m_b (0 = one row for every batch), or null
     long long m_b = 0;
     float scale = 1.0f;

@@ -436,6 +436,10 @@ class BertRunner:
                 d[name] = (w, mm.prepack(ctx, 1, w))
             for name in ("bq", "bk", "bv", "bo", "b1", "b2", "ln1_g", "ln1_b", "ln2_g", "ln2_b"):
                 d[name] = dev(getattr(L, name))
+            # fused path: Q, K, V projections as ONE 768 -> 2304 GEMM (the three MatMuls share their input)
+            wqkv = dev(np.ascontiguousarray(np.concatenate([L.wq, L.wk, L.wv], 1)))
+            d["wqkv"] = (wqkv, mm.prepack(ctx, 1, wqkv))
+            d["bqkv"] = dev(np.concatenate([L.bq, L.bk, L.bv]))
             self.layers.append(d)
         self.gather, self.add, self.gelu = O.GatherRows(), O.Add(), O.Gelu()
         self.ln = O.LayerNormalization(-1, spec.eps)
@@ -465,31 +469,33 @@ class BertRunner:
         x = self.ln.run(ctx, x, self.emb_g, self.emb_b)
         x = x.reshape(B * S, H)
         scale = 1.0 / math.sqrt(dh)
-        x3 = lambda t: t.view((B, S, H), (S * H, H, 1))
         for d in self.layers:
+            if self.fuse:
+                # one GEMM for Q | K | V (the three MatMuls share their input), then the Attention operator
+                # (src/ops/attention.rs:645-905) on strided [B,nh,S,dh] views of its output: for 128 keys / head size 64
+                # in single-pass TF32 one tcgen05 kernel (scores and probabilities never leave the SM, V transposed
+                # in shared memory); other shapes / the 3xTF32 mode compose MatMul -> Softmax -> MatMul
+                qkv = self._linear(x, d["wqkv"], d["bqkv"])                   # [B*S, 3H]
+                part = lambda i: qkv.view((B, nh, S, dh), (S * 3 * H, dh, 3 * H, 1), i * H)
+                att = ctx.empty((B * S, H))
+                self.attention.scale = scale
+                self.attention.run(ctx, part(0), part(1), part(2), attn_mask=add_mask, out=att.view((B, nh, S, dh), (S * H, dh, H, 1)))
+                y = self._linear(att, d["wo"], d["bo"], residual=x)
+                x = self.ln.run(ctx, y, d["ln1_g"], d["ln1_b"])
+                h = self._linear(x, d["w1"], d["b1"], act=O.ACT_GELU)
+                y = self._linear(h, d["w2"], d["b2"], residual=x)
+                x = self.ln.run(ctx, y, d["ln2_g"], d["ln2_b"])
+                continue
+            # unfused reference arrangement: three projections, scores / probabilities through HBM
             q = self._linear(x, d["wq"], d["bq"])
             k = self._linear(x, d["wk"], d["bk"])
             heads = lambda t: t.view((B, nh, S, dh), (S * H, dh, H, 1))      # [B,S,nh,dh] memory seen as [B,nh,S,dh]
             kt = k.view((B, nh, dh, S), (S * H, dh, 1, H))                   # K^T view
-            if self.fuse:
-                # V is written TRANSPOSED per batch ([B, H, S] memory: the MatMul output is a strided view), so that
-                # probs.V finds its reduction dimension (the sequence) contiguous and needs no re-layout
-                vt = ctx.empty((B, H, S))
-                w, pk = d["wv"]
-                O.FusedMatMul(None).run(ctx, x3(x), w, d["bv"], packed_b=pk, out=vt.view((B, S, H), (H * S, 1, S)))
-                v_heads = vt.view((B, nh, S, dh), (H * S, dh * S, 1, S))
-            else:
-                v_heads = heads(self._linear(x, d["wv"], d["bv"]))
+            v_heads = heads(self._linear(x, d["wv"], d["bv"]))
             att = ctx.empty((B * S, H))
-            if self.fuse:
-                # the Attention operator (src/ops/attention.rs:645-905): for 128 keys / head size 64 one tcgen05 kernel
-                # (scores and probabilities never leave the SM); other shapes / the 3xTF32 mode compose the three operators
-                self.attention.scale = scale
-                self.attention.run(ctx, heads(q), heads(k), v_heads, attn_mask=add_mask, out=att.view((B, nh, S, dh), (S * H, dh, H, 1)))
-            else:
-                scores = O.FusedMatMul(scale).run(ctx, heads(q), kt)         # [B,nh,S,S]
-                probs = self.addsoftmax.run(ctx, scores, add_mask, in_place=True)
-                O.MatMul().run(ctx, probs, v_heads, out=att.view((B, nh, S, dh), (S * H, dh, H, 1)))
+            scores = O.FusedMatMul(scale).run(ctx, heads(q), kt)             # [B,nh,S,S]
+            probs = self.addsoftmax.run(ctx, scores, add_mask, in_place=True)
+            O.MatMul().run(ctx, probs, v_heads, out=att.view((B, nh, S, dh), (S * H, dh, H, 1)))
             y = self._linear(att, d["wo"], d["bo"], residual=x)
             x = self.ln.run(ctx, y, d["ln1_g"], d["ln1_b"])
             h = self._linear(x, d["w1"], d["b1"], act=O.ACT_GELU)

@@ -1223,6 +1223,55 @@ def check_attention_decode(rt, oracle):
     return f"{n + 2} decode cases, worst rel err {worst:.1e}; composed q_seq=32 rel err {err:.1e}"
 
 
+def check_attention_encoder(rt, oracle):
+    """rten_b200_attention on encoder shapes (128 keys, head size 64, q_seq a multiple of 128) in the single-pass TF32 mode:
+    the one-kernel tcgen05 path (QK^T -> masked softmax -> PV inside the SM) against a float64 restatement of
+    src/ops/attention.rs:645-905, for every value layout the kernel takes -- contiguous [B,nh,S,dh], strided views of a
+    merged Q|K|V projection ([B,S,3H] memory, the layout BertRunner feeds it), and a transposed value tensor --
+    with and without an additive [B,1,1,S] mask, output written through a strided [B,S,H] view.  TF32 operands
+    (10-bit mantissas) in both products: |d| <= 4e-3 * max |ref| (stated); the composed 3xTF32 path must agree with the
+    float64 reference within 1e-4 on the same inputs."""
+    r = oracle.XorShiftRng(4242)
+    worst = 0.0
+    n = 0
+    for B, nh, S, use_mask in [(3, 5, 128, True), (2, 12, 128, False), (2, 3, 256, True)]:
+        dh, H = 64, nh * 64
+        kv = 128
+        qkv = r.uniform((B, max(S, kv), 3 * H), -1, 1)
+        q = qkv[:, :S, 0:H].reshape(B, S, nh, dh).transpose(0, 2, 1, 3)
+        k = qkv[:, :kv, H:2 * H].reshape(B, kv, nh, dh).transpose(0, 2, 1, 3)
+        v = qkv[:, :kv, 2 * H:].reshape(B, kv, nh, dh).transpose(0, 2, 1, 3)
+        mask = r.uniform((B, 1, 1, kv), -3, 0) if use_mask else None
+        s = 0.125 * np.einsum("bhqd,bhkd->bhqk", q.astype(np.float64), k.astype(np.float64))
+        if mask is not None:
+            s = s + mask
+        pr = np.exp(s - s.max(-1, keepdims=True))
+        ref = np.einsum("bhqk,bhkd->bhqd", pr / pr.sum(-1, keepdims=True), v.astype(np.float64))
+        for tf32 in (True, False):
+            ctx = new_ctx(rt, tf32=tf32)
+            dm = None if mask is None else ctx.to_device(mask)
+            Sm = qkv.shape[1]
+            dqkv = ctx.to_device(qkv)
+            part = lambda i, rows: dqkv.view((B, nh, rows, dh), (Sm * 3 * H, dh, 3 * H, 1), i * H)
+            layouts = {
+                "merged qkv views": (part(0, S), part(1, kv), part(2, kv)),
+                "contiguous": (ctx.to_device(np.ascontiguousarray(q)), ctx.to_device(np.ascontiguousarray(k)), ctx.to_device(np.ascontiguousarray(v))),
+            }
+            dvt = ctx.to_device(np.ascontiguousarray(v.transpose(0, 1, 3, 2)))
+            layouts["transposed value"] = (layouts["contiguous"][0], layouts["contiguous"][1], dvt.view((B, nh, kv, dh), (nh * dh * kv, dh * kv, 1, kv)))
+            for name, (dq, dk, dv) in layouts.items():
+                att = ctx.empty((B, S, H))
+                rt.Attention(scale=0.125).run(ctx, dq, dk, dv, attn_mask=dm, out=att.view((B, nh, S, dh), (S * H, dh, H, 1)))
+                got = att.numpy().reshape(B, S, nh, dh).transpose(0, 2, 1, 3)
+                err = float(np.abs(got - ref).max() / np.abs(ref).max())
+                tol = 4e-3 if tf32 else 1e-4
+                assert err <= tol, f"encoder Attention B={B} nh={nh} S={S} mask={use_mask} tf32={tf32} ({name}): rel err {err:.2e} > {tol}"
+                if tf32:
+                    worst = max(worst, err)
+                n += 1
+    return f"{n} cases (3 value layouts x 2 modes x 3 shapes), one-kernel TF32 path worst rel err {worst:.1e}"
+
+
 def check_skinny_f32(rt, oracle):
     """MatMul / Gemm / FusedMatMul with M <= 32 rows run the HBM-streaming skinny kernel in exact f32 FMA arithmetic
     (rten-gemm's gemv path): the reference's float rule against the oracle, in BOTH f32 modes (the mode does not
@@ -1526,7 +1575,7 @@ ALL_CHECKS = [
     ("conv_basic", check_conv_basic), ("conv_stride", check_conv_stride), ("conv_more", check_conv_more),
     ("conv_integer", check_conv_integer), ("plans", check_plans), ("tf32x3", check_tf32x3), ("sequence", check_sequence), ("conv_integer_fused", check_conv_integer_fused),
     ("resnet50_int8_model", check_resnet50_int8_model), ("gpt2_int8_kvcache", check_gpt2_int8_kvcache), ("mnist_model", check_mnist_model), ("resnet50_model", check_resnet50_model), ("bert_model", check_bert_model),
-    ("model_executor", check_model_executor), ("generator", check_generator), ("halo_conv", check_halo_conv), ("quantized_linear", check_quantized_linear), ("attention_decode", check_attention_decode), ("skinny_f32", check_skinny_f32),
+    ("model_executor", check_model_executor), ("generator", check_generator), ("halo_conv", check_halo_conv), ("quantized_linear", check_quantized_linear), ("attention_decode", check_attention_decode), ("attention_encoder", check_attention_encoder), ("skinny_f32", check_skinny_f32),
     ("reference_rule_f32", check_reference_rule_f32), ("graph_pool_isolation", check_graph_pool_isolation),
     ("resnet50_b32_baseline", check_resnet50_b32_baseline), ("bert_b16_baseline", check_bert_b16_baseline),
     ("resnet50_int8_b64_baseline", check_resnet50_int8_b64_baseline), ("gpt2_b8_baseline", check_gpt2_b8_baseline),
