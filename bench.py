@@ -305,7 +305,7 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     model = args.model
-    batch = MODELS[model]["batch"]
+    batch = int(os.environ.get("RTEN_BENCH_BATCH", MODELS[model]["batch"]))  # (the override is a tuning aid: not a BASELINE config)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -654,7 +654,12 @@ def main():
             # time the tensor-core kernels occupy the GPU is then bounded by the step itself.
             busy_us = min(kern_us, step_ms * 1e3) if kern_us else None
             ach = fl / (busy_us / 1e6) / 1e12 if busy_us else lb
-            return {"bound": "tensor", "kernel": f"rtb::umma_gemm_kernel<{1 if kind == 'int8' else 0}> (tcgen05 kind::{'i8' if kind == 'int8' else 'tf32'} implicit-GEMM conv / GEMM)",
+            lw = layerwise_floor_us(model, spec, batch, burst, peaks["hbm_gbs"])
+            if lw:
+                lw["frac"] = lw["floor_us"] / (step_ms * 1e3)
+                lw["how"] = ("sum over the conv layers of max(layer flops / tensor peak, layer HBM bytes / HBM peak) divided by the step time: "
+                             "the fraction of the per-layer roofline this step reaches (flops counted 1x in both f32 modes)")
+            return {"bound": "tensor", "layerwise": lw, "kernel": f"rtb::umma_gemm_kernel<{1 if kind == 'int8' else 0}> (tcgen05 kind::{'i8' if kind == 'int8' else 'tf32'} implicit-GEMM conv / GEMM)",
                     "achieved": ach, "peak": burst, "unit": "TFLOP/s" if kind == "tf32" else "TOP/s", "frac": ach / burst, "frac_of_sustained_peak": ach / sust,
                     "traffic": ncu_traffic(model),
                     "lower_bound": {"achieved": lb, "frac": lb / burst, "how": "algorithmic flops / whole step time (kernel time <= step time)"},
@@ -734,6 +739,40 @@ def hbm_bytes(model, spec, batch):
             total += conv(blk.down, h)[0]
         h = h3
     return total
+
+
+def layerwise_floor_us(model, spec, batch, tensor_tflops, hbm_gbs):
+    """Per-layer roofline of the ResNet-50 step: every conv layer takes at least max(flops / tensor peak, algorithmic HBM
+    bytes / HBM peak); the sum is the step's floor.  (A whole-step `flops / peak` ignores that the 1x1 layers of the first
+    stages are HBM-bound at this batch size: no kernel can run them at the tensor peak.)"""
+    if model not in ("resnet50", "resnet50_int8"):
+        return None
+    es_in = 1 if model == "resnet50_int8" else 4
+    rows = []
+
+    def conv(c, h_in, residual=False):
+        w = c.wq if hasattr(c, "wq") else c.w
+        o, i, k, _ = w.shape
+        ho = (h_in + 2 * c.pad - k) // c.stride + 1
+        by = batch * (i * h_in * h_in * es_in + o * ho * ho * 4 * (2 if residual else 1)) + w.size * es_in
+        fl = 2.0 * batch * o * ho * ho * i * k * k
+        rows.append((fl, by))
+        return ho
+
+    h = conv(spec.stem, 224)
+    h = (h + 2 - 3) // 2 + 1
+    for blk in spec.blocks:
+        h1 = conv(blk.c1, h)
+        h2 = conv(blk.c2, h1)
+        h3 = conv(blk.c3, h2, residual=True)
+        if blk.down is not None:
+            conv(blk.down, h)
+        h = h3
+    t_f = sum(fl / (tensor_tflops * 1e12) for fl, _ in rows) * 1e6
+    t_b = sum(by / (hbm_gbs * 1e9) for _, by in rows) * 1e6
+    t = sum(max(fl / (tensor_tflops * 1e12), by / (hbm_gbs * 1e9)) for fl, by in rows) * 1e6
+    return {"floor_us": t, "tensor_only_us": t_f, "hbm_only_us": t_b, "layers": len(rows),
+            "hbm_bound_layers": sum(1 for fl, by in rows if by / (hbm_gbs * 1e9) > fl / (tensor_tflops * 1e12))}
 
 
 def ncu_traffic(model):

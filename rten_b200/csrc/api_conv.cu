@@ -502,6 +502,7 @@ rten_status conv_core(OpScope& sc, ConvArgs& A, rten_tensor* out) {
             L.b.strides[1] = kh * kw * Cg;
             L.b.strides[2] = Cg;
             L.b.strides[3] = 0;
+            if (A.pw && A.kind == 0 && groups == 1 && wg == A.pw->data) L.b_x3_slot = &const_cast<rten_packed*>(A.pw)->x3;
             if (zb) {
                 // per-pixel window sums of the image = N=1 GEMM against an all-ones kernel row
                 int32_t* rs = nullptr;

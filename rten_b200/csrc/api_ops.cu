@@ -311,6 +311,7 @@ rten_status matmul_core(OpScope& sc, MatMulArgs& A, rten_tensor* out) {
         RTB_TRY(to_kmajor(ctx, esize, ma, &L.a));
         if (mb.z0 > 1 && mb.zs0 == 0) {}  // broadcast handled by stride 0
         RTB_TRY(to_kmajor(ctx, esize, mb, &L.b));
+        if (A.pb && A.kind == 0 && L.b.base == A.pb->data) L.b_x3_slot = &const_cast<rten_packed*>(A.pb)->x3;
 
         // residual (same shape as out, any strides) -> only contiguous or row-strided supported directly
         if (A.residual) {
@@ -463,6 +464,7 @@ void rten_b200_packed_free(rten_ctx* ctx, rten_packed* p) {
         pool_free(ctx, p->data);
         pool_free(ctx, p->colsum);
     }
+    if (p->x3) cudaFree(p->x3);
     delete p;
 }
 

@@ -15,6 +15,7 @@ struct rten_packed {
     int groups = 1;
     void* data = nullptr;
     int32_t* colsum = nullptr;  // int8: sum over K per output column / channel
+    void* x3 = nullptr;         // f32: [hi | lo | hi] copy for the 3xTF32 mode, built by the first launch that needs it (cudaMalloc)
 };
 
 namespace rtb {

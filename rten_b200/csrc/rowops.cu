@@ -1405,7 +1405,7 @@ struct SplitParams {
     long long d0, d0p, d1, d2, d3;
     long long s1, s2, s3;  // source strides (elements) of dims 1..3
     long long n;           // d3 * d2 * d1 * d0p
-    int role;              // 0: [lo | hi | hi] (A operand), 1: [hi | lo | hi] (B operand)
+    int role;              // 0: [lo | hi | hi] (A operand), 1: [hi | lo | hi] (B operand), 2: [lo] only (two-plane A)
 };
 
 __global__ void __launch_bounds__(256) tf32x3_split_kernel(const float* __restrict__ x, float* __restrict__ y, const SplitParams p) {
@@ -1420,6 +1420,10 @@ __global__ void __launch_bounds__(256) tf32x3_split_kernel(const float* __restri
         if (c < p.d0) v = x[i3 * p.s3 + i2 * p.s2 + i1 * p.s1 + c];
         const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
         const float lo = __fsub_rn(v, hi);
+        if (p.role == 2) {
+            y[((i3 * p.d2 + i2) * p.d1 + i1) * p.d0p + c] = lo;
+            continue;
+        }
         float* row = y + ((i3 * p.d2 + i2) * p.d1 + i1) * (3 * p.d0p);
         row[c] = p.role == 0 ? lo : hi;
         row[p.d0p + c] = p.role == 0 ? hi : lo;
@@ -1446,6 +1450,10 @@ __global__ void __launch_bounds__(256) tf32x3_split_vec_kernel(const float* __re
         hi.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
         hi.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
         lo = make_float4(__fsub_rn(v.x, hi.x), __fsub_rn(v.y, hi.y), __fsub_rn(v.z, hi.z), __fsub_rn(v.w, hi.w));
+        if (p.role == 2) {
+            reinterpret_cast<float4*>(y)[i] = lo;
+            continue;
+        }
         float4* row = reinterpret_cast<float4*>(y + (long long)(i / q0) * (3 * p.d0p)) + c4;
         row[0] = p.role == 0 ? lo : hi;
         row[q0] = p.role == 0 ? hi : lo;

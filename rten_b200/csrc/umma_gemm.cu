@@ -379,7 +379,7 @@ static rten_status ensure_splitk_counters(rten_ctx* ctx) {
 
 struct PendingLaunch {
     KParams p;
-    CUtensorMap maps[4];
+    CUtensorMap maps[5];  // a, b, d, residual, a2 (two-plane 3xTF32: low parts of A)
     size_t smem_bytes;
 };
 
@@ -428,7 +428,7 @@ static rten_status launch_single(rten_ctx* ctx, int cls, const PendingLaunch& pl
     auto launch = [&](auto kern) -> cudaError_t {
         cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e2 != cudaSuccess) return e2;
-        return cudaLaunchKernelEx(&cfg, kern, pl.maps[0], pl.maps[1], pl.maps[2], pl.maps[3], p);
+        return cudaLaunchKernelEx(&cfg, kern, pl.maps[0], pl.maps[1], pl.maps[2], pl.maps[3], pl.maps[4], p);
     };
     cudaError_t e;
     switch (cls * 2 + (p.cta2 ? 1 : 0)) {
@@ -557,7 +557,9 @@ static rten_status launch_plan(rten_ctx* ctx, const GemmLaunch& L, const Prepare
     CUtensorMap map_a, map_b;
     if (!encode_map(ctx, &map_a, L.a, q.esize, L.kind == 0, q.abox, q.aes)) return RTEN_ERR_UNSUPPORTED_VALUE;
     if (!encode_map(ctx, &map_b, L.b, q.esize, L.kind == 0, bbox, bes)) return RTEN_ERR_UNSUPPORTED_VALUE;
-    CUtensorMap map_d = map_a, map_r = map_a;
+    CUtensorMap map_d = map_a, map_r = map_a, map_a2 = map_a;
+    p.x3_cb = L.x3_cb;
+    if (L.x3_cb && !encode_map(ctx, &map_a2, L.a_lo, q.esize, true, q.abox, q.aes)) return RTEN_ERR_UNSUPPORTED_VALUE;
     if (p.tma_store && !encode_map(ctx, &map_d, q.od, 4, true, q.dbox, des)) {
         if (p.bn % 32 == 0 && false) return RTEN_ERR_UNSUPPORTED_VALUE;
         p.tma_store = 0;  // direct stores still work for any bn that is a multiple of 16
@@ -576,7 +578,7 @@ static rten_status launch_plan(rten_ctx* ctx, const GemmLaunch& L, const Prepare
     const size_t smem_bytes = (size_t)p.stages * p.stage_bytes + n_stg * STG_BYTES + 1024 /*align*/ + 1024 /*barriers*/;
     // specialised epilogue when every chunk qualifies for the register fast path
     const EpilogueDesc& ee = L.epi;
-    bool fastk = p.tma_store && (L.N % 32) == 0 && !ctx->trace && !getenv("RTEN_B200_NO_FAST");
+    bool fastk = p.tma_store && (L.N % 32) == 0 && (!ctx->trace || getenv("RTEN_B200_TRACE_FAST")) && !getenv("RTEN_B200_NO_FAST");
     if (L.kind == 0)
         fastk = fastk && ee.bias_kind != 2 && (ee.r == nullptr || p.res_tma) &&
                 (ee.bias_kind != 1 || (reinterpret_cast<uintptr_t>(ee.bias) & 15) == 0);
@@ -594,6 +596,7 @@ static rten_status launch_plan(rten_ctx* ctx, const GemmLaunch& L, const Prepare
     pend.maps[1] = map_b;
     pend.maps[2] = map_d;
     pend.maps[3] = map_r;
+    pend.maps[4] = map_a2;
     pend.smem_bytes = smem_bytes;
     // kernel class = data kind x epilogue variant (0 generic, 1 specialised, 2 specialised + out-of-line Gelu)
     const int cls = L.kind * 3 + (fastk ? (ee.act > 1 ? 2 : 1) : 0);
@@ -603,7 +606,7 @@ static rten_status launch_plan(rten_ctx* ctx, const GemmLaunch& L, const Prepare
     // cheaper than what PDL already overlaps), so separate launches stay the default.
     const char* seq_env = getenv("RTEN_B200_SEQ");
     const bool seq_on = seq_env && atoi(seq_env) != 0;
-    if (seq_on && ctx->capturing && !p.cta2 && !ctx->trace && !no_defer && cls % 3 != 2) {
+    if (seq_on && ctx->capturing && !p.cta2 && !p.x3_cb && !ctx->trace && !no_defer && cls % 3 != 2) {
         auto* q2 = pending_of(ctx);
         if (!q2->empty() && ctx->seq_class != cls) RTB_TRY(seq_flush(ctx));
         ctx->seq_class = cls;
@@ -620,7 +623,7 @@ static std::vector<long long> tune_key(const GemmLaunch& L, const Prepared& q) {
     const EpilogueDesc& e = L.epi;
     std::vector<long long> k = {L.kind, L.conv, L.M, L.N, L.K, L.z0, L.z1, q.tma_store, q.res_tma, e.act, e.bias_kind,
                                 e.r != nullptr, (e.za != nullptr || e.za8 != nullptr), e.zb != nullptr, e.scale != nullptr,
-                                L.a.strides[1], L.b.strides[1]};
+                                L.a.strides[1], L.b.strides[1], L.x3_cb};
     if (L.conv) {
         const ConvGeom& g = L.g;
         for (long long v : {g.B, g.H, g.W, g.C, g.OH, g.OW, g.kh, g.kw, g.sy, g.sx, g.dy, g.dx, g.pt, g.pl}) k.push_back(v);
@@ -641,26 +644,32 @@ static Plan plan_from_array(const std::array<int, 8>& a) {
     return pl;
 }
 
-// RTEN_F32_TF32X3: run the same kernel over split operands -- K (plain) or C (conv; K order is (ky, kx, c)) tripled.
+// RTEN_F32_TF32X3: run the same kernel over split operands -- K (plain) or C (conv; K order is (ky, kx, c)) tripled:
+// A' = [lo | hi | hi], B' = [hi | lo | hi]  =>  lo*hi + hi*lo + hi*hi, small terms first.
+//  * B: a constant operand (prepacked weights, `b_x3_slot`) is split ONCE and cached with its owner.
+//  * A: kind::tf32 ignores the 13 low mantissa bits, so the ORIGINAL tensor serves as both `hi` segments; only the low
+//    parts are written (4 B / element instead of 12) and the kernel's producer switches tensor maps per segment
+//    (KParams::x3_cb).  Needs K (C) % 32 == 0 and a TMA-addressable A; otherwise the three-segment copy is built.
 static rten_status launch_tf32x3(rten_ctx* ctx, const GemmLaunch& L0) {
     GemmLaunch L = L0;
     const long long d0 = L0.a.dims[0];               // K, or channels per group
     const long long d0p = (d0 + 3) / 4 * 4;          // thirds stay 16-byte aligned for TMA
-    auto split = [&](const OperandDesc& src, OperandDesc& dst, int role) -> rten_status {
-        long long dims[4], strides[4], n = 3 * d0p;
+    auto split = [&](const OperandDesc& src, OperandDesc& dst, int role, void* into) -> rten_status {
+        const long long planes = role == 2 ? 1 : 3;
+        long long dims[4], strides[4], n = planes * d0p;
         for (int i = 0; i < 4; i++) {
             // broadcast dims (stride 0) are split once and stay broadcast
             dims[i] = (i > 0 && src.strides[i] == 0) ? 1 : src.dims[i];
             strides[i] = src.strides[i];
         }
         for (int i = 1; i < 4; i++) n *= dims[i];
-        void* buf = nullptr;
-        RTB_TRY(temp_alloc(ctx, (size_t)n * 4, &buf));
+        void* buf = into;
+        if (!buf) RTB_TRY(temp_alloc(ctx, (size_t)n * 4, &buf));
         RTB_TRY(launch_tf32x3_split(ctx, (const float*)src.base, (float*)buf, dims, strides, d0p, role));
         dst = src;
         dst.base = buf;
-        dst.dims[0] = 3 * d0p;
-        long long st = 3 * d0p;
+        dst.dims[0] = planes * d0p;
+        long long st = planes * d0p;
         for (int i = 1; i < 4; i++) {
             dst.strides[i] = (src.strides[i] == 0 && src.dims[i] > 1) ? 0 : st;
             st *= dims[i];
@@ -668,11 +677,47 @@ static rten_status launch_tf32x3(rten_ctx* ctx, const GemmLaunch& L0) {
         return RTEN_OK;
     };
     if (L0.b.dims[0] != d0) return RTEN_ERR_UNSUPPORTED_VALUE;
-    RTB_TRY(split(L0.a, L.a, 0));
-    RTB_TRY(split(L0.b, L.b, 1));
+    // ---- B
+    if (L0.b_x3_slot && !getenv("RTEN_B200_X3_NO_CACHE")) {
+        if (!*L0.b_x3_slot && !ctx->capturing) {
+            long long n = 3 * d0p;
+            for (int i = 1; i < 4; i++) n *= (L0.b.strides[i] == 0 ? 1 : L0.b.dims[i]);
+            void* buf = nullptr;
+            if (cudaMalloc(&buf, (size_t)n * 4) != cudaSuccess) return fail(ctx, RTEN_ERR_CUDA, "cudaMalloc failed for the 3xTF32 copy of a prepacked operand");
+            OperandDesc tmp;
+            const rten_status st = split(L0.b, tmp, 1, buf);
+            if (st != RTEN_OK) {
+                cudaFree(buf);
+                return st;
+            }
+            *L0.b_x3_slot = buf;
+        }
+    }
+    if (L0.b_x3_slot && *L0.b_x3_slot && !getenv("RTEN_B200_X3_NO_CACHE")) {
+        L.b = L0.b;
+        L.b.base = *L0.b_x3_slot;
+        L.b.dims[0] = 3 * d0p;
+        long long st = 3 * d0p;
+        for (int i = 1; i < 4; i++) {
+            const long long di = L0.b.strides[i] == 0 ? 1 : L0.b.dims[i];
+            L.b.strides[i] = (L0.b.strides[i] == 0 && L0.b.dims[i] > 1) ? 0 : st;
+            st *= di;
+        }
+    } else {
+        RTB_TRY(split(L0.b, L.b, 1, nullptr));
+    }
+    // ---- A
+    const bool two_plane = d0 % 32 == 0 && tma_compatible(L0.a, 4, 4) && !getenv("RTEN_B200_X3_THREE_PLANES");
+    if (two_plane) {
+        RTB_TRY(split(L0.a, L.a_lo, 2, nullptr));
+        L.x3_cb = (int)(d0 / 32);
+    } else {
+        RTB_TRY(split(L0.a, L.a, 0, nullptr));
+    }
     if (L.conv)
         L.g.C = (int)(3 * d0p);
     L.K = L.conv ? (int)(L0.K / d0 * 3 * d0p) : (int)(3 * d0p);
+    L.b_x3_slot = nullptr;
     const int saved = ctx->f32_mode;
     ctx->f32_mode = RTEN_F32_TF32;
     const rten_status st = launch_umma_gemm(ctx, L);
@@ -684,7 +729,7 @@ rten_status launch_umma_gemm(rten_ctx* ctx, const GemmLaunch& L) {
     if (L.kind == 0 && ctx->f32_mode == RTEN_F32_TF32X3) return launch_tf32x3(ctx, L);
     // stride-1 windows (the 3x3 layers): the halo-reuse kernel moves the activations into shared memory once per channel
     // block instead of once per filter tap (umma_halo.cu); everything it does not cover falls through
-    if (L.conv && L.kind == 0 && L.g.kh * L.g.kw > 1 && !ctx->trace) {
+    if (L.conv && L.kind == 0 && L.g.kh * L.g.kw > 1 && !ctx->trace && !L.x3_cb) {
         const rten_status hs = launch_umma_halo_conv(ctx, L);
         if (hs != RTEN_ERR_UNSUPPORTED_VALUE) return hs;
     }

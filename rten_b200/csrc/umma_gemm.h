@@ -73,6 +73,12 @@ struct GemmLaunch {
     OperandDesc a;  // plain: (k, m, z0, z1); conv: (c, x, y, b)
     OperandDesc b;  // plain: (k, n, z0, z1) (stride 0 = broadcast); conv: (c, o, tap, 1)
     EpilogueDesc epi;
+    // 3xTF32 (RTEN_F32_TF32X3), set by the caller that owns a constant B: slot caching the split copy of `b`
+    // ([hi | lo | hi] along K) across launches -- weights are split once, not per call (owned by the rten_packed)
+    void** b_x3_slot = nullptr;
+    // internal (launch_tf32x3 -> kernel): two-plane A -- `a` is the original tensor (segments 1, 2), `a_lo` its low parts
+    int x3_cb = 0;
+    OperandDesc a_lo;
 };
 
 // Returns RTEN_OK and enqueues the kernel, or RTEN_ERR_UNSUPPORTED_VALUE (without touching ctx->err

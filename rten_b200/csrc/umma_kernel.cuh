@@ -81,6 +81,9 @@ struct KParams {
     int cta2;       // 1: CTA pairs (cluster 2x1x1) execute 256-row tcgen05.mma.cta_group::2 tiles; each CTA loads its own
                     //    128 rows of A and HALF of the B tile, so operand bytes entering an SM per flop drop by up to 2x
     int units_total;  // tiles_total * splitk
+    int x3_cb;      // > 0: 3xTF32 over TWO planes of A -- the K (channel) range is three segments of x3_cb K blocks,
+                    //      [lo | hi | hi]: segment 0 reads the low-part plane (tma_a2), segments 1 and 2 read the ORIGINAL f32
+                    //      tensor (kind::tf32 ignores the 13 low mantissa bits, so the raw values ARE the high parts)
     FastDiv d_tiles_n, d_units_m, d_z0, d_tiles_x, d_tiles_y, d_tiles_total, d_c_blocks, d_kw, d_tw, d_th;
     uint32_t* sk_ws;
     int* sk_cnt;
@@ -228,8 +231,8 @@ struct SmemLayout {
 // vector-addressable [residual via TMA], or raw i32): the epilogue is then a short straight-line loop.  The generic
 // variant (FAST = 0) keeps every edge case.
 template <int KIND, int FAST, int CTA2>
-__device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* tma_a, const CUtensorMap* tma_b,
-                                          const CUtensorMap* tma_d, const CUtensorMap* tma_r, const SmemLayout& L,
+__device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* tma_a, const CUtensorMap* tma_a2,
+                                          const CUtensorMap* tma_b, const CUtensorMap* tma_d, const CUtensorMap* tma_r, const SmemLayout& L,
                                           uint32_t tmem_base, int cta_rank, int worker, int n_workers, PipeState& st) {
     uint8_t* smem = L.smem;
     uint8_t* stg_base = smem + (size_t)p.stages * p.stage_bytes;
@@ -263,6 +266,13 @@ __device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* t
             int tap, cb, ky, kx;
             p.d_c_blocks.divmod(kb0, tap, cb);
             p.d_kw.divmod(tap, ky, kx);
+            // two-plane 3xTF32: segment of the K / channel range and block inside it (kept incrementally)
+            int seg = 0, sblk = p.conv ? cb : kb0;
+            if (p.x3_cb)
+                while (sblk >= p.x3_cb) {
+                    sblk -= p.x3_cb;
+                    seg++;
+                }
             // programmatic dependent launch: the producer is the first to touch the predecessor's output; everything
             // above (tile decode) ran while the predecessor grid was still draining
             if (u == worker) asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -289,20 +299,27 @@ __device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* t
                             else
                                 tma_load_4d_u32(dst, m, fb, c0, c1, c2, c3);
                         };
+                        const CUtensorMap* ma = (p.x3_cb && seg == 0) ? tma_a2 : tma_a;
                         if (p.conv) {
                             const int c0 = cb * p.kelems;
-                            load(sa, tma_a, c0, tc.ox0 * p.sx - p.pl + kx * p.dx, tc.oy0 * p.sy - p.pt + ky * p.dy, tc.b0);
+                            const int ca = p.x3_cb ? sblk * p.kelems : c0;
+                            load(sa, ma, ca, tc.ox0 * p.sx - p.pl + kx * p.dx, tc.oy0 * p.sy - p.pt + ky * p.dy, tc.b0);
                             if (p.pair)
-                                load(sa + A_STAGE_BYTES, tma_a, c0, tc1.ox0 * p.sx - p.pl + kx * p.dx,
+                                load(sa + A_STAGE_BYTES, ma, ca, tc1.ox0 * p.sx - p.pl + kx * p.dx,
                                      tc1.oy0 * p.sy - p.pt + ky * p.dy, tc1.b0);
                             load(sb, tma_b, c0, tc.n0 + b_row0, tap, 0);
                         } else {
                             const int k0 = (kb + a) * p.kelems;
+                            const int ka = p.x3_cb ? sblk * p.kelems : k0;
                             const int az0 = p.a_bcast0 ? 0 : tc.z0, az1 = p.a_bcast1 ? 0 : tc.z1;
-                            load(sa, tma_a, k0, tc.m0, az0, az1);
-                            if (p.pair) load(sa + A_STAGE_BYTES, tma_a, k0, tc1.m0, az0, az1);
+                            load(sa, ma, ka, tc.m0, az0, az1);
+                            if (p.pair) load(sa + A_STAGE_BYTES, ma, ka, tc1.m0, az0, az1);
                             load(sb, tma_b, k0, tc.n0 + b_row0, p.b_bcast0 ? 0 : tc.z0, p.b_bcast1 ? 0 : tc.z1);
                         }
+                    }
+                    if (p.x3_cb && ++sblk == p.x3_cb) {
+                        sblk = 0;
+                        seg = seg == 2 ? 0 : seg + 1;  // (conv: the next filter tap starts over at segment 0)
                     }
                     if (++cb == p.c_blocks) {
                         cb = 0;
@@ -395,6 +412,8 @@ __device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* t
         uint32_t ci = 0;
         uint32_t& rphase = st.rphase;
         float rg_lo = __int_as_float(0x7f800000), rg_hi = __int_as_float(0xff800000);  // output range (e.range)
+        const bool tr = p.trace && blockIdx.x == 0 && warp == 4 && lane == 0;  // (debug trace, RTEN_B200_TRACE_FAST)
+        const int it0 = st.it;
         for (int u = worker; u < p.units_total; u += n_workers, st.it++) {
             int t, ks_u;
             p.d_tiles_total.divmod(u, ks_u, t);
@@ -416,6 +435,7 @@ __device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* t
             };
             if (p.res_tma && p.splitk == 1 && issuer && grp * 32 < p.bn) first_residual();
             mbar_wait(&tmem_full[acc], acc_phase);
+            if (tr && st.it - it0 < 2048) p.trace[4096 + st.it - it0] = clock64();
             tc_fence_after();
             bool owner = true;
             if (p.splitk > 1) {
@@ -616,6 +636,7 @@ __device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* t
                 else
                     mbar_arrive(&tmem_empty[acc]);
             }
+            if (tr && st.it - it0 < 2048) p.trace[6144 + st.it - it0] = clock64();
         }
         if (e.range) range_commit(e.range, rg_lo, rg_hi);
         // shared memory must stay valid until the last bulk store has READ it; the global writes complete on their own
@@ -979,7 +1000,7 @@ template <int KIND, int FAST, int CTA2>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                  const __grid_constant__ CUtensorMap tma_d, const __grid_constant__ CUtensorMap tma_r,
-                 const __grid_constant__ KParams p) {
+                 const __grid_constant__ CUtensorMap tma_a2, const __grid_constant__ KParams p) {
     extern __shared__ uint8_t smem_raw[];
     const SmemLayout L = carve_smem(smem_raw);
     if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[6144 + 1100] = clock64();  // kernel entry
@@ -992,6 +1013,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         tma_prefetch_desc(&tma_b);
         if (p.tma_store) tma_prefetch_desc(&tma_d);
         if (p.res_tma) tma_prefetch_desc(&tma_r);
+        if (p.x3_cb) tma_prefetch_desc(&tma_a2);
     }
     const uint32_t tmem_base = kernel_setup<CTA2>(L);
     // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps
@@ -1001,7 +1023,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[6144 + 1102] = clock64();  // predecessor complete
     PipeState st;
-    run_layer<KIND, FAST, CTA2>(p, &tma_a, &tma_b, &tma_d, &tma_r, L, tmem_base, cta_rank, worker, n_workers, st);
+    run_layer<KIND, FAST, CTA2>(p, &tma_a, &tma_a2, &tma_b, &tma_d, &tma_r, L, tmem_base, cta_rank, worker, n_workers, st);
     if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[6144 + 1103] = clock64();  // control thread done
     kernel_teardown<CTA2>(tmem_base);
     if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[6144 + 1104] = clock64();  // exit
@@ -1045,7 +1067,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_seq_kernel(const __grid_c
     for (int l = 0; l < sp.n; l++) {
         const KParams& p = sp.layer[l];
         if (l + 1 == sp.n) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-        run_layer<KIND, FAST, 0>(p, &sp.maps[l][0], &sp.maps[l][1], &sp.maps[l][2], &sp.maps[l][3], L, tmem_base, 0,
+        run_layer<KIND, FAST, 0>(p, &sp.maps[l][0], &sp.maps[l][0], &sp.maps[l][1], &sp.maps[l][2], &sp.maps[l][3], L, tmem_base, 0,
                                  (int)blockIdx.x, (int)gridDim.x, st);
         if (l + 1 < sp.n) {
             // ---- layer boundary: this CTA's outputs are complete and visible, then wait for every other CTA's

@@ -792,6 +792,41 @@ def check_tf32x3(rt, oracle):
         w = max(w, _conv_case(rt, oracle, ctx, (2, 3, 32, 32), (16, 3, 7, 7), pads=(3, 3, 3, 3), strides=(2, 2), cl=True))   # stem-like
     finally:
         TF32_REL = saved
+    # The two-plane form (A = original tensor for both `hi` segments + a low-part plane; prepacked B split once and
+    # cached) must be BIT-IDENTICAL to the three-segment copies built per call: kind::tf32 ignores the 13 low
+    # mantissa bits, so feeding the raw f32 values is the same as feeding their truncations.
+    import os
+    r = oracle.XorShiftRng(99)
+    n_same = 0
+    for (xs, ws, pads, strides) in [((4, 64, 14, 14), (128, 64, 3, 3), (1, 1, 1, 1), (1, 1)), ((3, 256, 9, 9), (64, 256, 1, 1), (0, 0, 0, 0), (1, 1)),
+                                    ((2, 96, 12, 12), (32, 96, 3, 3), (1, 1, 1, 1), (2, 2))]:
+        x = ctx.to_device(r.f32(xs), channels_last=True)
+        wt = ctx.to_device(r.f32(ws))
+        op = rt.Conv(1, (1, 1), pads, strides, activation=rt.ACT_RELU)
+        pk = op.prepack(ctx, 1, wt)
+        two = op.run(ctx, x, wt, packed_w=pk).numpy()
+        os.environ["RTEN_B200_X3_THREE_PLANES"] = "1"
+        os.environ["RTEN_B200_X3_NO_CACHE"] = "1"
+        try:
+            three = op.run(ctx, x, wt, packed_w=pk).numpy()
+        finally:
+            os.environ.pop("RTEN_B200_X3_THREE_PLANES")
+            os.environ.pop("RTEN_B200_X3_NO_CACHE")
+        assert_bit_exact(two, three, f"3xTF32 conv {xs}x{ws}: two-plane vs three-segment operands")
+        n_same += 1
+    a, b = r.f32((300, 768)), r.f32((768, 320))
+    db = ctx.to_device(b)
+    pk = rt.MatMul().prepack(ctx, 1, db)
+    two = rt.MatMul().run(ctx, ctx.to_device(a), db, packed_b=pk).numpy()
+    os.environ["RTEN_B200_X3_THREE_PLANES"] = "1"
+    os.environ["RTEN_B200_X3_NO_CACHE"] = "1"
+    try:
+        three = rt.MatMul().run(ctx, ctx.to_device(a), db, packed_b=pk).numpy()
+    finally:
+        os.environ.pop("RTEN_B200_X3_THREE_PLANES")
+        os.environ.pop("RTEN_B200_X3_NO_CACHE")
+    assert_bit_exact(two, three, "3xTF32 MatMul 300x768x320: two-plane vs three-segment operands")
+    assert_reference_rule(two, oracle.matmul(a, b), "3xTF32 MatMul 300x768x320 (two-plane)")
     rng = oracle.XorShiftRng(5678)
     spec = graphs.make_resnet50(lambda s: rng.uniform(s))
     x = oracle.XorShiftRng(1234).uniform((2, 3, 224, 224))
@@ -799,7 +834,7 @@ def check_tf32x3(rt, oracle):
     got = graphs.ResNet50Runner(ctx, spec, fuse=True).run(ctx.to_device(x, channels_last=True)).numpy()
     rel = float(np.abs(got - ref).max() / np.abs(ref).max())
     assert rel <= 1e-4, f"ResNet-50 logits in 3xTF32 mode: rel err {rel:.3e}"
-    return f"worst err/bound {w:.3f} (bound 2^-18); ResNet-50 logits rel err {rel:.2e}"
+    return f"worst err/bound {w:.3f} (bound 2^-18); {n_same + 1} two-plane launches bit-identical to three-segment ones; ResNet-50 logits rel err {rel:.2e}"
 
 
 def check_mnist_model(rt, oracle):
