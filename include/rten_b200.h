@@ -254,6 +254,11 @@ typedef struct rten_comm rten_comm;
 rten_status rten_b200_comm_unique_id(void* id_out_128_bytes);
 rten_status rten_b200_comm_create(rten_ctx* ctx, const void* id_128_bytes, int rank, int world_size, rten_comm** out);
 void rten_b200_comm_destroy(rten_comm* comm);
+/* 1: the range exchange runs as one kernel over NVLink peer memory (mailboxes opened through CUDA IPC at comm_create);
+ * 0: the peers' memory could not be opened (or RTEN_B200_NCCL_RANGES=1) and two ncclAllReduce calls are used.  Both are exact. */
+int rten_b200_comm_uses_peer_memory(const rten_comm* comm);
+/* Exchanges that gave up waiting for a peer (~30 s) since comm_create: 0 in a healthy run, -1 if the device cannot be read. */
+int rten_b200_comm_timeouts(const rten_comm* comm);
 
 /* DynamicQuantizeLinear (src/ops/quantize.rs:352-468): y u8, scale f32 scalar, zero_point u8 scalar.
  * comm_or_null (a rten_comm*): when the batch is sharded over ranks, the local (min, max) is all-reduced over the ranks

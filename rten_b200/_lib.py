@@ -95,6 +95,8 @@ _SIGNATURES = {
     "rten_b200_comm_unique_id": (C.c_int, [_vp]),
     "rten_b200_comm_create": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.POINTER(_vp)]),
     "rten_b200_comm_destroy": (None, [_vp]),
+    "rten_b200_comm_uses_peer_memory": (C.c_int, [_vp]),
+    "rten_b200_comm_timeouts": (C.c_int, [_vp]),
     "rten_b200_relu": (C.c_int, [_vp, _TP, _TP]),
     "rten_b200_add": (C.c_int, [_vp, _TP, _TP, _TP]),
     "rten_b200_mul": (C.c_int, [_vp, _TP, _TP, _TP]),

@@ -256,7 +256,7 @@ rten_status conv_core(OpScope& sc, ConvArgs& A, rten_tensor* out) {
 
     // ---- small-channel path (C <= 4, e.g. the RGB stem): NHWC4 zero-padded copy, one 128-byte K block per filter
     //      row holding kw pixels x 4 channels; vertical padding / stride stay in the TMA tile addressing.
-    const bool smallc_ok = !implicit_ok && A.kind == 0 && ctx->f32_mode != RTEN_F32_TF32X3 && groups == 1 && Cg <= 4 && kw * 4 <= 32 && dil[1] == 1 &&
+    const bool smallc_ok = !implicit_ok && A.kind == 0 && groups == 1 && Cg <= 4 && kw * 4 <= 32 && dil[1] == 1 &&
                            (int64_t)B * OH * OW > 0 && !getenv("RTEN_B200_NO_SMALLC");
     if (smallc_ok) {
         const int64_t Wp = (OW - 1) * strides[1] + 8;  // every window of 8 pixels stays inside the padded row
@@ -297,6 +297,15 @@ rten_status conv_core(OpScope& sc, ConvArgs& A, rten_tensor* out) {
         L.a.strides[1] = strides[1] * 4;
         L.a.strides[2] = Wp * 4;
         L.a.strides[3] = H * Wp * 4;
+        if (ctx->f32_mode == RTEN_F32_TF32X3 && !getenv("RTEN_B200_X3_THREE_PLANES")) {
+            // 3xTF32: the low parts of the padded copy, once (the window view below overlaps itself 8 / stride times)
+            float* xlo = nullptr;
+            const long long n = (long long)B * H * Wp * 4;
+            RTB_TRY(temp_alloc(ctx, (size_t)n * 4, (void**)&xlo));
+            const long long fd[4] = {n, 1, 1, 1}, fs[4] = {1, n, n, n};
+            RTB_TRY(launch_tf32x3_split(ctx, xp, xlo, fd, fs, n, 2));
+            L.a_lo_base = xlo;
+        }
         L.b.base = wsm;
         L.b.dims[0] = 32;
         L.b.dims[1] = O;

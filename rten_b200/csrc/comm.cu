@@ -1,9 +1,19 @@
 // Cross-rank exchange for the batch-sharded int8 path: when a batch is split over GPUs, every rank must
 // quantise with the min / max of the WHOLE tensor to stay bit-identical to the unsharded reference
 // (src/ops/quantize.rs:352-434 computes one range per tensor).  That is an all-reduce of two numbers per
-// DynamicQuantizeLinear.  NCCL is resolved at run time (dlopen of libnccl.so.2 -- the copy already loaded in the process if
-// there is one), so the library itself keeps no link-time dependency on it.
+// DynamicQuantizeLinear -- 53 of them per ResNet-50 step, each on the critical path.
+//
+// Default path: ONE small kernel per exchange over NVLink peer memory.  Every rank owns a mailbox (cudaMalloc, opened
+// by the peers through CUDA IPC at comm_create); the kernel stores (epoch, min) and (epoch, max) as two 64-bit words
+// into its slot of every peer's mailbox, spins until every slot of its own mailbox carries the current epoch, and
+// reduces.  No fences are needed (each word is self-validating), slots are double-buffered by epoch parity (a rank
+// can be at most one exchange ahead of a peer), and the epoch lives in device memory so that CUDA-graph replays advance
+// it.  Measured against two ncclAllReduce calls of one int each (the fallback, RTEN_B200_NCCL_RANGES=1): DESIGN.md 5.
+// NCCL is resolved at run time (dlopen of libnccl.so.2 -- the copy already loaded in the process if there is one), so
+// the library itself keeps no link-time dependency on it; it also carries the IPC handles at start-up.
 #include <dlfcn.h>
+
+#include <vector>
 
 #include "common.h"
 
@@ -19,6 +29,7 @@ struct NcclApi {
     int (*CommInitRank)(void**, int, Id128, int) = nullptr;
     int (*CommDestroy)(void*) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
 };
 
@@ -36,21 +47,93 @@ bool load_nccl() {
     a.CommInitRank = reinterpret_cast<decltype(a.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
     a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
     a.AllReduce = reinterpret_cast<decltype(a.AllReduce)>(dlsym(h, "ncclAllReduce"));
+    a.AllGather = reinterpret_cast<decltype(a.AllGather)>(dlsym(h, "ncclAllGather"));
     a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
     if (!a.GetUniqueId || !a.CommInitRank || !a.CommDestroy || !a.AllReduce) return false;
     g_nccl = a;
     return true;
 }
 
+constexpr int kNcclInt8 = 0;   // ncclInt8 / ncclChar
 constexpr int kNcclInt32 = 2;  // ncclInt32
 constexpr int kNcclMax = 2;    // ncclMax
 constexpr int kNcclMin = 3;    // ncclMin
+
+constexpr int MAX_PEERS = 16;
+
+// one rank's mailbox: slot[parity][sender] = {(epoch << 32) | min, (epoch << 32) | max}
+struct Mailbox {
+    unsigned long long slot[2][MAX_PEERS][2];
+    unsigned epoch;     // exchanges completed by the owner (advanced by the kernel)
+    unsigned timeouts;  // exchanges that gave up waiting for a peer (reported by the next host call)
+};
+
+struct PeerTable {
+    Mailbox* box[MAX_PEERS];  // box[rank] = the local mailbox
+};
+
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// mm[0] / mm[1]: ordered-int encodings of the local min / max (integer order == float order)
+__global__ void __launch_bounds__(32) peer_minmax_kernel(int* mm, const PeerTable peers, int rank, int world) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const int lane = threadIdx.x;
+    Mailbox* mine = peers.box[rank];
+    const unsigned e = mine->epoch + 1;
+    const unsigned long long tag = (unsigned long long)e << 32;
+    int lo = 0x7fffffff, hi = (int)0x80000000;
+    if (lane < world) {
+        const unsigned long long w_lo = tag | (unsigned)mm[0], w_hi = tag | (unsigned)mm[1];
+        unsigned long long* dst = peers.box[lane]->slot[e & 1][rank];
+        st_relaxed_sys_u64(dst, w_lo);
+        st_relaxed_sys_u64(dst + 1, w_hi);
+        const unsigned long long* src = mine->slot[e & 1][lane];
+        const long long t0 = clock64();
+        unsigned long long a, b;
+        bool ok = true;
+        do {
+            a = ld_relaxed_sys_u64(src);
+            b = ld_relaxed_sys_u64(src + 1);
+            if ((a >> 32) == e && (b >> 32) == e) break;
+            if (clock64() - t0 > 60000000000LL) {  // ~30 s: a peer never arrived -- do not hang the GPU for ever, flag the error
+                ok = false;
+                break;
+            }
+        } while (true);
+        if (ok) {
+            lo = (int)(unsigned)a;
+            hi = (int)(unsigned)b;
+        } else {
+            atomicAdd(&mine->timeouts, 1u);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if (lane == 0) {
+        mm[0] = lo;
+        mm[1] = hi;
+        mine->epoch = e;
+    }
+}
 
 }  // namespace
 
 struct rten_comm {
     void* nccl = nullptr;
     int rank = 0, world = 1;
+    Mailbox* box = nullptr;       // local mailbox (cudaMalloc)
+    PeerTable peers = {};         // peers' mailboxes opened through CUDA IPC (peer_ok)
+    bool peer_ok = false;
 };
 
 namespace rtb {
@@ -60,6 +143,22 @@ namespace rtb {
 rten_status comm_allreduce_minmax(rten_ctx* ctx, rten_comm* comm, int* mm) {
     if (!comm || comm->world <= 1) return RTEN_OK;
     cudaStream_t s = launch_stream(ctx);
+    if (comm->peer_ok) {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(1);
+        cfg.blockDim = dim3(32);
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = getenv("RTEN_B200_NO_PDL") ? 0 : 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, peer_minmax_kernel, mm, comm->peers, comm->rank, comm->world);
+        if (e != cudaSuccess) return fail_cuda(ctx, e, "peer min/max exchange launch");
+        count_launch(ctx);
+        return RTEN_OK;
+    }
     int r = g_nccl.AllReduce(mm, mm, 1, kNcclInt32, kNcclMin, comm->nccl, s);
     if (r == 0) r = g_nccl.AllReduce(mm + 1, mm + 1, 1, kNcclInt32, kNcclMax, comm->nccl, s);
     if (r != 0) {
@@ -71,6 +170,70 @@ rten_status comm_allreduce_minmax(rten_ctx* ctx, rten_comm* comm, int* mm) {
 }
 
 }  // namespace rtb
+
+// Peer mailboxes: allocate, exchange the IPC handles through NCCL, open the peers'.  Any failure leaves the communicator
+// on the NCCL path (peer_ok = false) -- both are exact, the choice only changes the latency.
+static void setup_peer_mailboxes(rten_ctx* ctx, rten_comm* c) {
+    if (getenv("RTEN_B200_NCCL_RANGES") || c->world > MAX_PEERS || !g_nccl.AllGather) return;
+    if (cudaMalloc(&c->box, sizeof(Mailbox)) != cudaSuccess) {
+        cudaGetLastError();
+        c->box = nullptr;
+        return;
+    }
+    cudaMemset(c->box, 0, sizeof(Mailbox));
+    cudaIpcMemHandle_t mine;
+    int ok = cudaIpcGetMemHandle(&mine, c->box) == cudaSuccess ? 1 : 0;
+    // gather {handle, ok} of every rank (device staging buffers: NCCL moves device memory)
+    struct Entry {
+        cudaIpcMemHandle_t h;
+        int ok;
+        int pad[3];
+    };
+    Entry e_host;
+    memset(&e_host, 0, sizeof(e_host));
+    e_host.h = mine;
+    e_host.ok = ok;
+    Entry *d_send = nullptr, *d_recv = nullptr;
+    std::vector<Entry> all(c->world);
+    bool good = cudaMalloc(&d_send, sizeof(Entry)) == cudaSuccess && cudaMalloc(&d_recv, sizeof(Entry) * c->world) == cudaSuccess;
+    if (good) {
+        cudaMemcpy(d_send, &e_host, sizeof(Entry), cudaMemcpyHostToDevice);
+        cudaStream_t s = ctx->stream;
+        good = g_nccl.AllGather(d_send, d_recv, sizeof(Entry), kNcclInt8, c->nccl, s) == 0 && cudaStreamSynchronize(s) == cudaSuccess;
+        if (good) cudaMemcpy(all.data(), d_recv, sizeof(Entry) * c->world, cudaMemcpyDeviceToHost);
+    }
+    if (d_send) cudaFree(d_send);
+    if (d_recv) cudaFree(d_recv);
+    // every rank must take the same decision: all handles valid, and every open succeeds (second round below)
+    int opened = good ? 1 : 0;
+    for (int r = 0; r < c->world && opened; r++) opened = all[r].ok;
+    for (int r = 0; r < c->world && opened; r++) {
+        if (r == c->rank) {
+            c->peers.box[r] = c->box;
+            continue;
+        }
+        void* p = nullptr;
+        if (cudaIpcOpenMemHandle(&p, all[r].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaGetLastError();
+            opened = 0;
+            break;
+        }
+        c->peers.box[r] = reinterpret_cast<Mailbox*>(p);
+    }
+    // agree: min over ranks of `opened` (one int all-reduce; the last NCCL call of the set-up)
+    int* d_flag = nullptr;
+    if (cudaMalloc(&d_flag, 4) == cudaSuccess) {
+        cudaMemcpy(d_flag, &opened, 4, cudaMemcpyHostToDevice);
+        if (g_nccl.AllReduce(d_flag, d_flag, 1, kNcclInt32, kNcclMin, c->nccl, ctx->stream) == 0 && cudaStreamSynchronize(ctx->stream) == cudaSuccess)
+            cudaMemcpy(&opened, d_flag, 4, cudaMemcpyDeviceToHost);
+        else
+            opened = 0;
+        cudaFree(d_flag);
+    } else {
+        opened = 0;
+    }
+    c->peer_ok = opened != 0;
+}
 
 extern "C" {
 
@@ -96,12 +259,27 @@ rten_status rten_b200_comm_create(rten_ctx* ctx, const void* id128, int rank, in
         delete c;
         return RTEN_ERR_NCCL;
     }
+    setup_peer_mailboxes(ctx, c);
     *out = c;
     return RTEN_OK;
 }
 
+int rten_b200_comm_uses_peer_memory(const rten_comm* comm) { return comm && comm->peer_ok ? 1 : 0; }
+
+/* Exchanges that timed out waiting for a peer since comm_create (0 in a healthy run): host read of the local mailbox. */
+int rten_b200_comm_timeouts(const rten_comm* comm) {
+    if (!comm || !comm->box) return 0;
+    unsigned v = 0;
+    if (cudaMemcpy(&v, &comm->box->timeouts, 4, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return (int)v;
+}
+
 void rten_b200_comm_destroy(rten_comm* comm) {
     if (!comm) return;
+    if (comm->peer_ok)
+        for (int r = 0; r < comm->world; r++)
+            if (r != comm->rank && comm->peers.box[r]) cudaIpcCloseMemHandle(comm->peers.box[r]);
+    if (comm->box) cudaFree(comm->box);
     if (comm->nccl && g_nccl.CommDestroy) g_nccl.CommDestroy(comm->nccl);
     delete comm;
 }

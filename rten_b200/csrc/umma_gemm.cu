@@ -150,7 +150,7 @@ struct Prepared {
 };
 
 constexpr int SK_CNT_INTS = 1 << 16;
-static int smem_budget_for(int n_stg) { return 227 * 1024 - 2048 - n_stg * STG_BYTES; }
+static int smem_budget_for(int n_stg) { return 227 * 1024 - 3072 - n_stg * STG_BYTES; }  // 1 KB alignment slack, 1 KB barriers, 1 KB bias
 
 struct PlanShape {
     long long tiles_n, units_m, tiles, units;
@@ -234,6 +234,16 @@ static void enumerate_plans(const Prepared& q, int num_sms, std::vector<std::pai
                     const int kb_per = (p.k_blocks + sk - 1) / sk;
                     pl.nbuf = pl.acc1 ? 1 : ((q.res_tma || kb_per < 24) ? 2 : 1);
                     PlanShape ps;
+                    if (pl.nbuf == 2 && !getenv("RTEN_B200_NO_NBUF3")) {
+                        // A third staging buffer per group takes the wait for the previous store's shared-memory read (a
+                        // 16 KB bulk store drains at the SM's ~32 B/clk write port: ~900 clk) and, with a residual, the
+                        // late request of the next residual tile off the chunk's critical path -- as long as the operand
+                        // ring keeps three stages (or loses none)
+                        PlanShape ps2;
+                        const bool ok2 = plan_shape(q, pl, ps2);
+                        pl.nbuf = 3;
+                        if (!plan_shape(q, pl, ps) || (ps.stages < 3 && !(ok2 && ps.stages == ps2.stages))) pl.nbuf = 2;
+                    }
                     if (!plan_shape(q, pl, ps)) continue;
                     if (sk > 1 && ps.tiles * (cta2 + 1) >= 2 * num_sms) continue;  // enough parallelism without splitting K
                     if (ps.stages < 3 && !(katoms == 1 && ps.stages == 2)) continue;
@@ -378,6 +388,7 @@ static rten_status ensure_splitk_counters(rten_ctx* ctx) {
 }
 
 struct PendingLaunch {
+    bool plain = false;  // f32 launch that qualifies for the plain epilogue (kernel variant 3; a subset of variant 1)
     KParams p;
     CUtensorMap maps[5];  // a, b, d, residual, a2 (two-plane 3xTF32: low parts of A)
     size_t smem_bytes;
@@ -431,6 +442,9 @@ static rten_status launch_single(rten_ctx* ctx, int cls, const PendingLaunch& pl
         return cudaLaunchKernelEx(&cfg, kern, pl.maps[0], pl.maps[1], pl.maps[2], pl.maps[3], pl.maps[4], p);
     };
     cudaError_t e;
+    if (pl.plain && cls == 1) {
+        e = p.cta2 ? launch(umma_gemm_kernel<0, 3, 1>) : launch(umma_gemm_kernel<0, 3, 0>);
+    } else
     switch (cls * 2 + (p.cta2 ? 1 : 0)) {
         case 0: e = launch(umma_gemm_kernel<0, 0, 0>); break;
         case 1: e = launch(umma_gemm_kernel<0, 0, 1>); break;
@@ -575,7 +589,7 @@ static rten_status launch_plan(rten_ctx* ctx, const GemmLaunch& L, const Prepare
         fprintf(stderr, "[umma_gemm] kind=%d conv=%d M=%d N=%d K=%d kb=%d tiles_m=%d bn=%d pair=%d ksplit=%d katoms=%d splitk=%d acc1=%d cta2=%d units=%d stages=%d tma_store=%d res_tma=%d nbuf=%d box=%dx%dx%d\n",
                 L.kind, L.conv, L.M, L.N, L.K, p.k_blocks, p.tiles_m, p.bn, p.pair, p.ksplit, p.katoms, p.splitk, p.acc1, p.cta2,
                 p.units_total, p.stages, p.tma_store, p.res_tma, p.nbuf, p.tw, p.th, p.tb);
-    const size_t smem_bytes = (size_t)p.stages * p.stage_bytes + n_stg * STG_BYTES + 1024 /*align*/ + 1024 /*barriers*/;
+    const size_t smem_bytes = (size_t)p.stages * p.stage_bytes + n_stg * STG_BYTES + 1024 /*align*/ + 1024 /*barriers*/ + 1024 /*bias*/;
     // specialised epilogue when every chunk qualifies for the register fast path
     const EpilogueDesc& ee = L.epi;
     bool fastk = p.tma_store && (L.N % 32) == 0 && (!ctx->trace || getenv("RTEN_B200_TRACE_FAST")) && !getenv("RTEN_B200_NO_FAST");
@@ -591,6 +605,8 @@ static rten_status launch_plan(rten_ctx* ctx, const GemmLaunch& L, const Prepare
     // the generic epilogue takes a TMA-staged residual only on its register path (f32, act <= Relu)
     if (!fastk && (L.kind == 1 || ee.act > 1)) p.res_tma = 0;
     PendingLaunch pend;
+    pend.plain = fastk && L.kind == 0 && ee.alpha == 1.0f && ee.act <= 1 && !ee.range && p.splitk == 1 &&
+                 (ee.r == nullptr || (p.res_tma && ee.r_scale == 1.0f)) && !getenv("RTEN_B200_NO_PLAIN");
     pend.p = p;
     pend.maps[0] = map_a;
     pend.maps[1] = map_b;
@@ -708,7 +724,11 @@ static rten_status launch_tf32x3(rten_ctx* ctx, const GemmLaunch& L0) {
     }
     // ---- A
     const bool two_plane = d0 % 32 == 0 && tma_compatible(L0.a, 4, 4) && !getenv("RTEN_B200_X3_THREE_PLANES");
-    if (two_plane) {
+    if (two_plane && L0.a_lo_base) {
+        L.a_lo = L0.a;
+        L.a_lo.base = L0.a_lo_base;
+        L.x3_cb = (int)(d0 / 32);
+    } else if (two_plane) {
         RTB_TRY(split(L0.a, L.a_lo, 2, nullptr));
         L.x3_cb = (int)(d0 / 32);
     } else {
@@ -718,6 +738,7 @@ static rten_status launch_tf32x3(rten_ctx* ctx, const GemmLaunch& L0) {
         L.g.C = (int)(3 * d0p);
     L.K = L.conv ? (int)(L0.K / d0 * 3 * d0p) : (int)(3 * d0p);
     L.b_x3_slot = nullptr;
+    L.a_lo_base = nullptr;
     const int saved = ctx->f32_mode;
     ctx->f32_mode = RTEN_F32_TF32;
     const rten_status st = launch_umma_gemm(ctx, L);

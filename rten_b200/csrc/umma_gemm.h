@@ -76,6 +76,9 @@ struct GemmLaunch {
     // 3xTF32 (RTEN_F32_TF32X3), set by the caller that owns a constant B: slot caching the split copy of `b`
     // ([hi | lo | hi] along K) across launches -- weights are split once, not per call (owned by the rten_packed)
     void** b_x3_slot = nullptr;
+    // optional: low parts of A already computed by the caller, laid out exactly like `a` (same dims / strides) -- the
+    // small-channel stem splits its padded NHWC4 copy once instead of the 8x larger overlapping window view
+    const void* a_lo_base = nullptr;
     // internal (launch_tf32x3 -> kernel): two-plane A -- `a` is the original tensor (segments 1, 2), `a_lo` its low parts
     int x3_cb = 0;
     OperandDesc a_lo;

@@ -121,6 +121,15 @@ __device__ __forceinline__ TileCoord decode_tile(const KParams& p, int t, int su
     return c;
 }
 
+// (a0, a1) += (b0, b1): one packed FADD2, each half rounded to nearest like a scalar add
+__device__ __forceinline__ void add_f32x2(uint32_t& a0, uint32_t& a1, float b0, float b1) {
+    unsigned long long a, b, d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "r"(a0), "r"(a1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(a0), "=r"(a1) : "l"(d));
+}
+
 // cp.async.bulk.wait_group.read takes an immediate: leave at most `n` of this thread's bulk stores un-read
 __device__ __forceinline__ void bulk_wait_read(int n) {
     switch (n) {
@@ -224,6 +233,7 @@ struct SmemLayout {
     uint8_t* smem;  // operand stages (1024-B aligned), staging buffers behind them
     uint64_t *full_bar, *empty_bar, *tmem_full, *tmem_empty, *res_bar;
     int* sk_flag;
+    float* bias;
 };
 
 // One launch worth of work (all roles).  FAST = the launch satisfies, for EVERY chunk, the conditions of the register
@@ -398,6 +408,167 @@ __device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* t
                 if (++stage == p.stages) stage = 0;
             }
         }
+    } else if (FAST == 3 && warp >= 4) {
+        // ===================== epilogue (plain f32) =====================
+        // The common float case -- alpha = 1, optional column bias, optional residual (r_scale = 1, TMA-staged), act in
+        // {none, Relu}, no split-K / range -- as the shortest instruction stream the result
+        // allows: packed adds (add.rn.f32x2: the same IEEE roundings as two scalar adds), the bias of the unit's
+        // columns read from shared memory (loaded while the main loop runs) instead of eight dependent global loads
+        // behind the accumulator wait.   x = relu((acc + residual) + bias), rounded after each add like the generic path.
+        const EpilogueDesc& e = p.epi;
+        const int q = warp & 3;
+        const int grp = (warp - 4) >> 2;
+        const int r = q * 32 + lane;
+        const int sw = r & 7;
+        uint8_t* stg0 = stg_base + grp * nbuf * STG_BYTES;
+        const bool issuer = (q == 0 && lane == 0);
+        const bool has_bias = e.bias_kind == 1;
+        const bool do_relu = e.act == 1;
+        float* bias_s = L.bias + grp * 128;  // chunk k of this group (columns grp*32 + 64k ..) -> bias_s[32k .. 32k + 32)
+        uint32_t ci = 0;
+        uint32_t& rphase = st.rphase;
+        const bool tr = p.trace && blockIdx.x == 0 && warp == 4 && lane == 0;  // (debug trace, RTEN_B200_TRACE_FAST)
+        const int it0 = st.it;
+        for (int u = worker; u < p.units_total; u += n_workers, st.it++) {
+            const int t = u;  // (no split-K)
+            const int acc = p.acc1 ? 0 : (st.it & 1);
+            const uint32_t acc_phase = (st.acc >> acc) & 1;
+            st.acc ^= 1u << acc;
+            const TileCoord tc0 = decode_tile(p, t, 0, cta_rank);
+            if (p.res_tma && issuer && grp * 32 < p.bn) {  // residual of the first chunk: independent of the accumulator
+                const int b0 = ci % nbuf;
+                bulk_wait_read(nbuf - 1);
+                uint64_t* rb = &res_bar[grp * 4 + b0];
+                mbar_expect_tx(rb, p.res_tx_bytes);
+                if (p.conv)
+                    tma_load_4d(stg0 + b0 * STG_BYTES, tma_r, rb, tc0.n0 + grp * 32, tc0.ox0, tc0.oy0, tc0.b0);
+                else
+                    tma_load_4d(stg0 + b0 * STG_BYTES, tma_r, rb, tc0.n0 + grp * 32, tc0.m0, tc0.z0, tc0.z1);
+            }
+            float bv = 0.0f;
+            if (has_bias) {  // thread i of the group: column (i / 32) * 64 + grp * 32 + i % 32 of the tile
+                const int c = (r >> 5) * 64 + grp * 32 + (r & 31);
+                if (c < p.bn && tc0.n0 + c < p.N) bv = __ldg(e.bias + tc0.n0 + c);
+            }
+            mbar_wait(&tmem_full[acc], acc_phase);
+            if (tr && st.it - it0 < 2048) p.trace[4096 + st.it - it0] = clock64();
+            tc_fence_after();
+            // (the previous unit's readers of bias_s are past their last chunk barrier: every thread arrives there after its math)
+            bias_s[r] = bv;
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+            for (int sub = 0; sub <= p.pair; sub++) {
+                const TileCoord tc = decode_tile(p, t, sub, cta_rank);
+                const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_STRIDE + sub * p.bn;
+                int k = 0;
+                for (int c0 = grp * 32; c0 < p.bn; c0 += 64, k++) {
+                    uint32_t v[32];
+                    long long tp0 = 0;
+                    if (tr) tp0 = clock64();
+#define RTB_PLAIN_PHASE(i)                                \
+    if (tr) {                                             \
+        const long long tp1 = clock64();                  \
+        p.trace[6144 + 1024 + (i)] += tp1 - tp0;          \
+        tp0 = tp1;                                        \
+    }
+                    tmem_ld_32x32(t_row + c0, v);
+                    const int nbase = tc.n0 + c0;
+                    const int bcur = ci % nbuf;
+                    uint8_t* stg = stg0 + bcur * STG_BYTES;
+                    uint8_t* rowp = stg + r * 128;
+                    if (p.res_tma && issuer) {  // prefetch the next chunk's residual of this unit into the next ring slot
+                        int nsub = sub, nc0 = c0 + 64;
+                        if (nc0 >= p.bn) {
+                            nsub = sub + 1;
+                            nc0 = grp * 32;
+                        }
+                        if (nsub <= p.pair && nc0 < p.bn) {
+                            const TileCoord tn = decode_tile(p, t, nsub, cta_rank);
+                            const int bnext = (ci + 1) % nbuf;
+                            bulk_wait_read(nbuf - 2);
+                            uint64_t* rb = &res_bar[grp * 4 + bnext];
+                            mbar_expect_tx(rb, p.res_tx_bytes);
+                            if (p.conv)
+                                tma_load_4d(stg0 + bnext * STG_BYTES, tma_r, rb, tn.n0 + nc0, tn.ox0, tn.oy0, tn.b0);
+                            else
+                                tma_load_4d(stg0 + bnext * STG_BYTES, tma_r, rb, tn.n0 + nc0, tn.m0, tn.z0, tn.z1);
+                        }
+                    }
+                    RTB_PLAIN_PHASE(0)
+                    if (p.ksplit) {  // even / odd K blocks accumulated separately (KParams::ksplit): add the second accumulator
+                        uint32_t w0[16], w1[16];
+                        tmem_ld_32x16(t_row + p.bn + c0, w0);
+                        tmem_ld_wait();
+                        tmem_ld_32x16(t_row + p.bn + c0 + 16, w1);
+#pragma unroll
+                        for (int j = 0; j < 16; j += 2) add_f32x2(v[j], v[j + 1], __uint_as_float(w0[j]), __uint_as_float(w0[j + 1]));
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; j += 2) add_f32x2(v[16 + j], v[17 + j], __uint_as_float(w1[j]), __uint_as_float(w1[j + 1]));
+                    } else {
+                        tmem_ld_wait();
+                    }
+                    RTB_PLAIN_PHASE(1)
+                    if (p.res_tma) {
+                        mbar_wait(&res_bar[grp * 4 + bcur], (rphase >> bcur) & 1);
+                        rphase ^= 1u << bcur;
+                    }
+                    RTB_PLAIN_PHASE(2)
+                    if (nbase < p.N) {  // (a tile may overhang N by whole chunks: the TMA store clips them)
+                        const float4* bq = reinterpret_cast<const float4*>(bias_s + 32 * k);
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            if (p.res_tma) {
+                                const float4 rr = *reinterpret_cast<const float4*>(rowp + (((j >> 2) ^ sw) << 4));
+                                add_f32x2(v[j], v[j + 1], rr.x, rr.y);
+                                add_f32x2(v[j + 2], v[j + 3], rr.z, rr.w);
+                            }
+                            const float4 bb = bq[j >> 2];  // (zeros without a bias: x + 0 keeps the generic path's -0 -> +0)
+                            add_f32x2(v[j], v[j + 1], bb.x, bb.y);
+                            add_f32x2(v[j + 2], v[j + 3], bb.z, bb.w);
+                            if (do_relu) {
+#pragma unroll
+                                for (int w = 0; w < 4; w++) v[j + w] = __float_as_uint(fmaxf(__uint_as_float(v[j + w]), 0.0f));
+                            }
+                        }
+                    }
+                    RTB_PLAIN_PHASE(3)
+                    if (nbuf == 1) {  // single staging buffer: the previous store must have been read before it is rewritten
+                        if (issuer) bulk_wait_read(0);
+                        asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; j++)
+                        *reinterpret_cast<uint4*>(rowp + ((j ^ sw) << 4)) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    RTB_PLAIN_PHASE(4)
+                    if (issuer && !p.res_tma && nbuf > 1) bulk_wait_read(nbuf - 2);
+                    RTB_PLAIN_PHASE(5)
+                    fence_proxy_async();
+                    asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+                    RTB_PLAIN_PHASE(6)
+                    if (issuer) {
+                        if (p.conv)
+                            tma_store_4d(tma_d, stg, nbase, tc.ox0, tc.oy0, tc.b0);
+                        else
+                            tma_store_4d(tma_d, stg, nbase, tc.m0, tc.z0, tc.z1);
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                    RTB_PLAIN_PHASE(7)
+                    if (tr) p.trace[6144 + 1024 + 8] += 1;
+#undef RTB_PLAIN_PHASE
+                    ci++;
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (CTA2)
+                    mbar_arrive_cluster(smem_u32(&tmem_empty[acc]) & PEER_BIT_MASK);  // the leader's MMA warp waits on it
+                else
+                    mbar_arrive(&tmem_empty[acc]);
+            }
+            if (tr && st.it - it0 < 2048) p.trace[6144 + st.it - it0] = clock64();
+        }
+        if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     } else if (FAST && warp >= 4) {
         // ===================== epilogue (specialised) =====================
         const EpilogueDesc& e = p.epi;
@@ -470,6 +641,14 @@ __device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* t
                 }
                 for (int c0 = grp * 32; c0 < p.bn; c0 += 64) {
                     uint32_t v[32];
+                    long long tp0 = 0;
+                    if (tr) tp0 = clock64();
+#define RTB_FAST_PHASE(i)                                 \
+    if (tr) {                                             \
+        const long long tp1 = clock64();                  \
+        p.trace[6144 + 1024 + (i)] += tp1 - tp0;          \
+        tp0 = tp1;                                        \
+    }
                     if (p.splitk > 1)
                         splitk_sum<KIND>(p, CTA2 ? 2 * t + cta_rank : t, sub, c0, r, v);
                     else
@@ -496,6 +675,7 @@ __device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* t
                                 tma_load_4d(stg0 + bnext * STG_BYTES, tma_r, rb, tn.n0 + nc0, tn.m0, tn.z0, tn.z1);
                         }
                     }
+                    RTB_FAST_PHASE(0)  // next residual requested (incl. waiting for the slot's previous store)
                     tmem_ld_wait();
                     if (p.ksplit) {
 #pragma unroll
@@ -512,10 +692,12 @@ __device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* t
                             }
                         }
                     }
+                    RTB_FAST_PHASE(1)  // accumulator in registers
                     if (p.res_tma) {
                         mbar_wait(&res_bar[grp * 4 + bcur], (rphase >> bcur) & 1);
                         rphase ^= 1u << bcur;
                     }
+                    RTB_FAST_PHASE(2)  // residual landed
                     // a tile may overhang N (N % bn != 0): its last 32-column chunks are then entirely out of range -- the
                     // TMA store clips them, and neither the column vectors (bias, sums, scales) nor the range may touch them
                     const bool col_ok = nbase < p.N;
@@ -608,6 +790,7 @@ __device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* t
                             rg_hi = fmaxf(rg_hi, __uint_as_float(v[j]));
                         }
                     }
+                    RTB_FAST_PHASE(3)  // math
                     if (nbuf == 1) {  // single staging buffer: the previous store must have been read before it is rewritten
                         if (issuer) bulk_wait_read(0);
                         asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
@@ -615,9 +798,12 @@ __device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* t
 #pragma unroll
                     for (int j = 0; j < 8; j++)
                         *reinterpret_cast<uint4*>(rowp + ((j ^ sw) << 4)) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    RTB_FAST_PHASE(4)  // staged in shared memory
                     if (issuer && !p.res_tma && nbuf > 1) bulk_wait_read(nbuf - 2);
+                    RTB_FAST_PHASE(5)  // previous store's shared-memory read finished
                     fence_proxy_async();
                     asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+                    RTB_FAST_PHASE(6)  // fence + group barrier
                     if (issuer) {
                         if (p.conv)
                             tma_store_4d(tma_d, stg, nbase, tc.ox0, tc.oy0, tc.b0);
@@ -625,6 +811,9 @@ __device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* t
                             tma_store_4d(tma_d, stg, nbase, tc.m0, tc.z0, tc.z1);
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
+                    RTB_FAST_PHASE(7)  // store issued
+                    if (tr) p.trace[6144 + 1024 + 8] += 1;
+#undef RTB_FAST_PHASE
                     ci++;
                 }
             }
@@ -929,7 +1118,8 @@ __device__ __forceinline__ SmemLayout carve_smem(uint8_t* smem_raw) {
     L.tmem_empty = L.tmem_full + 2;
     L.res_bar = L.tmem_empty + 2;  // [group][buffer], up to 4 buffers per group
     L.sk_flag = reinterpret_cast<int*>(L.res_bar + 8) + 2;  // [group]; the two ints before it hold the TMEM base
-    L.smem = base + 1024;
+    L.bias = reinterpret_cast<float*>(base + 1024);  // [group][128]: the plain epilogue's column bias of the current unit
+    L.smem = base + 2048;
     return L;
 }
 

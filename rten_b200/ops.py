@@ -617,6 +617,14 @@ class Comm:
             raise OpError(st, "libnccl.so.2 could not be loaded")
         return buf.raw
 
+    @property
+    def uses_peer_memory(self) -> bool:
+        """True: quantisation ranges travel through NVLink peer mailboxes (one kernel per exchange); False: NCCL."""
+        return bool(self.ctx.lib.rten_b200_comm_uses_peer_memory(self.handle))
+
+    def timeouts(self) -> int:
+        return int(self.ctx.lib.rten_b200_comm_timeouts(self.handle))
+
     def close(self):
         if getattr(self, "handle", None):
             self.ctx.lib.rten_b200_comm_destroy(self.handle)

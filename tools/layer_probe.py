@@ -78,6 +78,7 @@ def trace(run):
     ctx.check(ctx.lib.rten_b200_debug_trace(ctx.handle, 0, buf))
     t = np.frombuffer(buf, dtype=np.int64).reshape(4, 2048).copy()
     marks = t[3][1100:1105].copy()
+    ph = t[3][1024:1033].copy()
     t[3][680:] = 0
     prod, mma, e0, e1 = (r[r > 0] for r in t)
     if not len(mma) or marks[0] <= 0:
@@ -89,6 +90,9 @@ def trace(run):
          f"epi dur med {np.median(e1[:n] - e0[:n]) if n else 0:.0f} | last epi end {e1.max() - m0 if n else -1} exit {marks[4] - m0}")
     if n > 1:
         s += f" | tile interval {np.diff(e0)[:4].tolist()}"
+    if ph[8] > 0:
+        names = ["res-prefetch", "tmem_ld", "res-wait", "math", "st.shared", "wait-prev-store", "fence+bar", "store-issue"]
+        s += "\n   epilogue phases (clk per 32-col chunk, warp 4 lane 0): " + ", ".join(f"{nm} {ph[i] / ph[8]:.0f}" for i, nm in enumerate(names)) + f"  ({ph[8]} chunks)"
     return s
 
 
