@@ -750,7 +750,7 @@ rten_status launch_umma_gemm(rten_ctx* ctx, const GemmLaunch& L) {
     if (L.kind == 0 && ctx->f32_mode == RTEN_F32_TF32X3) return launch_tf32x3(ctx, L);
     // stride-1 windows (the 3x3 layers): the halo-reuse kernel moves the activations into shared memory once per channel
     // block instead of once per filter tap (umma_halo.cu); everything it does not cover falls through
-    if (L.conv && L.kind == 0 && L.g.kh * L.g.kw > 1 && !ctx->trace && !L.x3_cb) {
+    if (L.conv && L.kind == 0 && L.g.kh * L.g.kw > 1 && (!ctx->trace || getenv("RTEN_B200_TRACE_FAST")) && !L.x3_cb) {
         const rten_status hs = launch_umma_halo_conv(ctx, L);
         if (hs != RTEN_ERR_UNSUPPORTED_VALUE) return hs;
     }
@@ -763,6 +763,10 @@ rten_status launch_umma_gemm(rten_ctx* ctx, const GemmLaunch& L) {
         auto hit = ctx->tune_cache.find(tune_key(L, q));
         if (hit != ctx->tune_cache.end()) {
             PlanShape ps;
+            if (hit->second[0] < 0) {  // the halo-reuse kernel measured faster: {-1, bn, T}
+                const rten_status hs = launch_umma_halo_conv(ctx, L, hit->second[1], hit->second[2]);
+                if (hs != RTEN_ERR_UNSUPPORTED_VALUE) return hs;
+            } else
             if (plan_shape(q, plan_from_array(hit->second), ps)) return launch_plan(ctx, L, q, plan_from_array(hit->second), verbose);
             // a stale entry (plans file written by another build / geometry): drop it and plan afresh
             if (verbose) fprintf(stderr, "[umma_gemm] recorded plan no longer valid for this problem: re-planning\n");
@@ -808,7 +812,11 @@ rten_status launch_umma_gemm(rten_ctx* ctx, const GemmLaunch& L) {
         const std::vector<long long> key = tune_key(L, q);
         auto it = ctx->tune_cache.find(key);
         PlanShape ps_hit;
-        if (it != ctx->tune_cache.end() && plan_shape(q, plan_from_array(it->second), ps_hit)) {
+        if (it != ctx->tune_cache.end() && it->second[0] < 0) {
+            const rten_status hs = launch_umma_halo_conv(ctx, L, it->second[1], it->second[2]);
+            if (hs != RTEN_ERR_UNSUPPORTED_VALUE) return hs;
+            ctx->tune_cache.erase(it);
+        } else if (it != ctx->tune_cache.end() && plan_shape(q, plan_from_array(it->second), ps_hit)) {
             plan = plan_from_array(it->second);
         } else if (ctx->autotune) {
             cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
@@ -874,8 +882,39 @@ rten_status launch_umma_gemm(rten_ctx* ctx, const GemmLaunch& L) {
                         plan = x;
                     }
                 }
+                // stride-1 windows: the halo-reuse kernel (umma_halo.cu) over a few unit shapes, same timing
+                int halo_bn = 0, halo_T = 0;
+                if (L.conv && L.kind == 0 && L.g.kh * L.g.kw > 1 && !L.x3_cb && !getenv("RTEN_B200_NO_HALO")) {
+                    for (int hbn : {64, 128, 256})
+                        for (int hT : {1, 2, 4}) {
+                            if (hbn > L.N || hT * hbn > 512) continue;
+                            auto time_halo = [&](int n) -> double {
+                                if (launch_umma_halo_conv(ctx, L, hbn, hT) != RTEN_OK) return -1.0;
+                                cudaEventRecord(e0, ctx->stream);
+                                bool ok = true;
+                                for (int r = 0; r < n && ok; r++) ok = launch_umma_halo_conv(ctx, L, hbn, hT) == RTEN_OK;
+                                cudaEventRecord(e1, ctx->stream);
+                                if (cudaEventSynchronize(e1) != cudaSuccess || !ok) return -1.0;
+                                float t = 0.f;
+                                cudaEventElapsedTime(&t, e0, e1);
+                                return (double)t / n;
+                            };
+                            double ms = time_halo(reps);
+                            if (ms > 0 && ms < best_ms * 1.05) ms = time_halo(2 * reps);  // a second, longer look at contenders
+                            if (verbose && ms > 0) fprintf(stderr, "[autotune] halo bn=%d T=%d -> %.2f us\n", hbn, hT, ms * 1e3);
+                            if (ms > 0 && ms < best_ms * 0.97) {  // must win clearly: the generic kernel is the better-trodden path
+                                best_ms = ms;
+                                halo_bn = hbn;
+                                halo_T = hT;
+                            }
+                        }
+                }
                 cudaEventDestroy(e0);
                 cudaEventDestroy(e1);
+                if (halo_bn) {
+                    ctx->tune_cache[key] = {-1, halo_bn, halo_T, 0, 0, 0, 0, 0};
+                    return launch_umma_halo_conv(ctx, L, halo_bn, halo_T);
+                }
                 ctx->tune_cache[key] = {plan.bn, plan.pair, plan.katoms, plan.ksplit, plan.splitk, plan.nbuf, plan.acc1, plan.cta2};
             }
         }

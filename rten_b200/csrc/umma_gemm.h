@@ -96,7 +96,7 @@ bool encode_map(rten_ctx* ctx, CUtensorMap* map, const OperandDesc& od, int esiz
 // Stride-1 convolutions with a kh x kw > 1 window on the halo-reuse kernel (umma_halo.cu): one activation patch per
 // channel block in shared memory, every filter tap a shifted window of it.  RTEN_ERR_UNSUPPORTED_VALUE = not applicable
 // (the caller then takes the generic implicit-GEMM kernel).
-rten_status launch_umma_halo_conv(rten_ctx* ctx, const GemmLaunch& L);
+rten_status launch_umma_halo_conv(rten_ctx* ctx, const GemmLaunch& L, int force_bn = 0, int force_T = 0);
 
 // true if `od` can be fed to TMA directly (16-B aligned base and strides, inner stride 1).
 bool tma_compatible(const OperandDesc& od, int esize, int rank);

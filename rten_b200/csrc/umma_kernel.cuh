@@ -462,14 +462,20 @@ __device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* t
                 int k = 0;
                 for (int c0 = grp * 32; c0 < p.bn; c0 += 64, k++) {
                     uint32_t v[32];
+#ifdef RTB_TRACE_PHASES
                     long long tp0 = 0;
                     if (tr) tp0 = clock64();
+#endif
+#ifdef RTB_TRACE_PHASES  // per-phase clocks of the chunk loop (tools/layer_probe.py); off in production builds
 #define RTB_PLAIN_PHASE(i)                                \
     if (tr) {                                             \
         const long long tp1 = clock64();                  \
         p.trace[6144 + 1024 + (i)] += tp1 - tp0;          \
         tp0 = tp1;                                        \
     }
+#else
+#define RTB_PLAIN_PHASE(i)
+#endif
                     tmem_ld_32x32(t_row + c0, v);
                     const int nbase = tc.n0 + c0;
                     const int bcur = ci % nbuf;
@@ -553,7 +559,9 @@ __device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* t
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
                     RTB_PLAIN_PHASE(7)
+#ifdef RTB_TRACE_PHASES
                     if (tr) p.trace[6144 + 1024 + 8] += 1;
+#endif
 #undef RTB_PLAIN_PHASE
                     ci++;
                 }
@@ -641,14 +649,6 @@ __device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* t
                 }
                 for (int c0 = grp * 32; c0 < p.bn; c0 += 64) {
                     uint32_t v[32];
-                    long long tp0 = 0;
-                    if (tr) tp0 = clock64();
-#define RTB_FAST_PHASE(i)                                 \
-    if (tr) {                                             \
-        const long long tp1 = clock64();                  \
-        p.trace[6144 + 1024 + (i)] += tp1 - tp0;          \
-        tp0 = tp1;                                        \
-    }
                     if (p.splitk > 1)
                         splitk_sum<KIND>(p, CTA2 ? 2 * t + cta_rank : t, sub, c0, r, v);
                     else
@@ -675,7 +675,6 @@ __device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* t
                                 tma_load_4d(stg0 + bnext * STG_BYTES, tma_r, rb, tn.n0 + nc0, tn.m0, tn.z0, tn.z1);
                         }
                     }
-                    RTB_FAST_PHASE(0)  // next residual requested (incl. waiting for the slot's previous store)
                     tmem_ld_wait();
                     if (p.ksplit) {
 #pragma unroll
@@ -692,12 +691,10 @@ __device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* t
                             }
                         }
                     }
-                    RTB_FAST_PHASE(1)  // accumulator in registers
                     if (p.res_tma) {
                         mbar_wait(&res_bar[grp * 4 + bcur], (rphase >> bcur) & 1);
                         rphase ^= 1u << bcur;
                     }
-                    RTB_FAST_PHASE(2)  // residual landed
                     // a tile may overhang N (N % bn != 0): its last 32-column chunks are then entirely out of range -- the
                     // TMA store clips them, and neither the column vectors (bias, sums, scales) nor the range may touch them
                     const bool col_ok = nbase < p.N;
@@ -790,7 +787,6 @@ __device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* t
                             rg_hi = fmaxf(rg_hi, __uint_as_float(v[j]));
                         }
                     }
-                    RTB_FAST_PHASE(3)  // math
                     if (nbuf == 1) {  // single staging buffer: the previous store must have been read before it is rewritten
                         if (issuer) bulk_wait_read(0);
                         asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
@@ -798,12 +794,9 @@ __device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* t
 #pragma unroll
                     for (int j = 0; j < 8; j++)
                         *reinterpret_cast<uint4*>(rowp + ((j ^ sw) << 4)) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                    RTB_FAST_PHASE(4)  // staged in shared memory
                     if (issuer && !p.res_tma && nbuf > 1) bulk_wait_read(nbuf - 2);
-                    RTB_FAST_PHASE(5)  // previous store's shared-memory read finished
                     fence_proxy_async();
                     asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
-                    RTB_FAST_PHASE(6)  // fence + group barrier
                     if (issuer) {
                         if (p.conv)
                             tma_store_4d(tma_d, stg, nbase, tc.ox0, tc.oy0, tc.b0);
@@ -811,9 +804,6 @@ __device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* t
                             tma_store_4d(tma_d, stg, nbase, tc.m0, tc.z0, tc.z1);
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
-                    RTB_FAST_PHASE(7)  // store issued
-                    if (tr) p.trace[6144 + 1024 + 8] += 1;
-#undef RTB_FAST_PHASE
                     ci++;
                 }
             }

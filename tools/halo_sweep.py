@@ -1,5 +1,5 @@
 """3x3 stride-1 ResNet-50 layers (batch 32): generic implicit-GEMM kernel (autotuned) vs the halo-reuse kernel over its
-unit shapes (RTEN_B200_HALO_BN / _T), CUDA-graph replay, L2 flushed.  Output: gpurun_out/halo_sweep.txt"""
+unit shapes (RTEN_B200_HALO_BN / _T), 10 chained launches per CUDA-graph replay (hot operands).  Output: gpurun_out/halo_sweep.txt"""
 import os
 import sys
 
@@ -27,22 +27,24 @@ def main():
         out.write(s + "\n")
         out.flush()
 
-    def timeit(fn):
+    def timeit(fn, reps=10):
+        # `reps` chained launches per graph replay (programmatic dependent launch, as in the model graph): hot operands,
+        # sub-microsecond resolution per launch
         fn()
         ctx.graph_begin()
-        fn()
+        for _ in range(reps):
+            fn()
         g = ctx.graph_end()
-        for _ in range(3):
+        for _ in range(2):
             g.launch()
         ts = []
-        for _ in range(9):
-            flush.zero_()
+        for _ in range(5):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(stream)
             g.launch()
             b.record(stream)
             torch.cuda.synchronize()
-            ts.append(a.elapsed_time(b))
+            ts.append(a.elapsed_time(b) / reps)
         return float(np.median(ts)) * 1e3
 
     B = int(os.environ.get("HALO_BATCH", "32"))

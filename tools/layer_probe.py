@@ -79,6 +79,7 @@ def trace(run):
     t = np.frombuffer(buf, dtype=np.int64).reshape(4, 2048).copy()
     marks = t[3][1100:1105].copy()
     ph = t[3][1024:1033].copy()
+    issue = t[3][1030:1036].copy()
     t[3][680:] = 0
     prod, mma, e0, e1 = (r[r > 0] for r in t)
     if not len(mma) or marks[0] <= 0:
@@ -90,7 +91,10 @@ def trace(run):
          f"epi dur med {np.median(e1[:n] - e0[:n]) if n else 0:.0f} | last epi end {e1.max() - m0 if n else -1} exit {marks[4] - m0}")
     if n > 1:
         s += f" | tile interval {np.diff(e0)[:4].tolist()}"
-    if ph[8] > 0:
+    if issue[1] > 0:
+        s += (f"\n   MMA warp clocks: issue {issue[0]} ({issue[0] / issue[1]:.0f} per instruction, {issue[1]} instructions), waiting for the accumulator {issue[2]}, "
+              f"for the patch {issue[3]}, for weight stages {issue[4]}, commits + bookkeeping {issue[5]}")
+    if ph[8] > 0 and issue[1] == 0:
         names = ["res-prefetch", "tmem_ld", "res-wait", "math", "st.shared", "wait-prev-store", "fence+bar", "store-issue"]
         s += "\n   epilogue phases (clk per 32-col chunk, warp 4 lane 0): " + ", ".join(f"{nm} {ph[i] / ph[8]:.0f}" for i, nm in enumerate(names)) + f"  ({ph[8]} chunks)"
     return s
@@ -126,6 +130,14 @@ if "layers" in which:
     for L in LAYERS:
         tot += COUNT[L[0]] * layer_line(*L)
     emit(f"sum over the model's conv layers (stem / fc excluded): {tot:.1f} us")
+if "halo" in which:
+    os.environ["RTEN_B200_HALO"] = "1"
+    os.environ["RTEN_B200_VERBOSE"] = "1"
+    for L in LAYERS:
+        if L[0].startswith("3x3 "):
+            layer_line("halo " + L[0], *L[1:])
+    os.environ.pop("RTEN_B200_HALO")
+    os.environ.pop("RTEN_B200_VERBOSE")
 if "kscale" in which:
     for (co, hw, res) in [(1024, 14, True), (256, 14, False), (256, 56, True), (64, 56, False), (2048, 7, True), (512, 28, True)]:
         emit(f"== K scaling: 1x1 K->{co} @{hw} res={res}")
