@@ -605,7 +605,7 @@ static rten_status launch_plan(rten_ctx* ctx, const GemmLaunch& L, const Prepare
     // the generic epilogue takes a TMA-staged residual only on its register path (f32, act <= Relu)
     if (!fastk && (L.kind == 1 || ee.act > 1)) p.res_tma = 0;
     PendingLaunch pend;
-    pend.plain = fastk && L.kind == 0 && ee.alpha == 1.0f && ee.act <= 1 && !ee.range && p.splitk == 1 &&
+    pend.plain = fastk && L.kind == 0 && ee.alpha == 1.0f && ee.act <= 1 && !ee.range &&
                  (ee.r == nullptr || (p.res_tma && ee.r_scale == 1.0f)) && !getenv("RTEN_B200_NO_PLAIN");
     pend.p = p;
     pend.maps[0] = map_a;

@@ -411,7 +411,7 @@ __device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* t
     } else if (FAST == 3 && warp >= 4) {
         // ===================== epilogue (plain f32) =====================
         // The common float case -- alpha = 1, optional column bias, optional residual (r_scale = 1, TMA-staged), act in
-        // {none, Relu}, no split-K / range -- as the shortest instruction stream the result
+        // {none, Relu}, no range output -- as the shortest instruction stream the result
         // allows: packed adds (add.rn.f32x2: the same IEEE roundings as two scalar adds), the bias of the unit's
         // columns read from shared memory (loaded while the main loop runs) instead of eight dependent global loads
         // behind the accumulator wait.   x = relu((acc + residual) + bias), rounded after each add like the generic path.
@@ -430,12 +430,15 @@ __device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* t
         const bool tr = p.trace && blockIdx.x == 0 && warp == 4 && lane == 0;  // (debug trace, RTEN_B200_TRACE_FAST)
         const int it0 = st.it;
         for (int u = worker; u < p.units_total; u += n_workers, st.it++) {
-            const int t = u;  // (no split-K)
+            int t, ks_u;
+            p.d_tiles_total.divmod(u, ks_u, t);
             const int acc = p.acc1 ? 0 : (st.it & 1);
             const uint32_t acc_phase = (st.acc >> acc) & 1;
             st.acc ^= 1u << acc;
             const TileCoord tc0 = decode_tile(p, t, 0, cta_rank);
-            if (p.res_tma && issuer && grp * 32 < p.bn) {  // residual of the first chunk: independent of the accumulator
+            // residual of the first chunk: independent of the accumulator -> requested before waiting for it (split-K: only
+            // once this CTA knows that it owns the tile's epilogue)
+            auto first_residual = [&]() {
                 const int b0 = ci % nbuf;
                 bulk_wait_read(nbuf - 1);
                 uint64_t* rb = &res_bar[grp * 4 + b0];
@@ -444,7 +447,8 @@ __device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* t
                     tma_load_4d(stg0 + b0 * STG_BYTES, tma_r, rb, tc0.n0 + grp * 32, tc0.ox0, tc0.oy0, tc0.b0);
                 else
                     tma_load_4d(stg0 + b0 * STG_BYTES, tma_r, rb, tc0.n0 + grp * 32, tc0.m0, tc0.z0, tc0.z1);
-            }
+            };
+            if (p.res_tma && p.splitk == 1 && issuer && grp * 32 < p.bn) first_residual();
             float bv = 0.0f;
             if (has_bias) {  // thread i of the group: column (i / 32) * 64 + grp * 32 + i % 32 of the tile
                 const int c = (r >> 5) * 64 + grp * 32 + (r & 31);
@@ -456,7 +460,13 @@ __device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* t
             // (the previous unit's readers of bias_s are past their last chunk barrier: every thread arrives there after its math)
             bias_s[r] = bv;
             asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
-            for (int sub = 0; sub <= p.pair; sub++) {
+            bool owner = true;
+            if (p.splitk > 1) {  // raw partial accumulators to the workspace; the LAST CTA of the tile sums them in split order
+                owner = splitk_publish(p, CTA2 ? 2 * t + cta_rank : t, ks_u, grp, q, lane,
+                                       tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_STRIDE, &sk_flag[grp]);
+                if (owner && p.res_tma && issuer && grp * 32 < p.bn) first_residual();
+            }
+            for (int sub = 0; owner && sub <= p.pair; sub++) {
                 const TileCoord tc = decode_tile(p, t, sub, cta_rank);
                 const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_STRIDE + sub * p.bn;
                 int k = 0;
@@ -476,7 +486,10 @@ __device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* t
 #else
 #define RTB_PLAIN_PHASE(i)
 #endif
-                    tmem_ld_32x32(t_row + c0, v);
+                    if (p.splitk > 1)
+                        splitk_sum<0>(p, CTA2 ? 2 * t + cta_rank : t, sub, c0, r, v);
+                    else
+                        tmem_ld_32x32(t_row + c0, v);
                     const int nbase = tc.n0 + c0;
                     const int bcur = ci % nbuf;
                     uint8_t* stg = stg0 + bcur * STG_BYTES;

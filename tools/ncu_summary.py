@@ -53,8 +53,25 @@ with open(out + ".csv", "w", newline="") as f:
     w = csv.DictWriter(f, fieldnames=[n for _, n in cols])
     w.writeheader()
     w.writerows(recs)
-umma = [r for r in recs if "umma_gemm" in r.get("kernel", "")]
+umma = [r for r in recs if "umma_gemm" in r.get("kernel", "") or "umma_halo" in r.get("kernel", "")]
 tot = sum(r["duration_ns"] for r in recs)
+
+
+def agg(rs):
+    t = sum(r["duration_ns"] for r in rs)
+    o = {"launches": len(rs), "time_us": t / 1e3, "share_of_time": t / tot if tot else None,
+         "avg_dram_bytes_per_launch": sum(r.get("dram_read", 0) + r.get("dram_write", 0) for r in rs) / len(rs),
+         "achieved_dram_gbs": sum(r.get("dram_read", 0) + r.get("dram_write", 0) for r in rs) / t if t else None}
+    for key in ("tensor_pipe_pct", "dram_pct", "l2_pct", "sm_pct"):
+        if rs and key in rs[0] and isinstance(rs[0][key], float):
+            o["time_weighted_" + key] = sum(r[key] * r["duration_ns"] for r in rs) / t
+    return o
+
+
+by = {}
+for r in recs:
+    name = r.get("kernel", "?").split("(")[0].replace("void ", "").strip()[:48]
+    by.setdefault(name, []).append(r)
 summ = {
     "launches": len(recs), "umma_launches": len(umma), "total_us": tot / 1e3,
     "umma_share_of_time": sum(r["duration_ns"] for r in umma) / tot if tot else None,
@@ -62,6 +79,8 @@ summ = {
     "umma_avg_duration_us": sum(r["duration_ns"] for r in umma) / len(umma) / 1e3 if umma else None,
     "umma_time_weighted_tensor_pipe_pct": sum(r["tensor_pipe_pct"] * r["duration_ns"] for r in umma) / sum(r["duration_ns"] for r in umma) if umma else None,
     "umma_time_weighted_dram_pct": sum(r["dram_pct"] * r["duration_ns"] for r in umma) / sum(r["duration_ns"] for r in umma) if umma and "dram_pct" in umma[0] else None,
+    "total_dram_bytes": sum(r.get("dram_read", 0) + r.get("dram_write", 0) for r in recs),
+    "by_kernel": {k: agg(v) for k, v in sorted(by.items(), key=lambda kv: -sum(r["duration_ns"] for r in kv[1]))},
 }
 json.dump(summ, open(out + ".json", "w"), indent=1)
-print(json.dumps(summ, indent=1))
+print(json.dumps({k: v for k, v in summ.items() if k != "by_kernel"}, indent=1))
