@@ -150,7 +150,8 @@ struct Prepared {
 };
 
 constexpr int SK_CNT_INTS = 1 << 16;
-static int smem_budget_for(int n_stg) { return 227 * 1024 - 3072 - n_stg * STG_BYTES; }  // 1 KB alignment slack, 1 KB barriers, 1 KB bias
+// 1 KB alignment slack, 1 KB barriers, column vectors of the plain epilogues (f32: 1 KB, integer kind: 3 KB)
+static int smem_budget_for(int n_stg, int kind) { return 227 * 1024 - (kind == 0 ? 3072 : 5120) - n_stg * STG_BYTES; }
 
 struct PlanShape {
     long long tiles_n, units_m, tiles, units;
@@ -180,7 +181,7 @@ static bool plan_shape(const Prepared& q, const Plan& pl, PlanShape& ps) {
     ps.atom_bytes = (pl.pair ? 2 : 1) * A_STAGE_BYTES + (pl.bn >> pl.cta2) * KBYTES;  // pair mode: half of B per CTA
     if (pl.katoms == 2 && ps.kb_per < 2) return false;
     ps.stage_bytes = ps.atom_bytes * pl.katoms;
-    ps.stages = std::min(MAX_STAGES, smem_budget_for(ps.n_stg) / ps.stage_bytes);
+    ps.stages = std::min(MAX_STAGES, smem_budget_for(ps.n_stg, q.esize == 4 ? 0 : 1) / ps.stage_bytes);
     if (ps.stages < 2) return false;
     return true;
 }
@@ -444,6 +445,8 @@ static rten_status launch_single(rten_ctx* ctx, int cls, const PendingLaunch& pl
     cudaError_t e;
     if (pl.plain && cls == 1) {
         e = p.cta2 ? launch(umma_gemm_kernel<0, 3, 1>) : launch(umma_gemm_kernel<0, 3, 0>);
+    } else if (pl.plain && cls == 4) {
+        e = p.cta2 ? launch(umma_gemm_kernel<1, 4, 1>) : launch(umma_gemm_kernel<1, 4, 0>);
     } else
     switch (cls * 2 + (p.cta2 ? 1 : 0)) {
         case 0: e = launch(umma_gemm_kernel<0, 0, 0>); break;
@@ -554,7 +557,7 @@ static rten_status launch_plan(rten_ctx* ctx, const GemmLaunch& L, const Prepare
     p.atom_bytes = ps.atom_bytes;
     p.stage_bytes = ps.stage_bytes;
     p.tx_bytes = (p.pair ? 2 : 1) * q.a_rows * KBYTES + (p.bn >> p.cta2) * KBYTES;  // per 128-byte K block and CTA
-    p.stages = std::min(MAX_STAGES, smem_budget_for(n_stg) / (int)p.stage_bytes);
+    p.stages = std::min(MAX_STAGES, smem_budget_for(n_stg, L.kind) / (int)p.stage_bytes);
     if (p.stages < 2) return RTEN_ERR_UNSUPPORTED_VALUE;
     if (L.kind == 0)
         p.idesc = make_idesc(1 /*F32*/, 2 /*TF32*/, 2, BM << p.cta2, p.bn);
@@ -589,7 +592,7 @@ static rten_status launch_plan(rten_ctx* ctx, const GemmLaunch& L, const Prepare
         fprintf(stderr, "[umma_gemm] kind=%d conv=%d M=%d N=%d K=%d kb=%d tiles_m=%d bn=%d pair=%d ksplit=%d katoms=%d splitk=%d acc1=%d cta2=%d units=%d stages=%d tma_store=%d res_tma=%d nbuf=%d box=%dx%dx%d\n",
                 L.kind, L.conv, L.M, L.N, L.K, p.k_blocks, p.tiles_m, p.bn, p.pair, p.ksplit, p.katoms, p.splitk, p.acc1, p.cta2,
                 p.units_total, p.stages, p.tma_store, p.res_tma, p.nbuf, p.tw, p.th, p.tb);
-    const size_t smem_bytes = (size_t)p.stages * p.stage_bytes + n_stg * STG_BYTES + 1024 /*align*/ + 1024 /*barriers*/ + 1024 /*bias*/;
+    const size_t smem_bytes = (size_t)p.stages * p.stage_bytes + n_stg * STG_BYTES + 1024 /*align*/ + 1024 /*barriers*/ + (L.kind == 0 ? 1024 : 3072) /*column vectors*/;
     // specialised epilogue when every chunk qualifies for the register fast path
     const EpilogueDesc& ee = L.epi;
     bool fastk = p.tma_store && (L.N % 32) == 0 && (!ctx->trace || getenv("RTEN_B200_TRACE_FAST")) && !getenv("RTEN_B200_NO_FAST");
@@ -605,8 +608,12 @@ static rten_status launch_plan(rten_ctx* ctx, const GemmLaunch& L, const Prepare
     // the generic epilogue takes a TMA-staged residual only on its register path (f32, act <= Relu)
     if (!fastk && (L.kind == 1 || ee.act > 1)) p.res_tma = 0;
     PendingLaunch pend;
-    pend.plain = fastk && L.kind == 0 && ee.alpha == 1.0f && ee.act <= 1 && !ee.range &&
-                 (ee.r == nullptr || (p.res_tma && ee.r_scale == 1.0f)) && !getenv("RTEN_B200_NO_PLAIN");
+    if (L.kind == 0)
+        pend.plain = fastk && ee.alpha == 1.0f && ee.act <= 1 && !ee.range && (ee.r == nullptr || (p.res_tma && ee.r_scale == 1.0f));
+    else  // integer kind: the *ToFloat operators with a scalar (or no) activation zero point and symmetric weights
+        pend.plain = fastk && ee.scale && !ee.za && !ee.zb && (ee.scale_len == 1 || ee.scale_len == L.N) && ee.act <= 1 && p.splitk == 1 &&
+                     (ee.r == nullptr || p.res_tma) && (!ee.za8 || ee.colsum);
+    if (getenv("RTEN_B200_NO_PLAIN")) pend.plain = false;
     pend.p = p;
     pend.maps[0] = map_a;
     pend.maps[1] = map_b;

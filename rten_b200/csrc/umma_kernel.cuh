@@ -130,6 +130,15 @@ __device__ __forceinline__ void add_f32x2(uint32_t& a0, uint32_t& a1, float b0, 
     asm("mov.b64 {%0, %1}, %2;" : "=r"(a0), "=r"(a1) : "l"(d));
 }
 
+// (a0, a1) *= (b0, b1): one packed FMUL2, each half rounded to nearest like a scalar multiply
+__device__ __forceinline__ void mul_f32x2(uint32_t& a0, uint32_t& a1, float b0, float b1) {
+    unsigned long long a, b, d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "r"(a0), "r"(a1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(a0), "=r"(a1) : "l"(d));
+}
+
 // cp.async.bulk.wait_group.read takes an immediate: leave at most `n` of this thread's bulk stores un-read
 __device__ __forceinline__ void bulk_wait_read(int n) {
     switch (n) {
@@ -408,7 +417,7 @@ __device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* t
                 if (++stage == p.stages) stage = 0;
             }
         }
-    } else if (FAST == 3 && warp >= 4) {
+    } else if (KIND == 0 && FAST == 3 && warp >= 4) {
         // ===================== epilogue (plain f32) =====================
         // The common float case -- alpha = 1, optional column bias, optional residual (r_scale = 1, TMA-staged), act in
         // {none, Relu}, no range output -- as the shortest instruction stream the result
@@ -589,6 +598,203 @@ __device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* t
             }
             if (tr && st.it - it0 < 2048) p.trace[6144 + st.it - it0] = clock64();
         }
+        if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    } else if (KIND == 1 && FAST == 4 && warp >= 4) {
+        // ===================== epilogue (plain, integer kind) =====================
+        // ConvIntegerToFloat / MatMulIntegerToFloat with a scalar activation zero point and symmetric weights -- the
+        // quantised ResNet-50 / GPT-2 layers:  x = relu(((f32(acc - za * colsum[n]) * (x_scale * w_scale[n])) + bias[n]) + residual)
+        // with every operation rounded separately (bit-identical to the operator chain), plus the output's (min, max)
+        // for the next DynamicQuantizeLinear.  The three column vectors of the unit are computed once into shared memory
+        // while the main loop runs (the specialised epilogue fetched them with 24 dependent 128-bit global loads per
+        // chunk behind the accumulator wait), products / sums use packed f32x2 instructions.
+        const EpilogueDesc& e = p.epi;
+        const int q = warp & 3;
+        const int grp = (warp - 4) >> 2;
+        const int r = q * 32 + lane;
+        const int sw = r & 7;
+        uint8_t* stg0 = stg_base + grp * nbuf * STG_BYTES;
+        const bool issuer = (q == 0 && lane == 0);
+        const bool has_bias = e.bias_kind == 1;
+        const bool do_relu = e.act == 1;
+        unsigned* zc_s = reinterpret_cast<unsigned*>(L.bias) + grp * 128;
+        float* scl_s = L.bias + 256 + grp * 128;
+        float* bias_s = L.bias + 512 + grp * 128;
+        uint32_t ci = 0;
+        uint32_t& rphase = st.rphase;
+        float rg_lo = __int_as_float(0x7f800000), rg_hi = __int_as_float(0xff800000);  // output range (e.range)
+        const bool tr = p.trace && blockIdx.x == 0 && warp == 4 && lane == 0;
+        const int it0 = st.it;
+        const unsigned za_v = e.za8 ? (unsigned)(e.za8_signed ? (int)(int8_t)__ldg(e.za8) : (int)__ldg(e.za8)) : 0u;
+        const float s2 = e.scale2 ? __ldg(e.scale2) : 1.0f;
+        for (int u = worker; u < p.units_total; u += n_workers, st.it++) {
+            const int t = u;  // (no split-K on this path)
+            const int acc = p.acc1 ? 0 : (st.it & 1);
+            const uint32_t acc_phase = (st.acc >> acc) & 1;
+            st.acc ^= 1u << acc;
+            const TileCoord tc0 = decode_tile(p, t, 0, cta_rank);
+            if (p.res_tma && issuer && grp * 32 < p.bn) {  // residual of the first chunk: independent of the accumulator
+                const int b0 = ci % nbuf;
+                bulk_wait_read(nbuf - 1);
+                uint64_t* rb = &res_bar[grp * 4 + b0];
+                mbar_expect_tx(rb, p.res_tx_bytes);
+                if (p.conv)
+                    tma_load_4d(stg0 + b0 * STG_BYTES, tma_r, rb, tc0.n0 + grp * 32, tc0.ox0, tc0.oy0, tc0.b0);
+                else
+                    tma_load_4d(stg0 + b0 * STG_BYTES, tma_r, rb, tc0.n0 + grp * 32, tc0.m0, tc0.z0, tc0.z1);
+            }
+            // thread i of the group: column (i / 32) * 64 + grp * 32 + i % 32 of the tile
+            unsigned zc = 0;
+            float sc = 0.0f, bv = 0.0f;
+            {
+                const int c = (r >> 5) * 64 + grp * 32 + (r & 31);
+                const int n = tc0.n0 + c;
+                if (c < p.bn && n < p.N) {
+                    if (e.za8) zc = za_v * (unsigned)__ldg(e.colsum + n);
+                    sc = e.scale_len == 1 ? __ldg(e.scale) : __ldg(e.scale + n);
+                    if (e.scale2) sc = __fmul_rn(s2, sc);
+                    if (has_bias) bv = __ldg(e.bias + n);
+                }
+            }
+            mbar_wait(&tmem_full[acc], acc_phase);
+            if (tr && st.it - it0 < 2048) p.trace[4096 + st.it - it0] = clock64();
+            tc_fence_after();
+            zc_s[r] = zc;
+            scl_s[r] = sc;
+            bias_s[r] = bv;
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+            for (int sub = 0; sub <= p.pair; sub++) {
+                const TileCoord tc = decode_tile(p, t, sub, cta_rank);
+                const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_STRIDE + sub * p.bn;
+                bool row_ok = true;
+                if (e.range) {  // rows of the tile beyond the tensor must not enter the range
+                    if (p.conv) {
+                        int xi, r2, yi, bi;
+                        p.d_tw.divmod(r, r2, xi);
+                        p.d_th.divmod(r2, bi, yi);
+                        row_ok = (bi < p.tb) && (tc.ox0 + xi < p.OW) && (tc.oy0 + yi < p.OH) && (tc.b0 + bi < p.Bn);
+                    } else {
+                        row_ok = tc.m0 + r < p.M;
+                    }
+                }
+                int k = 0;
+                for (int c0 = grp * 32; c0 < p.bn; c0 += 64, k++) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(t_row + c0, v);
+                    const int nbase = tc.n0 + c0;
+                    const int bcur = ci % nbuf;
+                    uint8_t* stg = stg0 + bcur * STG_BYTES;
+                    uint8_t* rowp = stg + r * 128;
+                    if (p.res_tma && issuer) {  // prefetch the next chunk's residual of this unit into the next ring slot
+                        int nsub = sub, nc0 = c0 + 64;
+                        if (nc0 >= p.bn) {
+                            nsub = sub + 1;
+                            nc0 = grp * 32;
+                        }
+                        if (nsub <= p.pair && nc0 < p.bn) {
+                            const TileCoord tn = decode_tile(p, t, nsub, cta_rank);
+                            const int bnext = (ci + 1) % nbuf;
+                            bulk_wait_read(nbuf - 2);
+                            uint64_t* rb = &res_bar[grp * 4 + bnext];
+                            mbar_expect_tx(rb, p.res_tx_bytes);
+                            if (p.conv)
+                                tma_load_4d(stg0 + bnext * STG_BYTES, tma_r, rb, tn.n0 + nc0, tn.ox0, tn.oy0, tn.b0);
+                            else
+                                tma_load_4d(stg0 + bnext * STG_BYTES, tma_r, rb, tn.n0 + nc0, tn.m0, tn.z0, tn.z1);
+                        }
+                    }
+                    if (p.ksplit) {  // even / odd K blocks accumulated separately: exact integer sum of the two accumulators
+                        uint32_t w0[16], w1[16];
+                        tmem_ld_32x16(t_row + p.bn + c0, w0);
+                        tmem_ld_wait();
+                        tmem_ld_32x16(t_row + p.bn + c0 + 16, w1);
+#pragma unroll
+                        for (int j = 0; j < 16; j++) v[j] += w0[j];
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; j++) v[16 + j] += w1[j];
+                    } else {
+                        tmem_ld_wait();
+                    }
+                    if (p.res_tma) {
+                        mbar_wait(&res_bar[grp * 4 + bcur], (rphase >> bcur) & 1);
+                        rphase ^= 1u << bcur;
+                    }
+                    const bool col_ok = nbase < p.N;  // (a tile may overhang N by whole chunks: the TMA store clips them)
+                    if (col_ok) {
+                        const uint4* zq = reinterpret_cast<const uint4*>(zc_s + 32 * k);
+                        const float4* sq = reinterpret_cast<const float4*>(scl_s + 32 * k);
+                        const float4* bq = reinterpret_cast<const float4*>(bias_s + 32 * k);
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const uint4 z = zq[j >> 2];
+                            const float4 s4 = sq[j >> 2];
+                            // exact i32 arithmetic with wrap-around, then f32(acc) * scale as ONE rounded product per element
+                            uint32_t f0 = __float_as_uint(__int2float_rn((int)(v[j] - z.x)));
+                            uint32_t f1 = __float_as_uint(__int2float_rn((int)(v[j + 1] - z.y)));
+                            uint32_t f2 = __float_as_uint(__int2float_rn((int)(v[j + 2] - z.z)));
+                            uint32_t f3 = __float_as_uint(__int2float_rn((int)(v[j + 3] - z.w)));
+                            mul_f32x2(f0, f1, s4.x, s4.y);
+                            mul_f32x2(f2, f3, s4.z, s4.w);
+                            if (has_bias) {
+                                const float4 bb = bq[j >> 2];
+                                add_f32x2(f0, f1, bb.x, bb.y);
+                                add_f32x2(f2, f3, bb.z, bb.w);
+                            }
+                            if (p.res_tma) {
+                                const float4 rr = *reinterpret_cast<const float4*>(rowp + (((j >> 2) ^ sw) << 4));
+                                add_f32x2(f0, f1, rr.x, rr.y);
+                                add_f32x2(f2, f3, rr.z, rr.w);
+                            }
+                            if (do_relu) {
+                                f0 = __float_as_uint(fmaxf(__uint_as_float(f0), 0.0f));
+                                f1 = __float_as_uint(fmaxf(__uint_as_float(f1), 0.0f));
+                                f2 = __float_as_uint(fmaxf(__uint_as_float(f2), 0.0f));
+                                f3 = __float_as_uint(fmaxf(__uint_as_float(f3), 0.0f));
+                            }
+                            v[j] = f0;
+                            v[j + 1] = f1;
+                            v[j + 2] = f2;
+                            v[j + 3] = f3;
+                        }
+                        if (e.range && row_ok) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 2) {
+                                rg_lo = fminf(rg_lo, fminf(__uint_as_float(v[j]), __uint_as_float(v[j + 1])));
+                                rg_hi = fmaxf(rg_hi, fmaxf(__uint_as_float(v[j]), __uint_as_float(v[j + 1])));
+                            }
+                        }
+                    }
+                    if (nbuf == 1) {  // single staging buffer: the previous store must have been read before it is rewritten
+                        if (issuer) bulk_wait_read(0);
+                        asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; j++)
+                        *reinterpret_cast<uint4*>(rowp + ((j ^ sw) << 4)) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    if (issuer && !p.res_tma && nbuf > 1) bulk_wait_read(nbuf - 2);
+                    fence_proxy_async();
+                    asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+                    if (issuer) {
+                        if (p.conv)
+                            tma_store_4d(tma_d, stg, nbase, tc.ox0, tc.oy0, tc.b0);
+                        else
+                            tma_store_4d(tma_d, stg, nbase, tc.m0, tc.z0, tc.z1);
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                    ci++;
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (CTA2)
+                    mbar_arrive_cluster(smem_u32(&tmem_empty[acc]) & PEER_BIT_MASK);  // the leader's MMA warp waits on it
+                else
+                    mbar_arrive(&tmem_empty[acc]);
+            }
+            if (tr && st.it - it0 < 2048) p.trace[6144 + st.it - it0] = clock64();
+        }
+        if (e.range) range_commit(e.range, rg_lo, rg_hi);
         if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     } else if (FAST && warp >= 4) {
         // ===================== epilogue (specialised) =====================
@@ -1111,6 +1317,7 @@ __device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* t
 
 // Shared-memory carve-up: a fixed 1 KB block of mbarriers first (so that it does not move when the stage geometry changes
 // from layer to layer of a sequence kernel), operand stages behind it.
+template <int KIND>
 __device__ __forceinline__ SmemLayout carve_smem(uint8_t* smem_raw) {
     // 1024-B alignment required by the 128B swizzle atoms / UMMA descriptors (base_offset = 0).
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -1121,8 +1328,10 @@ __device__ __forceinline__ SmemLayout carve_smem(uint8_t* smem_raw) {
     L.tmem_empty = L.tmem_full + 2;
     L.res_bar = L.tmem_empty + 2;  // [group][buffer], up to 4 buffers per group
     L.sk_flag = reinterpret_cast<int*>(L.res_bar + 8) + 2;  // [group]; the two ints before it hold the TMEM base
-    L.bias = reinterpret_cast<float*>(base + 1024);  // [group][128]: the plain epilogue's column bias of the current unit
-    L.smem = base + 2048;
+    // column vectors of the current unit for the plain epilogues: f32 [group][128] bias (1 KB); integer kind
+    // [3][group][128]: za * colsum, scale product, bias (3 KB)
+    L.bias = reinterpret_cast<float*>(base + 1024);
+    L.smem = base + (KIND == 0 ? 2048 : 4096);
     return L;
 }
 
@@ -1195,7 +1404,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                  const __grid_constant__ CUtensorMap tma_d, const __grid_constant__ CUtensorMap tma_r,
                  const __grid_constant__ CUtensorMap tma_a2, const __grid_constant__ KParams p) {
     extern __shared__ uint8_t smem_raw[];
-    const SmemLayout L = carve_smem(smem_raw);
+    const SmemLayout L = carve_smem<KIND>(smem_raw);
     if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[6144 + 1100] = clock64();  // kernel entry
     // CTA pair: cluster rank 0 is the leader (issues the MMAs); work is distributed over clusters
     const int cta_rank = CTA2 ? (int)cluster_ctarank() : 0;
@@ -1248,7 +1457,7 @@ __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
 template <int KIND, int FAST>
 __global__ void __launch_bounds__(NUM_THREADS, 1) umma_seq_kernel(const __grid_constant__ SeqParams sp) {
     extern __shared__ uint8_t smem_raw[];
-    const SmemLayout L = carve_smem(smem_raw);
+    const SmemLayout L = carve_smem<KIND>(smem_raw);
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&sp.maps[0][0]);
         tma_prefetch_desc(&sp.maps[0][1]);
