@@ -79,6 +79,84 @@ __device__ __forceinline__ float gelu_ref(float x) {
     return __fmul_rn(half_x, y);
 }
 
+// ---- two lanes at a time (packed f32x2 FMA / MUL / ADD: each half is the same IEEE operation as its scalar twin, so
+// gelu_ref_x2 is bit-identical to two gelu_ref calls with ~40 % fewer instructions -- the GEMM epilogue's Gelu)
+struct f32x2 {
+    unsigned long long v;
+};
+__device__ __forceinline__ f32x2 pack2(float a, float b) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 p, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(p.v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+    return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+__device__ __forceinline__ f32x2 splat2(float c) { return pack2(c, c); }
+
+__device__ __forceinline__ void gelu_ref_x2(float& x0, float& x1) {
+    const f32x2 x = pack2(x0, x1);
+    const f32x2 half_x = mul2(x, splat2(0.5f));
+    const f32x2 y = mul2(x, splat2(0.70710678118654752440f));
+    float y0, y1;
+    unpack2(y, y0, y1);
+    // ---- erf_ref(y)
+    const float a0 = fabsf(y0), a1 = fabsf(y1);
+    const f32x2 ax = pack2(a0, a1);
+    float d0, d1;
+    unpack2(fma2(ax, splat2(0.3275911f), splat2(1.0f)), d0, d1);
+    const f32x2 t = pack2(__frcp_rn(d0), __frcp_rn(d1));  // == __fdiv_rn(1.0f, d): both are the correctly rounded quotient
+    f32x2 pl = splat2(1.061405429f);
+    pl = fma2(pl, t, splat2(-1.453152027f));
+    pl = fma2(pl, t, splat2(1.421413741f));
+    pl = fma2(pl, t, splat2(-0.284496736f));
+    pl = fma2(pl, t, splat2(0.254829592f));
+    const f32x2 at = mul2(pl, t);
+    const f32x2 xm2 = mul2(pack2(-a0, -a1), ax);  // 0 - x*x: the negation of the rounded product, exactly
+    // ---- reduced_range_exp(xm2)
+    const float magic = 12582912.0f;
+    f32x2 j = fma2(xm2, splat2(1.44269504088896340736f), splat2(magic));
+    j = add2(j, splat2(-magic));
+    f32x2 r = fma2(j, splat2(-6.93145752e-1f), xm2);
+    r = fma2(j, splat2(-1.42860677e-6f), r);
+    f32x2 q = splat2(1.37805939e-3f);
+    q = fma2(q, r, splat2(8.37312452e-3f));
+    q = fma2(q, r, splat2(4.16695364e-2f));
+    q = fma2(q, r, splat2(1.66664720e-1f));
+    q = fma2(q, r, splat2(4.99999851e-1f));
+    q = fma2(q, r, splat2(1.0f));
+    q = fma2(q, r, splat2(1.0f));
+    float j0, j1, m0, m1;
+    unpack2(j, j0, j1);
+    unpack2(xm2, m0, m1);
+    const float p0 = __int_as_float((int)((unsigned)(trunc_i32_x86(j0) + 127) << 23));
+    const float p1 = __int_as_float((int)((unsigned)(trunc_i32_x86(j1) + 127) << 23));
+    float e0, e1;
+    unpack2(mul2(q, pack2(p0, p1)), e0, e1);
+    const float cutoff = -126.5f * 0.693147180559945309417f + 0.01f;
+    e0 = (m0 < cutoff) ? 0.0f : e0;
+    e1 = (m1 < cutoff) ? 0.0f : e1;
+    // ---- 1 - at * e (two roundings), sign, + 1, * x / 2
+    float r0, r1;
+    unpack2(fma2(mul2(at, pack2(e0, e1)), splat2(-1.0f), splat2(1.0f)), r0, r1);
+    r0 = (y0 < 0.0f) ? __fsub_rn(0.0f, r0) : r0;
+    r1 = (y1 < 0.0f) ? __fsub_rn(0.0f, r1) : r1;
+    unpack2(mul2(half_x, add2(pack2(r0, r1), splat2(1.0f))), x0, x1);
+}
+
 __device__ __forceinline__ float tanh_ref(float x) {
     bool neg = x <= 0.0f;
     float ax = fabsf(x);

@@ -833,21 +833,24 @@ dql_quantize_kernel(const float* __restrict__ x, uint8_t* __restrict__ y, long l
         *zp_out = (uint8_t)zp;
     }
     const long long stride = (long long)gridDim.x * blockDim.x;
-    // 16 elements per thread and iteration: four independent 128-bit loads in flight, one 128-bit store
-    const bool al = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
-    const long long n16 = al ? (n >> 4) : 0;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
-        const float4* xp = reinterpret_cast<const float4*>(x) + 4 * i;
-        const float4 v0 = xp[0], v1 = xp[1], v2 = xp[2], v3 = xp[3];
-        const float f[16] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w, v3.x, v3.y, v3.z, v3.w};
-        uint32_t w[4];
+    // A warp takes 2 KB of x per iteration as four fully coalesced 128-bit loads (lane l reads float4 j * 32 + l: whole
+    // 512-byte rows per instruction, all four in flight) and writes the 512 quantised bytes as four coalesced 32-bit
+    // stores.  (Sixteen consecutive floats per lane made every load instruction touch 32 half-used sectors.)
+    const bool al = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((reinterpret_cast<uintptr_t>(y) & 3) == 0);
+    const long long nblk = al ? (n >> 9) : 0;  // 512-element blocks, one per warp and iteration
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = stride >> 5;
+    for (long long b = warp; b < nblk; b += nwarps) {
+        const float4* xp = reinterpret_cast<const float4*>(x) + (b << 7) + lane;
+        const float4 v0 = xp[0], v1 = xp[32], v2 = xp[64], v3 = xp[96];
+        uint32_t* yp = reinterpret_cast<uint32_t*>(y) + (b << 7) + lane;
+        const float4 vv[4] = {v0, v1, v2, v3};
 #pragma unroll
         for (int g = 0; g < 4; g++)
-            w[g] = (uint32_t)quant1(f[4 * g], inv, zp) | ((uint32_t)quant1(f[4 * g + 1], inv, zp) << 8) |
-                   ((uint32_t)quant1(f[4 * g + 2], inv, zp) << 16) | ((uint32_t)quant1(f[4 * g + 3], inv, zp) << 24);
-        reinterpret_cast<uint4*>(y)[i] = make_uint4(w[0], w[1], w[2], w[3]);
+            yp[32 * g] = (uint32_t)quant1(vv[g].x, inv, zp) | ((uint32_t)quant1(vv[g].y, inv, zp) << 8) |
+                         ((uint32_t)quant1(vv[g].z, inv, zp) << 16) | ((uint32_t)quant1(vv[g].w, inv, zp) << 24);
     }
-    for (long long j = (n16 << 4) + (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride)
+    for (long long j = (nblk << 9) + (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride)
         y[j] = quant1(x[j], inv, zp);
 }
 

@@ -445,6 +445,8 @@ static rten_status launch_single(rten_ctx* ctx, int cls, const PendingLaunch& pl
     cudaError_t e;
     if (pl.plain && cls == 1) {
         e = p.cta2 ? launch(umma_gemm_kernel<0, 3, 1>) : launch(umma_gemm_kernel<0, 3, 0>);
+    } else if (pl.plain && cls == 2) {
+        e = p.cta2 ? launch(umma_gemm_kernel<0, 5, 1>) : launch(umma_gemm_kernel<0, 5, 0>);
     } else if (pl.plain && cls == 4) {
         e = p.cta2 ? launch(umma_gemm_kernel<1, 4, 1>) : launch(umma_gemm_kernel<1, 4, 0>);
     } else
@@ -609,7 +611,7 @@ static rten_status launch_plan(rten_ctx* ctx, const GemmLaunch& L, const Prepare
     if (!fastk && (L.kind == 1 || ee.act > 1)) p.res_tma = 0;
     PendingLaunch pend;
     if (L.kind == 0)
-        pend.plain = fastk && ee.alpha == 1.0f && ee.act <= 1 && !ee.range && (ee.r == nullptr || (p.res_tma && ee.r_scale == 1.0f));
+        pend.plain = fastk && ee.alpha == 1.0f && ee.act <= 3 && !ee.range && (ee.r == nullptr || (p.res_tma && ee.r_scale == 1.0f));
     else  // integer kind: the *ToFloat operators with a scalar (or no) activation zero point and symmetric weights
         pend.plain = fastk && ee.scale && !ee.za && !ee.zb && (ee.scale_len == 1 || ee.scale_len == L.N) && ee.act <= 1 && p.splitk == 1 &&
                      (ee.r == nullptr || p.res_tma) && (!ee.za8 || ee.colsum);

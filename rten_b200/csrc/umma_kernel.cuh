@@ -170,6 +170,11 @@ __device__ __forceinline__ void range_commit(int* range, float lo, float hi) {
 // code (an unrolled polynomial per element would multiply its size and thrash the instruction cache), yet Gelu no
 // longer forces a launch into the generic epilogue.
 __device__ __noinline__ float4 act4(float4 x, int act) {
+    if (act == 2) {  // Gelu: two lanes per packed instruction (bit-identical to gelu_ref, math.cuh)
+        gelu_ref_x2(x.x, x.y);
+        gelu_ref_x2(x.z, x.w);
+        return x;
+    }
     x.x = apply_act(x.x, act);
     x.y = apply_act(x.y, act);
     x.z = apply_act(x.z, act);
@@ -417,7 +422,7 @@ __device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* t
                 if (++stage == p.stages) stage = 0;
             }
         }
-    } else if (KIND == 0 && FAST == 3 && warp >= 4) {
+    } else if (KIND == 0 && (FAST == 3 || FAST == 5) && warp >= 4) {
         // ===================== epilogue (plain f32) =====================
         // The common float case -- alpha = 1, optional column bias, optional residual (r_scale = 1, TMA-staged), act in
         // {none, Relu}, no range output -- as the shortest instruction stream the result
@@ -556,6 +561,14 @@ __device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* t
                             if (do_relu) {
 #pragma unroll
                                 for (int w = 0; w < 4; w++) v[j + w] = __float_as_uint(fmaxf(__uint_as_float(v[j + w]), 0.0f));
+                            }
+                            if (FAST == 5) {  // Gelu / ApproxGelu (own instantiation; the polynomial stays an out-of-line call)
+                                const float4 g = act4(make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                                                  __uint_as_float(v[j + 3])), e.act);
+                                v[j] = __float_as_uint(g.x);
+                                v[j + 1] = __float_as_uint(g.y);
+                                v[j + 2] = __float_as_uint(g.z);
+                                v[j + 3] = __float_as_uint(g.w);
                             }
                         }
                     }

@@ -1307,6 +1307,37 @@ def check_attention_encoder(rt, oracle):
     return f"{n} cases (3 value layouts x 2 modes x 3 shapes), one-kernel TF32 path worst rel err {worst:.1e}"
 
 
+def check_gelu_epilogue(rt, oracle):
+    """The GEMM epilogue's Gelu (two lanes per packed f32x2 instruction, math.cuh gelu_ref_x2) must be BIT-IDENTICAL to
+    the Gelu operator (the reference's scalar recipe, bit-exact against the oracle in check_unary) applied to the same
+    product: FusedMatMul(bias, Gelu) vs FusedMatMul(bias) -> Gelu with the launch plan pinned (same accumulation order),
+    for erf-Gelu and the tanh form, values spanning the exp cut-off, zeros and large magnitudes."""
+    import os
+    ctx = new_ctx(rt, tf32=True)
+    r = oracle.XorShiftRng(2718)
+    forced = {"RTEN_B200_FORCE_BN": "128", "RTEN_B200_FORCE_PAIR": "0", "RTEN_B200_FORCE_KATOMS": "1", "RTEN_B200_FORCE_SPLITK": "1", "RTEN_B200_FORCE_CTA2": "0"}
+    os.environ.update(forced)
+    try:
+        n = 0
+        for (m, k, nn), amp in [((384, 64, 256), 1.0), ((256, 128, 384), 6.0), ((128, 32, 128), 40.0)]:
+            a = (r.uniform((m, k), -1, 1) * amp).astype(np.float32)
+            a[:4] = 0.0  # rows of exact zeros: Gelu(bias) alone
+            b = r.uniform((k, nn), -1, 1)
+            bias = r.uniform((nn,), -1, 1)
+            bias[:3] = 0.0
+            da, db, dbias = ctx.to_device(a), ctx.to_device(b), ctx.to_device(bias)
+            for act, approx in ((rt.ACT_GELU, False), (rt.ACT_GELU_TANH, True)):
+                fused = rt.FusedMatMul(None, activation=act).run(ctx, da, db, dbias).numpy()
+                plain = rt.FusedMatMul(None).run(ctx, da, db, dbias)
+                two = rt.Gelu(approximate=approx).run(ctx, plain).numpy()
+                assert_bit_exact(fused, two, f"Gelu epilogue (approximate={approx}) {m}x{k}x{nn} amp {amp}")
+                n += 1
+    finally:
+        for kname in forced:
+            os.environ.pop(kname, None)
+    return f"{n} fused-vs-operator comparisons bit-identical"
+
+
 def check_skinny_f32(rt, oracle):
     """MatMul / Gemm / FusedMatMul with M <= 32 rows run the HBM-streaming skinny kernel in exact f32 FMA arithmetic
     (rten-gemm's gemv path): the reference's float rule against the oracle, in BOTH f32 modes (the mode does not
@@ -1610,7 +1641,7 @@ ALL_CHECKS = [
     ("conv_basic", check_conv_basic), ("conv_stride", check_conv_stride), ("conv_more", check_conv_more),
     ("conv_integer", check_conv_integer), ("plans", check_plans), ("tf32x3", check_tf32x3), ("sequence", check_sequence), ("conv_integer_fused", check_conv_integer_fused),
     ("resnet50_int8_model", check_resnet50_int8_model), ("gpt2_int8_kvcache", check_gpt2_int8_kvcache), ("mnist_model", check_mnist_model), ("resnet50_model", check_resnet50_model), ("bert_model", check_bert_model),
-    ("model_executor", check_model_executor), ("generator", check_generator), ("halo_conv", check_halo_conv), ("quantized_linear", check_quantized_linear), ("attention_decode", check_attention_decode), ("attention_encoder", check_attention_encoder), ("skinny_f32", check_skinny_f32),
+    ("model_executor", check_model_executor), ("generator", check_generator), ("halo_conv", check_halo_conv), ("quantized_linear", check_quantized_linear), ("attention_decode", check_attention_decode), ("attention_encoder", check_attention_encoder), ("gelu_epilogue", check_gelu_epilogue), ("skinny_f32", check_skinny_f32),
     ("reference_rule_f32", check_reference_rule_f32), ("graph_pool_isolation", check_graph_pool_isolation),
     ("resnet50_b32_baseline", check_resnet50_b32_baseline), ("bert_b16_baseline", check_bert_b16_baseline),
     ("resnet50_int8_b64_baseline", check_resnet50_int8_b64_baseline), ("gpt2_b8_baseline", check_gpt2_b8_baseline),
