@@ -447,6 +447,8 @@ static rten_status launch_single(rten_ctx* ctx, int cls, const PendingLaunch& pl
         e = p.cta2 ? launch(umma_gemm_kernel<0, 3, 1>) : launch(umma_gemm_kernel<0, 3, 0>);
     } else if (pl.plain && cls == 2) {
         e = p.cta2 ? launch(umma_gemm_kernel<0, 5, 1>) : launch(umma_gemm_kernel<0, 5, 0>);
+    } else if (pl.plain && cls == 5) {
+        e = p.cta2 ? launch(umma_gemm_kernel<1, 6, 1>) : launch(umma_gemm_kernel<1, 6, 0>);
     } else if (pl.plain && cls == 4) {
         e = p.cta2 ? launch(umma_gemm_kernel<1, 4, 1>) : launch(umma_gemm_kernel<1, 4, 0>);
     } else
@@ -613,7 +615,7 @@ static rten_status launch_plan(rten_ctx* ctx, const GemmLaunch& L, const Prepare
     if (L.kind == 0)
         pend.plain = fastk && ee.alpha == 1.0f && ee.act <= 3 && !ee.range && (ee.r == nullptr || (p.res_tma && ee.r_scale == 1.0f));
     else  // integer kind: the *ToFloat operators with a scalar (or no) activation zero point and symmetric weights
-        pend.plain = fastk && ee.scale && !ee.za && !ee.zb && (ee.scale_len == 1 || ee.scale_len == L.N) && ee.act <= 1 && p.splitk == 1 &&
+        pend.plain = fastk && ee.scale && !ee.za && !ee.zb && (ee.scale_len == 1 || ee.scale_len == L.N) && ee.act <= 3 && p.splitk == 1 &&
                      (ee.r == nullptr || p.res_tma) && (!ee.za8 || ee.colsum);
     if (getenv("RTEN_B200_NO_PLAIN")) pend.plain = false;
     pend.p = p;

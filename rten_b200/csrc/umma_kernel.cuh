@@ -612,7 +612,7 @@ __device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* t
             if (tr && st.it - it0 < 2048) p.trace[6144 + st.it - it0] = clock64();
         }
         if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-    } else if (KIND == 1 && FAST == 4 && warp >= 4) {
+    } else if (KIND == 1 && (FAST == 4 || FAST == 6) && warp >= 4) {
         // ===================== epilogue (plain, integer kind) =====================
         // ConvIntegerToFloat / MatMulIntegerToFloat with a scalar activation zero point and symmetric weights -- the
         // quantised ResNet-50 / GPT-2 layers:  x = relu(((f32(acc - za * colsum[n]) * (x_scale * w_scale[n])) + bias[n]) + residual)
@@ -763,6 +763,13 @@ __device__ __forceinline__ void run_layer(const KParams& p, const CUtensorMap* t
                                 f1 = __float_as_uint(fmaxf(__uint_as_float(f1), 0.0f));
                                 f2 = __float_as_uint(fmaxf(__uint_as_float(f2), 0.0f));
                                 f3 = __float_as_uint(fmaxf(__uint_as_float(f3), 0.0f));
+                            }
+                            if (FAST == 6) {  // Gelu / ApproxGelu after the integer product (own instantiation, out-of-line polynomial)
+                                const float4 g = act4(make_float4(__uint_as_float(f0), __uint_as_float(f1), __uint_as_float(f2), __uint_as_float(f3)), e.act);
+                                f0 = __float_as_uint(g.x);
+                                f1 = __float_as_uint(g.y);
+                                f2 = __float_as_uint(g.z);
+                                f3 = __float_as_uint(g.w);
                             }
                             v[j] = f0;
                             v[j + 1] = f1;
