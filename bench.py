@@ -385,8 +385,10 @@ def main():
         out_dst = rt.from_torch(ctx, out_t)
         gather_bufs = [torch.empty(shard.gather_layout(world, out_shape), dtype=torch.float32, device="cuda") for _ in range(2)] if world > 1 else None
         graph, o_fixed = None, None
-        # with a communicator the step contains NCCL calls issued by the library (range all-reduce): not captured
-        use_graph = not args.no_graph and comm is None
+        # With a communicator the quantise kernels exchange their ranges over NVLink peer mailboxes inside the step: plain
+        # kernels, capturable (the epoch lives in device memory, so replays stay in step across ranks as long as every rank
+        # replays the same number of times).  Only the NCCL fallback (peer memory unavailable) keeps the step eager.
+        use_graph = not args.no_graph and (comm is None or comm.uses_peer_memory)
         if use_graph:
             ctx.graph_begin()
             o_fixed = step_fn()
@@ -455,8 +457,11 @@ def main():
                    cuda_graph=graph is not None, flops_per_step=flops)
         if flops:
             res["model_tflops"] = flops * world * args.steps / (ms / 1e3) / 1e12
-        if want_kernel_times and rank == 0 and graph is not None:
-            res["kernel_times"] = graph_kernel_times(torch, graph.launch)
+        if want_kernel_times and graph is not None and (rank == 0 or comm is not None):
+            # (a step with cross-rank exchanges must be replayed by every rank the same number of times)
+            kt = graph_kernel_times(torch, graph.launch)
+            if rank == 0:
+                res["kernel_times"] = kt
 
         # ---- e2e: pinned host inputs -> H2D -> step -> D2H of the result, every step, double-buffered on a copy stream
         pinned = []
@@ -523,6 +528,8 @@ def main():
                       "ms_per_step": ms_e2e / args.steps,
                       "how": "double-buffered: the copy stream moves step i+1's input H2D and step i-1's result D2H while step i computes; every step's H2D + D2H and the L2 flush are inside the timed region"}
         if comm is not None:
+            res["comm"] = {"range_exchange": "NVLink peer mailboxes (one kernel prologue per DynamicQuantizeLinear)" if comm.uses_peer_memory else "ncclAllReduce x2",
+                           "timeouts": comm.timeouts()}
             comm.close()
         return res
 
@@ -673,7 +680,7 @@ def main():
                                  "bytes": "algorithmic: every operand / output / residual of every conv and GEMM once, over the whole step time"}}
 
         def public(r):
-            keep = {k: r[k] for k in ("value", "ms_per_step", "gpu_launches", "clocks", "e2e", "cuda_graph") if k in r}
+            keep = {k: r[k] for k in ("value", "ms_per_step", "gpu_launches", "clocks", "e2e", "cuda_graph", "comm") if k in r}
             if r.get("model_tflops"):
                 keep["model_tflops"] = r["model_tflops"]
             if r.get("prefill_tokens_per_sec"):

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "api_shared.h"
+#include "comm_device.cuh"
 #include "api_util.h"
 #include "rowops.h"
 #include "skinny.h"
@@ -382,14 +383,18 @@ rten_status rten_b200_dynamic_quantize_linear_ranged(rten_ctx* ctx, const rten_t
                 st = temp_alloc(ctx, 8, (void**)&mm);
                 if (st == RTEN_OK) st = launch_minmax(ctx, (const float*)xc.data, n, mm);
             }
-            // batch-sharded run: the range is the range of the whole (unsharded) tensor
-            if (st == RTEN_OK && nccl_comm) st = comm_allreduce_minmax(ctx, reinterpret_cast<rten_comm*>(nccl_comm), mm);
+            // batch-sharded run: the range is the range of the whole (unsharded) tensor -- exchanged over NVLink peer
+            // mailboxes by the quantise kernel's own prologue, or by two ncclAllReduce calls in front of it
+            RangeExchange xch;
+            const bool fused_xch = nccl_comm && comm_range_exchange(reinterpret_cast<rten_comm*>(nccl_comm), &xch);
+            if (st == RTEN_OK && nccl_comm && !fused_xch) st = comm_allreduce_minmax(ctx, reinterpret_cast<rten_comm*>(nccl_comm), mm);
             if (st == RTEN_OK && rows_out)
                 st = launch_dql_quantize_rows(ctx, (const float*)xc.data, (uint8_t*)yv.data, xv.shape[0] * xv.shape[2],
                                               (int)(xv.shape[3] * xv.shape[1]), (int)xv.shape[2], yv.strides[2], yv.strides[0], mm,
-                                              (float*)sv.data, (uint8_t*)zv.data);
+                                              (float*)sv.data, (uint8_t*)zv.data, fused_xch ? &xch : nullptr);
             else if (st == RTEN_OK)
-                st = launch_dql_quantize(ctx, (const float*)xc.data, (uint8_t*)yv.data, n, mm, (float*)sv.data, (uint8_t*)zv.data);
+                st = launch_dql_quantize(ctx, (const float*)xc.data, (uint8_t*)yv.data, n, mm, (float*)sv.data, (uint8_t*)zv.data,
+                                         fused_xch ? &xch : nullptr);
         }
     }
     return sc.finish(st);

@@ -15,11 +15,14 @@
 
 #include <vector>
 
+#include "comm_device.cuh"
 #include "common.h"
 
 struct Id128 {  // ncclUniqueId: 128 opaque bytes, passed BY VALUE to ncclCommInitRank
     char bytes[128];
 };
+
+using namespace rtb;
 
 namespace {
 
@@ -59,71 +62,10 @@ constexpr int kNcclInt32 = 2;  // ncclInt32
 constexpr int kNcclMax = 2;    // ncclMax
 constexpr int kNcclMin = 3;    // ncclMin
 
-constexpr int MAX_PEERS = 16;
-
-// one rank's mailbox: slot[parity][sender] = {(epoch << 32) | min, (epoch << 32) | max}
-struct Mailbox {
-    unsigned long long slot[2][MAX_PEERS][2];
-    unsigned epoch;     // exchanges completed by the owner (advanced by the kernel)
-    unsigned timeouts;  // exchanges that gave up waiting for a peer (reported by the next host call)
-};
-
-struct PeerTable {
-    Mailbox* box[MAX_PEERS];  // box[rank] = the local mailbox
-};
-
-__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-
 // mm[0] / mm[1]: ordered-int encodings of the local min / max (integer order == float order)
 __global__ void __launch_bounds__(32) peer_minmax_kernel(int* mm, const PeerTable peers, int rank, int world) {
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    const int lane = threadIdx.x;
-    Mailbox* mine = peers.box[rank];
-    const unsigned e = mine->epoch + 1;
-    const unsigned long long tag = (unsigned long long)e << 32;
-    int lo = 0x7fffffff, hi = (int)0x80000000;
-    if (lane < world) {
-        const unsigned long long w_lo = tag | (unsigned)mm[0], w_hi = tag | (unsigned)mm[1];
-        unsigned long long* dst = peers.box[lane]->slot[e & 1][rank];
-        st_relaxed_sys_u64(dst, w_lo);
-        st_relaxed_sys_u64(dst + 1, w_hi);
-        const unsigned long long* src = mine->slot[e & 1][lane];
-        const long long t0 = clock64();
-        unsigned long long a, b;
-        bool ok = true;
-        do {
-            a = ld_relaxed_sys_u64(src);
-            b = ld_relaxed_sys_u64(src + 1);
-            if ((a >> 32) == e && (b >> 32) == e) break;
-            if (clock64() - t0 > 60000000000LL) {  // ~30 s: a peer never arrived -- do not hang the GPU for ever, flag the error
-                ok = false;
-                break;
-            }
-        } while (true);
-        if (ok) {
-            lo = (int)(unsigned)a;
-            hi = (int)(unsigned)b;
-        } else {
-            atomicAdd(&mine->timeouts, 1u);
-        }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
-    }
-    if (lane == 0) {
-        mm[0] = lo;
-        mm[1] = hi;
-        mine->epoch = e;
-    }
+    peer_minmax_warp(mm, peers, rank, world);
 }
 
 }  // namespace
@@ -167,6 +109,17 @@ rten_status comm_allreduce_minmax(rten_ctx* ctx, rten_comm* comm, int* mm) {
     }
     count_launch(ctx, 2);
     return RTEN_OK;
+}
+
+// the quantise kernels run the exchange themselves (rowops.cu): hand them the peer table, or world = 0 when this
+// communicator exchanges through NCCL (the caller then takes comm_allreduce_minmax first)
+bool comm_range_exchange(rten_comm* comm, RangeExchange* out) {
+    memset(out, 0, sizeof(*out));
+    if (!comm || comm->world <= 1 || !comm->peer_ok || getenv("RTEN_B200_UNFUSED_RANGE_EXCHANGE")) return false;
+    out->peers = comm->peers;
+    out->rank = comm->rank;
+    out->world = comm->world;
+    return true;
 }
 
 }  // namespace rtb

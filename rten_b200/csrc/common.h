@@ -146,6 +146,8 @@ inline void count_launch(rten_ctx* ctx, int n = 1) { ctx->launches += (uint64_t)
 
 // cross-rank min / max of the DynamicQuantizeLinear range (comm.cu)
 rten_status comm_allreduce_minmax(rten_ctx* ctx, struct ::rten_comm* comm, int* mm);
+struct RangeExchange;
+bool comm_range_exchange(struct ::rten_comm* comm, RangeExchange* out);  // true: the quantise kernel exchanges the range itself
 
 // Deferred tensor-core launches (graph capture batches them into sequence kernels, umma_gemm.cu) must be issued
 // before anything else is enqueued on the context stream: every other launch site asks for the stream through this.

@@ -16,6 +16,7 @@
 #include "math.cuh"
 #include "rowmath.cuh"
 #include "rowops.h"
+#include "comm_device.cuh"
 
 namespace rtb {
 
@@ -823,11 +824,14 @@ __global__ void __launch_bounds__(256) minmax_kernel(const float* __restrict__ x
 }
 
 __global__ void __launch_bounds__(256)
-dql_quantize_kernel(const float* __restrict__ x, uint8_t* __restrict__ y, long long n, const int* mm, float* scale_out,
-                    uint8_t* zp_out) {
+dql_quantize_kernel(const float* __restrict__ x, uint8_t* __restrict__ y, long long n, int* mm, float* scale_out,
+                    uint8_t* zp_out, const RangeExchange xch) {
+    // batch-sharded run: block 0 exchanges the local (min, max) with the other ranks over NVLink first (comm_device.cuh)
+    range_exchange_begin(mm, xch);
     float scale, inv;
     int zp;
     dql_params(mm, scale, inv, zp);
+    range_exchange_done(xch);  // (mm has been read by every thread of this block)
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         *scale_out = scale;
         *zp_out = (uint8_t)zp;
@@ -899,10 +903,12 @@ dql_small_kernel(const float* __restrict__ x, uint8_t* __restrict__ y, int n, fl
 // (r / rows_inner) * y_outer + (r % rows_inner) * y_inner -- the interior of a spatially pre-padded channels-last buffer.
 __global__ void __launch_bounds__(256)
 dql_quantize_rows_kernel(const float* __restrict__ x, uint8_t* __restrict__ y, long long rows, int row_len, int rows_inner,
-                         long long y_inner, long long y_outer, const int* mm, float* scale_out, uint8_t* zp_out) {
+                         long long y_inner, long long y_outer, int* mm, float* scale_out, uint8_t* zp_out, const RangeExchange xch) {
+    range_exchange_begin(mm, xch);
     float scale, inv;
     int zp;
     dql_params(mm, scale, inv, zp);
+    range_exchange_done(xch);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         *scale_out = scale;
         *zp_out = (uint8_t)zp;
@@ -933,11 +939,14 @@ dql_quantize_rows_kernel(const float* __restrict__ x, uint8_t* __restrict__ y, l
 }
 
 rten_status launch_dql_quantize_rows(rten_ctx* ctx, const float* x, uint8_t* y, long long rows, int row_len, int rows_inner,
-                                     long long y_inner, long long y_outer, const int* mm, float* scale_out, uint8_t* zp_out) {
+                                     long long y_inner, long long y_outer, int* mm, float* scale_out, uint8_t* zp_out,
+                                     const RangeExchange* xch) {
     const long long total = rows * ((row_len + 15) / 16);
     if (total == 0) return RTEN_OK;
+    RangeExchange none;
+    memset(&none, 0, sizeof(none));
     dql_quantize_rows_kernel<<<ew_grid(ctx, total), 256, 0, launch_stream(ctx)>>>(x, y, rows, row_len, rows_inner, y_inner, y_outer,
-                                                                          mm, scale_out, zp_out);
+                                                                          mm, scale_out, zp_out, xch ? *xch : none);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail_cuda(ctx, e, "dql launch");
     count_launch(ctx);
@@ -981,9 +990,11 @@ rten_status launch_minmax(rten_ctx* ctx, const float* x, long long n, int* mm) {
     return RTEN_OK;
 }
 
-rten_status launch_dql_quantize(rten_ctx* ctx, const float* x, uint8_t* y, long long n, const int* mm, float* scale_out,
-                                uint8_t* zp_out) {
-    dql_quantize_kernel<<<ew_grid(ctx, (n + 15) / 16), 256, 0, launch_stream(ctx)>>>(x, y, n, mm, scale_out, zp_out);
+rten_status launch_dql_quantize(rten_ctx* ctx, const float* x, uint8_t* y, long long n, int* mm, float* scale_out,
+                                uint8_t* zp_out, const RangeExchange* xch) {
+    RangeExchange none;
+    memset(&none, 0, sizeof(none));
+    dql_quantize_kernel<<<ew_grid(ctx, (n + 15) / 16), 256, 0, launch_stream(ctx)>>>(x, y, n, mm, scale_out, zp_out, xch ? *xch : none);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail_cuda(ctx, e, "dql launch");
     count_launch(ctx);

@@ -30,8 +30,10 @@ rten_status launch_nd_add(rten_ctx* ctx, const float* a, const float* b, float* 
                           const long long* sa, const long long* sb, const long long* sd, int relu);
 rten_status launch_add_flat(rten_ctx* ctx, const float* a, const float* b, float* d, long long n, int relu);
 rten_status launch_minmax(rten_ctx* ctx, const float* x, long long n, int* mm /* 2 ordered ints */);
-rten_status launch_dql_quantize(rten_ctx* ctx, const float* x, uint8_t* y, long long n, const int* mm,
-                                float* scale_out, uint8_t* zp_out);
+// `xch` (batch-sharded runs): the kernel first exchanges the local range in `mm` with the other ranks (comm_device.cuh)
+struct RangeExchange;
+rten_status launch_dql_quantize(rten_ctx* ctx, const float* x, uint8_t* y, long long n, int* mm,
+                                float* scale_out, uint8_t* zp_out, const RangeExchange* xch = nullptr);
 rten_status launch_rowsum8(rten_ctx* ctx, const void* a, int is_signed, long long rows, int K, long long ld, int* out);
 rten_status launch_zp_to_i32(rten_ctx* ctx, const void* zp, int is_signed, int n, long long zs, int* out);
 rten_status launch_fill8(rten_ctx* ctx, void* p, long long n, uint8_t v);
@@ -77,6 +79,7 @@ rten_status launch_smallc8_pack_w(rten_ctx* ctx, const void* w, void* wp, int O,
                                   long long ws_c, long long ws_h, long long ws_w);
 
 rten_status launch_dql_quantize_rows(rten_ctx* ctx, const float* x, uint8_t* y, long long rows, int row_len, int rows_inner,
-                                     long long y_inner, long long y_outer, const int* mm, float* scale_out, uint8_t* zp_out);
+                                     long long y_inner, long long y_outer, int* mm, float* scale_out, uint8_t* zp_out,
+                                     const RangeExchange* xch = nullptr);
 
 }  // namespace rtb

@@ -582,7 +582,6 @@ static rten_status launch_plan(rten_ctx* ctx, const GemmLaunch& L, const Prepare
     p.x3_cb = L.x3_cb;
     if (L.x3_cb && !encode_map(ctx, &map_a2, L.a_lo, q.esize, true, q.abox, q.aes)) return RTEN_ERR_UNSUPPORTED_VALUE;
     if (p.tma_store && !encode_map(ctx, &map_d, q.od, 4, true, q.dbox, des)) {
-        if (p.bn % 32 == 0 && false) return RTEN_ERR_UNSUPPORTED_VALUE;
         p.tma_store = 0;  // direct stores still work for any bn that is a multiple of 16
         p.res_tma = 0;
         map_d = map_a;
