@@ -1475,6 +1475,33 @@ __global__ void __launch_bounds__(256) tf32x3_split_vec_kernel(const float* __re
     }
 }
 
+// low parts of a DENSE tensor (role 2, no padding): a flat stream, 4 x 128 bits per lane and iteration, all loads of a warp
+// coalesced and in flight together -- no index arithmetic (the strided kernel spends ~40 integer instructions per float4
+// on its divisions, which caps it near 2.5 TB/s)
+__global__ void __launch_bounds__(256) tf32x3_lo_flat_kernel(const float4* __restrict__ x, float4* __restrict__ y, long long n4) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long nblk = n4 >> 7;  // 128 float4 per warp and iteration
+    auto lo4 = [](float4 v) {
+        float4 h;
+        h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+        h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+        h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+        h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+        return make_float4(__fsub_rn(v.x, h.x), __fsub_rn(v.y, h.y), __fsub_rn(v.z, h.z), __fsub_rn(v.w, h.w));
+    };
+    for (long long b = warp; b < nblk; b += nwarps) {
+        const float4* xp = x + (b << 7) + lane;
+        const float4 v0 = xp[0], v1 = xp[32], v2 = xp[64], v3 = xp[96];
+        float4* yp = y + (b << 7) + lane;
+        yp[0] = lo4(v0);
+        yp[32] = lo4(v1);
+        yp[64] = lo4(v2);
+        yp[96] = lo4(v3);
+    }
+    for (long long i = (nblk << 7) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) y[i] = lo4(x[i]);
+}
+
 rten_status launch_tf32x3_split(rten_ctx* ctx, const float* x, float* y, const long long dims[4], const long long strides[4],
                                 long long d0p, int role) {
     SplitParams p;
@@ -1489,6 +1516,16 @@ rten_status launch_tf32x3_split(rten_ctx* ctx, const float* x, float* y, const l
     p.n = p.d3 * p.d2 * p.d1 * p.d0p;
     p.role = role;
     if (p.n == 0) return RTEN_OK;
+    const bool dense = role == 2 && p.d0 == p.d0p && (p.d0 & 3) == 0 && (p.d1 == 1 || p.s1 == p.d0) && (p.d2 == 1 || p.s2 == p.d0 * p.d1) &&
+                       (p.d3 == 1 || p.s3 == p.d0 * p.d1 * p.d2) && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+                       (reinterpret_cast<uintptr_t>(y) & 15) == 0;
+    if (dense) {
+        tf32x3_lo_flat_kernel<<<ew_grid(ctx, p.n / 16), 256, 0, launch_stream(ctx)>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(y), p.n / 4);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return fail_cuda(ctx, e, "tf32x3 split launch");
+        count_launch(ctx);
+        return RTEN_OK;
+    }
     const bool vec = (p.d0 & 3) == 0 && (p.d0p & 3) == 0 && (p.s1 & 3) == 0 && (p.s2 & 3) == 0 && (p.s3 & 3) == 0 &&
                      (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 && p.n < 0x7fffffffLL;
     if (vec)
