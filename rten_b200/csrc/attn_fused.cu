@@ -155,32 +155,51 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
         mbar_wait(bar_s, 0);
         tc_fence_after();
         float mx = -FLT_MAX;
+        const f32x2 sc2 = splat2(p.scale);
 #pragma unroll
         for (int c = 0; c < 4; c++) {
             uint32_t v[32];
             tmem_ld_32x32(t_row + c * 32, v);
             tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; j++) {
-                float x = __uint_as_float(v[j]) * p.scale;            // FusedMatMul's alpha
-                if (mrow) x = __fadd_rn(x, __ldg(mrow + c * 32 + j));  // AddSoftmax: z = qk + mask
-                z[c * 32 + j] = x;
-                mx = fmaxf(mx, x);
+            for (int j = 0; j < 32; j += 4) {
+                // FusedMatMul's alpha, then AddSoftmax's z = qk + mask: two lanes per packed instruction (same roundings)
+                f32x2 a = mul2(pack2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), sc2);
+                f32x2 b2 = mul2(pack2(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])), sc2);
+                if (mrow) {
+                    const float4 m4 = __ldg(reinterpret_cast<const float4*>(mrow + c * 32 + j));
+                    a = add2(a, pack2(m4.x, m4.y));
+                    b2 = add2(b2, pack2(m4.z, m4.w));
+                }
+                unpack2(a, z[c * 32 + j], z[c * 32 + j + 1]);
+                unpack2(b2, z[c * 32 + j + 2], z[c * 32 + j + 3]);
+                mx = fmaxf(fmaxf(mx, z[c * 32 + j]), fmaxf(z[c * 32 + j + 1], fmaxf(z[c * 32 + j + 2], z[c * 32 + j + 3])));
             }
         }
-        // exponentials and the 16 lane partial sums, lane l owning the elements i = l (mod 16) in ascending i
-        float part[16];
+        // exponentials and the 16 lane partial sums, lane l owning the elements i = l (mod 16) in ascending i (pairs of lanes
+        // in one packed register: the same additions in the same order)
+        f32x2 part[8];
 #pragma unroll
-        for (int l = 0; l < 16; l++) part[l] = 0.0f;
+        for (int l = 0; l < 8; l++) part[l] = splat2(0.0f);
+        const f32x2 nmx = splat2(-mx);
 #pragma unroll
-        for (int i = 0; i < SK; i++) {
-            z[i] = reduced_range_exp(__fsub_rn(z[i], mx));
-            part[i & 15] = __fadd_rn(part[i & 15], z[i]);
+        for (int i = 0; i < SK; i += 2) {
+            float e0, e1;
+            unpack2(add2(pack2(z[i], z[i + 1]), nmx), e0, e1);  // z - max
+            reduced_range_exp_x2(e0, e1);
+            z[i] = e0;
+            z[i + 1] = e1;
+            part[(i & 15) >> 1] = add2(part[(i & 15) >> 1], pack2(e0, e1));
         }
         float s = 0.0f;
 #pragma unroll
-        for (int l = 0; l < 16; l++) s = __fadd_rn(s, part[l]);
-        const float inv = __fdiv_rn(1.0f, s);
+        for (int l = 0; l < 8; l++) {
+            float a, b2;
+            unpack2(part[l], a, b2);
+            s = __fadd_rn(s, a);
+            s = __fadd_rn(s, b2);
+        }
+        const f32x2 inv = splat2(__fdiv_rn(1.0f, s));
         // P as the A operand: tile c holds keys [32 c, 32 c + 32); row r = 128 bytes, 16-byte chunks XOR-swizzled by r & 7
         const int sw = r & 7;
 #pragma unroll
@@ -189,26 +208,40 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 const int i = c * 32 + 4 * j;
-                *reinterpret_cast<float4*>(rowp + ((j ^ sw) << 4)) =
-                    make_float4(__fmul_rn(z[i], inv), __fmul_rn(z[i + 1], inv), __fmul_rn(z[i + 2], inv), __fmul_rn(z[i + 3], inv));
+                float4 o;
+                unpack2(mul2(pack2(z[i], z[i + 1]), inv), o.x, o.y);
+                unpack2(mul2(pack2(z[i + 2], z[i + 3]), inv), o.z, o.w);
+                *reinterpret_cast<float4*>(rowp + ((j ^ sw) << 4)) = o;
             }
         }
         fence_proxy_async();  // the tensor core reads these bytes through the async proxy
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_p);
-        // ---- O row -> global (256 contiguous bytes per thread)
+        // ---- O rows -> shared memory (the P tiles are dead once P V has completed) -> global, two whole 256-byte rows per
+        // warp instruction (a thread writing its own row costs 32 half-used sectors per instruction: tools/store_probe.cu)
         mbar_wait(bar_o, 0);
         tc_fence_after();
-        float* orow = p.out + (long long)b * p.o_b + (long long)h * p.o_h + (long long)(qt * SQ + r) * p.o_s;
+        uint8_t* so = sp + warp * (32 * 256);  // this warp's 32 rows x 256 B
+        {
+            uint8_t* rowp = so + lane * 256;
 #pragma unroll
-        for (int c = 0; c < 2; c++) {
-            uint32_t v[32];
-            tmem_ld_32x32(t_row + 128 + c * 32, v);
-            tmem_ld_wait();
+            for (int c = 0; c < 2; c++) {
+                uint32_t v[32];
+                tmem_ld_32x32(t_row + 128 + c * 32, v);
+                tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(orow + c * 32 + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                for (int j = 0; j < 8; j++)
+                    *reinterpret_cast<uint4*>(rowp + c * 128 + ((j ^ (lane & 7)) << 4)) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+        }
+        __syncwarp();
+        float* obase = p.out + (long long)b * p.o_b + (long long)h * p.o_h + (long long)(qt * SQ + warp * 32) * p.o_s;
+#pragma unroll
+        for (int it = 0; it < 16; it++) {
+            const int row = it * 2 + (lane >> 4), jj = lane & 15;
+            const uint4 d = *reinterpret_cast<const uint4*>(so + row * 256 + (jj >> 3) * 128 + (((jj & 7) ^ (row & 7)) << 4));
+            *reinterpret_cast<uint4*>(obase + (long long)row * p.o_s + jj * 4) = d;
         }
     }
     tc_fence_before();
@@ -227,6 +260,7 @@ bool attn_fused_supported(const AttnFusedLaunch& L) {
     if (L.B < 1 || L.heads < 1) return false;
     auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
     if (!al16(L.out) || (L.o_b & 3) || (L.o_h & 3) || (L.o_s & 3)) return false;
+    if (L.mask && (!al16(L.mask) || (L.m_b & 3))) return false;  // the mask row is read 128 bits at a time
     // Q, K: head dimension contiguous; V: key dimension contiguous (a transposed value tensor)
     if (!tma_compatible(L.q, 4, 4) || !tma_compatible(L.k, 4, 4)) return false;
     if (L.v ? (!al16(L.v) || (L.v_b & 3) || (L.v_h & 3) || (L.v_s & 3)) : !tma_compatible(L.vt, 4, 4)) return false;

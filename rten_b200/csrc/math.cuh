@@ -107,6 +107,32 @@ __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
 }
 __device__ __forceinline__ f32x2 splat2(float c) { return pack2(c, c); }
 
+// reduced_range_exp of two lanes (same roundings as the scalar recipe)
+__device__ __forceinline__ void reduced_range_exp_x2(float& x0, float& x1) {
+    const f32x2 x = pack2(x0, x1);
+    const float magic = 12582912.0f;
+    f32x2 j = fma2(x, splat2(1.44269504088896340736f), splat2(magic));
+    j = add2(j, splat2(-magic));
+    f32x2 r = fma2(j, splat2(-6.93145752e-1f), x);
+    r = fma2(j, splat2(-1.42860677e-6f), r);
+    f32x2 q = splat2(1.37805939e-3f);
+    q = fma2(q, r, splat2(8.37312452e-3f));
+    q = fma2(q, r, splat2(4.16695364e-2f));
+    q = fma2(q, r, splat2(1.66664720e-1f));
+    q = fma2(q, r, splat2(4.99999851e-1f));
+    q = fma2(q, r, splat2(1.0f));
+    q = fma2(q, r, splat2(1.0f));
+    float j0, j1;
+    unpack2(j, j0, j1);
+    const float p0 = __int_as_float((int)((unsigned)(trunc_i32_x86(j0) + 127) << 23));
+    const float p1 = __int_as_float((int)((unsigned)(trunc_i32_x86(j1) + 127) << 23));
+    float e0, e1;
+    unpack2(mul2(q, pack2(p0, p1)), e0, e1);
+    const float cutoff = -126.5f * 0.693147180559945309417f + 0.01f;
+    x0 = (x0 < cutoff) ? 0.0f : e0;
+    x1 = (x1 < cutoff) ? 0.0f : e1;
+}
+
 __device__ __forceinline__ void gelu_ref_x2(float& x0, float& x1) {
     const f32x2 x = pack2(x0, x1);
     const f32x2 half_x = mul2(x, splat2(0.5f));

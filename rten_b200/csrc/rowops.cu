@@ -742,8 +742,56 @@ rten_status launch_nd_copy(rten_ctx* ctx, int esize, const void* src, void* dst,
     return RTEN_OK;
 }
 
+// a and d dense, b dense over the TRAILING dims and broadcast over the leading ones (bias rows, position embeddings):
+// d[i] = a[i] (+|*) b[i mod period], 128 bits per thread, 32-bit index arithmetic
+__global__ void __launch_bounds__(256)
+add_periodic_kernel(const float4* __restrict__ a, const float4* __restrict__ b, float4* __restrict__ d, unsigned n4, unsigned period4, int relu) {
+    const unsigned stride = gridDim.x * blockDim.x;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const float4 x = a[i];
+        const float4 y = b[i % period4];
+        float4 o = (relu & 2) ? make_float4(__fmul_rn(x.x, y.x), __fmul_rn(x.y, y.y), __fmul_rn(x.z, y.z), __fmul_rn(x.w, y.w))
+                              : make_float4(__fadd_rn(x.x, y.x), __fadd_rn(x.y, y.y), __fadd_rn(x.z, y.z), __fadd_rn(x.w, y.w));
+        if (relu & 1) {
+            o.x = o.x > 0.f ? o.x : 0.f;
+            o.y = o.y > 0.f ? o.y : 0.f;
+            o.z = o.z > 0.f ? o.z : 0.f;
+            o.w = o.w > 0.f ? o.w : 0.f;
+        }
+        d[i] = o;
+    }
+}
+
 rten_status launch_nd_add(rten_ctx* ctx, const float* a, const float* b, float* d, int ndim, const long long* shape,
                           const long long* sa, const long long* sb, const long long* sd, int relu) {
+    {
+        // fast path: a / d dense, b = a dense block of the trailing dims repeated over the leading ones
+        long long dense = 1, period = 0, n = 1;
+        bool ok = ndim >= 1, in_bcast = false;
+        for (int i = ndim - 1; i >= 0 && ok; i--) {
+            if (shape[i] != 1) {
+                ok = sa[i] == dense && sd[i] == dense;
+                if (!in_bcast && sb[i] == dense) {
+                } else if (sb[i] == 0) {
+                    if (!in_bcast) period = dense;
+                    in_bcast = true;
+                } else {
+                    ok = false;
+                }
+            }
+            dense *= shape[i];
+            n *= shape[i];
+        }
+        if (ok && in_bcast && period > 0 && (period & 3) == 0 && n < 0x7fffffffLL && n > 0 &&
+            ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(d)) & 15) == 0) {
+            add_periodic_kernel<<<ew_grid(ctx, n / 4), 256, 0, launch_stream(ctx)>>>(reinterpret_cast<const float4*>(a), reinterpret_cast<const float4*>(b),
+                                                                               reinterpret_cast<float4*>(d), (unsigned)(n / 4), (unsigned)(period / 4), relu);
+            cudaError_t e = cudaGetLastError();
+            if (e != cudaSuccess) return fail_cuda(ctx, e, "nd_add launch");
+            count_launch(ctx);
+            return RTEN_OK;
+        }
+    }
     NdParams p;
     memset(&p, 0, sizeof(p));
     p.ndim = ndim;
@@ -1303,9 +1351,31 @@ gather_rows_kernel(const float* __restrict__ table, const int* __restrict__ idx,
     }
 }
 
+// contiguous table rows, width % 4 == 0: one float4 per thread, 32-bit index arithmetic
+__global__ void __launch_bounds__(256)
+gather_rows_vec_kernel(const float* __restrict__ table, const int* __restrict__ idx, float4* __restrict__ out, unsigned n4, unsigned w4,
+                       long long t_rs, long long rows) {
+    const unsigned stride = gridDim.x * blockDim.x;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const unsigned r = i / w4, c4 = i - r * w4;
+        long long id = idx[r];
+        if (id < 0) id += rows;
+        out[i] = *reinterpret_cast<const float4*>(table + id * t_rs + 4 * c4);
+    }
+}
+
 rten_status launch_gather_rows(rten_ctx* ctx, const float* table, const int* idx, float* out, long long nidx, int width,
                                long long t_rs, long long t_cs, long long rows) {
     if (nidx * width == 0) return RTEN_OK;
+    if (t_cs == 1 && (width & 3) == 0 && (t_rs & 3) == 0 && nidx * width < 0x7fffffffLL &&
+        ((reinterpret_cast<uintptr_t>(table) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
+        gather_rows_vec_kernel<<<ew_grid(ctx, nidx * width / 4), 256, 0, launch_stream(ctx)>>>(table, idx, reinterpret_cast<float4*>(out),
+                                                                                       (unsigned)(nidx * width / 4), (unsigned)(width / 4), t_rs, rows);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return fail_cuda(ctx, e, "gather launch");
+        count_launch(ctx);
+        return RTEN_OK;
+    }
     gather_rows_kernel<<<ew_grid(ctx, nidx * width), 256, 0, launch_stream(ctx)>>>(table, idx, out, nidx, width, t_rs, t_cs,
                                                                             rows);
     cudaError_t e = cudaGetLastError();
