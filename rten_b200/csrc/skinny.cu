@@ -587,16 +587,20 @@ struct AttnDecodeParams {
     int* cnt;   // [B * q_heads] arrival counters (zero between launches)
 };
 
-constexpr int ATTN_CHUNK = 128;  // cached positions per CTA
+constexpr int ATTN_CHUNK = 128;  // cached positions per CTA (eight warps; the six-warp variant covers 96)
 
-template <int DH>
-__global__ void __launch_bounds__(256, DH == 64 ? 3 : 1) attn_decode_kernel(const AttnDecodeParams p) {
+// NW warps per CTA (8 or 6).  Registers cap the kernel at 80 per thread either way, so 256-thread CTAs run three to an SM
+// (444 on the chip) and 192-thread CTAs four (592): the launcher takes the variant whose grid needs fewer waves -- GPT-2's
+// 96 (batch x head) pairs over a 576-position cache are 480 CTAs of 8 warps (two waves, the second nearly empty) or 576 of 6
+// (one wave).
+template <int DH, int NW>
+__global__ void __launch_bounds__(NW * 32, DH == 64 ? (NW == 8 ? 3 : 4) : 1) attn_decode_kernel(const AttnDecodeParams p) {
     // Every warp owns 16 consecutive cached positions of the CTA's chunk and runs the whole attention on them by itself
-    // (scores, local max, exponentials, local sum, value product): no block barrier until the eight warps' partial
+    // (scores, local max, exponentials, local sum, value product): no block barrier until the warps' partial
     // (max, sum, output) triples are merged -- the same merge that later combines the splits of a (batch, head).
-    __shared__ __align__(16) float s_pw[8][16];
-    __shared__ float s_m[8], s_s[8];
-    __shared__ float s_o[8][DH];
+    __shared__ __align__(16) float s_pw[NW][16];
+    __shared__ float s_m[NW], s_s[NW];
+    __shared__ float s_o[NW][DH];
     __shared__ int s_last;
     const AttnDecodeLaunch& L = p.L;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -750,13 +754,13 @@ __global__ void __launch_bounds__(256, DH == 64 ? 3 : 1) attn_decode_kernel(cons
         s_s[warp] = sw;
     }
     __syncthreads();
-    // ---- merge the eight warps
+    // ---- merge the warps
     float m = -FLT_MAX, num = 0.0f, den = 0.0f;
     if (tid < DH) {
 #pragma unroll
-        for (int w = 0; w < 8; w++) m = fmaxf(m, s_m[w]);
+        for (int w = 0; w < NW; w++) m = fmaxf(m, s_m[w]);
 #pragma unroll
-        for (int w = 0; w < 8; w++) {
+        for (int w = 0; w < NW; w++) {
             const float e = reduced_range_exp(s_m[w] - m);
             den = fmaf(s_s[w], e, den);
             num = fmaf(s_o[w][tid], e, num);
@@ -823,11 +827,24 @@ rten_status launch_attn_decode(rten_ctx* ctx, const AttnDecodeLaunch& L) {
     AttnDecodeParams p;
     p.L = L;
     const int bh = L.B * L.q_heads;
-    // a split covers at most ATTN_CHUNK positions (rounded to 4); more splits when (batch x heads) alone leaves SMs idle
-    int ns = (L.kv_cap + ATTN_CHUNK - 4) / (ATTN_CHUNK - 3);
-    ns = std::max(ns, std::min(16, (2 * ctx->num_sms + bh - 1) / bh));
-    ns = std::max(1, std::min(ns, std::max(1, (L.kv_cap + 15) / 16)));
-    while ((((L.kv_cap + ns - 1) / ns + 3) & ~3) > ATTN_CHUNK) ns++;
+    // a split covers at most `chunk` positions (rounded to 4); more splits when (batch x heads) alone leaves SMs idle
+    auto splits_for = [&](int chunk) {
+        int ns = (L.kv_cap + chunk - 1) / chunk;
+        ns = std::max(ns, std::min(16, (2 * ctx->num_sms + bh - 1) / bh));
+        ns = std::max(1, std::min(ns, std::max(1, (L.kv_cap + 15) / 16)));
+        while ((((L.kv_cap + ns - 1) / ns + 3) & ~3) > chunk) ns++;
+        return ns;
+    };
+    int nw = 8, ns = splits_for(ATTN_CHUNK);
+    if (L.dh == 64 && !getenv("RTEN_B200_ATTN_8WARPS")) {  // six-warp CTAs when their grid needs fewer waves (see the kernel's comment)
+        const int ns6 = splits_for(96);
+        const long long waves8 = ((long long)bh * ns + 3LL * ctx->num_sms - 1) / (3LL * ctx->num_sms);
+        const long long waves6 = ((long long)bh * ns6 + 4LL * ctx->num_sms - 1) / (4LL * ctx->num_sms);
+        if (waves6 < waves8) {
+            nw = 6;
+            ns = ns6;
+        }
+    }
     p.nsplit = ns;
     p.ws = nullptr;
     p.cnt = nullptr;
@@ -849,14 +866,15 @@ rten_status launch_attn_decode(rten_ctx* ctx, const AttnDecodeLaunch& L) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(bh * ns);
-    cfg.blockDim = dim3(256);
+    cfg.blockDim = dim3(nw * 32);
     cfg.stream = launch_stream(ctx);
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = getenv("RTEN_B200_NO_PDL") ? 0 : 1;
-    cudaError_t e = L.dh == 64 ? cudaLaunchKernelEx(&cfg, attn_decode_kernel<64>, p) : cudaLaunchKernelEx(&cfg, attn_decode_kernel<128>, p);
+    cudaError_t e = L.dh == 64 ? (nw == 6 ? cudaLaunchKernelEx(&cfg, attn_decode_kernel<64, 6>, p) : cudaLaunchKernelEx(&cfg, attn_decode_kernel<64, 8>, p))
+                               : cudaLaunchKernelEx(&cfg, attn_decode_kernel<128, 8>, p);
     if (e != cudaSuccess) return fail_cuda(ctx, e, "attention launch");
     e = cudaGetLastError();
     if (e != cudaSuccess) return fail_cuda(ctx, e, "attention launch");
