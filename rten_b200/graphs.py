@@ -615,19 +615,51 @@ class GPT2Int8Runner:
     def forward(self, input_ids: np.ndarray) -> O.DeviceTensor:
         """input_ids: host int32 [B,T] -- the T tokens that follow the `self.past` cached positions (prefill: the whole
         prompt; decode: T = 1).  Returns the logits of the LAST position, [B, vocab]."""
-        ctx, s = self.ctx, self.spec
+        ctx = self.ctx
         B, T = input_ids.shape
         assert B == self.B and self.past + T <= self.max_seq
-        P, Ltot = self.past, self.past + T
+        ids = ctx.to_device(np.ascontiguousarray(input_ids, np.int32))
+        logits = self._forward_device(ids, self._causal_mask(self.past, T), self.past, T)
+        self.past += T
+        return logits
+
+    def _causal_mask(self, P: int, T: int) -> O.DeviceTensor:
+        """additive mask for the T new rows: position P+i attends to 0..P+i"""
+        Ltot = P + T
+        mask = np.where(np.arange(Ltot)[None, :] <= (P + np.arange(T))[:, None], 0.0, -np.inf).astype(np.float32)
+        return self.ctx.to_device(mask.reshape(1, 1, T, Ltot))
+
+    def build_prefill_graph(self, T: int):
+        """Capture the prefill of T tokens into an EMPTY cache as one CUDA graph (the launch list depends on T only): the
+        ~250 launches of a 12-layer prefill are host-bound when issued one by one.  prefill(ids) then replays it."""
+        ctx = self.ctx
+        assert T <= self.max_seq
+        self._pf_T = T
+        self._pf_ids = ctx.empty((self.B, T), np.int32)
+        self._pf_ids.copy_from(np.zeros((self.B, T), np.int32))
+        self._pf_mask = self._causal_mask(0, T)
+        self._forward_device(self._pf_ids, self._pf_mask, 0, T)  # warm-up: launch plans, pool
+        ctx.graph_begin()
+        self._pf_logits = self._forward_device(self._pf_ids, self._pf_mask, 0, T)
+        self._pf_graph = ctx.graph_end()
+
+    def prefill(self, input_ids: np.ndarray) -> O.DeviceTensor:
+        """Graph-replayed prefill of build_prefill_graph's length into an empty cache -> logits of the last position."""
+        assert self.past == 0 and input_ids.shape == (self.B, self._pf_T)
+        self._pf_ids.copy_from(np.ascontiguousarray(input_ids, np.int32))
+        self._pf_graph.launch()
+        self.past = self._pf_T
+        return self._pf_logits
+
+    def _forward_device(self, ids: O.DeviceTensor, mask: O.DeviceTensor, P: int, T: int) -> O.DeviceTensor:
+        ctx, s = self.ctx, self.spec
+        B = self.B
+        Ltot = P + T
         H, nh = s.hidden, s.heads
         dh = H // nh
-        ids = ctx.to_device(np.ascontiguousarray(input_ids, np.int32))
         x = self.gather.run(ctx, self.wte, ids)                                   # [B,T,H]
         x = self.add.run(ctx, x, self.wpe.view((T, H), (H, 1), P * H))
         x = x.reshape(B * T, H)
-        # causal mask for the new rows: position P+i attends to 0..P+i
-        mask = np.where(np.arange(Ltot)[None, :] <= (P + np.arange(T))[:, None], 0.0, -np.inf).astype(np.float32)
-        mask = ctx.to_device(mask.reshape(1, 1, T, Ltot))
         scale = 1.0 / math.sqrt(dh)
         M = self.max_seq
         for d in self.layers:
@@ -649,7 +681,6 @@ class GPT2Int8Runner:
             x = self._linear(f, d["fc2"], residual=x)
         last = x.view((B, H), (T * H, 1), (T - 1) * H)
         last = self.ln.run(ctx, last, *self.lnf)
-        self.past = Ltot
         return self._linear(last, self.lm_head)
 
     # ---- decode steps as ONE replayed CUDA graph ---------------------------------------------------------------

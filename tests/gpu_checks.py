@@ -1048,7 +1048,7 @@ def check_resnet50_int8_b64_baseline(rt, oracle):
 def check_gpt2_b8_baseline(rt, oracle):
     """configs[4] exactly as benched: GPT-2 small int8, 12 layers, vocabulary 50257, batch 8: prefill of 512 tokens, then
     8 decode steps replayed from ONE CUDA graph against the 576-position KV cache.  Last-position logits within
-    2e-2 * max |ref| of the oracle's at every step, greedy tokens equal."""
+    2e-2 * max |ref| of the oracle's at every step, greedy tokens equal; the graph-replayed prefill bit-identical to the eager one."""
     from rten_b200 import graphs
     import model_ref
     rng = oracle.XorShiftRng(5678)
@@ -1062,6 +1062,20 @@ def check_gpt2_b8_baseline(rt, oracle):
     ctx.set_autotune(True)
     runner = graphs.GPT2Int8Runner(ctx, spec, B, 576, fuse=True)
     outs = [runner.forward(steps[0]).numpy()]
+    # the prefill as ONE replayed CUDA graph (what bench.py times) must reproduce the eager prefill bit for bit: logits
+    # AND the KV cache it leaves behind
+    ctx.set_autotune(False)
+    k_eager, v_eager = runner.layers[-1]["k"].numpy().copy(), runner.layers[-1]["vt"].numpy().copy()
+    runner.reset()
+    runner.build_prefill_graph(T0)
+    runner.reset()
+    for d in runner.layers:
+        d["k"].copy_from(np.zeros(d["k"].shape, np.float32))
+        d["vt"].copy_from(np.zeros(d["vt"].shape, np.float32))
+    assert_bit_exact(runner.prefill(steps[0]).numpy(), outs[0], "GPT-2 int8 b8: graph-replayed prefill vs eager prefill")
+    assert_bit_exact(runner.layers[-1]["k"].numpy(), k_eager, "key cache after the graph-replayed prefill")
+    assert_bit_exact(runner.layers[-1]["vt"].numpy(), v_eager, "value cache after the graph-replayed prefill")
+    ctx.set_autotune(True)
     runner.build_decode_graph()
     ctx.set_autotune(False)
     outs += [runner.decode_step(st).numpy().copy() for st in steps[1:]]
