@@ -269,6 +269,15 @@ def test_conv_torch_goldens(oracle):
     assert eq_1e4(oracle.conv(INPUT, KERNEL, None, "same"), same)
 
 
+def test_conv_depthwise_golden(oracle):
+    # src/ops/conv.rs:990-1030 (test_conv_depthwise): one input channel per output channel, groups = 3
+    x = np.array([0.5946, 0.8249, 0.0448, 0.9552, 0.2041, 0.2501, 0.2693, 0.1007, 1.5202, 1.5592, 0.9939, 1.7475], np.float32).reshape(1, 3, 2, 2)
+    w = np.array([-0.0862, -0.4111, 0.0813, 0.4993, -0.4641, 0.1715, -0.0532, -0.2429, -0.4325, 0.4273, 0.4180, 0.4338], np.float32).reshape(3, 1, 2, 2)
+    bias = np.array([0.1, 0.2, 0.3], np.float32)
+    want = np.array([0.09020272 + 0.1, -0.09061745 + 0.2, 1.1822754 + 0.3], np.float32).reshape(1, 3, 1, 1)
+    assert eq_1e4(oracle.conv(x, w, bias, [0, 0, 0, 0], groups=3), want)
+
+
 def ref_conv(x, w, bias, pads, groups, strides, dil, x_zp=None, w_zp=None):
     """src/ops/conv.rs:629-747 reference_conv: 7-deep loop; padded taps are SKIPPED."""
     integer = np.issubdtype(x.dtype, np.integer)
